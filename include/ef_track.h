@@ -1,0 +1,222 @@
+/*
+ * ef_track.h -- C ABI of the B200-native dense frame-to-model tracker.
+ *
+ * Drop-in replacement for the CUDA directory of ElasticFusion as shipped in
+ * Fancomi2017/InstanceFusion (elasticfusionpublic/Core/src/Cuda: cudafuncs.cu, reduce.cu,
+ * containers/) and for the host driver above it (Core/src/Utils/RGBDOdometry.{h,cpp}).
+ * File:line citations are relative to elasticfusionpublic/Core/src/.
+ *
+ * Two tiers:
+ *   Tier 1  ef_tracker_* / ef_init_* / ef_get_incremental_transformation
+ *           = class RGBDOdometry (Utils/RGBDOdometry.h:31-134), one handle per instance.
+ *   Tier 2  ef_op_*  = the 16 free operator functions of Cuda/cudafuncs.cuh:64-177 on raw
+ *           (pointer, pitch, rows, cols) images, for callers that own their buffers and for
+ *           per-operator parity tests.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a positive cudaError_t value on a CUDA failure, or a
+ *     negative EF_ERR_* code; nothing prints or exits (the reference's cudaSafeCall exits the
+ *     process, Cuda/convenience.cuh:64-71).  ef_last_error() gives a message.
+ *   - all `d_` pointers are DEVICE pointers borrowed for the duration of the call; `h_` pointers
+ *     are host pointers.  Outputs are written to caller-provided host memory.
+ *   - a handle is single-threaded; distinct handles share no state (own stream, no globals), so
+ *     N handles x M GPUs can be driven from N x M host threads.
+ *   - "map3" = 3-plane SoA float image, 3*rows x cols, component c of pixel (x,y) at row
+ *     y + c*rows (Utils/RGBDOdometry.cpp:97-101).  "rgba32f" = 4 interleaved floats per pixel
+ *     (GL_RGBA32F texel), "rgba8" = 4 interleaved bytes per pixel.
+ *   - 3x3 matrices are row-major float[9] (memory image of the reference's mat33,
+ *     Cuda/types.cuh:61-73); poses are row-major float[16].
+ *   - there is NO CPU fallback: without a CUDA device every entry point fails with
+ *     EF_ERR_NO_DEVICE.
+ */
+#ifndef EF_TRACK_H_
+#define EF_TRACK_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EF_OK 0
+#define EF_ERR_INVALID_ARGUMENT (-1)
+#define EF_ERR_NO_DEVICE (-2)
+#define EF_ERR_BAD_STATE (-3)
+#define EF_ERR_UNSUPPORTED (-4)
+
+#define EF_ABI_VERSION 1
+
+/* ------------------------------------------------------------------------------------------ */
+/* Tier 1: tracker handle                                                                     */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct ef_tracker ef_tracker;
+
+/* public `last*` fields of RGBDOdometry (Utils/RGBDOdometry.h:64-73) + iteration counts */
+typedef struct ef_track_stats
+{
+    float last_icp_error, last_icp_count;
+    float last_rgb_error, last_rgb_count;
+    float last_so3_error, last_so3_count;
+    double last_A[36]; /* row-major 6x6 */
+    double last_b[6];
+    int so3_iterations;    /* so3Step calls made (<= 10) */
+    int se3_iterations[3]; /* Gauss-Newton iterations run per pyramid level */
+} ef_track_stats;
+
+/* ef_tracker_set_option keys */
+#define EF_OPT_SOLVE_MODE 1      /* EF_SOLVE_HOST (default) | EF_SOLVE_DEVICE */
+#define EF_OPT_USE_GRAPH 2       /* 0/1: replay the frame's kernels from a CUDA graph (device mode) */
+#define EF_OPT_FUSED_BUILD 3     /* 0/1: fused pyramid builders (default 1) instead of one kernel per operator */
+
+#define EF_SOLVE_HOST 0   /* one step kernel per operator call, 6x6 LDLT + pose update in double on the host,
+                             exactly the reference's control flow (RGBDOdometry.cpp:405-585) */
+#define EF_SOLVE_DEVICE 1 /* one persistent cooperative kernel runs the SO(3) loop and all Gauss-Newton
+                             iterations; the same double-precision LDLT runs in a single device thread */
+
+/* RGBDOdometry::RGBDOdometry (Utils/RGBDOdometry.cpp:21-111).  `stream` is a cudaStream_t or NULL
+ * (the handle then creates its own non-blocking stream).  Uses the current CUDA device. */
+int ef_tracker_create(int width, int height, float cx, float cy, float fx, float fy, float dist_thresh, float angle_thresh,
+                      void * stream, ef_tracker ** out);
+int ef_tracker_destroy(ef_tracker * t);
+int ef_tracker_set_option(ef_tracker * t, int key, int value);
+int ef_tracker_get_option(ef_tracker * t, int key, int * value);
+const char * ef_last_error(const ef_tracker * t);
+void * ef_tracker_stream(ef_tracker * t);
+int ef_tracker_synchronize(ef_tracker * t);
+
+/* default thresholds of the reference constructor (Utils/RGBDOdometry.h:38-39) */
+float ef_default_dist_thresh(void);
+float ef_default_angle_thresh(void);
+
+/* initICP(GPUTexture * filteredDepth, depthCutoff)                 RGBDOdometry.cpp:118-142
+ * d_depth: uint16 millimetres, rows of `pitch_bytes` bytes (0 = dense). */
+int ef_init_icp_depth(ef_tracker * t, const uint16_t * d_depth, size_t pitch_bytes, float depth_cutoff);
+/* initICP(GPUTexture * predictedVertices, GPUTexture * predictedNormals, depthCutoff)   :144-167 */
+int ef_init_icp_maps(ef_tracker * t, const float * d_vertices_rgba32f, const float * d_normals_rgba32f, float depth_cutoff);
+/* initICPModel(predictedVertices, predictedNormals, depthCutoff, modelPose)             :169-206 */
+int ef_init_icp_model(ef_tracker * t, const float * d_vertices_rgba32f, const float * d_normals_rgba32f, float depth_cutoff,
+                      const float * h_pose16);
+/* initRGB / initRGBModel / initFirstRGB (GPUTexture * rgb)                  :243-247, :237-241, :249-265
+ * NOTE (reference call-order contract, ElasticFusion.cpp:342): an initICP* call must precede
+ * initRGB*; the float depth pyramid is taken from the vertex map most recently passed to
+ * ef_init_icp_maps / ef_init_icp_model (the reference's vmaps_tmp reuse, RGBDOdometry.cpp:212). */
+int ef_init_rgb(ef_tracker * t, const uint8_t * d_rgba8, size_t pitch_bytes);
+int ef_init_rgb_model(ef_tracker * t, const uint8_t * d_rgba8, size_t pitch_bytes);
+int ef_init_first_rgb(ef_tracker * t, const uint8_t * d_rgba8, size_t pitch_bytes);
+
+/* cudaArray_t variants for CUDA<->GL interop callers (GPUTexture::cudaRes mapped with
+ * cudaGraphicsSubResourceGetMappedArray, RGBDOdometry.cpp:120-128): the array is copied into a
+ * handle-owned linear staging buffer on the handle's stream, then the pointer variant runs. */
+int ef_init_icp_depth_array(ef_tracker * t, void * cuda_array, float depth_cutoff);
+int ef_init_icp_maps_array(ef_tracker * t, void * vertices_array, void * normals_array, float depth_cutoff);
+int ef_init_icp_model_array(ef_tracker * t, void * vertices_array, void * normals_array, float depth_cutoff,
+                            const float * h_pose16);
+int ef_init_rgb_array(ef_tracker * t, void * rgba_array);
+int ef_init_rgb_model_array(ef_tracker * t, void * rgba_array);
+int ef_init_first_rgb_array(ef_tracker * t, void * rgba_array);
+
+/* host-buffer variants: asynchronous H2D into the handle's staging buffers (pinned host memory makes
+ * them truly asynchronous), then the pointer variant.  Dense rows. */
+int ef_init_icp_depth_host(ef_tracker * t, const uint16_t * h_depth, float depth_cutoff);
+int ef_init_icp_maps_host(ef_tracker * t, const float * h_vertices_rgba32f, const float * h_normals_rgba32f, float depth_cutoff);
+int ef_init_icp_model_host(ef_tracker * t, const float * h_vertices_rgba32f, const float * h_normals_rgba32f, float depth_cutoff,
+                           const float * h_pose16);
+int ef_init_rgb_host(ef_tracker * t, const uint8_t * h_rgba8);
+int ef_init_rgb_model_host(ef_tracker * t, const uint8_t * h_rgba8);
+int ef_init_first_rgb_host(ef_tracker * t, const uint8_t * h_rgba8);
+
+/* getIncrementalTransformation(trans, rot, rgbOnly, icpWeight, pyramid, fastOdom, so3)   :267-603
+ * trans[3] / rot[9] (row-major) are in/out exactly like the reference's Eigen references.
+ * Blocks until the result is on the host (the reference blocks on every step). `stats` may be NULL. */
+int ef_get_incremental_transformation(ef_tracker * t, float * trans3, float * rot9, int rgb_only, float icp_weight,
+                                      int pyramid, int fast_odom, int so3, ef_track_stats * stats);
+/* asynchronous split of the call above: _launch enqueues all work and returns, _finish waits for it
+ * and writes the outputs.  Exactly one _finish per _launch. */
+int ef_get_incremental_transformation_launch(ef_tracker * t, const float * trans3, const float * rot9, int rgb_only,
+                                             float icp_weight, int pyramid, int fast_odom, int so3);
+int ef_get_incremental_transformation_finish(ef_tracker * t, float * trans3, float * rot9, ef_track_stats * stats);
+
+/* getCovariance(): inverse of lastA                                                    :605-608 */
+int ef_get_covariance(ef_tracker * t, double * cov36);
+
+/* Test/diagnostic access to the handle's pyramids (dense rows): name in
+ * {"vmap_curr","nmap_curr","vmap_g_prev","nmap_g_prev","last_depth","next_depth","last_image",
+ *  "next_image","last_next_image","dIdx","dIdy","depth_tmp"}, level 0..2.  Synchronises the stream.
+ * Note dIdx/dIdy are only (re)computed inside ef_get_incremental_transformation when RGB is used. */
+int ef_tracker_download(ef_tracker * t, const char * name, int level, void * h_dst, size_t bytes);
+/* number of kernels this handle has launched since creation (bench.py's gpu_launches) */
+long long ef_tracker_launch_count(const ef_tracker * t);
+
+/* ------------------------------------------------------------------------------------------ */
+/* Tier 2: per-operator entry points (Cuda/cudafuncs.cuh:64-177).  All asynchronous on `stream`  */
+/* (cudaStream_t, NULL = legacy default stream) unless they return host results, in which case   */
+/* they synchronise `stream` before returning.  Pitches are in BYTES (0 = dense).                */
+/* ------------------------------------------------------------------------------------------ */
+/* pyrDown                     cudafuncs.cu:57-107   u16 src rows x cols -> dst rows/2 x cols/2 */
+int ef_op_pyr_down_u16(const uint16_t * d_src, size_t src_pitch, int src_rows, int src_cols, uint16_t * d_dst, size_t dst_pitch,
+                       void * stream);
+/* createVMap                  cudafuncs.cu:109-149  fx..cy already scaled to the level */
+int ef_op_create_vmap(const uint16_t * d_depth, size_t depth_pitch, int rows, int cols, float fx, float fy, float cx, float cy,
+                      float depth_cutoff, float * d_vmap3, size_t vmap_pitch, void * stream);
+/* createNMap                  cudafuncs.cu:151-204 */
+int ef_op_create_nmap(const float * d_vmap3, size_t vmap_pitch, int rows, int cols, float * d_nmap3, size_t nmap_pitch, void * stream);
+/* tranformMaps                cudafuncs.cu:206-268  (dst may alias src) */
+int ef_op_transform_maps(const float * d_vsrc3, const float * d_nsrc3, size_t src_pitch, int rows, int cols, const float * h_R9,
+                         const float * h_t3, float * d_vdst3, float * d_ndst3, size_t dst_pitch, void * stream);
+/* copyMaps                    cudafuncs.cu:270-330 */
+int ef_op_copy_maps(const float * d_v_rgba32f, const float * d_n_rgba32f, int rows, int cols, float * d_vmap3, float * d_nmap3,
+                    size_t dst_pitch, void * stream);
+/* resizeVMap / resizeNMap     cudafuncs.cu:365-444  normalize = 0 / 1 */
+int ef_op_resize_map(const float * d_in3, size_t in_pitch, int src_rows, int src_cols, float * d_out3, size_t out_pitch,
+                     int normalize, void * stream);
+/* verticesToDepth             cudafuncs.cu:526-546 */
+int ef_op_vertices_to_depth(const float * d_v_rgba32f, int rows, int cols, float cutoff, float * d_dst, size_t dst_pitch, void * stream);
+/* pyrDownGaussF               cudafuncs.cu:332-363, 446-468 */
+int ef_op_pyr_down_gauss_f32(const float * d_src, size_t src_pitch, int src_rows, int src_cols, float * d_dst, size_t dst_pitch,
+                             void * stream);
+/* pyrDownUcharGauss           cudafuncs.cu:470-524 */
+int ef_op_pyr_down_gauss_u8(const uint8_t * d_src, size_t src_pitch, int src_rows, int src_cols, uint8_t * d_dst, size_t dst_pitch,
+                            void * stream);
+/* imageBGRToIntensity         cudafuncs.cu:548-577  (linear rgba8 source instead of a texture reference) */
+int ef_op_bgr_to_intensity(const uint8_t * d_rgba8, size_t src_pitch, int rows, int cols, uint8_t * d_dst, size_t dst_pitch,
+                           void * stream);
+/* computeDerivativeImages     cudafuncs.cu:580-639 */
+int ef_op_derivative_images(const uint8_t * d_src, size_t src_pitch, int rows, int cols, int16_t * d_dx, int16_t * d_dy,
+                            size_t d_pitch, void * stream);
+/* projectToPointCloud         cudafuncs.cu:641-674  fx..cy = LEVEL-0 intrinsics, divided by 2^level inside;
+ * cloud = rows x cols float3 */
+int ef_op_project_point_cloud(const float * d_depth, size_t depth_pitch, int rows, int cols, float fx, float fy, float cx, float cy,
+                              int level, float * d_cloud3, size_t cloud_pitch, void * stream);
+
+/* icpStep                     reduce.cu:257-490.  Host outputs: A 6x6 row-major, b[6], residual[2] =
+ * {sum r^2, inlier count}.  `d_scratch` >= ef_op_scratch_bytes() bytes of device memory. */
+int ef_op_icp_step(const float * h_Rcurr9, const float * h_tcurr3, const float * d_vmap_curr3, const float * d_nmap_curr3,
+                   const float * h_Rprev_inv9, const float * h_tprev3, float fx, float fy, float cx, float cy,
+                   const float * d_vmap_g_prev3, const float * d_nmap_g_prev3, size_t map_pitch, float dist_thresh,
+                   float angle_thresh, int rows, int cols, void * d_scratch, float * h_A36, float * h_b6, float * h_residual2,
+                   void * stream);
+/* computeRgbResidual          reduce.cu:739-936.  d_corres = rows*cols 16-byte DataTerm records
+ * (Cuda/types.cuh:75-81), linear (the reference indexes it linearly, reduce.cu:515/839). */
+int ef_op_rgb_residual(float min_scale, const int16_t * d_dIdx, const int16_t * d_dIdy, size_t d_pitch, const float * d_last_depth,
+                       const float * d_next_depth, size_t depth_pitch, const uint8_t * d_last_image, const uint8_t * d_next_image,
+                       size_t image_pitch, void * d_corres, float max_depth_delta, const float * h_kt3, const float * h_krkinv9,
+                       int rows, int cols, void * d_scratch, int * h_sigma_sum, int * h_count, void * stream);
+/* rgbStep                     reduce.cu:494-678 */
+int ef_op_rgb_step(const void * d_corres, float sigma, const float * d_cloud3, size_t cloud_pitch, float fx, float fy,
+                   const int16_t * d_dIdx, const int16_t * d_dIdy, size_t d_pitch, float sobel_scale, int rows, int cols,
+                   void * d_scratch, float * h_A36, float * h_b6, void * stream);
+/* so3Step                     reduce.cu:938-1141 */
+int ef_op_so3_step(const uint8_t * d_last_image, const uint8_t * d_next_image, size_t image_pitch, const float * h_image_basis9,
+                   const float * h_kinv9, const float * h_krlr9, int rows, int cols, void * d_scratch, float * h_A9, float * h_b3,
+                   float * h_residual2, void * stream);
+size_t ef_op_scratch_bytes(void);
+
+int ef_abi_version(void);
+int ef_device_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* EF_TRACK_H_ */

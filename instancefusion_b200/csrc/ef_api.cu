@@ -1,0 +1,942 @@
+// ef_api.cu -- C ABI (include/ef_track.h): tracker handle (Tier 1) and per-operator wrappers (Tier 2).
+//
+// Tier 1 restates the control flow of elasticfusionpublic/Core/src/Utils/RGBDOdometry.cpp on top of
+// our own kernels.  EF_SOLVE_HOST keeps the reference's structure (one step kernel per operator call,
+// 6x6 LDLT + pose update in double on the host) minus its cudaMalloc/cudaFree and double syncs;
+// EF_SOLVE_DEVICE hands the whole SO(3) + Gauss-Newton loop to one persistent kernel
+// (ef_track_kernel.cu).  No CPU fallback exists: without a CUDA device every call fails.
+#include <cuda_runtime.h>
+#include <float.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+#include <utility>
+
+#include "ef_hostmath.h"
+#include "ef_kernels.h"
+#include "ef_tracker.h"
+
+using namespace ef;
+
+#define EF_API extern "C" __attribute__((visibility("default")))
+
+namespace
+{
+
+int fail(ef_tracker * t, int code, const char * what)
+{
+    if(t)
+    {
+        char buf[256];
+        if(code > 0) snprintf(buf, sizeof(buf), "%s: %s", what, cudaGetErrorString((cudaError_t)code));
+        else snprintf(buf, sizeof(buf), "%s (code %d)", what, code);
+        t->err = buf;
+    }
+    return code;
+}
+
+#define EF_CUDA(t, call)                                      \
+    do                                                        \
+    {                                                         \
+        cudaError_t e_ = (call);                              \
+        if(e_ != cudaSuccess) return fail((t), (int)e_, #call); \
+    } while(0)
+
+#define EF_LAUNCH(t, call)                                    \
+    do                                                        \
+    {                                                         \
+        cudaError_t e_ = (call);                              \
+        (t)->launches++;                                      \
+        if(e_ != cudaSuccess) return fail((t), (int)e_, #call); \
+    } while(0)
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct ArenaPlan
+{
+    size_t off = 0;
+    size_t take(size_t bytes)
+    {
+        const size_t o = off;
+        off = align_up(off + bytes, 256);
+        return o;
+    }
+};
+
+void level_intr(const ef_tracker * t, int level, float & fx, float & fy, float & cx, float & cy)
+{
+    const int div = 1 << level; // CameraModel::operator()(level), Cuda/types.cuh:94-98
+    fx = t->fx / div;
+    fy = t->fy / div;
+    cx = t->cx / div;
+    cy = t->cy / div;
+}
+
+} // namespace
+
+// ------------------------------------------------------------------------------------------------
+// handle lifetime
+// ------------------------------------------------------------------------------------------------
+EF_API int ef_abi_version(void) { return EF_ABI_VERSION; }
+
+EF_API int ef_device_count(void)
+{
+    int n = 0;
+    if(cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+EF_API float ef_default_dist_thresh(void) { return 0.10f; }
+EF_API float ef_default_angle_thresh(void) { return sinf(20.f * 3.14159254f / 180.f); } // RGBDOdometry.h:39
+
+EF_API size_t ef_op_scratch_bytes(void) { return kScratchBytes; }
+
+EF_API int ef_tracker_create(int width, int height, float cx, float cy, float fx, float fy, float dist_thresh, float angle_thresh, void * stream,
+                             ef_tracker ** out)
+{
+    if(!out || width <= 0 || height <= 0 || (width % 4) || (height % 4)) return EF_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    if(ef_device_count() <= 0) return EF_ERR_NO_DEVICE; // the product has no CPU path
+
+    ef_tracker * t = new(std::nothrow) ef_tracker();
+    if(!t) return EF_ERR_INVALID_ARGUMENT;
+    t->width = width; t->height = height;
+    t->cx = cx; t->cy = cy; t->fx = fx; t->fy = fy;
+    t->dist_thresh = dist_thresh; t->angle_thresh = angle_thresh;
+    t->sobel_scale = (float)(1.0 / pow(2.0, 3));
+    t->max_depth_delta_rgb = 0.07f;
+    t->max_depth_rgb = 6.0f;
+    t->min_grad[0] = 5; t->min_grad[1] = 3; t->min_grad[2] = 1;
+    for(int i = 0; i < kNumPyrs; i++) t->dims[i] = LevelDims{height >> i, width >> i};
+    t->solve_mode = EF_SOLVE_HOST;
+    t->use_graph = 0;
+    t->fused_build = 1;
+    t->launches = 0;
+    t->deriv_valid = false;
+    t->launch_pending = false;
+    t->track_state = nullptr;
+    t->h_track_out = nullptr;
+    memset(&t->st, 0, sizeof(t->st));
+    t->st.last_icp_count = t->st.last_rgb_count = t->st.last_so3_count = (float)(width * height); // RGBDOdometry.cpp:26-31
+
+    cudaError_t e = cudaGetDevice(&t->device);
+    if(e == cudaSuccess) e = cudaDeviceGetAttribute(&t->num_sms, cudaDevAttrMultiProcessorCount, t->device);
+    if(e != cudaSuccess) { delete t; return (int)e; }
+
+    if(stream) { t->stream = (cudaStream_t)stream; t->own_stream = false; }
+    else
+    {
+        e = cudaStreamCreateWithFlags(&t->stream, cudaStreamNonBlocking);
+        if(e != cudaSuccess) { delete t; return (int)e; }
+        t->own_stream = true;
+    }
+
+    // arena plan
+    ArenaPlan plan;
+    size_t o_depth_tmp[kNumPyrs], o_vc[kNumPyrs], o_nc[kNumPyrs], o_vp[kNumPyrs], o_np[kNumPyrs], o_ld[kNumPyrs], o_nd[kNumPyrs], o_li[kNumPyrs],
+        o_ni[kNumPyrs], o_lni[kNumPyrs], o_dx[kNumPyrs], o_dy[kNumPyrs], o_cor[kNumPyrs], o_cl[kNumPyrs];
+    for(int i = 0; i < kNumPyrs; i++)
+    {
+        const size_t n = t->dims[i].n();
+        o_depth_tmp[i] = plan.take(n * 2);
+        o_vc[i] = plan.take(n * 12); o_nc[i] = plan.take(n * 12);
+        o_vp[i] = plan.take(n * 12); o_np[i] = plan.take(n * 12);
+        o_ld[i] = plan.take(n * 4); o_nd[i] = plan.take(n * 4);
+        o_li[i] = plan.take(n); o_ni[i] = plan.take(n); o_lni[i] = plan.take(n);
+        o_dx[i] = plan.take(n * 2); o_dy[i] = plan.take(n * 2);
+        o_cor[i] = plan.take(n * 16); o_cl[i] = plan.take(n * 12);
+    }
+    const size_t n0 = t->dims[0].n();
+    const size_t o_tmpz = plan.take(n0 * 4);
+    const size_t o_scratch = plan.take(kScratchBytes);
+    const size_t o_sd = plan.take(n0 * 2), o_sr = plan.take(n0 * 4), o_sv = plan.take(n0 * 16), o_sn = plan.take(n0 * 16);
+    t->arena_bytes = plan.off;
+
+    e = cudaMalloc(&t->arena, t->arena_bytes);
+    if(e == cudaSuccess) e = cudaMemsetAsync(t->arena, 0, t->arena_bytes, t->stream);
+    if(e == cudaSuccess) e = cudaMallocHost((void **)&t->h_result, 64 * sizeof(float));
+    if(e != cudaSuccess)
+    {
+        if(t->arena) cudaFree(t->arena);
+        if(t->own_stream) cudaStreamDestroy(t->stream);
+        delete t;
+        return (int)e;
+    }
+    char * base = static_cast<char *>(t->arena);
+    for(int i = 0; i < kNumPyrs; i++)
+    {
+        t->depth_tmp[i] = (uint16_t *)(base + o_depth_tmp[i]);
+        t->vmap_curr[i] = (float *)(base + o_vc[i]); t->nmap_curr[i] = (float *)(base + o_nc[i]);
+        t->vmap_g_prev[i] = (float *)(base + o_vp[i]); t->nmap_g_prev[i] = (float *)(base + o_np[i]);
+        t->last_depth[i] = (float *)(base + o_ld[i]); t->next_depth[i] = (float *)(base + o_nd[i]);
+        t->last_image[i] = (uint8_t *)(base + o_li[i]); t->next_image[i] = (uint8_t *)(base + o_ni[i]);
+        t->last_next_image[i] = (uint8_t *)(base + o_lni[i]);
+        t->dIdx[i] = (int16_t *)(base + o_dx[i]); t->dIdy[i] = (int16_t *)(base + o_dy[i]);
+        t->corres[i] = base + o_cor[i];
+        t->cloud[i] = (float *)(base + o_cl[i]);
+    }
+    t->tmp_z = (float *)(base + o_tmpz);
+    t->scratch = base + o_scratch;
+    t->stage_depth = (uint16_t *)(base + o_sd);
+    t->stage_rgba = (uint8_t *)(base + o_sr);
+    t->stage_v = (float *)(base + o_sv);
+    t->stage_n = (float *)(base + o_sn);
+
+    const int rc = device_track_init(t);
+    if(rc != EF_OK)
+    {
+        cudaFree(t->arena);
+        cudaFreeHost(t->h_result);
+        if(t->own_stream) cudaStreamDestroy(t->stream);
+        delete t;
+        return rc;
+    }
+    e = cudaStreamSynchronize(t->stream);
+    if(e != cudaSuccess) { ef_tracker_destroy(t); return (int)e; }
+    *out = t;
+    return EF_OK;
+}
+
+EF_API int ef_tracker_destroy(ef_tracker * t)
+{
+    if(!t) return EF_OK;
+    cudaStreamSynchronize(t->stream);
+    device_track_destroy(t);
+    cudaFree(t->arena);
+    cudaFreeHost(t->h_result);
+    if(t->own_stream) cudaStreamDestroy(t->stream);
+    delete t;
+    return EF_OK;
+}
+
+EF_API int ef_tracker_set_option(ef_tracker * t, int key, int value)
+{
+    if(!t) return EF_ERR_INVALID_ARGUMENT;
+    switch(key)
+    {
+    case EF_OPT_SOLVE_MODE:
+        if(value != EF_SOLVE_HOST && value != EF_SOLVE_DEVICE) return fail(t, EF_ERR_INVALID_ARGUMENT, "bad solve mode");
+        t->solve_mode = value;
+        return EF_OK;
+    case EF_OPT_USE_GRAPH: t->use_graph = value ? 1 : 0; return EF_OK;
+    case EF_OPT_FUSED_BUILD: t->fused_build = value ? 1 : 0; return EF_OK;
+    default: return fail(t, EF_ERR_INVALID_ARGUMENT, "unknown option");
+    }
+}
+
+EF_API int ef_tracker_get_option(ef_tracker * t, int key, int * value)
+{
+    if(!t || !value) return EF_ERR_INVALID_ARGUMENT;
+    switch(key)
+    {
+    case EF_OPT_SOLVE_MODE: *value = t->solve_mode; return EF_OK;
+    case EF_OPT_USE_GRAPH: *value = t->use_graph; return EF_OK;
+    case EF_OPT_FUSED_BUILD: *value = t->fused_build; return EF_OK;
+    default: return EF_ERR_INVALID_ARGUMENT;
+    }
+}
+
+EF_API const char * ef_last_error(const ef_tracker * t) { return t ? t->err.c_str() : "null handle"; }
+EF_API void * ef_tracker_stream(ef_tracker * t) { return t ? (void *)t->stream : nullptr; }
+EF_API long long ef_tracker_launch_count(const ef_tracker * t) { return t ? t->launches : 0; }
+
+EF_API int ef_tracker_synchronize(ef_tracker * t)
+{
+    if(!t) return EF_ERR_INVALID_ARGUMENT;
+    EF_CUDA(t, cudaStreamSynchronize(t->stream));
+    return EF_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// pyramid builders
+// ------------------------------------------------------------------------------------------------
+// RGBDOdometry.cpp:118-142
+EF_API int ef_init_icp_depth(ef_tracker * t, const uint16_t * d_depth, size_t pitch_bytes, float depth_cutoff)
+{
+    if(!t || !d_depth) return EF_ERR_INVALID_ARGUMENT;
+    cudaStream_t s = t->stream;
+    // level 0 is read in place from the caller's buffer (the reference copies the texture into depth_tmp[0])
+    const size_t p0 = pitch_bytes ? pitch_bytes : (size_t)t->width * 2;
+    const uint16_t * src = d_depth;
+    size_t sp = p0;
+    // keep a dense copy of level 0 for ef_tracker_download("depth_tmp", 0)
+    EF_CUDA(t, cudaMemcpy2DAsync(t->depth_tmp[0], (size_t)t->width * 2, d_depth, p0, (size_t)t->width * 2, t->height, cudaMemcpyDeviceToDevice, s));
+    src = t->depth_tmp[0];
+    sp = 0;
+    for(int i = 1; i < kNumPyrs; ++i)
+    {
+        EF_LAUNCH(t, launch_pyr_down_u16(src, sp, t->dims[i - 1].rows, t->dims[i - 1].cols, t->depth_tmp[i], 0, s));
+        src = t->depth_tmp[i];
+        sp = 0;
+    }
+    for(int i = 0; i < kNumPyrs; ++i)
+    {
+        float fx, fy, cx, cy;
+        level_intr(t, i, fx, fy, cx, cy);
+        EF_LAUNCH(t, launch_create_vmap(t->depth_tmp[i], 0, t->dims[i].rows, t->dims[i].cols, fx, fy, cx, cy, depth_cutoff, t->vmap_curr[i], 0, s));
+        EF_LAUNCH(t, launch_create_nmap(t->vmap_curr[i], 0, t->dims[i].rows, t->dims[i].cols, t->nmap_curr[i], 0, s));
+    }
+    return EF_OK;
+}
+
+static int build_maps(ef_tracker * t, const float * d_v, const float * d_n, float ** vmaps, float ** nmaps)
+{
+    cudaStream_t s = t->stream;
+    // stands for the copy into vmaps_tmp (RGBDOdometry.cpp:150/178): only the z channel is ever read again (:212)
+    EF_LAUNCH(t, launch_extract_z(d_v, (int)t->dims[0].n(), t->tmp_z, s));
+    EF_LAUNCH(t, launch_copy_maps(d_v, d_n, t->height, t->width, vmaps[0], nmaps[0], 0, s));
+    for(int i = 1; i < kNumPyrs; ++i)
+    {
+        EF_LAUNCH(t, launch_resize_map(vmaps[i - 1], 0, t->dims[i - 1].rows, t->dims[i - 1].cols, vmaps[i], 0, 0, s));
+        EF_LAUNCH(t, launch_resize_map(nmaps[i - 1], 0, t->dims[i - 1].rows, t->dims[i - 1].cols, nmaps[i], 0, 1, s));
+    }
+    return EF_OK;
+}
+
+// RGBDOdometry.cpp:144-167
+EF_API int ef_init_icp_maps(ef_tracker * t, const float * d_v, const float * d_n, float depth_cutoff)
+{
+    (void)depth_cutoff; // unused by the reference as well
+    if(!t || !d_v || !d_n) return EF_ERR_INVALID_ARGUMENT;
+    return build_maps(t, d_v, d_n, t->vmap_curr, t->nmap_curr);
+}
+
+// RGBDOdometry.cpp:169-206
+EF_API int ef_init_icp_model(ef_tracker * t, const float * d_v, const float * d_n, float depth_cutoff, const float * pose)
+{
+    (void)depth_cutoff;
+    if(!t || !d_v || !d_n || !pose) return EF_ERR_INVALID_ARGUMENT;
+    const int rc = build_maps(t, d_v, d_n, t->vmap_g_prev, t->nmap_g_prev);
+    if(rc != EF_OK) return rc;
+    const float R[9] = {pose[0], pose[1], pose[2], pose[4], pose[5], pose[6], pose[8], pose[9], pose[10]};
+    const float tv[3] = {pose[3], pose[7], pose[11]};
+    for(int i = 0; i < kNumPyrs; ++i)
+        EF_LAUNCH(t, launch_transform_maps(t->vmap_g_prev[i], t->nmap_g_prev[i], 0, t->dims[i].rows, t->dims[i].cols, R, tv, t->vmap_g_prev[i],
+                                           t->nmap_g_prev[i], 0, t->stream));
+    return EF_OK;
+}
+
+// RGBDOdometry.cpp:208-235
+static int populate_rgbd(ef_tracker * t, const uint8_t * d_rgba, size_t pitch, float ** depths, uint8_t ** images)
+{
+    cudaStream_t s = t->stream;
+    EF_LAUNCH(t, launch_z_to_depth(t->tmp_z, t->height, t->width, t->max_depth_rgb, depths[0], 0, s));
+    for(int i = 0; i + 1 < kNumPyrs; i++)
+        EF_LAUNCH(t, launch_pyr_down_gauss_f32(depths[i], 0, t->dims[i].rows, t->dims[i].cols, depths[i + 1], 0, s));
+    EF_LAUNCH(t, launch_bgr_to_intensity(d_rgba, pitch, t->height, t->width, images[0], 0, s));
+    for(int i = 0; i + 1 < kNumPyrs; i++)
+        EF_LAUNCH(t, launch_pyr_down_gauss_u8(images[i], 0, t->dims[i].rows, t->dims[i].cols, images[i + 1], 0, s));
+    return EF_OK;
+}
+
+EF_API int ef_init_rgb(ef_tracker * t, const uint8_t * d_rgba, size_t pitch)
+{
+    if(!t || !d_rgba) return EF_ERR_INVALID_ARGUMENT;
+    t->deriv_valid = false;
+    return populate_rgbd(t, d_rgba, pitch, t->next_depth, t->next_image);
+}
+
+EF_API int ef_init_rgb_model(ef_tracker * t, const uint8_t * d_rgba, size_t pitch)
+{
+    if(!t || !d_rgba) return EF_ERR_INVALID_ARGUMENT;
+    return populate_rgbd(t, d_rgba, pitch, t->last_depth, t->last_image);
+}
+
+// RGBDOdometry.cpp:249-265
+EF_API int ef_init_first_rgb(ef_tracker * t, const uint8_t * d_rgba, size_t pitch)
+{
+    if(!t || !d_rgba) return EF_ERR_INVALID_ARGUMENT;
+    cudaStream_t s = t->stream;
+    EF_LAUNCH(t, launch_bgr_to_intensity(d_rgba, pitch, t->height, t->width, t->last_next_image[0], 0, s));
+    for(int i = 0; i + 1 < kNumPyrs; i++)
+        EF_LAUNCH(t, launch_pyr_down_gauss_u8(t->last_next_image[i], 0, t->dims[i].rows, t->dims[i].cols, t->last_next_image[i + 1], 0, s));
+    return EF_OK;
+}
+
+// ---- cudaArray variants (GL interop) ----
+static int stage_array(ef_tracker * t, void * dst, cudaArray_t arr, size_t row_bytes)
+{
+    if(!arr) return EF_ERR_INVALID_ARGUMENT;
+    EF_CUDA(t, cudaMemcpy2DFromArrayAsync(dst, row_bytes, arr, 0, 0, row_bytes, t->height, cudaMemcpyDeviceToDevice, t->stream));
+    return EF_OK;
+}
+
+EF_API int ef_init_icp_depth_array(ef_tracker * t, void * arr, float cutoff)
+{
+    if(!t) return EF_ERR_INVALID_ARGUMENT;
+    const int rc = stage_array(t, t->stage_depth, (cudaArray_t)arr, (size_t)t->width * 2);
+    return rc ? rc : ef_init_icp_depth(t, t->stage_depth, 0, cutoff);
+}
+
+EF_API int ef_init_icp_maps_array(ef_tracker * t, void * v, void * n, float cutoff)
+{
+    if(!t) return EF_ERR_INVALID_ARGUMENT;
+    int rc = stage_array(t, t->stage_v, (cudaArray_t)v, (size_t)t->width * 16);
+    if(!rc) rc = stage_array(t, t->stage_n, (cudaArray_t)n, (size_t)t->width * 16);
+    return rc ? rc : ef_init_icp_maps(t, t->stage_v, t->stage_n, cutoff);
+}
+
+EF_API int ef_init_icp_model_array(ef_tracker * t, void * v, void * n, float cutoff, const float * pose)
+{
+    if(!t) return EF_ERR_INVALID_ARGUMENT;
+    int rc = stage_array(t, t->stage_v, (cudaArray_t)v, (size_t)t->width * 16);
+    if(!rc) rc = stage_array(t, t->stage_n, (cudaArray_t)n, (size_t)t->width * 16);
+    return rc ? rc : ef_init_icp_model(t, t->stage_v, t->stage_n, cutoff, pose);
+}
+
+EF_API int ef_init_rgb_array(ef_tracker * t, void * arr)
+{
+    if(!t) return EF_ERR_INVALID_ARGUMENT;
+    const int rc = stage_array(t, t->stage_rgba, (cudaArray_t)arr, (size_t)t->width * 4);
+    return rc ? rc : ef_init_rgb(t, t->stage_rgba, 0);
+}
+
+EF_API int ef_init_rgb_model_array(ef_tracker * t, void * arr)
+{
+    if(!t) return EF_ERR_INVALID_ARGUMENT;
+    const int rc = stage_array(t, t->stage_rgba, (cudaArray_t)arr, (size_t)t->width * 4);
+    return rc ? rc : ef_init_rgb_model(t, t->stage_rgba, 0);
+}
+
+EF_API int ef_init_first_rgb_array(ef_tracker * t, void * arr)
+{
+    if(!t) return EF_ERR_INVALID_ARGUMENT;
+    const int rc = stage_array(t, t->stage_rgba, (cudaArray_t)arr, (size_t)t->width * 4);
+    return rc ? rc : ef_init_first_rgb(t, t->stage_rgba, 0);
+}
+
+// ---- host-buffer variants ----
+EF_API int ef_init_icp_depth_host(ef_tracker * t, const uint16_t * h, float cutoff)
+{
+    if(!t || !h) return EF_ERR_INVALID_ARGUMENT;
+    EF_CUDA(t, cudaMemcpyAsync(t->stage_depth, h, t->dims[0].n() * 2, cudaMemcpyHostToDevice, t->stream));
+    return ef_init_icp_depth(t, t->stage_depth, 0, cutoff);
+}
+
+EF_API int ef_init_icp_maps_host(ef_tracker * t, const float * hv, const float * hn, float cutoff)
+{
+    if(!t || !hv || !hn) return EF_ERR_INVALID_ARGUMENT;
+    EF_CUDA(t, cudaMemcpyAsync(t->stage_v, hv, t->dims[0].n() * 16, cudaMemcpyHostToDevice, t->stream));
+    EF_CUDA(t, cudaMemcpyAsync(t->stage_n, hn, t->dims[0].n() * 16, cudaMemcpyHostToDevice, t->stream));
+    return ef_init_icp_maps(t, t->stage_v, t->stage_n, cutoff);
+}
+
+EF_API int ef_init_icp_model_host(ef_tracker * t, const float * hv, const float * hn, float cutoff, const float * pose)
+{
+    if(!t || !hv || !hn) return EF_ERR_INVALID_ARGUMENT;
+    EF_CUDA(t, cudaMemcpyAsync(t->stage_v, hv, t->dims[0].n() * 16, cudaMemcpyHostToDevice, t->stream));
+    EF_CUDA(t, cudaMemcpyAsync(t->stage_n, hn, t->dims[0].n() * 16, cudaMemcpyHostToDevice, t->stream));
+    return ef_init_icp_model(t, t->stage_v, t->stage_n, cutoff, pose);
+}
+
+static int stage_rgba_host(ef_tracker * t, const uint8_t * h)
+{
+    EF_CUDA(t, cudaMemcpyAsync(t->stage_rgba, h, t->dims[0].n() * 4, cudaMemcpyHostToDevice, t->stream));
+    return EF_OK;
+}
+
+EF_API int ef_init_rgb_host(ef_tracker * t, const uint8_t * h)
+{
+    if(!t || !h) return EF_ERR_INVALID_ARGUMENT;
+    const int rc = stage_rgba_host(t, h);
+    return rc ? rc : ef_init_rgb(t, t->stage_rgba, 0);
+}
+
+EF_API int ef_init_rgb_model_host(ef_tracker * t, const uint8_t * h)
+{
+    if(!t || !h) return EF_ERR_INVALID_ARGUMENT;
+    // the model image must not overwrite a staged next image still in flight on the stream: both are
+    // consumed by kernels enqueued before the next H2D on the same stream, so one staging buffer is safe
+    const int rc = stage_rgba_host(t, h);
+    return rc ? rc : ef_init_rgb_model(t, t->stage_rgba, 0);
+}
+
+EF_API int ef_init_first_rgb_host(ef_tracker * t, const uint8_t * h)
+{
+    if(!t || !h) return EF_ERR_INVALID_ARGUMENT;
+    const int rc = stage_rgba_host(t, h);
+    return rc ? rc : ef_init_first_rgb(t, t->stage_rgba, 0);
+}
+
+// ------------------------------------------------------------------------------------------------
+// getIncrementalTransformation, host-solve path (RGBDOdometry.cpp:267-603)
+// ------------------------------------------------------------------------------------------------
+static int fetch_result(ef_tracker * t, int nfloats)
+{
+    EF_CUDA(t, cudaMemcpyAsync(t->h_result, static_cast<char *>(t->scratch) + kScratchResultOff, nfloats * sizeof(float), cudaMemcpyDeviceToHost,
+                               t->stream));
+    EF_CUDA(t, cudaStreamSynchronize(t->stream));
+    return EF_OK;
+}
+
+static int compute_derivatives(ef_tracker * t)
+{
+    for(int i = 0; i < kNumPyrs; i++) // RGBDOdometry.cpp:284-290
+        EF_LAUNCH(t, launch_derivative_images(t->next_image[i], 0, t->dims[i].rows, t->dims[i].cols, t->dIdx[i], t->dIdy[i], 0, t->stream));
+    t->deriv_valid = true;
+    return EF_OK;
+}
+
+static int track_host(ef_tracker * t, float * trans, float * rot, int rgb_only, float icp_weight, int pyramid, int fast_odom, int so3)
+{
+    cudaStream_t s = t->stream;
+    const bool icp = !rgb_only && icp_weight > 0; // :275
+    const bool rgb = rgb_only || icp_weight < 100; // :276
+
+    float Rprev[9], tprev[3], Rcurr[9], tcurr[3];
+    memcpy(Rprev, rot, sizeof(Rprev)); memcpy(tprev, trans, sizeof(tprev));
+    memcpy(Rcurr, rot, sizeof(Rcurr)); memcpy(tcurr, trans, sizeof(tcurr));
+
+    if(rgb)
+    {
+        const int rc = compute_derivatives(t);
+        if(rc) return rc;
+    }
+
+    double resultR[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    t->st.so3_iterations = 0;
+    t->st.se3_iterations[0] = t->st.se3_iterations[1] = t->st.se3_iterations[2] = 0;
+
+    if(so3) // :294-382
+    {
+        const int lvl = 2;
+        float R_lr[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+        float fx, fy, cx, cy;
+        level_intr(t, lvl, fx, fy, cx, cy);
+        const double K[9] = {fx, 0, cx, 0, fy, cy, 0, 0, 1};
+        double K_inv[9];
+        hm::inverse33(K, K_inv);
+        float lastError = FLT_MAX / 2, lastCount = FLT_MAX / 2;
+        double lastResultR[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+
+        for(int i = 0; i < 10; i++)
+        {
+            double KR[9], H[9];
+            hm::mul33(K, resultR, KR);
+            hm::mul33(KR, K_inv, H);
+            So3Args a;
+            a.last_image = t->last_next_image[lvl];
+            a.next_image = t->next_image[lvl];
+            a.image_pitch = 0;
+            for(int k = 0; k < 9; k++) { a.image_basis[k] = (float)H[k]; a.kinv[k] = (float)K_inv[k]; a.krlr[k] = (float)KR[k]; }
+            a.rows = t->dims[lvl].rows; a.cols = t->dims[lvl].cols;
+            EF_LAUNCH(t, launch_so3_step(a, t->scratch, s));
+            int rc = fetch_result(t, 11);
+            if(rc) return rc;
+            float jtj[9], jtr[3], residual[2];
+            hm::unpack_so3(t->h_result, jtj, jtr, residual);
+            t->st.so3_iterations++;
+
+            t->st.last_so3_error = sqrtf(residual[0]) / residual[1]; // :348
+            t->st.last_so3_count = residual[1];
+            if(t->st.last_so3_error < lastError && lastCount == t->st.last_so3_count) break; // :352
+            else if(t->st.last_so3_error > lastError + 0.001)                                 // :356
+            {
+                t->st.last_so3_error = lastError;
+                t->st.last_so3_count = lastCount;
+                memcpy(resultR, lastResultR, sizeof(resultR));
+                break;
+            }
+            lastError = t->st.last_so3_error;
+            lastCount = t->st.last_so3_count;
+            memcpy(lastResultR, resultR, sizeof(resultR));
+
+            float delta[3];
+            hm::ldlt_solve<float, 3>(jtj, jtr, delta); // :368
+            const double dd[3] = {delta[0], delta[1], delta[2]};
+            double rotUpdate[9];
+            hm::rodrigues(dd, rotUpdate);
+            float ru[9];
+            for(int k = 0; k < 9; k++) ru[k] = (float)rotUpdate[k];
+            hm::mul33(ru, R_lr, R_lr); // :372
+            for(int k = 0; k < 9; k++) resultR[k] = R_lr[k];
+        }
+    }
+
+    const int iterations[kNumPyrs] = {fast_odom ? 3 : 10, pyramid ? 5 : 0, pyramid ? 4 : 0}; // :384-386
+
+    float Rprev_inv[9];
+    hm::inverse33(Rprev, Rprev_inv); // :388
+
+    double resultRt[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+    if(so3)
+        for(int x = 0; x < 3; x++)
+            for(int y = 0; y < 3; y++) resultRt[x * 4 + y] = resultR[x * 3 + y];
+
+    for(int i = kNumPyrs - 1; i >= 0; i--) // :405
+    {
+        const int rows = t->dims[i].rows, cols = t->dims[i].cols;
+        float fx, fy, cx, cy;
+        level_intr(t, i, fx, fy, cx, cy);
+        if(rgb && iterations[i] > 0) // :409 (skipped when the level runs no iteration: its only consumer is rgbStep)
+            EF_LAUNCH(t, launch_project_points(t->last_depth[i], 0, rows, cols, fx, fy, cx, cy, t->cloud[i], 0, s));
+
+        const double K[9] = {fx, 0, cx, 0, fy, cy, 0, 0, 1};
+        double K_inv[9];
+        hm::inverse33(K, K_inv);
+        t->st.last_rgb_error = FLT_MAX; // :420
+
+        for(int j = 0; j < iterations[i]; j++)
+        {
+            float krkInv[9], kt[3];
+            hm::rgb_warp_params(resultRt, K, K_inv, krkInv, kt); // :424-434
+
+            int sigma = 0, rgbSize = 0;
+            if(rgb)
+            {
+                RgbResArgs a;
+                a.min_scale = (float)(pow(t->min_grad[i], 2.0) / pow(t->sobel_scale, 2.0)); // :442
+                a.max_depth_delta = t->max_depth_delta_rgb;
+                memcpy(a.kt, kt, sizeof(kt)); memcpy(a.krkinv, krkInv, sizeof(krkInv));
+                a.rows = rows; a.cols = cols;
+                a.dIdx = t->dIdx[i]; a.dIdy = t->dIdy[i]; a.d_pitch = 0;
+                a.last_depth = t->last_depth[i]; a.next_depth = t->next_depth[i]; a.depth_pitch = 0;
+                a.last_image = t->last_image[i]; a.next_image = t->next_image[i]; a.image_pitch = 0;
+                a.corres = t->corres[i];
+                EF_LAUNCH(t, launch_rgb_residual(a, t->scratch, s));
+                const int rc = fetch_result(t, 2);
+                if(rc) return rc;
+                rgbSize = reinterpret_cast<int *>(t->h_result)[0];
+                sigma = reinterpret_cast<int *>(t->h_result)[1];
+            }
+
+            float sigmaVal = (float)sqrt((double)(((float)sigma / (float)rgbSize == 0) ? 1 : rgbSize)); // :461 (precedence quirk kept)
+            const float rgbError = (float)(sqrt((double)sigma) / (rgbSize == 0 ? 1 : rgbSize));        // :462
+
+            if(rgb_only && rgbError > t->st.last_rgb_error) break; // :464
+            t->st.last_rgb_error = rgbError;
+            t->st.last_rgb_count = (float)rgbSize;
+            if(rgb_only) sigmaVal = -1; // :472
+
+            double A_icp[36] = {0}, b_icp[6] = {0}, A_rgb[36] = {0}, b_rgb[6] = {0};
+            if(icp)
+            {
+                IcpArgs a;
+                memcpy(a.Rcurr, Rcurr, sizeof(Rcurr)); memcpy(a.tcurr, tcurr, sizeof(tcurr));
+                memcpy(a.Rprev_inv, Rprev_inv, sizeof(Rprev_inv)); memcpy(a.tprev, tprev, sizeof(tprev));
+                a.fx = fx; a.fy = fy; a.cx = cx; a.cy = cy;
+                a.dist_thresh = t->dist_thresh; a.angle_thresh = t->angle_thresh;
+                a.rows = rows; a.cols = cols;
+                a.vmap_curr = t->vmap_curr[i]; a.nmap_curr = t->nmap_curr[i];
+                a.vmap_g_prev = t->vmap_g_prev[i]; a.nmap_g_prev = t->nmap_g_prev[i];
+                a.pitch = 0;
+                EF_LAUNCH(t, launch_icp_step(a, t->scratch, s));
+                const int rc = fetch_result(t, 29);
+                if(rc) return rc;
+                float residual[2];
+                hm::unpack_se3(t->h_result, A_icp, b_icp, residual);
+                // :515-516.  (When !icp the reference reads `residual` uninitialised; we keep the previous values.)
+                t->st.last_icp_error = sqrtf(residual[0]) / residual[1];
+                t->st.last_icp_count = residual[1];
+            }
+            if(rgb)
+            {
+                RgbStepArgs a;
+                a.corres = t->corres[i];
+                a.sigma = sigmaVal;
+                a.cloud = t->cloud[i]; a.cloud_pitch = 0;
+                a.fx = fx; a.fy = fy;
+                a.dIdx = t->dIdx[i]; a.dIdy = t->dIdy[i]; a.d_pitch = 0;
+                a.sobel_scale = t->sobel_scale;
+                a.rows = rows; a.cols = cols;
+                EF_LAUNCH(t, launch_rgb_step(a, t->scratch, s));
+                const int rc = fetch_result(t, 29);
+                if(rc) return rc;
+                hm::unpack_se3(t->h_result, A_rgb, b_rgb, (float *)nullptr);
+            }
+
+            double * lastA = t->st.last_A, * lastb = t->st.last_b, result[6];
+            if(icp && rgb) // :547-553
+            {
+                const double w = icp_weight;
+                for(int k = 0; k < 36; k++) lastA[k] = A_rgb[k] + w * w * A_icp[k];
+                for(int k = 0; k < 6; k++) lastb[k] = b_rgb[k] + w * b_icp[k];
+            }
+            else if(icp)
+            {
+                memcpy(lastA, A_icp, sizeof(A_icp));
+                memcpy(lastb, b_icp, sizeof(b_icp));
+            }
+            else
+            {
+                memcpy(lastA, A_rgb, sizeof(A_rgb));
+                memcpy(lastb, b_rgb, sizeof(b_rgb));
+            }
+            hm::ldlt_solve<double, 6>(lastA, lastb, result);
+            t->st.se3_iterations[i]++;
+
+            hm::update_se3(resultRt, result);                      // :573
+            hm::compose_pose(resultRt, Rprev, tprev, Rcurr, tcurr); // :575-583
+        }
+    }
+
+    if(rgb) // :587-591
+    {
+        const float d[3] = {tcurr[0] - tprev[0], tcurr[1] - tprev[1], tcurr[2] - tprev[2]};
+        if(sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]) > 0.3)
+        {
+            memcpy(Rcurr, Rprev, sizeof(Rcurr));
+            memcpy(tcurr, tprev, sizeof(tcurr));
+        }
+    }
+
+    memcpy(trans, tcurr, sizeof(tcurr));
+    memcpy(rot, Rcurr, sizeof(Rcurr));
+    return EF_OK;
+}
+
+static void swap_so3_images(ef_tracker * t)
+{
+    for(int i = 0; i < kNumPyrs; i++) std::swap(t->last_next_image[i], t->next_image[i]); // RGBDOdometry.cpp:593-599
+    t->deriv_valid = false;
+}
+
+EF_API int ef_get_incremental_transformation_launch(ef_tracker * t, const float * trans, const float * rot, int rgb_only, float icp_weight,
+                                                    int pyramid, int fast_odom, int so3)
+{
+    if(!t || !trans || !rot) return EF_ERR_INVALID_ARGUMENT;
+    if(t->launch_pending) return fail(t, EF_ERR_BAD_STATE, "a launch is already pending");
+    const bool icp = !rgb_only && icp_weight > 0, rgb = rgb_only || icp_weight < 100;
+    if(!icp && !rgb) return fail(t, EF_ERR_INVALID_ARGUMENT, "neither ICP nor RGB selected"); // the reference asserts (:566-569)
+    memcpy(t->pending.trans, trans, sizeof(t->pending.trans));
+    memcpy(t->pending.rot, rot, sizeof(t->pending.rot));
+    t->pending.rgb_only = rgb_only; t->pending.icp_weight = icp_weight; t->pending.pyramid = pyramid;
+    t->pending.fast_odom = fast_odom; t->pending.so3 = so3;
+    if(t->solve_mode == EF_SOLVE_DEVICE)
+    {
+        if(rgb && !t->deriv_valid)
+        {
+            const int rc = compute_derivatives(t);
+            if(rc) return rc;
+        }
+        const int rc = device_track_launch(t, trans, rot, rgb_only, icp_weight, pyramid, fast_odom, so3);
+        if(rc) return rc;
+    }
+    t->launch_pending = true;
+    return EF_OK;
+}
+
+EF_API int ef_get_incremental_transformation_finish(ef_tracker * t, float * trans, float * rot, ef_track_stats * stats)
+{
+    if(!t || !trans || !rot) return EF_ERR_INVALID_ARGUMENT;
+    if(!t->launch_pending) return fail(t, EF_ERR_BAD_STATE, "no launch pending");
+    t->launch_pending = false;
+    int rc;
+    if(t->solve_mode == EF_SOLVE_DEVICE) rc = device_track_finish(t, trans, rot);
+    else
+    {
+        memcpy(trans, t->pending.trans, sizeof(t->pending.trans));
+        memcpy(rot, t->pending.rot, sizeof(t->pending.rot));
+        rc = track_host(t, trans, rot, t->pending.rgb_only, t->pending.icp_weight, t->pending.pyramid, t->pending.fast_odom, t->pending.so3);
+    }
+    if(rc) return rc;
+    if(t->pending.so3) swap_so3_images(t);
+    if(stats) *stats = t->st;
+    return EF_OK;
+}
+
+EF_API int ef_get_incremental_transformation(ef_tracker * t, float * trans, float * rot, int rgb_only, float icp_weight, int pyramid,
+                                             int fast_odom, int so3, ef_track_stats * stats)
+{
+    const int rc = ef_get_incremental_transformation_launch(t, trans, rot, rgb_only, icp_weight, pyramid, fast_odom, so3);
+    if(rc) return rc;
+    return ef_get_incremental_transformation_finish(t, trans, rot, stats);
+}
+
+// RGBDOdometry.cpp:605-608
+EF_API int ef_get_covariance(ef_tracker * t, double * cov)
+{
+    if(!t || !cov) return EF_ERR_INVALID_ARGUMENT;
+    hm::inverseNN<double, 6>(t->st.last_A, cov);
+    return EF_OK;
+}
+
+EF_API int ef_tracker_download(ef_tracker * t, const char * name, int level, void * dst, size_t bytes)
+{
+    if(!t || !name || !dst || level < 0 || level >= kNumPyrs) return EF_ERR_INVALID_ARGUMENT;
+    const size_t n = t->dims[level].n();
+    const void * src = nullptr;
+    size_t need = 0;
+    if(!strcmp(name, "vmap_curr")) { src = t->vmap_curr[level]; need = n * 12; }
+    else if(!strcmp(name, "nmap_curr")) { src = t->nmap_curr[level]; need = n * 12; }
+    else if(!strcmp(name, "vmap_g_prev")) { src = t->vmap_g_prev[level]; need = n * 12; }
+    else if(!strcmp(name, "nmap_g_prev")) { src = t->nmap_g_prev[level]; need = n * 12; }
+    else if(!strcmp(name, "last_depth")) { src = t->last_depth[level]; need = n * 4; }
+    else if(!strcmp(name, "next_depth")) { src = t->next_depth[level]; need = n * 4; }
+    else if(!strcmp(name, "last_image")) { src = t->last_image[level]; need = n; }
+    else if(!strcmp(name, "next_image")) { src = t->next_image[level]; need = n; }
+    else if(!strcmp(name, "last_next_image")) { src = t->last_next_image[level]; need = n; }
+    else if(!strcmp(name, "dIdx")) { src = t->dIdx[level]; need = n * 2; }
+    else if(!strcmp(name, "dIdy")) { src = t->dIdy[level]; need = n * 2; }
+    else if(!strcmp(name, "depth_tmp")) { src = t->depth_tmp[level]; need = n * 2; }
+    else return fail(t, EF_ERR_INVALID_ARGUMENT, "unknown buffer name");
+    if(bytes < need) return fail(t, EF_ERR_INVALID_ARGUMENT, "destination too small");
+    EF_CUDA(t, cudaMemcpyAsync(dst, src, need, cudaMemcpyDeviceToHost, t->stream));
+    EF_CUDA(t, cudaStreamSynchronize(t->stream));
+    return EF_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Tier 2
+// ------------------------------------------------------------------------------------------------
+#define EF_OP_RET(call)                          \
+    do                                           \
+    {                                            \
+        if(ef_device_count() <= 0) return EF_ERR_NO_DEVICE; \
+        return (int)(call);                      \
+    } while(0)
+
+EF_API int ef_op_pyr_down_u16(const uint16_t * s, size_t sp, int r, int c, uint16_t * d, size_t dp, void * st)
+{
+    EF_OP_RET(launch_pyr_down_u16(s, sp, r, c, d, dp, (cudaStream_t)st));
+}
+EF_API int ef_op_create_vmap(const uint16_t * depth, size_t dp, int rows, int cols, float fx, float fy, float cx, float cy, float cutoff, float * v,
+                             size_t vp, void * st)
+{
+    EF_OP_RET(launch_create_vmap(depth, dp, rows, cols, fx, fy, cx, cy, cutoff, v, vp, (cudaStream_t)st));
+}
+EF_API int ef_op_create_nmap(const float * v, size_t vp, int rows, int cols, float * n, size_t np, void * st)
+{
+    EF_OP_RET(launch_create_nmap(v, vp, rows, cols, n, np, (cudaStream_t)st));
+}
+EF_API int ef_op_transform_maps(const float * vs, const float * ns, size_t sp, int rows, int cols, const float * R, const float * tv, float * vd,
+                                float * nd, size_t dp, void * st)
+{
+    EF_OP_RET(launch_transform_maps(vs, ns, sp, rows, cols, R, tv, vd, nd, dp, (cudaStream_t)st));
+}
+EF_API int ef_op_copy_maps(const float * v4, const float * n4, int rows, int cols, float * v, float * n, size_t dp, void * st)
+{
+    EF_OP_RET(launch_copy_maps(v4, n4, rows, cols, v, n, dp, (cudaStream_t)st));
+}
+EF_API int ef_op_resize_map(const float * in, size_t ip, int srows, int scols, float * out, size_t op, int normalize, void * st)
+{
+    EF_OP_RET(launch_resize_map(in, ip, srows, scols, out, op, normalize, (cudaStream_t)st));
+}
+EF_API int ef_op_vertices_to_depth(const float * v4, int rows, int cols, float cutoff, float * d, size_t dp, void * st)
+{
+    EF_OP_RET(launch_vertices_to_depth(v4, rows, cols, cutoff, d, dp, (cudaStream_t)st));
+}
+EF_API int ef_op_pyr_down_gauss_f32(const float * s, size_t sp, int r, int c, float * d, size_t dp, void * st)
+{
+    EF_OP_RET(launch_pyr_down_gauss_f32(s, sp, r, c, d, dp, (cudaStream_t)st));
+}
+EF_API int ef_op_pyr_down_gauss_u8(const uint8_t * s, size_t sp, int r, int c, uint8_t * d, size_t dp, void * st)
+{
+    EF_OP_RET(launch_pyr_down_gauss_u8(s, sp, r, c, d, dp, (cudaStream_t)st));
+}
+EF_API int ef_op_bgr_to_intensity(const uint8_t * s, size_t sp, int r, int c, uint8_t * d, size_t dp, void * st)
+{
+    EF_OP_RET(launch_bgr_to_intensity(s, sp, r, c, d, dp, (cudaStream_t)st));
+}
+EF_API int ef_op_derivative_images(const uint8_t * s, size_t sp, int r, int c, int16_t * dx, int16_t * dy, size_t dp, void * st)
+{
+    EF_OP_RET(launch_derivative_images(s, sp, r, c, dx, dy, dp, (cudaStream_t)st));
+}
+EF_API int ef_op_project_point_cloud(const float * depth, size_t dp, int rows, int cols, float fx, float fy, float cx, float cy, int level,
+                                     float * cloud, size_t cp, void * st)
+{
+    const int div = 1 << level; // CameraModel::operator()(level)
+    EF_OP_RET(launch_project_points(depth, dp, rows, cols, fx / div, fy / div, cx / div, cy / div, cloud, cp, (cudaStream_t)st));
+}
+
+static int op_fetch(void * scratch, void * host, size_t bytes, cudaStream_t s)
+{
+    cudaError_t e = cudaMemcpyAsync(host, static_cast<char *>(scratch) + kScratchResultOff, bytes, cudaMemcpyDeviceToHost, s);
+    if(e == cudaSuccess) e = cudaStreamSynchronize(s);
+    return (int)e;
+}
+
+static int op_reset_ticket(void * scratch, cudaStream_t s) { return (int)cudaMemsetAsync(scratch, 0, 128, s); }
+
+EF_API int ef_op_icp_step(const float * Rcurr, const float * tcurr, const float * vc, const float * nc, const float * Rprev_inv, const float * tprev,
+                          float fx, float fy, float cx, float cy, const float * vp, const float * np, size_t pitch, float dist_thresh,
+                          float angle_thresh, int rows, int cols, void * scratch, float * A, float * b, float * residual, void * st)
+{
+    if(ef_device_count() <= 0) return EF_ERR_NO_DEVICE;
+    if(!scratch) return EF_ERR_INVALID_ARGUMENT;
+    IcpArgs a;
+    memcpy(a.Rcurr, Rcurr, 36); memcpy(a.tcurr, tcurr, 12); memcpy(a.Rprev_inv, Rprev_inv, 36); memcpy(a.tprev, tprev, 12);
+    a.fx = fx; a.fy = fy; a.cx = cx; a.cy = cy;
+    a.dist_thresh = dist_thresh; a.angle_thresh = angle_thresh;
+    a.rows = rows; a.cols = cols;
+    a.vmap_curr = vc; a.nmap_curr = nc; a.vmap_g_prev = vp; a.nmap_g_prev = np;
+    a.pitch = pitch;
+    int rc = op_reset_ticket(scratch, (cudaStream_t)st);
+    if(rc) return rc;
+    rc = (int)launch_icp_step(a, scratch, (cudaStream_t)st);
+    if(rc) return rc;
+    float h[29];
+    rc = op_fetch(scratch, h, sizeof(h), (cudaStream_t)st);
+    if(rc) return rc;
+    hm::unpack_se3(h, A, b, residual);
+    return EF_OK;
+}
+
+EF_API int ef_op_rgb_residual(float min_scale, const int16_t * dIdx, const int16_t * dIdy, size_t d_pitch, const float * last_depth,
+                              const float * next_depth, size_t depth_pitch, const uint8_t * last_image, const uint8_t * next_image,
+                              size_t image_pitch, void * corres, float max_depth_delta, const float * kt, const float * krkinv, int rows, int cols,
+                              void * scratch, int * sigma_sum, int * count, void * st)
+{
+    if(ef_device_count() <= 0) return EF_ERR_NO_DEVICE;
+    if(!scratch || !corres) return EF_ERR_INVALID_ARGUMENT;
+    RgbResArgs a;
+    a.min_scale = min_scale; a.max_depth_delta = max_depth_delta;
+    memcpy(a.kt, kt, 12); memcpy(a.krkinv, krkinv, 36);
+    a.rows = rows; a.cols = cols;
+    a.dIdx = dIdx; a.dIdy = dIdy; a.d_pitch = d_pitch;
+    a.last_depth = last_depth; a.next_depth = next_depth; a.depth_pitch = depth_pitch;
+    a.last_image = last_image; a.next_image = next_image; a.image_pitch = image_pitch;
+    a.corres = corres;
+    int rc = op_reset_ticket(scratch, (cudaStream_t)st);
+    if(rc) return rc;
+    rc = (int)launch_rgb_residual(a, scratch, (cudaStream_t)st);
+    if(rc) return rc;
+    int h[2];
+    rc = op_fetch(scratch, h, sizeof(h), (cudaStream_t)st);
+    if(rc) return rc;
+    *count = h[0];
+    *sigma_sum = h[1];
+    return EF_OK;
+}
+
+EF_API int ef_op_rgb_step(const void * corres, float sigma, const float * cloud, size_t cloud_pitch, float fx, float fy, const int16_t * dIdx,
+                          const int16_t * dIdy, size_t d_pitch, float sobel_scale, int rows, int cols, void * scratch, float * A, float * b, void * st)
+{
+    if(ef_device_count() <= 0) return EF_ERR_NO_DEVICE;
+    if(!scratch) return EF_ERR_INVALID_ARGUMENT;
+    RgbStepArgs a;
+    a.corres = corres; a.sigma = sigma; a.cloud = cloud; a.cloud_pitch = cloud_pitch;
+    a.fx = fx; a.fy = fy; a.dIdx = dIdx; a.dIdy = dIdy; a.d_pitch = d_pitch; a.sobel_scale = sobel_scale;
+    a.rows = rows; a.cols = cols;
+    int rc = op_reset_ticket(scratch, (cudaStream_t)st);
+    if(rc) return rc;
+    rc = (int)launch_rgb_step(a, scratch, (cudaStream_t)st);
+    if(rc) return rc;
+    float h[29];
+    rc = op_fetch(scratch, h, sizeof(h), (cudaStream_t)st);
+    if(rc) return rc;
+    hm::unpack_se3(h, A, b, (float *)nullptr);
+    return EF_OK;
+}
+
+EF_API int ef_op_so3_step(const uint8_t * last_image, const uint8_t * next_image, size_t image_pitch, const float * image_basis, const float * kinv,
+                          const float * krlr, int rows, int cols, void * scratch, float * A, float * b, float * residual, void * st)
+{
+    if(ef_device_count() <= 0) return EF_ERR_NO_DEVICE;
+    if(!scratch) return EF_ERR_INVALID_ARGUMENT;
+    So3Args a;
+    a.last_image = last_image; a.next_image = next_image; a.image_pitch = image_pitch;
+    memcpy(a.image_basis, image_basis, 36); memcpy(a.kinv, kinv, 36); memcpy(a.krlr, krlr, 36);
+    a.rows = rows; a.cols = cols;
+    int rc = op_reset_ticket(scratch, (cudaStream_t)st);
+    if(rc) return rc;
+    rc = (int)launch_so3_step(a, scratch, (cudaStream_t)st);
+    if(rc) return rc;
+    float h[11];
+    rc = op_fetch(scratch, h, sizeof(h), (cudaStream_t)st);
+    if(rc) return rc;
+    hm::unpack_so3(h, A, b, residual);
+    return EF_OK;
+}

@@ -1,0 +1,234 @@
+// ef_hostmath.h -- host-side (and, where marked, device-side) small dense linear algebra of the tracker
+// driver: the operations RGBDOdometry.cpp delegates to Eigen (an un-vendored dependency of the
+// reference): fixed-size inverses, symmetric-pivoted LDL^T solves, Rodrigues' formula
+// (OdometryProvider.h:35-71) and the SE(3) update (OdometryProvider.h:73-93).
+//
+// Everything is templated on the scalar and written without FMA-sensitive tricks so the SAME source
+// runs on the host (EF_SOLVE_HOST) and inside the persistent kernel's single solver thread
+// (EF_SOLVE_DEVICE).
+#pragma once
+
+#include <math.h>
+
+#if defined(__CUDACC__)
+#define EF_HD __host__ __device__ __forceinline__
+#else
+#define EF_HD inline
+#endif
+
+namespace ef
+{
+namespace hm
+{
+
+template<class T> EF_HD T absT(T v) { return v < T(0) ? -v : v; }
+
+// C = A * B, 3x3 row-major (C may alias A or B)
+template<class T> EF_HD void mul33(const T * A, const T * B, T * C)
+{
+    T r[9];
+    for(int i = 0; i < 3; i++)
+        for(int j = 0; j < 3; j++) r[i * 3 + j] = A[i * 3 + 0] * B[0 * 3 + j] + A[i * 3 + 1] * B[1 * 3 + j] + A[i * 3 + 2] * B[2 * 3 + j];
+    for(int i = 0; i < 9; i++) C[i] = r[i];
+}
+
+// adjugate / determinant inverse (what Eigen uses for fixed 3x3)
+template<class T> EF_HD void inverse33(const T * m, T * o)
+{
+    const T c00 = m[4] * m[8] - m[5] * m[7];
+    const T c01 = m[5] * m[6] - m[3] * m[8];
+    const T c02 = m[3] * m[7] - m[4] * m[6];
+    const T det = m[0] * c00 + m[1] * c01 + m[2] * c02;
+    const T id = T(1) / det;
+    T r[9];
+    r[0] = c00 * id; r[1] = (m[2] * m[7] - m[1] * m[8]) * id; r[2] = (m[1] * m[5] - m[2] * m[4]) * id;
+    r[3] = c01 * id; r[4] = (m[0] * m[8] - m[2] * m[6]) * id; r[5] = (m[2] * m[3] - m[0] * m[5]) * id;
+    r[6] = c02 * id; r[7] = (m[1] * m[6] - m[0] * m[7]) * id; r[8] = (m[0] * m[4] - m[1] * m[3]) * id;
+    for(int i = 0; i < 9; i++) o[i] = r[i];
+}
+
+// general NxN inverse, Gauss-Jordan with partial pivoting (N = 4 for resultRt, 6 for the covariance)
+template<class T, int N> EF_HD void inverseNN(const T * M, T * Minv)
+{
+    T a[N][2 * N];
+    for(int i = 0; i < N; i++)
+        for(int j = 0; j < N; j++)
+        {
+            a[i][j] = M[i * N + j];
+            a[i][N + j] = (i == j) ? T(1) : T(0);
+        }
+    for(int c = 0; c < N; c++)
+    {
+        int p = c;
+        for(int r = c + 1; r < N; r++)
+            if(absT(a[r][c]) > absT(a[p][c])) p = r;
+        if(p != c)
+            for(int j = 0; j < 2 * N; j++)
+            {
+                const T t = a[c][j];
+                a[c][j] = a[p][j];
+                a[p][j] = t;
+            }
+        const T inv = T(1) / a[c][c];
+        for(int j = 0; j < 2 * N; j++) a[c][j] *= inv;
+        for(int r = 0; r < N; r++)
+            if(r != c)
+            {
+                const T f = a[r][c];
+                if(f != T(0))
+                    for(int j = 0; j < 2 * N; j++) a[r][j] -= f * a[c][j];
+            }
+    }
+    for(int i = 0; i < N; i++)
+        for(int j = 0; j < N; j++) Minv[i * N + j] = a[i][N + j];
+}
+
+// x = A^-1 b through a symmetric-pivoted LDL^T (Eigen's A.ldlt().solve(b))
+template<class T, int N> EF_HD void ldlt_solve(const T * A_in, const T * b, T * x)
+{
+    T A[N * N], y[N];
+    int perm[N];
+    for(int i = 0; i < N * N; i++) A[i] = A_in[i];
+    for(int i = 0; i < N; i++) perm[i] = i;
+    for(int k = 0; k < N; k++)
+    {
+        int p = k;
+        T best = absT(A[k * N + k]);
+        for(int i = k + 1; i < N; i++)
+            if(absT(A[i * N + i]) > best)
+            {
+                best = absT(A[i * N + i]);
+                p = i;
+            }
+        if(p != k)
+        {
+            for(int j = 0; j < N; j++) { const T t = A[k * N + j]; A[k * N + j] = A[p * N + j]; A[p * N + j] = t; }
+            for(int i = 0; i < N; i++) { const T t = A[i * N + k]; A[i * N + k] = A[i * N + p]; A[i * N + p] = t; }
+            const int t = perm[k]; perm[k] = perm[p]; perm[p] = t;
+        }
+        const T d = A[k * N + k];
+        if(d == T(0)) continue;
+        for(int i = k + 1; i < N; i++) A[i * N + k] /= d;
+        for(int i = k + 1; i < N; i++)
+            for(int j = k + 1; j <= i; j++)
+            {
+                A[i * N + j] -= A[i * N + k] * d * A[j * N + k];
+                A[j * N + i] = A[i * N + j];
+            }
+    }
+    for(int i = 0; i < N; i++) y[i] = b[perm[i]];
+    for(int i = 0; i < N; i++)
+        for(int j = 0; j < i; j++) y[i] -= A[i * N + j] * y[j];
+    for(int i = 0; i < N; i++) y[i] = (A[i * N + i] != T(0)) ? y[i] / A[i * N + i] : T(0);
+    for(int i = N - 1; i >= 0; i--)
+        for(int j = i + 1; j < N; j++) y[i] -= A[j * N + i] * y[j];
+    for(int i = 0; i < N; i++) x[perm[i]] = y[i];
+}
+
+// OdometryProvider.h:35-71
+EF_HD void rodrigues(const double * src, double * R)
+{
+    for(int k = 0; k < 9; k++) R[k] = (k % 4 == 0) ? 1.0 : 0.0;
+    double rx = src[0], ry = src[1], rz = src[2];
+    const double theta = sqrt(rx * rx + ry * ry + rz * rz);
+    if(theta >= 2.2204460492503131e-16)
+    {
+        const double c = cos(theta), s = sin(theta), c1 = 1. - c;
+        const double itheta = theta ? 1. / theta : 0.;
+        rx *= itheta; ry *= itheta; rz *= itheta;
+        const double rrt[9] = {rx * rx, rx * ry, rx * rz, rx * ry, ry * ry, ry * rz, rx * rz, ry * rz, rz * rz};
+        const double r_x[9] = {0, -rz, ry, rz, 0, -rx, -ry, rx, 0};
+        for(int k = 0; k < 9; k++) R[k] = c * ((k % 4 == 0) ? 1.0 : 0.0) + c1 * rrt[k] + s * r_x[k];
+    }
+}
+
+// OdometryProvider.h:73-93: resultRt = [rodrigues(x[3:6]) | x[0:3]] * resultRt (row-major 4x4 double)
+EF_HD void update_se3(double * resultRt, const double * x)
+{
+    double R[9], U[16], N[16];
+    rodrigues(x + 3, R);
+    for(int i = 0; i < 16; i++) U[i] = (i % 5 == 0) ? 1.0 : 0.0;
+    for(int r = 0; r < 3; r++)
+    {
+        for(int c = 0; c < 3; c++) U[r * 4 + c] = R[r * 3 + c];
+        U[r * 4 + 3] = x[r];
+    }
+    for(int r = 0; r < 4; r++)
+        for(int c = 0; c < 4; c++)
+        {
+            double s = 0;
+            for(int k = 0; k < 4; k++) s += U[r * 4 + k] * resultRt[k * 4 + c];
+            N[r * 4 + c] = s;
+        }
+    for(int i = 0; i < 16; i++) resultRt[i] = N[i];
+}
+
+// RGBDOdometry.cpp:571-583: [Rcurr|tcurr] = [Rprev|tprev] * (float(resultRt))^-1, with the Isometry3f
+// inverse (transpose rotation, -R^T t), all in float.
+EF_HD void compose_pose(const double * resultRt, const float * Rprev, const float * tprev, float * Rcurr, float * tcurr)
+{
+    float oR[9], ot[3], iR[9], it[3];
+    for(int r = 0; r < 3; r++)
+    {
+        for(int c = 0; c < 3; c++) oR[r * 3 + c] = (float)resultRt[r * 4 + c];
+        ot[r] = (float)resultRt[r * 4 + 3];
+    }
+    for(int r = 0; r < 3; r++)
+        for(int c = 0; c < 3; c++) iR[r * 3 + c] = oR[c * 3 + r];
+    for(int r = 0; r < 3; r++) it[r] = -(iR[r * 3] * ot[0] + iR[r * 3 + 1] * ot[1] + iR[r * 3 + 2] * ot[2]);
+    for(int r = 0; r < 3; r++)
+    {
+        for(int c = 0; c < 3; c++) Rcurr[r * 3 + c] = Rprev[r * 3] * iR[c] + Rprev[r * 3 + 1] * iR[3 + c] + Rprev[r * 3 + 2] * iR[6 + c];
+        tcurr[r] = Rprev[r * 3] * it[0] + Rprev[r * 3 + 1] * it[1] + Rprev[r * 3 + 2] * it[2] + tprev[r];
+    }
+}
+
+// RGBDOdometry.cpp:424-434: from resultRt build krkInv = K R K^-1 and kt = K t of Rt = resultRt^-1
+EF_HD void rgb_warp_params(const double * resultRt, const double * K, const double * K_inv, float * krkinv9, float * kt3)
+{
+    double Rt[16];
+    inverseNN<double, 4>(resultRt, Rt);
+    const double R[9] = {Rt[0], Rt[1], Rt[2], Rt[4], Rt[5], Rt[6], Rt[8], Rt[9], Rt[10]};
+    double tmp[9], KRK[9];
+    mul33(K, R, tmp);
+    mul33(tmp, K_inv, KRK);
+    for(int i = 0; i < 9; i++) krkinv9[i] = (float)KRK[i];
+    const double tv[3] = {Rt[3], Rt[7], Rt[11]};
+    for(int r = 0; r < 3; r++) kt3[r] = (float)(K[r * 3] * tv[0] + K[r * 3 + 1] * tv[1] + K[r * 3 + 2] * tv[2]);
+}
+
+// unpack the 29-float accumulator into A (6x6 row-major), b, residual[2]: reduce.cu:475-489
+template<class TA> EF_HD void unpack_se3(const float * h, TA * A, TA * b, float * residual)
+{
+    int shift = 0;
+    for(int i = 0; i < 6; ++i)
+        for(int j = i; j < 7; ++j)
+        {
+            const float value = h[shift++];
+            if(j == 6) b[i] = (TA)value;
+            else A[j * 6 + i] = A[i * 6 + j] = (TA)value;
+        }
+    if(residual)
+    {
+        residual[0] = h[27];
+        residual[1] = h[28];
+    }
+}
+
+// reduce.cu:1126-1140
+EF_HD void unpack_so3(const float * h, float * A, float * b, float * residual)
+{
+    int shift = 0;
+    for(int i = 0; i < 3; ++i)
+        for(int j = i; j < 4; ++j)
+        {
+            const float value = h[shift++];
+            if(j == 3) b[i] = value;
+            else A[j * 3 + i] = A[i * 3 + j] = value;
+        }
+    residual[0] = h[9];
+    residual[1] = h[10];
+}
+
+} // namespace hm
+} // namespace ef

@@ -1,0 +1,90 @@
+// ef_kernels.h -- internal launcher declarations shared by the C-ABI layer (ef_api.cu) and the kernels.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace ef
+{
+
+// ---- Tier-2 image operators (ef_ops_image.cu); pitches in bytes, 0 = dense ----
+cudaError_t launch_pyr_down_u16(const uint16_t * src, size_t sp, int srows, int scols, uint16_t * dst, size_t dp, cudaStream_t s);
+cudaError_t launch_create_vmap(const uint16_t * depth, size_t dp, int rows, int cols, float fx, float fy, float cx, float cy, float cutoff,
+                               float * vmap, size_t vp, cudaStream_t s);
+cudaError_t launch_create_nmap(const float * vmap, size_t vp, int rows, int cols, float * nmap, size_t np, cudaStream_t s);
+cudaError_t launch_transform_maps(const float * vsrc, const float * nsrc, size_t sp, int rows, int cols, const float * R, const float * t,
+                                  float * vdst, float * ndst, size_t dp, cudaStream_t s);
+cudaError_t launch_copy_maps(const float * v4, const float * n4, int rows, int cols, float * vdst, float * ndst, size_t dp, cudaStream_t s);
+cudaError_t launch_resize_map(const float * in, size_t ip, int srows, int scols, float * out, size_t op, int normalize, cudaStream_t s);
+cudaError_t launch_vertices_to_depth(const float * v4, int rows, int cols, float cutoff, float * dst, size_t dp, cudaStream_t s);
+cudaError_t launch_z_to_depth(const float * z, int rows, int cols, float cutoff, float * dst, size_t dp, cudaStream_t s);
+cudaError_t launch_extract_z(const float * v4, int n, float * z, cudaStream_t s);
+cudaError_t launch_pyr_down_gauss_f32(const float * src, size_t sp, int srows, int scols, float * dst, size_t dp, cudaStream_t s);
+cudaError_t launch_pyr_down_gauss_u8(const uint8_t * src, size_t sp, int srows, int scols, uint8_t * dst, size_t dp, cudaStream_t s);
+cudaError_t launch_bgr_to_intensity(const uint8_t * rgba, size_t sp, int rows, int cols, uint8_t * dst, size_t dp, cudaStream_t s);
+cudaError_t launch_derivative_images(const uint8_t * src, size_t sp, int rows, int cols, int16_t * dx, int16_t * dy, size_t dp, cudaStream_t s);
+cudaError_t launch_project_points(const float * depth, size_t dp, int rows, int cols, float fx, float fy, float cx, float cy, float * cloud,
+                                  size_t cp, cudaStream_t s);
+
+// ---- Tier-2 association + reduction operators (ef_ops_reduce.cu) ----
+// Scratch block layout (device): [0] ticket (u32) | [128] result (32 floats / 2 ints) | [256] partial rows
+constexpr size_t kScratchTicketOff = 0;
+constexpr size_t kScratchResultOff = 128;
+constexpr size_t kScratchPartialOff = 256;
+constexpr int kMaxReduceBlocks = 2048;
+constexpr size_t kScratchBytes = kScratchPartialOff + (size_t)kMaxReduceBlocks * 32 * sizeof(float);
+
+struct IcpArgs
+{
+    float Rcurr[9], tcurr[3], Rprev_inv[9], tprev[3];
+    float fx, fy, cx, cy; // level intrinsics
+    float dist_thresh, angle_thresh;
+    int rows, cols;
+    const float * vmap_curr, * nmap_curr, * vmap_g_prev, * nmap_g_prev;
+    size_t pitch; // bytes, same for the four maps (0 = dense)
+};
+// result: 29 floats at scratch + kScratchResultOff
+cudaError_t launch_icp_step(const IcpArgs & a, void * scratch, cudaStream_t s);
+
+struct RgbResArgs
+{
+    float min_scale, max_depth_delta;
+    float kt[3], krkinv[9];
+    int rows, cols;
+    const int16_t * dIdx, * dIdy;
+    size_t d_pitch;
+    const float * last_depth, * next_depth;
+    size_t depth_pitch;
+    const uint8_t * last_image, * next_image;
+    size_t image_pitch;
+    void * corres; // rows*cols 16-byte records, linear
+};
+// result: int2 {count, sigma} at scratch + kScratchResultOff
+cudaError_t launch_rgb_residual(const RgbResArgs & a, void * scratch, cudaStream_t s);
+
+struct RgbStepArgs
+{
+    const void * corres;
+    float sigma;
+    const float * cloud;
+    size_t cloud_pitch;
+    float fx, fy;
+    const int16_t * dIdx, * dIdy;
+    size_t d_pitch;
+    float sobel_scale;
+    int rows, cols;
+};
+cudaError_t launch_rgb_step(const RgbStepArgs & a, void * scratch, cudaStream_t s);
+
+struct So3Args
+{
+    const uint8_t * last_image, * next_image;
+    size_t image_pitch;
+    float image_basis[9], kinv[9], krlr[9];
+    int rows, cols;
+};
+// result: 11 floats
+cudaError_t launch_so3_step(const So3Args & a, void * scratch, cudaStream_t s);
+
+} // namespace ef

@@ -1,0 +1,91 @@
+// ef_tracker.h -- the tracker handle behind the C ABI (include/ef_track.h): device memory arena,
+// pyramids, staging buffers, pinned result block.  Mirrors the members of class RGBDOdometry
+// (elasticfusionpublic/Core/src/Utils/RGBDOdometry.h:75-133) with dense rows instead of
+// cudaMallocPitch'ed DeviceArray2D.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+
+#include "../../include/ef_track.h"
+
+namespace ef
+{
+
+constexpr int kNumPyrs = 3; // RGBDOdometry.h:107
+
+struct LevelDims
+{
+    int rows, cols;
+    size_t n() const { return (size_t)rows * cols; }
+};
+
+} // namespace ef
+
+struct ef_tracker
+{
+    int width, height;
+    float cx, cy, fx, fy;
+    float dist_thresh, angle_thresh;
+    float sobel_scale, max_depth_delta_rgb, max_depth_rgb; // RGBDOdometry.cpp:34-37
+    float min_grad[ef::kNumPyrs];                          // :107-110
+    ef::LevelDims dims[ef::kNumPyrs];
+
+    int device;
+    int num_sms;
+    cudaStream_t stream;
+    bool own_stream;
+
+    int solve_mode;  // EF_SOLVE_HOST | EF_SOLVE_DEVICE
+    int use_graph;
+    int fused_build;
+
+    // one device arena, sliced
+    void * arena;
+    size_t arena_bytes;
+
+    uint16_t * depth_tmp[ef::kNumPyrs];
+    float * tmp_z; // z channel of the vertex map last given to init_icp_maps/init_icp_model (stands for vmaps_tmp)
+    float * vmap_curr[ef::kNumPyrs], * nmap_curr[ef::kNumPyrs];
+    float * vmap_g_prev[ef::kNumPyrs], * nmap_g_prev[ef::kNumPyrs];
+    float * last_depth[ef::kNumPyrs], * next_depth[ef::kNumPyrs];
+    uint8_t * last_image[ef::kNumPyrs], * next_image[ef::kNumPyrs], * last_next_image[ef::kNumPyrs];
+    int16_t * dIdx[ef::kNumPyrs], * dIdy[ef::kNumPyrs];
+    void * corres[ef::kNumPyrs]; // 16-byte DataTerm records (host-solve path)
+    float * cloud[ef::kNumPyrs]; // float3 point clouds (host-solve path)
+    void * scratch;              // reduction scratch (ef_kernels.h layout)
+
+    // staging for the _host and _array entry points
+    uint16_t * stage_depth;
+    uint8_t * stage_rgba;
+    float * stage_v, * stage_n;
+
+    // persistent-kernel state (EF_SOLVE_DEVICE)
+    void * track_state; // device TrackState
+    void * h_track_out; // pinned TrackOutput
+    bool launch_pending;
+    struct
+    {
+        float trans[3], rot[9];
+        int rgb_only, pyramid, fast_odom, so3;
+        float icp_weight;
+    } pending;
+
+    float * h_result; // pinned, 32 floats
+    bool deriv_valid; // dIdx/dIdy match next_image
+
+    ef_track_stats st;
+    std::string err;
+    long long launches;
+};
+
+namespace ef
+{
+// EF_SOLVE_DEVICE path (ef_track_kernel.cu)
+int device_track_init(ef_tracker * t);
+void device_track_destroy(ef_tracker * t);
+int device_track_launch(ef_tracker * t, const float * trans, const float * rot, int rgb_only, float icp_weight, int pyramid, int fast_odom,
+                        int so3);
+int device_track_finish(ef_tracker * t, float * trans, float * rot);
+} // namespace ef

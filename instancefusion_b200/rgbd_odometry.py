@@ -1,0 +1,208 @@
+"""Python mirror of class RGBDOdometry (elasticfusionpublic/Core/src/Utils/RGBDOdometry.h:31-134)
+over the C ABI.  Same method names, argument meaning and call-order contract as the reference; a
+GPUTexture* argument becomes either a CUDA torch tensor (device pointer borrowed for the call) or a
+host numpy array / CPU tensor (copied through the handle's staging buffers, `_host` entry points).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import binding
+from .binding import EFError, TrackStats
+
+EF_OPT_SOLVE_MODE, EF_OPT_USE_GRAPH, EF_OPT_FUSED_BUILD = 1, 2, 3
+EF_SOLVE_HOST, EF_SOLVE_DEVICE = 0, 1
+
+_LEVEL_BUFFERS = {"vmap_curr": (np.float32, 3), "nmap_curr": (np.float32, 3), "vmap_g_prev": (np.float32, 3),
+                  "nmap_g_prev": (np.float32, 3), "last_depth": (np.float32, 1), "next_depth": (np.float32, 1),
+                  "last_image": (np.uint8, 1), "next_image": (np.uint8, 1), "last_next_image": (np.uint8, 1),
+                  "dIdx": (np.int16, 1), "dIdy": (np.int16, 1), "depth_tmp": (np.uint16, 1)}
+
+
+def _is_cuda_tensor(a) -> bool:
+    return hasattr(a, "is_cuda") and a.is_cuda
+
+
+def _dev_ptr(a, dtype_name: str):
+    import torch
+    want = getattr(torch, dtype_name)
+    if a.dtype != want or not a.is_contiguous():
+        raise ValueError(f"expected a contiguous {dtype_name} CUDA tensor, got {a.dtype}")
+    return C.c_void_p(a.data_ptr())
+
+
+def _host_arr(a, dtype):
+    if hasattr(a, "numpy"):
+        a = a.numpy()
+    return np.ascontiguousarray(a, dtype=dtype)
+
+
+class RGBDOdometry:
+    """RGBDOdometry(width, height, cx, cy, fx, fy, distThresh=0.10, angleThresh=sin(20 deg))"""
+
+    def __init__(self, width, height, cx, cy, fx, fy, distThresh=None, angleThresh=None, stream=None,
+                 solve_mode=EF_SOLVE_HOST):
+        self._L = binding.lib()
+        if distThresh is None:
+            distThresh = self._L.ef_default_dist_thresh()
+        if angleThresh is None:
+            angleThresh = self._L.ef_default_angle_thresh()
+        self.width, self.height = int(width), int(height)
+        h = C.c_void_p()
+        rc = self._L.ef_tracker_create(C.c_int(width), C.c_int(height), C.c_float(cx), C.c_float(cy), C.c_float(fx),
+                                       C.c_float(fy), C.c_float(distThresh), C.c_float(angleThresh),
+                                       C.c_void_p(stream), C.byref(h))
+        if rc != 0:
+            raise EFError(rc, "ef_tracker_create", "no CUDA device (no CPU fallback)" if rc == -2 else "")
+        self._h = h
+        self._stats = TrackStats()
+        # public fields of the reference class (RGBDOdometry.h:64-73)
+        self.lastICPError = 0.0
+        self.lastICPCount = float(width * height)
+        self.lastRGBError = 0.0
+        self.lastRGBCount = float(width * height)
+        self.lastSO3Error = 0.0
+        self.lastSO3Count = float(width * height)
+        self.lastA = np.zeros((6, 6))
+        self.lastb = np.zeros(6)
+        self.so3_iterations = 0
+        self.se3_iterations = [0, 0, 0]
+        if solve_mode != EF_SOLVE_HOST:
+            self.set_option(EF_OPT_SOLVE_MODE, solve_mode)
+
+    # -- plumbing ---------------------------------------------------------------------------------
+    def _check(self, rc, where):
+        if rc != 0:
+            raise EFError(rc, where, self._L.ef_last_error(self._h).decode())
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.ef_tracker_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_option(self, key, value):
+        self._check(self._L.ef_tracker_set_option(self._h, C.c_int(key), C.c_int(value)), "ef_tracker_set_option")
+
+    @property
+    def stream(self):
+        return self._L.ef_tracker_stream(self._h)
+
+    @property
+    def launch_count(self):
+        return int(self._L.ef_tracker_launch_count(self._h))
+
+    def synchronize(self):
+        self._check(self._L.ef_tracker_synchronize(self._h), "ef_tracker_synchronize")
+
+    # -- the reference API ------------------------------------------------------------------------
+    def initICP(self, *args):
+        """initICP(filteredDepth, depthCutoff)  or  initICP(predictedVertices, predictedNormals, depthCutoff)"""
+        if len(args) == 2:
+            depth, cutoff = args
+            if _is_cuda_tensor(depth):
+                self._check(self._L.ef_init_icp_depth(self._h, _dev_ptr(depth, "uint16"), C.c_size_t(0), C.c_float(cutoff)),
+                            "ef_init_icp_depth")
+            else:
+                d = _host_arr(depth, np.uint16)
+                self._keep = d
+                self._check(self._L.ef_init_icp_depth_host(self._h, d.ctypes.data_as(C.c_void_p), C.c_float(cutoff)),
+                            "ef_init_icp_depth_host")
+        elif len(args) == 3:
+            v, n, cutoff = args
+            if _is_cuda_tensor(v):
+                self._check(self._L.ef_init_icp_maps(self._h, _dev_ptr(v, "float32"), _dev_ptr(n, "float32"), C.c_float(cutoff)),
+                            "ef_init_icp_maps")
+            else:
+                hv, hn = _host_arr(v, np.float32), _host_arr(n, np.float32)
+                self._keep = (hv, hn)
+                self._check(self._L.ef_init_icp_maps_host(self._h, hv.ctypes.data_as(C.c_void_p), hn.ctypes.data_as(C.c_void_p),
+                                                          C.c_float(cutoff)), "ef_init_icp_maps_host")
+        else:
+            raise TypeError("initICP takes (depth, cutoff) or (vertices, normals, cutoff)")
+
+    def initICPModel(self, predictedVertices, predictedNormals, depthCutoff, modelPose):
+        pose = np.ascontiguousarray(np.asarray(modelPose, dtype=np.float32).reshape(16))
+        if _is_cuda_tensor(predictedVertices):
+            self._check(self._L.ef_init_icp_model(self._h, _dev_ptr(predictedVertices, "float32"), _dev_ptr(predictedNormals, "float32"),
+                                                  C.c_float(depthCutoff), pose.ctypes.data_as(C.c_void_p)), "ef_init_icp_model")
+        else:
+            hv, hn = _host_arr(predictedVertices, np.float32), _host_arr(predictedNormals, np.float32)
+            self._keep = (hv, hn)
+            self._check(self._L.ef_init_icp_model_host(self._h, hv.ctypes.data_as(C.c_void_p), hn.ctypes.data_as(C.c_void_p),
+                                                       C.c_float(depthCutoff), pose.ctypes.data_as(C.c_void_p)), "ef_init_icp_model_host")
+
+    def _rgb(self, name, rgb):
+        if _is_cuda_tensor(rgb):
+            self._check(getattr(self._L, name)(self._h, _dev_ptr(rgb, "uint8"), C.c_size_t(0)), name)
+        else:
+            h = _host_arr(rgb, np.uint8)
+            self._keep_rgb = h
+            self._check(getattr(self._L, name + "_host")(self._h, h.ctypes.data_as(C.c_void_p)), name + "_host")
+
+    def initRGB(self, rgb):
+        self._rgb("ef_init_rgb", rgb)
+
+    def initRGBModel(self, rgb):
+        self._rgb("ef_init_rgb_model", rgb)
+
+    def initFirstRGB(self, rgb):
+        self._rgb("ef_init_first_rgb", rgb)
+
+    def _publish(self):
+        s = self._stats
+        self.lastICPError, self.lastICPCount = s.last_icp_error, s.last_icp_count
+        self.lastRGBError, self.lastRGBCount = s.last_rgb_error, s.last_rgb_count
+        self.lastSO3Error, self.lastSO3Count = s.last_so3_error, s.last_so3_count
+        self.lastA = np.array(s.last_A[:]).reshape(6, 6)
+        self.lastb = np.array(s.last_b[:])
+        self.so3_iterations = s.so3_iterations
+        self.se3_iterations = list(s.se3_iterations[:])
+
+    def getIncrementalTransformation(self, trans, rot, rgbOnly, icpWeight, pyramid, fastOdom, so3):
+        """trans (3,) and rot (3,3 row-major) are the pose prior; returns the updated (trans, rot)."""
+        tr = np.ascontiguousarray(np.asarray(trans, dtype=np.float32).reshape(3)).copy()
+        ro = np.ascontiguousarray(np.asarray(rot, dtype=np.float32).reshape(9)).copy()
+        rc = self._L.ef_get_incremental_transformation(self._h, tr.ctypes.data_as(C.c_void_p), ro.ctypes.data_as(C.c_void_p),
+                                                       C.c_int(int(rgbOnly)), C.c_float(icpWeight), C.c_int(int(pyramid)),
+                                                       C.c_int(int(fastOdom)), C.c_int(int(so3)), C.byref(self._stats))
+        self._check(rc, "ef_get_incremental_transformation")
+        self._publish()
+        return tr, ro.reshape(3, 3)
+
+    def launch(self, trans, rot, rgbOnly, icpWeight, pyramid, fastOdom, so3):
+        tr = np.ascontiguousarray(np.asarray(trans, dtype=np.float32).reshape(3))
+        ro = np.ascontiguousarray(np.asarray(rot, dtype=np.float32).reshape(9))
+        rc = self._L.ef_get_incremental_transformation_launch(self._h, tr.ctypes.data_as(C.c_void_p), ro.ctypes.data_as(C.c_void_p),
+                                                              C.c_int(int(rgbOnly)), C.c_float(icpWeight), C.c_int(int(pyramid)),
+                                                              C.c_int(int(fastOdom)), C.c_int(int(so3)))
+        self._check(rc, "ef_get_incremental_transformation_launch")
+
+    def finish(self):
+        tr = np.zeros(3, np.float32)
+        ro = np.zeros(9, np.float32)
+        rc = self._L.ef_get_incremental_transformation_finish(self._h, tr.ctypes.data_as(C.c_void_p), ro.ctypes.data_as(C.c_void_p),
+                                                              C.byref(self._stats))
+        self._check(rc, "ef_get_incremental_transformation_finish")
+        self._publish()
+        return tr, ro.reshape(3, 3)
+
+    def getCovariance(self):
+        cov = np.zeros(36)
+        self._check(self._L.ef_get_covariance(self._h, cov.ctypes.data_as(C.c_void_p)), "ef_get_covariance")
+        return cov.reshape(6, 6)
+
+    # -- diagnostics ------------------------------------------------------------------------------
+    def buffer(self, name, level):
+        dt, planes = _LEVEL_BUFFERS[name]
+        out = np.zeros(((self.height >> level) * planes, self.width >> level), dt)
+        self._check(self._L.ef_tracker_download(self._h, name.encode(), C.c_int(level), out.ctypes.data_as(C.c_void_p),
+                                                C.c_size_t(out.nbytes)), "ef_tracker_download")
+        return out
