@@ -24,7 +24,10 @@ struct Intr
 
 __device__ __forceinline__ float3 operator-(const float3 & a, const float3 & b) { return make_float3(a.x - b.x, a.y - b.y, a.z - b.z); }
 __device__ __forceinline__ float3 operator+(const float3 & a, const float3 & b) { return make_float3(a.x + b.x, a.y + b.y, a.z + b.z); }
-__device__ __forceinline__ float dot3(const float3 & a, const float3 & b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+// a.x*b.x + a.y*b.y + a.z*b.z.  nvcc contracts this as  t = a.y*b.y (FMUL); t = fma(a.x, b.x, t); t = fma(a.z, b.z, t)
+// in every reference kernel (checked in its PTX: icpKernel, tranformMapsKernel), but which product it leaves
+// un-fused depends on use counts in the surrounding code -- so the order is pinned here with explicit FMAs.
+__device__ __forceinline__ float dot3(const float3 & a, const float3 & b) { return __fmaf_rn(a.z, b.z, __fmaf_rn(a.x, b.x, a.y * b.y)); }
 __device__ __forceinline__ float3 cross3(const float3 & a, const float3 & b)
 {
     return make_float3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);

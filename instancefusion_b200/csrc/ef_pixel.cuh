@@ -150,10 +150,16 @@ __device__ __forceinline__ bool rgb_residual_px(const RgbResParams & P, int x, i
     }
     if(!valid) return false;
 
-    // :813-815
-    const float transformed_d1 = (float)(d1 * (P.krkinv.r2.x * x + P.krkinv.r2.y * y + P.krkinv.r2.z) + P.kt.z);
-    u0 = __float2int_rn((d1 * (P.krkinv.r0.x * x + P.krkinv.r0.y * y + P.krkinv.r0.z) + P.kt.x) / transformed_d1);
-    v0 = __float2int_rn((d1 * (P.krkinv.r1.x * x + P.krkinv.r1.y * y + P.krkinv.r1.z) + P.kt.y) / transformed_d1);
+    // :813-815.  The reference binary evaluates  k.x*x + k.y*y + k.z  as  fma(k.x, x, k.y*y) + k.z  and the outer
+    // d1*(..) + kt as one FMA (its PTX); pinned with explicit FMAs because a 1-ulp difference flips the
+    // round-to-nearest pixel index at exact .5 ties.
+    const float xf = (float)x, yf = (float)y;
+    const float s2 = __fmaf_rn(P.krkinv.r2.x, xf, P.krkinv.r2.y * yf) + P.krkinv.r2.z;
+    const float s0 = __fmaf_rn(P.krkinv.r0.x, xf, P.krkinv.r0.y * yf) + P.krkinv.r0.z;
+    const float s1 = __fmaf_rn(P.krkinv.r1.x, xf, P.krkinv.r1.y * yf) + P.krkinv.r1.z;
+    const float transformed_d1 = __fmaf_rn(d1, s2, P.kt.z);
+    u0 = __float2int_rn(__fmaf_rn(d1, s0, P.kt.x) / transformed_d1);
+    v0 = __float2int_rn(__fmaf_rn(d1, s1, P.kt.y) / transformed_d1);
 
     if(!(u0 >= 0 && v0 >= 0 && u0 < P.cols && v0 < P.rows)) return false; // :817
 

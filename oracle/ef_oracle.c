@@ -29,8 +29,9 @@ typedef struct { float x, y, z; } f3;
 static inline f3 f3_make(float x, float y, float z) { f3 r = {x, y, z}; return r; }
 static inline f3 f3_sub(f3 a, f3 b) { return f3_make(a.x - b.x, a.y - b.y, a.z - b.z); }
 static inline f3 f3_add(f3 a, f3 b) { return f3_make(a.x + b.x, a.y + b.y, a.z + b.z); }
-/* operators.cuh:72-75, contracted the way nvcc contracts a*b + c*d + e*f */
-static inline float f3_dot(f3 a, f3 b) { return fmaf(a.z, b.z, fmaf(a.y, b.y, a.x * b.x)); }
+/* operators.cuh:72-75, contracted the way nvcc 12.9 contracts a*b + c*d + e*f for sm_100a (checked in
+ * SASS): t = c*d (FMUL); t = fma(a, b, t); t = fma(e, f, t) */
+static inline float f3_dot(f3 a, f3 b) { return fmaf(a.z, b.z, fmaf(a.x, b.x, a.y * b.y)); }
 /* operators.cuh:67-70 */
 static inline f3 f3_cross(f3 a, f3 b)
 {
@@ -366,8 +367,8 @@ void efo_bgr_to_intensity(const uint8_t * rgba, int rows, int cols, uint8_t * ds
     for(int i = 0; i < rows * cols; i++)
     {
         const uint8_t * p = rgba + (size_t)i * 4;
-        /* :560  x*0.114f + y*0.299f + z*0.587f, contracted left to right */
-        float v = fmaf((float)p[2], 0.587f, fmaf((float)p[1], 0.299f, (float)p[0] * 0.114f));
+        /* :560  x*0.114f + y*0.299f + z*0.587f ; nvcc: t = y*.299; t = fma(x,.114,t); t = fma(z,.587,t) */
+        float v = fmaf((float)p[2], 0.587f, fmaf((float)p[0], 0.114f, (float)p[1] * 0.299f));
         dst[i] = (uint8_t)float2int_rz(v);
     }
 }
@@ -560,9 +561,9 @@ void efo_rgb_residual(float min_scale, const int16_t * dIdx, const int16_t * dId
                         {
                             const float xf = (float)x, yf = (float)y;
                             /* :813-815 */
-                            float td1 = fmaf(d1, fmaf(K[7], yf, K[6] * xf) + K[8], kt[2]);
-                            int u0 = float2int_rn(fmaf(d1, fmaf(K[1], yf, K[0] * xf) + K[2], kt[0]) / td1);
-                            int v0 = float2int_rn(fmaf(d1, fmaf(K[4], yf, K[3] * xf) + K[5], kt[1]) / td1);
+                            float td1 = fmaf(d1, fmaf(K[6], xf, K[7] * yf) + K[8], kt[2]);
+                            int u0 = float2int_rn(fmaf(d1, fmaf(K[0], xf, K[1] * yf) + K[2], kt[0]) / td1);
+                            int v0 = float2int_rn(fmaf(d1, fmaf(K[3], xf, K[4] * yf) + K[5], kt[1]) / td1);
                             if(u0 >= 0 && v0 >= 0 && u0 < cols && v0 < rows)
                             {
                                 const size_t k0 = (size_t)v0 * cols + u0;
@@ -618,11 +619,11 @@ void efo_rgb_step(const efo_data_term * corres, float sigma, const float * cloud
             float dI_dy = w * sobel_scale * (float)dIdy[(size_t)c->one_y * cols + c->one_x];
             float v0 = dI_dx * fx * invz;
             float v1 = dI_dy * fy * invz;
-            float v2 = -(fmaf(v1, Y, v0 * X)) * invz;         /* :544 */
+            float v2 = -(fmaf(v0, X, v1 * Y)) * invz;         /* :544 */
             row[0] = v0; row[1] = v1; row[2] = v2;
-            row[3] = fmaf(Y, v2, -Z * v1);                    /* :549-551 */
-            row[4] = fmaf(-X, v2, Z * v0);
-            row[5] = fmaf(X, v1, -Y * v0);
+            row[3] = fmaf(-Z, v1, Y * v2);                    /* :549-551 */
+            row[4] = fmaf(Z, v0, -(X * v2));
+            row[5] = fmaf(-Y, v0, X * v1);
             products_se3(row, 1.0f, acc);
         }
     }

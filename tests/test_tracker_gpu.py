@@ -22,7 +22,10 @@ MODES = {
     "joint_so3": dict(rgbOnly=False, icpWeight=10.0, pyramid=True, fastOdom=False, so3=True),
     "rgb_only": dict(rgbOnly=True, icpWeight=10.0, pyramid=True, fastOdom=False, so3=False),
     "fast_nopyr": dict(rgbOnly=False, icpWeight=10.0, pyramid=False, fastOdom=True, so3=True),
+    # Ferns::findFrame's relocalisation call (Ferns.cpp:576-592): 80x60, maps overload, ICP only, no pyramid
+    "ferns": dict(rgbOnly=False, icpWeight=100.0, pyramid=False, fastOdom=False, so3=False),
 }
+FULL_MODES = ["icp_only", "joint", "joint_so3", "rgb_only", "fast_nopyr"]
 
 
 def _kw(m):
@@ -72,8 +75,12 @@ def test_tracker_matches_reference_cuda(size, solve_mode):
         _feed(prod, pose0f, f0, f1)
         _feed(ref, pose0f, f0, f1)
         _pyramids_match(prod, ref, h)
-        for name, m in MODES.items():
-            if name != "icp_only":
+        # 80x60 is the fern relocaliser's resolution: its coarse levels (20x15) carry no usable signal, so only
+        # the call Ferns actually makes is a meaningful parity case there
+        names = FULL_MODES if w >= 640 else ["ferns", "fast_nopyr"]
+        for name in names:
+            m = MODES[name]
+            if name != names[0]:
                 # so3 swaps next/lastNext images at the end of a call: re-feed so both start equal
                 _feed(prod, pose0f, f0, f1)
                 _feed(ref, pose0f, f0, f1)

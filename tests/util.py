@@ -88,9 +88,12 @@ def masked_map_compare(got, want, rows):
 
 
 def rot_err(Ra, Rb):
+    """rotation angle (rad) of Ra * Rb^T, computed from the skew part so it stays accurate near 0
+    (acos(1 - eps) would amplify float32 rounding of the inputs to ~3e-4)."""
     R = np.asarray(Ra, np.float64) @ np.asarray(Rb, np.float64).T
+    s = 0.5 * np.array([R[2, 1] - R[1, 2], R[0, 2] - R[2, 0], R[1, 0] - R[0, 1]])
     c = (np.trace(R) - 1) / 2
-    return math.acos(max(-1.0, min(1.0, c)))
+    return math.atan2(float(np.linalg.norm(s)), float(c))
 
 
 def se3_level_params(K, level):
