@@ -68,6 +68,7 @@ typedef struct ef_track_stats
 #define EF_OPT_SOLVE_MODE 1      /* EF_SOLVE_HOST (default) | EF_SOLVE_DEVICE */
 #define EF_OPT_USE_GRAPH 2       /* 0/1: replay the frame's kernels from a CUDA graph (device mode) */
 #define EF_OPT_FUSED_BUILD 3     /* 0/1: fused pyramid builders (default 1) instead of one kernel per operator */
+#define EF_OPT_PROFILE 4         /* 0/1: bracket the solve of every getIncrementalTransformation with CUDA events */
 
 #define EF_SOLVE_HOST 0   /* one step kernel per operator call, 6x6 LDLT + pose update in double on the host,
                              exactly the reference's control flow (RGBDOdometry.cpp:405-585) */
@@ -147,6 +148,10 @@ int ef_get_covariance(ef_tracker * t, double * cov36);
 int ef_tracker_download(ef_tracker * t, const char * name, int level, void * h_dst, size_t bytes);
 /* number of kernels this handle has launched since creation (bench.py's gpu_launches) */
 long long ef_tracker_launch_count(const ef_tracker * t);
+/* EF_OPT_PROFILE: device time (CUDA events on the handle's stream) spent in the solve part of
+ * getIncrementalTransformation -- the persistent tracker kernel in EF_SOLVE_DEVICE, the whole step loop in
+ * EF_SOLVE_HOST -- accumulated over `calls` calls since the last read; reading resets the accumulator. */
+int ef_tracker_profile(ef_tracker * t, double * solve_ms_total, long long * calls);
 
 /* ------------------------------------------------------------------------------------------ */
 /* Tier 2: per-operator entry points (Cuda/cudafuncs.cuh:64-177).  All asynchronous on `stream`  */

@@ -114,6 +114,11 @@ EF_API int ef_tracker_create(int width, int height, float cx, float cy, float fx
     t->use_graph = 0;
     t->fused_build = 1;
     t->launches = 0;
+    t->profile = 0;
+    t->ev_begin = t->ev_end = nullptr;
+    t->ev_pending = false;
+    t->prof_ms = 0.0;
+    t->prof_calls = 0;
     t->deriv_valid = false;
     t->launch_pending = false;
     t->track_state = nullptr;
@@ -203,6 +208,8 @@ EF_API int ef_tracker_destroy(ef_tracker * t)
 {
     if(!t) return EF_OK;
     cudaStreamSynchronize(t->stream);
+    if(t->ev_begin) cudaEventDestroy(t->ev_begin);
+    if(t->ev_end) cudaEventDestroy(t->ev_end);
     device_track_destroy(t);
     cudaFree(t->arena);
     cudaFreeHost(t->h_result);
@@ -222,6 +229,14 @@ EF_API int ef_tracker_set_option(ef_tracker * t, int key, int value)
         return EF_OK;
     case EF_OPT_USE_GRAPH: t->use_graph = value ? 1 : 0; return EF_OK;
     case EF_OPT_FUSED_BUILD: t->fused_build = value ? 1 : 0; return EF_OK;
+    case EF_OPT_PROFILE:
+        if(value && !t->ev_begin)
+        {
+            EF_CUDA(t, cudaEventCreate(&t->ev_begin));
+            EF_CUDA(t, cudaEventCreate(&t->ev_end));
+        }
+        t->profile = value ? 1 : 0;
+        return EF_OK;
     default: return fail(t, EF_ERR_INVALID_ARGUMENT, "unknown option");
     }
 }
@@ -234,6 +249,7 @@ EF_API int ef_tracker_get_option(ef_tracker * t, int key, int * value)
     case EF_OPT_SOLVE_MODE: *value = t->solve_mode; return EF_OK;
     case EF_OPT_USE_GRAPH: *value = t->use_graph; return EF_OK;
     case EF_OPT_FUSED_BUILD: *value = t->fused_build; return EF_OK;
+    case EF_OPT_PROFILE: *value = t->profile; return EF_OK;
     default: return EF_ERR_INVALID_ARGUMENT;
     }
 }
@@ -241,6 +257,16 @@ EF_API int ef_tracker_get_option(ef_tracker * t, int key, int * value)
 EF_API const char * ef_last_error(const ef_tracker * t) { return t ? t->err.c_str() : "null handle"; }
 EF_API void * ef_tracker_stream(ef_tracker * t) { return t ? (void *)t->stream : nullptr; }
 EF_API long long ef_tracker_launch_count(const ef_tracker * t) { return t ? t->launches : 0; }
+
+EF_API int ef_tracker_profile(ef_tracker * t, double * ms, long long * calls)
+{
+    if(!t || !ms || !calls) return EF_ERR_INVALID_ARGUMENT;
+    *ms = t->prof_ms;
+    *calls = t->prof_calls;
+    t->prof_ms = 0.0;
+    t->prof_calls = 0;
+    return EF_OK;
+}
 
 EF_API int ef_tracker_synchronize(ef_tracker * t)
 {
@@ -711,8 +737,14 @@ EF_API int ef_get_incremental_transformation_launch(ef_tracker * t, const float 
             const int rc = compute_derivatives(t);
             if(rc) return rc;
         }
+        if(t->profile) EF_CUDA(t, cudaEventRecord(t->ev_begin, t->stream));
         const int rc = device_track_launch(t, trans, rot, rgb_only, icp_weight, pyramid, fast_odom, so3);
         if(rc) return rc;
+        if(t->profile)
+        {
+            EF_CUDA(t, cudaEventRecord(t->ev_end, t->stream));
+            t->ev_pending = true;
+        }
     }
     t->launch_pending = true;
     return EF_OK;
@@ -729,9 +761,24 @@ EF_API int ef_get_incremental_transformation_finish(ef_tracker * t, float * tran
     {
         memcpy(trans, t->pending.trans, sizeof(t->pending.trans));
         memcpy(rot, t->pending.rot, sizeof(t->pending.rot));
+        if(t->profile) EF_CUDA(t, cudaEventRecord(t->ev_begin, t->stream));
         rc = track_host(t, trans, rot, t->pending.rgb_only, t->pending.icp_weight, t->pending.pyramid, t->pending.fast_odom, t->pending.so3);
+        if(!rc && t->profile)
+        {
+            EF_CUDA(t, cudaEventRecord(t->ev_end, t->stream));
+            EF_CUDA(t, cudaEventSynchronize(t->ev_end));
+            t->ev_pending = true;
+        }
     }
     if(rc) return rc;
+    if(t->ev_pending)
+    {
+        float ms = 0.f;
+        EF_CUDA(t, cudaEventElapsedTime(&ms, t->ev_begin, t->ev_end));
+        t->prof_ms += ms;
+        t->prof_calls++;
+        t->ev_pending = false;
+    }
     if(t->pending.so3) swap_so3_images(t);
     if(stats) *stats = t->st;
     return EF_OK;

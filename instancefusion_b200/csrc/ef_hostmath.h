@@ -27,8 +27,13 @@ template<class T> EF_HD T absT(T v) { return v < T(0) ? -v : v; }
 template<class T> EF_HD void mul33(const T * A, const T * B, T * C)
 {
     T r[9];
+#pragma unroll
     for(int i = 0; i < 3; i++)
+    {
+#pragma unroll
         for(int j = 0; j < 3; j++) r[i * 3 + j] = A[i * 3 + 0] * B[0 * 3 + j] + A[i * 3 + 1] * B[1 * 3 + j] + A[i * 3 + 2] * B[2 * 3 + j];
+    }
+#pragma unroll
     for(int i = 0; i < 9; i++) C[i] = r[i];
 }
 
@@ -44,6 +49,7 @@ template<class T> EF_HD void inverse33(const T * m, T * o)
     r[0] = c00 * id; r[1] = (m[2] * m[7] - m[1] * m[8]) * id; r[2] = (m[1] * m[5] - m[2] * m[4]) * id;
     r[3] = c01 * id; r[4] = (m[0] * m[8] - m[2] * m[6]) * id; r[5] = (m[2] * m[3] - m[0] * m[5]) * id;
     r[6] = c02 * id; r[7] = (m[1] * m[6] - m[0] * m[7]) * id; r[8] = (m[0] * m[4] - m[1] * m[3]) * id;
+#pragma unroll
     for(int i = 0; i < 9; i++) o[i] = r[i];
 }
 
@@ -83,51 +89,121 @@ template<class T, int N> EF_HD void inverseNN(const T * M, T * Minv)
         for(int j = 0; j < N; j++) Minv[i * N + j] = a[i][N + j];
 }
 
-// x = A^-1 b through a symmetric-pivoted LDL^T (Eigen's A.ldlt().solve(b))
+// x = A^-1 b through a symmetric-pivoted LDL^T (Eigen's A.ldlt().solve(b): pivot = largest remaining
+// |diagonal|).  Every loop bound and array index is a compile-time constant -- the pivot exchange is a chain
+// of predicated swaps -- so on the device the whole factorisation lives in registers (dynamic indexing
+// would put A in local memory and cost the single solver thread tens of microseconds).
+template<class T> EF_HD void swap_if(bool c, T & a, T & b)
+{
+    const T ta = a, tb = b;
+    a = c ? tb : ta;
+    b = c ? ta : tb;
+}
+
 template<class T, int N> EF_HD void ldlt_solve(const T * A_in, const T * b, T * x)
 {
     T A[N * N], y[N];
     int perm[N];
+#pragma unroll
     for(int i = 0; i < N * N; i++) A[i] = A_in[i];
+#pragma unroll
     for(int i = 0; i < N; i++) perm[i] = i;
+#pragma unroll
     for(int k = 0; k < N; k++)
     {
         int p = k;
         T best = absT(A[k * N + k]);
+#pragma unroll
         for(int i = k + 1; i < N; i++)
-            if(absT(A[i * N + i]) > best)
-            {
-                best = absT(A[i * N + i]);
-                p = i;
-            }
-        if(p != k)
         {
-            for(int j = 0; j < N; j++) { const T t = A[k * N + j]; A[k * N + j] = A[p * N + j]; A[p * N + j] = t; }
-            for(int i = 0; i < N; i++) { const T t = A[i * N + k]; A[i * N + k] = A[i * N + p]; A[i * N + p] = t; }
-            const int t = perm[k]; perm[k] = perm[p]; perm[p] = t;
+            const T d = absT(A[i * N + i]);
+            const bool g = d > best;
+            best = g ? d : best;
+            p = g ? i : p;
+        }
+#pragma unroll
+        for(int i = k + 1; i < N; i++)
+        {
+            const bool sw = (p == i);
+#pragma unroll
+            for(int j = 0; j < N; j++) swap_if(sw, A[k * N + j], A[i * N + j]); // rows k <-> i
+#pragma unroll
+            for(int j = 0; j < N; j++) swap_if(sw, A[j * N + k], A[j * N + i]); // cols k <-> i
+            swap_if(sw, perm[k], perm[i]);
         }
         const T d = A[k * N + k];
-        if(d == T(0)) continue;
-        for(int i = k + 1; i < N; i++) A[i * N + k] /= d;
-        for(int i = k + 1; i < N; i++)
-            for(int j = k + 1; j <= i; j++)
+        if(d != T(0))
+        {
+#pragma unroll
+            for(int i = k + 1; i < N; i++) A[i * N + k] /= d;
+#pragma unroll
+            for(int i = k + 1; i < N; i++)
             {
-                A[i * N + j] -= A[i * N + k] * d * A[j * N + k];
-                A[j * N + i] = A[i * N + j];
+#pragma unroll
+                for(int j = k + 1; j <= i; j++)
+                {
+                    A[i * N + j] -= A[i * N + k] * d * A[j * N + k];
+                    A[j * N + i] = A[i * N + j];
+                }
             }
+        }
     }
-    for(int i = 0; i < N; i++) y[i] = b[perm[i]];
+    // y = P b
+#pragma unroll
     for(int i = 0; i < N; i++)
+    {
+        T v = T(0);
+#pragma unroll
+        for(int j = 0; j < N; j++) v = (perm[i] == j) ? b[j] : v;
+        y[i] = v;
+    }
+#pragma unroll
+    for(int i = 0; i < N; i++)
+    {
+#pragma unroll
         for(int j = 0; j < i; j++) y[i] -= A[i * N + j] * y[j];
+    }
+#pragma unroll
     for(int i = 0; i < N; i++) y[i] = (A[i * N + i] != T(0)) ? y[i] / A[i * N + i] : T(0);
+#pragma unroll
     for(int i = N - 1; i >= 0; i--)
+    {
+#pragma unroll
         for(int j = i + 1; j < N; j++) y[i] -= A[j * N + i] * y[j];
-    for(int i = 0; i < N; i++) x[perm[i]] = y[i];
+    }
+    // x = P^T y
+#pragma unroll
+    for(int j = 0; j < N; j++)
+    {
+        T v = T(0);
+#pragma unroll
+        for(int i = 0; i < N; i++) v = (perm[i] == j) ? y[i] : v;
+        x[j] = v;
+    }
+}
+
+// inverse of an affine 4x4 [A t; 0 0 0 1] (row-major): [A^-1, -A^-1 t; 0 0 0 1].  This IS the general
+// inverse for such a matrix (no orthogonality assumed); resultRt keeps an exact (0,0,0,1) last row because
+// every update multiplies by a matrix with that last row (OdometryProvider.h:79-88).
+template<class T> EF_HD void inverse_affine44(const T * M, T * Minv)
+{
+    const T A[9] = {M[0], M[1], M[2], M[4], M[5], M[6], M[8], M[9], M[10]};
+    T Ai[9];
+    inverse33(A, Ai);
+#pragma unroll
+    for(int r = 0; r < 3; r++)
+    {
+#pragma unroll
+        for(int c = 0; c < 3; c++) Minv[r * 4 + c] = Ai[r * 3 + c];
+        Minv[r * 4 + 3] = -(Ai[r * 3 + 0] * M[3] + Ai[r * 3 + 1] * M[7] + Ai[r * 3 + 2] * M[11]);
+    }
+    Minv[12] = T(0); Minv[13] = T(0); Minv[14] = T(0); Minv[15] = T(1);
 }
 
 // OdometryProvider.h:35-71
 EF_HD void rodrigues(const double * src, double * R)
 {
+#pragma unroll
     for(int k = 0; k < 9; k++) R[k] = (k % 4 == 0) ? 1.0 : 0.0;
     double rx = src[0], ry = src[1], rz = src[2];
     const double theta = sqrt(rx * rx + ry * ry + rz * rz);
@@ -138,29 +214,76 @@ EF_HD void rodrigues(const double * src, double * R)
         rx *= itheta; ry *= itheta; rz *= itheta;
         const double rrt[9] = {rx * rx, rx * ry, rx * rz, rx * ry, ry * ry, ry * rz, rx * rz, ry * rz, rz * rz};
         const double r_x[9] = {0, -rz, ry, rz, 0, -rx, -ry, rx, 0};
+#pragma unroll
         for(int k = 0; k < 9; k++) R[k] = c * ((k % 4 == 0) ? 1.0 : 0.0) + c1 * rrt[k] + s * r_x[k];
     }
 }
 
-// OdometryProvider.h:73-93: resultRt = [rodrigues(x[3:6]) | x[0:3]] * resultRt (row-major 4x4 double)
+// OdometryProvider.h:73-93: resultRt = [rodrigues(x[3:6]) | x[0:3]] * resultRt (row-major 4x4 double).
+// Both factors are affine (last row exactly 0 0 0 1), so the terms the reference's full 4x4 product adds
+// for that row are exact zeros / ones: this evaluates the same sums in the same order.
 EF_HD void update_se3(double * resultRt, const double * x)
 {
-    double R[9], U[16], N[16];
+    double R[9], N[16];
     rodrigues(x + 3, R);
-    for(int i = 0; i < 16; i++) U[i] = (i % 5 == 0) ? 1.0 : 0.0;
+#pragma unroll
     for(int r = 0; r < 3; r++)
     {
-        for(int c = 0; c < 3; c++) U[r * 4 + c] = R[r * 3 + c];
-        U[r * 4 + 3] = x[r];
+#pragma unroll
+        for(int c = 0; c < 3; c++)
+            N[r * 4 + c] = R[r * 3 + 0] * resultRt[0 * 4 + c] + R[r * 3 + 1] * resultRt[1 * 4 + c] + R[r * 3 + 2] * resultRt[2 * 4 + c];
+        N[r * 4 + 3] = R[r * 3 + 0] * resultRt[3] + R[r * 3 + 1] * resultRt[7] + R[r * 3 + 2] * resultRt[11] + x[r];
     }
-    for(int r = 0; r < 4; r++)
-        for(int c = 0; c < 4; c++)
+#pragma unroll
+    for(int i = 0; i < 12; i++) resultRt[i] = N[i];
+    resultRt[12] = 0.0; resultRt[13] = 0.0; resultRt[14] = 0.0; resultRt[15] = 1.0;
+}
+
+// Unpivoted LDL^T solve of a symmetric positive-definite 6x6 system given as the 27 leading entries of the
+// JtJJtrSE3 accumulator (types.cuh:101-152: for i < 6, for j = i..6: [J|r]_i * [J|r]_j, so row i holds A(i,i..5)
+// followed by b(i)) -- used by the single device solver thread, where Eigen-style pivoting would cost hundreds
+// of predicated swaps.  For the SPD normal equations of the tracker both factorisations give the same solution
+// to ~1e-15 relative; a zero pivot (no correspondences) yields x = 0 like the pivoted routine.
+EF_HD int acc_index(int i, int j) { return i * 7 - i * (i - 1) / 2 + (j - i); } // j >= i, j == 6 selects b(i)
+
+EF_HD void ldlt_solve_spd6_acc(const double * S, double * x)
+{
+    double L[6][6], d[6], y[6];
+#pragma unroll
+    for(int j = 0; j < 6; j++)
+    {
+        double dj = S[acc_index(j, j)];
+#pragma unroll
+        for(int k = 0; k < j; k++) dj -= L[j][k] * L[j][k] * d[k];
+        d[j] = dj;
+        const double inv = (dj != 0.0) ? 1.0 / dj : 0.0;
+#pragma unroll
+        for(int i = j + 1; i < 6; i++)
         {
-            double s = 0;
-            for(int k = 0; k < 4; k++) s += U[r * 4 + k] * resultRt[k * 4 + c];
-            N[r * 4 + c] = s;
+            double v = S[acc_index(j, i)]; // A(i,j) = A(j,i)
+#pragma unroll
+            for(int k = 0; k < j; k++) v -= L[i][k] * L[j][k] * d[k];
+            L[i][j] = v * inv;
         }
-    for(int i = 0; i < 16; i++) resultRt[i] = N[i];
+    }
+#pragma unroll
+    for(int i = 0; i < 6; i++)
+    {
+        double v = S[acc_index(i, 6)];
+#pragma unroll
+        for(int k = 0; k < i; k++) v -= L[i][k] * y[k];
+        y[i] = v;
+    }
+#pragma unroll
+    for(int i = 0; i < 6; i++) y[i] = (d[i] != 0.0) ? y[i] / d[i] : 0.0;
+#pragma unroll
+    for(int i = 5; i >= 0; i--)
+    {
+        double v = y[i];
+#pragma unroll
+        for(int k = i + 1; k < 6; k++) v -= L[k][i] * x[k];
+        x[i] = v;
+    }
 }
 
 // RGBDOdometry.cpp:571-583: [Rcurr|tcurr] = [Rprev|tprev] * (float(resultRt))^-1, with the Isometry3f
@@ -168,16 +291,23 @@ EF_HD void update_se3(double * resultRt, const double * x)
 EF_HD void compose_pose(const double * resultRt, const float * Rprev, const float * tprev, float * Rcurr, float * tcurr)
 {
     float oR[9], ot[3], iR[9], it[3];
+#pragma unroll
     for(int r = 0; r < 3; r++)
     {
+#pragma unroll
         for(int c = 0; c < 3; c++) oR[r * 3 + c] = (float)resultRt[r * 4 + c];
         ot[r] = (float)resultRt[r * 4 + 3];
     }
+#pragma unroll
     for(int r = 0; r < 3; r++)
+#pragma unroll
         for(int c = 0; c < 3; c++) iR[r * 3 + c] = oR[c * 3 + r];
+#pragma unroll
     for(int r = 0; r < 3; r++) it[r] = -(iR[r * 3] * ot[0] + iR[r * 3 + 1] * ot[1] + iR[r * 3 + 2] * ot[2]);
+#pragma unroll
     for(int r = 0; r < 3; r++)
     {
+#pragma unroll
         for(int c = 0; c < 3; c++) Rcurr[r * 3 + c] = Rprev[r * 3] * iR[c] + Rprev[r * 3 + 1] * iR[3 + c] + Rprev[r * 3 + 2] * iR[6 + c];
         tcurr[r] = Rprev[r * 3] * it[0] + Rprev[r * 3 + 1] * it[1] + Rprev[r * 3 + 2] * it[2] + tprev[r];
     }
@@ -187,13 +317,15 @@ EF_HD void compose_pose(const double * resultRt, const float * Rprev, const floa
 EF_HD void rgb_warp_params(const double * resultRt, const double * K, const double * K_inv, float * krkinv9, float * kt3)
 {
     double Rt[16];
-    inverseNN<double, 4>(resultRt, Rt);
+    inverse_affine44(resultRt, Rt);
     const double R[9] = {Rt[0], Rt[1], Rt[2], Rt[4], Rt[5], Rt[6], Rt[8], Rt[9], Rt[10]};
     double tmp[9], KRK[9];
     mul33(K, R, tmp);
     mul33(tmp, K_inv, KRK);
+#pragma unroll
     for(int i = 0; i < 9; i++) krkinv9[i] = (float)KRK[i];
     const double tv[3] = {Rt[3], Rt[7], Rt[11]};
+#pragma unroll
     for(int r = 0; r < 3; r++) kt3[r] = (float)(K[r * 3] * tv[0] + K[r * 3 + 1] * tv[1] + K[r * 3 + 2] * tv[2]);
 }
 
@@ -201,7 +333,9 @@ EF_HD void rgb_warp_params(const double * resultRt, const double * K, const doub
 template<class TA> EF_HD void unpack_se3(const float * h, TA * A, TA * b, float * residual)
 {
     int shift = 0;
+#pragma unroll
     for(int i = 0; i < 6; ++i)
+#pragma unroll
         for(int j = i; j < 7; ++j)
         {
             const float value = h[shift++];
@@ -219,7 +353,9 @@ template<class TA> EF_HD void unpack_se3(const float * h, TA * A, TA * b, float 
 EF_HD void unpack_so3(const float * h, float * A, float * b, float * residual)
 {
     int shift = 0;
+#pragma unroll
     for(int i = 0; i < 3; ++i)
+#pragma unroll
         for(int j = i; j < 4; ++j)
         {
             const float value = h[shift++];

@@ -82,20 +82,45 @@ __device__ __forceinline__ void accumulate_so3(float * acc, const float * row)
     acc[10] += 1.0f;
 }
 
-// ICPReduction::search + getProducts (reduce.cu:282-347).  vcurr / ncurr are the current-frame vertex
-// and normal of this pixel (already loaded, possibly NaN-x).  Returns true and fills row[7] when a
-// correspondence is found.
+// ICPReduction::search, first half (reduce.cu:285-298): transform the current vertex into the global and the
+// previous-camera frame and project it.  Returns false when the projection leaves the image or lies behind
+// the camera (:297).  A NaN vertex projects to pixel (0,0) (cvt.rni of NaN) and is rejected later by `dist`.
+__device__ __forceinline__ bool icp_project(const IcpParams & P, const float3 & vcurr, float3 & vcurr_g, int & ux, int & uy)
+{
+    vcurr_g = P.Rcurr * vcurr + P.tcurr;
+    const float3 vcurr_cp = P.Rprev_inv * (vcurr_g - P.tprev);
+    ux = __float2int_rn(vcurr_cp.x * P.intr.fx / vcurr_cp.z + P.intr.cx); // :294
+    uy = __float2int_rn(vcurr_cp.y * P.intr.fy / vcurr_cp.z + P.intr.cy);
+    return !(ux < 0 || uy < 0 || ux >= P.cols || uy >= P.rows || vcurr_cp.z < 0); // :297
+}
+
+// ICPReduction::search, second half + getProducts (reduce.cu:310-347) once the model vertex / normal at the
+// projected pixel are known.  Returns true and fills row[7] when the correspondence is accepted.
+__device__ __forceinline__ bool icp_finish(const IcpParams & P, const float3 & vcurr_g, const float3 & ncurr, const float3 & vprev_g,
+                                           const float3 & nprev_g, float * row)
+{
+    const float3 ncurr_g = P.Rcurr * ncurr;
+    const float dist = norm3(vprev_g - vcurr_g);           // :317
+    const float sine = norm3(cross3(ncurr_g, nprev_g));    // :318
+    if(!(sine < P.angle_thresh && dist <= P.dist_thresh && !isnan(ncurr.x) && !isnan(nprev_g.x))) return false; // :324
+
+    const float3 s_cp = P.Rprev_inv * (vcurr_g - P.tprev); // :341-343
+    const float3 d_cp = P.Rprev_inv * (vprev_g - P.tprev);
+    const float3 n_cp = P.Rprev_inv * nprev_g;
+    const float3 c = cross3(s_cp, n_cp);
+    row[0] = n_cp.x; row[1] = n_cp.y; row[2] = n_cp.z;
+    row[3] = c.x; row[4] = c.y; row[5] = c.z;
+    row[6] = dot3(n_cp, s_cp - d_cp);                      // :347
+    return true;
+}
+
+// both halves with the gather in between (stand-alone operator kernel)
 __device__ __forceinline__ bool icp_row(const IcpParams & P, const float3 & vcurr, const float3 & ncurr, const Map3 & vprev,
                                         const Map3 & nprev, float * row)
 {
-    const float3 vcurr_g = P.Rcurr * vcurr + P.tcurr;
-    const float3 vcurr_cp = P.Rprev_inv * (vcurr_g - P.tprev);
-
-    const int ux = __float2int_rn(vcurr_cp.x * P.intr.fx / vcurr_cp.z + P.intr.cx); // :294
-    const int uy = __float2int_rn(vcurr_cp.y * P.intr.fy / vcurr_cp.z + P.intr.cy);
-
-    if(ux < 0 || uy < 0 || ux >= P.cols || uy >= P.rows || vcurr_cp.z < 0) return false; // :297
-
+    float3 vcurr_g;
+    int ux, uy;
+    if(!icp_project(P, vcurr, vcurr_g, ux, uy)) return false;
     float3 vprev_g, nprev_g;
     vprev_g.x = __ldg(vprev.row(0, uy) + ux);
     vprev_g.y = __ldg(vprev.row(1, uy) + ux);
@@ -103,23 +128,39 @@ __device__ __forceinline__ bool icp_row(const IcpParams & P, const float3 & vcur
     nprev_g.x = __ldg(nprev.row(0, uy) + ux);
     nprev_g.y = __ldg(nprev.row(1, uy) + ux);
     nprev_g.z = __ldg(nprev.row(2, uy) + ux);
+    return icp_finish(P, vcurr_g, ncurr, vprev_g, nprev_g, row);
+}
 
-    const float3 ncurr_g = P.Rcurr * ncurr;
+// RGBResidual::getProducts, the warp of pixel (x, y) with depth d1 into the last image (reduce.cu:813-817).
+// The reference binary evaluates  k.x*x + k.y*y + k.z  as  fma(k.x, x, k.y*y) + k.z  and the outer d1*(..) + kt as
+// one FMA (its PTX); pinned with explicit FMAs because a 1-ulp difference flips the round-to-nearest pixel
+// index at exact .5 ties.  Returns false when the warped pixel leaves the image.
+__device__ __forceinline__ bool rgb_warp(const RgbResParams & P, int x, int y, float d1, int & u0, int & v0, float & transformed_d1)
+{
+    const float xf = (float)x, yf = (float)y;
+    const float s2 = __fmaf_rn(P.krkinv.r2.x, xf, P.krkinv.r2.y * yf) + P.krkinv.r2.z;
+    const float s0 = __fmaf_rn(P.krkinv.r0.x, xf, P.krkinv.r0.y * yf) + P.krkinv.r0.z;
+    const float s1 = __fmaf_rn(P.krkinv.r1.x, xf, P.krkinv.r1.y * yf) + P.krkinv.r1.z;
+    transformed_d1 = __fmaf_rn(d1, s2, P.kt.z);
+    u0 = __float2int_rn(__fmaf_rn(d1, s0, P.kt.x) / transformed_d1);
+    v0 = __float2int_rn(__fmaf_rn(d1, s1, P.kt.y) / transformed_d1);
+    return (u0 >= 0 && v0 >= 0 && u0 < P.cols && v0 < P.rows); // :817
+}
 
-    const float dist = norm3(vprev_g - vcurr_g);           // :317
-    const float sine = norm3(cross3(ncurr_g, nprev_g));    // :318
+// reduce.cu:821
+__device__ __forceinline__ bool rgb_accept(const RgbResParams & P, float transformed_d1, float d0, uint8_t last)
+{
+    return d0 > 0 && fabsf(transformed_d1 - d0) <= P.max_depth_delta && last != 0;
+}
 
-    if(!(sine < P.angle_thresh && dist <= P.dist_thresh && !isnan(ncurr.x) && !isnan(nprev_g.x))) return false; // :324
-
-    const float3 s_cp = P.Rprev_inv * (vcurr_g - P.tprev); // :341-343
-    const float3 d_cp = P.Rprev_inv * (vprev_g - P.tprev);
-    const float3 n_cp = P.Rprev_inv * nprev_g;
-    const float3 c = cross3(s_cp, n_cp);
-
-    row[0] = n_cp.x; row[1] = n_cp.y; row[2] = n_cp.z;
-    row[3] = c.x; row[4] = c.y; row[5] = c.z;
-    row[6] = dot3(n_cp, s_cp - d_cp);                      // :347
-    return true;
+// the cheap per-pixel gates of RGBResidual::getProducts that need no gather (reduce.cu:779-783, :800-811)
+__device__ __forceinline__ bool rgb_gate(const RgbResParams & P, int x, int y, int valx, int valy, float d1)
+{
+    const int border = 16; // :779
+    if(!(y >= border && y < P.rows - border && x >= border && x < P.cols - border)) return false; // :781
+    if(!(x < P.cols - 5 && y < P.rows - 1)) return false;                                          // :783
+    const float mTwo = (valx * valx) + (valy * valy); // :802 (int arithmetic, then to float)
+    return (mTwo >= P.min_scale) && !isnan(d1);       // :804, :811
 }
 
 // RGBResidual::getProducts (reduce.cu:768-842) for pixel (x, y).  On success returns true and
@@ -130,13 +171,7 @@ __device__ __forceinline__ bool rgb_residual_px(const RgbResParams & P, int x, i
                                                 const uint8_t * __restrict__ last_image, const float * __restrict__ last_depth,
                                                 int depth_pitch, int & u0, int & v0, float & diff, float & d0)
 {
-    const int border = 16; // :779
-    if(!(y >= border && y < P.rows - border && x >= border && x < P.cols - border)) return false; // :781
-    if(!(x < P.cols - 5 && y < P.rows - 1)) return false;                                          // :783
-
-    const float mTwo = (valx * valx) + (valy * valy); // :802 (int arithmetic, then to float)
-    if(!(mTwo >= P.min_scale)) return false;          // :804
-    if(isnan(d1)) return false;                       // :811
+    if(!rgb_gate(P, x, y, valx, valy, d1)) return false;
 
     // :787-793  4x4 neighbourhood [y-2, y+2) x [x-2, x+2) of the next image must be non-zero
     // (inside the 16-pixel border the max/min clamps of the reference are no-ops)
@@ -150,22 +185,12 @@ __device__ __forceinline__ bool rgb_residual_px(const RgbResParams & P, int x, i
     }
     if(!valid) return false;
 
-    // :813-815.  The reference binary evaluates  k.x*x + k.y*y + k.z  as  fma(k.x, x, k.y*y) + k.z  and the outer
-    // d1*(..) + kt as one FMA (its PTX); pinned with explicit FMAs because a 1-ulp difference flips the
-    // round-to-nearest pixel index at exact .5 ties.
-    const float xf = (float)x, yf = (float)y;
-    const float s2 = __fmaf_rn(P.krkinv.r2.x, xf, P.krkinv.r2.y * yf) + P.krkinv.r2.z;
-    const float s0 = __fmaf_rn(P.krkinv.r0.x, xf, P.krkinv.r0.y * yf) + P.krkinv.r0.z;
-    const float s1 = __fmaf_rn(P.krkinv.r1.x, xf, P.krkinv.r1.y * yf) + P.krkinv.r1.z;
-    const float transformed_d1 = __fmaf_rn(d1, s2, P.kt.z);
-    u0 = __float2int_rn(__fmaf_rn(d1, s0, P.kt.x) / transformed_d1);
-    v0 = __float2int_rn(__fmaf_rn(d1, s1, P.kt.y) / transformed_d1);
-
-    if(!(u0 >= 0 && v0 >= 0 && u0 < P.cols && v0 < P.rows)) return false; // :817
+    float transformed_d1;
+    if(!rgb_warp(P, x, y, d1, u0, v0, transformed_d1)) return false;
 
     d0 = __ldg(last_depth + (size_t)v0 * depth_pitch + u0);
     const uint8_t l = __ldg(last_image + (size_t)v0 * img_pitch + u0);
-    if(!(d0 > 0 && fabsf(transformed_d1 - d0) <= P.max_depth_delta && l != 0)) return false; // :821
+    if(!rgb_accept(P, transformed_d1, d0, l)) return false; // :821
 
     diff = static_cast<float>(__ldg(next_image + (size_t)y * img_pitch + x)) - static_cast<float>(l); // :827
     return true;

@@ -4,25 +4,26 @@
 // Why: at 640x480 a Gauss-Newton iteration touches ~19 MB that already sits in the 126 MB L2, i.e. a
 // couple of microseconds of memory time, while the reference pays 3-4 launches, 3-4 device syncs and
 // blocking D2H copies per iteration (57+ host round trips per frame).  Here one CTA per SM stays
-// resident for the whole solve:
+// resident for the whole solve and an iteration costs a handful of L2 round trips:
 //
-//   per iteration   phase A  every thread: ICP association + 29 fp32 sums for its pixels (registers),
-//                            photometric association -> correspondence records in SHARED memory,
-//                            {count, sum diff^2} by integer atomics
-//                   barrier  (only when RGB is on: sigma depends on the global count)
-//                   phase B  photometric rows from the records in shared memory -> 29 more sums
-//                   reduce   transpose-reduce butterfly -> per-CTA 64-float partial row in global memory
-//                   solve    CTA 0 waits for all arrivals, adds the rows in CTA order (deterministic),
-//                            one thread runs the reference's host step in double (6x6 LDLT, exp map,
-//                            pose composition: ef_hostmath.h, the same code the host path runs) and
-//                            publishes the next iteration's parameters; everyone else spins on a flag.
+//   phase A   every thread, for its 4-pixel groups: all coalesced loads first (current v/n maps as 128-bit
+//             loads, gradients, depth, 4x4 validity window as 12 words), then both projections, then all
+//             gathers, then the math: 29 ICP sums in registers, photometric correspondences -> SHARED memory.
+//   barrier B (only with RGB: the weight needs the global count) ONE 64-bit atomic per CTA carries
+//             arrivals | count | sum diff^2; whoever polls it gets all three in one load.
+//   phase B   photometric rows from the records in shared memory -> 29 more sums.
+//   reduce    transpose-reduce butterfly -> per-CTA 64-float partial row -> red.release arrival.
+//   solve     CTA 0 sees the last arrival, adds the rows in CTA order (deterministic), ONE thread runs the
+//             reference's host step in double (LDL^T, exp map, pose composition; ef_hostmath.h) and
+//             publishes the next parameters in a 128-byte line whose four 32-byte sectors each carry the
+//             epoch, so the other CTAs poll and load the parameters with the same single load.
 //
 // No DataTerm image, no point cloud, no reduceSum launch, no host involvement until the final pose is
-// stored straight into pinned host memory.  Grid barriers are hand-rolled (red.release / ld.acquire on
-// monotonically increasing counters); co-residency is guaranteed by a cooperative launch with
-// gridDim = number of SMs.
-#include <cooperative_groups.h>
+// stored straight into pinned host memory.  Co-residency of the spinning CTAs is guaranteed by a
+// cooperative launch with gridDim = number of SMs.
 #include <float.h>
+#include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "ef_hostmath.h"
@@ -37,9 +38,12 @@ namespace ef
 namespace
 {
 
-constexpr int kThreads = 512;
+constexpr int kThreads = 640;    // 20 warps = 5 per scheduler (96 registers each); 640x480 level 0 has 519 four-pixel groups per CTA -> one pass
 constexpr int kWarps = kThreads / 32;
-constexpr int kMaxIters = 32; // SE3 iterations per call (19 in the reference schedule)
+constexpr int kRedThreads = 512; // threads of CTA 0 used by the final cross-CTA sum (8 parts x 64 slots)
+constexpr int kMaxIters = 32;    // SE3 iterations per call (19 in the reference schedule)
+constexpr int kMaxGrid = 160;    // final-reduce unroll bound (B200: 148 SMs)
+constexpr int kDbgStamps = 10;
 
 struct LevelArgs
 {
@@ -52,25 +56,23 @@ struct LevelArgs
     float inv_fx, inv_fy;                         // host 1.0f / f (cudafuncs.cu:671)
     float min_scale;
     int iterations;
+    double K_inv[9];                              // host double inverse of K (RGBDOdometry.cpp:428)
 };
 
-// parameters the solver publishes for the next phase (read by every CTA after the barrier)
-struct TrackParams
+// one 128-byte line: sector s = words [8s, 8s+7), word 8s+7 = epoch.  28 payload floats.
+struct alignas(128) ParamLine
 {
-    float Rcurr[9], tcurr[3];   // ICP
-    float krkinv[9], kt[3];     // RGB warp
-    float H[9], krlr[9];        // SO3 homography and K*R
-    int so3_done;
-    int pad[3];
+    unsigned w[32];
 };
+// SE3 payload: Rcurr[9] tcurr[3] krkinv[9] kt[3];  SO3 payload: H[9] krlr[9] done
+constexpr int kPayload = 28;
 
-struct TrackCtl
+struct alignas(128) TrackCtl
 {
     unsigned arrive;  unsigned pad0[31];          // solve barrier: arrivals (monotonic within a launch)
-    unsigned release; unsigned pad1[31];          // solve barrier: epochs released by CTA 0
-    unsigned arrive_b; unsigned pad2[31];         // phase A -> B barrier arrivals
-    int rgb_cnt[kMaxIters][2];                    // per SE3 iteration {count, sum (int)(diff^2)}
-    TrackParams params;
+    ParamLine line;                               // parameters + epoch, written by the solver thread
+    unsigned long long bar_b[kMaxIters];          // per SE3 iteration: arrivals | count << 8 | sigma << 32
+    double last_S[27];                            // combined normal equations of the last solve (for lastA / lastb)
 };
 
 struct TrackOutput // pinned host memory, written by the solver thread
@@ -92,39 +94,77 @@ struct TrackArgs
     TrackCtl * ctl;
     float * partials;                             // gridDim.x * 64 floats
     TrackOutput * out;
-    int corr_slots;                               // int4 records per thread in dynamic shared memory
+    long long * dbg;                              // optional clock64 stamps of CTA 0 (EF_TRACK_TIMING=1)
 };
 
-// ---- memory-ordering primitives ----
-__device__ __forceinline__ unsigned ld_acquire(const unsigned * p)
+// ---- memory-ordering primitives (PTX memory model, gpu scope) ----
+__device__ __forceinline__ unsigned ld_relaxed(const unsigned * p)
 {
     unsigned v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ void st_release(unsigned * p, unsigned v)
+__device__ __forceinline__ unsigned long long ld_relaxed64(const unsigned long long * p)
 {
-    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed(unsigned * p, unsigned v)
+{
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void red_release_add(unsigned * p, unsigned v)
+{
+    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void fence_acq_rel()
+{
+    asm volatile("fence.acq_rel.gpu;" ::: "memory");
 }
 
-// all threads of the CTA call; thread 0 signals arrival after the CTA's writes are visible
+// all threads of the CTA call; the CTA's prior writes are ordered before the arrival (bar.sync + release)
 __device__ __forceinline__ void cta_arrive(unsigned * counter)
 {
     __syncthreads();
-    if(threadIdx.x == 0)
-    {
-        __threadfence();
-        atomicAdd(counter, 1u);
-    }
+    if(threadIdx.x == 0) red_release_add(counter, 1u);
 }
 
-// all threads call; returns when *counter >= target (acquire)
-__device__ __forceinline__ void cta_wait_ge(const unsigned * counter, unsigned target)
+// CTA 0 only: wait until `target` arrivals are visible, then acquire
+__device__ __forceinline__ void cta_wait_arrivals(const unsigned * counter, unsigned target)
 {
     if(threadIdx.x == 0)
     {
-        while(ld_acquire(counter) < target) { }
-        __threadfence();
+        while(ld_relaxed(counter) < target) { }
+        fence_acq_rel();
+    }
+    __syncthreads();
+}
+
+// solver thread: payload first, fence, then the four epoch words (each sector is validated on its own)
+__device__ __forceinline__ void publish_line(ParamLine * L, const float * payload, unsigned epoch)
+{
+#pragma unroll
+    for(int i = 0; i < kPayload; i++) st_relaxed(&L->w[(i / 7) * 8 + (i % 7)], __float_as_uint(payload[i]));
+    fence_acq_rel();
+#pragma unroll
+    for(int s = 0; s < 4; s++) st_relaxed(&L->w[s * 8 + 7], epoch);
+}
+
+// all threads call: warp 0 spins on the line until every sector shows `epoch`, then the payload is in smem.
+// A 32-byte sector is read atomically, and a sector's epoch is written after (fence) its payload, so a
+// sector that shows the new epoch also shows the new payload.
+__device__ __forceinline__ void wait_line(const ParamLine * L, unsigned epoch, float * s_payload)
+{
+    if(threadIdx.x < 32)
+    {
+        const unsigned lane = threadIdx.x;
+        unsigned v;
+        do
+        {
+            v = ld_relaxed(&L->w[lane]);
+        } while(!__all_sync(kFullMask, ((lane & 7u) != 7u) || v == epoch));
+        if((lane & 7u) != 7u) s_payload[(lane >> 3) * 7 + (lane & 7u)] = __uint_as_float(v);
     }
     __syncthreads();
 }
@@ -145,132 +185,180 @@ struct Solver
 {
     double resultRt[16];
     float Rcurr[9], tcurr[3];
-    ef_track_stats st;
+    float last_icp_error, last_icp_count, last_rgb_error, last_rgb_count, last_so3_error, last_so3_count;
+    int so3_iterations, se3_iterations[3];
 };
 
-// CTA 0 only, after all arrivals: add the partial rows in CTA-index order -> s_final[64]
-__device__ __forceinline__ void cta0_final_reduce(const float * __restrict__ partials, float * s_red, float * s_final)
+// RGBDOdometry.cpp:515-516, :541-583 -- runs in ONE thread (thread 0 of CTA 0).  Kept out of line so its
+// double-precision register needs do not inflate the per-pixel phases of the kernel.  s_final: 64 floats in
+// shared memory = ICP accumulator (29, padded to 32) followed by the RGB accumulator.
+__device__ __noinline__ void solve_se3(Solver & S, const float * s_final, double * last_S, int icp, int rgb, float icp_weight,
+                                       const float * Rprev, const float * tprev, int level)
 {
-    const int slot = threadIdx.x & 63, part = threadIdx.x >> 6; // 8 parts of 64 lanes
-    float s = 0.f;
-    for(unsigned b = part; b < gridDim.x; b += kThreads / 64) s += __ldcg(partials + b * 64 + slot);
-    __syncthreads();
-    s_red[part * 64 + slot] = s;
-    __syncthreads();
-    if(threadIdx.x < 64)
-    {
-        float tot = 0.f;
-#pragma unroll
-        for(int p = 0; p < kThreads / 64; p++) tot += s_red[p * 64 + threadIdx.x];
-        s_final[threadIdx.x] = tot;
-    }
-    __syncthreads();
-}
-
-
-// RGBDOdometry.cpp:515-516, :541-583 -- runs in ONE thread (thread 0 of CTA 0).  Kept out of line so
-// its double-precision register needs do not inflate the per-pixel phases of the kernel.
-__device__ __noinline__ void solve_se3(Solver & S, const float * s_final, int icp, int rgb, float icp_weight, const float * Rprev,
-                                       const float * tprev, int level)
-{
-    double A_icp[36], b_icp[6], A_rgb[36], b_rgb[6];
     if(icp)
     {
-        float residual[2];
-        hm::unpack_se3(s_final, A_icp, b_icp, residual);
-        S.st.last_icp_error = sqrtf(residual[0]) / residual[1]; // :515-516
-        S.st.last_icp_count = residual[1];
+        S.last_icp_error = sqrtf(s_final[27]) / s_final[28]; // :515-516
+        S.last_icp_count = s_final[28];
     }
-    if(rgb) hm::unpack_se3(s_final + 32, A_rgb, b_rgb, (float *)nullptr);
-    double * lastA = S.st.last_A, * lastb = S.st.last_b, result[6];
-    if(icp && rgb) // :547-553
+    double Sm[27];
+    const double w = icp_weight;
+    if(icp && rgb) // :547-553  A = A_rgb + w^2 A_icp ; b = b_rgb + w b_icp
     {
-        const double w = icp_weight;
-        for(int k = 0; k < 36; k++) lastA[k] = A_rgb[k] + w * w * A_icp[k];
-        for(int k = 0; k < 6; k++) lastb[k] = b_rgb[k] + w * b_icp[k];
-    }
-    else if(icp)
-    {
-        for(int k = 0; k < 36; k++) lastA[k] = A_icp[k];
-        for(int k = 0; k < 6; k++) lastb[k] = b_icp[k];
+#pragma unroll
+        for(int i = 0; i < 6; i++)
+        {
+#pragma unroll
+            for(int j = i; j < 7; j++)
+            {
+                const int k = hm::acc_index(i, j);
+                Sm[k] = (j == 6) ? ((double)s_final[32 + k] + w * (double)s_final[k]) : ((double)s_final[32 + k] + w * w * (double)s_final[k]);
+            }
+        }
     }
     else
     {
-        for(int k = 0; k < 36; k++) lastA[k] = A_rgb[k];
-        for(int k = 0; k < 6; k++) lastb[k] = b_rgb[k];
+        const int o = icp ? 0 : 32;
+#pragma unroll
+        for(int k = 0; k < 27; k++) Sm[k] = (double)s_final[o + k];
     }
-    hm::ldlt_solve<double, 6>(lastA, lastb, result);
-    S.st.se3_iterations[level]++;
+#pragma unroll
+    for(int k = 0; k < 27; k++) last_S[k] = Sm[k];
+    double result[6];
+    hm::ldlt_solve_spd6_acc(Sm, result);
+    S.se3_iterations[level]++;
     hm::update_se3(S.resultRt, result);                           // :573
     hm::compose_pose(S.resultRt, Rprev, tprev, S.Rcurr, S.tcurr); // :575-583
 }
 
-// :424-434 -- publish the parameters of the next SE3 iteration (solver thread)
-__device__ __noinline__ void publish_se3(const Solver & S, TrackParams * p, int rgb, float fx, float fy, float cx, float cy)
+// :424-434 -- parameters of the next SE3 iteration (solver thread) -> payload[28]
+__device__ __noinline__ void make_se3_payload(const Solver & S, float * payload, int rgb, float fx, float fy, float cx, float cy,
+                                              const double * K_inv)
 {
-    for(int i = 0; i < 9; i++) p->Rcurr[i] = S.Rcurr[i];
-    for(int i = 0; i < 3; i++) p->tcurr[i] = S.tcurr[i];
+#pragma unroll
+    for(int i = 0; i < 9; i++) payload[i] = S.Rcurr[i];
+#pragma unroll
+    for(int i = 0; i < 3; i++) payload[9 + i] = S.tcurr[i];
     if(rgb)
     {
         const double K[9] = {fx, 0, cx, 0, fy, cy, 0, 0, 1};
-        double K_inv[9];
-        hm::inverse33(K, K_inv);
-        hm::rgb_warp_params(S.resultRt, K, K_inv, p->krkinv, p->kt);
+        hm::rgb_warp_params(S.resultRt, K, K_inv, payload + 12, payload + 21);
     }
+    else
+    {
+#pragma unroll
+        for(int i = 12; i < 24; i++) payload[i] = 0.f;
+    }
+#pragma unroll
+    for(int i = 24; i < kPayload; i++) payload[i] = 0.f;
 }
 
-// :348-380 -- digest one so3Step evaluation; returns done
 struct So3State
 {
     double resultR[9], lastResultR[9];
     float R_lr[9], lastError, lastCount;
 };
 
+// :348-380 -- digest one so3Step evaluation; returns done
 __device__ __noinline__ int solve_so3(Solver & S, So3State & Z, const float * s_final, int it)
 {
     int done = 0;
     float jtj[9], jtr[3], residual[2];
     hm::unpack_so3(s_final, jtj, jtr, residual);
-    S.st.so3_iterations++;
-    S.st.last_so3_error = sqrtf(residual[0]) / residual[1];                           // :348
-    S.st.last_so3_count = residual[1];
-    if(S.st.last_so3_error < Z.lastError && Z.lastCount == S.st.last_so3_count) done = 1; // :352
-    else if(S.st.last_so3_error > Z.lastError + 0.001)                                 // :356
+    S.so3_iterations++;
+    S.last_so3_error = sqrtf(residual[0]) / residual[1];                        // :348
+    S.last_so3_count = residual[1];
+    if(S.last_so3_error < Z.lastError && Z.lastCount == S.last_so3_count) done = 1; // :352
+    else if(S.last_so3_error > Z.lastError + 0.001)                              // :356
     {
-        S.st.last_so3_error = Z.lastError;
-        S.st.last_so3_count = Z.lastCount;
+        S.last_so3_error = Z.lastError;
+        S.last_so3_count = Z.lastCount;
+#pragma unroll
         for(int i = 0; i < 9; i++) Z.resultR[i] = Z.lastResultR[i];
         done = 1;
     }
     if(!done)
     {
-        Z.lastError = S.st.last_so3_error;
-        Z.lastCount = S.st.last_so3_count;
+        Z.lastError = S.last_so3_error;
+        Z.lastCount = S.last_so3_count;
+#pragma unroll
         for(int i = 0; i < 9; i++) Z.lastResultR[i] = Z.resultR[i];
         float delta[3];
-        hm::ldlt_solve<float, 3>(jtj, jtr, delta);                                     // :368
+        hm::ldlt_solve<float, 3>(jtj, jtr, delta);                               // :368
         const double dd[3] = {delta[0], delta[1], delta[2]};
         double rotUpdate[9];
         hm::rodrigues(dd, rotUpdate);
         float ru[9];
+#pragma unroll
         for(int i = 0; i < 9; i++) ru[i] = (float)rotUpdate[i];
-        hm::mul33(ru, Z.R_lr, Z.R_lr);                                                  // :372
+        hm::mul33(ru, Z.R_lr, Z.R_lr);                                            // :372
+#pragma unroll
         for(int i = 0; i < 9; i++) Z.resultR[i] = Z.R_lr[i];
         if(it == 10) done = 1; // ten evaluations made
     }
     return done;
 }
 
-// :318-329 -- homography K R K^-1 and K R for the next so3Step
-__device__ __noinline__ void publish_so3(const So3State & Z, TrackParams * p, int done, float fx, float fy, float cx, float cy)
+// :318-329 -- homography K R K^-1 and K R for the next so3Step -> payload[28]
+__device__ __noinline__ void make_so3_payload(const So3State & Z, float * payload, int done, float fx, float fy, float cx, float cy,
+                                              const double * K_inv)
 {
     const double K[9] = {fx, 0, cx, 0, fy, cy, 0, 0, 1};
-    double K_inv[9], KR[9], H[9];
-    hm::inverse33(K, K_inv);
+    double KR[9], H[9];
     hm::mul33(K, Z.resultR, KR);
     hm::mul33(KR, K_inv, H);
-    for(int i = 0; i < 9; i++) { p->H[i] = (float)H[i]; p->krlr[i] = (float)KR[i]; }
-    p->so3_done = done;
+#pragma unroll
+    for(int i = 0; i < 9; i++)
+    {
+        payload[i] = (float)H[i];
+        payload[9 + i] = (float)KR[i];
+    }
+    payload[18] = done ? 1.f : 0.f;
+#pragma unroll
+    for(int i = 19; i < kPayload; i++) payload[i] = 0.f;
+}
+
+// CTA 0 only, after all arrivals: add the partial rows in CTA-index order -> s_final[SLOTS].
+// Loads are issued as one unrolled batch (independent), the adds stay in row order.
+template<int SLOTS>
+__device__ __forceinline__ void cta0_final_reduce(const float * __restrict__ partials, float * s_red, float * s_final)
+{
+    constexpr int kParts = kRedThreads / SLOTS;
+    constexpr int kPer = (kMaxGrid + kParts - 1) / kParts;
+    const int slot = threadIdx.x % SLOTS, part = threadIdx.x / SLOTS;
+    if(threadIdx.x < kRedThreads)
+    {
+        float v[kPer];
+#pragma unroll
+        for(int i = 0; i < kPer; i++)
+        {
+            const unsigned b = part + i * kParts;
+            v[i] = (b < gridDim.x) ? __ldcg(partials + b * 64 + slot) : 0.f;
+        }
+        float s = 0.f;
+#pragma unroll
+        for(int i = 0; i < kPer; i++) s += v[i];
+        s_red[part * SLOTS + slot] = s;
+    }
+    __syncthreads();
+    if(threadIdx.x < SLOTS)
+    {
+        float tot = 0.f;
+#pragma unroll
+        for(int p = 0; p < kParts; p++) tot += s_red[p * SLOTS + threadIdx.x];
+        s_final[threadIdx.x] = tot;
+    }
+    __syncthreads();
+}
+
+// bytes k+2 .. k+5 of the 12-byte run (a0 a1 a2) all 0xFF ?  (4x4 validity window of pixel k of a group)
+__device__ __forceinline__ bool window_ok(unsigned a0, unsigned a1, unsigned a2, int k)
+{
+    unsigned m;
+    if(k == 0) m = __byte_perm(a0, a1, 0x5432);
+    else if(k == 1) m = __byte_perm(a0, a1, 0x6543);
+    else if(k == 2) m = a1;
+    else m = __byte_perm(a1, a2, 0x4321);
+    return m == 0xffffffffu;
 }
 
 __global__ void __launch_bounds__(kThreads, 1) k_track(const TrackArgs A)
@@ -278,31 +366,41 @@ __global__ void __launch_bounds__(kThreads, 1) k_track(const TrackArgs A)
     extern __shared__ int4 s_corr[];            // [corr_slots][kThreads]
     __shared__ float s_red[kWarps * 64];
     __shared__ float s_final[64];
-    __shared__ TrackParams s_par;
-    __shared__ int s_cnt[kWarps], s_sig[kWarps];
+    __shared__ float s_par[kPayload];
+    __shared__ int s_cnt, s_sig;
+    __shared__ int s_wcnt[kWarps], s_wsig[kWarps];
 
     TrackCtl * ctl = A.ctl;
     const unsigned grid = gridDim.x;
     const bool is_solver_cta = (blockIdx.x == 0);
     const bool is_solver = is_solver_cta && threadIdx.x == 0;
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     float * my_row = A.partials + (size_t)blockIdx.x * 64;
 
     // barrier bookkeeping, tracked identically by every thread of the grid
-    unsigned rel = 0;   // parameter publications (release epochs)
-    unsigned arr = 0;   // completed arrival rounds on ctl->arrive
-    unsigned arr_b = 0; // completed arrival rounds on ctl->arrive_b
+    unsigned rel = 0; // parameter publications (epochs)
+    unsigned arr = 0; // completed arrival rounds on ctl->arrive
 
     Solver S;
     if(is_solver)
     {
+#pragma unroll
         for(int i = 0; i < 16; i++) S.resultRt[i] = (i % 5 == 0) ? 1.0 : 0.0;
+#pragma unroll
         for(int i = 0; i < 9; i++) S.Rcurr[i] = A.Rprev[i];
+#pragma unroll
         for(int i = 0; i < 3; i++) S.tcurr[i] = A.tprev[i];
-        memset(&S.st, 0, sizeof(S.st));
-        S.st.last_icp_error = A.prev_icp_error; S.st.last_icp_count = A.prev_icp_count;
-        S.st.last_so3_error = A.prev_so3_error; S.st.last_so3_count = A.prev_so3_count;
-        S.st.last_rgb_error = A.prev_rgb_error; S.st.last_rgb_count = A.prev_rgb_count;
+        S.last_icp_error = A.prev_icp_error; S.last_icp_count = A.prev_icp_count;
+        S.last_so3_error = A.prev_so3_error; S.last_so3_count = A.prev_so3_count;
+        S.last_rgb_error = A.prev_rgb_error; S.last_rgb_count = A.prev_rgb_count;
+        S.so3_iterations = 0;
+        S.se3_iterations[0] = S.se3_iterations[1] = S.se3_iterations[2] = 0;
     }
+
+    int dbg_it = 0;
+    auto stamp = [&](int k) {
+        if(A.dbg && is_solver && dbg_it < kMaxIters) A.dbg[dbg_it * kDbgStamps + k] = clock64();
+    };
 
     // ============================================================================================
     // SO(3) pre-alignment: RGBDOdometry.cpp:294-382 (level 2, at most 10 so3Step evaluations)
@@ -317,6 +415,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_track(const TrackArgs A)
         So3State Z; // solver-private loop state
         if(is_solver)
         {
+#pragma unroll
             for(int i = 0; i < 9; i++) { Z.resultR[i] = Z.lastResultR[i] = (i % 4 == 0) ? 1.0 : 0.0; Z.R_lr[i] = (i % 4 == 0) ? 1.f : 0.f; }
             Z.lastError = FLT_MAX / 2;
             Z.lastCount = FLT_MAX / 2;
@@ -331,40 +430,26 @@ __global__ void __launch_bounds__(kThreads, 1) k_track(const TrackArgs A)
             // ---- CTA 0: digest the previous evaluation (:348-380), publish the next homography ----
             if(is_solver_cta)
             {
-                int done = 0;
                 if(it > 0)
                 {
-                    cta_wait_ge(&ctl->arrive, arr * grid);
-                    const int slot = threadIdx.x & 15, part = threadIdx.x >> 4; // 32 parts
-                    float s = 0.f;
-                    for(unsigned b = part; b < grid; b += kThreads / 16) s += __ldcg(A.partials + b * 64 + slot);
-                    s_red[part * 16 + slot] = s;
-                    __syncthreads();
-                    if(threadIdx.x < 16)
-                    {
-                        float tot = 0.f;
-                        for(int p = 0; p < kThreads / 16; p++) tot += s_red[p * 16 + threadIdx.x];
-                        s_final[threadIdx.x] = tot;
-                    }
-                    __syncthreads();
+                    cta_wait_arrivals(&ctl->arrive, arr * grid);
+                    cta0_final_reduce<16>(A.partials, s_red, s_final);
                 }
                 if(is_solver)
                 {
+                    int done = 0;
                     if(it > 0) done = solve_so3(S, Z, s_final, it);
-                    publish_so3(Z, &ctl->params, done, L.fx, L.fy, L.cx, L.cy);
-                    __threadfence();
-                    st_release(&ctl->release, rel + 1);
+                    float payload[kPayload];
+                    make_so3_payload(Z, payload, done, L.fx, L.fy, L.cx, L.cy, L.K_inv);
+                    publish_line(&ctl->line, payload, rel + 1);
                 }
             }
             ++rel;
-            cta_wait_ge(&ctl->release, rel);
-            if(threadIdx.x < 18) (&s_par.H[0])[threadIdx.x] = __ldcg(&ctl->params.H[0] + threadIdx.x); // H then krlr are contiguous
-            if(threadIdx.x == 32) s_par.so3_done = __ldcg(&ctl->params.so3_done);
-            __syncthreads();
-            const int done = s_par.so3_done;
-            P.image_basis = mat_from(s_par.H);
-            P.krlr = mat_from(s_par.krlr);
-            __syncthreads();
+            wait_line(&ctl->line, rel, s_par);
+            const bool done = s_par[18] != 0.f;
+            P.image_basis = mat_from(s_par);
+            P.krlr = mat_from(s_par + 9);
+            __syncthreads(); // s_par is rewritten by the next wait_line
             if(done) break;
 
             // ---- so3Step over this CTA's pixels ----
@@ -378,24 +463,27 @@ __global__ void __launch_bounds__(kThreads, 1) k_track(const TrackArgs A)
                 if(so3_row(P, x, y, A.so3_last, A.so3_next, L.cols, row)) accumulate_so3(acc, row);
             }
             const float lane_value = warp_transpose_reduce16(acc);
+            if(lane < 16) s_red[warp * 16 + lane] = lane_value;
+            __syncthreads();
+            if(threadIdx.x < 16)
             {
-                const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-                if(lane < 16) s_red[warp * 16 + lane] = lane_value;
-                __syncthreads();
-                if(threadIdx.x < 16)
-                {
-                    float s = 0.f;
+                float s = 0.f;
 #pragma unroll
-                    for(int w = 0; w < kWarps; w++) s += s_red[w * 16 + threadIdx.x];
-                    my_row[threadIdx.x] = s;
-                }
+                for(int w = 0; w < kWarps; w++) s += s_red[w * 16 + threadIdx.x];
+                my_row[threadIdx.x] = s;
             }
             cta_arrive(&ctl->arrive);
             ++arr;
         }
         if(is_solver)
+        {
+#pragma unroll
             for(int x = 0; x < 3; x++)
+            {
+#pragma unroll
                 for(int y = 0; y < 3; y++) S.resultRt[x * 4 + y] = Z.resultR[x * 3 + y]; // :394-403
+            }
+        }
     }
 
     // ============================================================================================
@@ -414,9 +502,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_track(const TrackArgs A)
     // CTA 0: wait for the outstanding arrival round, add the partial rows in CTA order, run the
     // reference's host step (:541-583) in the solver thread
     auto solve_pending = [&]() {
-        cta_wait_ge(&ctl->arrive, arr * grid);
-        cta0_final_reduce(A.partials, s_red, s_final);
-        if(is_solver) solve_se3(S, s_final, A.icp, A.rgb, A.icp_weight, A.Rprev, A.tprev, pending_level);
+        cta_wait_arrivals(&ctl->arrive, arr * grid);
+        stamp(1);
+        cta0_final_reduce<64>(A.partials, s_red, s_final);
+        stamp(2);
+        if(is_solver) solve_se3(S, s_final, ctl->last_S, A.icp, A.rgb, A.icp_weight, A.Rprev, A.tprev, pending_level);
+        stamp(3);
     };
 
     for(int lv = kNumPyrs - 1; lv >= 0; lv--)
@@ -436,42 +527,46 @@ __global__ void __launch_bounds__(kThreads, 1) k_track(const TrackArgs A)
         SP.fx = L.fx; SP.fy = L.fy; SP.inv_fx = L.inv_fx; SP.inv_fy = L.inv_fy; SP.cx = L.cx; SP.cy = L.cy;
         SP.sobel_scale = A.sobel_scale;
         SP.sigma = 0.f;
-        const Map3 vc{L.vc, L.cols, L.rows}, nc{L.nc, L.cols, L.rows}, vp{L.vp, L.cols, L.rows}, np{L.np, L.cols, L.rows};
+        const int cols = L.cols;
+        const size_t plane = (size_t)L.rows * cols;
 
         float lastRGBError = FLT_MAX;      // every thread tracks it for the uniform rgb_only break (:464)
         bool first_of_level = true;
 
         // this CTA's contiguous run of 4-pixel groups
-        const int gpr = L.cols >> 2;
+        const int gpr = cols >> 2;
         const int ngroups = gpr * L.rows;
         const int per_cta = (ngroups + grid - 1) / grid;
         const int g_begin = min(ngroups, (int)blockIdx.x * per_cta), g_end = min(ngroups, g_begin + per_cta);
 
         for(int j = 0; j < L.iterations; j++)
         {
-            const int cnt_slot = it_global++; // one {count, sigma} slot per started iteration (also when it breaks)
+            const int cnt_slot = it_global++; // one barrier-B word per started iteration (also when it breaks)
+            dbg_it = cnt_slot;
+            stamp(0);
             // ---- CTA 0: finish the previous iteration, publish this one's parameters (:424-434, :480-481) ----
             if(is_solver_cta)
             {
                 if(pending) solve_pending();
                 if(is_solver)
                 {
-                    if(first_of_level) S.st.last_rgb_error = FLT_MAX; // :420
-                    publish_se3(S, &ctl->params, A.rgb, L.fx, L.fy, L.cx, L.cy);
-                    __threadfence();
-                    st_release(&ctl->release, rel + 1);
+                    if(first_of_level) S.last_rgb_error = FLT_MAX; // :420
+                    float payload[kPayload];
+                    make_se3_payload(S, payload, A.rgb, L.fx, L.fy, L.cx, L.cy, L.K_inv);
+                    publish_line(&ctl->line, payload, rel + 1);
                 }
             }
             pending = false;
             first_of_level = false;
             ++rel;
-            cta_wait_ge(&ctl->release, rel);
-            if(threadIdx.x < 24) (&s_par.Rcurr[0])[threadIdx.x] = __ldcg(&ctl->params.Rcurr[0] + threadIdx.x); // Rcurr,tcurr,krkinv,kt
-            __syncthreads();
-            IP.Rcurr = mat_from(s_par.Rcurr);
-            IP.tcurr = make_float3(s_par.tcurr[0], s_par.tcurr[1], s_par.tcurr[2]);
-            RP.krkinv = mat_from(s_par.krkinv);
-            RP.kt = make_float3(s_par.kt[0], s_par.kt[1], s_par.kt[2]);
+            wait_line(&ctl->line, rel, s_par);
+            IP.Rcurr = mat_from(s_par);
+            IP.tcurr = make_float3(s_par[9], s_par[10], s_par[11]);
+            RgbResParams RPi = RP;
+            RPi.krkinv = mat_from(s_par + 12);
+            RPi.kt = make_float3(s_par[21], s_par[22], s_par[23]);
+            __syncthreads(); // s_par is rewritten by the next wait_line
+            stamp(4);
 
             float accI[32];
 #pragma unroll
@@ -484,56 +579,126 @@ __global__ void __launch_bounds__(kThreads, 1) k_track(const TrackArgs A)
             {
                 const int y = g / gpr;
                 const int x0 = (g - y * gpr) << 2;
-                const size_t o = (size_t)y * L.cols + x0;
+                const size_t o = (size_t)y * cols + x0;
+
+                // stage 0: every load that does not depend on arithmetic
+                float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a, c = a, d = a, e = a, f = a;
                 if(A.icp)
                 {
-                    const float4 a = *reinterpret_cast<const float4 *>(vc.row(0, y) + x0);
-                    const float4 b = *reinterpret_cast<const float4 *>(vc.row(1, y) + x0);
-                    const float4 c = *reinterpret_cast<const float4 *>(vc.row(2, y) + x0);
-                    const float4 d = *reinterpret_cast<const float4 *>(nc.row(0, y) + x0);
-                    const float4 e = *reinterpret_cast<const float4 *>(nc.row(1, y) + x0);
-                    const float4 f = *reinterpret_cast<const float4 *>(nc.row(2, y) + x0);
-                    const float vx[4] = {a.x, a.y, a.z, a.w}, vy[4] = {b.x, b.y, b.z, b.w}, vz[4] = {c.x, c.y, c.z, c.w};
-                    const float nx[4] = {d.x, d.y, d.z, d.w}, ny[4] = {e.x, e.y, e.z, e.w}, nz[4] = {f.x, f.y, f.z, f.w};
+                    a = *reinterpret_cast<const float4 *>(L.vc + o);
+                    b = *reinterpret_cast<const float4 *>(L.vc + plane + o);
+                    c = *reinterpret_cast<const float4 *>(L.vc + 2 * plane + o);
+                    d = *reinterpret_cast<const float4 *>(L.nc + o);
+                    e = *reinterpret_cast<const float4 *>(L.nc + plane + o);
+                    f = *reinterpret_cast<const float4 *>(L.nc + 2 * plane + o);
+                }
+                // the 16-pixel border of RGBResidual (:779-783) excludes whole groups: x0 is a multiple of 4
+                const bool rgb_group = A.rgb && y >= 16 && y < L.rows - 16 && x0 >= 16 && x0 < cols - 16;
+                short4 gx4 = make_short4(0, 0, 0, 0), gy4 = make_short4(0, 0, 0, 0);
+                float4 d14 = make_float4(0.f, 0.f, 0.f, 0.f);
+                unsigned ni4 = 0;
+                unsigned m0 = 0, m1 = 0, m2 = 0;
+                if(rgb_group)
+                {
+                    gx4 = *reinterpret_cast<const short4 *>(L.dIdx + o);
+                    gy4 = *reinterpret_cast<const short4 *>(L.dIdy + o);
+                    d14 = *reinterpret_cast<const float4 *>(L.next_depth + o);
+                    // 4 rows x 12 bytes [x0-4, x0+8) of the next image: non-zero masks, ANDed over the rows (:787-793)
+                    m0 = m1 = m2 = 0xffffffffu;
 #pragma unroll
-                    for(int k = 0; k < 4; k++)
+                    for(int r = -2; r < 2; r++)
                     {
-                        float row[7];
-                        if(icp_row(IP, make_float3(vx[k], vy[k], vz[k]), make_float3(nx[k], ny[k], nz[k]), vp, np, row)) accumulate_se3(accI, row);
+                        const unsigned * wp = reinterpret_cast<const unsigned *>(L.next_image + (size_t)(y + r) * cols + x0 - 4);
+                        const unsigned w0 = __ldg(wp), w1 = __ldg(wp + 1), w2 = __ldg(wp + 2);
+                        m0 &= __vcmpne4(w0, 0u);
+                        m1 &= __vcmpne4(w1, 0u);
+                        m2 &= __vcmpne4(w2, 0u);
+                        if(r == 0) ni4 = w1;
                     }
+                }
+
+                // stage 1: projections
+                float3 vg[4];
+                int ux[4], uy[4];
+                bool in1[4] = {false, false, false, false};
+                const float vx[4] = {a.x, a.y, a.z, a.w}, vy[4] = {b.x, b.y, b.z, b.w}, vz[4] = {c.x, c.y, c.z, c.w};
+                const float nx[4] = {d.x, d.y, d.z, d.w}, ny[4] = {e.x, e.y, e.z, e.w}, nz[4] = {f.x, f.y, f.z, f.w};
+                if(A.icp)
+                {
+#pragma unroll
+                    for(int k = 0; k < 4; k++) in1[k] = icp_project(IP, make_float3(vx[k], vy[k], vz[k]), vg[k], ux[k], uy[k]);
+                }
+                const short gxs[4] = {gx4.x, gx4.y, gx4.z, gx4.w}, gys[4] = {gy4.x, gy4.y, gy4.z, gy4.w};
+                const float d1s[4] = {d14.x, d14.y, d14.z, d14.w};
+                int u0[4], v0[4];
+                float td1[4];
+                bool in2[4];
+#pragma unroll
+                for(int k = 0; k < 4; k++)
+                {
+                    in2[k] = rgb_group && rgb_gate(RPi, x0 + k, y, gxs[k], gys[k], d1s[k]) && window_ok(m0, m1, m2, k);
+                    if(in2[k]) in2[k] = rgb_warp(RPi, x0 + k, y, d1s[k], u0[k], v0[k], td1[k]);
+                }
+
+                // stage 2: gathers
+                float3 vp[4], np[4];
+#pragma unroll
+                for(int k = 0; k < 4; k++)
+                {
+                    if(in1[k])
+                    {
+                        const size_t q = (size_t)uy[k] * cols + ux[k];
+                        vp[k].x = __ldg(L.vp + q); vp[k].y = __ldg(L.vp + plane + q); vp[k].z = __ldg(L.vp + 2 * plane + q);
+                        np[k].x = __ldg(L.np + q); np[k].y = __ldg(L.np + plane + q); np[k].z = __ldg(L.np + 2 * plane + q);
+                    }
+                }
+                float d0s[4];
+                unsigned ls[4];
+#pragma unroll
+                for(int k = 0; k < 4; k++)
+                {
+                    if(in2[k])
+                    {
+                        const size_t q = (size_t)v0[k] * cols + u0[k];
+                        d0s[k] = __ldg(L.last_depth + q);
+                        ls[k] = __ldg(L.last_image + q);
+                    }
+                }
+
+                // stage 3: math
+#pragma unroll
+                for(int k = 0; k < 4; k++)
+                {
+                    float row[7];
+                    if(in1[k] && icp_finish(IP, vg[k], make_float3(nx[k], ny[k], nz[k]), vp[k], np[k], row)) accumulate_se3(accI, row);
                 }
                 if(A.rgb)
                 {
-                    const short4 gx4 = *reinterpret_cast<const short4 *>(L.dIdx + o);
-                    const short4 gy4 = *reinterpret_cast<const short4 *>(L.dIdy + o);
-                    const float4 d14 = *reinterpret_cast<const float4 *>(L.next_depth + o);
-                    const short gxs[4] = {gx4.x, gx4.y, gx4.z, gx4.w}, gys[4] = {gy4.x, gy4.y, gy4.z, gy4.w};
-                    const float d1s[4] = {d14.x, d14.y, d14.z, d14.w};
 #pragma unroll
                     for(int k = 0; k < 4; k++)
                     {
-                        int u0 = 0, v0 = 0;
-                        float diff = 0.f, d0 = 0.f;
-                        const bool ok = rgb_residual_px(RP, x0 + k, y, gxs[k], gys[k], d1s[k], L.next_image, L.cols, L.last_image, L.last_depth,
-                                                        L.cols, u0, v0, diff, d0);
+                        const bool ok = in2[k] && rgb_accept(RPi, td1[k], d0s[k], (uint8_t)ls[k]);
                         int4 rec;
-                        rec.x = ok ? ((u0 & 0xffff) | (v0 << 16)) : -1;
-                        rec.y = __float_as_int(diff);
-                        rec.z = __float_as_int(d0);
-                        rec.w = ((int)gxs[k] & 0xffff) | ((int)gys[k] << 16);
-                        s_corr[(slot * 4 + k) * kThreads + threadIdx.x] = rec;
+                        rec.x = -1;
+                        rec.y = rec.z = rec.w = 0;
                         if(ok)
                         {
+                            const float diff = static_cast<float>((ni4 >> (8 * k)) & 0xffu) - static_cast<float>(ls[k]); // reduce.cu:827
+                            rec.x = (u0[k] & 0xffff) | (v0[k] << 16);
+                            rec.y = __float_as_int(diff);
+                            rec.z = __float_as_int(d0s[k]);
+                            rec.w = ((int)gxs[k] & 0xffff) | ((int)gys[k] << 16);
                             cnt += 1;
                             sig += (int)(diff * diff); // reduce.cu:830
                         }
+                        s_corr[(slot * 4 + k) * kThreads + threadIdx.x] = rec;
                     }
                 }
             }
+            stamp(5);
 
             // ICP sums leave the registers before the photometric phase needs its own 29
             {
-                const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
                 float vi = 0.f;
                 if(A.icp) vi = warp_transpose_reduce32(accI);
                 s_red[warp * 64 + lane] = vi;
@@ -545,31 +710,30 @@ __global__ void __launch_bounds__(kThreads, 1) k_track(const TrackArgs A)
             bool level_break = false;
             if(A.rgb)
             {
-                // ---- {count, sigma}: integer adds are exact in any order ----
+                // ---- barrier B: arrivals | count << 8 | sigma << 32 in one 64-bit word.  Integer adds are exact in
+                //      any order; sigma wraps mod 2^32 in the top bits exactly like the reference's int sum ----
                 cnt = __reduce_add_sync(kFullMask, cnt);
                 sig = __reduce_add_sync(kFullMask, sig);
-                const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-                if(lane == 0) { s_cnt[warp] = cnt; s_sig[warp] = sig; }
+                if(lane == 0) { s_wcnt[warp] = cnt; s_wsig[warp] = sig; }
                 __syncthreads();
                 if(threadIdx.x == 0)
                 {
-                    int c = 0, s = 0;
+                    unsigned c = 0, s = 0;
 #pragma unroll
-                    for(int w = 0; w < kWarps; w++) { c += s_cnt[w]; s += s_sig[w]; }
-                    if(c) atomicAdd(&ctl->rgb_cnt[cnt_slot][0], c);
-                    if(s) atomicAdd(&ctl->rgb_cnt[cnt_slot][1], s);
-                }
-                cta_arrive(&ctl->arrive_b);
-                ++arr_b;
-                cta_wait_ge(&ctl->arrive_b, arr_b * grid);
-                if(threadIdx.x == 0)
-                {
-                    s_cnt[0] = __ldcg(&ctl->rgb_cnt[cnt_slot][0]);
-                    s_sig[0] = __ldcg(&ctl->rgb_cnt[cnt_slot][1]);
+                    for(int w = 0; w < kWarps; w++) { c += (unsigned)s_wcnt[w]; s += (unsigned)s_wsig[w]; }
+                    unsigned long long * word = &ctl->bar_b[cnt_slot];
+                    atomicAdd(word, 1ull | ((unsigned long long)c << 8) | ((unsigned long long)s << 32));
+                    unsigned long long v;
+                    do
+                    {
+                        v = ld_relaxed64(word);
+                    } while((unsigned)(v & 0xffull) < grid);
+                    s_cnt = (int)((v >> 8) & 0xffffffull);
+                    s_sig = (int)(unsigned)(v >> 32);
                 }
                 __syncthreads();
-                const int rgbSize = s_cnt[0], sigma = s_sig[0];
-                __syncthreads();
+                const int rgbSize = s_cnt, sigma = s_sig;
+                stamp(6);
 
                 // RGBDOdometry.cpp:461-475 (the precedence quirk of :461 is kept)
                 float sigmaVal = (float)sqrt((double)((((float)sigma / (float)rgbSize) == 0) ? 1 : rgbSize));
@@ -580,8 +744,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_track(const TrackArgs A)
                     lastRGBError = rgbError;
                     if(is_solver)
                     {
-                        S.st.last_rgb_error = rgbError;
-                        S.st.last_rgb_count = (float)rgbSize;
+                        S.last_rgb_error = rgbError;
+                        S.last_rgb_count = (float)rgbSize;
                     }
                     if(A.rgb_only) sigmaVal = -1;
                     SP.sigma = sigmaVal;
@@ -596,9 +760,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_track(const TrackArgs A)
                             const int4 rec = s_corr[(sl * 4 + k) * kThreads + threadIdx.x];
                             if(rec.x != -1)
                             {
-                                const int u0 = rec.x & 0xffff, v0 = rec.x >> 16;
+                                const int pu = rec.x & 0xffff, pv = rec.x >> 16;
                                 const float Z = __int_as_float(rec.z);
-                                const float3 cp = project_point(u0, v0, Z, SP.inv_fx, SP.inv_fy, SP.cx, SP.cy);
+                                const float3 cp = project_point(pu, pv, Z, SP.inv_fx, SP.inv_fy, SP.cx, SP.cy);
                                 float row[7];
                                 rgb_row(SP, __int_as_float(rec.y), cp.x, cp.y, cp.z, (short)(rec.w & 0xffff), (short)(rec.w >> 16), row);
                                 accumulate_se3(accR, row);
@@ -610,14 +774,14 @@ __global__ void __launch_bounds__(kThreads, 1) k_track(const TrackArgs A)
             else if(is_solver)
             {
                 // :461-470 run even without RGB: sigma = rgbSize = 0 -> rgbError 0, count 0
-                S.st.last_rgb_error = 0.f;
-                S.st.last_rgb_count = 0.f;
+                S.last_rgb_error = 0.f;
+                S.last_rgb_count = 0.f;
             }
             if(level_break) break; // no arrival outstanding: every CTA takes the same branch
+            stamp(7);
 
             // ---- reduce; the sums are digested by CTA 0 at the top of the next iteration ----
             {
-                const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
                 float vr = 0.f;
                 if(A.rgb) vr = warp_transpose_reduce32(accR);
                 s_red[warp * 64 + 32 + lane] = vr;
@@ -631,6 +795,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_track(const TrackArgs A)
                 }
             }
             cta_arrive(&ctl->arrive);
+            stamp(8);
             ++arr;
             pending = true;
             pending_level = lv;
@@ -642,14 +807,14 @@ __global__ void __launch_bounds__(kThreads, 1) k_track(const TrackArgs A)
     // ============================================================================================
     if(!pending)
     {
-        // make sure every CTA has left its last wait before CTA 0 resets the counters
+        // make sure every CTA has left its last wait before CTA 0 resets the control block
         cta_arrive(&ctl->arrive);
         ++arr;
     }
     if(is_solver_cta)
     {
         if(pending) solve_pending();
-        else cta_wait_ge(&ctl->arrive, arr * grid);
+        else cta_wait_arrivals(&ctl->arrive, arr * grid);
     }
     if(is_solver)
     {
@@ -658,26 +823,55 @@ __global__ void __launch_bounds__(kThreads, 1) k_track(const TrackArgs A)
             const float d[3] = {S.tcurr[0] - A.tprev[0], S.tcurr[1] - A.tprev[1], S.tcurr[2] - A.tprev[2]};
             if(sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]) > 0.3)
             {
+#pragma unroll
                 for(int i = 0; i < 9; i++) S.Rcurr[i] = A.Rprev[i];
+#pragma unroll
                 for(int i = 0; i < 3; i++) S.tcurr[i] = A.tprev[i];
             }
         }
         TrackOutput * out = A.out;
+#pragma unroll
         for(int i = 0; i < 3; i++) out->trans[i] = S.tcurr[i];
+#pragma unroll
         for(int i = 0; i < 9; i++) out->rot[i] = S.Rcurr[i];
-        out->st = S.st;
-        out->status = 1;
+        out->st.last_icp_error = S.last_icp_error; out->st.last_icp_count = S.last_icp_count;
+        out->st.last_rgb_error = S.last_rgb_error; out->st.last_rgb_count = S.last_rgb_count;
+        out->st.last_so3_error = S.last_so3_error; out->st.last_so3_count = S.last_so3_count;
+        out->st.so3_iterations = S.so3_iterations;
+#pragma unroll
+        for(int i = 0; i < 3; i++) out->st.se3_iterations[i] = S.se3_iterations[i];
+        if(S.se3_iterations[0] + S.se3_iterations[1] + S.se3_iterations[2] > 0)
+        {
+            // lastA / lastb of the last solve (reduce.cu:475-486 unpack order)
+#pragma unroll
+            for(int i = 0; i < 6; i++)
+            {
+#pragma unroll
+                for(int j = i; j < 7; j++)
+                {
+                    const double v = ctl->last_S[hm::acc_index(i, j)];
+                    if(j == 6) out->st.last_b[i] = v;
+                    else out->st.last_A[j * 6 + i] = out->st.last_A[i * 6 + j] = v;
+                }
+            }
+            out->status = 1;
+        }
+        else
+            out->status = 2; // no solve ran: lastA / lastb keep their previous values (host side)
         __threadfence_system();
         // every other CTA has made its last arrival and waits on nothing more
         ctl->arrive = 0;
-        ctl->release = 0;
-        ctl->arrive_b = 0;
-        for(int i = 0; i < kMaxIters; i++) { ctl->rgb_cnt[i][0] = 0; ctl->rgb_cnt[i][1] = 0; }
+#pragma unroll
+        for(int s = 0; s < 4; s++) ctl->line.w[s * 8 + 7] = 0;
+        for(int i = 0; i < kMaxIters; i++) ctl->bar_b[i] = 0ull;
     }
 }
 
 struct DeviceTrack
 {
+    long long * dbg;      // device, kMaxIters * kDbgStamps stamps (EF_TRACK_TIMING=1)
+    double dbg_acc[kMaxIters][kDbgStamps];
+    long long dbg_n;
     TrackCtl * ctl;
     float * partials;
     TrackOutput * out; // pinned
@@ -693,7 +887,7 @@ int device_track_init(ef_tracker * t)
     DeviceTrack * d = new DeviceTrack();
     memset(d, 0, sizeof(*d));
     t->track_state = d;
-    d->grid = t->num_sms;
+    d->grid = t->num_sms < kMaxGrid ? t->num_sms : kMaxGrid;
     const int groups0 = (t->width / 4) * t->height;
     const int per_cta = (groups0 + d->grid - 1) / d->grid;
     d->corr_slots = (per_cta + kThreads - 1) / kThreads * 4;
@@ -703,6 +897,12 @@ int device_track_init(ef_tracker * t)
     if(e == cudaSuccess) e = cudaMalloc((void **)&d->partials, (size_t)d->grid * 64 * sizeof(float));
     if(e == cudaSuccess) e = cudaMemsetAsync(d->partials, 0, (size_t)d->grid * 64 * sizeof(float), t->stream);
     if(e == cudaSuccess) e = cudaHostAlloc((void **)&d->out, sizeof(TrackOutput), cudaHostAllocMapped);
+    const char * env = getenv("EF_TRACK_TIMING");
+    if(e == cudaSuccess && env && env[0] == '1')
+    {
+        e = cudaMalloc((void **)&d->dbg, sizeof(long long) * kMaxIters * kDbgStamps);
+        if(e == cudaSuccess) e = cudaMemsetAsync(d->dbg, 0, sizeof(long long) * kMaxIters * kDbgStamps, t->stream);
+    }
     if(e == cudaSuccess && d->smem_bytes <= 200 * 1024)
         e = cudaFuncSetAttribute(k_track, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->smem_bytes);
     if(e != cudaSuccess)
@@ -718,6 +918,27 @@ void device_track_destroy(ef_tracker * t)
 {
     DeviceTrack * d = static_cast<DeviceTrack *>(t->track_state);
     if(!d) return;
+    if(d->dbg)
+    {
+        if(d->dbg_n > 0)
+        {
+            // stamps (cycles of CTA 0's SM): 0 loop top | 1 arrivals seen | 2 final reduce | 3 solve | 4 params published
+            // + loaded | 5 phase A | 6 barrier B | 7 phase B | 8 reduce + arrive
+            fprintf(stderr, "[ef_track timing] avg cycles per SE3 iteration over %lld calls (wait reduce solve publish | phaseA barB phaseB arrive | total)\n",
+                    d->dbg_n);
+            for(int it = 0; it < kMaxIters; it++)
+            {
+                const double * a = d->dbg_acc[it];
+                if(a[4] == 0) continue;
+                const double n = (double)d->dbg_n;
+                const bool first = a[1] == 0;
+                fprintf(stderr, "  it %2d: %7.0f %7.0f %7.0f %7.0f | %7.0f %7.0f %7.0f %7.0f | %8.0f\n", it, first ? 0.0 : (a[1] - a[0]) / n,
+                        first ? 0.0 : (a[2] - a[1]) / n, first ? 0.0 : (a[3] - a[2]) / n, (a[4] - (first ? a[0] : a[3])) / n, (a[5] - a[4]) / n,
+                        (a[6] - a[5]) / n, (a[7] - a[6]) / n, (a[8] - a[7]) / n, (a[8] - a[0]) / n);
+            }
+        }
+        cudaFree(d->dbg);
+    }
     if(d->ctl) cudaFree(d->ctl);
     if(d->partials) cudaFree(d->partials);
     if(d->out) cudaFreeHost(d->out);
@@ -729,7 +950,7 @@ int device_track_launch(ef_tracker * t, const float * trans, const float * rot, 
 {
     DeviceTrack * d = static_cast<DeviceTrack *>(t->track_state);
     if(!d) return EF_ERR_BAD_STATE;
-    if(d->smem_bytes > 200 * 1024)
+    if(d->smem_bytes > 200 * 1024 || (size_t)t->width * t->height >= (1u << 24))
     {
         t->err = "image too large for the shared-memory correspondence store of EF_SOLVE_DEVICE";
         return EF_ERR_UNSUPPORTED;
@@ -737,7 +958,6 @@ int device_track_launch(ef_tracker * t, const float * trans, const float * rot, 
     TrackArgs A;
     memset(&A, 0, sizeof(A));
     const int iterations[kNumPyrs] = {fast_odom ? 3 : 10, pyramid ? 5 : 0, pyramid ? 4 : 0}; // :384-386
-    if(iterations[0] + iterations[1] + iterations[2] > kMaxIters) return EF_ERR_INVALID_ARGUMENT;
     for(int i = 0; i < kNumPyrs; i++)
     {
         LevelArgs & L = A.lvl[i];
@@ -751,15 +971,12 @@ int device_track_launch(ef_tracker * t, const float * trans, const float * rot, 
         L.inv_fx = 1.0f / L.fx; L.inv_fy = 1.0f / L.fy;
         L.min_scale = (float)(pow(t->min_grad[i], 2.0) / pow(t->sobel_scale, 2.0)); // :442
         L.iterations = iterations[i];
+        const double K[9] = {L.fx, 0, L.cx, 0, L.fy, L.cy, 0, 0, 1};
+        hm::inverse33(K, L.K_inv);
     }
     A.so3_last = t->last_next_image[2];
     A.so3_next = t->next_image[2];
-    {
-        const double K2[9] = {A.lvl[2].fx, 0, A.lvl[2].cx, 0, A.lvl[2].fy, A.lvl[2].cy, 0, 0, 1};
-        double Ki[9];
-        hm::inverse33(K2, Ki);
-        for(int i = 0; i < 9; i++) A.so3_kinv[i] = (float)Ki[i];
-    }
+    for(int i = 0; i < 9; i++) A.so3_kinv[i] = (float)A.lvl[2].K_inv[i];
     memcpy(A.Rprev, rot, sizeof(A.Rprev));
     memcpy(A.tprev, trans, sizeof(A.tprev));
     hm::inverse33(A.Rprev, A.Rprev_inv); // :388
@@ -775,7 +992,7 @@ int device_track_launch(ef_tracker * t, const float * trans, const float * rot, 
     A.ctl = d->ctl;
     A.partials = d->partials;
     A.out = d->out; // UVA: pinned + mapped host memory is addressable from the device
-    A.corr_slots = d->corr_slots;
+    A.dbg = d->dbg;
 
     d->out->status = 0;
     void * args[] = {&A};
@@ -799,14 +1016,35 @@ int device_track_finish(ef_tracker * t, float * trans, float * rot)
         t->err = std::string("track kernel: ") + cudaGetErrorString(e);
         return (int)e;
     }
-    if(d->out->status != 1)
+    if(d->out->status != 1 && d->out->status != 2)
     {
         t->err = "track kernel produced no result";
         return EF_ERR_BAD_STATE;
     }
     memcpy(trans, d->out->trans, sizeof(d->out->trans));
     memcpy(rot, d->out->rot, sizeof(d->out->rot));
-    t->st = d->out->st;
+    const ef_track_stats & o = d->out->st;
+    t->st.last_icp_error = o.last_icp_error; t->st.last_icp_count = o.last_icp_count;
+    t->st.last_rgb_error = o.last_rgb_error; t->st.last_rgb_count = o.last_rgb_count;
+    t->st.last_so3_error = o.last_so3_error; t->st.last_so3_count = o.last_so3_count;
+    t->st.so3_iterations = o.so3_iterations;
+    for(int i = 0; i < 3; i++) t->st.se3_iterations[i] = o.se3_iterations[i];
+    if(d->out->status == 1)
+    {
+        memcpy(t->st.last_A, o.last_A, sizeof(o.last_A));
+        memcpy(t->st.last_b, o.last_b, sizeof(o.last_b));
+    }
+    if(d->dbg)
+    {
+        long long h[kMaxIters * kDbgStamps];
+        if(cudaMemcpy(h, d->dbg, sizeof(h), cudaMemcpyDeviceToHost) == cudaSuccess)
+        {
+            for(int it = 0; it < kMaxIters; it++)
+                for(int k = 0; k < kDbgStamps; k++) d->dbg_acc[it][k] += (double)h[it * kDbgStamps + k];
+            d->dbg_n++;
+            cudaMemset(d->dbg, 0, sizeof(h));
+        }
+    }
     return EF_OK;
 }
 

@@ -75,6 +75,13 @@ struct ef_tracker
     float * h_result; // pinned, 32 floats
     bool deriv_valid; // dIdx/dIdy match next_image
 
+    // EF_OPT_PROFILE
+    int profile;
+    cudaEvent_t ev_begin, ev_end;
+    bool ev_pending;
+    double prof_ms;
+    long long prof_calls;
+
     ef_track_stats st;
     std::string err;
     long long launches;

@@ -12,7 +12,7 @@ import numpy as np
 from . import binding
 from .binding import EFError, TrackStats
 
-EF_OPT_SOLVE_MODE, EF_OPT_USE_GRAPH, EF_OPT_FUSED_BUILD = 1, 2, 3
+EF_OPT_SOLVE_MODE, EF_OPT_USE_GRAPH, EF_OPT_FUSED_BUILD, EF_OPT_PROFILE = 1, 2, 3, 4
 EF_SOLVE_HOST, EF_SOLVE_DEVICE = 0, 1
 
 _LEVEL_BUFFERS = {"vmap_curr": (np.float32, 3), "nmap_curr": (np.float32, 3), "vmap_g_prev": (np.float32, 3),
@@ -98,6 +98,12 @@ class RGBDOdometry:
     @property
     def launch_count(self):
         return int(self._L.ef_tracker_launch_count(self._h))
+
+    def profile(self):
+        """(solve_ms_total, calls) accumulated since the last read (needs set_option(EF_OPT_PROFILE, 1))."""
+        ms, n = C.c_double(0), C.c_longlong(0)
+        self._check(self._L.ef_tracker_profile(self._h, C.byref(ms), C.byref(n)), "ef_tracker_profile")
+        return ms.value, n.value
 
     def synchronize(self):
         self._check(self._L.ef_tracker_synchronize(self._h), "ef_tracker_synchronize")
