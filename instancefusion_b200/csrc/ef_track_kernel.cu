@@ -38,12 +38,16 @@ namespace ef
 namespace
 {
 
-constexpr int kThreads = 640;    // 20 warps = 5 per scheduler (96 registers each); 640x480 level 0 has 519 four-pixel groups per CTA -> one pass
+constexpr int kThreads = 640;    // 20 warps = 5 per scheduler (96 registers each)
 constexpr int kWarps = kThreads / 32;
-constexpr int kRedThreads = 512; // threads of CTA 0 used by the final cross-CTA sum (8 parts x 64 slots)
 constexpr int kMaxIters = 32;    // SE3 iterations per call (19 in the reference schedule)
-constexpr int kMaxGrid = 160;    // final-reduce unroll bound (B200: 148 SMs)
 constexpr int kDbgStamps = 10;
+constexpr int kRowChunks = 20;   // a partial row = 20 x (3 floats + flag) = 60 floats >= 29 ICP + 29 RGB sums
+constexpr int kRowFloats = kRowChunks * 3;
+constexpr int kSo3Chunks = 4;    // SO3 rows carry 11 floats
+constexpr int kLineChunks = 8;   // the parameter line = 8 x (3 floats + flag) = 24 floats
+constexpr int kPayload = kLineChunks * 3;
+constexpr int kParts = kThreads / 64; // final cross-CTA sum: 10 parts x 64 slots
 
 struct LevelArgs
 {
@@ -56,24 +60,21 @@ struct LevelArgs
     float inv_fx, inv_fy;                         // host 1.0f / f (cudafuncs.cu:671)
     float min_scale;
     int iterations;
+    int px;                                       // pixels per thread unit at this level (4 or 1)
     double K_inv[9];                              // host double inverse of K (RGBDOdometry.cpp:428)
 };
 
-// one 128-byte line: sector s = words [8s, 8s+7), word 8s+7 = epoch.  28 payload floats.
-struct alignas(128) ParamLine
-{
-    unsigned w[32];
-};
-// SE3 payload: Rcurr[9] tcurr[3] krkinv[9] kt[3];  SO3 payload: H[9] krlr[9] done
-constexpr int kPayload = 28;
-
+// Flagged 16-byte chunks (the NCCL "LL" idea): a chunk is written with ONE 128-bit store and read with ONE
+// 128-bit load, so its three payload words and its flag are always observed together.  No fence, no separate
+// "ready" counter: whoever polls a chunk gets the data with the same load that tells it the data is there.
+// Flags are launch-unique epochs (launch_seq << 8 | n), so nothing has to be reset between launches.
 struct alignas(128) TrackCtl
 {
-    unsigned arrive;  unsigned pad0[31];          // solve barrier: arrivals (monotonic within a launch)
-    ParamLine line;                               // parameters + epoch, written by the solver thread
+    uint4 line[kLineChunks];                      // parameters of the next phase, written by the solver thread
     unsigned long long bar_b[kMaxIters];          // per SE3 iteration: arrivals | count << 8 | sigma << 32
     double last_S[27];                            // combined normal equations of the last solve (for lastA / lastb)
 };
+// SE3 payload: Rcurr[9] tcurr[3] krkinv[9] kt[3];  SO3 payload: H[9] krlr[9] done
 
 struct TrackOutput // pinned host memory, written by the solver thread
 {
@@ -91,18 +92,23 @@ struct TrackArgs
     float dist_thresh, angle_thresh, max_depth_delta, sobel_scale, icp_weight;
     int icp, rgb, rgb_only, so3;
     float prev_icp_error, prev_icp_count, prev_so3_error, prev_so3_count, prev_rgb_error, prev_rgb_count;
+    unsigned epoch_base;                          // launch_seq << 8
     TrackCtl * ctl;
-    float * partials;                             // gridDim.x * 64 floats
+    uint4 * rows;                                 // (gridDim.x - 1) * kRowChunks flagged chunks, one row per worker CTA
     TrackOutput * out;
     long long * dbg;                              // optional clock64 stamps of CTA 0 (EF_TRACK_TIMING=1)
 };
 
-// ---- memory-ordering primitives (PTX memory model, gpu scope) ----
-__device__ __forceinline__ unsigned ld_relaxed(const unsigned * p)
+// ---- 128-bit relaxed (L2-coherent) accesses ----
+__device__ __forceinline__ uint4 ld_relaxed_v4(const uint4 * p)
 {
-    unsigned v;
-    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    uint4 v;
+    asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
     return v;
+}
+__device__ __forceinline__ void st_relaxed_v4(uint4 * p, const uint4 & v)
+{
+    asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 __device__ __forceinline__ unsigned long long ld_relaxed64(const unsigned long long * p)
 {
@@ -110,61 +116,79 @@ __device__ __forceinline__ unsigned long long ld_relaxed64(const unsigned long l
     asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ void st_relaxed(unsigned * p, unsigned v)
-{
-    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ void red_release_add(unsigned * p, unsigned v)
-{
-    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ void fence_acq_rel()
-{
-    asm volatile("fence.acq_rel.gpu;" ::: "memory");
-}
 
-// all threads of the CTA call; the CTA's prior writes are ordered before the arrival (bar.sync + release)
-__device__ __forceinline__ void cta_arrive(unsigned * counter)
-{
-    __syncthreads();
-    if(threadIdx.x == 0) red_release_add(counter, 1u);
-}
-
-// CTA 0 only: wait until `target` arrivals are visible, then acquire
-__device__ __forceinline__ void cta_wait_arrivals(const unsigned * counter, unsigned target)
-{
-    if(threadIdx.x == 0)
-    {
-        while(ld_relaxed(counter) < target) { }
-        fence_acq_rel();
-    }
-    __syncthreads();
-}
-
-// solver thread: payload first, fence, then the four epoch words (each sector is validated on its own)
-__device__ __forceinline__ void publish_line(ParamLine * L, const float * payload, unsigned epoch)
+// solver thread: eight self-validating chunks
+__device__ __forceinline__ void publish_line(uint4 * line, const float * payload, unsigned epoch)
 {
 #pragma unroll
-    for(int i = 0; i < kPayload; i++) st_relaxed(&L->w[(i / 7) * 8 + (i % 7)], __float_as_uint(payload[i]));
-    fence_acq_rel();
-#pragma unroll
-    for(int s = 0; s < 4; s++) st_relaxed(&L->w[s * 8 + 7], epoch);
+    for(int c = 0; c < kLineChunks; c++)
+        st_relaxed_v4(line + c, make_uint4(__float_as_uint(payload[3 * c]), __float_as_uint(payload[3 * c + 1]), __float_as_uint(payload[3 * c + 2]), epoch));
 }
 
-// all threads call: warp 0 spins on the line until every sector shows `epoch`, then the payload is in smem.
-// A 32-byte sector is read atomically, and a sector's epoch is written after (fence) its payload, so a
-// sector that shows the new epoch also shows the new payload.
-__device__ __forceinline__ void wait_line(const ParamLine * L, unsigned epoch, float * s_payload)
+// all threads call: lanes 0..7 of warp 0 spin on their chunk until it shows `epoch`; payload -> smem
+__device__ __forceinline__ void wait_line(const uint4 * line, unsigned epoch, float * s_payload)
 {
     if(threadIdx.x < 32)
     {
         const unsigned lane = threadIdx.x;
-        unsigned v;
+        uint4 v = make_uint4(0, 0, 0, epoch);
         do
         {
-            v = ld_relaxed(&L->w[lane]);
-        } while(!__all_sync(kFullMask, ((lane & 7u) != 7u) || v == epoch));
-        if((lane & 7u) != 7u) s_payload[(lane >> 3) * 7 + (lane & 7u)] = __uint_as_float(v);
+            if(lane < kLineChunks) v = ld_relaxed_v4(line + lane);
+        } while(!__all_sync(kFullMask, v.w == epoch));
+        if(lane < kLineChunks)
+        {
+            s_payload[3 * lane] = __uint_as_float(v.x);
+            s_payload[3 * lane + 1] = __uint_as_float(v.y);
+            s_payload[3 * lane + 2] = __uint_as_float(v.z);
+        }
+    }
+    __syncthreads();
+}
+
+// worker CTA: publish this CTA's partial sums (already in shared memory) as flagged chunks
+__device__ __forceinline__ void publish_row(uint4 * my_row, const float * s_row, int chunks, unsigned epoch)
+{
+    if((int)threadIdx.x < chunks)
+    {
+        const int c = threadIdx.x;
+        st_relaxed_v4(my_row + c, make_uint4(__float_as_uint(s_row[3 * c]), __float_as_uint(s_row[3 * c + 1]), __float_as_uint(s_row[3 * c + 2]), epoch));
+    }
+}
+
+// CTA 0: collect every worker's row (poll + load in one), then add the rows in worker order -> s_final[64]
+__device__ __forceinline__ void gather_rows(const uint4 * rows, int workers, int chunks, unsigned epoch, float * s_rows /*[workers][kRowFloats]*/,
+                                            float * s_red, float * s_final)
+{
+    const int total = workers * chunks;
+    for(int i = threadIdx.x; i < total; i += kThreads)
+    {
+        const int w = i / chunks, c = i - w * chunks;
+        const uint4 * p = rows + (size_t)w * kRowChunks + c;
+        uint4 v;
+        do
+        {
+            v = ld_relaxed_v4(p);
+        } while(v.w != epoch);
+        float * d = s_rows + w * kRowFloats + 3 * c;
+        d[0] = __uint_as_float(v.x);
+        d[1] = __uint_as_float(v.y);
+        d[2] = __uint_as_float(v.z);
+    }
+    __syncthreads();
+    const int nfl = chunks * 3;
+    const int slot = threadIdx.x & 63, part = threadIdx.x >> 6;
+    float s = 0.f;
+    if(slot < nfl)
+        for(int w = part; w < workers; w += kParts) s += s_rows[w * kRowFloats + slot];
+    s_red[part * 64 + slot] = s;
+    __syncthreads();
+    if(threadIdx.x < 64)
+    {
+        float tot = 0.f;
+#pragma unroll
+        for(int p = 0; p < kParts; p++) tot += s_red[p * 64 + threadIdx.x];
+        s_final[threadIdx.x] = tot;
     }
     __syncthreads();
 }
@@ -190,8 +214,8 @@ struct Solver
 };
 
 // RGBDOdometry.cpp:515-516, :541-583 -- runs in ONE thread (thread 0 of CTA 0).  Kept out of line so its
-// double-precision register needs do not inflate the per-pixel phases of the kernel.  s_final: 64 floats in
-// shared memory = ICP accumulator (29, padded to 32) followed by the RGB accumulator.
+// double-precision register needs do not inflate the per-pixel phases of the kernel.  s_final (shared memory):
+// ICP accumulator [0, 29) followed by the RGB accumulator [29, 58).
 __device__ __noinline__ void solve_se3(Solver & S, const float * s_final, double * last_S, int icp, int rgb, float icp_weight,
                                        const float * Rprev, const float * tprev, int level)
 {
@@ -211,13 +235,13 @@ __device__ __noinline__ void solve_se3(Solver & S, const float * s_final, double
             for(int j = i; j < 7; j++)
             {
                 const int k = hm::acc_index(i, j);
-                Sm[k] = (j == 6) ? ((double)s_final[32 + k] + w * (double)s_final[k]) : ((double)s_final[32 + k] + w * w * (double)s_final[k]);
+                Sm[k] = (j == 6) ? ((double)s_final[29 + k] + w * (double)s_final[k]) : ((double)s_final[29 + k] + w * w * (double)s_final[k]);
             }
         }
     }
     else
     {
-        const int o = icp ? 0 : 32;
+        const int o = icp ? 0 : 29;
 #pragma unroll
         for(int k = 0; k < 27; k++) Sm[k] = (double)s_final[o + k];
     }
@@ -317,39 +341,6 @@ __device__ __noinline__ void make_so3_payload(const So3State & Z, float * payloa
     for(int i = 19; i < kPayload; i++) payload[i] = 0.f;
 }
 
-// CTA 0 only, after all arrivals: add the partial rows in CTA-index order -> s_final[SLOTS].
-// Loads are issued as one unrolled batch (independent), the adds stay in row order.
-template<int SLOTS>
-__device__ __forceinline__ void cta0_final_reduce(const float * __restrict__ partials, float * s_red, float * s_final)
-{
-    constexpr int kParts = kRedThreads / SLOTS;
-    constexpr int kPer = (kMaxGrid + kParts - 1) / kParts;
-    const int slot = threadIdx.x % SLOTS, part = threadIdx.x / SLOTS;
-    if(threadIdx.x < kRedThreads)
-    {
-        float v[kPer];
-#pragma unroll
-        for(int i = 0; i < kPer; i++)
-        {
-            const unsigned b = part + i * kParts;
-            v[i] = (b < gridDim.x) ? __ldcg(partials + b * 64 + slot) : 0.f;
-        }
-        float s = 0.f;
-#pragma unroll
-        for(int i = 0; i < kPer; i++) s += v[i];
-        s_red[part * SLOTS + slot] = s;
-    }
-    __syncthreads();
-    if(threadIdx.x < SLOTS)
-    {
-        float tot = 0.f;
-#pragma unroll
-        for(int p = 0; p < kParts; p++) tot += s_red[p * SLOTS + threadIdx.x];
-        s_final[threadIdx.x] = tot;
-    }
-    __syncthreads();
-}
-
 // bytes k+2 .. k+5 of the 12-byte run (a0 a1 a2) all 0xFF ?  (4x4 validity window of pixel k of a group)
 __device__ __forceinline__ bool window_ok(unsigned a0, unsigned a1, unsigned a2, int k)
 {
@@ -361,9 +352,188 @@ __device__ __forceinline__ bool window_ok(unsigned a0, unsigned a1, unsigned a2,
     return m == 0xffffffffu;
 }
 
+// ------------------------------------------------------------------------------------------------
+// per-unit pixel work.  A "unit" is PX consecutive pixels of one row handled by one thread (PX = 4 with
+// 128-bit loads at the fine levels, PX = 1 at the coarse ones so that the few pixels spread over many threads).
+// ------------------------------------------------------------------------------------------------
+template<int PX>
+__device__ __forceinline__ void rgb_assoc_unit(const LevelArgs & L, const RgbResParams & RP, int y, int x0, int4 * s_corr, int rec_base, int & cnt,
+                                               int & sig)
+{
+    const int cols = L.cols;
+    // the 16-pixel border of RGBResidual (:779-783); x0 is a multiple of PX so a 4-pixel unit is all in or all out
+    const bool in_region = y >= 16 && y < L.rows - 16 && x0 >= 16 && x0 < cols - 16;
+    short gxs[PX], gys[PX];
+    float d1s[PX];
+    unsigned ni4 = 0, m0 = 0, m1 = 0, m2 = 0;
+    const int xa = x0 & ~3; // aligned start of the 12-byte validity run [xa-4, xa+8)
+    if(in_region)
+    {
+        const size_t o = (size_t)y * cols + x0;
+        if constexpr(PX == 4)
+        {
+            const short4 gx4 = *reinterpret_cast<const short4 *>(L.dIdx + o);
+            const short4 gy4 = *reinterpret_cast<const short4 *>(L.dIdy + o);
+            const float4 d14 = *reinterpret_cast<const float4 *>(L.next_depth + o);
+            gxs[0] = gx4.x; gxs[1] = gx4.y; gxs[2] = gx4.z; gxs[3] = gx4.w;
+            gys[0] = gy4.x; gys[1] = gy4.y; gys[2] = gy4.z; gys[3] = gy4.w;
+            d1s[0] = d14.x; d1s[1] = d14.y; d1s[2] = d14.z; d1s[3] = d14.w;
+        }
+        else
+        {
+            gxs[0] = L.dIdx[o];
+            gys[0] = L.dIdy[o];
+            d1s[0] = L.next_depth[o];
+        }
+        // 4 rows x 12 bytes of the next image: non-zero masks, ANDed over the rows (:787-793)
+        m0 = m1 = m2 = 0xffffffffu;
+#pragma unroll
+        for(int r = -2; r < 2; r++)
+        {
+            const unsigned * wp = reinterpret_cast<const unsigned *>(L.next_image + (size_t)(y + r) * cols + xa - 4);
+            const unsigned w0 = __ldg(wp), w1 = __ldg(wp + 1), w2 = __ldg(wp + 2);
+            m0 &= __vcmpne4(w0, 0u);
+            m1 &= __vcmpne4(w1, 0u);
+            m2 &= __vcmpne4(w2, 0u);
+            if(r == 0) ni4 = w1;
+        }
+    }
+    int u0[PX], v0[PX];
+    float td1[PX];
+    bool ok[PX];
+#pragma unroll
+    for(int k = 0; k < PX; k++)
+    {
+        const int kk = (x0 + k) & 3;
+        ok[k] = in_region && rgb_gate(RP, x0 + k, y, gxs[k], gys[k], d1s[k]) && window_ok(m0, m1, m2, kk);
+        if(ok[k]) ok[k] = rgb_warp(RP, x0 + k, y, d1s[k], u0[k], v0[k], td1[k]);
+    }
+    float d0s[PX];
+    unsigned ls[PX];
+#pragma unroll
+    for(int k = 0; k < PX; k++)
+    {
+        if(ok[k])
+        {
+            const size_t q = (size_t)v0[k] * cols + u0[k];
+            d0s[k] = __ldg(L.last_depth + q);
+            ls[k] = __ldg(L.last_image + q);
+        }
+    }
+#pragma unroll
+    for(int k = 0; k < PX; k++)
+    {
+        const int kk = (x0 + k) & 3;
+        const bool good = ok[k] && rgb_accept(RP, td1[k], d0s[k], (uint8_t)ls[k]);
+        int4 rec;
+        rec.x = -1;
+        rec.y = rec.z = rec.w = 0;
+        if(good)
+        {
+            const float diff = static_cast<float>((ni4 >> (8 * kk)) & 0xffu) - static_cast<float>(ls[k]); // reduce.cu:827
+            rec.x = (u0[k] & 0xffff) | (v0[k] << 16);
+            rec.y = __float_as_int(diff);
+            rec.z = __float_as_int(d0s[k]);
+            rec.w = ((int)gxs[k] & 0xffff) | ((int)gys[k] << 16);
+            cnt += 1;
+            sig += (int)(diff * diff); // reduce.cu:830
+        }
+        s_corr[(rec_base + k) * kThreads + threadIdx.x] = rec;
+    }
+}
+
+template<int PX>
+__device__ __forceinline__ void icp_unit(const LevelArgs & L, const IcpParams & IP, int y, int x0, float * accI)
+{
+    const int cols = L.cols;
+    const size_t plane = (size_t)L.rows * cols;
+    const size_t o = (size_t)y * cols + x0;
+    float vx[PX], vy[PX], vz[PX], nx[PX], ny[PX], nz[PX];
+    if constexpr(PX == 4)
+    {
+        const float4 a = *reinterpret_cast<const float4 *>(L.vc + o);
+        const float4 b = *reinterpret_cast<const float4 *>(L.vc + plane + o);
+        const float4 c = *reinterpret_cast<const float4 *>(L.vc + 2 * plane + o);
+        const float4 d = *reinterpret_cast<const float4 *>(L.nc + o);
+        const float4 e = *reinterpret_cast<const float4 *>(L.nc + plane + o);
+        const float4 f = *reinterpret_cast<const float4 *>(L.nc + 2 * plane + o);
+        vx[0] = a.x; vx[1] = a.y; vx[2] = a.z; vx[3] = a.w;
+        vy[0] = b.x; vy[1] = b.y; vy[2] = b.z; vy[3] = b.w;
+        vz[0] = c.x; vz[1] = c.y; vz[2] = c.z; vz[3] = c.w;
+        nx[0] = d.x; nx[1] = d.y; nx[2] = d.z; nx[3] = d.w;
+        ny[0] = e.x; ny[1] = e.y; ny[2] = e.z; ny[3] = e.w;
+        nz[0] = f.x; nz[1] = f.y; nz[2] = f.z; nz[3] = f.w;
+    }
+    else
+    {
+        vx[0] = L.vc[o]; vy[0] = L.vc[plane + o]; vz[0] = L.vc[2 * plane + o];
+        nx[0] = L.nc[o]; ny[0] = L.nc[plane + o]; nz[0] = L.nc[2 * plane + o];
+    }
+    float3 vg[PX], vp[PX], np[PX];
+    int ux[PX], uy[PX];
+    bool in1[PX];
+#pragma unroll
+    for(int k = 0; k < PX; k++) in1[k] = icp_project(IP, make_float3(vx[k], vy[k], vz[k]), vg[k], ux[k], uy[k]);
+#pragma unroll
+    for(int k = 0; k < PX; k++)
+    {
+        if(in1[k])
+        {
+            const size_t q = (size_t)uy[k] * cols + ux[k];
+            vp[k].x = __ldg(L.vp + q); vp[k].y = __ldg(L.vp + plane + q); vp[k].z = __ldg(L.vp + 2 * plane + q);
+            np[k].x = __ldg(L.np + q); np[k].y = __ldg(L.np + plane + q); np[k].z = __ldg(L.np + 2 * plane + q);
+        }
+    }
+#pragma unroll
+    for(int k = 0; k < PX; k++)
+    {
+        float row[7];
+        if(in1[k] && icp_finish(IP, vg[k], make_float3(nx[k], ny[k], nz[k]), vp[k], np[k], row)) accumulate_se3(accI, row);
+    }
+}
+
+template<int PX>
+__device__ __forceinline__ void rgb_rows_unit(const RgbStepParams & SP, const int4 * s_corr, int rec_base, float * accR)
+{
+#pragma unroll
+    for(int k = 0; k < PX; k++)
+    {
+        const int4 rec = s_corr[(rec_base + k) * kThreads + threadIdx.x];
+        if(rec.x != -1)
+        {
+            const int pu = rec.x & 0xffff, pv = rec.x >> 16;
+            const float Z = __int_as_float(rec.z);
+            const float3 cp = project_point(pu, pv, Z, SP.inv_fx, SP.inv_fy, SP.cx, SP.cy);
+            float row[7];
+            rgb_row(SP, __int_as_float(rec.y), cp.x, cp.y, cp.z, (short)(rec.w & 0xffff), (short)(rec.w >> 16), row);
+            accumulate_se3(accR, row);
+        }
+    }
+}
+
+// Units are dealt to the worker CTAs in 32-unit chunks, round-robin, so that image regions with no work (the
+// photometric border, depth holes) are spread evenly: chunk c -> worker c % W, handled by warp (c / W) % kWarps
+// in pass (c / W) / kWarps.
+struct UnitIter
+{
+    int units, W, worker, lane, warp;
+    __device__ __forceinline__ int unit(int pass) const
+    {
+        const int local_chunk = pass * kWarps + warp;
+        const int u = (local_chunk * W + worker) * 32 + lane;
+        return u < units ? u : -1;
+    }
+    __device__ __forceinline__ int passes() const
+    {
+        const int chunks = (units + 31) / 32;
+        const int per_worker = (chunks + W - 1) / W;
+        return (per_worker + kWarps - 1) / kWarps;
+    }
+};
+
 __global__ void __launch_bounds__(kThreads, 1) k_track(const TrackArgs A)
 {
-    extern __shared__ int4 s_corr[];            // [corr_slots][kThreads]
+    extern __shared__ int4 s_dyn[];             // workers: correspondence records; CTA 0: gathered rows
     __shared__ float s_red[kWarps * 64];
     __shared__ float s_final[64];
     __shared__ float s_par[kPayload];
@@ -372,14 +542,17 @@ __global__ void __launch_bounds__(kThreads, 1) k_track(const TrackArgs A)
 
     TrackCtl * ctl = A.ctl;
     const unsigned grid = gridDim.x;
+    const int W = (int)grid - 1;                // worker CTAs (blockIdx 1 .. grid-1); CTA 0 only gathers and solves
     const bool is_solver_cta = (blockIdx.x == 0);
     const bool is_solver = is_solver_cta && threadIdx.x == 0;
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    float * my_row = A.partials + (size_t)blockIdx.x * 64;
+    uint4 * my_row = A.rows + (size_t)(blockIdx.x == 0 ? 0 : blockIdx.x - 1) * kRowChunks;
+    int4 * s_corr = s_dyn;
+    float * s_rows = reinterpret_cast<float *>(s_dyn);
 
-    // barrier bookkeeping, tracked identically by every thread of the grid
-    unsigned rel = 0; // parameter publications (epochs)
-    unsigned arr = 0; // completed arrival rounds on ctl->arrive
+    // epochs, tracked identically by every thread of the grid
+    unsigned rel = A.epoch_base; // parameter publications
+    unsigned arr = A.epoch_base; // row rounds
 
     Solver S;
     if(is_solver)
@@ -420,47 +593,47 @@ __global__ void __launch_bounds__(kThreads, 1) k_track(const TrackArgs A)
             Z.lastError = FLT_MAX / 2;
             Z.lastCount = FLT_MAX / 2;
         }
-
-        const int npix = L.rows * L.cols;
-        const int per_cta = (npix + grid - 1) / grid;
-        const int p_begin = min(npix, (int)blockIdx.x * per_cta), p_end = min(npix, p_begin + per_cta);
+        UnitIter U{L.rows * L.cols, W, (int)blockIdx.x - 1, (int)lane, (int)warp};
+        const int passes = U.passes();
 
         for(int it = 0; it <= 10; it++)
         {
             // ---- CTA 0: digest the previous evaluation (:348-380), publish the next homography ----
             if(is_solver_cta)
             {
-                if(it > 0)
-                {
-                    cta_wait_arrivals(&ctl->arrive, arr * grid);
-                    cta0_final_reduce<16>(A.partials, s_red, s_final);
-                }
+                if(it > 0) gather_rows(A.rows, W, kSo3Chunks, arr, s_rows, s_red, s_final);
                 if(is_solver)
                 {
                     int done = 0;
                     if(it > 0) done = solve_so3(S, Z, s_final, it);
                     float payload[kPayload];
                     make_so3_payload(Z, payload, done, L.fx, L.fy, L.cx, L.cy, L.K_inv);
-                    publish_line(&ctl->line, payload, rel + 1);
+                    publish_line(ctl->line, payload, rel + 1);
                 }
             }
             ++rel;
-            wait_line(&ctl->line, rel, s_par);
+            wait_line(ctl->line, rel, s_par);
             const bool done = s_par[18] != 0.f;
             P.image_basis = mat_from(s_par);
             P.krlr = mat_from(s_par + 9);
             __syncthreads(); // s_par is rewritten by the next wait_line
             if(done) break;
+            ++arr;
+            if(is_solver_cta) continue;
 
-            // ---- so3Step over this CTA's pixels ----
+            // ---- workers: so3Step over this CTA's pixels ----
             float acc[16];
 #pragma unroll
             for(int i = 0; i < 16; i++) acc[i] = 0.f;
-            for(int k = p_begin + threadIdx.x; k < p_end; k += kThreads)
+            for(int p = 0; p < passes; p++)
             {
-                const int y = k / L.cols, x = k - y * L.cols;
-                float row[4];
-                if(so3_row(P, x, y, A.so3_last, A.so3_next, L.cols, row)) accumulate_so3(acc, row);
+                const int u = U.unit(p);
+                if(u >= 0)
+                {
+                    const int y = u / L.cols, x = u - y * L.cols;
+                    float row[4];
+                    if(so3_row(P, x, y, A.so3_last, A.so3_next, L.cols, row)) accumulate_so3(acc, row);
+                }
             }
             const float lane_value = warp_transpose_reduce16(acc);
             if(lane < 16) s_red[warp * 16 + lane] = lane_value;
@@ -470,10 +643,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_track(const TrackArgs A)
                 float s = 0.f;
 #pragma unroll
                 for(int w = 0; w < kWarps; w++) s += s_red[w * 16 + threadIdx.x];
-                my_row[threadIdx.x] = s;
+                s_final[threadIdx.x] = (threadIdx.x < 11) ? s : 0.f;
             }
-            cta_arrive(&ctl->arrive);
-            ++arr;
+            __syncthreads();
+            publish_row(my_row, s_final, kSo3Chunks, arr);
         }
         if(is_solver)
         {
@@ -496,15 +669,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_track(const TrackArgs A)
     IP.angle_thresh = A.angle_thresh;
 
     int it_global = 0;
-    bool pending = false; // an arrival round whose sums CTA 0 has not digested yet
+    bool pending = false; // a row round CTA 0 has not digested yet
     int pending_level = 0;
 
-    // CTA 0: wait for the outstanding arrival round, add the partial rows in CTA order, run the
-    // reference's host step (:541-583) in the solver thread
+    // CTA 0: collect the outstanding row round, add the rows in worker order, run the reference's host step
+    // (:541-583) in the solver thread
     auto solve_pending = [&]() {
-        cta_wait_arrivals(&ctl->arrive, arr * grid);
-        stamp(1);
-        cta0_final_reduce<64>(A.partials, s_red, s_final);
+        gather_rows(A.rows, W, kRowChunks, arr, s_rows, s_red, s_final);
         stamp(2);
         if(is_solver) solve_se3(S, s_final, ctl->last_S, A.icp, A.rgb, A.icp_weight, A.Rprev, A.tprev, pending_level);
         stamp(3);
@@ -528,16 +699,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_track(const TrackArgs A)
         SP.sobel_scale = A.sobel_scale;
         SP.sigma = 0.f;
         const int cols = L.cols;
-        const size_t plane = (size_t)L.rows * cols;
+        const int px = L.px;
+        const int upr = cols / px; // units per row
+        UnitIter U{upr * L.rows, W, (int)blockIdx.x - 1, (int)lane, (int)warp};
+        const int passes = U.passes();
 
         float lastRGBError = FLT_MAX;      // every thread tracks it for the uniform rgb_only break (:464)
         bool first_of_level = true;
-
-        // this CTA's contiguous run of 4-pixel groups
-        const int gpr = cols >> 2;
-        const int ngroups = gpr * L.rows;
-        const int per_cta = (ngroups + grid - 1) / grid;
-        const int g_begin = min(ngroups, (int)blockIdx.x * per_cta), g_end = min(ngroups, g_begin + per_cta);
 
         for(int j = 0; j < L.iterations; j++)
         {
@@ -553,165 +721,44 @@ __global__ void __launch_bounds__(kThreads, 1) k_track(const TrackArgs A)
                     if(first_of_level) S.last_rgb_error = FLT_MAX; // :420
                     float payload[kPayload];
                     make_se3_payload(S, payload, A.rgb, L.fx, L.fy, L.cx, L.cy, L.K_inv);
-                    publish_line(&ctl->line, payload, rel + 1);
+                    stamp(1);
+                    publish_line(ctl->line, payload, rel + 1);
                 }
             }
             pending = false;
             first_of_level = false;
             ++rel;
-            wait_line(&ctl->line, rel, s_par);
+            wait_line(ctl->line, rel, s_par);
             IP.Rcurr = mat_from(s_par);
             IP.tcurr = make_float3(s_par[9], s_par[10], s_par[11]);
-            RgbResParams RPi = RP;
-            RPi.krkinv = mat_from(s_par + 12);
-            RPi.kt = make_float3(s_par[21], s_par[22], s_par[23]);
+            RP.krkinv = mat_from(s_par + 12);
+            RP.kt = make_float3(s_par[21], s_par[22], s_par[23]);
             __syncthreads(); // s_par is rewritten by the next wait_line
             stamp(4);
 
-            float accI[32];
-#pragma unroll
-            for(int i = 0; i < 32; i++) accI[i] = 0.f;
-            int cnt = 0, sig = 0;
+            int rgbSize = 0, sigma = 0;
+            unsigned long long * word = &ctl->bar_b[cnt_slot];
 
-            // ---- phase A ----
-            int slot = 0;
-            for(int g = g_begin + threadIdx.x; g < g_end; g += kThreads, slot++)
+            // ---- workers, phase A1: photometric association -> records in shared memory, then the barrier-B arrival
+            //      (arrivals | count << 8 | sigma << 32 in one 64-bit word; integer adds are exact in any order and
+            //      sigma wraps mod 2^32 in the top bits exactly like the reference's int sum) ----
+            if(!is_solver_cta && A.rgb)
             {
-                const int y = g / gpr;
-                const int x0 = (g - y * gpr) << 2;
-                const size_t o = (size_t)y * cols + x0;
-
-                // stage 0: every load that does not depend on arithmetic
-                float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a, c = a, d = a, e = a, f = a;
-                if(A.icp)
+                int cnt = 0, sig = 0;
+                for(int p = 0; p < passes; p++)
                 {
-                    a = *reinterpret_cast<const float4 *>(L.vc + o);
-                    b = *reinterpret_cast<const float4 *>(L.vc + plane + o);
-                    c = *reinterpret_cast<const float4 *>(L.vc + 2 * plane + o);
-                    d = *reinterpret_cast<const float4 *>(L.nc + o);
-                    e = *reinterpret_cast<const float4 *>(L.nc + plane + o);
-                    f = *reinterpret_cast<const float4 *>(L.nc + 2 * plane + o);
-                }
-                // the 16-pixel border of RGBResidual (:779-783) excludes whole groups: x0 is a multiple of 4
-                const bool rgb_group = A.rgb && y >= 16 && y < L.rows - 16 && x0 >= 16 && x0 < cols - 16;
-                short4 gx4 = make_short4(0, 0, 0, 0), gy4 = make_short4(0, 0, 0, 0);
-                float4 d14 = make_float4(0.f, 0.f, 0.f, 0.f);
-                unsigned ni4 = 0;
-                unsigned m0 = 0, m1 = 0, m2 = 0;
-                if(rgb_group)
-                {
-                    gx4 = *reinterpret_cast<const short4 *>(L.dIdx + o);
-                    gy4 = *reinterpret_cast<const short4 *>(L.dIdy + o);
-                    d14 = *reinterpret_cast<const float4 *>(L.next_depth + o);
-                    // 4 rows x 12 bytes [x0-4, x0+8) of the next image: non-zero masks, ANDed over the rows (:787-793)
-                    m0 = m1 = m2 = 0xffffffffu;
-#pragma unroll
-                    for(int r = -2; r < 2; r++)
+                    const int u = U.unit(p);
+                    if(u >= 0)
                     {
-                        const unsigned * wp = reinterpret_cast<const unsigned *>(L.next_image + (size_t)(y + r) * cols + x0 - 4);
-                        const unsigned w0 = __ldg(wp), w1 = __ldg(wp + 1), w2 = __ldg(wp + 2);
-                        m0 &= __vcmpne4(w0, 0u);
-                        m1 &= __vcmpne4(w1, 0u);
-                        m2 &= __vcmpne4(w2, 0u);
-                        if(r == 0) ni4 = w1;
+                        const int y = u / upr, x0 = (u - y * upr) * px;
+                        if(px == 4) rgb_assoc_unit<4>(L, RP, y, x0, s_corr, p * 4, cnt, sig);
+                        else rgb_assoc_unit<1>(L, RP, y, x0, s_corr, p, cnt, sig);
+                    }
+                    else
+                    {
+                        for(int k = 0; k < px; k++) s_corr[(p * px + k) * kThreads + threadIdx.x] = make_int4(-1, 0, 0, 0);
                     }
                 }
-
-                // stage 1: projections
-                float3 vg[4];
-                int ux[4], uy[4];
-                bool in1[4] = {false, false, false, false};
-                const float vx[4] = {a.x, a.y, a.z, a.w}, vy[4] = {b.x, b.y, b.z, b.w}, vz[4] = {c.x, c.y, c.z, c.w};
-                const float nx[4] = {d.x, d.y, d.z, d.w}, ny[4] = {e.x, e.y, e.z, e.w}, nz[4] = {f.x, f.y, f.z, f.w};
-                if(A.icp)
-                {
-#pragma unroll
-                    for(int k = 0; k < 4; k++) in1[k] = icp_project(IP, make_float3(vx[k], vy[k], vz[k]), vg[k], ux[k], uy[k]);
-                }
-                const short gxs[4] = {gx4.x, gx4.y, gx4.z, gx4.w}, gys[4] = {gy4.x, gy4.y, gy4.z, gy4.w};
-                const float d1s[4] = {d14.x, d14.y, d14.z, d14.w};
-                int u0[4], v0[4];
-                float td1[4];
-                bool in2[4];
-#pragma unroll
-                for(int k = 0; k < 4; k++)
-                {
-                    in2[k] = rgb_group && rgb_gate(RPi, x0 + k, y, gxs[k], gys[k], d1s[k]) && window_ok(m0, m1, m2, k);
-                    if(in2[k]) in2[k] = rgb_warp(RPi, x0 + k, y, d1s[k], u0[k], v0[k], td1[k]);
-                }
-
-                // stage 2: gathers
-                float3 vp[4], np[4];
-#pragma unroll
-                for(int k = 0; k < 4; k++)
-                {
-                    if(in1[k])
-                    {
-                        const size_t q = (size_t)uy[k] * cols + ux[k];
-                        vp[k].x = __ldg(L.vp + q); vp[k].y = __ldg(L.vp + plane + q); vp[k].z = __ldg(L.vp + 2 * plane + q);
-                        np[k].x = __ldg(L.np + q); np[k].y = __ldg(L.np + plane + q); np[k].z = __ldg(L.np + 2 * plane + q);
-                    }
-                }
-                float d0s[4];
-                unsigned ls[4];
-#pragma unroll
-                for(int k = 0; k < 4; k++)
-                {
-                    if(in2[k])
-                    {
-                        const size_t q = (size_t)v0[k] * cols + u0[k];
-                        d0s[k] = __ldg(L.last_depth + q);
-                        ls[k] = __ldg(L.last_image + q);
-                    }
-                }
-
-                // stage 3: math
-#pragma unroll
-                for(int k = 0; k < 4; k++)
-                {
-                    float row[7];
-                    if(in1[k] && icp_finish(IP, vg[k], make_float3(nx[k], ny[k], nz[k]), vp[k], np[k], row)) accumulate_se3(accI, row);
-                }
-                if(A.rgb)
-                {
-#pragma unroll
-                    for(int k = 0; k < 4; k++)
-                    {
-                        const bool ok = in2[k] && rgb_accept(RPi, td1[k], d0s[k], (uint8_t)ls[k]);
-                        int4 rec;
-                        rec.x = -1;
-                        rec.y = rec.z = rec.w = 0;
-                        if(ok)
-                        {
-                            const float diff = static_cast<float>((ni4 >> (8 * k)) & 0xffu) - static_cast<float>(ls[k]); // reduce.cu:827
-                            rec.x = (u0[k] & 0xffff) | (v0[k] << 16);
-                            rec.y = __float_as_int(diff);
-                            rec.z = __float_as_int(d0s[k]);
-                            rec.w = ((int)gxs[k] & 0xffff) | ((int)gys[k] << 16);
-                            cnt += 1;
-                            sig += (int)(diff * diff); // reduce.cu:830
-                        }
-                        s_corr[(slot * 4 + k) * kThreads + threadIdx.x] = rec;
-                    }
-                }
-            }
-            stamp(5);
-
-            // ICP sums leave the registers before the photometric phase needs its own 29
-            {
-                float vi = 0.f;
-                if(A.icp) vi = warp_transpose_reduce32(accI);
-                s_red[warp * 64 + lane] = vi;
-            }
-            float accR[32];
-#pragma unroll
-            for(int i = 0; i < 32; i++) accR[i] = 0.f;
-
-            bool level_break = false;
-            if(A.rgb)
-            {
-                // ---- barrier B: arrivals | count << 8 | sigma << 32 in one 64-bit word.  Integer adds are exact in
-                //      any order; sigma wraps mod 2^32 in the top bits exactly like the reference's int sum ----
                 cnt = __reduce_add_sync(kFullMask, cnt);
                 sig = __reduce_add_sync(kFullMask, sig);
                 if(lane == 0) { s_wcnt[warp] = cnt; s_wsig[warp] = sig; }
@@ -721,18 +768,52 @@ __global__ void __launch_bounds__(kThreads, 1) k_track(const TrackArgs A)
                     unsigned c = 0, s = 0;
 #pragma unroll
                     for(int w = 0; w < kWarps; w++) { c += (unsigned)s_wcnt[w]; s += (unsigned)s_wsig[w]; }
-                    unsigned long long * word = &ctl->bar_b[cnt_slot];
                     atomicAdd(word, 1ull | ((unsigned long long)c << 8) | ((unsigned long long)s << 32));
+                }
+            }
+            stamp(5);
+
+            // ---- workers, phase A2: ICP association + 29 sums (hides the barrier-B latency and the inter-CTA skew) ----
+            float accI[32];
+#pragma unroll
+            for(int i = 0; i < 32; i++) accI[i] = 0.f;
+            if(!is_solver_cta && A.icp)
+            {
+                for(int p = 0; p < passes; p++)
+                {
+                    const int u = U.unit(p);
+                    if(u >= 0)
+                    {
+                        const int y = u / upr, x0 = (u - y * upr) * px;
+                        if(px == 4) icp_unit<4>(L, IP, y, x0, accI);
+                        else icp_unit<1>(L, IP, y, x0, accI);
+                    }
+                }
+            }
+            if(!is_solver_cta)
+            {
+                float vi = 0.f;
+                if(A.icp) vi = warp_transpose_reduce32(accI);
+                if(lane < 29) s_red[warp * 64 + lane] = vi;
+            }
+
+            // ---- barrier B: everybody (CTA 0 included, it needs the count for the statistics) reads the word ----
+            bool level_break = false;
+            if(A.rgb)
+            {
+                if(threadIdx.x == 0)
+                {
                     unsigned long long v;
                     do
                     {
                         v = ld_relaxed64(word);
-                    } while((unsigned)(v & 0xffull) < grid);
+                    } while((int)(v & 0xffull) < W);
                     s_cnt = (int)((v >> 8) & 0xffffffull);
                     s_sig = (int)(unsigned)(v >> 32);
                 }
                 __syncthreads();
-                const int rgbSize = s_cnt, sigma = s_sig;
+                rgbSize = s_cnt;
+                sigma = s_sig;
                 stamp(6);
 
                 // RGBDOdometry.cpp:461-475 (the precedence quirk of :461 is kept)
@@ -749,26 +830,6 @@ __global__ void __launch_bounds__(kThreads, 1) k_track(const TrackArgs A)
                     }
                     if(A.rgb_only) sigmaVal = -1;
                     SP.sigma = sigmaVal;
-
-                    // ---- phase B: photometric rows from the records in shared memory ----
-                    int sl = 0;
-                    for(int g = g_begin + threadIdx.x; g < g_end; g += kThreads, sl++)
-                    {
-#pragma unroll
-                        for(int k = 0; k < 4; k++)
-                        {
-                            const int4 rec = s_corr[(sl * 4 + k) * kThreads + threadIdx.x];
-                            if(rec.x != -1)
-                            {
-                                const int pu = rec.x & 0xffff, pv = rec.x >> 16;
-                                const float Z = __int_as_float(rec.z);
-                                const float3 cp = project_point(pu, pv, Z, SP.inv_fx, SP.inv_fy, SP.cx, SP.cy);
-                                float row[7];
-                                rgb_row(SP, __int_as_float(rec.y), cp.x, cp.y, cp.z, (short)(rec.w & 0xffff), (short)(rec.w >> 16), row);
-                                accumulate_se3(accR, row);
-                            }
-                        }
-                    }
                 }
             }
             else if(is_solver)
@@ -777,44 +838,63 @@ __global__ void __launch_bounds__(kThreads, 1) k_track(const TrackArgs A)
                 S.last_rgb_error = 0.f;
                 S.last_rgb_count = 0.f;
             }
-            if(level_break) break; // no arrival outstanding: every CTA takes the same branch
-            stamp(7);
+            if(level_break) break; // no row outstanding: every CTA takes the same branch
 
-            // ---- reduce; the sums are digested by CTA 0 at the top of the next iteration ----
-            {
-                float vr = 0.f;
-                if(A.rgb) vr = warp_transpose_reduce32(accR);
-                s_red[warp * 64 + 32 + lane] = vr;
-                __syncthreads();
-                if(threadIdx.x < 64)
-                {
-                    float sum = 0.f;
-#pragma unroll
-                    for(int w = 0; w < kWarps; w++) sum += s_red[w * 64 + threadIdx.x];
-                    my_row[threadIdx.x] = sum;
-                }
-            }
-            cta_arrive(&ctl->arrive);
-            stamp(8);
             ++arr;
             pending = true;
             pending_level = lv;
+            if(is_solver_cta) continue;
+
+            // ---- workers, phase B: photometric rows from the records in shared memory -> 29 more sums ----
+            float accR[32];
+#pragma unroll
+            for(int i = 0; i < 32; i++) accR[i] = 0.f;
+            if(A.rgb)
+            {
+                for(int p = 0; p < passes; p++)
+                {
+                    if(px == 4) rgb_rows_unit<4>(SP, s_corr, p * 4, accR);
+                    else rgb_rows_unit<1>(SP, s_corr, p, accR);
+                }
+            }
+            {
+                float vr = 0.f;
+                if(A.rgb) vr = warp_transpose_reduce32(accR);
+                if(lane < 29) s_red[warp * 64 + 29 + lane] = vr;
+                __syncthreads();
+                if(threadIdx.x < kRowFloats)
+                {
+                    float sum = 0.f;
+                    if(threadIdx.x < 58)
+                    {
+#pragma unroll
+                        for(int w = 0; w < kWarps; w++) sum += s_red[w * 64 + threadIdx.x];
+                    }
+                    s_final[threadIdx.x] = sum;
+                }
+                __syncthreads();
+                publish_row(my_row, s_final, kRowChunks, arr);
+            }
         }
     }
 
     // ============================================================================================
-    // epilogue: last solve, jump rejection (:587-591), outputs, leave the control block clean
+    // epilogue: last solve, jump rejection (:587-591), outputs, leave the barrier-B words clean
     // ============================================================================================
     if(!pending)
     {
-        // make sure every CTA has left its last wait before CTA 0 resets the control block
-        cta_arrive(&ctl->arrive);
+        // a row round without payload: tells CTA 0 that every worker is past its last barrier-B wait
         ++arr;
+        if(!is_solver_cta)
+        {
+            __syncthreads();
+            publish_row(my_row, s_final, kSo3Chunks, arr);
+        }
     }
     if(is_solver_cta)
     {
         if(pending) solve_pending();
-        else cta_wait_arrivals(&ctl->arrive, arr * grid);
+        else gather_rows(A.rows, W, kSo3Chunks, arr, s_rows, s_red, s_final);
     }
     if(is_solver)
     {
@@ -859,10 +939,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_track(const TrackArgs A)
         else
             out->status = 2; // no solve ran: lastA / lastb keep their previous values (host side)
         __threadfence_system();
-        // every other CTA has made its last arrival and waits on nothing more
-        ctl->arrive = 0;
-#pragma unroll
-        for(int s = 0; s < 4; s++) ctl->line.w[s * 8 + 7] = 0;
+        // every worker has published its last row and touches the control block no more
         for(int i = 0; i < kMaxIters; i++) ctl->bar_b[i] = 0ull;
     }
 }
@@ -873,11 +950,12 @@ struct DeviceTrack
     double dbg_acc[kMaxIters][kDbgStamps];
     long long dbg_n;
     TrackCtl * ctl;
-    float * partials;
+    uint4 * rows;
     TrackOutput * out; // pinned
     int grid;
-    int corr_slots;
+    int px[kNumPyrs];
     size_t smem_bytes;
+    unsigned launch_seq;
 };
 
 } // namespace
@@ -887,15 +965,28 @@ int device_track_init(ef_tracker * t)
     DeviceTrack * d = new DeviceTrack();
     memset(d, 0, sizeof(*d));
     t->track_state = d;
-    d->grid = t->num_sms < kMaxGrid ? t->num_sms : kMaxGrid;
-    const int groups0 = (t->width / 4) * t->height;
-    const int per_cta = (groups0 + d->grid - 1) / d->grid;
-    d->corr_slots = (per_cta + kThreads - 1) / kThreads * 4;
-    d->smem_bytes = (size_t)d->corr_slots * kThreads * sizeof(int4);
+    d->grid = t->num_sms < 255 ? t->num_sms : 255; // arrivals live in 8 bits of the barrier-B word
+    const int W = d->grid - 1;
+    // pixels per thread unit and passes per level -> shared-memory records per thread
+    int max_records = 1;
+    for(int i = 0; i < kNumPyrs; i++)
+    {
+        const int npix = t->dims[i].rows * t->dims[i].cols;
+        const int px = ((npix + W - 1) / W > kThreads && (t->dims[i].cols % 4) == 0) ? 4 : 1;
+        d->px[i] = px;
+        const int chunks = (npix / px + 31) / 32;
+        const int per_worker = (chunks + W - 1) / W;
+        const int passes = (per_worker + kWarps - 1) / kWarps;
+        if(passes * px > max_records) max_records = passes * px;
+    }
+    d->smem_bytes = (size_t)max_records * kThreads * sizeof(int4);
+    const size_t rows_smem = (size_t)W * kRowFloats * sizeof(float);
+    if(rows_smem > d->smem_bytes) d->smem_bytes = rows_smem;
+    d->launch_seq = 0;
     cudaError_t e = cudaMalloc((void **)&d->ctl, sizeof(TrackCtl));
     if(e == cudaSuccess) e = cudaMemsetAsync(d->ctl, 0, sizeof(TrackCtl), t->stream);
-    if(e == cudaSuccess) e = cudaMalloc((void **)&d->partials, (size_t)d->grid * 64 * sizeof(float));
-    if(e == cudaSuccess) e = cudaMemsetAsync(d->partials, 0, (size_t)d->grid * 64 * sizeof(float), t->stream);
+    if(e == cudaSuccess) e = cudaMalloc((void **)&d->rows, (size_t)d->grid * kRowChunks * sizeof(uint4));
+    if(e == cudaSuccess) e = cudaMemsetAsync(d->rows, 0, (size_t)d->grid * kRowChunks * sizeof(uint4), t->stream);
     if(e == cudaSuccess) e = cudaHostAlloc((void **)&d->out, sizeof(TrackOutput), cudaHostAllocMapped);
     const char * env = getenv("EF_TRACK_TIMING");
     if(e == cudaSuccess && env && env[0] == '1')
@@ -924,23 +1015,22 @@ void device_track_destroy(ef_tracker * t)
         {
             // stamps (cycles of CTA 0's SM): 0 loop top | 1 arrivals seen | 2 final reduce | 3 solve | 4 params published
             // + loaded | 5 phase A | 6 barrier B | 7 phase B | 8 reduce + arrive
-            fprintf(stderr, "[ef_track timing] avg cycles per SE3 iteration over %lld calls (wait reduce solve publish | phaseA barB phaseB arrive | total)\n",
-                    d->dbg_n);
+            fprintf(stderr, "[ef_track timing] avg cycles of CTA 0 per SE3 iteration over %lld calls\n", d->dbg_n);
             for(int it = 0; it < kMaxIters; it++)
             {
                 const double * a = d->dbg_acc[it];
                 if(a[4] == 0) continue;
                 const double n = (double)d->dbg_n;
-                const bool first = a[1] == 0;
-                fprintf(stderr, "  it %2d: %7.0f %7.0f %7.0f %7.0f | %7.0f %7.0f %7.0f %7.0f | %8.0f\n", it, first ? 0.0 : (a[1] - a[0]) / n,
-                        first ? 0.0 : (a[2] - a[1]) / n, first ? 0.0 : (a[3] - a[2]) / n, (a[4] - (first ? a[0] : a[3])) / n, (a[5] - a[4]) / n,
-                        (a[6] - a[5]) / n, (a[7] - a[6]) / n, (a[8] - a[7]) / n, (a[8] - a[0]) / n);
+                const bool first = a[2] == 0;
+                fprintf(stderr, "  it %2d: gather %7.0f solve %7.0f payload %7.0f publish+detect %7.0f | to-barB-seen %7.0f | total %8.0f\n", it,
+                        first ? 0.0 : (a[2] - a[0]) / n, first ? 0.0 : (a[3] - a[2]) / n, (a[1] - (first ? a[0] : a[3])) / n, (a[4] - a[1]) / n,
+                        (a[6] - a[4]) / n, (a[6] - a[0]) / n);
             }
         }
         cudaFree(d->dbg);
     }
     if(d->ctl) cudaFree(d->ctl);
-    if(d->partials) cudaFree(d->partials);
+    if(d->rows) cudaFree(d->rows);
     if(d->out) cudaFreeHost(d->out);
     delete d;
     t->track_state = nullptr;
@@ -950,7 +1040,7 @@ int device_track_launch(ef_tracker * t, const float * trans, const float * rot, 
 {
     DeviceTrack * d = static_cast<DeviceTrack *>(t->track_state);
     if(!d) return EF_ERR_BAD_STATE;
-    if(d->smem_bytes > 200 * 1024 || (size_t)t->width * t->height >= (1u << 24))
+    if(d->smem_bytes > 200 * 1024 || (size_t)t->width * t->height >= (1u << 24) || t->width >= 32768 || t->height >= 32768)
     {
         t->err = "image too large for the shared-memory correspondence store of EF_SOLVE_DEVICE";
         return EF_ERR_UNSUPPORTED;
@@ -971,6 +1061,7 @@ int device_track_launch(ef_tracker * t, const float * trans, const float * rot, 
         L.inv_fx = 1.0f / L.fx; L.inv_fy = 1.0f / L.fy;
         L.min_scale = (float)(pow(t->min_grad[i], 2.0) / pow(t->sobel_scale, 2.0)); // :442
         L.iterations = iterations[i];
+        L.px = d->px[i];
         const double K[9] = {L.fx, 0, L.cx, 0, L.fy, L.cy, 0, 0, 1};
         hm::inverse33(K, L.K_inv);
     }
@@ -989,8 +1080,18 @@ int device_track_launch(ef_tracker * t, const float * trans, const float * rot, 
     A.prev_icp_error = t->st.last_icp_error; A.prev_icp_count = t->st.last_icp_count;
     A.prev_so3_error = t->st.last_so3_error; A.prev_so3_count = t->st.last_so3_count;
     A.prev_rgb_error = t->st.last_rgb_error; A.prev_rgb_count = t->st.last_rgb_count;
+    // launch-unique flag epochs: nothing in the control block or the rows needs resetting between launches.  After
+    // 2^24 launches the sequence wraps; stale flags are wiped then.
+    d->launch_seq++;
+    if((d->launch_seq & 0xffffffu) == 0)
+    {
+        d->launch_seq = 1;
+        cudaMemsetAsync(d->rows, 0, (size_t)d->grid * kRowChunks * sizeof(uint4), t->stream);
+        cudaMemsetAsync(d->ctl, 0, sizeof(TrackCtl), t->stream);
+    }
+    A.epoch_base = d->launch_seq << 8;
     A.ctl = d->ctl;
-    A.partials = d->partials;
+    A.rows = d->rows;
     A.out = d->out; // UVA: pinned + mapped host memory is addressable from the device
     A.dbg = d->dbg;
 
