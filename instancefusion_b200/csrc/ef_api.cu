@@ -283,6 +283,19 @@ EF_API int ef_init_icp_depth(ef_tracker * t, const uint16_t * d_depth, size_t pi
 {
     if(!t || !d_depth) return EF_ERR_INVALID_ARGUMENT;
     cudaStream_t s = t->stream;
+    if(t->fused_build)
+    {
+        // one launch per level: vertex map + normal map (+ dense copy of level 0) + bilateral pyrDown to the next level
+        for(int i = 0; i < kNumPyrs; ++i)
+        {
+            float fx, fy, cx, cy;
+            level_intr(t, i, fx, fy, cx, cy);
+            EF_LAUNCH(t, launch_depth_level(i == 0 ? d_depth : t->depth_tmp[i], i == 0 ? pitch_bytes : 0, t->dims[i].rows, t->dims[i].cols, fx, fy, cx,
+                                            cy, depth_cutoff, t->vmap_curr[i], t->nmap_curr[i], i == 0 ? t->depth_tmp[0] : nullptr,
+                                            i + 1 < kNumPyrs ? t->depth_tmp[i + 1] : nullptr, s));
+        }
+        return EF_OK;
+    }
     // level 0 is read in place from the caller's buffer (the reference copies the texture into depth_tmp[0])
     const size_t p0 = pitch_bytes ? pitch_bytes : (size_t)t->width * 2;
     const uint16_t * src = d_depth;
@@ -307,9 +320,14 @@ EF_API int ef_init_icp_depth(ef_tracker * t, const uint16_t * d_depth, size_t pi
     return EF_OK;
 }
 
-static int build_maps(ef_tracker * t, const float * d_v, const float * d_n, float ** vmaps, float ** nmaps)
+static int build_maps(ef_tracker * t, const float * d_v, const float * d_n, float ** vmaps, float ** nmaps, const float * R, const float * tv)
 {
     cudaStream_t s = t->stream;
+    if(t->fused_build)
+    {
+        EF_LAUNCH(t, launch_build_maps(d_v, d_n, t->height, t->width, vmaps, nmaps, t->tmp_z, R, tv, s));
+        return EF_OK;
+    }
     // stands for the copy into vmaps_tmp (RGBDOdometry.cpp:150/178): only the z channel is ever read again (:212)
     EF_LAUNCH(t, launch_extract_z(d_v, (int)t->dims[0].n(), t->tmp_z, s));
     EF_LAUNCH(t, launch_copy_maps(d_v, d_n, t->height, t->width, vmaps[0], nmaps[0], 0, s));
@@ -318,6 +336,9 @@ static int build_maps(ef_tracker * t, const float * d_v, const float * d_n, floa
         EF_LAUNCH(t, launch_resize_map(vmaps[i - 1], 0, t->dims[i - 1].rows, t->dims[i - 1].cols, vmaps[i], 0, 0, s));
         EF_LAUNCH(t, launch_resize_map(nmaps[i - 1], 0, t->dims[i - 1].rows, t->dims[i - 1].cols, nmaps[i], 0, 1, s));
     }
+    if(R)
+        for(int i = 0; i < kNumPyrs; ++i)
+            EF_LAUNCH(t, launch_transform_maps(vmaps[i], nmaps[i], 0, t->dims[i].rows, t->dims[i].cols, R, tv, vmaps[i], nmaps[i], 0, s));
     return EF_OK;
 }
 
@@ -326,7 +347,7 @@ EF_API int ef_init_icp_maps(ef_tracker * t, const float * d_v, const float * d_n
 {
     (void)depth_cutoff; // unused by the reference as well
     if(!t || !d_v || !d_n) return EF_ERR_INVALID_ARGUMENT;
-    return build_maps(t, d_v, d_n, t->vmap_curr, t->nmap_curr);
+    return build_maps(t, d_v, d_n, t->vmap_curr, t->nmap_curr, nullptr, nullptr);
 }
 
 // RGBDOdometry.cpp:169-206
@@ -334,20 +355,21 @@ EF_API int ef_init_icp_model(ef_tracker * t, const float * d_v, const float * d_
 {
     (void)depth_cutoff;
     if(!t || !d_v || !d_n || !pose) return EF_ERR_INVALID_ARGUMENT;
-    const int rc = build_maps(t, d_v, d_n, t->vmap_g_prev, t->nmap_g_prev);
-    if(rc != EF_OK) return rc;
     const float R[9] = {pose[0], pose[1], pose[2], pose[4], pose[5], pose[6], pose[8], pose[9], pose[10]};
     const float tv[3] = {pose[3], pose[7], pose[11]};
-    for(int i = 0; i < kNumPyrs; ++i)
-        EF_LAUNCH(t, launch_transform_maps(t->vmap_g_prev[i], t->nmap_g_prev[i], 0, t->dims[i].rows, t->dims[i].cols, R, tv, t->vmap_g_prev[i],
-                                           t->nmap_g_prev[i], 0, t->stream));
-    return EF_OK;
+    return build_maps(t, d_v, d_n, t->vmap_g_prev, t->nmap_g_prev, R, tv);
 }
 
 // RGBDOdometry.cpp:208-235
 static int populate_rgbd(ef_tracker * t, const uint8_t * d_rgba, size_t pitch, float ** depths, uint8_t ** images)
 {
     cudaStream_t s = t->stream;
+    if(t->fused_build)
+    {
+        EF_LAUNCH(t, launch_rgbd_level0(d_rgba, pitch, t->tmp_z, t->max_depth_rgb, t->height, t->width, images[0], depths[0], images[1], depths[1], s));
+        EF_LAUNCH(t, launch_rgbd_level1(images[1], depths[1], t->dims[1].rows, t->dims[1].cols, images[2], depths[2], s));
+        return EF_OK;
+    }
     EF_LAUNCH(t, launch_z_to_depth(t->tmp_z, t->height, t->width, t->max_depth_rgb, depths[0], 0, s));
     for(int i = 0; i + 1 < kNumPyrs; i++)
         EF_LAUNCH(t, launch_pyr_down_gauss_f32(depths[i], 0, t->dims[i].rows, t->dims[i].cols, depths[i + 1], 0, s));
@@ -375,6 +397,12 @@ EF_API int ef_init_first_rgb(ef_tracker * t, const uint8_t * d_rgba, size_t pitc
 {
     if(!t || !d_rgba) return EF_ERR_INVALID_ARGUMENT;
     cudaStream_t s = t->stream;
+    if(t->fused_build)
+    {
+        EF_LAUNCH(t, launch_rgbd_level0(d_rgba, pitch, nullptr, 0.f, t->height, t->width, t->last_next_image[0], nullptr, t->last_next_image[1], nullptr, s));
+        EF_LAUNCH(t, launch_rgbd_level1(t->last_next_image[1], nullptr, t->dims[1].rows, t->dims[1].cols, t->last_next_image[2], nullptr, s));
+        return EF_OK;
+    }
     EF_LAUNCH(t, launch_bgr_to_intensity(d_rgba, pitch, t->height, t->width, t->last_next_image[0], 0, s));
     for(int i = 0; i + 1 < kNumPyrs; i++)
         EF_LAUNCH(t, launch_pyr_down_gauss_u8(t->last_next_image[i], 0, t->dims[i].rows, t->dims[i].cols, t->last_next_image[i + 1], 0, s));
@@ -499,6 +527,14 @@ static int fetch_result(ef_tracker * t, int nfloats)
 
 static int compute_derivatives(ef_tracker * t)
 {
+    if(t->fused_build)
+    {
+        int rows[3], cols[3];
+        for(int i = 0; i < kNumPyrs; i++) { rows[i] = t->dims[i].rows; cols[i] = t->dims[i].cols; }
+        EF_LAUNCH(t, launch_derivatives3(t->next_image, t->dIdx, t->dIdy, rows, cols, t->stream));
+        t->deriv_valid = true;
+        return EF_OK;
+    }
     for(int i = 0; i < kNumPyrs; i++) // RGBDOdometry.cpp:284-290
         EF_LAUNCH(t, launch_derivative_images(t->next_image[i], 0, t->dims[i].rows, t->dims[i].cols, t->dIdx[i], t->dIdy[i], 0, t->stream));
     t->deriv_valid = true;

@@ -27,6 +27,20 @@ cudaError_t launch_derivative_images(const uint8_t * src, size_t sp, int rows, i
 cudaError_t launch_project_points(const float * depth, size_t dp, int rows, int cols, float fx, float fy, float cx, float cy, float * cloud,
                                   size_t cp, cudaStream_t s);
 
+// ---- fused pyramid builders (ef_build_fused.cu); dense outputs ----
+// R == nullptr: no transform (initICP maps overload); else v' = R v + t, n' = R n at every level (initICPModel)
+cudaError_t launch_build_maps(const float * v4, const float * n4, int rows, int cols, float * const vmaps[3], float * const nmaps[3], float * tmp_z,
+                              const float * R, const float * t, cudaStream_t s);
+// vertex + normal map of one level (+ dense copy of the level's depth, + pyrDown into next_depth; either may be null)
+cudaError_t launch_depth_level(const uint16_t * depth, size_t dpitch_bytes, int rows, int cols, float fx, float fy, float cx, float cy, float cutoff,
+                               float * vmap, float * nmap, uint16_t * depth_copy, uint16_t * next_depth, cudaStream_t s);
+// intensity (+ float depth from the kept z channel when depth0 != null) at level 0 and their Gaussian pyrDowns to level 1
+cudaError_t launch_rgbd_level0(const uint8_t * rgba, size_t pitch_bytes, const float * tmp_z, float cutoff, int rows, int cols, uint8_t * img0,
+                               float * depth0, uint8_t * img1, float * depth1, cudaStream_t s);
+cudaError_t launch_rgbd_level1(const uint8_t * img1, const float * depth1, int rows1, int cols1, uint8_t * img2, float * depth2, cudaStream_t s);
+cudaError_t launch_derivatives3(const uint8_t * const img[3], int16_t * const dx[3], int16_t * const dy[3], const int rows[3], const int cols[3],
+                                cudaStream_t s);
+
 // ---- Tier-2 association + reduction operators (ef_ops_reduce.cu) ----
 // Scratch block layout (device): [0] ticket (u32) | [128] result (32 floats / 2 ints) | [256] partial rows
 constexpr size_t kScratchTicketOff = 0;

@@ -4,7 +4,7 @@
 // These are the per-operator drop-ins (and the building blocks of the non-fused tracker path);
 // the fused pyramid builders used by the fast path live in ef_build_fused.cu.
 #include "ef_kernels.h"
-#include "ef_math.cuh"
+#include "ef_image_px.cuh"
 
 namespace ef
 {
@@ -32,31 +32,7 @@ __global__ void k_pyr_down_u16(const uint16_t * __restrict__ src, size_t sp, int
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y * blockDim.y + threadIdx.y;
     if(x >= dcols || y >= drows) return;
-
-    const int D = 5;
-    const float sigma_color = 30.f; // :103
-    const int center = rowp(src, sp, 2 * y)[2 * x];
-
-    const int x_mi = max(0, 2 * x - D / 2) - 2 * x;
-    const int y_mi = max(0, 2 * y - D / 2) - 2 * y;
-    const int x_ma = min(scols, 2 * x - D / 2 + D) - 2 * x;
-    const int y_ma = min(srows, 2 * y - D / 2 + D) - 2 * y;
-
-    float sum = 0;
-    float wall = 0;
-    const float weights[] = {0.375f, 0.25f, 0.0625f};
-
-    for(int yi = y_mi; yi < y_ma; ++yi)
-        for(int xi = x_mi; xi < x_ma; ++xi)
-        {
-            const int val = __ldg(rowp(src, sp, 2 * y + yi) + 2 * x + xi);
-            if(abs(val - center) < 3 * sigma_color)
-            {
-                sum += val * weights[abs(xi)] * weights[abs(yi)];
-                wall += weights[abs(xi)] * weights[abs(yi)];
-            }
-        }
-    rowp(dst, dp, y)[x] = static_cast<int>(sum / wall);
+    rowp(dst, dp, y)[x] = pyr_down_u16_px(src, (int)(sp / 2), srows, scols, x, y);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -69,14 +45,12 @@ __global__ void k_create_vmap(const uint16_t * __restrict__ depth, size_t dp, in
     const int v = threadIdx.y + blockIdx.y * blockDim.y;
     if(u < cols && v < rows)
     {
-        const float z = rowp(depth, dp, v)[u] / 1000.f;
-        if(z != 0 && z < cutoff)
+        float3 vtx;
+        if(vertex_px(rowp(depth, dp, v)[u], u, v, fx_inv, fy_inv, cx, cy, cutoff, vtx))
         {
-            const float vx = z * (u - cx) * fx_inv;
-            const float vy = z * (v - cy) * fy_inv;
-            rowp(vmap, vp, v)[u] = vx;
-            rowp(vmap, vp, v + rows)[u] = vy;
-            rowp(vmap, vp, v + rows * 2)[u] = z;
+            rowp(vmap, vp, v)[u] = vtx.x;
+            rowp(vmap, vp, v + rows)[u] = vtx.y;
+            rowp(vmap, vp, v + rows * 2)[u] = vtx.z;
         }
         else
             rowp(vmap, vp, v)[u] = qnan(); // x plane only (:130)
@@ -112,7 +86,7 @@ __global__ void k_create_nmap(int rows, int cols, const float * __restrict__ vma
         v01.z = rowp(vmap, vp, v + 2 * rows)[u + 1];
         v10.z = rowp(vmap, vp, v + 1 + 2 * rows)[u];
 
-        const float3 r = normalized3(cross3(v01 - v00, v10 - v00));
+        const float3 r = normal_px(v00, v01, v10);
         rowp(nmap, np, v)[u] = r.x;
         rowp(nmap, np, v + rows)[u] = r.y;
         rowp(nmap, np, v + 2 * rows)[u] = r.z;
@@ -226,7 +200,7 @@ __global__ void k_vertices_to_depth(const float * __restrict__ vsrc, int rows, i
     const int y = blockIdx.y * blockDim.y + threadIdx.y;
     if(x >= cols || y >= rows) return;
     const float z = __ldg(vsrc + ((size_t)y * cols + x) * 4 + 2);
-    rowp(dst, dp, y)[x] = (z > cutoff || z <= 0) ? qnan() : z;
+    rowp(dst, dp, y)[x] = depth_from_z(z, cutoff);
 }
 
 // same predicate on a compact z image (the handle keeps only the z channel of vmaps_tmp)
@@ -236,7 +210,7 @@ __global__ void k_z_to_depth(const float * __restrict__ zsrc, int rows, int cols
     const int y = blockIdx.y * blockDim.y + threadIdx.y;
     if(x >= cols || y >= rows) return;
     const float z = __ldg(zsrc + (size_t)y * cols + x);
-    rowp(dst, dp, y)[x] = (z > cutoff || z <= 0) ? qnan() : z;
+    rowp(dst, dp, y)[x] = depth_from_z(z, cutoff);
 }
 
 __global__ void k_extract_z(const float4 * __restrict__ vsrc, int n, float * __restrict__ z)
@@ -248,39 +222,13 @@ __global__ void k_extract_z(const float4 * __restrict__ vsrc, int n, float * __r
 // ---------------------------------------------------------------------------------------------
 // pyrDownKernelGaussF  cudafuncs.cu:332-363 ; binomial taps as constants instead of a malloc'd table
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ float gauss5(int i)
-{
-    // {1,4,6,4,1} (x) {1,4,6,4,1}, i = r*5 + c   (cudafuncs.cu:453-457)
-    const float k1[5] = {1.f, 4.f, 6.f, 4.f, 1.f};
-    return k1[i / 5] * k1[i % 5];
-}
-
 __global__ void k_pyr_down_gauss_f32(const float * __restrict__ src, size_t sp, int srows, int scols, float * __restrict__ dst, size_t dp,
                                      int drows, int dcols)
 {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y * blockDim.y + threadIdx.y;
     if(x >= dcols || y >= drows) return;
-
-    const int D = 5;
-    const int tx = min(2 * x - D / 2 + D, scols - 1);
-    const int ty = min(2 * y - D / 2 + D, srows - 1);
-    int cy = max(0, 2 * y - D / 2);
-
-    float sum = 0;
-    int count = 0;
-    for(; cy < ty; ++cy)
-        for(int cx = max(0, 2 * x - D / 2); cx < tx; ++cx)
-        {
-            const float s = __ldg(rowp(src, sp, cy) + cx);
-            if(!isnan(s))
-            {
-                const float k = gauss5((ty - cy - 1) * 5 + (tx - cx - 1));
-                sum += s * k;
-                count += k;
-            }
-        }
-    rowp(dst, dp, y)[x] = (float)(sum / (float)count);
+    rowp(dst, dp, y)[x] = pyr_down_gauss_f32_px([&](int cy, int cx) { return __ldg(rowp(src, sp, cy) + cx); }, srows, scols, x, y);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -292,26 +240,7 @@ __global__ void k_pyr_down_gauss_u8(const uint8_t * __restrict__ src, size_t sp,
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y * blockDim.y + threadIdx.y;
     if(x >= dcols || y >= drows) return;
-
-    const int D = 5;
-    const int tx = min(2 * x - D / 2 + D, scols - 1);
-    const int ty = min(2 * y - D / 2 + D, srows - 1);
-    int cy = max(0, 2 * y - D / 2);
-
-    float sum = 0;
-    int count = 0;
-    for(; cy < ty; ++cy)
-        for(int cx = max(0, 2 * x - D / 2); cx < tx; ++cx)
-        {
-            const uint8_t s = __ldg(rowp(src, sp, cy) + cx);
-            if(s > 0)
-            {
-                const float k = gauss5((ty - cy - 1) * 5 + (tx - cx - 1));
-                sum += s * k;
-                count += k;
-            }
-        }
-    rowp(dst, dp, y)[x] = (sum / (float)count);
+    rowp(dst, dp, y)[x] = pyr_down_gauss_u8_px([&](int cy, int cx) { return __ldg(rowp(src, sp, cy) + cx); }, srows, scols, x, y);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -322,45 +251,22 @@ __global__ void k_bgr_to_intensity(const uint8_t * __restrict__ src, size_t sp, 
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y * blockDim.y + threadIdx.y;
     if(x >= cols || y >= rows) return;
-    const uchar4 s = __ldg(reinterpret_cast<const uchar4 *>(rowp(src, sp, y)) + x);
-    const int value = (float)s.x * 0.114f + (float)s.y * 0.299f + (float)s.z * 0.587f;
-    rowp(dst, dp, y)[x] = value;
+    rowp(dst, dp, y)[x] = intensity_px(__ldg(reinterpret_cast<const uchar4 *>(rowp(src, sp, y)) + x));
 }
 
 // ---------------------------------------------------------------------------------------------
-// applyKernel  cudafuncs.cu:583-607 ; taps as literals (:615-621), zero taps skipped (adding +-0 is exact)
+// applyKernel  cudafuncs.cu:583-607 ; taps as literals (:615-621)
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ float sobel_x_tap(int k)
-{
-    const float t[9] = {0.52201f, 0.00000f, -0.52201f, 0.79451f, -0.00000f, -0.79451f, 0.52201f, 0.00000f, -0.52201f};
-    return t[k];
-}
-__device__ __forceinline__ float sobel_y_tap(int k)
-{
-    const float t[9] = {0.52201f, 0.79451f, 0.52201f, 0.00000f, 0.00000f, 0.00000f, -0.52201f, -0.79451f, -0.52201f};
-    return t[k];
-}
-
 __global__ void k_derivative_images(const uint8_t * __restrict__ src, size_t sp, int rows, int cols, int16_t * __restrict__ dx,
                                     int16_t * __restrict__ dy, size_t dp)
 {
     const int x = threadIdx.x + blockIdx.x * blockDim.x;
     const int y = threadIdx.y + blockIdx.y * blockDim.y;
     if(x >= cols || y >= rows) return;
-
-    float dxVal = 0;
-    float dyVal = 0;
-    int kernelIndex = 8; // counts down over VISITED taps (:594-603)
-    for(int j = max(y - 1, 0); j <= min(y + 1, rows - 1); j++)
-        for(int i = max(x - 1, 0); i <= min(x + 1, cols - 1); i++)
-        {
-            const float s = (float)__ldg(rowp(src, sp, j) + i);
-            dxVal += s * sobel_x_tap(kernelIndex);
-            dyVal += s * sobel_y_tap(kernelIndex);
-            --kernelIndex;
-        }
-    rowp(dx, dp, y)[x] = dxVal;
-    rowp(dy, dp, y)[x] = dyVal;
+    short gx, gy;
+    derivative_px([&](int j, int i) { return __ldg(rowp(src, sp, j) + i); }, rows, cols, x, y, gx, gy);
+    rowp(dx, dp, y)[x] = gx;
+    rowp(dy, dp, y)[x] = gy;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -206,3 +206,42 @@ def test_large_jump_is_rejected():
     finally:
         prod.close()
         ref.close()
+
+
+def test_fused_and_per_operator_builders_agree():
+    """EF_OPT_FUSED_BUILD on/off: identical pyramids (bit for bit where the reference defines the value) and poses."""
+    w, h = 640, 480
+    K, pose0, pose1, f0, f1 = util.frame_pair(w, h)
+    f1 = dict(f1, depth=util.punch_holes(f1["depth"]))
+    v4, n4 = util.holes_in_maps(f0["vmap"], f0["nmap"])
+    f0 = dict(f0, vmap=v4, nmap=n4)
+    pose0f = pose0.astype(np.float32)
+    a = ef.RGBDOdometry(w, h, K.cx, K.cy, K.fx, K.fy)
+    b = ef.RGBDOdometry(w, h, K.cx, K.cy, K.fx, K.fy)
+    b.set_option(RO.EF_OPT_FUSED_BUILD, 0)
+    try:
+        for tr in (a, b):
+            _feed(tr, pose0f, f0, f1)
+        for lvl in range(3):
+            rows = h >> lvl
+            for name in ("depth_tmp", "last_image", "next_image", "last_next_image"):
+                assert np.array_equal(a.buffer(name, lvl), b.buffer(name, lvl)), (name, lvl)
+            for name in ("vmap_curr", "nmap_curr", "vmap_g_prev", "nmap_g_prev"):
+                assert util.masked_map_compare(a.buffer(name, lvl), b.buffer(name, lvl), rows) == 0, (name, lvl)
+            for name in ("last_depth", "next_depth"):
+                assert np.array_equal(a.buffer(name, lvl), b.buffer(name, lvl), equal_nan=True), (name, lvl)
+        m = MODES["joint_so3"]
+        ra = a.getIncrementalTransformation(pose0f[:3, 3], pose0f[:3, :3], **m)
+        rb = b.getIncrementalTransformation(pose0f[:3, 3], pose0f[:3, :3], **m)
+        assert np.array_equal(ra[0], rb[0]) and np.array_equal(ra[1], rb[1])
+        for lvl in range(3):
+            assert np.array_equal(a.buffer("dIdx", lvl), b.buffer("dIdx", lvl)) and np.array_equal(a.buffer("dIdy", lvl), b.buffer("dIdy", lvl))
+        # the maps overload (modelToModel / Ferns) through the fused builder
+        a.initICP(f1["vmap"], f1["nmap"], 20.0)
+        b.initICP(f1["vmap"], f1["nmap"], 20.0)
+        for lvl in range(3):
+            for name in ("vmap_curr", "nmap_curr"):
+                assert util.masked_map_compare(a.buffer(name, lvl), b.buffer(name, lvl), h >> lvl) == 0, (name, lvl)
+    finally:
+        a.close()
+        b.close()
