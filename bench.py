@@ -178,12 +178,9 @@ def run_ours(args, rank, world, device):
 
     def step_resident(i):
         k = 1 + (i % (F - 1))
-        p = posef[k - 1]
-        tr.initICPModel(vmap[k - 1], nmap[k - 1], 20.0, p)
-        tr.initRGBModel(rgba[k - 1])
-        tr.initICP(depth[k], 20.0)
-        tr.initRGB(rgba[k])
-        return tr.getIncrementalTransformation(p[:3, 3], p[:3, :3], False, args.icp_weight, True, False, so3), k
+        # = initICPModel, initRGBModel, initICP, initRGB, getIncrementalTransformation (ef_track_frame_to_model)
+        return tr.trackFrameToModel(vmap[k - 1], nmap[k - 1], rgba[k - 1], depth[k], rgba[k], 20.0, posef[k - 1], False, args.icp_weight,
+                                    True, False, so3), k
 
     if so3:
         tr.initFirstRGB(rgba[0])
@@ -237,16 +234,8 @@ def run_ours(args, rank, world, device):
 
         def submit(trk, i):
             k = 1 + (i % (FE - 1))
-            p = posef[k - 1]
-            pp = np.ascontiguousarray(p.reshape(16))
-            h = trk._h
-            rc = L.ef_init_icp_model_host(h, C.c_void_p(h_vmap[k - 1].data_ptr()), C.c_void_p(h_nmap[k - 1].data_ptr()), C.c_float(20.0),
-                                          pp.ctypes.data_as(C.c_void_p))
-            rc |= L.ef_init_rgb_model_host(h, C.c_void_p(h_rgba[k - 1].data_ptr()))
-            rc |= L.ef_init_icp_depth_host(h, C.c_void_p(h_depth[k].data_ptr()), C.c_float(20.0))
-            rc |= L.ef_init_rgb_host(h, C.c_void_p(h_rgba[k].data_ptr()))
-            assert rc == 0, trk._L.ef_last_error(h)
-            trk.launch(p[:3, 3], p[:3, :3], False, args.icp_weight, True, False, so3)
+            trk.trackFrameToModelLaunch(h_vmap[k - 1], h_nmap[k - 1], h_rgba[k - 1], h_depth[k], h_rgba[k], 20.0, posef[k - 1], False,
+                                        args.icp_weight, True, False, so3)
 
         if so3:
             trs[1].initFirstRGB(rgba[0])

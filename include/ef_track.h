@@ -138,6 +138,27 @@ int ef_get_incremental_transformation_launch(ef_tracker * t, const float * trans
                                              float icp_weight, int pyramid, int fast_odom, int so3);
 int ef_get_incremental_transformation_finish(ef_tracker * t, float * trans3, float * rot9, ef_track_stats * stats);
 
+/* The frameToModel call sequence of ElasticFusion::processFrame (ElasticFusion.cpp:343-368) as one call:
+ *   initICPModel(vertices, normals, depth_cutoff, pose) ; initRGBModel(model_rgba8) ; initICP(depth, depth_cutoff) ;
+ *   initRGB(rgba8) ; getIncrementalTransformation(trans = pose.t, rot = pose.R, ...)
+ * `on_host` selects host pointers (dense rows, ideally pinned) or device pointers (dense rows) for all five
+ * images.  Same results as the five separate calls; it only saves call overhead for FFI callers. */
+typedef struct ef_frame_inputs
+{
+    const float * vertices_rgba32f;
+    const float * normals_rgba32f;
+    const uint8_t * model_rgba8;
+    const uint16_t * depth;
+    const uint8_t * rgba8;
+    float depth_cutoff;
+    int on_host;
+} ef_frame_inputs;
+int ef_track_frame_to_model_launch(ef_tracker * t, const ef_frame_inputs * in, const float * h_pose16, int rgb_only, float icp_weight,
+                                   int pyramid, int fast_odom, int so3);
+/* = _launch + ef_get_incremental_transformation_finish */
+int ef_track_frame_to_model(ef_tracker * t, const ef_frame_inputs * in, const float * h_pose16, float * trans3, float * rot9, int rgb_only,
+                            float icp_weight, int pyramid, int fast_odom, int so3, ef_track_stats * stats);
+
 /* getCovariance(): inverse of lastA                                                    :605-608 */
 int ef_get_covariance(ef_tracker * t, double * cov36);
 

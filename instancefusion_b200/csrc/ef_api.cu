@@ -828,6 +828,40 @@ EF_API int ef_get_incremental_transformation(ef_tracker * t, float * trans, floa
     return ef_get_incremental_transformation_finish(t, trans, rot, stats);
 }
 
+// ElasticFusion.cpp:343-368 in one call
+EF_API int ef_track_frame_to_model_launch(ef_tracker * t, const ef_frame_inputs * in, const float * pose, int rgb_only, float icp_weight, int pyramid,
+                                          int fast_odom, int so3)
+{
+    if(!t || !in || !pose) return EF_ERR_INVALID_ARGUMENT;
+    int rc;
+    if(in->on_host)
+    {
+        rc = ef_init_icp_model_host(t, in->vertices_rgba32f, in->normals_rgba32f, in->depth_cutoff, pose);
+        if(!rc) rc = ef_init_rgb_model_host(t, in->model_rgba8);
+        if(!rc) rc = ef_init_icp_depth_host(t, in->depth, in->depth_cutoff);
+        if(!rc) rc = ef_init_rgb_host(t, in->rgba8);
+    }
+    else
+    {
+        rc = ef_init_icp_model(t, in->vertices_rgba32f, in->normals_rgba32f, in->depth_cutoff, pose);
+        if(!rc) rc = ef_init_rgb_model(t, in->model_rgba8, 0);
+        if(!rc) rc = ef_init_icp_depth(t, in->depth, 0, in->depth_cutoff);
+        if(!rc) rc = ef_init_rgb(t, in->rgba8, 0);
+    }
+    if(rc) return rc;
+    const float trans[3] = {pose[3], pose[7], pose[11]};
+    const float rot[9] = {pose[0], pose[1], pose[2], pose[4], pose[5], pose[6], pose[8], pose[9], pose[10]};
+    return ef_get_incremental_transformation_launch(t, trans, rot, rgb_only, icp_weight, pyramid, fast_odom, so3);
+}
+
+EF_API int ef_track_frame_to_model(ef_tracker * t, const ef_frame_inputs * in, const float * pose, float * trans, float * rot, int rgb_only,
+                                   float icp_weight, int pyramid, int fast_odom, int so3, ef_track_stats * stats)
+{
+    const int rc = ef_track_frame_to_model_launch(t, in, pose, rgb_only, icp_weight, pyramid, fast_odom, so3);
+    if(rc) return rc;
+    return ef_get_incremental_transformation_finish(t, trans, rot, stats);
+}
+
 // RGBDOdometry.cpp:605-608
 EF_API int ef_get_covariance(ef_tracker * t, double * cov)
 {

@@ -244,24 +244,40 @@ __global__ void __launch_bounds__(256) k_depth_level(const uint16_t * __restrict
 // populateRGBDData (RGBDOdometry.cpp:208-235), level 0 and level 1: a thread owns one level-1 pixel = a 2x2
 // block of level 0.  The 5x5 windows of the pyrDowns re-derive their level-0 taps from the inputs.
 // ------------------------------------------------------------------------------------------------
+constexpr int kTileW = 2 * 32 + 3, kTileH = 2 * 8 + 3; // level-0 footprint of a 32x8 block of level-1 pixels
+
 template<bool WITH_DEPTH>
 __global__ void __launch_bounds__(256) k_rgbd_level0(const uint8_t * __restrict__ rgba, int rgba_pitch /*bytes*/, const float * __restrict__ tmp_z,
                                                      float cutoff, int rows, int cols, uint8_t * __restrict__ img0, float * __restrict__ depth0,
                                                      uint8_t * __restrict__ img1, float * __restrict__ depth1)
 {
+    __shared__ uint8_t s_img[kTileH][kTileW + 1];
+    __shared__ float s_dep[WITH_DEPTH ? kTileH : 1][WITH_DEPTH ? kTileW : 1];
+    const int cols1 = cols >> 1, rows1 = rows >> 1;
+    const int ox = 2 * (int)(blockIdx.x * blockDim.x) - 2, oy = 2 * (int)(blockIdx.y * blockDim.y) - 2; // tile origin in level 0
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+    // stage the level-0 intensity (and depth) of the whole footprint once: every texel is converted once per block
+    for(int i = tid; i < kTileW * kTileH; i += 256)
+    {
+        const int ty = i / kTileW, tx = i - ty * kTileW;
+        const int gx = ox + tx, gy = oy + ty;
+        if(gx >= 0 && gy >= 0 && gx < cols && gy < rows)
+        {
+            s_img[ty][tx] = intensity_px(__ldg(reinterpret_cast<const uchar4 *>(rgba + (size_t)gy * rgba_pitch) + gx));
+            if(WITH_DEPTH) s_dep[ty][tx] = depth_from_z(__ldg(tmp_z + (size_t)gy * cols + gx), cutoff);
+        }
+    }
+    __syncthreads();
     const int x1 = blockIdx.x * blockDim.x + threadIdx.x;
     const int y1 = blockIdx.y * blockDim.y + threadIdx.y;
-    const int cols1 = cols >> 1, rows1 = rows >> 1;
     if(x1 >= cols1 || y1 >= rows1) return;
-    auto texel = [&](int y, int x) { return __ldg(reinterpret_cast<const uchar4 *>(rgba + (size_t)y * rgba_pitch) + x); };
-    auto inten = [&](int y, int x) { return intensity_px(texel(y, x)); };
-    auto dep = [&](int y, int x) { return depth_from_z(__ldg(tmp_z + (size_t)y * cols + x), cutoff); };
+    auto inten = [&](int y, int x) { return s_img[y - oy][x - ox]; };
+    auto dep = [&](int y, int x) { return s_dep[WITH_DEPTH ? y - oy : 0][WITH_DEPTH ? x - ox : 0]; };
 #pragma unroll
     for(int j = 0; j < 2; j++)
     {
         const int y = 2 * y1 + j, x = 2 * x1;
-        const uint8_t a = inten(y, x), b = inten(y, x + 1);
-        *reinterpret_cast<uchar2 *>(img0 + (size_t)y * cols + x) = make_uchar2(a, b);
+        *reinterpret_cast<uchar2 *>(img0 + (size_t)y * cols + x) = make_uchar2(inten(y, x), inten(y, x + 1));
         if(WITH_DEPTH) *reinterpret_cast<float2 *>(depth0 + (size_t)y * cols + x) = make_float2(dep(y, x), dep(y, x + 1));
     }
     img1[(size_t)y1 * cols1 + x1] = pyr_down_gauss_u8_px(inten, rows, cols, x1, y1);

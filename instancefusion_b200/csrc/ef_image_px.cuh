@@ -75,6 +75,28 @@ template<class F>
 __device__ __forceinline__ float pyr_down_gauss_f32_px(F at, int srows, int scols, int x, int y)
 {
     const int D = 5;
+    if(x >= 1 && y >= 1 && 2 * x + 3 <= scols - 1 && 2 * y + 3 <= srows - 1)
+    {
+        // interior: no clamp is active, the window is the full 5x5 and the (mirrored) kernel index runs 24..0;
+        // same raster order and the same FMA chain as the general loop, with the binomial taps as literals
+        const float k1[5] = {1.f, 4.f, 6.f, 4.f, 1.f};
+        float sum = 0;
+        int count = 0;
+#pragma unroll
+        for(int j = 0; j < 5; j++)
+#pragma unroll
+            for(int i = 0; i < 5; i++)
+            {
+                const float s = at(2 * y - 2 + j, 2 * x - 2 + i);
+                if(!isnan(s))
+                {
+                    const float k = k1[4 - j] * k1[4 - i];
+                    sum = __fmaf_rn(s, k, sum);
+                    count += k;
+                }
+            }
+        return (float)(sum / (float)count);
+    }
     const int tx = min(2 * x - D / 2 + D, scols - 1);
     const int ty = min(2 * y - D / 2 + D, srows - 1);
     int cy = max(0, 2 * y - D / 2);
@@ -99,6 +121,27 @@ template<class F>
 __device__ __forceinline__ uint8_t pyr_down_gauss_u8_px(F at, int srows, int scols, int x, int y)
 {
     const int D = 5;
+    if(x >= 1 && y >= 1 && 2 * x + 3 <= scols - 1 && 2 * y + 3 <= srows - 1)
+    {
+        // interior fast path (all sums are exact small integers in binary32, so only the taps' membership matters)
+        const int k1[5] = {1, 4, 6, 4, 1};
+        int isum = 0, count = 0;
+#pragma unroll
+        for(int j = 0; j < 5; j++)
+#pragma unroll
+            for(int i = 0; i < 5; i++)
+            {
+                const int s = at(2 * y - 2 + j, 2 * x - 2 + i);
+                const int k = k1[j] * k1[i];
+                if(s > 0)
+                {
+                    isum += s * k;
+                    count += k;
+                }
+            }
+        const uint8_t r = ((float)isum / (float)count);
+        return r;
+    }
     const int tx = min(2 * x - D / 2 + D, scols - 1);
     const int ty = min(2 * y - D / 2 + D, srows - 1);
     int cy = max(0, 2 * y - D / 2);
@@ -146,6 +189,30 @@ __device__ __forceinline__ float sobel_y_tap(int k)
 template<class F>
 __device__ __forceinline__ void derivative_px(F at, int rows, int cols, int x, int y, short & dx, short & dy)
 {
+    if(x >= 1 && y >= 1 && x + 1 <= cols - 1 && y + 1 <= rows - 1)
+    {
+        // interior: all nine taps are visited, kernelIndex runs 8..0 in raster order.  Zero taps are skipped
+        // (fma(s, +-0, acc) == acc exactly); the non-zero ones keep their order.
+        const float tl = (float)at(y - 1, x - 1), tm = (float)at(y - 1, x), tr = (float)at(y - 1, x + 1);
+        const float ml = (float)at(y, x - 1), mr = (float)at(y, x + 1);
+        const float bl = (float)at(y + 1, x - 1), bm = (float)at(y + 1, x), br = (float)at(y + 1, x + 1);
+        float gx = 0, gy = 0;
+        gx = __fmaf_rn(tl, -0.52201f, gx);
+        gx = __fmaf_rn(tr, 0.52201f, gx);
+        gx = __fmaf_rn(ml, -0.79451f, gx);
+        gx = __fmaf_rn(mr, 0.79451f, gx);
+        gx = __fmaf_rn(bl, -0.52201f, gx);
+        gx = __fmaf_rn(br, 0.52201f, gx);
+        gy = __fmaf_rn(tl, -0.52201f, gy);
+        gy = __fmaf_rn(tm, -0.79451f, gy);
+        gy = __fmaf_rn(tr, -0.52201f, gy);
+        gy = __fmaf_rn(bl, 0.52201f, gy);
+        gy = __fmaf_rn(bm, 0.79451f, gy);
+        gy = __fmaf_rn(br, 0.52201f, gy);
+        dx = gx;
+        dy = gy;
+        return;
+    }
     float dxVal = 0;
     float dyVal = 0;
     int kernelIndex = 8;

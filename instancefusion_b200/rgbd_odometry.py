@@ -200,6 +200,31 @@ class RGBDOdometry:
         self._publish()
         return tr, ro.reshape(3, 3)
 
+    # -- ElasticFusion::processFrame's frameToModel sequence (ElasticFusion.cpp:343-368) in one C call ---------
+    def _frame_inputs(self, vertices, normals, model_rgba, depth, rgba, depthCutoff):
+        from .binding import FrameInputs
+        on_host = not _is_cuda_tensor(vertices)
+        if on_host:
+            ptr = lambda a: a.data_ptr() if hasattr(a, "data_ptr") else a.ctypes.data
+        else:
+            ptr = lambda a: a.data_ptr()
+        self._keep_frame = (vertices, normals, model_rgba, depth, rgba)
+        return FrameInputs(ptr(vertices), ptr(normals), ptr(model_rgba), ptr(depth), ptr(rgba), float(depthCutoff), int(on_host))
+
+    def trackFrameToModelLaunch(self, vertices, normals, model_rgba, depth, rgba, depthCutoff, modelPose, rgbOnly, icpWeight, pyramid,
+                                fastOdom, so3):
+        fi = self._frame_inputs(vertices, normals, model_rgba, depth, rgba, depthCutoff)
+        pose = np.ascontiguousarray(np.asarray(modelPose, dtype=np.float32).reshape(16))
+        rc = self._L.ef_track_frame_to_model_launch(self._h, C.byref(fi), pose.ctypes.data_as(C.c_void_p), C.c_int(int(rgbOnly)),
+                                                    C.c_float(icpWeight), C.c_int(int(pyramid)), C.c_int(int(fastOdom)), C.c_int(int(so3)))
+        self._check(rc, "ef_track_frame_to_model_launch")
+
+    def trackFrameToModel(self, vertices, normals, model_rgba, depth, rgba, depthCutoff, modelPose, rgbOnly, icpWeight, pyramid, fastOdom,
+                          so3):
+        self.trackFrameToModelLaunch(vertices, normals, model_rgba, depth, rgba, depthCutoff, modelPose, rgbOnly, icpWeight, pyramid,
+                                     fastOdom, so3)
+        return self.finish()
+
     def getCovariance(self):
         cov = np.zeros(36)
         self._check(self._L.ef_get_covariance(self._h, cov.ctypes.data_as(C.c_void_p)), "ef_get_covariance")

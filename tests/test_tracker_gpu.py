@@ -245,3 +245,30 @@ def test_fused_and_per_operator_builders_agree():
     finally:
         a.close()
         b.close()
+
+
+def test_frame_to_model_single_call_equals_five_calls():
+    """ef_track_frame_to_model == initICPModel, initRGBModel, initICP, initRGB, getIncrementalTransformation (host and device inputs)."""
+    import torch
+    w, h = 640, 480
+    K, pose0, pose1, f0, f1 = util.frame_pair(w, h)
+    pose0f = pose0.astype(np.float32)
+    a = ef.RGBDOdometry(w, h, K.cx, K.cy, K.fx, K.fy, solve_mode=RO.EF_SOLVE_DEVICE)
+    b = ef.RGBDOdometry(w, h, K.cx, K.cy, K.fx, K.fy, solve_mode=RO.EF_SOLVE_DEVICE)
+    try:
+        m = MODES["joint"]
+        _feed(a, pose0f, f0, f1, first_rgb=False)
+        ta, Ra = a.getIncrementalTransformation(pose0f[:3, 3], pose0f[:3, :3], **m)
+        args = (20.0, pose0f, m["rgbOnly"], m["icpWeight"], m["pyramid"], m["fastOdom"], m["so3"])
+        tb, Rb = b.trackFrameToModel(f0["vmap"], f0["nmap"], f0["rgba"], f1["depth"], f1["rgba"], *args)
+        assert np.array_equal(ta, tb) and np.array_equal(Ra, Rb)
+        dev = [torch.from_numpy(x).cuda() for x in (f0["vmap"], f0["nmap"], f0["rgba"])]
+        dev.append(torch.from_numpy(f1["depth"].view(np.int16)).cuda().view(torch.uint16))
+        dev.append(torch.from_numpy(f1["rgba"]).cuda())
+        torch.cuda.synchronize()
+        tc, Rc = b.trackFrameToModel(*dev, *args)
+        assert np.array_equal(ta, tc) and np.array_equal(Ra, Rc)
+        assert b.lastICPCount == a.lastICPCount and b.lastRGBCount == a.lastRGBCount
+    finally:
+        a.close()
+        b.close()
