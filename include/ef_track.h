@@ -69,6 +69,8 @@ typedef struct ef_track_stats
 #define EF_OPT_USE_GRAPH 2       /* 0/1: replay the frame's kernels from a CUDA graph (device mode) */
 #define EF_OPT_FUSED_BUILD 3     /* 0/1: fused pyramid builders (default 1) instead of one kernel per operator */
 #define EF_OPT_PROFILE 4         /* 0/1: bracket the solve of every getIncrementalTransformation with CUDA events */
+#define EF_OPT_GRID_CTAS 5       /* device mode: CTAs (= SMs) the persistent tracker kernel occupies; 0 = all.  Lets k handles
+                                    track k independent sequences concurrently on disjoint SMs of one GPU */
 
 #define EF_SOLVE_HOST 0   /* one step kernel per operator call, 6x6 LDLT + pose update in double on the host,
                              exactly the reference's control flow (RGBDOdometry.cpp:405-585) */

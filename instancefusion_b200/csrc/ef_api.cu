@@ -114,6 +114,7 @@ EF_API int ef_tracker_create(int width, int height, float cx, float cy, float fx
     t->use_graph = 0;
     t->fused_build = 1;
     t->launches = 0;
+    t->grid_ctas = 0;
     t->profile = 0;
     t->ev_begin = t->ev_end = nullptr;
     t->ev_pending = false;
@@ -229,6 +230,10 @@ EF_API int ef_tracker_set_option(ef_tracker * t, int key, int value)
         return EF_OK;
     case EF_OPT_USE_GRAPH: t->use_graph = value ? 1 : 0; return EF_OK;
     case EF_OPT_FUSED_BUILD: t->fused_build = value ? 1 : 0; return EF_OK;
+    case EF_OPT_GRID_CTAS:
+        if(t->launch_pending) return fail(t, EF_ERR_BAD_STATE, "a launch is pending");
+        t->grid_ctas = value;
+        return device_track_configure(t, value);
     case EF_OPT_PROFILE:
         if(value && !t->ev_begin)
         {
@@ -250,6 +255,7 @@ EF_API int ef_tracker_get_option(ef_tracker * t, int key, int * value)
     case EF_OPT_USE_GRAPH: *value = t->use_graph; return EF_OK;
     case EF_OPT_FUSED_BUILD: *value = t->fused_build; return EF_OK;
     case EF_OPT_PROFILE: *value = t->profile; return EF_OK;
+    case EF_OPT_GRID_CTAS: *value = t->grid_ctas; return EF_OK;
     default: return EF_ERR_INVALID_ARGUMENT;
     }
 }

@@ -960,14 +960,18 @@ struct DeviceTrack
 
 } // namespace
 
-int device_track_init(ef_tracker * t)
+// (re)derive the launch geometry for a grid of `grid` CTAs: pixels per thread unit and passes per level ->
+// shared-memory records per thread.  A handle normally owns every SM; EF_OPT_GRID_CTAS lets several handles
+// share the GPU (e.g. two sequences tracked concurrently on 74 SMs each).
+int device_track_configure(ef_tracker * t, int grid)
 {
-    DeviceTrack * d = new DeviceTrack();
-    memset(d, 0, sizeof(*d));
-    t->track_state = d;
-    d->grid = t->num_sms < 255 ? t->num_sms : 255; // arrivals live in 8 bits of the barrier-B word
+    DeviceTrack * d = static_cast<DeviceTrack *>(t->track_state);
+    if(!d) return EF_ERR_BAD_STATE;
+    const int max_grid = t->num_sms < 255 ? t->num_sms : 255; // arrivals live in 8 bits of the barrier-B word
+    if(grid <= 0 || grid > max_grid) grid = max_grid;
+    if(grid < 2) grid = 2;
+    d->grid = grid;
     const int W = d->grid - 1;
-    // pixels per thread unit and passes per level -> shared-memory records per thread
     int max_records = 1;
     for(int i = 0; i < kNumPyrs; i++)
     {
@@ -982,11 +986,21 @@ int device_track_init(ef_tracker * t)
     d->smem_bytes = (size_t)max_records * kThreads * sizeof(int4);
     const size_t rows_smem = (size_t)W * kRowFloats * sizeof(float);
     if(rows_smem > d->smem_bytes) d->smem_bytes = rows_smem;
+    return EF_OK;
+}
+
+int device_track_init(ef_tracker * t)
+{
+    DeviceTrack * d = new DeviceTrack();
+    memset(d, 0, sizeof(*d));
+    t->track_state = d;
+    device_track_configure(t, 0);
+    const int max_grid = t->num_sms < 255 ? t->num_sms : 255;
     d->launch_seq = 0;
     cudaError_t e = cudaMalloc((void **)&d->ctl, sizeof(TrackCtl));
     if(e == cudaSuccess) e = cudaMemsetAsync(d->ctl, 0, sizeof(TrackCtl), t->stream);
-    if(e == cudaSuccess) e = cudaMalloc((void **)&d->rows, (size_t)d->grid * kRowChunks * sizeof(uint4));
-    if(e == cudaSuccess) e = cudaMemsetAsync(d->rows, 0, (size_t)d->grid * kRowChunks * sizeof(uint4), t->stream);
+    if(e == cudaSuccess) e = cudaMalloc((void **)&d->rows, (size_t)max_grid * kRowChunks * sizeof(uint4));
+    if(e == cudaSuccess) e = cudaMemsetAsync(d->rows, 0, (size_t)max_grid * kRowChunks * sizeof(uint4), t->stream);
     if(e == cudaSuccess) e = cudaHostAlloc((void **)&d->out, sizeof(TrackOutput), cudaHostAllocMapped);
     const char * env = getenv("EF_TRACK_TIMING");
     if(e == cudaSuccess && env && env[0] == '1')
@@ -994,8 +1008,7 @@ int device_track_init(ef_tracker * t)
         e = cudaMalloc((void **)&d->dbg, sizeof(long long) * kMaxIters * kDbgStamps);
         if(e == cudaSuccess) e = cudaMemsetAsync(d->dbg, 0, sizeof(long long) * kMaxIters * kDbgStamps, t->stream);
     }
-    if(e == cudaSuccess && d->smem_bytes <= 200 * 1024)
-        e = cudaFuncSetAttribute(k_track, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->smem_bytes);
+    if(e == cudaSuccess) e = cudaFuncSetAttribute(k_track, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if(e != cudaSuccess)
     {
         device_track_destroy(t);
@@ -1086,7 +1099,7 @@ int device_track_launch(ef_tracker * t, const float * trans, const float * rot, 
     if((d->launch_seq & 0xffffffu) == 0)
     {
         d->launch_seq = 1;
-        cudaMemsetAsync(d->rows, 0, (size_t)d->grid * kRowChunks * sizeof(uint4), t->stream);
+        cudaMemsetAsync(d->rows, 0, (size_t)(t->num_sms < 255 ? t->num_sms : 255) * kRowChunks * sizeof(uint4), t->stream);
         cudaMemsetAsync(d->ctl, 0, sizeof(TrackCtl), t->stream);
     }
     A.epoch_base = d->launch_seq << 8;

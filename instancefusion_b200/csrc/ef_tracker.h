@@ -40,6 +40,7 @@ struct ef_tracker
     int solve_mode;  // EF_SOLVE_HOST | EF_SOLVE_DEVICE
     int use_graph;
     int fused_build;
+    int grid_ctas;   // EF_OPT_GRID_CTAS (0 = every SM)
 
     // one device arena, sliced
     void * arena;
@@ -91,6 +92,7 @@ namespace ef
 {
 // EF_SOLVE_DEVICE path (ef_track_kernel.cu)
 int device_track_init(ef_tracker * t);
+int device_track_configure(ef_tracker * t, int grid_ctas);
 void device_track_destroy(ef_tracker * t);
 int device_track_launch(ef_tracker * t, const float * trans, const float * rot, int rgb_only, float icp_weight, int pyramid, int fast_odom,
                         int so3);
