@@ -572,7 +572,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_track(const TrackArgs A)
 
     int dbg_it = 0;
     auto stamp = [&](int k) {
-        if(A.dbg && is_solver && dbg_it < kMaxIters) A.dbg[dbg_it * kDbgStamps + k] = clock64();
+        if(A.dbg && threadIdx.x == 0 && dbg_it < kMaxIters) A.dbg[((size_t)blockIdx.x * kMaxIters + dbg_it) * kDbgStamps + k] = clock64();
     };
 
     // ============================================================================================
@@ -759,6 +759,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_track(const TrackArgs A)
                         for(int k = 0; k < px; k++) s_corr[(p * px + k) * kThreads + threadIdx.x] = make_int4(-1, 0, 0, 0);
                     }
                 }
+                stamp(7);
                 cnt = __reduce_add_sync(kFullMask, cnt);
                 sig = __reduce_add_sync(kFullMask, sig);
                 if(lane == 0) { s_wcnt[warp] = cnt; s_wsig[warp] = sig; }
@@ -795,6 +796,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_track(const TrackArgs A)
                 float vi = 0.f;
                 if(A.icp) vi = warp_transpose_reduce32(accI);
                 if(lane < 29) s_red[warp * 64 + lane] = vi;
+                stamp(8);
             }
 
             // ---- barrier B: everybody (CTA 0 included, it needs the count for the statistics) reads the word ----
@@ -874,6 +876,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_track(const TrackArgs A)
                 }
                 __syncthreads();
                 publish_row(my_row, s_final, kRowChunks, arr);
+                stamp(9);
             }
         }
     }
@@ -946,8 +949,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_track(const TrackArgs A)
 
 struct DeviceTrack
 {
-    long long * dbg;      // device, kMaxIters * kDbgStamps stamps (EF_TRACK_TIMING=1)
+    long long * dbg;      // device, max_grid * kMaxIters * kDbgStamps stamps (EF_TRACK_TIMING=1)
     double dbg_acc[kMaxIters][kDbgStamps];
+    double wrk_mean[kMaxIters][5], wrk_max[kMaxIters][5]; // worker phase durations, mean / max over the worker CTAs
+    long long * dbg_host;
+    int dbg_grid;
     long long dbg_n;
     TrackCtl * ctl;
     uint4 * rows;
@@ -1005,8 +1011,10 @@ int device_track_init(ef_tracker * t)
     const char * env = getenv("EF_TRACK_TIMING");
     if(e == cudaSuccess && env && env[0] == '1')
     {
-        e = cudaMalloc((void **)&d->dbg, sizeof(long long) * kMaxIters * kDbgStamps);
-        if(e == cudaSuccess) e = cudaMemsetAsync(d->dbg, 0, sizeof(long long) * kMaxIters * kDbgStamps, t->stream);
+        d->dbg_grid = max_grid;
+        d->dbg_host = (long long *)malloc(sizeof(long long) * max_grid * kMaxIters * kDbgStamps);
+        e = cudaMalloc((void **)&d->dbg, sizeof(long long) * max_grid * kMaxIters * kDbgStamps);
+        if(e == cudaSuccess) e = cudaMemsetAsync(d->dbg, 0, sizeof(long long) * max_grid * kMaxIters * kDbgStamps, t->stream);
     }
     if(e == cudaSuccess) e = cudaFuncSetAttribute(k_track, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if(e != cudaSuccess)
@@ -1039,8 +1047,21 @@ void device_track_destroy(ef_tracker * t)
                         first ? 0.0 : (a[2] - a[0]) / n, first ? 0.0 : (a[3] - a[2]) / n, (a[1] - (first ? a[0] : a[3])) / n, (a[4] - a[1]) / n,
                         (a[6] - a[4]) / n, (a[6] - a[0]) / n);
             }
+            // worker CTAs: params wait (0->4) | photometric association + CTA sync (4->5) | ICP + warp reduce (5->8) |
+            // barrier-B wait (8->6) | photometric rows + CTA reduce + publish (6->9)
+            fprintf(stderr, "[ef_track timing] worker CTAs, cycles mean/max over workers\n");
+            for(int it = 0; it < kMaxIters; it++)
+            {
+                if(d->dbg_acc[it][4] == 0) continue;
+                const double n = (double)d->dbg_n;
+                const double * m = d->wrk_mean[it];
+                const double * x = d->wrk_max[it];
+                fprintf(stderr, "  it %2d: wait-params %6.0f/%6.0f  rgb-assoc %6.0f/%6.0f  icp %6.0f/%6.0f  wait-barB %6.0f/%6.0f  rgb-rows+publish %6.0f/%6.0f\n", it,
+                        m[0] / n, x[0] / n, m[1] / n, x[1] / n, m[2] / n, x[2] / n, m[3] / n, x[3] / n, m[4] / n, x[4] / n);
+            }
         }
         cudaFree(d->dbg);
+        free(d->dbg_host);
     }
     if(d->ctl) cudaFree(d->ctl);
     if(d->rows) cudaFree(d->rows);
@@ -1150,13 +1171,36 @@ int device_track_finish(ef_tracker * t, float * trans, float * rot)
     }
     if(d->dbg)
     {
-        long long h[kMaxIters * kDbgStamps];
-        if(cudaMemcpy(h, d->dbg, sizeof(h), cudaMemcpyDeviceToHost) == cudaSuccess)
+        long long * h = d->dbg_host;
+        const size_t bytes = sizeof(long long) * d->dbg_grid * kMaxIters * kDbgStamps;
+        if(cudaMemcpy(h, d->dbg, bytes, cudaMemcpyDeviceToHost) == cudaSuccess)
         {
             for(int it = 0; it < kMaxIters; it++)
+            {
                 for(int k = 0; k < kDbgStamps; k++) d->dbg_acc[it][k] += (double)h[it * kDbgStamps + k];
+                static const int from[5] = {0, 4, 5, 8, 6}, to[5] = {4, 5, 8, 6, 9};
+                for(int ph = 0; ph < 5; ph++)
+                {
+                    double sum = 0, mx = 0;
+                    int cnt = 0;
+                    for(int c = 1; c < d->grid; c++)
+                    {
+                        const long long * w = h + ((size_t)c * kMaxIters + it) * kDbgStamps;
+                        if(w[from[ph]] == 0 || w[to[ph]] == 0) continue;
+                        const double v = (double)(w[to[ph]] - w[from[ph]]);
+                        sum += v;
+                        if(v > mx) mx = v;
+                        cnt++;
+                    }
+                    if(cnt)
+                    {
+                        d->wrk_mean[it][ph] += sum / cnt;
+                        d->wrk_max[it][ph] += mx;
+                    }
+                }
+            }
             d->dbg_n++;
-            cudaMemset(d->dbg, 0, sizeof(h));
+            cudaMemset(d->dbg, 0, bytes);
         }
     }
     return EF_OK;
