@@ -6,7 +6,8 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_SO = os.path.join(_HERE, "libef_track.so")
+# EF_TRACK_LIB: developer override (kernel-variant sweeps, tools/build_variant.sh); the product is libef_track.so
+_SO = os.environ.get("EF_TRACK_LIB") or os.path.join(_HERE, "libef_track.so")
 _lib = None
 
 

@@ -246,42 +246,35 @@ EF_HD void update_se3(double * resultRt, const double * x)
 // to ~1e-15 relative; a zero pivot (no correspondences) yields x = 0 like the pivoted routine.
 EF_HD int acc_index(int i, int j) { return i * 7 - i * (i - 1) / 2 + (j - i); } // j >= i, j == 6 selects b(i)
 
-EF_HD void ldlt_solve_spd6_acc(const double * S, double * x)
+EF_HD void ldlt_solve_spd6_acc(double * a, double * x)
 {
-    double L[6][6], d[6], y[6];
+    // In place on the accumulator (destroyed), right-looking: pivot j scales its row once (ONE reciprocal per pivot)
+    // and updates the trailing rows including the right-hand side column, so the forward substitution rides along
+    // and all updates of a pivot are independent.  Afterwards a(j,i) = L(i,j) and a(j,6) = (L^-1 b)(j).
+    double inv[6];
 #pragma unroll
     for(int j = 0; j < 6; j++)
     {
-        double dj = S[acc_index(j, j)];
+        const double dj = a[acc_index(j, j)];
+        inv[j] = (dj != 0.0) ? 1.0 / dj : 0.0;
+        double l[6];
 #pragma unroll
-        for(int k = 0; k < j; k++) dj -= L[j][k] * L[j][k] * d[k];
-        d[j] = dj;
-        const double inv = (dj != 0.0) ? 1.0 / dj : 0.0;
+        for(int i = j + 1; i < 6; i++) l[i] = a[acc_index(j, i)] * inv[j];
 #pragma unroll
         for(int i = j + 1; i < 6; i++)
         {
-            double v = S[acc_index(j, i)]; // A(i,j) = A(j,i)
 #pragma unroll
-            for(int k = 0; k < j; k++) v -= L[i][k] * L[j][k] * d[k];
-            L[i][j] = v * inv;
+            for(int k = i; k < 7; k++) a[acc_index(i, k)] -= l[i] * a[acc_index(j, k)];
         }
+#pragma unroll
+        for(int i = j + 1; i < 6; i++) a[acc_index(j, i)] = l[i];
     }
-#pragma unroll
-    for(int i = 0; i < 6; i++)
-    {
-        double v = S[acc_index(i, 6)];
-#pragma unroll
-        for(int k = 0; k < i; k++) v -= L[i][k] * y[k];
-        y[i] = v;
-    }
-#pragma unroll
-    for(int i = 0; i < 6; i++) y[i] = (d[i] != 0.0) ? y[i] / d[i] : 0.0;
 #pragma unroll
     for(int i = 5; i >= 0; i--)
     {
-        double v = y[i];
+        double v = a[acc_index(i, 6)] * inv[i];
 #pragma unroll
-        for(int k = i + 1; k < 6; k++) v -= L[k][i] * x[k];
+        for(int k = i + 1; k < 6; k++) v -= a[acc_index(i, k)] * x[k];
         x[i] = v;
     }
 }
@@ -327,6 +320,43 @@ EF_HD void rgb_warp_params(const double * resultRt, const double * K, const doub
     const double tv[3] = {Rt[3], Rt[7], Rt[11]};
 #pragma unroll
     for(int r = 0; r < 3; r++) kt3[r] = (float)(K[r * 3] * tv[0] + K[r * 3 + 1] * tv[1] + K[r * 3 + 2] * tv[2]);
+}
+
+// K = [fx 0 cx; 0 fy cy; 0 0 1] and its inverse have five structural zeros: K R K^-1 and K t with the zero terms
+// dropped.  Dropping  + 0 * x  terms is exact, so this equals the dense products of rgb_warp_params / the SO(3)
+// homography (RGBDOdometry.cpp:318-329, :424-434) evaluated with fused multiply-adds; used by the device solver
+// thread, where every double-precision instruction is on the critical path of the iteration.
+EF_HD void krk_sparse(const double * R, double fx, double fy, double cx, double cy, const double * K_inv, double * KR, double * KRK)
+{
+#pragma unroll
+    for(int j = 0; j < 3; j++)
+    {
+        KR[j] = fma(cx, R[6 + j], fx * R[j]);
+        KR[3 + j] = fma(cy, R[6 + j], fy * R[3 + j]);
+        KR[6 + j] = R[6 + j];
+    }
+#pragma unroll
+    for(int i = 0; i < 3; i++)
+    {
+        KRK[i * 3 + 0] = KR[i * 3 + 0] * K_inv[0];
+        KRK[i * 3 + 1] = KR[i * 3 + 1] * K_inv[4];
+        KRK[i * 3 + 2] = fma(KR[i * 3 + 2], K_inv[8], fma(KR[i * 3 + 1], K_inv[5], KR[i * 3 + 0] * K_inv[2]));
+    }
+}
+
+EF_HD void rgb_warp_params_sparse(const double * resultRt, double fx, double fy, double cx, double cy, const double * K_inv, float * krkinv9,
+                                  float * kt3)
+{
+    double Rt[16];
+    inverse_affine44(resultRt, Rt);
+    const double R[9] = {Rt[0], Rt[1], Rt[2], Rt[4], Rt[5], Rt[6], Rt[8], Rt[9], Rt[10]};
+    double KR[9], KRK[9];
+    krk_sparse(R, fx, fy, cx, cy, K_inv, KR, KRK);
+#pragma unroll
+    for(int i = 0; i < 9; i++) krkinv9[i] = (float)KRK[i];
+    kt3[0] = (float)fma(cx, Rt[11], fx * Rt[3]);
+    kt3[1] = (float)fma(cy, Rt[11], fy * Rt[7]);
+    kt3[2] = (float)Rt[11];
 }
 
 // unpack the 29-float accumulator into A (6x6 row-major), b, residual[2]: reduce.cu:475-489

@@ -6,21 +6,24 @@
 // blocking D2H copies per iteration (57+ host round trips per frame).  Here one CTA per SM stays
 // resident for the whole solve and an iteration costs a handful of L2 round trips:
 //
-//   phase A   every thread, for its 4-pixel groups: all coalesced loads first (current v/n maps as 128-bit
-//             loads, gradients, depth, 4x4 validity window as 12 words), then both projections, then all
-//             gathers, then the math: 29 ICP sums in registers, photometric correspondences -> SHARED memory.
-//   barrier B (only with RGB: the weight needs the global count) ONE 64-bit atomic per CTA carries
-//             arrivals | count | sum diff^2; whoever polls it gets all three in one load.
+//   level start  every worker CTA evaluates the ITERATION-INVARIANT photometric gates of its pixels once
+//             (16-pixel border, gradient magnitude, depth validity, 4x4 validity window: reduce.cu:779-811) and
+//             compacts the survivors, in a fixed order, into a candidate list in SHARED memory (pixel, intensity,
+//             gradients, depth = 12 B each).  This runs while the solver CTA is still busy with the previous solve.
+//   phase A1  photometric association of the candidates (warp + gather + accept, reduce.cu:813-830) ->
+//             8-byte match records in shared memory; ONE 64-bit atomic per CTA carries
+//             arrivals | count | sum diff^2 ("barrier B": the robust weight needs the global sums).
+//   phase A2  ICP association + 29 sums in registers over 4-pixel units (128-bit loads); hides barrier B.
 //   phase B   photometric rows from the records in shared memory -> 29 more sums.
-//   reduce    transpose-reduce butterfly -> per-CTA 64-float partial row -> red.release arrival.
-//   solve     CTA 0 sees the last arrival, adds the rows in CTA order (deterministic), ONE thread runs the
-//             reference's host step in double (LDL^T, exp map, pose composition; ef_hostmath.h) and
-//             publishes the next parameters in a 128-byte line whose four 32-byte sectors each carry the
-//             epoch, so the other CTAs poll and load the parameters with the same single load.
+//   reduce    transpose-reduce butterfly per warp (skipped by warps that had no pixel) -> per-CTA 58-float row ->
+//             published as flagged 16-byte chunks.
+//   solve     CTA 0 polls all rows with independent loads in flight, adds them in worker order (deterministic),
+//             ONE thread runs the reference's host step in double (LDL^T, exp map, pose composition;
+//             ef_hostmath.h) out of shared memory and publishes the next parameters as 8 flagged chunks.
 //
 // No DataTerm image, no point cloud, no reduceSum launch, no host involvement until the final pose is
 // stored straight into pinned host memory.  Co-residency of the spinning CTAs is guaranteed by a
-// cooperative launch with gridDim = number of SMs.
+// cooperative launch with gridDim <= number of SMs.
 #include <float.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -38,7 +41,18 @@ namespace ef
 namespace
 {
 
-constexpr int kThreads = 640;    // 20 warps = 5 per scheduler (96 registers each)
+#ifndef EF_TRACK_THREADS
+#define EF_TRACK_THREADS 256
+#endif
+constexpr int kThreads = EF_TRACK_THREADS; // 8 warps, up to 255 registers each: measured best of {128..640} (tools/sweep.sh)
+#ifndef EF_TRACK_ICP_BATCH
+#define EF_TRACK_ICP_BATCH 3
+#endif
+constexpr int kIcpBatch = EF_TRACK_ICP_BATCH; // pixels of one thread whose loads and gathers are in flight together
+#ifndef EF_TRACK_ICP_SPLIT
+#define EF_TRACK_ICP_SPLIT 0
+#endif
+constexpr bool kIcpSplit = EF_TRACK_ICP_SPLIT != 0;
 constexpr int kWarps = kThreads / 32;
 constexpr int kMaxIters = 32;    // SE3 iterations per call (19 in the reference schedule)
 constexpr int kDbgStamps = 10;
@@ -47,7 +61,13 @@ constexpr int kRowFloats = kRowChunks * 3;
 constexpr int kSo3Chunks = 4;    // SO3 rows carry 11 floats
 constexpr int kLineChunks = 8;   // the parameter line = 8 x (3 floats + flag) = 24 floats
 constexpr int kPayload = kLineChunks * 3;
-constexpr int kParts = kThreads / 64; // final cross-CTA sum: 10 parts x 64 slots
+constexpr int kParts = kThreads / 64; // final cross-CTA sum: kParts x 64 slots
+constexpr int kMaxGrid = 255;    // arrivals live in 8 bits of the barrier-B word
+constexpr unsigned kNoMatch = 0xffffffffu;
+constexpr int kCandBytes = 20;   // 12-byte candidate + 8-byte match record
+constexpr int kMaxDynSmem = 200 * 1024;
+
+static_assert(kThreads % 32 == 0 && kThreads >= 128 && kThreads <= 1024, "EF_TRACK_THREADS");
 
 struct LevelArgs
 {
@@ -60,7 +80,6 @@ struct LevelArgs
     float inv_fx, inv_fy;                         // host 1.0f / f (cudafuncs.cu:671)
     float min_scale;
     int iterations;
-    int px;                                       // pixels per thread unit at this level (4 or 1)
     double K_inv[9];                              // host double inverse of K (RGBDOdometry.cpp:428)
 };
 
@@ -68,12 +87,15 @@ struct LevelArgs
 // 128-bit load, so its three payload words and its flag are always observed together.  No fence, no separate
 // "ready" counter: whoever polls a chunk gets the data with the same load that tells it the data is there.
 // Flags are launch-unique epochs (launch_seq << 8 | n), so nothing has to be reset between launches.
-struct alignas(128) TrackCtl
-{
-    uint4 line[kLineChunks];                      // parameters of the next phase, written by the solver thread
-    unsigned long long bar_b[kMaxIters];          // per SE3 iteration: arrivals | count << 8 | sigma << 32
-    double last_S[27];                            // combined normal equations of the last solve (for lastA / lastb)
-};
+// Nobody polls a line together with more than ~20 other CTAs (148 CTAs spinning on one line serialise in its L2 slice):
+//   par      the parameter line (8 chunks), kReplicas copies 256 bytes apart; worker w reads copy w % kReplicas.
+//            Chunks 0..3 = pose (Rcurr, tcurr), published as soon as the solve is done; chunks 4..7 = photometric warp
+//            (K R K^-1, K t), published later -- the workers start their ICP pixels in between.
+//   bslot[w] worker w's barrier-B arrival {count, sum diff^2}, polled by thread w of CTA 0
+//   bres[w]  the barrier-B result for worker w {sigma, rgbError, count}, written by thread w of CTA 0
+//   rows     worker w's partial sums of a round at rows[w * chunks ..), polled by CTA 0
+constexpr int kReplicas = 8;
+constexpr int kReplicaStride = 16; // chunks
 // SE3 payload: Rcurr[9] tcurr[3] krkinv[9] kt[3];  SO3 payload: H[9] krlr[9] done
 
 struct TrackOutput // pinned host memory, written by the solver thread
@@ -91,12 +113,14 @@ struct TrackArgs
     float Rprev[9], tprev[3], Rprev_inv[9];
     float dist_thresh, angle_thresh, max_depth_delta, sobel_scale, icp_weight;
     int icp, rgb, rgb_only, so3;
+    int cand_cap;                                 // capacity of the shared-memory candidate list
     float prev_icp_error, prev_icp_count, prev_so3_error, prev_so3_count, prev_rgb_error, prev_rgb_count;
     unsigned epoch_base;                          // launch_seq << 8
-    TrackCtl * ctl;
-    uint4 * rows;                                 // (gridDim.x - 1) * kRowChunks flagged chunks, one row per worker CTA
+    uint4 * par;                                  // kReplicas parameter lines
+    uint4 * bslot, * bres;                        // one flagged chunk per worker each
+    uint4 * rows;                                 // flagged chunks: worker w's row of a round at rows[w * chunks ..)
     TrackOutput * out;
-    long long * dbg;                              // optional clock64 stamps of CTA 0 (EF_TRACK_TIMING=1)
+    long long * dbg;                              // optional clock64 stamps of every CTA (EF_TRACK_TIMING=1)
 };
 
 // ---- 128-bit relaxed (L2-coherent) accesses ----
@@ -110,37 +134,38 @@ __device__ __forceinline__ void st_relaxed_v4(uint4 * p, const uint4 & v)
 {
     asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
-__device__ __forceinline__ unsigned long long ld_relaxed64(const unsigned long long * p)
+
+// warp 0 of CTA 0, payload already in shared memory: chunks [first, first + n) of every replica of the parameter
+// line; with n = 4 that is ONE store per lane
+__device__ __forceinline__ void warp_publish(uint4 * par, const float * s_payload, int first, int n, unsigned epoch)
 {
-    unsigned long long v;
-    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
+    __syncwarp();
+    for(int i = threadIdx.x & 31; i < kReplicas * n; i += 32)
+    {
+        const int r = i / n, c = first + (i - r * n);
+        st_relaxed_v4(par + r * kReplicaStride + c,
+                      make_uint4(__float_as_uint(s_payload[3 * c]), __float_as_uint(s_payload[3 * c + 1]), __float_as_uint(s_payload[3 * c + 2]), epoch));
+    }
 }
 
-// solver thread: eight self-validating chunks
-__device__ __forceinline__ void publish_line(uint4 * line, const float * payload, unsigned epoch)
-{
-#pragma unroll
-    for(int c = 0; c < kLineChunks; c++)
-        st_relaxed_v4(line + c, make_uint4(__float_as_uint(payload[3 * c]), __float_as_uint(payload[3 * c + 1]), __float_as_uint(payload[3 * c + 2]), epoch));
-}
-
-// all threads call: lanes 0..7 of warp 0 spin on their chunk until it shows `epoch`; payload -> smem
-__device__ __forceinline__ void wait_line(const uint4 * line, unsigned epoch, float * s_payload)
+// all threads of a worker CTA call: lanes 0..n-1 of warp 0 spin on chunks [first, first + n) of this CTA's replica until
+// they show `epoch`; payload -> smem
+__device__ __forceinline__ void wait_chunks(const uint4 * line, int first, int n, unsigned epoch, float * s_payload)
 {
     if(threadIdx.x < 32)
     {
-        const unsigned lane = threadIdx.x;
+        const int lane = threadIdx.x;
         uint4 v = make_uint4(0, 0, 0, epoch);
         do
         {
-            if(lane < kLineChunks) v = ld_relaxed_v4(line + lane);
+            if(lane < n) v = ld_relaxed_v4(line + first + lane);
         } while(!__all_sync(kFullMask, v.w == epoch));
-        if(lane < kLineChunks)
+        if(lane < n)
         {
-            s_payload[3 * lane] = __uint_as_float(v.x);
-            s_payload[3 * lane + 1] = __uint_as_float(v.y);
-            s_payload[3 * lane + 2] = __uint_as_float(v.z);
+            float * d = s_payload + 3 * (first + lane);
+            d[0] = __uint_as_float(v.x);
+            d[1] = __uint_as_float(v.y);
+            d[2] = __uint_as_float(v.z);
         }
     }
     __syncthreads();
@@ -156,32 +181,45 @@ __device__ __forceinline__ void publish_row(uint4 * my_row, const float * s_row,
     }
 }
 
-// CTA 0: collect every worker's row (poll + load in one), then add the rows in worker order -> s_final[64]
-__device__ __forceinline__ void gather_rows(const uint4 * rows, int workers, int chunks, unsigned epoch, float * s_rows /*[workers][kRowFloats]*/,
+// CTA 0: collect every worker's row -- all of a thread's chunks are requested before the first one is examined, so
+// the round costs one L2 round trip after the last row landed -- then add the rows in worker order -> s_final[64]
+__device__ __forceinline__ void gather_rows(const uint4 * rows, int workers, int chunks, unsigned epoch, float * s_rows /*[workers][chunks * 3]*/,
                                             float * s_red, float * s_final)
 {
     const int total = workers * chunks;
-    for(int i = threadIdx.x; i < total; i += kThreads)
+    for(int i0 = threadIdx.x; i0 < total; i0 += 4 * kThreads)
     {
-        const int w = i / chunks, c = i - w * chunks;
-        const uint4 * p = rows + (size_t)w * kRowChunks + c;
-        uint4 v;
-        do
+        uint4 v[4];
+#pragma unroll
+        for(int k = 0; k < 4; k++)
         {
-            v = ld_relaxed_v4(p);
-        } while(v.w != epoch);
-        float * d = s_rows + w * kRowFloats + 3 * c;
-        d[0] = __uint_as_float(v.x);
-        d[1] = __uint_as_float(v.y);
-        d[2] = __uint_as_float(v.z);
+            const int i = i0 + k * kThreads;
+            v[k] = (i < total) ? ld_relaxed_v4(rows + i) : make_uint4(0, 0, 0, epoch);
+        }
+#pragma unroll
+        for(int k = 0; k < 4; k++)
+        {
+            const int i = i0 + k * kThreads;
+            if(i < total)
+            {
+                while(v[k].w != epoch) v[k] = ld_relaxed_v4(rows + i);
+                float * d = s_rows + 3 * i;
+                d[0] = __uint_as_float(v[k].x);
+                d[1] = __uint_as_float(v[k].y);
+                d[2] = __uint_as_float(v[k].z);
+            }
+        }
     }
     __syncthreads();
     const int nfl = chunks * 3;
     const int slot = threadIdx.x & 63, part = threadIdx.x >> 6;
-    float s = 0.f;
-    if(slot < nfl)
-        for(int w = part; w < workers; w += kParts) s += s_rows[w * kRowFloats + slot];
-    s_red[part * 64 + slot] = s;
+    if(part < kParts)
+    {
+        float s = 0.f;
+        if(slot < nfl)
+            for(int w = part; w < workers; w += kParts) s += s_rows[w * nfl + slot];
+        s_red[part * 64 + slot] = s;
+    }
     __syncthreads();
     if(threadIdx.x < 64)
     {
@@ -203,133 +241,256 @@ __device__ __forceinline__ Mat33 mat_from(const float * m)
 }
 
 // ------------------------------------------------------------------------------------------------
-// solver state kept by thread 0 of CTA 0 across iterations
+// solver state: shared memory of CTA 0, touched by its thread 0 only (kept out of registers so that the
+// double-precision host step does not inflate the register needs of the per-pixel phases)
 // ------------------------------------------------------------------------------------------------
 struct Solver
 {
     double resultRt[16];
+    double last_S[27];                            // combined normal equations of the last solve (lastA / lastb)
+    double so3_R[9], so3_lastR[9];
     float Rcurr[9], tcurr[3];
+    float Rprev[9], tprev[3];                     // copies of the launch constants (indexed per lane by the warp solver)
+    float so3_R_lr[9], so3_lastError, so3_lastCount;
     float last_icp_error, last_icp_count, last_rgb_error, last_rgb_count, last_so3_error, last_so3_count;
     int so3_iterations, se3_iterations[3];
 };
 
-// RGBDOdometry.cpp:515-516, :541-583 -- runs in ONE thread (thread 0 of CTA 0).  Kept out of line so its
-// double-precision register needs do not inflate the per-pixel phases of the kernel.  s_final (shared memory):
-// ICP accumulator [0, 29) followed by the RGB accumulator [29, 58).
-__device__ __noinline__ void solve_se3(Solver & S, const float * s_final, double * last_S, int icp, int rgb, float icp_weight,
-                                       const float * Rprev, const float * tprev, int level)
+__device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(kFullMask, v, src); }
+__device__ __forceinline__ float shfl_f(float v, int src) { return __shfl_sync(kFullMask, v, src); }
+
+// RGBDOdometry.cpp:515-516, :541-583 -- the reference's host step after a Gauss-Newton evaluation, run by WARP 0 of
+// CTA 0 with the data spread over the lanes: the 27 entries of the combined normal equations live one per lane, so the
+// right-looking LDL^T, the exponential map, the SE(3) update and the pose composition are a few shuffles and ONE
+// double-precision operation per lane and step -- no arrays, no local memory, ~30 registers.  All in double like the
+// reference.  s_final (shared memory): ICP accumulator [0, 29) followed by the RGB accumulator [29, 58).
+__device__ __forceinline__ void warp_solve_se3(Solver * S, const float * s_final, int icp, int rgb, float icp_weight, int level,
+                                               long long * dbg = nullptr)
 {
-    if(icp)
-    {
-        S.last_icp_error = sqrtf(s_final[27]) / s_final[28]; // :515-516
-        S.last_icp_count = s_final[28];
-    }
-    double Sm[27];
+    long long tk[5] = {0, 0, 0, 0, 0};
+    if(dbg) tk[0] = clock64();
+    const int lane = threadIdx.x & 31;
+    __syncwarp();
+    // accumulator slot `lane` = entry (r, c), r <= c <= 6, of [A | b] (types.cuh:101-152 order); rs = slot of (r, r)
+    const int r = (lane >= 7) + (lane >= 13) + (lane >= 18) + (lane >= 22) + (lane >= 25);
+    const int rs = r * 7 - (r * (r - 1)) / 2;
+    const int c = lane - rs + r;
+    const bool live = lane < 27;
+
+    // NOTE: no divergent branch may precede the last shuffle of this function -- nvcc does not re-converge the two
+    // sides of an `if(lane < n)` here and every later shuffle then takes the WARPSYNC.COLLECTIVE slow path (~150 cycles
+    // each, measured).  Lane-dependent values are therefore selected arithmetically and all stores come last.
+    const int sl = live ? lane : 0;
     const double w = icp_weight;
-    if(icp && rgb) // :547-553  A = A_rgb + w^2 A_icp ; b = b_rgb + w b_icp
+    const double s_icp = (double)s_final[sl], s_rgb = (double)s_final[29 + sl];
+    double a = (icp && rgb) ? ((c == 6) ? (s_rgb + w * s_icp) : (s_rgb + (w * w) * s_icp)) : (icp ? s_icp : s_rgb); // :547-553
+    a = live ? a : 0.0;
+    const double a_in = a;
+
+    // x = A^-1 b (:552-564): unpivoted LDL^T of the symmetric positive definite system (hm::ldlt_solve_spd6_acc is the
+    // scalar statement of the same steps).  Pivot j: every trailing entry (r, c), r > j, subtracts l(r) a(j, c) with
+    // l(r) = a(j, r) / d(j); the right-hand side column c = 6 rides along, row j itself is scaled to L(., j).
+    double myinv = 0.0;
+#pragma unroll
+    for(int j = 0; j < 6; j++)
     {
+        const int pj = j * 7 - (j * (j - 1)) / 2;
+        const double dj = shfl_d(a, pj);
+        const double inv = (dj != 0.0) ? 1.0 / dj : 0.0;
+        const bool trail = live && r > j;
+        const double ajr = shfl_d(a, trail ? pj + (r - j) : lane);
+        const double ajc = shfl_d(a, trail ? pj + (c - j) : lane);
+        if(trail) a -= (ajr * inv) * ajc;
+        const bool row_j = live && r == j;
+        a = (row_j && c > j && c < 6) ? a * inv : a;
+        myinv = row_j ? inv : myinv;
+    }
+    if(dbg) tk[1] = clock64();
+    // back substitution, column oriented: lane (r, 6) holds w(r); x(i) is final once rows > i were applied
+    double wv = (live && c == 6) ? a * myinv : 0.0;
+    double x[6];
 #pragma unroll
-        for(int i = 0; i < 6; i++)
+    for(int i = 5; i >= 0; i--)
+    {
+        const int pi6 = i * 7 - (i * (i - 1)) / 2 + (6 - i);
+        const double xi = shfl_d(wv, pi6);
+        x[i] = xi;
+        const bool up = live && c == 6 && r < i;
+        const double lir = shfl_d(a, up ? rs + (i - r) : lane); // L(i, r) sits in slot (r, i)
+        if(up) wv -= lir * xi;
+    }
+
+    if(dbg) tk[2] = clock64();
+    // OdometryProvider.h:35-71 rodrigues(x[3:6]) -- element e = (er, ec) of the rotation on lane e < 9
+    const int e = lane < 9 ? lane : 0;
+    const int er = e / 3, ec = e - er * 3;
+    double rx = x[3], ry = x[4], rz = x[5];
+    const double theta = sqrt(rx * rx + ry * ry + rz * rz);
+    const double eye = (er == ec) ? 1.0 : 0.0;
+    double Re = eye;
+    if(theta >= 2.2204460492503131e-16)
+    {
+        double sn, cs;
+        sincos(theta, &sn, &cs);
+        const double c1 = 1. - cs;
+        const double itheta = theta ? 1. / theta : 0.;
+        rx *= itheta; ry *= itheta; rz *= itheta;
+        const double ra = (er == 0) ? rx : (er == 1) ? ry : rz;
+        const double rb = (ec == 0) ? rx : (ec == 1) ? ry : rz;
+        // r_x = [0 -rz ry; rz 0 -rx; -ry rx 0]
+        double sk = 0.0;
+        sk = (e == 1) ? -rz : sk; sk = (e == 2) ? ry : sk; sk = (e == 3) ? rz : sk;
+        sk = (e == 5) ? -rx : sk; sk = (e == 6) ? -ry : sk; sk = (e == 7) ? rx : sk;
+        Re = cs * eye + c1 * (ra * rb) + sn * sk;
+    }
+
+    if(dbg) tk[3] = clock64();
+    // OdometryProvider.h:73-93: resultRt = [R | x[0:3]] * resultRt; entry (r4, c4) of the 3x4 block on lane l < 12
+    const int l = lane < 12 ? lane : 0;
+    const int r4 = l >> 2, c4 = l & 3;
+    const double rt = S->resultRt[r4 * 4 + c4];
+    double N = shfl_d(Re, r4 * 3 + 0) * shfl_d(rt, 0 * 4 + c4);
+    N = fma(shfl_d(Re, r4 * 3 + 1), shfl_d(rt, 1 * 4 + c4), N);
+    N = fma(shfl_d(Re, r4 * 3 + 2), shfl_d(rt, 2 * 4 + c4), N);
+    N += (c4 == 3) ? ((r4 == 0) ? x[0] : (r4 == 1) ? x[1] : x[2]) : 0.0;
+
+    // :571-583: [Rcurr | tcurr] = [Rprev | tprev] * (float(resultRt))^-1 with the Isometry3f inverse (R^T, -R^T t), float
+    const float orf = (float)N; // oR(i, k) on lane i * 4 + k, ot(i) on lane i * 4 + 3
+    const float ot0 = shfl_f(orf, 3), ot1 = shfl_f(orf, 7), ot2 = shfl_f(orf, 11);
+    const int k3 = lane < 3 ? lane : 0;
+    const float itk = -(shfl_f(orf, 0 + k3) * ot0 + shfl_f(orf, 4 + k3) * ot1 + shfl_f(orf, 8 + k3) * ot2); // it(k) on lane k < 3
+    const float q0 = shfl_f(orf, ec * 4 + 0), q1 = shfl_f(orf, ec * 4 + 1), q2 = shfl_f(orf, ec * 4 + 2);  // iR(k, ec) = oR(ec, k)
+    const float Rc = S->Rprev[er * 3] * q0 + S->Rprev[er * 3 + 1] * q1 + S->Rprev[er * 3 + 2] * q2;
+    const float it0 = shfl_f(itk, 0), it1 = shfl_f(itk, 1), it2 = shfl_f(itk, 2);
+    const float tc = S->Rprev[k3 * 3] * it0 + S->Rprev[k3 * 3 + 1] * it1 + S->Rprev[k3 * 3 + 2] * it2 + S->tprev[k3];
+    if(dbg) tk[4] = clock64();
+    // ---- all shuffles done: stores ----
+    if(dbg && lane == 0)
+    {
+        dbg[8] = tk[1] - tk[0]; // combine + LDL^T
+        dbg[9] = tk[2] - tk[1]; // back substitution
+        dbg[5] = tk[3] - tk[2]; // exponential map
+        dbg[4] = tk[4] - tk[3]; // update + compose
+    }
+    if(live) S->last_S[lane] = a_in;
+    if(lane < 12) S->resultRt[r4 * 4 + c4] = N;
+    if(lane < 9) S->Rcurr[lane] = Rc;
+    if(lane < 3) S->tcurr[lane] = tc;
+    if(lane == 0)
+    {
+        S->se3_iterations[level]++;
+        if(icp)
         {
-#pragma unroll
-            for(int j = i; j < 7; j++)
-            {
-                const int k = hm::acc_index(i, j);
-                Sm[k] = (j == 6) ? ((double)s_final[29 + k] + w * (double)s_final[k]) : ((double)s_final[29 + k] + w * w * (double)s_final[k]);
-            }
+            S->last_icp_error = sqrtf(s_final[27]) / s_final[28]; // :515-516
+            S->last_icp_count = s_final[28];
         }
     }
-    else
-    {
-        const int o = icp ? 0 : 29;
-#pragma unroll
-        for(int k = 0; k < 27; k++) Sm[k] = (double)s_final[o + k];
-    }
-#pragma unroll
-    for(int k = 0; k < 27; k++) last_S[k] = Sm[k];
-    double result[6];
-    hm::ldlt_solve_spd6_acc(Sm, result);
-    S.se3_iterations[level]++;
-    hm::update_se3(S.resultRt, result);                           // :573
-    hm::compose_pose(S.resultRt, Rprev, tprev, S.Rcurr, S.tcurr); // :575-583
+    __syncwarp();
 }
 
-// :424-434 -- parameters of the next SE3 iteration (solver thread) -> payload[28]
-__device__ __noinline__ void make_se3_payload(const Solver & S, float * payload, int rgb, float fx, float fy, float cx, float cy,
-                                              const double * K_inv)
+// :480-481 -- pose of the next SE3 iteration (warp 0 of CTA 0) -> payload[0, 12) in shared memory
+__device__ __forceinline__ void warp_make_pose(const Solver * S, float * payload /*shared*/)
 {
-#pragma unroll
-    for(int i = 0; i < 9; i++) payload[i] = S.Rcurr[i];
-#pragma unroll
-    for(int i = 0; i < 3; i++) payload[9 + i] = S.tcurr[i];
-    if(rgb)
-    {
-        const double K[9] = {fx, 0, cx, 0, fy, cy, 0, 0, 1};
-        hm::rgb_warp_params(S.resultRt, K, K_inv, payload + 12, payload + 21);
-    }
-    else
-    {
-#pragma unroll
-        for(int i = 12; i < 24; i++) payload[i] = 0.f;
-    }
-#pragma unroll
-    for(int i = 24; i < kPayload; i++) payload[i] = 0.f;
+    const int lane = threadIdx.x & 31;
+    __syncwarp();
+    if(lane < 12) payload[lane] = (lane < 9) ? S->Rcurr[lane] : S->tcurr[lane - 9];
 }
 
-struct So3State
+// :424-434 -- photometric warp of the next SE3 iteration (warp 0 of CTA 0) -> payload[12, 24) in shared memory:
+// krkinv[9] kt[3] with Rt = resultRt^-1 (general affine inverse: adjugate / determinant),
+// krkinv = K R K^-1, kt = K t in double (hm::rgb_warp_params_sparse is the scalar statement)
+__device__ __forceinline__ void warp_make_rgb_params(const Solver * S, float * payload /*shared*/, float fxf, float fyf, float cxf, float cyf,
+                                                     const double * K_inv)
 {
-    double resultR[9], lastResultR[9];
-    float R_lr[9], lastError, lastCount;
-};
+    const int lane = threadIdx.x & 31;
+    __syncwarp();
+    // no divergent branch before the last shuffle (see warp_solve_se3): stores come last
+    const double fx = fxf, fy = fyf, cx = cxf, cy = cyf;
+    const int l = lane < 12 ? lane : 0;
+    const double m = S->resultRt[(l >> 2) * 4 + (l & 3)]; // entry (i, k) of the 3x4 block on lane i * 4 + k
+    const int e = lane < 9 ? lane : 0;
+    const int er = e / 3, ec = e - er * 3;
+    // inverse33: entry e of adj(M) = m[a] m[b] - m[c] m[d], 3x3 indices per entry packed four bits each
+    const unsigned long long ta = 0x013205124ull, tb = 0x467386578ull, tc = 0x104023215ull, td = 0x376568487ull;
+    const int ia = (int)((ta >> (4 * e)) & 15), ib = (int)((tb >> (4 * e)) & 15), ic = (int)((tc >> (4 * e)) & 15), id_ = (int)((td >> (4 * e)) & 15);
+    const double ma = shfl_d(m, (ia / 3) * 4 + ia % 3), mb = shfl_d(m, (ib / 3) * 4 + ib % 3);
+    const double mc = shfl_d(m, (ic / 3) * 4 + ic % 3), md = shfl_d(m, (id_ / 3) * 4 + id_ % 3);
+    const double cof = ma * mb - mc * md;
+    const double det = shfl_d(m, 0) * shfl_d(cof, 0) + shfl_d(m, 1) * shfl_d(cof, 3) + shfl_d(m, 2) * shfl_d(cof, 6);
+    const double Ai = cof * (1.0 / det);                   // R of Rt = resultRt^-1, entry e
+    const double t0 = shfl_d(m, 3), t1 = shfl_d(m, 7), t2 = shfl_d(m, 11);
+    const int k3 = lane < 3 ? lane : 0;
+    const double tinv = -(shfl_d(Ai, k3 * 3) * t0 + shfl_d(Ai, k3 * 3 + 1) * t1 + shfl_d(Ai, k3 * 3 + 2) * t2); // t of Rt, entry k3
+    // K R (rows: fx R0 + cx R2 ; fy R1 + cy R2 ; R2), then (K R) K^-1 with the structural zeros of K^-1 dropped
+    const double A2 = shfl_d(Ai, 6 + ec);
+    const double KR = (er == 0) ? fma(cx, A2, fx * Ai) : (er == 1) ? fma(cy, A2, fy * Ai) : Ai;
+    const double kr0 = shfl_d(KR, er * 3), kr1 = shfl_d(KR, er * 3 + 1);
+    const double KRK = (ec == 0) ? KR * K_inv[0] : (ec == 1) ? KR * K_inv[4] : fma(KR, K_inv[8], fma(kr1, K_inv[5], kr0 * K_inv[2]));
+    const double tz = shfl_d(tinv, 2);
+    const double kt = (k3 == 0) ? fma(cx, tz, fx * tinv) : (k3 == 1) ? fma(cy, tz, fy * tinv) : tinv;
+    if(lane < 9) payload[12 + lane] = (float)KRK;
+    if(lane < 3) payload[21 + lane] = (float)kt;
+    __syncwarp();
+}
 
 // :348-380 -- digest one so3Step evaluation; returns done
-__device__ __noinline__ int solve_so3(Solver & S, So3State & Z, const float * s_final, int it)
+__device__ __noinline__ int solve_so3(Solver * S, const float * s_final, int it)
 {
     int done = 0;
     float jtj[9], jtr[3], residual[2];
     hm::unpack_so3(s_final, jtj, jtr, residual);
-    S.so3_iterations++;
-    S.last_so3_error = sqrtf(residual[0]) / residual[1];                        // :348
-    S.last_so3_count = residual[1];
-    if(S.last_so3_error < Z.lastError && Z.lastCount == S.last_so3_count) done = 1; // :352
-    else if(S.last_so3_error > Z.lastError + 0.001)                              // :356
+    S->so3_iterations++;
+    float err = sqrtf(residual[0]) / residual[1];                              // :348
+    float cnt = residual[1];
+    if(err < S->so3_lastError && S->so3_lastCount == cnt) done = 1;            // :352
+    else if(err > S->so3_lastError + 0.001)                                     // :356
     {
-        S.last_so3_error = Z.lastError;
-        S.last_so3_count = Z.lastCount;
+        err = S->so3_lastError;
+        cnt = S->so3_lastCount;
 #pragma unroll
-        for(int i = 0; i < 9; i++) Z.resultR[i] = Z.lastResultR[i];
+        for(int i = 0; i < 9; i++) S->so3_R[i] = S->so3_lastR[i];
         done = 1;
     }
+    S->last_so3_error = err;
+    S->last_so3_count = cnt;
     if(!done)
     {
-        Z.lastError = S.last_so3_error;
-        Z.lastCount = S.last_so3_count;
+        S->so3_lastError = err;
+        S->so3_lastCount = cnt;
 #pragma unroll
-        for(int i = 0; i < 9; i++) Z.lastResultR[i] = Z.resultR[i];
+        for(int i = 0; i < 9; i++) S->so3_lastR[i] = S->so3_R[i];
         float delta[3];
         hm::ldlt_solve<float, 3>(jtj, jtr, delta);                               // :368
         const double dd[3] = {delta[0], delta[1], delta[2]};
         double rotUpdate[9];
         hm::rodrigues(dd, rotUpdate);
-        float ru[9];
+        float ru[9], rl[9];
 #pragma unroll
-        for(int i = 0; i < 9; i++) ru[i] = (float)rotUpdate[i];
-        hm::mul33(ru, Z.R_lr, Z.R_lr);                                            // :372
+        for(int i = 0; i < 9; i++)
+        {
+            ru[i] = (float)rotUpdate[i];
+            rl[i] = S->so3_R_lr[i];
+        }
+        hm::mul33(ru, rl, rl);                                                    // :372
 #pragma unroll
-        for(int i = 0; i < 9; i++) Z.resultR[i] = Z.R_lr[i];
+        for(int i = 0; i < 9; i++)
+        {
+            S->so3_R_lr[i] = rl[i];
+            S->so3_R[i] = rl[i];
+        }
         if(it == 10) done = 1; // ten evaluations made
     }
     return done;
 }
 
-// :318-329 -- homography K R K^-1 and K R for the next so3Step -> payload[28]
-__device__ __noinline__ void make_so3_payload(const So3State & Z, float * payload, int done, float fx, float fy, float cx, float cy,
-                                              const double * K_inv)
+// :318-329 -- homography K R K^-1 and K R for the next so3Step -> payload in shared memory
+__device__ __noinline__ void make_so3_params(const Solver * S, float * payload /*shared*/, int done, float fx, float fy, float cx, float cy,
+                                             const double * K_inv)
 {
-    const double K[9] = {fx, 0, cx, 0, fy, cy, 0, 0, 1};
-    double KR[9], H[9];
-    hm::mul33(K, Z.resultR, KR);
-    hm::mul33(KR, K_inv, H);
+    double R[9], KR[9], H[9];
+#pragma unroll
+    for(int i = 0; i < 9; i++) R[i] = S->so3_R[i];
+    hm::krk_sparse(R, fx, fy, cx, cy, K_inv, KR, H);
 #pragma unroll
     for(int i = 0; i < 9; i++)
     {
@@ -341,179 +502,10 @@ __device__ __noinline__ void make_so3_payload(const So3State & Z, float * payloa
     for(int i = 19; i < kPayload; i++) payload[i] = 0.f;
 }
 
-// bytes k+2 .. k+5 of the 12-byte run (a0 a1 a2) all 0xFF ?  (4x4 validity window of pixel k of a group)
-__device__ __forceinline__ bool window_ok(unsigned a0, unsigned a1, unsigned a2, int k)
-{
-    unsigned m;
-    if(k == 0) m = __byte_perm(a0, a1, 0x5432);
-    else if(k == 1) m = __byte_perm(a0, a1, 0x6543);
-    else if(k == 2) m = a1;
-    else m = __byte_perm(a1, a2, 0x4321);
-    return m == 0xffffffffu;
-}
 
-// ------------------------------------------------------------------------------------------------
-// per-unit pixel work.  A "unit" is PX consecutive pixels of one row handled by one thread (PX = 4 with
-// 128-bit loads at the fine levels, PX = 1 at the coarse ones so that the few pixels spread over many threads).
-// ------------------------------------------------------------------------------------------------
-template<int PX>
-__device__ __forceinline__ void rgb_assoc_unit(const LevelArgs & L, const RgbResParams & RP, int y, int x0, int4 * s_corr, int rec_base, int & cnt,
-                                               int & sig)
-{
-    const int cols = L.cols;
-    // the 16-pixel border of RGBResidual (:779-783); x0 is a multiple of PX so a 4-pixel unit is all in or all out
-    const bool in_region = y >= 16 && y < L.rows - 16 && x0 >= 16 && x0 < cols - 16;
-    short gxs[PX], gys[PX];
-    float d1s[PX];
-    unsigned ni4 = 0, m0 = 0, m1 = 0, m2 = 0;
-    const int xa = x0 & ~3; // aligned start of the 12-byte validity run [xa-4, xa+8)
-    if(in_region)
-    {
-        const size_t o = (size_t)y * cols + x0;
-        if constexpr(PX == 4)
-        {
-            const short4 gx4 = *reinterpret_cast<const short4 *>(L.dIdx + o);
-            const short4 gy4 = *reinterpret_cast<const short4 *>(L.dIdy + o);
-            const float4 d14 = *reinterpret_cast<const float4 *>(L.next_depth + o);
-            gxs[0] = gx4.x; gxs[1] = gx4.y; gxs[2] = gx4.z; gxs[3] = gx4.w;
-            gys[0] = gy4.x; gys[1] = gy4.y; gys[2] = gy4.z; gys[3] = gy4.w;
-            d1s[0] = d14.x; d1s[1] = d14.y; d1s[2] = d14.z; d1s[3] = d14.w;
-        }
-        else
-        {
-            gxs[0] = L.dIdx[o];
-            gys[0] = L.dIdy[o];
-            d1s[0] = L.next_depth[o];
-        }
-        // 4 rows x 12 bytes of the next image: non-zero masks, ANDed over the rows (:787-793)
-        m0 = m1 = m2 = 0xffffffffu;
-#pragma unroll
-        for(int r = -2; r < 2; r++)
-        {
-            const unsigned * wp = reinterpret_cast<const unsigned *>(L.next_image + (size_t)(y + r) * cols + xa - 4);
-            const unsigned w0 = __ldg(wp), w1 = __ldg(wp + 1), w2 = __ldg(wp + 2);
-            m0 &= __vcmpne4(w0, 0u);
-            m1 &= __vcmpne4(w1, 0u);
-            m2 &= __vcmpne4(w2, 0u);
-            if(r == 0) ni4 = w1;
-        }
-    }
-    int u0[PX], v0[PX];
-    float td1[PX];
-    bool ok[PX];
-#pragma unroll
-    for(int k = 0; k < PX; k++)
-    {
-        const int kk = (x0 + k) & 3;
-        ok[k] = in_region && rgb_gate(RP, x0 + k, y, gxs[k], gys[k], d1s[k]) && window_ok(m0, m1, m2, kk);
-        if(ok[k]) ok[k] = rgb_warp(RP, x0 + k, y, d1s[k], u0[k], v0[k], td1[k]);
-    }
-    float d0s[PX];
-    unsigned ls[PX];
-#pragma unroll
-    for(int k = 0; k < PX; k++)
-    {
-        if(ok[k])
-        {
-            const size_t q = (size_t)v0[k] * cols + u0[k];
-            d0s[k] = __ldg(L.last_depth + q);
-            ls[k] = __ldg(L.last_image + q);
-        }
-    }
-#pragma unroll
-    for(int k = 0; k < PX; k++)
-    {
-        const int kk = (x0 + k) & 3;
-        const bool good = ok[k] && rgb_accept(RP, td1[k], d0s[k], (uint8_t)ls[k]);
-        int4 rec;
-        rec.x = -1;
-        rec.y = rec.z = rec.w = 0;
-        if(good)
-        {
-            const float diff = static_cast<float>((ni4 >> (8 * kk)) & 0xffu) - static_cast<float>(ls[k]); // reduce.cu:827
-            rec.x = (u0[k] & 0xffff) | (v0[k] << 16);
-            rec.y = __float_as_int(diff);
-            rec.z = __float_as_int(d0s[k]);
-            rec.w = ((int)gxs[k] & 0xffff) | ((int)gys[k] << 16);
-            cnt += 1;
-            sig += (int)(diff * diff); // reduce.cu:830
-        }
-        s_corr[(rec_base + k) * kThreads + threadIdx.x] = rec;
-    }
-}
-
-template<int PX>
-__device__ __forceinline__ void icp_unit(const LevelArgs & L, const IcpParams & IP, int y, int x0, float * accI)
-{
-    const int cols = L.cols;
-    const size_t plane = (size_t)L.rows * cols;
-    const size_t o = (size_t)y * cols + x0;
-    float vx[PX], vy[PX], vz[PX], nx[PX], ny[PX], nz[PX];
-    if constexpr(PX == 4)
-    {
-        const float4 a = *reinterpret_cast<const float4 *>(L.vc + o);
-        const float4 b = *reinterpret_cast<const float4 *>(L.vc + plane + o);
-        const float4 c = *reinterpret_cast<const float4 *>(L.vc + 2 * plane + o);
-        const float4 d = *reinterpret_cast<const float4 *>(L.nc + o);
-        const float4 e = *reinterpret_cast<const float4 *>(L.nc + plane + o);
-        const float4 f = *reinterpret_cast<const float4 *>(L.nc + 2 * plane + o);
-        vx[0] = a.x; vx[1] = a.y; vx[2] = a.z; vx[3] = a.w;
-        vy[0] = b.x; vy[1] = b.y; vy[2] = b.z; vy[3] = b.w;
-        vz[0] = c.x; vz[1] = c.y; vz[2] = c.z; vz[3] = c.w;
-        nx[0] = d.x; nx[1] = d.y; nx[2] = d.z; nx[3] = d.w;
-        ny[0] = e.x; ny[1] = e.y; ny[2] = e.z; ny[3] = e.w;
-        nz[0] = f.x; nz[1] = f.y; nz[2] = f.z; nz[3] = f.w;
-    }
-    else
-    {
-        vx[0] = L.vc[o]; vy[0] = L.vc[plane + o]; vz[0] = L.vc[2 * plane + o];
-        nx[0] = L.nc[o]; ny[0] = L.nc[plane + o]; nz[0] = L.nc[2 * plane + o];
-    }
-    float3 vg[PX], vp[PX], np[PX];
-    int ux[PX], uy[PX];
-    bool in1[PX];
-#pragma unroll
-    for(int k = 0; k < PX; k++) in1[k] = icp_project(IP, make_float3(vx[k], vy[k], vz[k]), vg[k], ux[k], uy[k]);
-#pragma unroll
-    for(int k = 0; k < PX; k++)
-    {
-        if(in1[k])
-        {
-            const size_t q = (size_t)uy[k] * cols + ux[k];
-            vp[k].x = __ldg(L.vp + q); vp[k].y = __ldg(L.vp + plane + q); vp[k].z = __ldg(L.vp + 2 * plane + q);
-            np[k].x = __ldg(L.np + q); np[k].y = __ldg(L.np + plane + q); np[k].z = __ldg(L.np + 2 * plane + q);
-        }
-    }
-#pragma unroll
-    for(int k = 0; k < PX; k++)
-    {
-        float row[7];
-        if(in1[k] && icp_finish(IP, vg[k], make_float3(nx[k], ny[k], nz[k]), vp[k], np[k], row)) accumulate_se3(accI, row);
-    }
-}
-
-template<int PX>
-__device__ __forceinline__ void rgb_rows_unit(const RgbStepParams & SP, const int4 * s_corr, int rec_base, float * accR)
-{
-#pragma unroll
-    for(int k = 0; k < PX; k++)
-    {
-        const int4 rec = s_corr[(rec_base + k) * kThreads + threadIdx.x];
-        if(rec.x != -1)
-        {
-            const int pu = rec.x & 0xffff, pv = rec.x >> 16;
-            const float Z = __int_as_float(rec.z);
-            const float3 cp = project_point(pu, pv, Z, SP.inv_fx, SP.inv_fy, SP.cx, SP.cy);
-            float row[7];
-            rgb_row(SP, __int_as_float(rec.y), cp.x, cp.y, cp.z, (short)(rec.w & 0xffff), (short)(rec.w >> 16), row);
-            accumulate_se3(accR, row);
-        }
-    }
-}
-
-// Units are dealt to the worker CTAs in 32-unit chunks, round-robin, so that image regions with no work (the
-// photometric border, depth holes) are spread evenly: chunk c -> worker c % W, handled by warp (c / W) % kWarps
-// in pass (c / W) / kWarps.
+// Pixels are dealt to the worker CTAs in 32-pixel chunks (one coalesced warp load), round-robin, so that image
+// regions with no work (the photometric border, depth holes) are spread evenly and every CTA owns the same number
+// of pixels +-32: chunk c -> worker c % W, handled by warp (c / W) % kWarps in pass (c / W) / kWarps.
 struct UnitIter
 {
     int units, W, worker, lane, warp;
@@ -531,48 +523,278 @@ struct UnitIter
     }
 };
 
-__global__ void __launch_bounds__(kThreads, 1) k_track(const TrackArgs A)
+// ------------------------------------------------------------------------------------------------
+// photometric candidates of a worker CTA (shared memory, structure of arrays)
+//   c0  x | y << 12 | I_next(x,y) << 24        c1  dIdx & 0xffff | dIdy << 16        c2  nextDepth(x,y)
+//   r0  u | v << 12 | I_last(u,v) << 24  or kNoMatch                                 r1  lastDepth(u,v)
+// ------------------------------------------------------------------------------------------------
+struct CandStore
 {
-    extern __shared__ int4 s_dyn[];             // workers: correspondence records; CTA 0: gathered rows
+    unsigned * c0, * c1;
+    float * c2;
+    unsigned * r0;
+    float * r1;
+};
+
+// Level start: the iteration-invariant gates of RGBResidual::getProducts (reduce.cu:779-811) for this CTA's pixels,
+// survivors compacted in (pass, warp, lane) order.  Returns the candidate count (uniform over the CTA).
+__device__ __forceinline__ int compact_candidates(const LevelArgs & L, const RgbResParams & RP, const UnitIter & U, int passes, const CandStore & C,
+                                                  int * s_wtot /*[2][kWarps]*/)
+{
+    const int cols = L.cols;
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    int base = 0;
+    for(int p = 0; p < passes; p++)
+    {
+        const int u = U.unit(p);
+        unsigned w0 = 0, w1 = 0;
+        float d1 = 0.f;
+        bool keep = false;
+        if(u >= 0)
+        {
+            const int y = u / cols, x = u - y * cols;
+            // the 16-pixel border of RGBResidual (:779-783)
+            if(y >= 16 && y < L.rows - 16 && x >= 16 && x < cols - 16)
+            {
+                const size_t o = (size_t)y * cols + x;
+                const short gx = L.dIdx[o], gy = L.dIdy[o];
+                d1 = L.next_depth[o];
+                if(rgb_gate(RP, x, y, gx, gy, d1))
+                {
+                    // 4x4 window [y-2, y+2) x [x-2, x+2) of the next image must be non-zero (:787-793): per row the four
+                    // bytes are cut out of the aligned 8-byte run that holds them
+                    unsigned win = 0xffffffffu, inext = 0;
+#pragma unroll
+                    for(int r = -2; r < 2; r++)
+                    {
+                        const size_t lin = (size_t)(y + r) * cols + x - 2;
+                        const unsigned * wp = reinterpret_cast<const unsigned *>(L.next_image + (lin & ~(size_t)3));
+                        const unsigned bytes = __funnelshift_r(__ldg(wp), __ldg(wp + 1), 8 * (unsigned)(lin & 3));
+                        win &= __vcmpne4(bytes, 0u);
+                        if(r == 0) inext = (bytes >> 16) & 0xffu; // I_next(x, y)
+                    }
+                    keep = (win == 0xffffffffu);
+                    w0 = (unsigned)x | ((unsigned)y << 12) | (inext << 24);
+                    w1 = ((unsigned)gx & 0xffffu) | ((unsigned)gy << 16);
+                }
+            }
+        }
+        const unsigned ballot = __ballot_sync(kFullMask, keep);
+        int * wt = s_wtot + (p & 1) * kWarps;
+        if(lane == 0) wt[warp] = __popc(ballot);
+        __syncthreads();
+        int woff = 0, tot = 0;
+#pragma unroll
+        for(int w = 0; w < kWarps; w++)
+        {
+            const int v = wt[w];
+            tot += v;
+            woff += (w < (int)warp) ? v : 0;
+        }
+        if(keep)
+        {
+            const int pos = base + woff + __popc(ballot & ((1u << lane) - 1u));
+            C.c0[pos] = w0;
+            C.c1[pos] = w1;
+            C.c2[pos] = d1;
+        }
+        base += tot;
+    }
+    __syncthreads();
+    return base;
+}
+
+// phase A1: RGBResidual::getProducts past the gates (reduce.cu:813-830) for this thread's candidates; four
+// candidates at a time so that their gathers are in flight together
+__device__ __forceinline__ void rgb_assoc_cands(const LevelArgs & L, const RgbResParams & RP, const CandStore & C, int n_cand, int & cnt, int & sig)
+{
+    const int cols = L.cols;
+    for(int c0 = threadIdx.x; c0 < n_cand; c0 += 4 * kThreads)
+    {
+        int u0[4], v0[4];
+        float td1[4], d0s[4];
+        unsigned ls[4], inext[4];
+        bool ok[4];
+#pragma unroll
+        for(int k = 0; k < 4; k++)
+        {
+            const int c = c0 + k * kThreads;
+            ok[k] = false;
+            if(c < n_cand)
+            {
+                const unsigned w = C.c0[c];
+                inext[k] = w >> 24;
+                ok[k] = rgb_warp(RP, (int)(w & 0xfffu), (int)((w >> 12) & 0xfffu), C.c2[c], u0[k], v0[k], td1[k]);
+            }
+        }
+#pragma unroll
+        for(int k = 0; k < 4; k++)
+        {
+            if(ok[k])
+            {
+                const size_t q = (size_t)v0[k] * cols + u0[k];
+                d0s[k] = __ldg(L.last_depth + q);
+                ls[k] = __ldg(L.last_image + q);
+            }
+        }
+#pragma unroll
+        for(int k = 0; k < 4; k++)
+        {
+            const int c = c0 + k * kThreads;
+            if(c < n_cand)
+            {
+                unsigned rec = kNoMatch;
+                if(ok[k] && rgb_accept(RP, td1[k], d0s[k], (uint8_t)ls[k]))
+                {
+                    const float diff = static_cast<float>(inext[k]) - static_cast<float>(ls[k]); // reduce.cu:827
+                    rec = (unsigned)u0[k] | ((unsigned)v0[k] << 12) | (ls[k] << 24);
+                    C.r1[c] = d0s[k];
+                    cnt += 1;
+                    sig += (int)(diff * diff); // reduce.cu:830
+                }
+                C.r0[c] = rec;
+            }
+        }
+    }
+}
+
+// phase B: RGBReduction::getProducts (reduce.cu:512-595) for this thread's matched candidates
+__device__ __forceinline__ bool rgb_rows_cands(const RgbStepParams & SP, const CandStore & C, int n_cand, float * accR)
+{
+    bool any = false;
+    for(int c = threadIdx.x; c < n_cand; c += kThreads)
+    {
+        const unsigned rec = C.r0[c];
+        if(rec != kNoMatch)
+        {
+            const unsigned w = C.c0[c], g = C.c1[c];
+            const float Z = C.r1[c];
+            const float diff = static_cast<float>(w >> 24) - static_cast<float>(rec >> 24);
+            const float3 cp = project_point((int)(rec & 0xfffu), (int)((rec >> 12) & 0xfffu), Z, SP.inv_fx, SP.inv_fy, SP.cx, SP.cy);
+            float row[7];
+            rgb_row(SP, diff, cp.x, cp.y, cp.z, (short)(g & 0xffffu), (short)(g >> 16), row);
+            accumulate_se3(accR, row);
+            any = true;
+        }
+    }
+    return any;
+}
+
+// phase A2: ICPReduction (reduce.cu:285-347) for up to B of this thread's pixels (passes p0 .. p0 + B): all the
+// coalesced loads first, then the projections, then all the gathers, then the products
+template<int B>
+__device__ __forceinline__ bool icp_batch(const LevelArgs & L, const IcpParams & IP, const UnitIter & U, int p0, int passes, float * accI)
+{
+    const int cols = L.cols;
+    const size_t plane = (size_t)L.rows * cols;
+    float3 v[B], n[B];
+    bool in1[B];
+    bool any = false;
+#pragma unroll
+    for(int k = 0; k < B; k++)
+    {
+        const int u = (p0 + k < passes) ? U.unit(p0 + k) : -1;
+        in1[k] = u >= 0;
+        if(in1[k])
+        {
+            v[k].x = L.vc[u]; v[k].y = L.vc[plane + u]; v[k].z = L.vc[2 * plane + u];
+            n[k].x = L.nc[u]; n[k].y = L.nc[plane + u]; n[k].z = L.nc[2 * plane + u];
+            any = true;
+        }
+    }
+    float3 vg[B], vp[B], np[B];
+    int ux[B], uy[B];
+#pragma unroll
+    for(int k = 0; k < B; k++)
+        if(in1[k]) in1[k] = icp_project(IP, v[k], vg[k], ux[k], uy[k]);
+#pragma unroll
+    for(int k = 0; k < B; k++)
+    {
+        if(in1[k])
+        {
+            const size_t q = (size_t)uy[k] * cols + ux[k];
+            vp[k].x = __ldg(L.vp + q); vp[k].y = __ldg(L.vp + plane + q); vp[k].z = __ldg(L.vp + 2 * plane + q);
+            np[k].x = __ldg(L.np + q); np[k].y = __ldg(L.np + plane + q); np[k].z = __ldg(L.np + 2 * plane + q);
+        }
+    }
+#pragma unroll
+    for(int k = 0; k < B; k++)
+    {
+        float row[7];
+        if(in1[k] && icp_finish(IP, vg[k], n[k], vp[k], np[k], row)) accumulate_se3(accI, row);
+    }
+    return any;
+}
+
+// RGBDOdometry.cpp:461-462 from the barrier-B sums (the precedence quirk of :461 is kept)
+__device__ __forceinline__ void sigma_from_sums(int sigma, int rgbSize, float & sigmaVal, float & rgbError)
+{
+    sigmaVal = (float)sqrt((double)((((float)sigma / (float)rgbSize) == 0) ? 1 : rgbSize));
+    rgbError = (float)(sqrt((double)sigma) / (double)(rgbSize == 0 ? 1 : rgbSize));
+}
+
+template<bool TIMING>
+__global__ void __launch_bounds__(kThreads, 1) k_track(const __grid_constant__ TrackArgs A)
+{
+    extern __shared__ int4 s_dyn[];             // workers: candidates + match records; CTA 0: gathered rows
     __shared__ float s_red[kWarps * 64];
     __shared__ float s_final[64];
-    __shared__ float s_par[kPayload];
-    __shared__ int s_cnt, s_sig;
+    __shared__ float s_par[2][kPayload];
+    __shared__ float s_sigma[3];                // sigmaVal, rgbError, (float)rgbSize of the current iteration
     __shared__ int s_wcnt[kWarps], s_wsig[kWarps];
+    __shared__ int s_wtot[2 * kWarps];
+    __shared__ int s_flag;
+    __shared__ Solver s_solver;
 
-    TrackCtl * ctl = A.ctl;
+    const uint4 * my_par = A.par + (size_t)((blockIdx.x == 0 ? 0 : blockIdx.x - 1) % kReplicas) * kReplicaStride;
     const unsigned grid = gridDim.x;
     const int W = (int)grid - 1;                // worker CTAs (blockIdx 1 .. grid-1); CTA 0 only gathers and solves
     const bool is_solver_cta = (blockIdx.x == 0);
     const bool is_solver = is_solver_cta && threadIdx.x == 0;
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    uint4 * my_row = A.rows + (size_t)(blockIdx.x == 0 ? 0 : blockIdx.x - 1) * kRowChunks;
-    int4 * s_corr = s_dyn;
+    const int widx = is_solver_cta ? 0 : (int)blockIdx.x - 1;
     float * s_rows = reinterpret_cast<float *>(s_dyn);
+    CandStore C;
+    {
+        unsigned * base = reinterpret_cast<unsigned *>(s_dyn);
+        const int cap = A.cand_cap;
+        C.c0 = base;
+        C.c1 = base + cap;
+        C.c2 = reinterpret_cast<float *>(base + 2 * cap);
+        C.r0 = base + 3 * cap;
+        C.r1 = reinterpret_cast<float *>(base + 4 * cap);
+    }
+    Solver * S = &s_solver;
 
     // epochs, tracked identically by every thread of the grid
     unsigned rel = A.epoch_base; // parameter publications
     unsigned arr = A.epoch_base; // row rounds
 
-    Solver S;
     if(is_solver)
     {
 #pragma unroll
-        for(int i = 0; i < 16; i++) S.resultRt[i] = (i % 5 == 0) ? 1.0 : 0.0;
+        for(int i = 0; i < 16; i++) S->resultRt[i] = (i % 5 == 0) ? 1.0 : 0.0;
 #pragma unroll
-        for(int i = 0; i < 9; i++) S.Rcurr[i] = A.Rprev[i];
+        for(int i = 0; i < 9; i++) S->Rcurr[i] = A.Rprev[i];
 #pragma unroll
-        for(int i = 0; i < 3; i++) S.tcurr[i] = A.tprev[i];
-        S.last_icp_error = A.prev_icp_error; S.last_icp_count = A.prev_icp_count;
-        S.last_so3_error = A.prev_so3_error; S.last_so3_count = A.prev_so3_count;
-        S.last_rgb_error = A.prev_rgb_error; S.last_rgb_count = A.prev_rgb_count;
-        S.so3_iterations = 0;
-        S.se3_iterations[0] = S.se3_iterations[1] = S.se3_iterations[2] = 0;
+        for(int i = 0; i < 3; i++) S->tcurr[i] = A.tprev[i];
+#pragma unroll
+        for(int i = 0; i < 9; i++) S->Rprev[i] = A.Rprev[i];
+#pragma unroll
+        for(int i = 0; i < 3; i++) S->tprev[i] = A.tprev[i];
+        S->last_icp_error = A.prev_icp_error; S->last_icp_count = A.prev_icp_count;
+        S->last_so3_error = A.prev_so3_error; S->last_so3_count = A.prev_so3_count;
+        S->last_rgb_error = A.prev_rgb_error; S->last_rgb_count = A.prev_rgb_count;
+        S->so3_iterations = 0;
+        S->se3_iterations[0] = S->se3_iterations[1] = S->se3_iterations[2] = 0;
     }
 
     int dbg_it = 0;
     auto stamp = [&](int k) {
-        if(A.dbg && threadIdx.x == 0 && dbg_it < kMaxIters) A.dbg[((size_t)blockIdx.x * kMaxIters + dbg_it) * kDbgStamps + k] = clock64();
+        if constexpr(TIMING)
+        {
+            if(threadIdx.x == 0 && dbg_it < kMaxIters) A.dbg[((size_t)blockIdx.x * kMaxIters + dbg_it) * kDbgStamps + k] = clock64();
+        }
     };
 
     // ============================================================================================
@@ -585,38 +807,47 @@ __global__ void __launch_bounds__(kThreads, 1) k_track(const TrackArgs A)
         P.rows = L.rows;
         P.cols = L.cols;
         P.kinv = mat_from(A.so3_kinv);
-        So3State Z; // solver-private loop state
         if(is_solver)
         {
 #pragma unroll
-            for(int i = 0; i < 9; i++) { Z.resultR[i] = Z.lastResultR[i] = (i % 4 == 0) ? 1.0 : 0.0; Z.R_lr[i] = (i % 4 == 0) ? 1.f : 0.f; }
-            Z.lastError = FLT_MAX / 2;
-            Z.lastCount = FLT_MAX / 2;
+            for(int i = 0; i < 9; i++)
+            {
+                S->so3_R[i] = S->so3_lastR[i] = (i % 4 == 0) ? 1.0 : 0.0;
+                S->so3_R_lr[i] = (i % 4 == 0) ? 1.f : 0.f;
+            }
+            S->so3_lastError = FLT_MAX / 2;
+            S->so3_lastCount = FLT_MAX / 2;
         }
-        UnitIter U{L.rows * L.cols, W, (int)blockIdx.x - 1, (int)lane, (int)warp};
+        UnitIter U{L.rows * L.cols, W, widx, (int)lane, (int)warp};
         const int passes = U.passes();
 
         for(int it = 0; it <= 10; it++)
         {
-            // ---- CTA 0: digest the previous evaluation (:348-380), publish the next homography ----
+            bool done;
+            ++rel;
             if(is_solver_cta)
             {
+                // ---- CTA 0: digest the previous evaluation (:348-380), publish the next homography ----
                 if(it > 0) gather_rows(A.rows, W, kSo3Chunks, arr, s_rows, s_red, s_final);
                 if(is_solver)
                 {
-                    int done = 0;
-                    if(it > 0) done = solve_so3(S, Z, s_final, it);
-                    float payload[kPayload];
-                    make_so3_payload(Z, payload, done, L.fx, L.fy, L.cx, L.cy, L.K_inv);
-                    publish_line(ctl->line, payload, rel + 1);
+                    int d = 0;
+                    if(it > 0) d = solve_so3(S, s_final, it);
+                    make_so3_params(S, s_par[rel & 1u], d, L.fx, L.fy, L.cx, L.cy, L.K_inv);
+                    s_flag = d;
                 }
+                __syncthreads();
+                if(warp == 0) warp_publish(A.par, s_par[rel & 1u], 0, kLineChunks, rel);
+                done = s_flag != 0;
             }
-            ++rel;
-            wait_line(ctl->line, rel, s_par);
-            const bool done = s_par[18] != 0.f;
-            P.image_basis = mat_from(s_par);
-            P.krlr = mat_from(s_par + 9);
-            __syncthreads(); // s_par is rewritten by the next wait_line
+            else
+            {
+                float * par = s_par[rel & 1u];
+                wait_chunks(my_par, 0, kLineChunks, rel, par);
+                done = par[18] != 0.f;
+                P.image_basis = mat_from(par);
+                P.krlr = mat_from(par + 9);
+            }
             if(done) break;
             ++arr;
             if(is_solver_cta) continue;
@@ -646,7 +877,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_track(const TrackArgs A)
                 s_final[threadIdx.x] = (threadIdx.x < 11) ? s : 0.f;
             }
             __syncthreads();
-            publish_row(my_row, s_final, kSo3Chunks, arr);
+            publish_row(A.rows + (size_t)widx * kSo3Chunks, s_final, kSo3Chunks, arr);
         }
         if(is_solver)
         {
@@ -654,7 +885,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_track(const TrackArgs A)
             for(int x = 0; x < 3; x++)
             {
 #pragma unroll
-                for(int y = 0; y < 3; y++) S.resultRt[x * 4 + y] = Z.resultR[x * 3 + y]; // :394-403
+                for(int y = 0; y < 3; y++) S->resultRt[x * 4 + y] = S->so3_R[x * 3 + y]; // :394-403
             }
         }
     }
@@ -677,7 +908,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_track(const TrackArgs A)
     auto solve_pending = [&]() {
         gather_rows(A.rows, W, kRowChunks, arr, s_rows, s_red, s_final);
         stamp(2);
-        if(is_solver) solve_se3(S, s_final, ctl->last_S, A.icp, A.rgb, A.icp_weight, A.Rprev, A.tprev, pending_level);
+        if(warp == 0)
+            warp_solve_se3(S, s_final, A.icp, A.rgb, A.icp_weight, pending_level,
+                           (TIMING && dbg_it < kMaxIters) ? A.dbg + (size_t)dbg_it * kDbgStamps : nullptr);
         stamp(3);
     };
 
@@ -698,11 +931,16 @@ __global__ void __launch_bounds__(kThreads, 1) k_track(const TrackArgs A)
         SP.fx = L.fx; SP.fy = L.fy; SP.inv_fx = L.inv_fx; SP.inv_fy = L.inv_fy; SP.cx = L.cx; SP.cy = L.cy;
         SP.sobel_scale = A.sobel_scale;
         SP.sigma = 0.f;
-        const int cols = L.cols;
-        const int px = L.px;
-        const int upr = cols / px; // units per row
-        UnitIter U{upr * L.rows, W, (int)blockIdx.x - 1, (int)lane, (int)warp};
+        UnitIter U{L.rows * L.cols, W, widx, (int)lane, (int)warp};
         const int passes = U.passes();
+
+        // ---- workers, level start: candidate list of this CTA (overlaps the solve of the previous level) ----
+        int n_cand = 0;
+        if(!is_solver_cta && A.rgb)
+        {
+            __syncthreads(); // every thread is done with the previous level's records
+            n_cand = compact_candidates(L, RP, U, passes, C, s_wtot);
+        }
 
         float lastRGBError = FLT_MAX;      // every thread tracks it for the uniform rgb_only break (:464)
         bool first_of_level = true;
@@ -712,54 +950,67 @@ __global__ void __launch_bounds__(kThreads, 1) k_track(const TrackArgs A)
             const int cnt_slot = it_global++; // one barrier-B word per started iteration (also when it breaks)
             dbg_it = cnt_slot;
             stamp(0);
-            // ---- CTA 0: finish the previous iteration, publish this one's parameters (:424-434, :480-481) ----
+            ++rel;
+            // ---- CTA 0: finish the previous iteration; publish this one's pose (:480-481) at once and the photometric
+            //      warp (:424-434) when it is ready -- the workers run their first ICP pixels in between ----
+            // ICP passes done before the photometric association (EF_TRACK_ICP_SPLIT: measured slower at 640x480 -- two
+            // short batches cost more L2 round trips than the hidden parameter latency saves -- so off by default)
+            const int split = (kIcpSplit && A.icp && A.rgb && passes >= 4) ? passes / 2 : 0;
+            float accI[32];
+#pragma unroll
+            for(int i = 0; i < 32; i++) accI[i] = 0.f;
+            bool anyI = false;
             if(is_solver_cta)
             {
                 if(pending) solve_pending();
-                if(is_solver)
+                if(is_solver && first_of_level) S->last_rgb_error = FLT_MAX; // :420
+                if(warp == 0)
                 {
-                    if(first_of_level) S.last_rgb_error = FLT_MAX; // :420
-                    float payload[kPayload];
-                    make_se3_payload(S, payload, A.rgb, L.fx, L.fy, L.cx, L.cy, L.K_inv);
-                    stamp(1);
-                    publish_line(ctl->line, payload, rel + 1);
+                    float * par = s_par[rel & 1u];
+                    warp_make_pose(S, par);
+                    warp_publish(A.par, par, 0, 4, rel);
+                    stamp(7);
+                    if(A.rgb)
+                    {
+                        warp_make_rgb_params(S, par, L.fx, L.fy, L.cx, L.cy, L.K_inv);
+                        warp_publish(A.par, par, 4, 4, rel);
+                    }
                 }
+                stamp(1);
+            }
+            else
+            {
+                float * par = s_par[rel & 1u];
+                if(split > 0)
+                {
+                    wait_chunks(my_par, 0, 4, rel, par);
+                    IP.Rcurr = mat_from(par);
+                    IP.tcurr = make_float3(par[9], par[10], par[11]);
+                    stamp(4);
+                    // ---- workers, phase A0: the first ICP pixels of every thread while CTA 0 computes the warp ----
+                    for(int p0 = 0; p0 < split; p0 += kIcpBatch) anyI |= icp_batch<kIcpBatch>(L, IP, U, p0, split, accI);
+                    wait_chunks(my_par, 4, 4, rel, par);
+                }
+                else
+                {
+                    wait_chunks(my_par, A.icp ? 0 : 4, (A.icp && A.rgb) ? 8 : 4, rel, par);
+                    IP.Rcurr = mat_from(par);
+                    IP.tcurr = make_float3(par[9], par[10], par[11]);
+                    stamp(4);
+                }
+                RP.krkinv = mat_from(par + 12);
+                RP.kt = make_float3(par[21], par[22], par[23]);
             }
             pending = false;
             first_of_level = false;
-            ++rel;
-            wait_line(ctl->line, rel, s_par);
-            IP.Rcurr = mat_from(s_par);
-            IP.tcurr = make_float3(s_par[9], s_par[10], s_par[11]);
-            RP.krkinv = mat_from(s_par + 12);
-            RP.kt = make_float3(s_par[21], s_par[22], s_par[23]);
-            __syncthreads(); // s_par is rewritten by the next wait_line
-            stamp(4);
 
-            int rgbSize = 0, sigma = 0;
-            unsigned long long * word = &ctl->bar_b[cnt_slot];
-
-            // ---- workers, phase A1: photometric association -> records in shared memory, then the barrier-B arrival
-            //      (arrivals | count << 8 | sigma << 32 in one 64-bit word; integer adds are exact in any order and
-            //      sigma wraps mod 2^32 in the top bits exactly like the reference's int sum) ----
+            // ---- workers, phase A1: photometric association of the candidates -> records in shared memory, then the
+            //      barrier-B arrival: this CTA's {count, sum diff^2} as one flagged chunk in its own slot (integer sums are
+            //      exact in any order and sigma wraps mod 2^32 exactly like the reference's int sum) ----
             if(!is_solver_cta && A.rgb)
             {
                 int cnt = 0, sig = 0;
-                for(int p = 0; p < passes; p++)
-                {
-                    const int u = U.unit(p);
-                    if(u >= 0)
-                    {
-                        const int y = u / upr, x0 = (u - y * upr) * px;
-                        if(px == 4) rgb_assoc_unit<4>(L, RP, y, x0, s_corr, p * 4, cnt, sig);
-                        else rgb_assoc_unit<1>(L, RP, y, x0, s_corr, p, cnt, sig);
-                    }
-                    else
-                    {
-                        for(int k = 0; k < px; k++) s_corr[(p * px + k) * kThreads + threadIdx.x] = make_int4(-1, 0, 0, 0);
-                    }
-                }
-                stamp(7);
+                rgb_assoc_cands(L, RP, C, n_cand, cnt, sig);
                 cnt = __reduce_add_sync(kFullMask, cnt);
                 sig = __reduce_add_sync(kFullMask, sig);
                 if(lane == 0) { s_wcnt[warp] = cnt; s_wsig[warp] = sig; }
@@ -769,76 +1020,96 @@ __global__ void __launch_bounds__(kThreads, 1) k_track(const TrackArgs A)
                     unsigned c = 0, s = 0;
 #pragma unroll
                     for(int w = 0; w < kWarps; w++) { c += (unsigned)s_wcnt[w]; s += (unsigned)s_wsig[w]; }
-                    atomicAdd(word, 1ull | ((unsigned long long)c << 8) | ((unsigned long long)s << 32));
+                    st_relaxed_v4(A.bslot + widx, make_uint4(c, s, 0u, rel));
                 }
             }
-            stamp(5);
+            if(!is_solver_cta) stamp(5);
 
-            // ---- workers, phase A2: ICP association + 29 sums (hides the barrier-B latency and the inter-CTA skew) ----
-            float accI[32];
-#pragma unroll
-            for(int i = 0; i < 32; i++) accI[i] = 0.f;
-            if(!is_solver_cta && A.icp)
-            {
-                for(int p = 0; p < passes; p++)
-                {
-                    const int u = U.unit(p);
-                    if(u >= 0)
-                    {
-                        const int y = u / upr, x0 = (u - y * upr) * px;
-                        if(px == 4) icp_unit<4>(L, IP, y, x0, accI);
-                        else icp_unit<1>(L, IP, y, x0, accI);
-                    }
-                }
-            }
+            // ---- workers, phase A2: the remaining ICP pixels (hides the barrier-B round trip and the inter-CTA skew) ----
             if(!is_solver_cta)
             {
                 float vi = 0.f;
-                if(A.icp) vi = warp_transpose_reduce32(accI);
+                if(A.icp)
+                {
+                    for(int p0 = split; p0 < passes; p0 += kIcpBatch) anyI |= icp_batch<kIcpBatch>(L, IP, U, p0, passes, accI);
+                    if(__any_sync(kFullMask, anyI)) vi = warp_transpose_reduce32(accI); // a warp without pixels contributes zeros
+                }
                 if(lane < 29) s_red[warp * 64 + lane] = vi;
                 stamp(8);
             }
 
-            // ---- barrier B: everybody (CTA 0 included, it needs the count for the statistics) reads the word ----
+            // ---- barrier B: CTA 0 (idle while the workers compute) collects the arrivals, one per thread, adds them and
+            //      hands every worker the robust-weight scale (:461-462) in its own inbox; the workers get there after their
+            //      ICP phase ----
             bool level_break = false;
             if(A.rgb)
             {
-                if(threadIdx.x == 0)
+                if(is_solver_cta)
                 {
-                    unsigned long long v;
-                    do
+                    int c = 0, sg = 0;
+                    for(int w = threadIdx.x; w < W; w += kThreads)
                     {
-                        v = ld_relaxed64(word);
-                    } while((int)(v & 0xffull) < W);
-                    s_cnt = (int)((v >> 8) & 0xffffffull);
-                    s_sig = (int)(unsigned)(v >> 32);
+                        uint4 v;
+                        do
+                        {
+                            v = ld_relaxed_v4(A.bslot + w);
+                        } while(v.w != rel);
+                        c += (int)v.x;
+                        sg += (int)v.y;
+                    }
+                    c = __reduce_add_sync(kFullMask, c);
+                    sg = __reduce_add_sync(kFullMask, sg);
+                    if(lane == 0) { s_wcnt[warp] = c; s_wsig[warp] = sg; }
+                    __syncthreads();
+                    if(threadIdx.x == 0)
+                    {
+                        unsigned cc = 0, ss = 0;
+#pragma unroll
+                        for(int w = 0; w < kWarps; w++) { cc += (unsigned)s_wcnt[w]; ss += (unsigned)s_wsig[w]; }
+                        float sigmaVal, rgbError;
+                        sigma_from_sums((int)ss, (int)cc, sigmaVal, rgbError); // :461-462
+                        s_sigma[0] = sigmaVal;
+                        s_sigma[1] = rgbError;
+                        s_sigma[2] = (float)(int)cc;
+                    }
+                    __syncthreads();
+                    for(int w = threadIdx.x; w < W; w += kThreads)
+                        st_relaxed_v4(A.bres + w, make_uint4(__float_as_uint(s_sigma[0]), __float_as_uint(s_sigma[1]), __float_as_uint(s_sigma[2]), rel));
                 }
-                __syncthreads();
-                rgbSize = s_cnt;
-                sigma = s_sig;
+                else
+                {
+                    if(threadIdx.x == 0)
+                    {
+                        uint4 v;
+                        do
+                        {
+                            v = ld_relaxed_v4(A.bres + widx);
+                        } while(v.w != rel);
+                        s_sigma[0] = __uint_as_float(v.x);
+                        s_sigma[1] = __uint_as_float(v.y);
+                        s_sigma[2] = __uint_as_float(v.z);
+                    }
+                    __syncthreads();
+                }
                 stamp(6);
-
-                // RGBDOdometry.cpp:461-475 (the precedence quirk of :461 is kept)
-                float sigmaVal = (float)sqrt((double)((((float)sigma / (float)rgbSize) == 0) ? 1 : rgbSize));
-                const float rgbError = (float)(sqrt((double)sigma) / (double)(rgbSize == 0 ? 1 : rgbSize));
+                const float rgbError = s_sigma[1];
                 if(A.rgb_only && rgbError > lastRGBError) level_break = true; // :464 (uniform across the grid)
                 if(!level_break)
                 {
                     lastRGBError = rgbError;
                     if(is_solver)
                     {
-                        S.last_rgb_error = rgbError;
-                        S.last_rgb_count = (float)rgbSize;
+                        S->last_rgb_error = rgbError; // :469-470
+                        S->last_rgb_count = s_sigma[2];
                     }
-                    if(A.rgb_only) sigmaVal = -1;
-                    SP.sigma = sigmaVal;
+                    SP.sigma = A.rgb_only ? -1.f : s_sigma[0]; // :472-475
                 }
             }
             else if(is_solver)
             {
                 // :461-470 run even without RGB: sigma = rgbSize = 0 -> rgbError 0, count 0
-                S.last_rgb_error = 0.f;
-                S.last_rgb_count = 0.f;
+                S->last_rgb_error = 0.f;
+                S->last_rgb_count = 0.f;
             }
             if(level_break) break; // no row outstanding: every CTA takes the same branch
 
@@ -848,20 +1119,16 @@ __global__ void __launch_bounds__(kThreads, 1) k_track(const TrackArgs A)
             if(is_solver_cta) continue;
 
             // ---- workers, phase B: photometric rows from the records in shared memory -> 29 more sums ----
-            float accR[32];
-#pragma unroll
-            for(int i = 0; i < 32; i++) accR[i] = 0.f;
-            if(A.rgb)
-            {
-                for(int p = 0; p < passes; p++)
-                {
-                    if(px == 4) rgb_rows_unit<4>(SP, s_corr, p * 4, accR);
-                    else rgb_rows_unit<1>(SP, s_corr, p, accR);
-                }
-            }
             {
                 float vr = 0.f;
-                if(A.rgb) vr = warp_transpose_reduce32(accR);
+                if(A.rgb)
+                {
+                    float accR[32];
+#pragma unroll
+                    for(int i = 0; i < 32; i++) accR[i] = 0.f;
+                    const bool any = rgb_rows_cands(SP, C, n_cand, accR);
+                    if(__any_sync(kFullMask, any)) vr = warp_transpose_reduce32(accR);
+                }
                 if(lane < 29) s_red[warp * 64 + 29 + lane] = vr;
                 __syncthreads();
                 if(threadIdx.x < kRowFloats)
@@ -875,7 +1142,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_track(const TrackArgs A)
                     s_final[threadIdx.x] = sum;
                 }
                 __syncthreads();
-                publish_row(my_row, s_final, kRowChunks, arr);
+                publish_row(A.rows + (size_t)widx * kRowChunks, s_final, kRowChunks, arr);
                 stamp(9);
             }
         }
@@ -891,7 +1158,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_track(const TrackArgs A)
         if(!is_solver_cta)
         {
             __syncthreads();
-            publish_row(my_row, s_final, kSo3Chunks, arr);
+            publish_row(A.rows + (size_t)widx * kSo3Chunks, s_final, kSo3Chunks, arr);
         }
     }
     if(is_solver_cta)
@@ -901,29 +1168,34 @@ __global__ void __launch_bounds__(kThreads, 1) k_track(const TrackArgs A)
     }
     if(is_solver)
     {
+        float Rc[9], tc[3];
+#pragma unroll
+        for(int i = 0; i < 9; i++) Rc[i] = S->Rcurr[i];
+#pragma unroll
+        for(int i = 0; i < 3; i++) tc[i] = S->tcurr[i];
         if(A.rgb)
         {
-            const float d[3] = {S.tcurr[0] - A.tprev[0], S.tcurr[1] - A.tprev[1], S.tcurr[2] - A.tprev[2]};
+            const float d[3] = {tc[0] - A.tprev[0], tc[1] - A.tprev[1], tc[2] - A.tprev[2]};
             if(sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]) > 0.3)
             {
 #pragma unroll
-                for(int i = 0; i < 9; i++) S.Rcurr[i] = A.Rprev[i];
+                for(int i = 0; i < 9; i++) Rc[i] = A.Rprev[i];
 #pragma unroll
-                for(int i = 0; i < 3; i++) S.tcurr[i] = A.tprev[i];
+                for(int i = 0; i < 3; i++) tc[i] = A.tprev[i];
             }
         }
         TrackOutput * out = A.out;
 #pragma unroll
-        for(int i = 0; i < 3; i++) out->trans[i] = S.tcurr[i];
+        for(int i = 0; i < 3; i++) out->trans[i] = tc[i];
 #pragma unroll
-        for(int i = 0; i < 9; i++) out->rot[i] = S.Rcurr[i];
-        out->st.last_icp_error = S.last_icp_error; out->st.last_icp_count = S.last_icp_count;
-        out->st.last_rgb_error = S.last_rgb_error; out->st.last_rgb_count = S.last_rgb_count;
-        out->st.last_so3_error = S.last_so3_error; out->st.last_so3_count = S.last_so3_count;
-        out->st.so3_iterations = S.so3_iterations;
+        for(int i = 0; i < 9; i++) out->rot[i] = Rc[i];
+        out->st.last_icp_error = S->last_icp_error; out->st.last_icp_count = S->last_icp_count;
+        out->st.last_rgb_error = S->last_rgb_error; out->st.last_rgb_count = S->last_rgb_count;
+        out->st.last_so3_error = S->last_so3_error; out->st.last_so3_count = S->last_so3_count;
+        out->st.so3_iterations = S->so3_iterations;
 #pragma unroll
-        for(int i = 0; i < 3; i++) out->st.se3_iterations[i] = S.se3_iterations[i];
-        if(S.se3_iterations[0] + S.se3_iterations[1] + S.se3_iterations[2] > 0)
+        for(int i = 0; i < 3; i++) out->st.se3_iterations[i] = S->se3_iterations[i];
+        if(S->se3_iterations[0] + S->se3_iterations[1] + S->se3_iterations[2] > 0)
         {
             // lastA / lastb of the last solve (reduce.cu:475-486 unpack order)
 #pragma unroll
@@ -932,7 +1204,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_track(const TrackArgs A)
 #pragma unroll
                 for(int j = i; j < 7; j++)
                 {
-                    const double v = ctl->last_S[hm::acc_index(i, j)];
+                    const double v = S->last_S[hm::acc_index(i, j)];
                     if(j == 6) out->st.last_b[i] = v;
                     else out->st.last_A[j * 6 + i] = out->st.last_A[i * 6 + j] = v;
                 }
@@ -942,8 +1214,6 @@ __global__ void __launch_bounds__(kThreads, 1) k_track(const TrackArgs A)
         else
             out->status = 2; // no solve ran: lastA / lastb keep their previous values (host side)
         __threadfence_system();
-        // every worker has published its last row and touches the control block no more
-        for(int i = 0; i < kMaxIters; i++) ctl->bar_b[i] = 0ull;
     }
 }
 
@@ -955,11 +1225,11 @@ struct DeviceTrack
     long long * dbg_host;
     int dbg_grid;
     long long dbg_n;
-    TrackCtl * ctl;
+    uint4 * par, * bslot, * bres;
     uint4 * rows;
     TrackOutput * out; // pinned
     int grid;
-    int px[kNumPyrs];
+    int cand_cap;
     size_t smem_bytes;
     unsigned launch_seq;
 };
@@ -973,23 +1243,21 @@ int device_track_configure(ef_tracker * t, int grid)
 {
     DeviceTrack * d = static_cast<DeviceTrack *>(t->track_state);
     if(!d) return EF_ERR_BAD_STATE;
-    const int max_grid = t->num_sms < 255 ? t->num_sms : 255; // arrivals live in 8 bits of the barrier-B word
+    const int max_grid = t->num_sms < kMaxGrid ? t->num_sms : kMaxGrid; // arrivals live in 8 bits of the barrier-B word
     if(grid <= 0 || grid > max_grid) grid = max_grid;
     if(grid < 2) grid = 2;
     d->grid = grid;
     const int W = d->grid - 1;
-    int max_records = 1;
+    int max_cand = 1;
     for(int i = 0; i < kNumPyrs; i++)
     {
         const int npix = t->dims[i].rows * t->dims[i].cols;
-        const int px = ((npix + W - 1) / W > kThreads && (t->dims[i].cols % 4) == 0) ? 4 : 1;
-        d->px[i] = px;
-        const int chunks = (npix / px + 31) / 32;
+        const int chunks = (npix + 31) / 32;
         const int per_worker = (chunks + W - 1) / W;
-        const int passes = (per_worker + kWarps - 1) / kWarps;
-        if(passes * px > max_records) max_records = passes * px;
+        if(per_worker * 32 > max_cand) max_cand = per_worker * 32;
     }
-    d->smem_bytes = (size_t)max_records * kThreads * sizeof(int4);
+    d->cand_cap = max_cand;
+    d->smem_bytes = (size_t)max_cand * kCandBytes;
     const size_t rows_smem = (size_t)W * kRowFloats * sizeof(float);
     if(rows_smem > d->smem_bytes) d->smem_bytes = rows_smem;
     return EF_OK;
@@ -1001,10 +1269,13 @@ int device_track_init(ef_tracker * t)
     memset(d, 0, sizeof(*d));
     t->track_state = d;
     device_track_configure(t, 0);
-    const int max_grid = t->num_sms < 255 ? t->num_sms : 255;
+    const int max_grid = t->num_sms < kMaxGrid ? t->num_sms : kMaxGrid;
     d->launch_seq = 0;
-    cudaError_t e = cudaMalloc((void **)&d->ctl, sizeof(TrackCtl));
-    if(e == cudaSuccess) e = cudaMemsetAsync(d->ctl, 0, sizeof(TrackCtl), t->stream);
+    const size_t ctl_chunks = (size_t)kReplicas * kReplicaStride + 2 * (size_t)((max_grid + 7) & ~7);
+    cudaError_t e = cudaMalloc((void **)&d->par, ctl_chunks * sizeof(uint4));
+    if(e == cudaSuccess) e = cudaMemsetAsync(d->par, 0, ctl_chunks * sizeof(uint4), t->stream);
+    d->bslot = d->par ? d->par + (size_t)kReplicas * kReplicaStride : nullptr;
+    d->bres = d->par ? d->bslot + ((max_grid + 7) & ~7) : nullptr;
     if(e == cudaSuccess) e = cudaMalloc((void **)&d->rows, (size_t)max_grid * kRowChunks * sizeof(uint4));
     if(e == cudaSuccess) e = cudaMemsetAsync(d->rows, 0, (size_t)max_grid * kRowChunks * sizeof(uint4), t->stream);
     if(e == cudaSuccess) e = cudaHostAlloc((void **)&d->out, sizeof(TrackOutput), cudaHostAllocMapped);
@@ -1016,7 +1287,8 @@ int device_track_init(ef_tracker * t)
         e = cudaMalloc((void **)&d->dbg, sizeof(long long) * max_grid * kMaxIters * kDbgStamps);
         if(e == cudaSuccess) e = cudaMemsetAsync(d->dbg, 0, sizeof(long long) * max_grid * kMaxIters * kDbgStamps, t->stream);
     }
-    if(e == cudaSuccess) e = cudaFuncSetAttribute(k_track, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if(e == cudaSuccess) e = cudaFuncSetAttribute(k_track<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
+    if(e == cudaSuccess) e = cudaFuncSetAttribute(k_track<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
     if(e != cudaSuccess)
     {
         device_track_destroy(t);
@@ -1034,25 +1306,25 @@ void device_track_destroy(ef_tracker * t)
     {
         if(d->dbg_n > 0)
         {
-            // stamps (cycles of CTA 0's SM): 0 loop top | 1 arrivals seen | 2 final reduce | 3 solve | 4 params published
-            // + loaded | 5 phase A | 6 barrier B | 7 phase B | 8 reduce + arrive
+            // stamps (cycles of CTA 0's SM): 0 loop top | 2 rows gathered + added | 3 solved | 1 parameters published | 6 barrier B seen
             fprintf(stderr, "[ef_track timing] avg cycles of CTA 0 per SE3 iteration over %lld calls\n", d->dbg_n);
             for(int it = 0; it < kMaxIters; it++)
             {
                 const double * a = d->dbg_acc[it];
-                if(a[4] == 0) continue;
+                if(a[1] == 0) continue;
                 const double n = (double)d->dbg_n;
                 const bool first = a[2] == 0;
-                fprintf(stderr, "  it %2d: gather %7.0f solve %7.0f payload %7.0f publish+detect %7.0f | to-barB-seen %7.0f | total %8.0f\n", it,
-                        first ? 0.0 : (a[2] - a[0]) / n, first ? 0.0 : (a[3] - a[2]) / n, (a[1] - (first ? a[0] : a[3])) / n, (a[4] - a[1]) / n,
-                        (a[6] - a[4]) / n, (a[6] - a[0]) / n);
+                fprintf(stderr, "  it %2d: gather %7.0f solve %7.0f (ldlt %5.0f backsub %5.0f exp %5.0f update+compose %5.0f) params %7.0f publish %7.0f | to-barB-seen %7.0f | total %8.0f\n", it,
+                        first ? 0.0 : (a[2] - a[0]) / n, first ? 0.0 : (a[3] - a[2]) / n, a[8] / n, a[9] / n, a[5] / n, a[4] / n,
+                        (a[7] - (first ? a[0] : a[3])) / n, (a[1] - a[7]) / n,
+                        (a[6] - a[1]) / n, (a[6] - a[0]) / n);
             }
             // worker CTAs: params wait (0->4) | photometric association + CTA sync (4->5) | ICP + warp reduce (5->8) |
             // barrier-B wait (8->6) | photometric rows + CTA reduce + publish (6->9)
             fprintf(stderr, "[ef_track timing] worker CTAs, cycles mean/max over workers\n");
             for(int it = 0; it < kMaxIters; it++)
             {
-                if(d->dbg_acc[it][4] == 0) continue;
+                if(d->dbg_acc[it][1] == 0) continue;
                 const double n = (double)d->dbg_n;
                 const double * m = d->wrk_mean[it];
                 const double * x = d->wrk_max[it];
@@ -1063,7 +1335,7 @@ void device_track_destroy(ef_tracker * t)
         cudaFree(d->dbg);
         free(d->dbg_host);
     }
-    if(d->ctl) cudaFree(d->ctl);
+    if(d->par) cudaFree(d->par);
     if(d->rows) cudaFree(d->rows);
     if(d->out) cudaFreeHost(d->out);
     delete d;
@@ -1074,9 +1346,9 @@ int device_track_launch(ef_tracker * t, const float * trans, const float * rot, 
 {
     DeviceTrack * d = static_cast<DeviceTrack *>(t->track_state);
     if(!d) return EF_ERR_BAD_STATE;
-    if(d->smem_bytes > 200 * 1024 || (size_t)t->width * t->height >= (1u << 24) || t->width >= 32768 || t->height >= 32768)
+    if(d->smem_bytes > (size_t)kMaxDynSmem || (size_t)t->width * t->height >= (1u << 24) || t->width > 4094 || t->height > 4094)
     {
-        t->err = "image too large for the shared-memory correspondence store of EF_SOLVE_DEVICE";
+        t->err = "image too large for the shared-memory candidate store of EF_SOLVE_DEVICE";
         return EF_ERR_UNSUPPORTED;
     }
     TrackArgs A;
@@ -1095,7 +1367,6 @@ int device_track_launch(ef_tracker * t, const float * trans, const float * rot, 
         L.inv_fx = 1.0f / L.fx; L.inv_fy = 1.0f / L.fy;
         L.min_scale = (float)(pow(t->min_grad[i], 2.0) / pow(t->sobel_scale, 2.0)); // :442
         L.iterations = iterations[i];
-        L.px = d->px[i];
         const double K[9] = {L.fx, 0, L.cx, 0, L.fy, L.cy, 0, 0, 1};
         hm::inverse33(K, L.K_inv);
     }
@@ -1120,18 +1391,23 @@ int device_track_launch(ef_tracker * t, const float * trans, const float * rot, 
     if((d->launch_seq & 0xffffffu) == 0)
     {
         d->launch_seq = 1;
-        cudaMemsetAsync(d->rows, 0, (size_t)(t->num_sms < 255 ? t->num_sms : 255) * kRowChunks * sizeof(uint4), t->stream);
-        cudaMemsetAsync(d->ctl, 0, sizeof(TrackCtl), t->stream);
+        cudaMemsetAsync(d->rows, 0, (size_t)(t->num_sms < kMaxGrid ? t->num_sms : kMaxGrid) * kRowChunks * sizeof(uint4), t->stream);
+        const int mg = t->num_sms < kMaxGrid ? t->num_sms : kMaxGrid;
+        cudaMemsetAsync(d->par, 0, ((size_t)kReplicas * kReplicaStride + 2 * (size_t)((mg + 7) & ~7)) * sizeof(uint4), t->stream);
     }
     A.epoch_base = d->launch_seq << 8;
-    A.ctl = d->ctl;
+    A.par = d->par;
+    A.bslot = d->bslot;
+    A.bres = d->bres;
     A.rows = d->rows;
     A.out = d->out; // UVA: pinned + mapped host memory is addressable from the device
     A.dbg = d->dbg;
+    A.cand_cap = d->cand_cap;
 
     d->out->status = 0;
     void * args[] = {&A};
-    cudaError_t e = cudaLaunchCooperativeKernel((const void *)k_track, dim3(d->grid), dim3(kThreads), args, d->smem_bytes, t->stream);
+    const void * fn = d->dbg ? (const void *)k_track<true> : (const void *)k_track<false>;
+    cudaError_t e = cudaLaunchCooperativeKernel(fn, dim3(d->grid), dim3(kThreads), args, d->smem_bytes, t->stream);
     t->launches++;
     if(e != cudaSuccess)
     {
