@@ -230,10 +230,21 @@ def run_ours(args, rank, world, device):
     if not args.no_e2e:
         NH = max(1, args.inflight)
         sms = torch.cuda.get_device_properties(device).multi_processor_count
+        if mode == RO.EF_SOLVE_DEVICE:
+            # a handle's share of the SMs must be able to hold its photometric candidates in shared memory: halve the
+            # number of handles until the tracker accepts the split (1280x720 takes 2 handles, 640x480 takes 4)
+            while NH > 1:
+                try:
+                    tr.set_option(RO.EF_OPT_GRID_CTAS, sms // NH)
+                    break
+                except Exception:
+                    NH //= 2
+            if NH == 1:
+                tr.set_option(RO.EF_OPT_GRID_CTAS, 0)
         trs = [tr] + [make() for _ in range(NH - 1)]
         if mode == RO.EF_SOLVE_DEVICE:
-            for t_ in trs:
-                t_.set_option(RO.EF_OPT_GRID_CTAS, sms // NH)
+            for t_ in trs[1:]:
+                t_.set_option(RO.EF_OPT_GRID_CTAS, sms // NH if NH > 1 else 0)
         if so3:
             for t_ in trs[1:]:
                 t_.initFirstRGB(rgba[0])

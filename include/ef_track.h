@@ -72,6 +72,10 @@ typedef struct ef_track_stats
 #define EF_OPT_GRID_CTAS 5       /* device mode: CTAs (= SMs) the persistent tracker kernel occupies; 0 = all.  Lets k handles
                                     track k independent sequences concurrently on disjoint SMs of one GPU */
 
+#define EF_OPT_AUX_STREAMS 6     /* 0/1 (default 1): the pyramid builders that do not depend on each other (current-frame depth
+                                    pyramid, model RGB-D pyramid) run on two internal streams beside the handle's stream and
+                                    are joined before the solve; 0 = everything in order on the handle's stream */
+
 #define EF_SOLVE_HOST 0   /* one step kernel per operator call, 6x6 LDLT + pose update in double on the host,
                              exactly the reference's control flow (RGBDOdometry.cpp:405-585) */
 #define EF_SOLVE_DEVICE 1 /* one persistent cooperative kernel runs the SO(3) loop and all Gauss-Newton

@@ -93,6 +93,48 @@ EF_API float ef_default_angle_thresh(void) { return sinf(20.f * 3.14159254f / 18
 
 EF_API size_t ef_op_scratch_bytes(void) { return kScratchBytes; }
 
+static void destroy_aux(ef_tracker * t)
+{
+    for(int i = 0; i < 2; i++)
+    {
+        if(t->aux[i]) cudaStreamDestroy(t->aux[i]);
+        if(t->ev_join[i]) cudaEventDestroy(t->ev_join[i]);
+        t->aux[i] = nullptr;
+        t->ev_join[i] = nullptr;
+    }
+    if(t->ev_fork) cudaEventDestroy(t->ev_fork);
+    t->ev_fork = nullptr;
+}
+
+// Fork/join of independent builders.  The current-frame depth pyramid (aux 0) and the model RGB-D pyramid (aux 1)
+// depend on nothing the other builders of a frame produce except what is already enqueued on the handle's stream, so
+// they run on internal streams ordered AFTER the handle's stream position at the time of the call (fork) and every
+// consumer -- the solve, downloads, builders that write the same buffers -- first waits for them (join).
+static cudaStream_t fork_stream(ef_tracker * t, int which)
+{
+    if(!t->aux_streams) return t->stream;
+    if(cudaEventRecord(t->ev_fork, t->stream) != cudaSuccess || cudaStreamWaitEvent(t->aux[which], t->ev_fork, 0) != cudaSuccess) return t->stream;
+    return t->aux[which];
+}
+
+static void fork_done(ef_tracker * t, int which, cudaStream_t s)
+{
+    if(s == t->stream) return;
+    if(cudaEventRecord(t->ev_join[which], s) == cudaSuccess) t->aux_dirty[which] = true;
+    else cudaStreamSynchronize(s);
+}
+
+static int join_streams(ef_tracker * t)
+{
+    for(int i = 0; i < 2; i++)
+    {
+        if(!t->aux_dirty[i]) continue;
+        t->aux_dirty[i] = false;
+        EF_CUDA(t, cudaStreamWaitEvent(t->stream, t->ev_join[i], 0));
+    }
+    return EF_OK;
+}
+
 EF_API int ef_tracker_create(int width, int height, float cx, float cy, float fx, float fy, float dist_thresh, float angle_thresh, void * stream,
                              ef_tracker ** out)
 {
@@ -115,6 +157,10 @@ EF_API int ef_tracker_create(int width, int height, float cx, float cy, float fx
     t->fused_build = 1;
     t->launches = 0;
     t->grid_ctas = 0;
+    t->aux_streams = 1;
+    t->aux[0] = t->aux[1] = nullptr;
+    t->ev_fork = t->ev_join[0] = t->ev_join[1] = nullptr;
+    t->aux_dirty[0] = t->aux_dirty[1] = false;
     t->profile = 0;
     t->ev_begin = t->ev_end = nullptr;
     t->ev_pending = false;
@@ -137,6 +183,20 @@ EF_API int ef_tracker_create(int width, int height, float cx, float cy, float fx
         e = cudaStreamCreateWithFlags(&t->stream, cudaStreamNonBlocking);
         if(e != cudaSuccess) { delete t; return (int)e; }
         t->own_stream = true;
+    }
+
+    for(int i = 0; i < 2 && e == cudaSuccess; i++)
+    {
+        e = cudaStreamCreateWithFlags(&t->aux[i], cudaStreamNonBlocking);
+        if(e == cudaSuccess) e = cudaEventCreateWithFlags(&t->ev_join[i], cudaEventDisableTiming);
+    }
+    if(e == cudaSuccess) e = cudaEventCreateWithFlags(&t->ev_fork, cudaEventDisableTiming);
+    if(e != cudaSuccess)
+    {
+        destroy_aux(t);
+        if(t->own_stream) cudaStreamDestroy(t->stream);
+        delete t;
+        return (int)e;
     }
 
     // arena plan
@@ -166,6 +226,7 @@ EF_API int ef_tracker_create(int width, int height, float cx, float cy, float fx
     if(e != cudaSuccess)
     {
         if(t->arena) cudaFree(t->arena);
+        destroy_aux(t);
         if(t->own_stream) cudaStreamDestroy(t->stream);
         delete t;
         return (int)e;
@@ -195,6 +256,7 @@ EF_API int ef_tracker_create(int width, int height, float cx, float cy, float fx
     {
         cudaFree(t->arena);
         cudaFreeHost(t->h_result);
+        destroy_aux(t);
         if(t->own_stream) cudaStreamDestroy(t->stream);
         delete t;
         return rc;
@@ -208,7 +270,10 @@ EF_API int ef_tracker_create(int width, int height, float cx, float cy, float fx
 EF_API int ef_tracker_destroy(ef_tracker * t)
 {
     if(!t) return EF_OK;
+    for(int i = 0; i < 2; i++)
+        if(t->aux[i]) cudaStreamSynchronize(t->aux[i]);
     cudaStreamSynchronize(t->stream);
+    destroy_aux(t);
     if(t->ev_begin) cudaEventDestroy(t->ev_begin);
     if(t->ev_end) cudaEventDestroy(t->ev_end);
     device_track_destroy(t);
@@ -230,10 +295,20 @@ EF_API int ef_tracker_set_option(ef_tracker * t, int key, int value)
         return EF_OK;
     case EF_OPT_USE_GRAPH: t->use_graph = value ? 1 : 0; return EF_OK;
     case EF_OPT_FUSED_BUILD: t->fused_build = value ? 1 : 0; return EF_OK;
+    case EF_OPT_AUX_STREAMS:
+    {
+        const int rc = join_streams(t);
+        if(rc) return rc;
+        t->aux_streams = value ? 1 : 0;
+        return EF_OK;
+    }
     case EF_OPT_GRID_CTAS:
         if(t->launch_pending) return fail(t, EF_ERR_BAD_STATE, "a launch is pending");
-        t->grid_ctas = value;
-        return device_track_configure(t, value);
+    {
+        const int rc = device_track_configure(t, value);
+        if(rc == EF_OK) t->grid_ctas = value;
+        return rc;
+    }
     case EF_OPT_PROFILE:
         if(value && !t->ev_begin)
         {
@@ -256,6 +331,7 @@ EF_API int ef_tracker_get_option(ef_tracker * t, int key, int * value)
     case EF_OPT_FUSED_BUILD: *value = t->fused_build; return EF_OK;
     case EF_OPT_PROFILE: *value = t->profile; return EF_OK;
     case EF_OPT_GRID_CTAS: *value = t->grid_ctas; return EF_OK;
+    case EF_OPT_AUX_STREAMS: *value = t->aux_streams; return EF_OK;
     default: return EF_ERR_INVALID_ARGUMENT;
     }
 }
@@ -277,6 +353,8 @@ EF_API int ef_tracker_profile(ef_tracker * t, double * ms, long long * calls)
 EF_API int ef_tracker_synchronize(ef_tracker * t)
 {
     if(!t) return EF_ERR_INVALID_ARGUMENT;
+    const int rc = join_streams(t);
+    if(rc) return rc;
     EF_CUDA(t, cudaStreamSynchronize(t->stream));
     return EF_OK;
 }
@@ -288,10 +366,11 @@ EF_API int ef_tracker_synchronize(ef_tracker * t)
 EF_API int ef_init_icp_depth(ef_tracker * t, const uint16_t * d_depth, size_t pitch_bytes, float depth_cutoff)
 {
     if(!t || !d_depth) return EF_ERR_INVALID_ARGUMENT;
-    cudaStream_t s = t->stream;
     if(t->fused_build)
     {
-        // one launch per level: vertex map + normal map (+ dense copy of level 0) + bilateral pyrDown to the next level
+        // one launch per level: vertex map + normal map (+ dense copy of level 0) + bilateral pyrDown to the next level;
+        // nothing else a frame builds is read here, so the three launches go to an internal stream (aux 0)
+        cudaStream_t s = fork_stream(t, 0);
         for(int i = 0; i < kNumPyrs; ++i)
         {
             float fx, fy, cx, cy;
@@ -300,7 +379,13 @@ EF_API int ef_init_icp_depth(ef_tracker * t, const uint16_t * d_depth, size_t pi
                                             cy, depth_cutoff, t->vmap_curr[i], t->nmap_curr[i], i == 0 ? t->depth_tmp[0] : nullptr,
                                             i + 1 < kNumPyrs ? t->depth_tmp[i + 1] : nullptr, s));
         }
+        fork_done(t, 0, s);
         return EF_OK;
+    }
+    cudaStream_t s = t->stream;
+    {
+        const int rc = join_streams(t);
+        if(rc) return rc;
     }
     // level 0 is read in place from the caller's buffer (the reference copies the texture into depth_tmp[0])
     const size_t p0 = pitch_bytes ? pitch_bytes : (size_t)t->width * 2;
@@ -329,6 +414,11 @@ EF_API int ef_init_icp_depth(ef_tracker * t, const uint16_t * d_depth, size_t pi
 static int build_maps(ef_tracker * t, const float * d_v, const float * d_n, float ** vmaps, float ** nmaps, const float * R, const float * tv)
 {
     cudaStream_t s = t->stream;
+    {
+        // writes tmp_z (read by the forked model RGB-D builder) and possibly the maps the forked depth builder writes
+        const int rc = join_streams(t);
+        if(rc) return rc;
+    }
     if(t->fused_build)
     {
         EF_LAUNCH(t, launch_build_maps(d_v, d_n, t->height, t->width, vmaps, nmaps, t->tmp_z, R, tv, s));
@@ -367,9 +457,8 @@ EF_API int ef_init_icp_model(ef_tracker * t, const float * d_v, const float * d_
 }
 
 // RGBDOdometry.cpp:208-235
-static int populate_rgbd(ef_tracker * t, const uint8_t * d_rgba, size_t pitch, float ** depths, uint8_t ** images)
+static int populate_rgbd(ef_tracker * t, const uint8_t * d_rgba, size_t pitch, float ** depths, uint8_t ** images, cudaStream_t s)
 {
-    cudaStream_t s = t->stream;
     if(t->fused_build)
     {
         EF_LAUNCH(t, launch_rgbd_level0(d_rgba, pitch, t->tmp_z, t->max_depth_rgb, t->height, t->width, images[0], depths[0], images[1], depths[1], s));
@@ -389,13 +478,17 @@ EF_API int ef_init_rgb(ef_tracker * t, const uint8_t * d_rgba, size_t pitch)
 {
     if(!t || !d_rgba) return EF_ERR_INVALID_ARGUMENT;
     t->deriv_valid = false;
-    return populate_rgbd(t, d_rgba, pitch, t->next_depth, t->next_image);
+    return populate_rgbd(t, d_rgba, pitch, t->next_depth, t->next_image, t->stream);
 }
 
 EF_API int ef_init_rgb_model(ef_tracker * t, const uint8_t * d_rgba, size_t pitch)
 {
     if(!t || !d_rgba) return EF_ERR_INVALID_ARGUMENT;
-    return populate_rgbd(t, d_rgba, pitch, t->last_depth, t->last_image);
+    // reads tmp_z (already enqueued on the handle's stream), writes only the "last" pyramids: internal stream (aux 1)
+    cudaStream_t s = t->fused_build ? fork_stream(t, 1) : t->stream;
+    const int rc = populate_rgbd(t, d_rgba, pitch, t->last_depth, t->last_image, s);
+    fork_done(t, 1, s);
+    return rc;
 }
 
 // RGBDOdometry.cpp:249-265
@@ -550,6 +643,10 @@ static int compute_derivatives(ef_tracker * t)
 static int track_host(ef_tracker * t, float * trans, float * rot, int rgb_only, float icp_weight, int pyramid, int fast_odom, int so3)
 {
     cudaStream_t s = t->stream;
+    {
+        const int rc = join_streams(t);
+        if(rc) return rc;
+    }
     const bool icp = !rgb_only && icp_weight > 0; // :275
     const bool rgb = rgb_only || icp_weight < 100; // :276
 
@@ -779,6 +876,10 @@ EF_API int ef_get_incremental_transformation_launch(ef_tracker * t, const float 
             const int rc = compute_derivatives(t);
             if(rc) return rc;
         }
+        {
+            const int rc = join_streams(t);
+            if(rc) return rc;
+        }
         if(t->profile) EF_CUDA(t, cudaEventRecord(t->ev_begin, t->stream));
         const int rc = device_track_launch(t, trans, rot, rgb_only, icp_weight, pyramid, fast_odom, so3);
         if(rc) return rc;
@@ -896,6 +997,10 @@ EF_API int ef_tracker_download(ef_tracker * t, const char * name, int level, voi
     else if(!strcmp(name, "depth_tmp")) { src = t->depth_tmp[level]; need = n * 2; }
     else return fail(t, EF_ERR_INVALID_ARGUMENT, "unknown buffer name");
     if(bytes < need) return fail(t, EF_ERR_INVALID_ARGUMENT, "destination too small");
+    {
+        const int rc = join_streams(t);
+        if(rc) return rc;
+    }
     EF_CUDA(t, cudaMemcpyAsync(dst, src, need, cudaMemcpyDeviceToHost, t->stream));
     EF_CUDA(t, cudaStreamSynchronize(t->stream));
     return EF_OK;

@@ -62,7 +62,7 @@ constexpr int kSo3Chunks = 4;    // SO3 rows carry 11 floats
 constexpr int kLineChunks = 8;   // the parameter line = 8 x (3 floats + flag) = 24 floats
 constexpr int kPayload = kLineChunks * 3;
 constexpr int kParts = kThreads / 64; // final cross-CTA sum: kParts x 64 slots
-constexpr int kMaxGrid = 255;    // arrivals live in 8 bits of the barrier-B word
+constexpr int kMaxGrid = 255;    // CTAs of one launch (sizes the control buffers)
 constexpr unsigned kNoMatch = 0xffffffffu;
 constexpr int kCandBytes = 20;   // 12-byte candidate + 8-byte match record
 constexpr int kMaxDynSmem = 200 * 1024;
@@ -1243,11 +1243,10 @@ int device_track_configure(ef_tracker * t, int grid)
 {
     DeviceTrack * d = static_cast<DeviceTrack *>(t->track_state);
     if(!d) return EF_ERR_BAD_STATE;
-    const int max_grid = t->num_sms < kMaxGrid ? t->num_sms : kMaxGrid; // arrivals live in 8 bits of the barrier-B word
+    const int max_grid = t->num_sms < kMaxGrid ? t->num_sms : kMaxGrid;
     if(grid <= 0 || grid > max_grid) grid = max_grid;
     if(grid < 2) grid = 2;
-    d->grid = grid;
-    const int W = d->grid - 1;
+    const int W = grid - 1;
     int max_cand = 1;
     for(int i = 0; i < kNumPyrs; i++)
     {
@@ -1256,10 +1255,18 @@ int device_track_configure(ef_tracker * t, int grid)
         const int per_worker = (chunks + W - 1) / W;
         if(per_worker * 32 > max_cand) max_cand = per_worker * 32;
     }
-    d->cand_cap = max_cand;
-    d->smem_bytes = (size_t)max_cand * kCandBytes;
+    size_t smem = (size_t)max_cand * kCandBytes;
     const size_t rows_smem = (size_t)W * kRowFloats * sizeof(float);
-    if(rows_smem > d->smem_bytes) d->smem_bytes = rows_smem;
+    if(rows_smem > smem) smem = rows_smem;
+    if(smem > (size_t)kMaxDynSmem && d->grid > 0)
+    {
+        // too few CTAs for this image: the photometric candidates of a CTA must fit its shared memory; keep the old grid
+        t->err = "EF_OPT_GRID_CTAS: too few CTAs for the shared-memory candidate store at this image size";
+        return EF_ERR_UNSUPPORTED;
+    }
+    d->grid = grid;
+    d->cand_cap = max_cand;
+    d->smem_bytes = smem;
     return EF_OK;
 }
 

@@ -41,6 +41,12 @@ struct ef_tracker
     int use_graph;
     int fused_build;
     int grid_ctas;   // EF_OPT_GRID_CTAS (0 = every SM)
+    int aux_streams; // EF_OPT_AUX_STREAMS
+
+    // internal fork/join streams for builders that are independent of each other (ef_api.cu: fork_stream / join_streams)
+    cudaStream_t aux[2];
+    cudaEvent_t ev_fork, ev_join[2];
+    bool aux_dirty[2];
 
     // one device arena, sliced
     void * arena;
