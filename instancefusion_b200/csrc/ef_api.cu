@@ -871,7 +871,10 @@ EF_API int ef_get_incremental_transformation_launch(ef_tracker * t, const float 
     t->pending.fast_odom = fast_odom; t->pending.so3 = so3;
     if(t->solve_mode == EF_SOLVE_DEVICE)
     {
-        if(rgb && !t->deriv_valid)
+        // computeDerivativeImages (RGBDOdometry.cpp:436-440) is fused into the tracker kernel: every worker CTA derives
+        // dIdx / dIdy of its own pixels while it builds its candidate list (device_track_launch reads !deriv_valid).
+        // Levels without iterations (pyramid = 0) keep the stand-alone kernel so that all three levels are valid afterwards.
+        if(rgb && !t->deriv_valid && !pyramid)
         {
             const int rc = compute_derivatives(t);
             if(rc) return rc;
@@ -883,6 +886,7 @@ EF_API int ef_get_incremental_transformation_launch(ef_tracker * t, const float 
         if(t->profile) EF_CUDA(t, cudaEventRecord(t->ev_begin, t->stream));
         const int rc = device_track_launch(t, trans, rot, rgb_only, icp_weight, pyramid, fast_odom, so3);
         if(rc) return rc;
+        if(rgb) t->deriv_valid = true;
         if(t->profile)
         {
             EF_CUDA(t, cudaEventRecord(t->ev_end, t->stream));

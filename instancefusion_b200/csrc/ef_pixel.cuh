@@ -114,6 +114,26 @@ __device__ __forceinline__ bool icp_finish(const IcpParams & P, const float3 & v
     return true;
 }
 
+// icp_finish without control flow: the row is always computed (garbage in, garbage out) and the verdict is returned,
+// so that the caller can interleave several pixels and zero the rows of rejected ones with selects.  Same expressions,
+// same bits as icp_finish for accepted pixels.
+__device__ __forceinline__ bool icp_finish_select(const IcpParams & P, const float3 & vcurr_g, const float3 & ncurr, const float3 & vprev_g,
+                                                  const float3 & nprev_g, float * row)
+{
+    const float3 ncurr_g = P.Rcurr * ncurr;
+    const float dist = norm3(vprev_g - vcurr_g);           // :317
+    const float sine = norm3(cross3(ncurr_g, nprev_g));    // :318
+    const bool ok = sine < P.angle_thresh && dist <= P.dist_thresh && !isnan(ncurr.x) && !isnan(nprev_g.x); // :324
+    const float3 s_cp = P.Rprev_inv * (vcurr_g - P.tprev); // :341-343
+    const float3 d_cp = P.Rprev_inv * (vprev_g - P.tprev);
+    const float3 n_cp = P.Rprev_inv * nprev_g;
+    const float3 c = cross3(s_cp, n_cp);
+    row[0] = n_cp.x; row[1] = n_cp.y; row[2] = n_cp.z;
+    row[3] = c.x; row[4] = c.y; row[5] = c.z;
+    row[6] = dot3(n_cp, s_cp - d_cp);                      // :347
+    return ok;
+}
+
 // both halves with the gather in between (stand-alone operator kernel)
 __device__ __forceinline__ bool icp_row(const IcpParams & P, const float3 & vcurr, const float3 & ncurr, const Map3 & vprev,
                                         const Map3 & nprev, float * row)

@@ -30,6 +30,7 @@
 #include <string.h>
 
 #include "ef_hostmath.h"
+#include "ef_image_px.cuh"
 #include "ef_kernels.h"
 #include "ef_pixel.cuh"
 #include "ef_reduce.cuh"
@@ -62,9 +63,11 @@ constexpr int kSo3Chunks = 4;    // SO3 rows carry 11 floats
 constexpr int kLineChunks = 8;   // the parameter line = 8 x (3 floats + flag) = 24 floats
 constexpr int kPayload = kLineChunks * 3;
 constexpr int kParts = kThreads / 64; // final cross-CTA sum: kParts x 64 slots
+constexpr int kGatherBatch = 12; // row chunks a CTA-0 thread requests before it examines the first (147 x 20 / 256 = 11.5)
 constexpr int kMaxGrid = 255;    // CTAs of one launch (sizes the control buffers)
 constexpr unsigned kNoMatch = 0xffffffffu;
 constexpr int kCandBytes = 20;   // 12-byte candidate + 8-byte match record
+constexpr int kIcpBytes = 24;    // current-frame vertex + normal of a pixel (icp_in_smem)
 constexpr int kMaxDynSmem = 200 * 1024;
 
 static_assert(kThreads % 32 == 0 && kThreads >= 128 && kThreads <= 1024, "EF_TRACK_THREADS");
@@ -74,7 +77,7 @@ struct LevelArgs
     const float * vc, * nc, * vp, * np;           // 3-plane maps, dense
     const float * last_depth, * next_depth;
     const uint8_t * last_image, * next_image;
-    const int16_t * dIdx, * dIdy;
+    int16_t * dIdx, * dIdy;                       // written here when TrackArgs::make_derivatives (computeDerivativeImages fused in)
     int rows, cols;
     float fx, fy, cx, cy;                         // level intrinsics
     float inv_fx, inv_fy;                         // host 1.0f / f (cudafuncs.cu:671)
@@ -114,6 +117,8 @@ struct TrackArgs
     float dist_thresh, angle_thresh, max_depth_delta, sobel_scale, icp_weight;
     int icp, rgb, rgb_only, so3;
     int cand_cap;                                 // capacity of the shared-memory candidate list
+    int make_derivatives;                         // dIdx / dIdy are not valid yet: compute them at level start
+    int icp_in_smem;                              // the CTA's current-frame vertices / normals fit shared memory beside the candidates
     float prev_icp_error, prev_icp_count, prev_so3_error, prev_so3_count, prev_rgb_error, prev_rgb_count;
     unsigned epoch_base;                          // launch_seq << 8
     uint4 * par;                                  // kReplicas parameter lines
@@ -187,27 +192,29 @@ __device__ __forceinline__ void gather_rows(const uint4 * rows, int workers, int
                                             float * s_red, float * s_final)
 {
     const int total = workers * chunks;
-    for(int i0 = threadIdx.x; i0 < total; i0 += 4 * kThreads)
+    for(int i0 = threadIdx.x; i0 < total; i0 += kGatherBatch * kThreads)
     {
-        uint4 v[4];
+        uint4 v[kGatherBatch];
+        unsigned todo = 0;
 #pragma unroll
-        for(int k = 0; k < 4; k++)
+        for(int k = 0; k < kGatherBatch; k++)
+            if(i0 + k * kThreads < total) todo |= 1u << k;
+        // rounds: every chunk still missing is requested again, all requests of a round in flight together
+        while(todo)
         {
-            const int i = i0 + k * kThreads;
-            v[k] = (i < total) ? ld_relaxed_v4(rows + i) : make_uint4(0, 0, 0, epoch);
-        }
 #pragma unroll
-        for(int k = 0; k < 4; k++)
-        {
-            const int i = i0 + k * kThreads;
-            if(i < total)
-            {
-                while(v[k].w != epoch) v[k] = ld_relaxed_v4(rows + i);
-                float * d = s_rows + 3 * i;
-                d[0] = __uint_as_float(v[k].x);
-                d[1] = __uint_as_float(v[k].y);
-                d[2] = __uint_as_float(v[k].z);
-            }
+            for(int k = 0; k < kGatherBatch; k++)
+                if(todo & (1u << k)) v[k] = ld_relaxed_v4(rows + i0 + k * kThreads);
+#pragma unroll
+            for(int k = 0; k < kGatherBatch; k++)
+                if((todo & (1u << k)) && v[k].w == epoch)
+                {
+                    todo &= ~(1u << k);
+                    float * d = s_rows + 3 * (i0 + k * kThreads);
+                    d[0] = __uint_as_float(v[k].x);
+                    d[1] = __uint_as_float(v[k].y);
+                    d[2] = __uint_as_float(v[k].z);
+                }
         }
     }
     __syncthreads();
@@ -538,6 +545,7 @@ struct CandStore
 
 // Level start: the iteration-invariant gates of RGBResidual::getProducts (reduce.cu:779-811) for this CTA's pixels,
 // survivors compacted in (pass, warp, lane) order.  Returns the candidate count (uniform over the CTA).
+template<bool DERIV>
 __device__ __forceinline__ int compact_candidates(const LevelArgs & L, const RgbResParams & RP, const UnitIter & U, int passes, const CandStore & C,
                                                   int * s_wtot /*[2][kWarps]*/)
 {
@@ -553,11 +561,25 @@ __device__ __forceinline__ int compact_candidates(const LevelArgs & L, const Rgb
         if(u >= 0)
         {
             const int y = u / cols, x = u - y * cols;
+            short gx = 0, gy = 0;
+            if constexpr(DERIV)
+            {
+                // computeDerivativeImages (cudafuncs.cu:583-639) fused in: this CTA's pixels of dIdx / dIdy, kept in global
+                // memory as well because they are an output of the call (ef_tracker_download) and input of host-solve mode
+                const uint8_t * img = L.next_image;
+                derivative_px([&](int j, int i) { return __ldg(img + (size_t)j * cols + i); }, L.rows, cols, x, y, gx, gy);
+                L.dIdx[u] = gx;
+                L.dIdy[u] = gy;
+            }
             // the 16-pixel border of RGBResidual (:779-783)
             if(y >= 16 && y < L.rows - 16 && x >= 16 && x < cols - 16)
             {
                 const size_t o = (size_t)y * cols + x;
-                const short gx = L.dIdx[o], gy = L.dIdy[o];
+                if constexpr(!DERIV)
+                {
+                    gx = L.dIdx[o];
+                    gy = L.dIdy[o];
+                }
                 d1 = L.next_depth[o];
                 if(rgb_gate(RP, x, y, gx, gy, d1))
                 {
@@ -604,86 +626,132 @@ __device__ __forceinline__ int compact_candidates(const LevelArgs & L, const Rgb
     return base;
 }
 
-// phase A1: RGBResidual::getProducts past the gates (reduce.cu:813-830) for this thread's candidates; four
-// candidates at a time so that their gathers are in flight together
-__device__ __forceinline__ void rgb_assoc_cands(const LevelArgs & L, const RgbResParams & RP, const CandStore & C, int n_cand, int & cnt, int & sig)
+// phase A1: RGBResidual::getProducts past the gates (reduce.cu:813-830) for B of this thread's candidates (rounds
+// j0 .. j0 + B of the CTA's list): no control flow, so the B candidates interleave and their gathers are in flight
+// together; a slot past the end of the list re-reads candidate 0 and stores nothing
+template<int B>
+__device__ __forceinline__ void rgb_assoc_batch(const LevelArgs & L, const RgbResParams & RP, const CandStore & C, int n_cand, int j0, int & cnt,
+                                                int & sig)
 {
     const int cols = L.cols;
-    for(int c0 = threadIdx.x; c0 < n_cand; c0 += 4 * kThreads)
+    int u0[B], v0[B];
+    float td1[B];
+    unsigned inext[B];
+    bool valid[B], ok[B];
+    size_t q[B];
+#pragma unroll
+    for(int k = 0; k < B; k++)
     {
-        int u0[4], v0[4];
-        float td1[4], d0s[4];
-        unsigned ls[4], inext[4];
-        bool ok[4];
+        const int c = threadIdx.x + (j0 + k) * kThreads;
+        valid[k] = c < n_cand;
+        const int cc = valid[k] ? c : 0;
+        const unsigned w = C.c0[cc];
+        inext[k] = w >> 24;
+        ok[k] = rgb_warp(RP, (int)(w & 0xfffu), (int)((w >> 12) & 0xfffu), C.c2[cc], u0[k], v0[k], td1[k]) && valid[k];
+        q[k] = ok[k] ? (size_t)v0[k] * cols + u0[k] : 0;
+    }
+    float d0s[B];
+    unsigned ls[B];
 #pragma unroll
-        for(int k = 0; k < 4; k++)
-        {
-            const int c = c0 + k * kThreads;
-            ok[k] = false;
-            if(c < n_cand)
-            {
-                const unsigned w = C.c0[c];
-                inext[k] = w >> 24;
-                ok[k] = rgb_warp(RP, (int)(w & 0xfffu), (int)((w >> 12) & 0xfffu), C.c2[c], u0[k], v0[k], td1[k]);
-            }
-        }
+    for(int k = 0; k < B; k++)
+    {
+        d0s[k] = __ldg(L.last_depth + q[k]);
+        ls[k] = __ldg(L.last_image + q[k]);
+    }
 #pragma unroll
-        for(int k = 0; k < 4; k++)
+    for(int k = 0; k < B; k++)
+    {
+        const int c = threadIdx.x + (j0 + k) * kThreads;
+        const bool good = ok[k] && rgb_accept(RP, td1[k], d0s[k], (uint8_t)ls[k]);
+        const float diff = static_cast<float>(inext[k]) - static_cast<float>(ls[k]); // reduce.cu:827
+        const unsigned rec = good ? ((unsigned)u0[k] | ((unsigned)v0[k] << 12) | (ls[k] << 24)) : kNoMatch;
+        if(valid[k])
         {
-            if(ok[k])
-            {
-                const size_t q = (size_t)v0[k] * cols + u0[k];
-                d0s[k] = __ldg(L.last_depth + q);
-                ls[k] = __ldg(L.last_image + q);
-            }
+            C.r0[c] = rec;
+            C.r1[c] = d0s[k];
         }
-#pragma unroll
-        for(int k = 0; k < 4; k++)
-        {
-            const int c = c0 + k * kThreads;
-            if(c < n_cand)
-            {
-                unsigned rec = kNoMatch;
-                if(ok[k] && rgb_accept(RP, td1[k], d0s[k], (uint8_t)ls[k]))
-                {
-                    const float diff = static_cast<float>(inext[k]) - static_cast<float>(ls[k]); // reduce.cu:827
-                    rec = (unsigned)u0[k] | ((unsigned)v0[k] << 12) | (ls[k] << 24);
-                    C.r1[c] = d0s[k];
-                    cnt += 1;
-                    sig += (int)(diff * diff); // reduce.cu:830
-                }
-                C.r0[c] = rec;
-            }
-        }
+        cnt += good ? 1 : 0;
+        sig += good ? (int)(diff * diff) : 0; // reduce.cu:830
     }
 }
 
-// phase B: RGBReduction::getProducts (reduce.cu:512-595) for this thread's matched candidates
-__device__ __forceinline__ bool rgb_rows_cands(const RgbStepParams & SP, const CandStore & C, int n_cand, float * accR)
+__device__ __forceinline__ void rgb_assoc_cands(const LevelArgs & L, const RgbResParams & RP, const CandStore & C, int n_cand, int & cnt, int & sig)
+{
+    const int rounds = (n_cand + kThreads - 1) / kThreads; // uniform over the CTA
+    int j = 0;
+    for(; j + 3 <= rounds; j += 3) rgb_assoc_batch<3>(L, RP, C, n_cand, j, cnt, sig);
+    if(rounds - j == 2) rgb_assoc_batch<2>(L, RP, C, n_cand, j, cnt, sig);
+    else if(rounds - j == 1) rgb_assoc_batch<1>(L, RP, C, n_cand, j, cnt, sig);
+}
+
+// phase B: RGBReduction::getProducts (reduce.cu:512-595) for B of this thread's candidates, again without control
+// flow: unmatched candidates contribute rows of exact zeros
+template<int B>
+__device__ __forceinline__ bool rgb_rows_batch(const RgbStepParams & SP, const CandStore & C, int n_cand, int j0, float * accR)
 {
     bool any = false;
-    for(int c = threadIdx.x; c < n_cand; c += kThreads)
+#pragma unroll
+    for(int k = 0; k < B; k++)
     {
-        const unsigned rec = C.r0[c];
-        if(rec != kNoMatch)
+        const int c = threadIdx.x + (j0 + k) * kThreads;
+        const int cc = c < n_cand ? c : 0;
+        const unsigned rec = C.r0[cc];
+        const bool good = c < n_cand && rec != kNoMatch;
+        const unsigned w = C.c0[cc], g = C.c1[cc];
+        const float Z = C.r1[cc];
+        const float diff = static_cast<float>(w >> 24) - static_cast<float>(rec >> 24);
+        const float3 cp = project_point((int)(rec & 0xfffu), (int)((rec >> 12) & 0xfffu), Z, SP.inv_fx, SP.inv_fy, SP.cx, SP.cy);
+        float row[7];
+        rgb_row(SP, diff, cp.x, cp.y, cp.z, (short)(g & 0xffffu), (short)(g >> 16), row);
+#pragma unroll
+        for(int i = 0; i < 7; i++) row[i] = good ? row[i] : 0.f;
+        int kk = 0;
+#pragma unroll
+        for(int i = 0; i < 6; i++)
         {
-            const unsigned w = C.c0[c], g = C.c1[c];
-            const float Z = C.r1[c];
-            const float diff = static_cast<float>(w >> 24) - static_cast<float>(rec >> 24);
-            const float3 cp = project_point((int)(rec & 0xfffu), (int)((rec >> 12) & 0xfffu), Z, SP.inv_fx, SP.inv_fy, SP.cx, SP.cy);
-            float row[7];
-            rgb_row(SP, diff, cp.x, cp.y, cp.z, (short)(g & 0xffffu), (short)(g >> 16), row);
-            accumulate_se3(accR, row);
-            any = true;
+#pragma unroll
+            for(int j = i; j < 7; j++) accR[kk++] += row[i] * row[j];
         }
+        accR[27] += row[6] * row[6];
+        accR[28] += good ? 1.0f : 0.f;
+        any |= good;
     }
     return any;
 }
 
+__device__ __forceinline__ bool rgb_rows_cands(const RgbStepParams & SP, const CandStore & C, int n_cand, float * accR)
+{
+    const int rounds = (n_cand + kThreads - 1) / kThreads;
+    bool any = false;
+    int j = 0;
+    for(; j + 3 <= rounds; j += 3) any |= rgb_rows_batch<3>(SP, C, n_cand, j, accR);
+    if(rounds - j == 2) any |= rgb_rows_batch<2>(SP, C, n_cand, j, accR);
+    else if(rounds - j == 1) any |= rgb_rows_batch<1>(SP, C, n_cand, j, accR);
+    return any;
+}
+
+// Level start: the current-frame vertex / normal of this CTA's pixels -> shared memory (they do not change over the
+// iterations of a level; 24 B per pixel, structure of arrays, slot = pass * kThreads + thread)
+__device__ __forceinline__ void stage_current_maps(const LevelArgs & L, const UnitIter & U, int passes, float * s_vn, int cap)
+{
+    const size_t plane = (size_t)L.rows * L.cols;
+    for(int p = 0; p < passes; p++)
+    {
+        const int u = U.unit(p);
+        if(u >= 0)
+        {
+            float * q = s_vn + p * kThreads + threadIdx.x;
+            q[0] = L.vc[u]; q[cap] = L.vc[plane + u]; q[2 * cap] = L.vc[2 * plane + u];
+            q[3 * cap] = L.nc[u]; q[4 * cap] = L.nc[plane + u]; q[5 * cap] = L.nc[2 * plane + u];
+        }
+    }
+}
+
 // phase A2: ICPReduction (reduce.cu:285-347) for up to B of this thread's pixels (passes p0 .. p0 + B): all the
 // coalesced loads first, then the projections, then all the gathers, then the products
-template<int B>
-__device__ __forceinline__ bool icp_batch(const LevelArgs & L, const IcpParams & IP, const UnitIter & U, int p0, int passes, float * accI)
+template<int B, bool SMEM>
+__device__ __forceinline__ bool icp_batch(const LevelArgs & L, const IcpParams & IP, const UnitIter & U, int p0, int passes, float * accI,
+                                          const float * s_vn, int cap)
 {
     const int cols = L.cols;
     const size_t plane = (size_t)L.rows * cols;
@@ -693,36 +761,74 @@ __device__ __forceinline__ bool icp_batch(const LevelArgs & L, const IcpParams &
 #pragma unroll
     for(int k = 0; k < B; k++)
     {
-        const int u = (p0 + k < passes) ? U.unit(p0 + k) : -1;
-        in1[k] = u >= 0;
-        if(in1[k])
+        const int uu = (p0 + k < passes) ? U.unit(p0 + k) : -1;
+        in1[k] = uu >= 0;
+        any |= in1[k];
+        const int u = in1[k] ? uu : 0;
+        if constexpr(SMEM)
+        {
+            // iteration-invariant: staged once per level (stage_current_maps), slot = pass * kThreads + thread
+            const float * sq = s_vn + (in1[k] ? (p0 + k) * kThreads + threadIdx.x : 0);
+            v[k].x = sq[0]; v[k].y = sq[cap]; v[k].z = sq[2 * cap];
+            n[k].x = sq[3 * cap]; n[k].y = sq[4 * cap]; n[k].z = sq[5 * cap];
+        }
+        else
         {
             v[k].x = L.vc[u]; v[k].y = L.vc[plane + u]; v[k].z = L.vc[2 * plane + u];
             n[k].x = L.nc[u]; n[k].y = L.nc[plane + u]; n[k].z = L.nc[2 * plane + u];
-            any = true;
         }
     }
+    // from here on no control flow: the B pixels interleave (two warps per scheduler need the instruction-level
+    // parallelism); rejected pixels gather pixel 0 and contribute rows of exact zeros
     float3 vg[B], vp[B], np[B];
-    int ux[B], uy[B];
-#pragma unroll
-    for(int k = 0; k < B; k++)
-        if(in1[k]) in1[k] = icp_project(IP, v[k], vg[k], ux[k], uy[k]);
+    size_t q[B];
 #pragma unroll
     for(int k = 0; k < B; k++)
     {
-        if(in1[k])
-        {
-            const size_t q = (size_t)uy[k] * cols + ux[k];
-            vp[k].x = __ldg(L.vp + q); vp[k].y = __ldg(L.vp + plane + q); vp[k].z = __ldg(L.vp + 2 * plane + q);
-            np[k].x = __ldg(L.np + q); np[k].y = __ldg(L.np + plane + q); np[k].z = __ldg(L.np + 2 * plane + q);
-        }
+        int ux, uy;
+        in1[k] = icp_project(IP, v[k], vg[k], ux, uy) && in1[k];
+        q[k] = in1[k] ? (size_t)uy * cols + ux : 0;
+    }
+#pragma unroll
+    for(int k = 0; k < B; k++)
+    {
+        vp[k].x = __ldg(L.vp + q[k]); vp[k].y = __ldg(L.vp + plane + q[k]); vp[k].z = __ldg(L.vp + 2 * plane + q[k]);
+        np[k].x = __ldg(L.np + q[k]); np[k].y = __ldg(L.np + plane + q[k]); np[k].z = __ldg(L.np + 2 * plane + q[k]);
     }
 #pragma unroll
     for(int k = 0; k < B; k++)
     {
         float row[7];
-        if(in1[k] && icp_finish(IP, vg[k], n[k], vp[k], np[k], row)) accumulate_se3(accI, row);
+        const bool ok = icp_finish_select(IP, vg[k], n[k], vp[k], np[k], row) && in1[k];
+#pragma unroll
+        for(int i = 0; i < 7; i++) row[i] = ok ? row[i] : 0.f;
+        int kk = 0;
+#pragma unroll
+        for(int i = 0; i < 6; i++)
+        {
+#pragma unroll
+            for(int j = i; j < 7; j++) accI[kk++] += row[i] * row[j];
+        }
+        accI[27] += row[6] * row[6];
+        accI[28] += ok ? 1.0f : 0.f;
     }
+    return any;
+}
+
+// all ICP passes [p_begin, p_end) of this thread in batches of kIcpBatch; the remainder runs in a batch of its own
+// size so that no empty pixel slot is computed (p_begin, p_end are uniform over the CTA)
+template<bool SMEM>
+__device__ __forceinline__ bool icp_passes(const LevelArgs & L, const IcpParams & IP, const UnitIter & U, int p_begin, int p_end, float * accI,
+                                           const float * s_vn, int cap)
+{
+    static_assert(kIcpBatch >= 1 && kIcpBatch <= 4, "EF_TRACK_ICP_BATCH");
+    bool any = false;
+    int p = p_begin;
+    for(; p + kIcpBatch <= p_end; p += kIcpBatch) any |= icp_batch<kIcpBatch, SMEM>(L, IP, U, p, p_end, accI, s_vn, cap);
+    const int rem = p_end - p;
+    if(rem == 3) any |= icp_batch<3, SMEM>(L, IP, U, p, p_end, accI, s_vn, cap);
+    else if(rem == 2) any |= icp_batch<2, SMEM>(L, IP, U, p, p_end, accI, s_vn, cap);
+    else if(rem == 1) any |= icp_batch<1, SMEM>(L, IP, U, p, p_end, accI, s_vn, cap);
     return any;
 }
 
@@ -764,6 +870,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_track(const __grid_constant__ T
         C.r0 = base + 3 * cap;
         C.r1 = reinterpret_cast<float *>(base + 4 * cap);
     }
+    float * s_vn = reinterpret_cast<float *>(s_dyn) + 5 * (size_t)A.cand_cap; // 6 planes of cand_cap floats (icp_in_smem)
     Solver * S = &s_solver;
 
     // epochs, tracked identically by every thread of the grid
@@ -939,8 +1046,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_track(const __grid_constant__ T
         if(!is_solver_cta && A.rgb)
         {
             __syncthreads(); // every thread is done with the previous level's records
-            n_cand = compact_candidates(L, RP, U, passes, C, s_wtot);
+            n_cand = A.make_derivatives ? compact_candidates<true>(L, RP, U, passes, C, s_wtot) : compact_candidates<false>(L, RP, U, passes, C, s_wtot);
         }
+
+        if(!is_solver_cta && A.icp && A.icp_in_smem) stage_current_maps(L, U, passes, s_vn, A.cand_cap); // read by the staging thread only
 
         float lastRGBError = FLT_MAX;      // every thread tracks it for the uniform rgb_only break (:464)
         bool first_of_level = true;
@@ -988,7 +1097,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_track(const __grid_constant__ T
                     IP.tcurr = make_float3(par[9], par[10], par[11]);
                     stamp(4);
                     // ---- workers, phase A0: the first ICP pixels of every thread while CTA 0 computes the warp ----
-                    for(int p0 = 0; p0 < split; p0 += kIcpBatch) anyI |= icp_batch<kIcpBatch>(L, IP, U, p0, split, accI);
+                    anyI |= A.icp_in_smem ? icp_passes<true>(L, IP, U, 0, split, accI, s_vn, A.cand_cap) : icp_passes<false>(L, IP, U, 0, split, accI, s_vn, A.cand_cap);
                     wait_chunks(my_par, 4, 4, rel, par);
                 }
                 else
@@ -1031,7 +1140,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_track(const __grid_constant__ T
                 float vi = 0.f;
                 if(A.icp)
                 {
-                    for(int p0 = split; p0 < passes; p0 += kIcpBatch) anyI |= icp_batch<kIcpBatch>(L, IP, U, p0, passes, accI);
+                    anyI |= A.icp_in_smem ? icp_passes<true>(L, IP, U, split, passes, accI, s_vn, A.cand_cap)
+                                          : icp_passes<false>(L, IP, U, split, passes, accI, s_vn, A.cand_cap);
                     if(__any_sync(kFullMask, anyI)) vi = warp_transpose_reduce32(accI); // a warp without pixels contributes zeros
                 }
                 if(lane < 29) s_red[warp * 64 + lane] = vi;
@@ -1229,7 +1339,7 @@ struct DeviceTrack
     uint4 * rows;
     TrackOutput * out; // pinned
     int grid;
-    int cand_cap;
+    int cand_cap, icp_in_smem;
     size_t smem_bytes;
     unsigned launch_seq;
 };
@@ -1256,6 +1366,8 @@ int device_track_configure(ef_tracker * t, int grid)
         if(per_worker * 32 > max_cand) max_cand = per_worker * 32;
     }
     size_t smem = (size_t)max_cand * kCandBytes;
+    const bool icp_in_smem = (size_t)max_cand * (kCandBytes + kIcpBytes) <= (size_t)kMaxDynSmem;
+    if(icp_in_smem) smem = (size_t)max_cand * (kCandBytes + kIcpBytes);
     const size_t rows_smem = (size_t)W * kRowFloats * sizeof(float);
     if(rows_smem > smem) smem = rows_smem;
     if(smem > (size_t)kMaxDynSmem && d->grid > 0)
@@ -1266,6 +1378,7 @@ int device_track_configure(ef_tracker * t, int grid)
     }
     d->grid = grid;
     d->cand_cap = max_cand;
+    d->icp_in_smem = icp_in_smem ? 1 : 0;
     d->smem_bytes = smem;
     return EF_OK;
 }
@@ -1410,6 +1523,8 @@ int device_track_launch(ef_tracker * t, const float * trans, const float * rot, 
     A.out = d->out; // UVA: pinned + mapped host memory is addressable from the device
     A.dbg = d->dbg;
     A.cand_cap = d->cand_cap;
+    A.make_derivatives = (A.rgb && !t->deriv_valid) ? 1 : 0;
+    A.icp_in_smem = d->icp_in_smem;
 
     d->out->status = 0;
     void * args[] = {&A};

@@ -1,0 +1,178 @@
+"""Edge cases of the device-solve tracker (the persistent kernel, ef_track_kernel.cu), through the C ABI:
+ragged image sizes, empty and nearly empty inputs, SM subsets, internal streams, repeated calls.
+
+The persistent kernel is checked against the reference CUDA operators (oracle/_ref) where the reference defines
+the answer, and against the host-solve mode of the product (same per-pixel bodies, one kernel per operator, host
+LDLT) where only self-consistency can be asked (degenerate inputs)."""
+import numpy as np
+import pytest
+
+import instancefusion_b200 as ef
+from instancefusion_b200 import rgbd_odometry as RO
+from oracle import oracle as O
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+JOINT = dict(rgbOnly=False, icpWeight=10.0, pyramid=True, fastOdom=False, so3=False)
+JOINT_SO3 = dict(JOINT, so3=True)
+KW = lambda m: dict(rgb_only=m["rgbOnly"], icp_weight=m["icpWeight"], pyramid=m["pyramid"], fast_odom=m["fastOdom"], so3=m["so3"])
+
+
+def _feed(tr, pose0f, f0, f1):
+    if isinstance(tr, O.OracleTracker):
+        tr.init_first_rgb(f0["rgba"])
+        tr.init_icp_model(f0["vmap"], f0["nmap"], 20.0, pose0f)
+        tr.init_rgb_model(f0["rgba"])
+        tr.init_icp_depth(f1["depth"], 20.0)
+        tr.init_rgb(f1["rgba"])
+    else:
+        tr.initFirstRGB(f0["rgba"])
+        tr.initICPModel(f0["vmap"], f0["nmap"], 20.0, pose0f)
+        tr.initRGBModel(f0["rgba"])
+        tr.initICP(f1["depth"], 20.0)
+        tr.initRGB(f1["rgba"])
+
+
+# widths whose coarse levels are not multiples of 4 / 32, heights that leave ragged last chunks
+@pytest.mark.parametrize("size", [(320, 240), (200, 152), (168, 120), (96, 64)])
+def test_ragged_sizes_match_reference(size):
+    w, h = size
+    K, pose0, pose1, f0, f1 = util.frame_pair(w, h)
+    f1 = dict(f1, depth=util.punch_holes(f1["depth"]))
+    pose0f = pose0.astype(np.float32)
+    dev = ef.RGBDOdometry(w, h, K.cx, K.cy, K.fx, K.fy, solve_mode=RO.EF_SOLVE_DEVICE)
+    ref = O.OracleTracker(w, h, K.cx, K.cy, K.fx, K.fy, impl="ref")
+    try:
+        modes = (JOINT, JOINT_SO3, dict(JOINT, icpWeight=100.0), dict(JOINT, rgbOnly=True))
+        if w < 160:
+            # like 80x60 in test_tracker_gpu.py: the coarse levels (24x16) carry no usable signal and the 6x6 system is
+            # near singular there, so only the no-pyramid calls Ferns makes are meaningful parity cases
+            modes = (dict(JOINT, icpWeight=100.0, pyramid=False), dict(JOINT, pyramid=False, fastOdom=True, so3=True))
+        for m in modes:
+            _feed(dev, pose0f, f0, f1)
+            _feed(ref, pose0f, f0, f1)
+            t, R = dev.getIncrementalTransformation(pose0f[:3, 3], pose0f[:3, :3], **m)
+            tr, Rr, st = ref.get_incremental_transformation(pose0f[:3, 3], pose0f[:3, :3], **KW(m))
+            # RGB-only stops after 1-2 iterations per level on the rising-error rule (:464) and is poorly conditioned at
+            # these small sizes: the reference's own result moves by > 1e-5 with its launch shape (float sums), and the
+            # host-solve mode of the product is 3e-5 away from it at 320x240.  Joint / ICP-only keep BASELINE's 1e-5.
+            tol = 5e-4 if m["rgbOnly"] else 1e-5
+            assert float(np.abs(t - tr).max()) <= tol and util.rot_err(R, Rr) <= tol, (size, m)
+            assert dev.se3_iterations == st["se3_iterations"], (size, m)
+            if m["icpWeight"] < 100 or m["rgbOnly"]:
+                assert dev.lastRGBCount == pytest.approx(st["last_rgb_count"], rel=2e-3, abs=2)
+                for lvl in range(3):  # derivative images are produced inside the persistent kernel
+                    assert np.array_equal(dev.buffer("dIdx", lvl), ref.buffer("dIdx", lvl)), (size, lvl)
+                    assert np.array_equal(dev.buffer("dIdy", lvl), ref.buffer("dIdy", lvl)), (size, lvl)
+    finally:
+        dev.close()
+        ref.close()
+
+
+def test_empty_depth_and_black_image_do_not_hang_and_keep_the_pose():
+    """no ICP correspondence and no photometric candidate at all: every sum is zero, the zero-pivot LDLT returns a
+    zero update, the pose stays where it was -- in both solve modes."""
+    w, h = 320, 240
+    K, pose0, pose1, f0, f1 = util.frame_pair(w, h)
+    pose0f = pose0.astype(np.float32)
+    f1 = dict(f1, depth=np.zeros_like(f1["depth"]), rgba=np.zeros_like(f1["rgba"]))
+    outs = []
+    for mode in (RO.EF_SOLVE_HOST, RO.EF_SOLVE_DEVICE):
+        tr = ef.RGBDOdometry(w, h, K.cx, K.cy, K.fx, K.fy, solve_mode=mode)
+        try:
+            _feed(tr, pose0f, f0, f1)
+            t, R = tr.getIncrementalTransformation(pose0f[:3, 3], pose0f[:3, :3], **JOINT)
+            outs.append((t, R, tr.lastICPCount, tr.lastRGBCount))
+        finally:
+            tr.close()
+    for t, R, icp_count, rgb_count in outs:
+        assert icp_count == 0 and rgb_count == 0
+        assert np.allclose(t, pose0f[:3, 3], atol=1e-6) and np.allclose(R, pose0f[:3, :3], atol=1e-6)
+
+
+def test_sparse_depth_matches_host_mode():
+    """a frame with < 1 % valid depth: most worker CTAs of the persistent kernel own no valid pixel at all"""
+    w, h = 640, 480
+    K, pose0, pose1, f0, f1 = util.frame_pair(w, h)
+    pose0f = pose0.astype(np.float32)
+    d = np.zeros_like(f1["depth"])
+    d[200:230, 300:380] = f1["depth"][200:230, 300:380]
+    f1 = dict(f1, depth=d)
+    res = []
+    for mode in (RO.EF_SOLVE_HOST, RO.EF_SOLVE_DEVICE):
+        tr = ef.RGBDOdometry(w, h, K.cx, K.cy, K.fx, K.fy, solve_mode=mode)
+        try:
+            _feed(tr, pose0f, f0, f1)
+            res.append(tr.getIncrementalTransformation(pose0f[:3, 3], pose0f[:3, :3], **JOINT) + (tr.lastICPCount, tr.lastRGBCount))
+        finally:
+            tr.close()
+    (th, Rh, ich, rch), (td, Rd, icd, rcd) = res
+    # the two modes add the same products in different orders: poses agree to ~1e-6 and a borderline pixel may flip
+    assert abs(ich - icd) <= 3 and abs(rch - rcd) <= 3
+    assert float(np.abs(th - td).max()) <= 1e-5 and util.rot_err(Rh, Rd) <= 1e-5
+
+
+@pytest.mark.parametrize("ctas", [74, 37, 9, 2])
+def test_sm_subsets_give_the_same_pose(ctas):
+    """EF_OPT_GRID_CTAS: fewer, fatter worker CTAs change the summation tree only"""
+    w, h = 640, 480
+    K, pose0, pose1, f0, f1 = util.frame_pair(w, h)
+    pose0f = pose0.astype(np.float32)
+    a = ef.RGBDOdometry(w, h, K.cx, K.cy, K.fx, K.fy, solve_mode=RO.EF_SOLVE_DEVICE)
+    b = ef.RGBDOdometry(w, h, K.cx, K.cy, K.fx, K.fy, solve_mode=RO.EF_SOLVE_DEVICE)
+    try:
+        try:
+            b.set_option(RO.EF_OPT_GRID_CTAS, ctas)
+        except Exception:
+            # too few CTAs for the shared-memory candidate store: refused loudly, handle keeps working on all SMs
+            assert ctas <= 9
+        for m in (JOINT, JOINT_SO3):
+            _feed(a, pose0f, f0, f1)
+            _feed(b, pose0f, f0, f1)
+            ta, Ra = a.getIncrementalTransformation(pose0f[:3, 3], pose0f[:3, :3], **m)
+            tb, Rb = b.getIncrementalTransformation(pose0f[:3, 3], pose0f[:3, :3], **m)
+            assert float(np.abs(ta - tb).max()) <= 2e-6 and util.rot_err(Ra, Rb) <= 2e-6, (ctas, m)
+            assert abs(a.lastRGBCount - b.lastRGBCount) <= 3 and abs(a.lastICPCount - b.lastICPCount) <= 3
+    finally:
+        a.close()
+        b.close()
+
+
+def test_internal_streams_do_not_change_a_bit():
+    """EF_OPT_AUX_STREAMS on/off: same pyramids, same pose, bit for bit; repeated frames on one handle stay ordered"""
+    w, h = 640, 480
+    K, pose0, pose1, f0, f1 = util.frame_pair(w, h)
+    pose0f = pose0.astype(np.float32)
+    a = ef.RGBDOdometry(w, h, K.cx, K.cy, K.fx, K.fy, solve_mode=RO.EF_SOLVE_DEVICE)
+    b = ef.RGBDOdometry(w, h, K.cx, K.cy, K.fx, K.fy, solve_mode=RO.EF_SOLVE_DEVICE)
+    b.set_option(RO.EF_OPT_AUX_STREAMS, 0)
+    try:
+        args = (20.0, pose0f, False, 10.0, True, False, False)
+        for rep in range(6):  # alternate two different frames so that a stale pyramid would show
+            fa, fb = (f0, f1) if rep % 2 == 0 else (f1, f0)
+            ra = a.trackFrameToModel(fa["vmap"], fa["nmap"], fa["rgba"], fb["depth"], fb["rgba"], *args)
+            rb = b.trackFrameToModel(fa["vmap"], fa["nmap"], fa["rgba"], fb["depth"], fb["rgba"], *args)
+            assert np.array_equal(ra[0], rb[0]) and np.array_equal(ra[1], rb[1]), rep
+        for lvl in range(3):
+            for name in ("vmap_curr", "nmap_curr", "last_depth", "next_depth", "last_image", "next_image", "dIdx", "dIdy"):
+                assert np.array_equal(a.buffer(name, lvl), b.buffer(name, lvl), equal_nan=True), (name, lvl)
+    finally:
+        a.close()
+        b.close()
+
+
+def test_many_calls_on_one_handle_are_stable():
+    """launch-unique epochs: 200 consecutive launches on one handle, every one returns the same bits"""
+    w, h = 320, 240
+    K, pose0, pose1, f0, f1 = util.frame_pair(w, h)
+    pose0f = pose0.astype(np.float32)
+    tr = ef.RGBDOdometry(w, h, K.cx, K.cy, K.fx, K.fy, solve_mode=RO.EF_SOLVE_DEVICE)
+    try:
+        args = (20.0, pose0f, False, 10.0, True, False, False)
+        first = tr.trackFrameToModel(f0["vmap"], f0["nmap"], f0["rgba"], f1["depth"], f1["rgba"], *args)
+        for _ in range(200):
+            r = tr.trackFrameToModel(f0["vmap"], f0["nmap"], f0["rgba"], f1["depth"], f1["rgba"], *args)
+            assert np.array_equal(r[0], first[0]) and np.array_equal(r[1], first[1])
+    finally:
+        tr.close()
