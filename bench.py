@@ -11,8 +11,9 @@ Open-loop protocol: the model maps for frame k are ray-cast at the ground-truth 
   value  frames/s with every input already resident in HBM (device pointers into a pre-rendered sequence
          larger than L2), one tracker handle, blocking API -- timed with CUDA events on the handle's stream.
   e2e    frames/s through the host-buffer entry points of the C ABI (ef_init_*_host): every step copies
-         its 11.6 MB of inputs from pinned host memory and reads the pose + stats back.  Two handles
-         alternate frames so the copies of one overlap the solve of the other.
+         its 12.9 MB of inputs from pinned host memory and reads the pose + stats back.  Three full-GPU
+         handles take turns so that the copies of two overlap the solve of the third (the copies are the
+         bound: 54.6 GB/s measured -> 4 229 frames/s).
   roofline  the persistent tracker kernel (all 19 Gauss-Newton iterations of a frame in one launch):
          algorithmic bytes (ICP 48 B/px/iter + RGB 28 B/px/iter) / its CUDA-event duration
          against the measured HBM copy bandwidth.
@@ -60,6 +61,12 @@ def parse_args():
     ap.add_argument("--ref-kind", choices=["cuda", "port"], default="cuda")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--inflight", type=int, default=4, help="handles (frames in flight) of the pipelined / e2e runs")
+    ap.add_argument("--handle-ctas", type=int, default=-1,
+                    help="resident pipelined run: CTAs (SMs) each in-flight handle's tracker kernel occupies: -1 = SMs / inflight "
+                         "(disjoint SM subsets), 0 = every SM")
+    ap.add_argument("--e2e-inflight", type=int, default=3,
+                    help="handles of the e2e run; each uses EVERY SM, so their tracker kernels take turns while the other "
+                         "handles' host->device copies run (measured best: 3; the copies are the bound)")
     return ap.parse_args()
 
 
@@ -230,21 +237,26 @@ def run_ours(args, rank, world, device):
     if not args.no_e2e:
         NH = max(1, args.inflight)
         sms = torch.cuda.get_device_properties(device).multi_processor_count
-        if mode == RO.EF_SOLVE_DEVICE:
+        share = 0
+        if mode == RO.EF_SOLVE_DEVICE and args.handle_ctas != 0:
             # a handle's share of the SMs must be able to hold its photometric candidates in shared memory: halve the
             # number of handles until the tracker accepts the split (1280x720 takes 2 handles, 640x480 takes 4)
             while NH > 1:
+                share = args.handle_ctas if args.handle_ctas > 0 else sms // NH
                 try:
-                    tr.set_option(RO.EF_OPT_GRID_CTAS, sms // NH)
+                    tr.set_option(RO.EF_OPT_GRID_CTAS, share)
                     break
                 except Exception:
                     NH //= 2
             if NH == 1:
-                tr.set_option(RO.EF_OPT_GRID_CTAS, 0)
+                share = 0
+        if mode == RO.EF_SOLVE_DEVICE:
+            tr.set_option(RO.EF_OPT_GRID_CTAS, share)
         trs = [tr] + [make() for _ in range(NH - 1)]
         if mode == RO.EF_SOLVE_DEVICE:
             for t_ in trs[1:]:
-                t_.set_option(RO.EF_OPT_GRID_CTAS, sms // NH if NH > 1 else 0)
+                t_.set_option(RO.EF_OPT_GRID_CTAS, share)
+        ctas_per_handle = share if share > 0 else sms
         if so3:
             for t_ in trs[1:]:
                 t_.initFirstRGB(rgba[0])
@@ -272,8 +284,20 @@ def run_ours(args, rank, world, device):
             trk.trackFrameToModelLaunch(vmap[k - 1], nmap[k - 1], rgba[k - 1], depth[k], rgba[k], 20.0, posef[k - 1], False, args.icp_weight,
                                         True, False, so3)
 
-        concurrent = {"seconds": pipelined(submit_resident, args.steps), "frames": args.steps, "handles": NH, "ctas_per_handle": sms // NH}
+        concurrent = {"seconds": pipelined(submit_resident, args.steps), "frames": args.steps, "handles": NH, "ctas_per_handle": ctas_per_handle}
 
+        # e2e: host buffers.  The 12.9 MB of a frame take 0.24 ms over PCIe (54.6 GB/s measured), about as long as the
+        # whole solve, so the best schedule is full-GPU handles taking turns: one computes while the others copy.
+        NE = max(1, min(args.e2e_inflight, 8))
+        while len(trs) < NE:
+            trs.append(make())
+            if so3:
+                trs[-1].initFirstRGB(rgba[0])
+        if mode == RO.EF_SOLVE_DEVICE:
+            for t_ in trs:
+                t_.set_option(RO.EF_OPT_GRID_CTAS, 0)
+        NH_resident = NH
+        trs_all, trs, NH = trs, trs[:NE], NE
         FE = min(args.e2e_frames, F)
         pin = lambda t: t.cpu().pin_memory()
         h_depth = [pin(depth[k].view(torch.int16)) for k in range(FE)]
@@ -288,8 +312,9 @@ def run_ours(args, rank, world, device):
 
         e2e_s = pipelined(submit_host, args.steps)
         h2d = args.width * args.height * (2 + 4 + 16 + 16 + 4)  # depth + rgb + vmap + nmap + model rgb
-        e2e = {"seconds": e2e_s, "frames": args.steps, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 48 + 384, "handles": NH,
-               "ctas_per_handle": sms // NH}
+        e2e = {"seconds": e2e_s, "frames": args.steps, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 48 + 384, "handles": NE,
+               "ctas_per_handle": sms}
+        trs = trs_all
         for t_ in trs[1:]:
             t_.close()
 
@@ -454,11 +479,12 @@ def main():
             line["e2e"] = {"value": total_frames / (e2e_ms * 1e-3), "unit": "frames/s",
                            "h2d_bytes_per_step": r["e2e"]["h2d_bytes_per_step"], "d2h_bytes_per_step": r["e2e"]["d2h_bytes_per_step"],
                            "inflight_frames": r["e2e"]["handles"], "ctas_per_handle": r["e2e"]["ctas_per_handle"],
-                           "note": "C ABI ef_track_frame_to_model with pinned host buffers; handles on disjoint SM subsets, frames pipelined"}
+                           "note": "C ABI ef_track_frame_to_model with pinned host buffers; full-GPU handles take turns: one solves while "
+                                   "the others copy (PCIe bound: 12.9 MB per frame at 640x480)"}
             line["value_pipelined"] = {"value": total_frames / (conc_ms * 1e-3), "unit": "frames/s", "handles": r["concurrent"]["handles"],
                                        "ctas_per_handle": r["concurrent"]["ctas_per_handle"],
-                                       "note": "inputs resident, same handles as e2e: throughput when consecutive frames may overlap "
-                                               "(`value` is the single-handle, one-frame-at-a-time rate)"}
+                                       "note": "inputs resident, handles on disjoint SM subsets: throughput when consecutive frames may "
+                                               "overlap (`value` is the single-handle, one-frame-at-a-time rate)"}
         if r["cpu_baseline"]:
             line["cpu_baseline"] = r["cpu_baseline"]
         print(json.dumps(line))
