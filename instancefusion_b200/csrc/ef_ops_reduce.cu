@@ -56,15 +56,21 @@ inline int grid_for(int work_items)
 // ------------------------------------------------------------------------------------------------
 // icpStep  (reduce.cu:257-490)
 // ------------------------------------------------------------------------------------------------
+// Without control flow in the pixel body: the PX pixels of a thread interleave, all their gathers are in flight
+// together, rejected pixels gather pixel 0 and contribute rows of exact zeros (same bits as the branching form).
+// ~220 instructions per 48 bytes: at 1280x720 the instruction issue (7 M warp instructions / 592 schedulers) costs
+// about as much as the 44 MB from HBM, so the grid is sized to the real occupancy (no partial second wave) and the
+// kernel runs grid-stride.
 template<int PX>
-__global__ void __launch_bounds__(kBlock) k_icp_step(const IcpParams P, const Map3 vc, const Map3 nc, const Map3 vp, const Map3 np,
-                                                     int groups_per_row, int total_groups, float * __restrict__ partials,
-                                                     unsigned * ticket, float * __restrict__ out)
+__global__ void __launch_bounds__(kBlock, 2) k_icp_step(const IcpParams P, const Map3 vc, const Map3 nc, const Map3 vp, const Map3 np,
+                                                        int groups_per_row, int total_groups, float * __restrict__ partials,
+                                                        unsigned * ticket, float * __restrict__ out)
 {
     __shared__ float smem[32 * 32];
     float acc[32];
 #pragma unroll
     for(int i = 0; i < 32; i++) acc[i] = 0.f;
+    const size_t plane = (size_t)vp.rows * vp.pitch; // the four maps share rows and pitch (launch_icp_step)
 
     for(int g = blockIdx.x * blockDim.x + threadIdx.x; g < total_groups; g += gridDim.x * blockDim.x)
     {
@@ -91,17 +97,58 @@ __global__ void __launch_bounds__(kBlock) k_icp_step(const IcpParams P, const Ma
             vx[0] = vc.row(0, y)[x0]; vy[0] = vc.row(1, y)[x0]; vz[0] = vc.row(2, y)[x0];
             nx[0] = nc.row(0, y)[x0]; ny[0] = nc.row(1, y)[x0]; nz[0] = nc.row(2, y)[x0];
         }
+        float3 vg[PX], mv[PX], mn[PX];
+        bool in1[PX];
+        size_t q[PX];
+#pragma unroll
+        for(int k = 0; k < PX; k++)
+        {
+            int ux, uy;
+            in1[k] = icp_project(P, make_float3(vx[k], vy[k], vz[k]), vg[k], ux, uy);
+            q[k] = in1[k] ? (size_t)uy * vp.pitch + ux : 0;
+        }
+#pragma unroll
+        for(int k = 0; k < PX; k++)
+        {
+            mv[k].x = __ldg(vp.p + q[k]); mv[k].y = __ldg(vp.p + plane + q[k]); mv[k].z = __ldg(vp.p + 2 * plane + q[k]);
+            mn[k].x = __ldg(np.p + q[k]); mn[k].y = __ldg(np.p + plane + q[k]); mn[k].z = __ldg(np.p + 2 * plane + q[k]);
+        }
 #pragma unroll
         for(int k = 0; k < PX; k++)
         {
             float row[7];
-            if(icp_row(P, make_float3(vx[k], vy[k], vz[k]), make_float3(nx[k], ny[k], nz[k]), vp, np, row)) accumulate_se3(acc, row);
+            const bool ok = icp_finish_select(P, vg[k], make_float3(nx[k], ny[k], nz[k]), mv[k], mn[k], row) && in1[k];
+#pragma unroll
+            for(int i = 0; i < 7; i++) row[i] = ok ? row[i] : 0.f;
+            int kk = 0;
+#pragma unroll
+            for(int i = 0; i < 6; i++)
+            {
+#pragma unroll
+                for(int j = i; j < 7; j++) acc[kk++] += row[i] * row[j];
+            }
+            acc[27] += row[6] * row[6];
+            acc[28] += ok ? 1.0f : 0.f;
         }
     }
 
     const float lane_value = warp_transpose_reduce32(acc);
     const float block_total = block_reduce_slots<32>(lane_value, smem);
     grid_reduce_last_block<32>(block_total, partials, ticket, out, smem);
+}
+
+// blocks for `work_items` threads of `kernel`, at most one full wave of resident blocks (grid-stride kernels)
+template<class K>
+inline int grid_one_wave(K kernel, int work_items)
+{
+    int occ = 0;
+    if(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kBlock, 0) != cudaSuccess || occ < 1) occ = 1;
+    int blocks = (work_items + kBlock - 1) / kBlock;
+    const int cap = num_sms() * occ;
+    if(blocks > cap) blocks = cap;
+    if(blocks > kMaxReduceBlocks) blocks = kMaxReduceBlocks;
+    if(blocks < 1) blocks = 1;
+    return blocks;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -269,12 +316,12 @@ cudaError_t launch_icp_step(const IcpArgs & a, void * scratch, cudaStream_t s)
     if(vec)
     {
         const int gpr = a.cols / 4, total = gpr * a.rows;
-        k_icp_step<4><<<grid_for(total), kBlock, 0, s>>>(P, vc, nc, vp, np, gpr, total, partials, ticket, out);
+        k_icp_step<4><<<grid_one_wave(k_icp_step<4>, total), kBlock, 0, s>>>(P, vc, nc, vp, np, gpr, total, partials, ticket, out);
     }
     else
     {
         const int total = a.cols * a.rows;
-        k_icp_step<1><<<grid_for(total), kBlock, 0, s>>>(P, vc, nc, vp, np, a.cols, total, partials, ticket, out);
+        k_icp_step<1><<<grid_one_wave(k_icp_step<1>, total), kBlock, 0, s>>>(P, vc, nc, vp, np, a.cols, total, partials, ticket, out);
     }
     return cudaGetLastError();
 }
