@@ -99,6 +99,10 @@ float ef_default_angle_thresh(void);
 /* initICP(GPUTexture * filteredDepth, depthCutoff)                 RGBDOdometry.cpp:118-142
  * d_depth: uint16 millimetres, rows of `pitch_bytes` bytes (0 = dense). */
 int ef_init_icp_depth(ef_tracker * t, const uint16_t * d_depth, size_t pitch_bytes, float depth_cutoff);
+/* filterDepth + initICP in one call (ElasticFusion.cpp:309 + :348): RAW sensor depth in, bilateral filter with the range gate
+ * [300 mm, max_depth_m] on the way (into a buffer the handle owns), then as ef_init_icp_depth */
+int ef_init_icp_depth_raw(ef_tracker * t, const uint16_t * d_raw_depth, size_t pitch_bytes, float max_depth_m, float depth_cutoff);
+int ef_init_icp_depth_raw_host(ef_tracker * t, const uint16_t * h_raw_depth, float max_depth_m, float depth_cutoff);
 /* initICP(GPUTexture * predictedVertices, GPUTexture * predictedNormals, depthCutoff)   :144-167 */
 int ef_init_icp_maps(ef_tracker * t, const float * d_vertices_rgba32f, const float * d_normals_rgba32f, float depth_cutoff);
 /* initICPModel(predictedVertices, predictedNormals, depthCutoff, modelPose)             :169-206 */
@@ -220,6 +224,15 @@ int ef_op_derivative_images(const uint8_t * d_src, size_t src_pitch, int rows, i
  * cloud = rows x cols float3 */
 int ef_op_project_point_cloud(const float * d_depth, size_t depth_pitch, int rows, int cols, float fx, float fy, float cx, float cy,
                               int level, float * d_cloud3, size_t cloud_pitch, void * stream);
+
+/* ---- the step before the tracker, GLSL in the reference ---- */
+/* ElasticFusion::filterDepth   ElasticFusion.cpp:775-784, Shaders/depth_bilateral.frag:30-76: 13x13 bilateral filter of the raw
+ * depth in millimetres; pixels outside [300 mm, max_depth_m] become 0 */
+int ef_op_depth_bilateral(const uint16_t * d_src, size_t src_pitch, int rows, int cols, float max_depth_m, uint16_t * d_dst,
+                          size_t dst_pitch, void * stream);
+/* ElasticFusion::metriciseDepth ElasticFusion.cpp:765-773, Shaders/depth_metric.frag:28-40: millimetres -> metres, same gate */
+int ef_op_depth_metric(const uint16_t * d_src, size_t src_pitch, int rows, int cols, float max_depth_m, float * d_dst, size_t dst_pitch,
+                       void * stream);
 
 /* icpStep                     reduce.cu:257-490.  Host outputs: A 6x6 row-major, b[6], residual[2] =
  * {sum r^2, inlier count}.  `d_scratch` >= ef_op_scratch_bytes() bytes of device memory. */

@@ -65,7 +65,7 @@ def lib() -> C.CDLL:
 EXPORTED = [
     "ef_tracker_create", "ef_tracker_destroy", "ef_tracker_set_option", "ef_tracker_get_option", "ef_last_error",
     "ef_tracker_stream", "ef_tracker_synchronize", "ef_default_dist_thresh", "ef_default_angle_thresh",
-    "ef_init_icp_depth", "ef_init_icp_maps", "ef_init_icp_model", "ef_init_rgb", "ef_init_rgb_model", "ef_init_first_rgb",
+    "ef_init_icp_depth", "ef_init_icp_depth_raw", "ef_init_icp_depth_raw_host", "ef_init_icp_maps", "ef_init_icp_model", "ef_init_rgb", "ef_init_rgb_model", "ef_init_first_rgb",
     "ef_init_icp_depth_array", "ef_init_icp_maps_array", "ef_init_icp_model_array", "ef_init_rgb_array",
     "ef_init_rgb_model_array", "ef_init_first_rgb_array",
     "ef_init_icp_depth_host", "ef_init_icp_maps_host", "ef_init_icp_model_host", "ef_init_rgb_host", "ef_init_rgb_model_host",
@@ -74,6 +74,6 @@ EXPORTED = [
     "ef_get_incremental_transformation_finish", "ef_track_frame_to_model_launch", "ef_track_frame_to_model", "ef_get_covariance", "ef_tracker_download", "ef_tracker_launch_count", "ef_tracker_profile",
     "ef_op_pyr_down_u16", "ef_op_create_vmap", "ef_op_create_nmap", "ef_op_transform_maps", "ef_op_copy_maps",
     "ef_op_resize_map", "ef_op_vertices_to_depth", "ef_op_pyr_down_gauss_f32", "ef_op_pyr_down_gauss_u8",
-    "ef_op_bgr_to_intensity", "ef_op_derivative_images", "ef_op_project_point_cloud", "ef_op_icp_step",
+    "ef_op_bgr_to_intensity", "ef_op_depth_bilateral", "ef_op_depth_metric", "ef_op_derivative_images", "ef_op_project_point_cloud", "ef_op_icp_step",
     "ef_op_rgb_residual", "ef_op_rgb_step", "ef_op_so3_step", "ef_op_scratch_bytes", "ef_abi_version", "ef_device_count",
 ]

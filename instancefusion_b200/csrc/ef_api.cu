@@ -216,6 +216,7 @@ EF_API int ef_tracker_create(int width, int height, float cx, float cy, float fx
     }
     const size_t n0 = t->dims[0].n();
     const size_t o_tmpz = plan.take(n0 * 4);
+    const size_t o_filt = plan.take(n0 * 2);
     const size_t o_scratch = plan.take(kScratchBytes);
     const size_t o_sd = plan.take(n0 * 2), o_sr = plan.take(n0 * 4), o_sv = plan.take(n0 * 16), o_sn = plan.take(n0 * 16);
     t->arena_bytes = plan.off;
@@ -245,6 +246,7 @@ EF_API int ef_tracker_create(int width, int height, float cx, float cy, float fx
         t->cloud[i] = (float *)(base + o_cl[i]);
     }
     t->tmp_z = (float *)(base + o_tmpz);
+    t->filt_depth = (uint16_t *)(base + o_filt);
     t->scratch = base + o_scratch;
     t->stage_depth = (uint16_t *)(base + o_sd);
     t->stage_rgba = (uint8_t *)(base + o_sr);
@@ -362,8 +364,9 @@ EF_API int ef_tracker_synchronize(ef_tracker * t)
 // ------------------------------------------------------------------------------------------------
 // pyramid builders
 // ------------------------------------------------------------------------------------------------
-// RGBDOdometry.cpp:118-142
-EF_API int ef_init_icp_depth(ef_tracker * t, const uint16_t * d_depth, size_t pitch_bytes, float depth_cutoff)
+// RGBDOdometry.cpp:118-142.  raw_max_depth_m > 0: d_depth is the RAW sensor depth and ElasticFusion::filterDepth
+// (ElasticFusion.cpp:775-784) runs first, on the same stream, into the handle's own DEPTH_FILTERED buffer.
+static int init_icp_depth(ef_tracker * t, const uint16_t * d_depth, size_t pitch_bytes, float depth_cutoff, float raw_max_depth_m)
 {
     if(!t || !d_depth) return EF_ERR_INVALID_ARGUMENT;
     if(t->fused_build)
@@ -371,6 +374,12 @@ EF_API int ef_init_icp_depth(ef_tracker * t, const uint16_t * d_depth, size_t pi
         // one launch per level: vertex map + normal map (+ dense copy of level 0) + bilateral pyrDown to the next level;
         // nothing else a frame builds is read here, so the three launches go to an internal stream (aux 0)
         cudaStream_t s = fork_stream(t, 0);
+        if(raw_max_depth_m > 0.f)
+        {
+            EF_LAUNCH(t, launch_depth_bilateral(d_depth, pitch_bytes, t->height, t->width, raw_max_depth_m, t->filt_depth, 0, s));
+            d_depth = t->filt_depth;
+            pitch_bytes = 0;
+        }
         for(int i = 0; i < kNumPyrs; ++i)
         {
             float fx, fy, cx, cy;
@@ -386,6 +395,12 @@ EF_API int ef_init_icp_depth(ef_tracker * t, const uint16_t * d_depth, size_t pi
     {
         const int rc = join_streams(t);
         if(rc) return rc;
+    }
+    if(raw_max_depth_m > 0.f)
+    {
+        EF_LAUNCH(t, launch_depth_bilateral(d_depth, pitch_bytes, t->height, t->width, raw_max_depth_m, t->filt_depth, 0, s));
+        d_depth = t->filt_depth;
+        pitch_bytes = 0;
     }
     // level 0 is read in place from the caller's buffer (the reference copies the texture into depth_tmp[0])
     const size_t p0 = pitch_bytes ? pitch_bytes : (size_t)t->width * 2;
@@ -409,6 +424,18 @@ EF_API int ef_init_icp_depth(ef_tracker * t, const uint16_t * d_depth, size_t pi
         EF_LAUNCH(t, launch_create_nmap(t->vmap_curr[i], 0, t->dims[i].rows, t->dims[i].cols, t->nmap_curr[i], 0, s));
     }
     return EF_OK;
+}
+
+EF_API int ef_init_icp_depth(ef_tracker * t, const uint16_t * d_depth, size_t pitch_bytes, float depth_cutoff)
+{
+    return init_icp_depth(t, d_depth, pitch_bytes, depth_cutoff, 0.f);
+}
+
+// ElasticFusion.cpp:309 (filterDepth) + :348 (initICP) in one call
+EF_API int ef_init_icp_depth_raw(ef_tracker * t, const uint16_t * d_raw_depth, size_t pitch_bytes, float max_depth_m, float depth_cutoff)
+{
+    if(!(max_depth_m > 0.f)) return t ? fail(t, EF_ERR_INVALID_ARGUMENT, "max_depth_m must be positive") : EF_ERR_INVALID_ARGUMENT;
+    return init_icp_depth(t, d_raw_depth, pitch_bytes, depth_cutoff, max_depth_m);
 }
 
 static int build_maps(ef_tracker * t, const float * d_v, const float * d_n, float ** vmaps, float ** nmaps, const float * R, const float * tv)
@@ -566,6 +593,13 @@ EF_API int ef_init_icp_depth_host(ef_tracker * t, const uint16_t * h, float cuto
     if(!t || !h) return EF_ERR_INVALID_ARGUMENT;
     EF_CUDA(t, cudaMemcpyAsync(t->stage_depth, h, t->dims[0].n() * 2, cudaMemcpyHostToDevice, t->stream));
     return ef_init_icp_depth(t, t->stage_depth, 0, cutoff);
+}
+
+EF_API int ef_init_icp_depth_raw_host(ef_tracker * t, const uint16_t * h, float max_depth_m, float cutoff)
+{
+    if(!t || !h) return EF_ERR_INVALID_ARGUMENT;
+    EF_CUDA(t, cudaMemcpyAsync(t->stage_depth, h, t->dims[0].n() * 2, cudaMemcpyHostToDevice, t->stream));
+    return ef_init_icp_depth_raw(t, t->stage_depth, 0, max_depth_m, cutoff);
 }
 
 EF_API int ef_init_icp_maps_host(ef_tracker * t, const float * hv, const float * hn, float cutoff)
@@ -999,6 +1033,7 @@ EF_API int ef_tracker_download(ef_tracker * t, const char * name, int level, voi
     else if(!strcmp(name, "dIdx")) { src = t->dIdx[level]; need = n * 2; }
     else if(!strcmp(name, "dIdy")) { src = t->dIdy[level]; need = n * 2; }
     else if(!strcmp(name, "depth_tmp")) { src = t->depth_tmp[level]; need = n * 2; }
+    else if(!strcmp(name, "filt_depth") && level == 0) { src = t->filt_depth; need = n * 2; }
     else return fail(t, EF_ERR_INVALID_ARGUMENT, "unknown buffer name");
     if(bytes < need) return fail(t, EF_ERR_INVALID_ARGUMENT, "destination too small");
     {
@@ -1061,6 +1096,14 @@ EF_API int ef_op_pyr_down_gauss_u8(const uint8_t * s, size_t sp, int r, int c, u
 EF_API int ef_op_bgr_to_intensity(const uint8_t * s, size_t sp, int r, int c, uint8_t * d, size_t dp, void * st)
 {
     EF_OP_RET(launch_bgr_to_intensity(s, sp, r, c, d, dp, (cudaStream_t)st));
+}
+EF_API int ef_op_depth_bilateral(const uint16_t * s, size_t sp, int r, int c, float max_depth_m, uint16_t * d, size_t dp, void * st)
+{
+    EF_OP_RET(launch_depth_bilateral(s, sp, r, c, max_depth_m, d, dp, (cudaStream_t)st));
+}
+EF_API int ef_op_depth_metric(const uint16_t * s, size_t sp, int r, int c, float max_depth_m, float * d, size_t dp, void * st)
+{
+    EF_OP_RET(launch_depth_metric(s, sp, r, c, max_depth_m, d, dp, (cudaStream_t)st));
 }
 EF_API int ef_op_derivative_images(const uint8_t * s, size_t sp, int r, int c, int16_t * dx, int16_t * dy, size_t dp, void * st)
 {

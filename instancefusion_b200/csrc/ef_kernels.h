@@ -27,6 +27,10 @@ cudaError_t launch_derivative_images(const uint8_t * src, size_t sp, int rows, i
 cudaError_t launch_project_points(const float * depth, size_t dp, int rows, int cols, float fx, float fy, float cx, float cy, float * cloud,
                                   size_t cp, cudaStream_t s);
 
+// ---- the step before the tracker (ef_ops_depth.cu): ElasticFusion::filterDepth / metriciseDepth ----
+cudaError_t launch_depth_bilateral(const uint16_t * src, size_t sp, int rows, int cols, float max_depth_m, uint16_t * dst, size_t dp, cudaStream_t s);
+cudaError_t launch_depth_metric(const uint16_t * src, size_t sp, int rows, int cols, float max_depth_m, float * dst, size_t dp, cudaStream_t s);
+
 // ---- fused pyramid builders (ef_build_fused.cu); dense outputs ----
 // R == nullptr: no transform (initICP maps overload); else v' = R v + t, n' = R n at every level (initICPModel)
 cudaError_t launch_build_maps(const float * v4, const float * n4, int rows, int cols, float * const vmaps[3], float * const nmaps[3], float * tmp_z,

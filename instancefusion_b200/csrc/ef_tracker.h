@@ -53,6 +53,7 @@ struct ef_tracker
     size_t arena_bytes;
 
     uint16_t * depth_tmp[ef::kNumPyrs];
+    uint16_t * filt_depth; // bilateral-filtered raw depth (ef_init_icp_depth_raw; textures[DEPTH_FILTERED] of ElasticFusion.cpp:188)
     float * tmp_z; // z channel of the vertex map last given to init_icp_maps/init_icp_model (stands for vmaps_tmp)
     float * vmap_curr[ef::kNumPyrs], * nmap_curr[ef::kNumPyrs];
     float * vmap_g_prev[ef::kNumPyrs], * nmap_g_prev[ef::kNumPyrs];

@@ -154,6 +154,26 @@ def pyrDownUcharGauss(src):
     return _np(d)
 
 
+def depthBilateral(depth, maxD):
+    """ElasticFusion::filterDepth (Shaders/depth_bilateral.frag): raw u16 millimetres -> filtered u16 millimetres."""
+    L = binding.lib()
+    s = _dev(depth, torch.uint16)
+    r, c = s.shape
+    d = torch.zeros((r, c), dtype=torch.uint16, device="cuda")
+    _chk(L.ef_op_depth_bilateral(_p(s), C.c_size_t(0), r, c, C.c_float(maxD), _p(d), C.c_size_t(0), _stream()), "ef_op_depth_bilateral")
+    return _np(d)
+
+
+def depthMetric(depth, maxD):
+    """ElasticFusion::metriciseDepth (Shaders/depth_metric.frag): u16 millimetres -> float metres."""
+    L = binding.lib()
+    s = _dev(depth, torch.uint16)
+    r, c = s.shape
+    d = torch.zeros((r, c), dtype=torch.float32, device="cuda")
+    _chk(L.ef_op_depth_metric(_p(s), C.c_size_t(0), r, c, C.c_float(maxD), _p(d), C.c_size_t(0), _stream()), "ef_op_depth_metric")
+    return _np(d)
+
+
 def imageBGRToIntensity(rgba):
     L = binding.lib()
     s = _dev(rgba, torch.uint8)

@@ -18,7 +18,7 @@ EF_SOLVE_HOST, EF_SOLVE_DEVICE = 0, 1
 _LEVEL_BUFFERS = {"vmap_curr": (np.float32, 3), "nmap_curr": (np.float32, 3), "vmap_g_prev": (np.float32, 3),
                   "nmap_g_prev": (np.float32, 3), "last_depth": (np.float32, 1), "next_depth": (np.float32, 1),
                   "last_image": (np.uint8, 1), "next_image": (np.uint8, 1), "last_next_image": (np.uint8, 1),
-                  "dIdx": (np.int16, 1), "dIdy": (np.int16, 1), "depth_tmp": (np.uint16, 1)}
+                  "dIdx": (np.int16, 1), "dIdy": (np.int16, 1), "depth_tmp": (np.uint16, 1), "filt_depth": (np.uint16, 1)}
 
 
 def _is_cuda_tensor(a) -> bool:
@@ -133,6 +133,17 @@ class RGBDOdometry:
                                                           C.c_float(cutoff)), "ef_init_icp_maps_host")
         else:
             raise TypeError("initICP takes (depth, cutoff) or (vertices, normals, cutoff)")
+
+    def initICPRaw(self, rawDepth, maxDepth, depthCutoff):
+        """filterDepth + initICP (ElasticFusion.cpp:309, :348): RAW sensor depth (u16 mm) -> bilateral filter -> pyramids."""
+        if _is_cuda_tensor(rawDepth):
+            self._check(self._L.ef_init_icp_depth_raw(self._h, _dev_ptr(rawDepth, "uint16"), C.c_size_t(0), C.c_float(maxDepth),
+                                                      C.c_float(depthCutoff)), "ef_init_icp_depth_raw")
+        else:
+            d = _host_arr(rawDepth, np.uint16)
+            self._keep = d
+            self._check(self._L.ef_init_icp_depth_raw_host(self._h, d.ctypes.data_as(C.c_void_p), C.c_float(maxDepth),
+                                                           C.c_float(depthCutoff)), "ef_init_icp_depth_raw_host")
 
     def initICPModel(self, predictedVertices, predictedNormals, depthCutoff, modelPose):
         pose = np.ascontiguousarray(np.asarray(modelPose, dtype=np.float32).reshape(16))

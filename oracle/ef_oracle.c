@@ -1319,3 +1319,56 @@ void efo_get_covariance(const efo_tracker * t, double * cov)
     for(int i = 0; i < 6; i++)
         for(int j = 0; j < 6; j++) cov[i * 6 + j] = a[i][6 + j];
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * ElasticFusion::filterDepth -- Shaders/depth_bilateral.frag:30-76 (GLSL in the reference; there is no reference CUDA
+ * for it).  Restated with exact texel fetches at (cx, cy) -- the shader samples at float(cx)/cols, the left EDGE of the
+ * texel, where the nearest-texel choice of a GL implementation is not pinned -- IEEE float arithmetic in the shader's
+ * order without contraction, libm expf for exp(), round-half-away for round().  Parity therefore is unpinned against
+ * the reference's GL output; it is pinned against this restatement.
+ * ------------------------------------------------------------------------------------------------ */
+void efo_depth_bilateral(const uint16_t * src, int rows, int cols, float max_depth_m, uint16_t * dst)
+{
+    const unsigned max_mm = (unsigned)(max_depth_m * 1000.0f); /* :36 uint(maxD * 1000.0f) */
+    const float sigma_space2_inv_half = 0.024691358f;          /* :42 */
+    const float sigma_color2_inv_half = 0.000555556f;          /* :43 */
+    const int R = 6, D = R * 2 + 1;                            /* :45-46 */
+#pragma omp parallel for schedule(static)
+    for(int y = 0; y < rows; y++)
+        for(int x = 0; x < cols; x++)
+        {
+            const unsigned value = src[(size_t)y * cols + x];
+            if(value > max_mm || value < 300u)
+            {
+                dst[(size_t)y * cols + x] = 0;
+                continue;
+            }
+            const int tx = (x - D / 2 + D) < cols ? (x - D / 2 + D) : cols; /* :48 */
+            const int ty = (y - D / 2 + D) < rows ? (y - D / 2 + D) : rows; /* :49 */
+            float sum1 = 0.f, sum2 = 0.f;
+            for(int cy = (y - D / 2 > 0 ? y - D / 2 : 0); cy < ty; ++cy)
+                for(int cx = (x - D / 2 > 0 ? x - D / 2 : 0); cx < tx; ++cx)
+                {
+                    const unsigned tmp = src[(size_t)cy * cols + cx];
+                    const float dx = (float)x - (float)cx, dy = (float)y - (float)cy;
+                    const float space2 = dx * dx + dy * dy;                               /* :61 */
+                    const float dc = (float)value - (float)tmp;
+                    const float color2 = dc * dc;                                         /* :62 */
+                    const float weight = expf(-(space2 * sigma_space2_inv_half + color2 * sigma_color2_inv_half)); /* :64 */
+                    sum1 += (float)tmp * weight;                                          /* :66 */
+                    sum2 += weight;
+                }
+            dst[(size_t)y * cols + x] = (uint16_t)(unsigned)roundf(sum1 / sum2);          /* :71 */
+        }
+}
+
+/* ElasticFusion::metriciseDepth -- Shaders/depth_metric.frag:28-40 */
+void efo_depth_metric(const uint16_t * src, int rows, int cols, float max_depth_m, float * dst)
+{
+    const unsigned max_mm = (unsigned)(max_depth_m * 1000.0f);
+    for(size_t i = 0; i < (size_t)rows * cols; i++)
+    {
+        const unsigned value = src[i];
+        dst[i] = (value > max_mm || value < 300u) ? 0.f : (float)value / 1000.0f;
+    }
+}

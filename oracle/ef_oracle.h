@@ -57,6 +57,10 @@ void efo_bgr_to_intensity(const uint8_t * rgba8, int rows, int cols, uint8_t * d
 /* cudafuncs.cu:580-639 */
 void efo_derivative_images(const uint8_t * src, int rows, int cols, int16_t * dx, int16_t * dy);
 /* cudafuncs.cu:641-674 ; intr already scaled to the level; cloud = rows x cols x 3 floats */
+/* the step before the tracker (GLSL in the reference): Shaders/depth_bilateral.frag:30-76, depth_metric.frag:28-40 */
+void efo_depth_bilateral(const uint16_t * src, int rows, int cols, float max_depth_m, uint16_t * dst);
+void efo_depth_metric(const uint16_t * src, int rows, int cols, float max_depth_m, float * dst);
+
 void efo_project_point_cloud(const float * depth, int rows, int cols, float fx, float fy, float cx, float cy, float * cloud);
 
 /* reduce.cu:257-490.  out29 = 27 upper-triangle products of [J|r] + residual + inliers,

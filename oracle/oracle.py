@@ -200,6 +200,23 @@ def derivative_images(img, impl="cpu"):
     return dx, dy
 
 
+def depth_bilateral(depth, max_depth_m):
+    """Shaders/depth_bilateral.frag (CPU restatement only: the reference runs it as GLSL, there is no reference CUDA)."""
+    depth = _c(depth, np.uint16)
+    r, c = depth.shape
+    dst = np.zeros((r, c), np.uint16)
+    cpu().efo_depth_bilateral(_fp(depth), C.c_int(r), C.c_int(c), C.c_float(max_depth_m), _fp(dst))
+    return dst
+
+
+def depth_metric(depth, max_depth_m):
+    depth = _c(depth, np.uint16)
+    r, c = depth.shape
+    dst = np.zeros((r, c), np.float32)
+    cpu().efo_depth_metric(_fp(depth), C.c_int(r), C.c_int(c), C.c_float(max_depth_m), _fp(dst))
+    return dst
+
+
 def project_point_cloud(depth, fx, fy, cx, cy, level=0, impl="cpu"):
     """fx..cy are LEVEL-0 intrinsics; `level` divides them by 2^level like CameraModel::operator()."""
     depth = _c(depth, np.float32)
