@@ -248,7 +248,7 @@ constexpr int kTileW = 2 * 32 + 3, kTileH = 2 * 8 + 3; // level-0 footprint of a
 
 template<bool WITH_DEPTH>
 __global__ void __launch_bounds__(256) k_rgbd_level0(const uint8_t * __restrict__ rgba, int rgba_pitch /*bytes*/, const float * __restrict__ tmp_z,
-                                                     float cutoff, int rows, int cols, uint8_t * __restrict__ img0, float * __restrict__ depth0,
+                                                     int z_stride, float cutoff, int rows, int cols, uint8_t * __restrict__ img0, float * __restrict__ depth0,
                                                      uint8_t * __restrict__ img1, float * __restrict__ depth1)
 {
     __shared__ uint8_t s_img[kTileH][kTileW + 1];
@@ -264,7 +264,7 @@ __global__ void __launch_bounds__(256) k_rgbd_level0(const uint8_t * __restrict_
         if(gx >= 0 && gy >= 0 && gx < cols && gy < rows)
         {
             s_img[ty][tx] = intensity_px(__ldg(reinterpret_cast<const uchar4 *>(rgba + (size_t)gy * rgba_pitch) + gx));
-            if(WITH_DEPTH) s_dep[ty][tx] = depth_from_z(__ldg(tmp_z + (size_t)gy * cols + gx), cutoff);
+            if(WITH_DEPTH) s_dep[ty][tx] = depth_from_z(__ldg(tmp_z + ((size_t)gy * cols + gx) * z_stride), cutoff);
         }
     }
     __syncthreads();
@@ -378,16 +378,16 @@ cudaError_t launch_depth_level(const uint16_t * depth, size_t dpitch_bytes, int 
     return cudaGetLastError();
 }
 
-cudaError_t launch_rgbd_level0(const uint8_t * rgba, size_t pitch_bytes, const float * tmp_z, float cutoff, int rows, int cols, uint8_t * img0,
+cudaError_t launch_rgbd_level0(const uint8_t * rgba, size_t pitch_bytes, const float * tmp_z, int z_stride, float cutoff, int rows, int cols, uint8_t * img0,
                                float * depth0, uint8_t * img1, float * depth1, cudaStream_t s)
 {
     const dim3 block(32, 8);
     const dim3 grid((cols / 2 + 31) / 32, (rows / 2 + 7) / 8);
     const int p = (int)(pitch_bytes ? pitch_bytes : (size_t)cols * 4);
     if(depth0)
-        k_rgbd_level0<true><<<grid, block, 0, s>>>(rgba, p, tmp_z, cutoff, rows, cols, img0, depth0, img1, depth1);
+        k_rgbd_level0<true><<<grid, block, 0, s>>>(rgba, p, tmp_z, z_stride, cutoff, rows, cols, img0, depth0, img1, depth1);
     else
-        k_rgbd_level0<false><<<grid, block, 0, s>>>(rgba, p, tmp_z, cutoff, rows, cols, img0, nullptr, img1, nullptr);
+        k_rgbd_level0<false><<<grid, block, 0, s>>>(rgba, p, tmp_z, 1, cutoff, rows, cols, img0, nullptr, img1, nullptr);
     return cudaGetLastError();
 }
 

@@ -39,8 +39,9 @@ cudaError_t launch_build_maps(const float * v4, const float * n4, int rows, int 
 cudaError_t launch_depth_level(const uint16_t * depth, size_t dpitch_bytes, int rows, int cols, float fx, float fy, float cx, float cy, float cutoff,
                                float * vmap, float * nmap, uint16_t * depth_copy, uint16_t * next_depth, cudaStream_t s);
 // intensity (+ float depth from the kept z channel when depth0 != null) at level 0 and their Gaussian pyrDowns to level 1
-cudaError_t launch_rgbd_level0(const uint8_t * rgba, size_t pitch_bytes, const float * tmp_z, float cutoff, int rows, int cols, uint8_t * img0,
-                               float * depth0, uint8_t * img1, float * depth1, cudaStream_t s);
+// z: the kept z channel (z_stride 1) or the z component of the RGBA32F vertex texture itself (z = &v4[2], z_stride 4)
+cudaError_t launch_rgbd_level0(const uint8_t * rgba, size_t pitch_bytes, const float * z, int z_stride, float cutoff, int rows, int cols,
+                               uint8_t * img0, float * depth0, uint8_t * img1, float * depth1, cudaStream_t s);
 cudaError_t launch_rgbd_level1(const uint8_t * img1, const float * depth1, int rows1, int cols1, uint8_t * img2, float * depth2, cudaStream_t s);
 cudaError_t launch_derivatives3(const uint8_t * const img[3], int16_t * const dx[3], int16_t * const dy[3], const int rows[3], const int cols[3],
                                 cudaStream_t s);

@@ -44,9 +44,9 @@ struct ef_tracker
     int aux_streams; // EF_OPT_AUX_STREAMS
 
     // internal fork/join streams for builders that are independent of each other (ef_api.cu: fork_stream / join_streams)
-    cudaStream_t aux[2];
-    cudaEvent_t ev_fork, ev_join[2];
-    bool aux_dirty[2];
+    cudaStream_t aux[3];            // 0: current-frame depth chain, 1: model RGB-D chain, 2: model maps (single-call entry)
+    cudaEvent_t ev_fork, ev_join[3];
+    bool aux_dirty[3];
 
     // one device arena, sliced
     void * arena;
@@ -66,7 +66,7 @@ struct ef_tracker
 
     // staging for the _host and _array entry points
     uint16_t * stage_depth;
-    uint8_t * stage_rgba;
+    uint8_t * stage_rgba, * stage_rgba_model; // two: the model image is read on an internal stream while the next copy runs
     float * stage_v, * stage_n;
 
     // persistent-kernel state (EF_SOLVE_DEVICE)
