@@ -1,0 +1,55 @@
+// ef_track_dispatch.cu -- picks the CTA shape of the persistent tracker kernel per handle.
+// ef_track_kernel.cu is compiled twice (EF_TRACK_THREADS = 256 and 384, see its header); small images run the 8-warp
+// variant, large ones the 12-warp variant.  EF_TRACK_VARIANT=256|384 in the environment overrides (sweeps).
+#include <stdlib.h>
+
+#include "ef_tracker.h"
+
+namespace ef
+{
+
+#define EF_DECLARE_VARIANT(T)                                                                                                              \
+    int device_track_init_t##T(ef_tracker * t);                                                                                            \
+    int device_track_configure_t##T(ef_tracker * t, int grid_ctas);                                                                        \
+    void device_track_destroy_t##T(ef_tracker * t);                                                                                        \
+    int device_track_launch_t##T(ef_tracker * t, const float * trans, const float * rot, int rgb_only, float icp_weight, int pyramid,     \
+                                 int fast_odom, int so3);                                                                                  \
+    int device_track_finish_t##T(ef_tracker * t, float * trans, float * rot);
+EF_DECLARE_VARIANT(256)
+EF_DECLARE_VARIANT(384)
+
+static int pick_variant(const ef_tracker * t)
+{
+    const char * env = getenv("EF_TRACK_VARIANT");
+    if(env && atoi(env) == 256) return 256;
+    if(env && atoi(env) == 384) return 384;
+    // measured crossover between 640x480 (256 threads 3 % faster) and 1280x720 (384 threads 10 % faster)
+    return ((size_t)t->width * t->height >= (size_t)600000) ? 384 : 256;
+}
+
+int device_track_init(ef_tracker * t)
+{
+    t->track_variant = pick_variant(t);
+    return t->track_variant == 384 ? device_track_init_t384(t) : device_track_init_t256(t);
+}
+int device_track_configure(ef_tracker * t, int grid_ctas)
+{
+    return t->track_variant == 384 ? device_track_configure_t384(t, grid_ctas) : device_track_configure_t256(t, grid_ctas);
+}
+void device_track_destroy(ef_tracker * t)
+{
+    if(t->track_variant == 384) device_track_destroy_t384(t);
+    else device_track_destroy_t256(t);
+}
+int device_track_launch(ef_tracker * t, const float * trans, const float * rot, int rgb_only, float icp_weight, int pyramid, int fast_odom,
+                        int so3)
+{
+    return t->track_variant == 384 ? device_track_launch_t384(t, trans, rot, rgb_only, icp_weight, pyramid, fast_odom, so3)
+                                   : device_track_launch_t256(t, trans, rot, rgb_only, icp_weight, pyramid, fast_odom, so3);
+}
+int device_track_finish(ef_tracker * t, float * trans, float * rot)
+{
+    return t->track_variant == 384 ? device_track_finish_t384(t, trans, rot) : device_track_finish_t256(t, trans, rot);
+}
+
+} // namespace ef

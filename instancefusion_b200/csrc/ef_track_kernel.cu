@@ -36,18 +36,33 @@
 #include "ef_reduce.cuh"
 #include "ef_tracker.h"
 
+// This file is compiled TWICE (csrc/Makefile): 256 threads per CTA (8 warps, <= 255 registers) is the best shape up to
+// ~640x480, 384 threads (12 warps, <= 168 registers) from ~1280x720 on, where a thread owns ~25 pixels per level-0 iteration
+// and the extra warps hide more latency than the longer reductions cost (profiles/r01_k_track_thread_sweep.txt).
+// ef_track_dispatch.cu picks the variant per handle from the image size.
+#ifndef EF_TRACK_THREADS
+#define EF_TRACK_THREADS 256
+#endif
+#define EF_TRACK_CAT2(a, b) a##_t##b
+#define EF_TRACK_CAT(a, b) EF_TRACK_CAT2(a, b)
+#define EF_TRACK_FN(name) EF_TRACK_CAT(name, EF_TRACK_THREADS)
+
 namespace ef
 {
+
+void EF_TRACK_FN(device_track_destroy)(ef_tracker * t);
+int EF_TRACK_FN(device_track_configure)(ef_tracker * t, int grid);
 
 namespace
 {
 
-#ifndef EF_TRACK_THREADS
-#define EF_TRACK_THREADS 256
-#endif
 constexpr int kThreads = EF_TRACK_THREADS; // 8 warps, up to 255 registers each: measured best of {128..640} (tools/sweep.sh)
 #ifndef EF_TRACK_ICP_BATCH
+#if EF_TRACK_THREADS >= 384
+#define EF_TRACK_ICP_BATCH 2 // 168 registers: two pixels in flight per thread
+#else
 #define EF_TRACK_ICP_BATCH 3
+#endif
 #endif
 constexpr int kIcpBatch = EF_TRACK_ICP_BATCH; // pixels of one thread whose loads and gathers are in flight together
 #ifndef EF_TRACK_ICP_SPLIT
@@ -1349,7 +1364,7 @@ struct DeviceTrack
 // (re)derive the launch geometry for a grid of `grid` CTAs: pixels per thread unit and passes per level ->
 // shared-memory records per thread.  A handle normally owns every SM; EF_OPT_GRID_CTAS lets several handles
 // share the GPU (e.g. two sequences tracked concurrently on 74 SMs each).
-int device_track_configure(ef_tracker * t, int grid)
+int EF_TRACK_FN(device_track_configure)(ef_tracker * t, int grid)
 {
     DeviceTrack * d = static_cast<DeviceTrack *>(t->track_state);
     if(!d) return EF_ERR_BAD_STATE;
@@ -1383,12 +1398,12 @@ int device_track_configure(ef_tracker * t, int grid)
     return EF_OK;
 }
 
-int device_track_init(ef_tracker * t)
+int EF_TRACK_FN(device_track_init)(ef_tracker * t)
 {
     DeviceTrack * d = new DeviceTrack();
     memset(d, 0, sizeof(*d));
     t->track_state = d;
-    device_track_configure(t, 0);
+    EF_TRACK_FN(device_track_configure)(t, 0);
     const int max_grid = t->num_sms < kMaxGrid ? t->num_sms : kMaxGrid;
     d->launch_seq = 0;
     const size_t ctl_chunks = (size_t)kReplicas * kReplicaStride + 2 * (size_t)((max_grid + 7) & ~7);
@@ -1411,14 +1426,14 @@ int device_track_init(ef_tracker * t)
     if(e == cudaSuccess) e = cudaFuncSetAttribute(k_track<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
     if(e != cudaSuccess)
     {
-        device_track_destroy(t);
+        EF_TRACK_FN(device_track_destroy)(t);
         return (int)e;
     }
     t->h_track_out = d->out;
     return EF_OK;
 }
 
-void device_track_destroy(ef_tracker * t)
+void EF_TRACK_FN(device_track_destroy)(ef_tracker * t)
 {
     DeviceTrack * d = static_cast<DeviceTrack *>(t->track_state);
     if(!d) return;
@@ -1462,7 +1477,7 @@ void device_track_destroy(ef_tracker * t)
     t->track_state = nullptr;
 }
 
-int device_track_launch(ef_tracker * t, const float * trans, const float * rot, int rgb_only, float icp_weight, int pyramid, int fast_odom, int so3)
+int EF_TRACK_FN(device_track_launch)(ef_tracker * t, const float * trans, const float * rot, int rgb_only, float icp_weight, int pyramid, int fast_odom, int so3)
 {
     DeviceTrack * d = static_cast<DeviceTrack *>(t->track_state);
     if(!d) return EF_ERR_BAD_STATE;
@@ -1539,7 +1554,7 @@ int device_track_launch(ef_tracker * t, const float * trans, const float * rot, 
     return EF_OK;
 }
 
-int device_track_finish(ef_tracker * t, float * trans, float * rot)
+int EF_TRACK_FN(device_track_finish)(ef_tracker * t, float * trans, float * rot)
 {
     DeviceTrack * d = static_cast<DeviceTrack *>(t->track_state);
     if(!d) return EF_ERR_BAD_STATE;

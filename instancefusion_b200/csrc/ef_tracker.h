@@ -70,6 +70,7 @@ struct ef_tracker
     float * stage_v, * stage_n;
 
     // persistent-kernel state (EF_SOLVE_DEVICE)
+    int track_variant;  // threads per CTA of the tracker-kernel build this handle uses (ef_track_dispatch.cu)
     void * track_state; // device TrackState
     void * h_track_out; // pinned TrackOutput
     bool launch_pending;
