@@ -268,7 +268,7 @@ __device__ __forceinline__ Mat33 mat_from(const float * m)
 // ------------------------------------------------------------------------------------------------
 struct Solver
 {
-    double resultRt[16];
+    double resultRt[32];                          // 3x4 block row-major in [0, 12); [12, 32) is scratch so that all lanes may store
     double last_S[27];                            // combined normal equations of the last solve (lastA / lastb)
     double so3_R[9], so3_lastR[9];
     float Rcurr[9], tcurr[3];
@@ -277,6 +277,20 @@ struct Solver
     float last_icp_error, last_icp_count, last_rgb_error, last_rgb_count, last_so3_error, last_so3_count;
     int so3_iterations, se3_iterations[3];
 };
+
+// 1 / d to double precision without the IEEE-division slow path: hardware seed (2^-20) + two Newton steps
+// (error < 2^-52 relative; the pivots of the SPD normal equations are normal numbers); 0 -> 0 like the scalar routine
+__device__ __forceinline__ double fast_rcp(double d)
+{
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+    r = fma(fma(-d, r, 1.0), r, r);
+    r = fma(fma(-d, r, 1.0), r, r);
+    return (d != 0.0) ? r : 0.0;
+}
+
+// warps 0 and 1 of CTA 0: hand-over of resultRt from the solver warp to the warp that derives the photometric warp
+__device__ __forceinline__ void solver_pair_sync() { asm volatile("bar.sync 1, 64;" ::: "memory"); }
 
 __device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(kFullMask, v, src); }
 __device__ __forceinline__ float shfl_f(float v, int src) { return __shfl_sync(kFullMask, v, src); }
@@ -287,7 +301,7 @@ __device__ __forceinline__ float shfl_f(float v, int src) { return __shfl_sync(k
 // double-precision operation per lane and step -- no arrays, no local memory, ~30 registers.  All in double like the
 // reference.  s_final (shared memory): ICP accumulator [0, 29) followed by the RGB accumulator [29, 58).
 __device__ __forceinline__ void warp_solve_se3(Solver * S, const float * s_final, int icp, int rgb, float icp_weight, int level,
-                                               long long * dbg = nullptr)
+                                               bool hand_over, long long * dbg = nullptr)
 {
     long long tk[5] = {0, 0, 0, 0, 0};
     if(dbg) tk[0] = clock64();
@@ -318,7 +332,7 @@ __device__ __forceinline__ void warp_solve_se3(Solver * S, const float * s_final
     {
         const int pj = j * 7 - (j * (j - 1)) / 2;
         const double dj = shfl_d(a, pj);
-        const double inv = (dj != 0.0) ? 1.0 / dj : 0.0;
+        const double inv = fast_rcp(dj);
         const bool trail = live && r > j;
         const double ajr = shfl_d(a, trail ? pj + (r - j) : lane);
         const double ajc = shfl_d(a, trail ? pj + (c - j) : lane);
@@ -347,23 +361,42 @@ __device__ __forceinline__ void warp_solve_se3(Solver * S, const float * s_final
     const int e = lane < 9 ? lane : 0;
     const int er = e / 3, ec = e - er * 3;
     double rx = x[3], ry = x[4], rz = x[5];
-    const double theta = sqrt(rx * rx + ry * ry + rz * rz);
+    const double t2 = rx * rx + ry * ry + rz * rz;
     const double eye = (er == ec) ? 1.0 : 0.0;
+    const double ra = (er == 0) ? rx : (er == 1) ? ry : rz;
+    const double rb = (ec == 0) ? rx : (ec == 1) ? ry : rz;
+    // r_x = [0 -rz ry; rz 0 -rx; -ry rx 0]
+    double sk = 0.0;
+    sk = (e == 1) ? -rz : sk; sk = (e == 2) ? ry : sk; sk = (e == 3) ? rz : sk;
+    sk = (e == 5) ? -rx : sk; sk = (e == 6) ? -ry : sk; sk = (e == 7) ? rx : sk;
     double Re = eye;
-    if(theta >= 2.2204460492503131e-16)
+    if(t2 < 0.0625)
     {
+        // R = cos(t) I + (1 - cos t) r^ r^T + sin(t) [r^]x  with r^ = r / t  (:52-68)
+        //   = (1 - B t^2) I + B r r^T + A [r]x,  A = sin(t)/t, B = (1 - cos t)/t^2: two short alternating series in t^2
+        // (|t| < 0.25 rad: 9 terms reach 2^-60), no square root, no division, no argument reduction -- a Gauss-Newton
+        // update of a tracked frame is a few milliradians.  Equal to the closed form to double rounding; t -> 0 gives the
+        // identity, which is also what the reference returns below DBL_EPSILON (:45).
+        double A = 1.0 / 121645100408832000.0, B = 1.0 / 2432902008176640000.0; // 1/19!, 1/20!
+        A = fma(-t2, A, 1.0 / 355687428096000.0);    B = fma(-t2, B, 1.0 / 6402373705728000.0);  // 1/17!, 1/18!
+        A = fma(-t2, A, 1.0 / 1307674368000.0);      B = fma(-t2, B, 1.0 / 20922789888000.0);    // 1/15!, 1/16!
+        A = fma(-t2, A, 1.0 / 6227020800.0);         B = fma(-t2, B, 1.0 / 87178291200.0);       // 1/13!, 1/14!
+        A = fma(-t2, A, 1.0 / 39916800.0);           B = fma(-t2, B, 1.0 / 479001600.0);         // 1/11!, 1/12!
+        A = fma(-t2, A, 1.0 / 362880.0);             B = fma(-t2, B, 1.0 / 3628800.0);           // 1/9!,  1/10!
+        A = fma(-t2, A, 1.0 / 5040.0);               B = fma(-t2, B, 1.0 / 40320.0);             // 1/7!,  1/8!
+        A = fma(-t2, A, 1.0 / 120.0);                B = fma(-t2, B, 1.0 / 720.0);               // 1/5!,  1/6!
+        A = fma(-t2, A, 1.0 / 6.0);                  B = fma(-t2, B, 1.0 / 24.0);                // 1/3!,  1/4!
+        A = fma(-t2, A, 1.0);                        B = fma(-t2, B, 0.5);                       // 1/1!,  1/2!
+        Re = fma(-B, t2, 1.0) * eye + B * (ra * rb) + A * sk;
+    }
+    else
+    {
+        const double theta = sqrt(t2);
         double sn, cs;
         sincos(theta, &sn, &cs);
         const double c1 = 1. - cs;
-        const double itheta = theta ? 1. / theta : 0.;
-        rx *= itheta; ry *= itheta; rz *= itheta;
-        const double ra = (er == 0) ? rx : (er == 1) ? ry : rz;
-        const double rb = (ec == 0) ? rx : (ec == 1) ? ry : rz;
-        // r_x = [0 -rz ry; rz 0 -rx; -ry rx 0]
-        double sk = 0.0;
-        sk = (e == 1) ? -rz : sk; sk = (e == 2) ? ry : sk; sk = (e == 3) ? rz : sk;
-        sk = (e == 5) ? -rx : sk; sk = (e == 6) ? -ry : sk; sk = (e == 7) ? rx : sk;
-        Re = cs * eye + c1 * (ra * rb) + sn * sk;
+        const double itheta = 1. / theta;
+        Re = cs * eye + c1 * ((ra * itheta) * (rb * itheta)) + sn * (sk * itheta);
     }
 
     if(dbg) tk[3] = clock64();
@@ -375,6 +408,10 @@ __device__ __forceinline__ void warp_solve_se3(Solver * S, const float * s_final
     N = fma(shfl_d(Re, r4 * 3 + 1), shfl_d(rt, 1 * 4 + c4), N);
     N = fma(shfl_d(Re, r4 * 3 + 2), shfl_d(rt, 2 * 4 + c4), N);
     N += (c4 == 3) ? ((r4 == 0) ? x[0] : (r4 == 1) ? x[1] : x[2]) : 0.0;
+    // resultRt is complete: store it (every lane stores -- lanes >= 12 into scratch -- so the warp stays converged for the
+    // shuffles below) and let warp 1 derive the photometric warp from it while this warp composes the pose
+    S->resultRt[lane] = N;
+    if(hand_over) solver_pair_sync();
 
     // :571-583: [Rcurr | tcurr] = [Rprev | tprev] * (float(resultRt))^-1 with the Isometry3f inverse (R^T, -R^T t), float
     const float orf = (float)N; // oR(i, k) on lane i * 4 + k, ot(i) on lane i * 4 + 3
@@ -395,7 +432,6 @@ __device__ __forceinline__ void warp_solve_se3(Solver * S, const float * s_final
         dbg[4] = tk[4] - tk[3]; // update + compose
     }
     if(live) S->last_S[lane] = a_in;
-    if(lane < 12) S->resultRt[r4 * 4 + c4] = N;
     if(lane < 9) S->Rcurr[lane] = Rc;
     if(lane < 3) S->tcurr[lane] = tc;
     if(lane == 0)
@@ -1027,11 +1063,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_track(const __grid_constant__ T
 
     // CTA 0: collect the outstanding row round, add the rows in worker order, run the reference's host step
     // (:541-583) in the solver thread
-    auto solve_pending = [&]() {
+    auto solve_pending = [&](bool hand_over) {
         gather_rows(A.rows, W, kRowChunks, arr, s_rows, s_red, s_final);
         stamp(2);
         if(warp == 0)
-            warp_solve_se3(S, s_final, A.icp, A.rgb, A.icp_weight, pending_level,
+            warp_solve_se3(S, s_final, A.icp, A.rgb, A.icp_weight, pending_level, hand_over,
                            (TIMING && dbg_it < kMaxIters) ? A.dbg + (size_t)dbg_it * kDbgStamps : nullptr);
         stamp(3);
     };
@@ -1086,19 +1122,25 @@ __global__ void __launch_bounds__(kThreads, 1) k_track(const __grid_constant__ T
             bool anyI = false;
             if(is_solver_cta)
             {
-                if(pending) solve_pending();
+                const bool was_pending = pending;
+                if(pending) solve_pending(A.rgb != 0); // warp 1 takes resultRt over right after the SE(3) update
                 if(is_solver && first_of_level) S->last_rgb_error = FLT_MAX; // :420
                 if(warp == 0)
                 {
+                    // (with a solve pending the hand-over to warp 1 happened inside warp_solve_se3, right after the SE(3) update)
+                    if(!was_pending && A.rgb) solver_pair_sync();
                     float * par = s_par[rel & 1u];
                     warp_make_pose(S, par);
                     warp_publish(A.par, par, 0, 4, rel);
                     stamp(7);
-                    if(A.rgb)
-                    {
-                        warp_make_rgb_params(S, par, L.fx, L.fy, L.cx, L.cy, L.K_inv);
-                        warp_publish(A.par, par, 4, 4, rel);
-                    }
+                }
+                else if(warp == 1 && A.rgb)
+                {
+                    // the photometric warp K R K^-1, K t of this iteration, in parallel with warp 0's pose composition
+                    solver_pair_sync();
+                    float * par = s_par[rel & 1u];
+                    warp_make_rgb_params(S, par, L.fx, L.fy, L.cx, L.cy, L.K_inv);
+                    warp_publish(A.par, par, 4, 4, rel);
                 }
                 stamp(1);
             }
@@ -1288,7 +1330,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_track(const __grid_constant__ T
     }
     if(is_solver_cta)
     {
-        if(pending) solve_pending();
+        if(pending) solve_pending(false);
         else gather_rows(A.rows, W, kSo3Chunks, arr, s_rows, s_red, s_final);
     }
     if(is_solver)
