@@ -6,20 +6,22 @@
 // blocking D2H copies per iteration (57+ host round trips per frame).  Here one CTA per SM stays
 // resident for the whole solve and an iteration costs a handful of L2 round trips:
 //
-//   level start  every worker CTA evaluates the ITERATION-INVARIANT photometric gates of its pixels once
-//             (16-pixel border, gradient magnitude, depth validity, 4x4 validity window: reduce.cu:779-811) and
-//             compacts the survivors, in a fixed order, into a candidate list in SHARED memory (pixel, intensity,
-//             gradients, depth = 12 B each).  This runs while the solver CTA is still busy with the previous solve.
-//   phase A1  photometric association of the candidates (warp + gather + accept, reduce.cu:813-830) ->
-//             8-byte match records in shared memory; ONE 64-bit atomic per CTA carries
-//             arrivals | count | sum diff^2 ("barrier B": the robust weight needs the global sums).
-//   phase A2  ICP association + 29 sums in registers over 4-pixel units (128-bit loads); hides barrier B.
+//   level start  every worker CTA (147 of them; pixels are dealt round-robin in 32-pixel chunks) derives dIdx / dIdy of its
+//             pixels (computeDerivativeImages fused in), evaluates the ITERATION-INVARIANT photometric gates once (16-pixel
+//             border, gradient magnitude, depth validity, 4x4 validity window: reduce.cu:779-811), compacts the survivors in
+//             a fixed order into a candidate list in SHARED memory (pixel, intensity, gradients, depth = 12 B each) and stages
+//             the current-frame vertices / normals of its pixels there too.  This overlaps the previous level's last solve.
+//   phase A1  photometric association of the candidates (warp + gather + accept, reduce.cu:813-830) -> 8-byte match
+//             records in shared memory; the CTA's {count, sum diff^2} leaves as ONE flagged chunk ("barrier B": the robust
+//             weight needs the global sums); CTA 0 adds the 147 arrivals and answers every worker with one chunk.
+//   phase A2  ICP association + 29 sums in registers, 3 pixels of a thread interleaved, no control flow; hides barrier B.
 //   phase B   photometric rows from the records in shared memory -> 29 more sums.
 //   reduce    transpose-reduce butterfly per warp (skipped by warps that had no pixel) -> per-CTA 58-float row ->
 //             published as flagged 16-byte chunks.
-//   solve     CTA 0 polls all rows with independent loads in flight, adds them in worker order (deterministic),
-//             ONE thread runs the reference's host step in double (LDL^T, exp map, pose composition;
-//             ef_hostmath.h) out of shared memory and publishes the next parameters as 8 flagged chunks.
+//   solve     CTA 0 polls all rows with up to 12 independent loads in flight per thread, adds them in worker order
+//             (deterministic); its WARP 0 runs the reference's host step in double with the 27 normal-equation entries
+//             spread over the lanes (LDL^T, exp map, SE(3) update, pose composition), warp 1 derives the photometric warp
+//             K R K^-1, K t meanwhile; both publish their half of the parameter line as flagged chunks, 8 replicas.
 //
 // No DataTerm image, no point cloud, no reduceSum launch, no host involvement until the final pose is
 // stored straight into pinned host memory.  Co-residency of the spinning CTAs is guaranteed by a
