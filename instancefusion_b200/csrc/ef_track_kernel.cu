@@ -81,6 +81,7 @@ constexpr int kLineChunks = 8;   // the parameter line = 8 x (3 floats + flag) =
 constexpr int kPayload = kLineChunks * 3;
 constexpr int kParts = kThreads / 64; // final cross-CTA sum: kParts x 64 slots
 constexpr int kGatherBatch = 12; // row chunks a CTA-0 thread requests before it examines the first (147 x 20 / 256 = 11.5)
+constexpr int kCompactGroup = 4; // passes of the level-start compaction evaluated together
 constexpr int kMaxGrid = 255;    // CTAs of one launch (sizes the control buffers)
 constexpr unsigned kNoMatch = 0xffffffffu;
 constexpr int kCandBytes = 20;   // 12-byte candidate + 8-byte match record
@@ -598,82 +599,103 @@ struct CandStore
 
 // Level start: the iteration-invariant gates of RGBResidual::getProducts (reduce.cu:779-811) for this CTA's pixels,
 // survivors compacted in (pass, warp, lane) order.  Returns the candidate count (uniform over the CTA).
+// the gates of one pixel (pass p of this thread); returns whether it is a candidate and its packed words
 template<bool DERIV>
-__device__ __forceinline__ int compact_candidates(const LevelArgs & L, const RgbResParams & RP, const UnitIter & U, int passes, const CandStore & C,
-                                                  int * s_wtot /*[2][kWarps]*/)
+__device__ __forceinline__ bool candidate_of(const LevelArgs & L, const RgbResParams & RP, int u, unsigned & w0, unsigned & w1, float & d1)
 {
     const int cols = L.cols;
+    w0 = w1 = 0;
+    d1 = 0.f;
+    if(u < 0) return false;
+    bool keep = false;
+    const int y = u / cols, x = u - y * cols;
+    short gx = 0, gy = 0;
+    if constexpr(DERIV)
+    {
+        // computeDerivativeImages (cudafuncs.cu:583-639) fused in: this CTA's pixels of dIdx / dIdy, kept in global
+        // memory as well because they are an output of the call (ef_tracker_download) and input of host-solve mode
+        const uint8_t * img = L.next_image;
+        derivative_px([&](int j, int i) { return __ldg(img + (size_t)j * cols + i); }, L.rows, cols, x, y, gx, gy);
+        L.dIdx[u] = gx;
+        L.dIdy[u] = gy;
+    }
+    // the 16-pixel border of RGBResidual (:779-783)
+    if(y >= 16 && y < L.rows - 16 && x >= 16 && x < cols - 16)
+    {
+        const size_t o = (size_t)y * cols + x;
+        if constexpr(!DERIV)
+        {
+            gx = L.dIdx[o];
+            gy = L.dIdy[o];
+        }
+        d1 = L.next_depth[o];
+        if(rgb_gate(RP, x, y, gx, gy, d1))
+        {
+            // 4x4 window [y-2, y+2) x [x-2, x+2) of the next image must be non-zero (:787-793): per row the four
+            // bytes are cut out of the aligned 8-byte run that holds them
+            unsigned win = 0xffffffffu, inext = 0;
+#pragma unroll
+            for(int r = -2; r < 2; r++)
+            {
+                const size_t lin = (size_t)(y + r) * cols + x - 2;
+                const unsigned * wp = reinterpret_cast<const unsigned *>(L.next_image + (lin & ~(size_t)3));
+                const unsigned bytes = __funnelshift_r(__ldg(wp), __ldg(wp + 1), 8 * (unsigned)(lin & 3));
+                win &= __vcmpne4(bytes, 0u);
+                if(r == 0) inext = (bytes >> 16) & 0xffu; // I_next(x, y)
+            }
+            keep = (win == 0xffffffffu);
+            w0 = (unsigned)x | ((unsigned)y << 12) | (inext << 24);
+            w1 = ((unsigned)gx & 0xffffu) | ((unsigned)gy << 16);
+        }
+    }
+    return keep;
+}
+
+// Level start: the iteration-invariant gates of RGBResidual::getProducts (reduce.cu:779-811) for this CTA's pixels,
+// survivors compacted in (pass, warp, lane) order.  kCompactGroup passes are evaluated together (their loads overlap)
+// and share one CTA barrier.  Returns the candidate count (uniform over the CTA).
+template<bool DERIV>
+__device__ __forceinline__ int compact_candidates(const LevelArgs & L, const RgbResParams & RP, const UnitIter & U, int passes, const CandStore & C,
+                                                  int * s_wtot /*[2][kCompactGroup][kWarps]*/)
+{
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     int base = 0;
-    for(int p = 0; p < passes; p++)
+    for(int p0 = 0, grp = 0; p0 < passes; p0 += kCompactGroup, grp++)
     {
-        const int u = U.unit(p);
-        unsigned w0 = 0, w1 = 0;
-        float d1 = 0.f;
-        bool keep = false;
-        if(u >= 0)
-        {
-            const int y = u / cols, x = u - y * cols;
-            short gx = 0, gy = 0;
-            if constexpr(DERIV)
-            {
-                // computeDerivativeImages (cudafuncs.cu:583-639) fused in: this CTA's pixels of dIdx / dIdy, kept in global
-                // memory as well because they are an output of the call (ef_tracker_download) and input of host-solve mode
-                const uint8_t * img = L.next_image;
-                derivative_px([&](int j, int i) { return __ldg(img + (size_t)j * cols + i); }, L.rows, cols, x, y, gx, gy);
-                L.dIdx[u] = gx;
-                L.dIdy[u] = gy;
-            }
-            // the 16-pixel border of RGBResidual (:779-783)
-            if(y >= 16 && y < L.rows - 16 && x >= 16 && x < cols - 16)
-            {
-                const size_t o = (size_t)y * cols + x;
-                if constexpr(!DERIV)
-                {
-                    gx = L.dIdx[o];
-                    gy = L.dIdy[o];
-                }
-                d1 = L.next_depth[o];
-                if(rgb_gate(RP, x, y, gx, gy, d1))
-                {
-                    // 4x4 window [y-2, y+2) x [x-2, x+2) of the next image must be non-zero (:787-793): per row the four
-                    // bytes are cut out of the aligned 8-byte run that holds them
-                    unsigned win = 0xffffffffu, inext = 0;
+        unsigned w0[kCompactGroup], w1[kCompactGroup], ballot[kCompactGroup];
+        float d1[kCompactGroup];
+        bool keep[kCompactGroup];
+        int * wt = s_wtot + (grp & 1) * kCompactGroup * kWarps;
 #pragma unroll
-                    for(int r = -2; r < 2; r++)
-                    {
-                        const size_t lin = (size_t)(y + r) * cols + x - 2;
-                        const unsigned * wp = reinterpret_cast<const unsigned *>(L.next_image + (lin & ~(size_t)3));
-                        const unsigned bytes = __funnelshift_r(__ldg(wp), __ldg(wp + 1), 8 * (unsigned)(lin & 3));
-                        win &= __vcmpne4(bytes, 0u);
-                        if(r == 0) inext = (bytes >> 16) & 0xffu; // I_next(x, y)
-                    }
-                    keep = (win == 0xffffffffu);
-                    w0 = (unsigned)x | ((unsigned)y << 12) | (inext << 24);
-                    w1 = ((unsigned)gx & 0xffffu) | ((unsigned)gy << 16);
-                }
-            }
+        for(int g = 0; g < kCompactGroup; g++)
+            keep[g] = candidate_of<DERIV>(L, RP, (p0 + g < passes) ? U.unit(p0 + g) : -1, w0[g], w1[g], d1[g]);
+#pragma unroll
+        for(int g = 0; g < kCompactGroup; g++)
+        {
+            ballot[g] = __ballot_sync(kFullMask, keep[g]);
+            if(lane == 0) wt[g * kWarps + warp] = __popc(ballot[g]);
         }
-        const unsigned ballot = __ballot_sync(kFullMask, keep);
-        int * wt = s_wtot + (p & 1) * kWarps;
-        if(lane == 0) wt[warp] = __popc(ballot);
         __syncthreads();
-        int woff = 0, tot = 0;
 #pragma unroll
-        for(int w = 0; w < kWarps; w++)
+        for(int g = 0; g < kCompactGroup; g++)
         {
-            const int v = wt[w];
-            tot += v;
-            woff += (w < (int)warp) ? v : 0;
+            int woff = 0, tot = 0;
+#pragma unroll
+            for(int w = 0; w < kWarps; w++)
+            {
+                const int v = wt[g * kWarps + w];
+                tot += v;
+                woff += (w < (int)warp) ? v : 0;
+            }
+            if(keep[g])
+            {
+                const int pos = base + woff + __popc(ballot[g] & ((1u << lane) - 1u));
+                C.c0[pos] = w0[g];
+                C.c1[pos] = w1[g];
+                C.c2[pos] = d1[g];
+            }
+            base += tot;
         }
-        if(keep)
-        {
-            const int pos = base + woff + __popc(ballot & ((1u << lane) - 1u));
-            C.c0[pos] = w0;
-            C.c1[pos] = w1;
-            C.c2[pos] = d1;
-        }
-        base += tot;
     }
     __syncthreads();
     return base;
@@ -869,7 +891,9 @@ __device__ __forceinline__ bool icp_batch(const LevelArgs & L, const IcpParams &
 }
 
 // all ICP passes [p_begin, p_end) of this thread in batches of kIcpBatch; the remainder runs in a batch of its own
-// size so that no empty pixel slot is computed (p_begin, p_end are uniform over the CTA)
+// size so that no empty pixel slot is computed (p_begin, p_end are uniform over the CTA).  (Software-pipelining the
+// batches -- gathers of batch k+1 issued before batch k is finished -- was measured: no gain in the ICP phase, which
+// is bound by instruction issue with two warps per scheduler, and the 255 registers it needs slow the other phases.)
 template<bool SMEM>
 __device__ __forceinline__ bool icp_passes(const LevelArgs & L, const IcpParams & IP, const UnitIter & U, int p_begin, int p_end, float * accI,
                                            const float * s_vn, int cap)
@@ -901,7 +925,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_track(const __grid_constant__ T
     __shared__ float s_par[2][kPayload];
     __shared__ float s_sigma[3];                // sigmaVal, rgbError, (float)rgbSize of the current iteration
     __shared__ int s_wcnt[kWarps], s_wsig[kWarps];
-    __shared__ int s_wtot[2 * kWarps];
+    __shared__ int s_wtot[2 * kCompactGroup * kWarps];
     __shared__ int s_flag;
     __shared__ Solver s_solver;
 
