@@ -179,6 +179,8 @@ def run_ours(args, rank, world, device):
 
     def make():
         tr = ef.RGBDOdometry(args.width, args.height, K.cx, K.cy, K.fx, K.fy, solve_mode=mode)
+        if os.environ.get("EF_FRAME_BUILD"):  # A/B switch for experiments: EF_OPT_FRAME_BUILD 0 / 1 / 2
+            tr.set_option(RO.EF_OPT_FRAME_BUILD, int(os.environ["EF_FRAME_BUILD"]))
         return tr
 
     tr = make()

@@ -160,6 +160,7 @@ EF_API int ef_tracker_create(int width, int height, float cx, float cy, float fx
     t->launches = 0;
     t->grid_ctas = 0;
     t->aux_streams = 1;
+    t->frame_build = 1;
     for(int i = 0; i < kNumAux; i++)
     {
         t->aux[i] = nullptr;
@@ -311,6 +312,10 @@ EF_API int ef_tracker_set_option(ef_tracker * t, int key, int value)
         t->aux_streams = value ? 1 : 0;
         return EF_OK;
     }
+    case EF_OPT_FRAME_BUILD:
+        if(value < 0 || value > 2) return fail(t, EF_ERR_INVALID_ARGUMENT, "bad frame-build mode");
+        t->frame_build = value;
+        return EF_OK;
     case EF_OPT_GRID_CTAS:
         if(t->launch_pending) return fail(t, EF_ERR_BAD_STATE, "a launch is pending");
     {
@@ -341,6 +346,7 @@ EF_API int ef_tracker_get_option(ef_tracker * t, int key, int * value)
     case EF_OPT_PROFILE: *value = t->profile; return EF_OK;
     case EF_OPT_GRID_CTAS: *value = t->grid_ctas; return EF_OK;
     case EF_OPT_AUX_STREAMS: *value = t->aux_streams; return EF_OK;
+    case EF_OPT_FRAME_BUILD: *value = t->frame_build; return EF_OK;
     default: return EF_ERR_INVALID_ARGUMENT;
     }
 }
@@ -997,7 +1003,58 @@ EF_API int ef_track_frame_to_model_launch(ef_tracker * t, const ef_frame_inputs 
     if(!t || !in || !pose) return EF_ERR_INVALID_ARGUMENT;
     if(!in->vertices_rgba32f || !in->normals_rgba32f || !in->model_rgba8 || !in->depth || !in->rgba8) return EF_ERR_INVALID_ARGUMENT;
     int rc = EF_OK;
-    if(t->fused_build && t->aux_streams && !in->on_host)
+    if(t->fused_build && (in->on_host ? t->frame_build == 2 : t->frame_build >= 1))
+    {
+        // k_build_frame (ef_build_fused.cu): all five inputs are known at once, so every pyramid of the frame comes from
+        // one launch -- no chained kernels, no stream forks and joins; the tracker kernel follows on the same stream.
+        rc = join_streams(t);
+        if(rc) return rc;
+        ef::FrameBuildArgs a;
+        a.rows = t->height;
+        a.cols = t->width;
+        a.v4 = static_cast<const float *>(in->vertices_rgba32f);
+        a.n4 = static_cast<const float *>(in->normals_rgba32f);
+        a.model_rgba = static_cast<const uint8_t *>(in->model_rgba8);
+        a.depth = static_cast<const uint16_t *>(in->depth);
+        a.rgba = static_cast<const uint8_t *>(in->rgba8);
+        if(in->on_host)
+        {
+            const size_t n = t->dims[0].n();
+            EF_CUDA(t, cudaMemcpyAsync(t->stage_v, a.v4, n * 16, cudaMemcpyHostToDevice, t->stream));
+            EF_CUDA(t, cudaMemcpyAsync(t->stage_n, a.n4, n * 16, cudaMemcpyHostToDevice, t->stream));
+            EF_CUDA(t, cudaMemcpyAsync(t->stage_rgba_model, a.model_rgba, n * 4, cudaMemcpyHostToDevice, t->stream));
+            EF_CUDA(t, cudaMemcpyAsync(t->stage_depth, a.depth, n * 2, cudaMemcpyHostToDevice, t->stream));
+            EF_CUDA(t, cudaMemcpyAsync(t->stage_rgba, a.rgba, n * 4, cudaMemcpyHostToDevice, t->stream));
+            a.v4 = t->stage_v;
+            a.n4 = t->stage_n;
+            a.model_rgba = t->stage_rgba_model;
+            a.depth = t->stage_depth;
+            a.rgba = t->stage_rgba;
+        }
+        a.depth_pitch_bytes = 0;
+        const float R[9] = {pose[0], pose[1], pose[2], pose[4], pose[5], pose[6], pose[8], pose[9], pose[10]};
+        memcpy(a.R, R, sizeof(R));
+        a.t[0] = pose[3]; a.t[1] = pose[7]; a.t[2] = pose[11];
+        a.depth_cutoff = in->depth_cutoff;
+        a.rgb_depth_cutoff = t->max_depth_rgb;
+        a.tmp_z = t->tmp_z;
+        for(int i = 0; i < kNumPyrs; ++i)
+        {
+            level_intr(t, i, a.fx[i], a.fy[i], a.cx[i], a.cy[i]);
+            a.vmap_g_prev[i] = t->vmap_g_prev[i];
+            a.nmap_g_prev[i] = t->nmap_g_prev[i];
+            a.vmap_curr[i] = t->vmap_curr[i];
+            a.nmap_curr[i] = t->nmap_curr[i];
+            a.depth_pyr[i] = t->depth_tmp[i];
+            a.next_image[i] = t->next_image[i];
+            a.last_image[i] = t->last_image[i];
+            a.next_depth[i] = t->next_depth[i];
+            a.last_depth[i] = t->last_depth[i];
+        }
+        t->deriv_valid = false;
+        EF_LAUNCH(t, launch_build_frame(a, t->stream));
+    }
+    else if(t->fused_build && t->aux_streams && !in->on_host)
     {
         // (Host inputs keep the five-call order below: there the copies are the bound, and builders that trickle in between
         // them delay the cooperative launches of the OTHER handles taking turns on the GPU -- measured 3 640 -> 3 040 frames/s.)

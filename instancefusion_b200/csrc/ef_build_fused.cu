@@ -50,16 +50,16 @@ struct MapsOut
 };
 
 template<bool TRANSFORM>
-__global__ void __launch_bounds__(256) k_build_maps(const float4 * __restrict__ vsrc, const float4 * __restrict__ nsrc, int rows, int cols,
-                                                    MapsOut out, float * __restrict__ tmp_z, Mat33 R, float3 t)
+__device__ __forceinline__ void build_maps_block(int block_x, int block_y, const float4 * __restrict__ vsrc, const float4 * __restrict__ nsrc, int rows,
+                                                 int cols, const MapsOut & out, float * __restrict__ tmp_z, const Mat33 & R, const float3 & t)
 {
     const int lane = threadIdx.x & 31;
     const int warp_in_block = threadIdx.x >> 5;
     const int xp = lane & 1, yp = (lane >> 1) & 1, xb = lane >> 2;
     const int cols1 = cols >> 1, rows1 = rows >> 1, cols2 = cols >> 2, rows2 = rows >> 2;
     // a warp covers 16 x 2 level-1 pixels; blockDim.x = 256 = 8 warps side by side in x
-    const int x1 = (blockIdx.x * 8 + warp_in_block) * 16 + xb * 2 + xp;
-    const int y1 = blockIdx.y * 2 + yp;
+    const int x1 = (block_x * 8 + warp_in_block) * 16 + xb * 2 + xp;
+    const int y1 = block_y * 2 + yp;
     const bool inside = x1 < cols1 && y1 < rows1;
 
     float3 v1 = make_float3(0.f, 0.f, 0.f), n1 = v1;
@@ -170,6 +170,13 @@ __global__ void __launch_bounds__(256) k_build_maps(const float4 * __restrict__ 
         store3(out.v[2], plane2, idx2, vok, vo);
         store3(out.n[2], plane2, idx2, nok && !isnan(n2.x), no);
     }
+}
+
+template<bool TRANSFORM>
+__global__ void __launch_bounds__(256) k_build_maps(const float4 * __restrict__ vsrc, const float4 * __restrict__ nsrc, int rows, int cols,
+                                                    MapsOut out, float * __restrict__ tmp_z, Mat33 R, float3 t)
+{
+    build_maps_block<TRANSFORM>(blockIdx.x, blockIdx.y, vsrc, nsrc, rows, cols, out, tmp_z, R, t);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -324,6 +331,343 @@ __global__ void __launch_bounds__(256) k_derivatives3(Deriv3 D)
     D.dy[lvl][i] = gy;
 }
 
+// ------------------------------------------------------------------------------------------------
+// k_build_frame: EVERY pyramid of a frame-to-model frame (ElasticFusion.cpp:343-368: initICPModel, initRGBModel,
+// initICP(depth), initRGB) in ONE launch.  The level dependencies (level n+1 = pyrDown of level n) are resolved
+// inside a CTA instead of between launches: a CTA owns a tile of kT2W x kT2H level-2 pixels, stages the level-0
+// footprint of that tile plus the halo of the two 5x5 pyrDowns in shared memory, forms the level-1 footprint there,
+// and writes the levels of its tile.  Halo pixels are evaluated by more than one CTA (1.5x of the taps, their loads
+// are L2 hits) -- which costs less than the launch gaps and stream joins of chained kernels.  The kernel's duration
+// is the instruction stream of its longest warp, so the work is cut into many short, independent jobs:
+//   [intensity pyramid of the current image | of the model image | float depth pyramid | u16 depth levels 1, 2 with
+//    their vertex / normal maps | vertex / normal map of level 0 | model map blocks (k_build_maps)]
+// Per-pixel arithmetic: the same ef_image_px.cuh bodies as everywhere else.
+// ------------------------------------------------------------------------------------------------
+constexpr int kT2W = 16, kT2H = 8;                                 // level-2 pixels a tile owns
+constexpr int kDep1W = 2 * kT2W + 5, kDep1H = 2 * kT2H + 5;        // u16 depth: level-1 footprint (normals need +1, pyrDown +-2)
+constexpr int kDep0W = 2 * kDep1W + 3, kDep0H = 2 * kDep1H + 3;    // u16 depth: level-0 footprint
+constexpr int kRgb1W = 2 * kT2W + 3, kRgb1H = 2 * kT2H + 3;        // Gaussian pyramids: level-1 footprint
+constexpr int kRgb0W = 2 * kRgb1W + 3, kRgb0H = 2 * kRgb1H + 3;    // Gaussian pyramids: level-0 footprint
+constexpr int kBuildJobs = 6;
+
+struct FrameBuild
+{
+    int rows, cols;
+    int tiles_x, tiles_y, maps_bx, maps_by;
+    int first_block[kBuildJobs + 1];
+    // map blocks
+    const float4 * vsrc, * nsrc;
+    MapsOut maps;
+    float * tmp_z;
+    Mat33 R;
+    float3 t;
+    // depth tiles
+    const uint16_t * depth;
+    int dpitch; // elements
+    float cutoff;
+    float fx_inv[3], fy_inv[3], cx[3], cy[3];
+    float * vmap[3], * nmap[3];
+    uint16_t * depth_out[3]; // dense copy of level 0, pyrDown levels 1 and 2
+    // Gaussian pyramids: intensity of the current (0) and the model (1) image; ONE float depth pyramid written to both
+    // the "next" and the "last" set (the reference derives both from the same vmaps_tmp, RGBDOdometry.cpp:212/239/245)
+    const uint8_t * rgba[2];
+    int rgba_pitch[2]; // bytes
+    const float * z;
+    int z_stride;
+    float cutoff_rgb;
+    uint8_t * img[2][3];
+    float * dep_a[3], * dep_b[3];
+};
+
+struct alignas(16) BuildSmem
+{
+    union
+    {
+        struct
+        {
+            uint16_t d0[kDep0H][kDep0W + 1];
+            uint16_t d1[kDep1H][kDep1W + 1];
+            uint16_t d2[kT2H + 1][kT2W + 2];
+        } dep;
+        struct
+        {
+            float z0[kRgb0H][kRgb0W];
+            float z1[kRgb1H][kRgb1W];
+        } zp;
+        struct
+        {
+            uint8_t i0[kRgb0H][kRgb0W + 3];
+            uint8_t i1[kRgb1H][kRgb1W + 1];
+        } im;
+    };
+};
+
+struct TileGeom
+{
+    int rows, cols, rows1, cols1, rows2, cols2;
+    int x2_0, y2_0, x1_0, y1_0, x0_0, y0_0; // first owned pixel per level
+    int ox1, oy1, ox0, oy0;                 // origin of the level-1 / level-0 footprint
+    __device__ __forceinline__ TileGeom(const FrameBuild & P, int tile)
+    {
+        const int ty = tile / P.tiles_x, tx = tile - ty * P.tiles_x;
+        rows = P.rows; cols = P.cols; rows1 = rows >> 1; cols1 = cols >> 1; rows2 = rows1 >> 1; cols2 = cols1 >> 1;
+        x2_0 = tx * kT2W; y2_0 = ty * kT2H; x1_0 = 2 * x2_0; y1_0 = 2 * y2_0; x0_0 = 2 * x1_0; y0_0 = 2 * y1_0;
+        ox1 = x1_0 - 2; oy1 = y1_0 - 2; ox0 = 2 * ox1 - 2; oy0 = 2 * oy1 - 2;
+    }
+    __device__ __forceinline__ bool own0(int gx, int gy) const { return gx >= x0_0 && gx < x0_0 + 4 * kT2W && gy >= y0_0 && gy < y0_0 + 4 * kT2H; }
+    __device__ __forceinline__ bool own1(int gx, int gy) const { return gx >= x1_0 && gx < x1_0 + 2 * kT2W && gy >= y1_0 && gy < y1_0 + 2 * kT2H; }
+};
+
+// vertex + normal map of the pixels [x_lo, x_lo + w) x [y_lo, y_lo + h) of one level, the depth read through `at`
+template<class F>
+__device__ __forceinline__ void vn_from_depth(F at, int rows, int cols, int x_lo, int y_lo, int w, int h, float fxi, float fyi, float cx, float cy,
+                                              float cutoff, float * __restrict__ vmap, float * __restrict__ nmap)
+{
+    const size_t plane = (size_t)rows * cols;
+    for(int i = threadIdx.x; i < w * h; i += 256)
+    {
+        const int ly = i / w, lx = i - ly * w;
+        const int x = x_lo + lx, y = y_lo + ly;
+        if(x >= cols || y >= rows) continue;
+        const size_t idx = (size_t)y * cols + x;
+        const bool edge = x == cols - 1 || y == rows - 1;
+        const uint16_t d00 = at(y, x), d01 = edge ? 0 : at(y, x + 1), d10 = edge ? 0 : at(y + 1, x);
+        float3 v00, v01, v10;
+        const bool ok00 = vertex_px(d00, x, y, fxi, fyi, cx, cy, cutoff, v00);
+        const bool ok01 = vertex_px(d01, x + 1, y, fxi, fyi, cx, cy, cutoff, v01);
+        const bool ok10 = vertex_px(d10, x, y + 1, fxi, fyi, cx, cy, cutoff, v10);
+        // computeVmapKernel (:116-131): an invalid pixel only gets NaN in plane x
+        if(ok00)
+        {
+            vmap[idx] = v00.x;
+            vmap[plane + idx] = v00.y;
+            vmap[2 * plane + idx] = v00.z;
+        }
+        else
+            vmap[idx] = qnan();
+        // computeNmapKernel (:159-187)
+        if(ok00 && ok01 && ok10 && !edge)
+        {
+            const float3 n = normal_px(v00, v01, v10);
+            nmap[idx] = n.x;
+            nmap[plane + idx] = n.y;
+            nmap[2 * plane + idx] = n.z;
+        }
+        else
+            nmap[idx] = qnan();
+    }
+}
+
+// initICP(depth), level 0: no pyrDown involved, three depth reads per pixel straight from the input
+__device__ __forceinline__ void depth_level0_tile(const FrameBuild & P, int tile)
+{
+    const TileGeom G(P, tile);
+    const uint16_t * depth = P.depth;
+    const int dp = P.dpitch, cols = G.cols;
+    uint16_t * copy = P.depth_out[0];
+    vn_from_depth(
+        [&](int r, int c) {
+            const uint16_t d = __ldg(depth + (size_t)r * dp + c);
+            return d;
+        },
+        G.rows, G.cols, G.x0_0, G.y0_0, 4 * kT2W, 4 * kT2H, P.fx_inv[0], P.fy_inv[0], P.cx[0], P.cy[0], P.cutoff, P.vmap[0], P.nmap[0]);
+    // dense copy of the input (depth_tmp[0] of the reference)
+    for(int i = threadIdx.x; i < 4 * kT2W * 4 * kT2H; i += 256)
+    {
+        const int ly = i / (4 * kT2W), lx = i - ly * (4 * kT2W);
+        const int x = G.x0_0 + lx, y = G.y0_0 + ly;
+        if(x < cols && y < G.rows) copy[(size_t)y * cols + x] = __ldg(depth + (size_t)y * dp + x);
+    }
+}
+
+// initICP(depth), levels 1 and 2: bilateral pyrDown twice through shared memory, then the vertex / normal maps
+__device__ __forceinline__ void depth_level12_tile(const FrameBuild & P, BuildSmem & S, int tile)
+{
+    const TileGeom G(P, tile);
+    const int ox0 = G.ox0, oy0 = G.oy0, ox1 = G.ox1, oy1 = G.oy1;
+    // level 0 footprint; kStage loads of a thread are in flight together
+    constexpr int kStage = 7;
+    for(int i0 = threadIdx.x; i0 < kDep0W * kDep0H; i0 += kStage * 256)
+    {
+        uint16_t d[kStage];
+#pragma unroll
+        for(int k = 0; k < kStage; k++)
+        {
+            const int i = i0 + k * 256;
+            const int ly = i / kDep0W, lx = i - ly * kDep0W;
+            const int gx = ox0 + lx, gy = oy0 + ly;
+            d[k] = 0;
+            if(i < kDep0W * kDep0H && gx >= 0 && gy >= 0 && gx < G.cols && gy < G.rows) d[k] = __ldg(P.depth + (size_t)gy * P.dpitch + gx);
+        }
+#pragma unroll
+        for(int k = 0; k < kStage; k++)
+        {
+            const int i = i0 + k * 256;
+            const int ly = i / kDep0W, lx = i - ly * kDep0W;
+            if(i < kDep0W * kDep0H) S.dep.d0[ly][lx] = d[k];
+        }
+    }
+    __syncthreads();
+    auto at0 = [&](int r, int c) { return (int)S.dep.d0[r - oy0][c - ox0]; };
+    for(int i = threadIdx.x; i < kDep1W * kDep1H; i += 256)
+    {
+        const int ly = i / kDep1W, lx = i - ly * kDep1W;
+        const int gx = ox1 + lx, gy = oy1 + ly;
+        uint16_t d = 0;
+        if(gx >= 0 && gy >= 0 && gx < G.cols1 && gy < G.rows1)
+        {
+            d = pyr_down_u16_at(at0, G.rows, G.cols, gx, gy);
+            if(G.own1(gx, gy)) P.depth_out[1][(size_t)gy * G.cols1 + gx] = d;
+        }
+        S.dep.d1[ly][lx] = d;
+    }
+    __syncthreads();
+    auto at1 = [&](int r, int c) { return (int)S.dep.d1[r - oy1][c - ox1]; };
+    for(int i = threadIdx.x; i < (kT2W + 1) * (kT2H + 1); i += 256)
+    {
+        const int ly = i / (kT2W + 1), lx = i - ly * (kT2W + 1);
+        const int gx = G.x2_0 + lx, gy = G.y2_0 + ly;
+        uint16_t d = 0;
+        if(gx < G.cols2 && gy < G.rows2)
+        {
+            d = pyr_down_u16_at(at1, G.rows1, G.cols1, gx, gy);
+            if(lx < kT2W && ly < kT2H) P.depth_out[2][(size_t)gy * G.cols2 + gx] = d;
+        }
+        S.dep.d2[ly][lx] = d;
+    }
+    vn_from_depth([&](int r, int c) { return S.dep.d1[r - oy1][c - ox1]; }, G.rows1, G.cols1, G.x1_0, G.y1_0, 2 * kT2W, 2 * kT2H, P.fx_inv[1],
+                  P.fy_inv[1], P.cx[1], P.cy[1], P.cutoff, P.vmap[1], P.nmap[1]);
+    __syncthreads();
+    const int x2_0 = G.x2_0, y2_0 = G.y2_0;
+    vn_from_depth([&](int r, int c) { return S.dep.d2[r - y2_0][c - x2_0]; }, G.rows2, G.cols2, x2_0, y2_0, kT2W, kT2H, P.fx_inv[2], P.fy_inv[2],
+                  P.cx[2], P.cy[2], P.cutoff, P.vmap[2], P.nmap[2]);
+}
+
+// populateRGBDData (RGBDOdometry.cpp:208-235): one Gaussian pyramid of a tile.  DEPTH = false: intensity of image `job`;
+// DEPTH = true: the float depth pyramid (z of the model vertices), written to both depth sets.
+template<bool DEPTH>
+__device__ __forceinline__ void gauss_pyramid_tile(const FrameBuild & P, BuildSmem & S, int job, int tile)
+{
+    const TileGeom G(P, tile);
+    const int ox0 = G.ox0, oy0 = G.oy0, ox1 = G.ox1, oy1 = G.oy1;
+    const uint8_t * rgba = P.rgba[job];
+    const int pitch = P.rgba_pitch[job];
+    uint8_t * const * img = P.img[job];
+    // level 0 of the footprint, converted once per CTA; owned pixels are stored.  kStage texels of a thread are requested
+    // together (the inputs of a frame come from HBM).
+    constexpr int kStage = 6;
+    for(int i0 = threadIdx.x; i0 < kRgb0W * kRgb0H; i0 += kStage * 256)
+    {
+        uchar4 px[kStage];
+        float zz[kStage];
+#pragma unroll
+        for(int k = 0; k < kStage; k++)
+        {
+            const int i = i0 + k * 256;
+            const int ly = i / kRgb0W, lx = i - ly * kRgb0W;
+            const int gx = ox0 + lx, gy = oy0 + ly;
+            px[k] = make_uchar4(0, 0, 0, 0);
+            zz[k] = 0.f;
+            if(i < kRgb0W * kRgb0H && gx >= 0 && gy >= 0 && gx < G.cols && gy < G.rows)
+            {
+                if(DEPTH) zz[k] = __ldg(P.z + ((size_t)gy * G.cols + gx) * P.z_stride);
+                else px[k] = __ldg(reinterpret_cast<const uchar4 *>(rgba + (size_t)gy * pitch) + gx);
+            }
+        }
+#pragma unroll
+        for(int k = 0; k < kStage; k++)
+        {
+            const int i = i0 + k * 256;
+            const int ly = i / kRgb0W, lx = i - ly * kRgb0W;
+            const int gx = ox0 + lx, gy = oy0 + ly;
+            if(i < kRgb0W * kRgb0H && gx >= 0 && gy >= 0 && gx < G.cols && gy < G.rows)
+            {
+                const bool own = G.own0(gx, gy);
+                if(DEPTH)
+                {
+                    const float d = depth_from_z(zz[k], P.cutoff_rgb);
+                    S.zp.z0[ly][lx] = d;
+                    if(own)
+                    {
+                        P.dep_a[0][(size_t)gy * G.cols + gx] = d;
+                        P.dep_b[0][(size_t)gy * G.cols + gx] = d;
+                    }
+                }
+                else
+                {
+                    const uint8_t v = intensity_px(px[k]);
+                    S.im.i0[ly][lx] = v;
+                    if(own) img[0][(size_t)gy * G.cols + gx] = v;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    auto i0 = [&](int r, int c) { return S.im.i0[r - oy0][c - ox0]; };
+    auto z0 = [&](int r, int c) { return S.zp.z0[r - oy0][c - ox0]; };
+    for(int i = threadIdx.x; i < kRgb1W * kRgb1H; i += 256)
+    {
+        const int ly = i / kRgb1W, lx = i - ly * kRgb1W;
+        const int gx = ox1 + lx, gy = oy1 + ly;
+        if(gx >= 0 && gy >= 0 && gx < G.cols1 && gy < G.rows1)
+        {
+            const bool own = G.own1(gx, gy);
+            if(DEPTH)
+            {
+                const float d = pyr_down_gauss_f32_px(z0, G.rows, G.cols, gx, gy);
+                S.zp.z1[ly][lx] = d;
+                if(own)
+                {
+                    P.dep_a[1][(size_t)gy * G.cols1 + gx] = d;
+                    P.dep_b[1][(size_t)gy * G.cols1 + gx] = d;
+                }
+            }
+            else
+            {
+                const uint8_t v = pyr_down_gauss_u8_px(i0, G.rows, G.cols, gx, gy);
+                S.im.i1[ly][lx] = v;
+                if(own) img[1][(size_t)gy * G.cols1 + gx] = v;
+            }
+        }
+    }
+    __syncthreads();
+    auto i1 = [&](int r, int c) { return S.im.i1[r - oy1][c - ox1]; };
+    auto z1 = [&](int r, int c) { return S.zp.z1[r - oy1][c - ox1]; };
+    if(threadIdx.x < kT2W * kT2H)
+    {
+        const int ly = threadIdx.x / kT2W, lx = threadIdx.x - ly * kT2W;
+        const int gx = G.x2_0 + lx, gy = G.y2_0 + ly;
+        if(gx < G.cols2 && gy < G.rows2)
+        {
+            if(DEPTH)
+            {
+                const float d = pyr_down_gauss_f32_px(z1, G.rows1, G.cols1, gx, gy);
+                P.dep_a[2][(size_t)gy * G.cols2 + gx] = d;
+                P.dep_b[2][(size_t)gy * G.cols2 + gx] = d;
+            }
+            else
+                img[2][(size_t)gy * G.cols2 + gx] = pyr_down_gauss_u8_px(i1, G.rows1, G.cols1, gx, gy);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256, 5) k_build_frame(const __grid_constant__ FrameBuild P)
+{
+    __shared__ BuildSmem S;
+    const int b = blockIdx.x;
+    if(b < P.first_block[1]) depth_level12_tile(P, S, b);
+    else if(b < P.first_block[2]) gauss_pyramid_tile<true>(P, S, 0, b - P.first_block[1]);
+    else if(b < P.first_block[3]) gauss_pyramid_tile<false>(P, S, 0, b - P.first_block[2]);
+    else if(b < P.first_block[4]) gauss_pyramid_tile<false>(P, S, 1, b - P.first_block[3]);
+    else if(b < P.first_block[5]) depth_level0_tile(P, b - P.first_block[4]);
+    else
+    {
+        const int m = b - P.first_block[5];
+        const int by = m / P.maps_bx, bx = m - by * P.maps_bx;
+        build_maps_block<true>(bx, by, P.vsrc, P.nsrc, P.rows, P.cols, P.maps, P.tmp_z, P.R, P.t);
+    }
+}
+
 inline Mat33 to_mat(const float * m)
 {
     Mat33 r;
@@ -419,6 +763,53 @@ cudaError_t launch_derivatives3(const uint8_t * const img[3], int16_t * const dx
     }
     D.first_block[3] = blocks;
     k_derivatives3<<<blocks, 256, 0, s>>>(D);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_build_frame(const FrameBuildArgs & a, cudaStream_t s)
+{
+    FrameBuild P;
+    P.rows = a.rows;
+    P.cols = a.cols;
+    P.tiles_x = (a.cols + 4 * kT2W - 1) / (4 * kT2W);
+    P.tiles_y = (a.rows + 4 * kT2H - 1) / (4 * kT2H);
+    const int cols1 = a.cols / 2, rows1 = a.rows / 2;
+    P.maps_bx = (cols1 + 127) / 128;
+    P.maps_by = (rows1 + 1) / 2;
+    const int tiles = P.tiles_x * P.tiles_y;
+    for(int j = 0; j < kBuildJobs; j++) P.first_block[j] = j * tiles; // five tile jobs, then the map blocks
+    P.first_block[kBuildJobs] = (kBuildJobs - 1) * tiles + P.maps_bx * P.maps_by;
+    P.vsrc = reinterpret_cast<const float4 *>(a.v4);
+    P.nsrc = reinterpret_cast<const float4 *>(a.n4);
+    P.tmp_z = a.tmp_z;
+    P.R = to_mat(a.R);
+    P.t = make_float3(a.t[0], a.t[1], a.t[2]);
+    P.depth = a.depth;
+    P.dpitch = (int)((a.depth_pitch_bytes ? a.depth_pitch_bytes : (size_t)a.cols * 2) / 2);
+    P.cutoff = a.depth_cutoff;
+    P.rgba[0] = a.rgba;
+    P.rgba[1] = a.model_rgba;
+    P.rgba_pitch[0] = P.rgba_pitch[1] = a.cols * 4;
+    P.z = a.v4 + 2; // the depth of BOTH RGB-D pyramids is the z of the model vertices (RGBDOdometry.cpp:212)
+    P.z_stride = 4;
+    P.cutoff_rgb = a.rgb_depth_cutoff;
+    for(int i = 0; i < 3; i++)
+    {
+        P.maps.v[i] = a.vmap_g_prev[i];
+        P.maps.n[i] = a.nmap_g_prev[i];
+        P.fx_inv[i] = 1.f / a.fx[i]; // createVMap (:147)
+        P.fy_inv[i] = 1.f / a.fy[i];
+        P.cx[i] = a.cx[i];
+        P.cy[i] = a.cy[i];
+        P.vmap[i] = a.vmap_curr[i];
+        P.nmap[i] = a.nmap_curr[i];
+        P.depth_out[i] = a.depth_pyr[i];
+        P.img[0][i] = a.next_image[i];
+        P.img[1][i] = a.last_image[i];
+        P.dep_a[i] = a.next_depth[i];
+        P.dep_b[i] = a.last_depth[i];
+    }
+    k_build_frame<<<P.first_block[kBuildJobs], 256, 0, s>>>(P);
     return cudaGetLastError();
 }
 

@@ -9,33 +9,59 @@
 namespace ef
 {
 
-// pyrDownGaussKernel  cudafuncs.cu:57-94: output pixel (x, y) of the half-resolution u16 depth
-__device__ __forceinline__ uint16_t pyr_down_u16_px(const uint16_t * __restrict__ src, int sp, int srows, int scols, int x, int y)
+// pyrDownGaussKernel  cudafuncs.cu:57-94: output pixel (x, y) of the half-resolution u16 depth, the source read
+// through `at(row, col)` (global memory or a shared-memory tile)
+// Integer evaluation: the taps are {6, 4, 1} / 16 per axis, so every product val * w(xi) * w(yi) is a multiple of 2^-8 below
+// 2^16 * 9/64 and the float sums the reference forms (`sum`, `wall`) are exact in binary32 whatever their order -- the same
+// two floats come out of integer accumulators scaled by 2^-8.  Only the final division rounds, and it is the same operation.
+template<class F>
+__device__ __forceinline__ uint16_t pyr_down_u16_at(F at, int srows, int scols, int x, int y)
 {
     const int D = 5;
-    const float sigma_color = 30.f; // :103
-    const int center = __ldg(src + (size_t)(2 * y) * sp + 2 * x);
-
-    const int x_mi = max(0, 2 * x - D / 2) - 2 * x;
-    const int y_mi = max(0, 2 * y - D / 2) - 2 * y;
-    const int x_ma = min(scols, 2 * x - D / 2 + D) - 2 * x;
-    const int y_ma = min(srows, 2 * y - D / 2 + D) - 2 * y;
-
-    float sum = 0;
-    float wall = 0;
-    const float weights[] = {0.375f, 0.25f, 0.0625f};
-
-    for(int yi = y_mi; yi < y_ma; ++yi)
-        for(int xi = x_mi; xi < x_ma; ++xi)
-        {
-            const int val = __ldg(src + (size_t)(2 * y + yi) * sp + 2 * x + xi);
-            if(abs(val - center) < 3 * sigma_color)
+    const int color_gate = 90; // 3 * sigma_color, sigma_color = 30 (:64, :103)
+    const int center = at(2 * y, 2 * x);
+    int isum = 0, iwall = 0;
+    if(x >= 1 && y >= 1 && 2 * x + 2 < scols && 2 * y + 2 < srows)
+    {
+        // interior: no clamp is active
+#pragma unroll
+        for(int yi = -2; yi <= 2; ++yi)
+#pragma unroll
+            for(int xi = -2; xi <= 2; ++xi)
             {
-                sum += val * weights[abs(xi)] * weights[abs(yi)];
-                wall += weights[abs(xi)] * weights[abs(yi)];
+                const int val = at(2 * y + yi, 2 * x + xi);
+                const int w = ((xi == 0) ? 6 : (xi == 1 || xi == -1) ? 4 : 1) * ((yi == 0) ? 6 : (yi == 1 || yi == -1) ? 4 : 1);
+                const bool in = abs(val - center) < color_gate;
+                isum += in ? val * w : 0;
+                iwall += in ? w : 0;
             }
-        }
+    }
+    else
+    {
+        const int x_mi = max(0, 2 * x - D / 2) - 2 * x;
+        const int y_mi = max(0, 2 * y - D / 2) - 2 * y;
+        const int x_ma = min(scols, 2 * x - D / 2 + D) - 2 * x;
+        const int y_ma = min(srows, 2 * y - D / 2 + D) - 2 * y;
+#pragma unroll
+        for(int yi = -2; yi <= 2; ++yi)
+#pragma unroll
+            for(int xi = -2; xi <= 2; ++xi)
+            {
+                const bool in_win = yi >= y_mi && yi < y_ma && xi >= x_mi && xi < x_ma;
+                const int val = in_win ? (int)at(2 * y + yi, 2 * x + xi) : center;
+                const int w = ((xi == 0) ? 6 : (xi == 1 || xi == -1) ? 4 : 1) * ((yi == 0) ? 6 : (yi == 1 || yi == -1) ? 4 : 1);
+                const bool in = in_win && abs(val - center) < color_gate;
+                isum += in ? val * w : 0;
+                iwall += in ? w : 0;
+            }
+    }
+    const float sum = (float)isum * 0.00390625f, wall = (float)iwall * 0.00390625f;
     return static_cast<int>(sum / wall);
+}
+
+__device__ __forceinline__ uint16_t pyr_down_u16_px(const uint16_t * __restrict__ src, int sp, int srows, int scols, int x, int y)
+{
+    return pyr_down_u16_at([&](int r, int c) { return (int)__ldg(src + (size_t)r * sp + c); }, srows, scols, x, y);
 }
 
 // computeVmapKernel  cudafuncs.cu:116-131: vertex of pixel (u, v) from raw depth; returns false (invalid) when
@@ -63,12 +89,8 @@ __device__ __forceinline__ float3 normal_px(const float3 & v00, const float3 & v
     return normalized3(cross3(v01 - v00, v10 - v00));
 }
 
-// {1,4,6,4,1} (x) {1,4,6,4,1}, i = r*5 + c   (cudafuncs.cu:453-457)
-__device__ __forceinline__ float gauss5(int i)
-{
-    const float k1[5] = {1.f, 4.f, 6.f, 4.f, 1.f};
-    return k1[i / 5] * k1[i % 5];
-}
+// {1,4,6,4,1}[k], 0 <= k <= 4 (cudafuncs.cu:453-457: the 5x5 kernel is the outer product of this row with itself)
+__device__ __forceinline__ int gauss5_tap(int k) { return (0x14641 >> (4 * (k & 7))) & 15; }
 
 // pyrDownKernelGaussF  cudafuncs.cu:332-363, reading the source through `at(cy, cx)`
 template<class F>
@@ -97,20 +119,26 @@ __device__ __forceinline__ float pyr_down_gauss_f32_px(F at, int srows, int scol
             }
         return (float)(sum / (float)count);
     }
+    // border: the window [max(0, 2x-2), tx) x [max(0, 2y-2), ty) with tx / ty clamped to cols-1 / rows-1 (exclusive, :340-341)
+    // and the kernel index counted back from that clamped end (:352) -- the same raster order as the reference loop, written
+    // as 25 predicated taps so that a warp with one border pixel does not fall into a data-dependent loop
     const int tx = min(2 * x - D / 2 + D, scols - 1);
     const int ty = min(2 * y - D / 2 + D, srows - 1);
-    int cy = max(0, 2 * y - D / 2);
     float sum = 0;
     int count = 0;
-    for(; cy < ty; ++cy)
-        for(int cx = max(0, 2 * x - D / 2); cx < tx; ++cx)
+#pragma unroll
+    for(int j = 0; j < 5; j++)
+#pragma unroll
+        for(int i = 0; i < 5; i++)
         {
-            const float s = at(cy, cx);
+            const int cy = 2 * y - 2 + j, cx = 2 * x - 2 + i;
+            const bool in = cy >= 0 && cy < ty && cx >= 0 && cx < tx;
+            const float s = in ? at(cy, cx) : qnan();
             if(!isnan(s))
             {
-                const float k = gauss5((ty - cy - 1) * 5 + (tx - cx - 1));
-                sum = __fmaf_rn(s, k, sum); // the reference binary contracts `sum += s * k` into one FMA
-                count += k;
+                const int w = gauss5_tap(ty - cy - 1) * gauss5_tap(tx - cx - 1);
+                sum = __fmaf_rn(s, (float)w, sum); // the reference binary contracts `sum += s * k` into one FMA
+                count += w;
             }
         }
     return (float)(sum / (float)count);
@@ -142,23 +170,27 @@ __device__ __forceinline__ uint8_t pyr_down_gauss_u8_px(F at, int srows, int sco
         const uint8_t r = ((float)isum / (float)count);
         return r;
     }
+    // border: 25 predicated taps, kernel index counted back from the clamped window end (see pyr_down_gauss_f32_px); the
+    // float sums of the reference are exact small integers, so they are formed as integers
     const int tx = min(2 * x - D / 2 + D, scols - 1);
     const int ty = min(2 * y - D / 2 + D, srows - 1);
-    int cy = max(0, 2 * y - D / 2);
-    float sum = 0;
-    int count = 0;
-    for(; cy < ty; ++cy)
-        for(int cx = max(0, 2 * x - D / 2); cx < tx; ++cx)
+    int isum = 0, count = 0;
+#pragma unroll
+    for(int j = 0; j < 5; j++)
+#pragma unroll
+        for(int i = 0; i < 5; i++)
         {
-            const uint8_t s = at(cy, cx);
+            const int cy = 2 * y - 2 + j, cx = 2 * x - 2 + i;
+            const bool in = cy >= 0 && cy < ty && cx >= 0 && cx < tx;
+            const int s = in ? (int)at(cy, cx) : 0;
             if(s > 0)
             {
-                const float k = gauss5((ty - cy - 1) * 5 + (tx - cx - 1));
-                sum += s * k;
-                count += k;
+                const int w = gauss5_tap(ty - cy - 1) * gauss5_tap(tx - cx - 1);
+                isum += s * w;
+                count += w;
             }
         }
-    const uint8_t r = (sum / (float)count);
+    const uint8_t r = ((float)isum / (float)count);
     return r;
 }
 

@@ -46,6 +46,25 @@ cudaError_t launch_rgbd_level1(const uint8_t * img1, const float * depth1, int r
 cudaError_t launch_derivatives3(const uint8_t * const img[3], int16_t * const dx[3], int16_t * const dy[3], const int rows[3], const int cols[3],
                                 cudaStream_t s);
 
+// every pyramid of a frame-to-model frame (initICPModel + initRGBModel + initICP(depth) + initRGB) in one launch
+struct FrameBuildArgs
+{
+    int rows, cols;
+    const float * v4, * n4;      // model vertex / normal textures (RGBA32F)
+    const uint8_t * model_rgba, * rgba;
+    const uint16_t * depth;
+    size_t depth_pitch_bytes;    // 0 = dense
+    float R[9], t[3];            // pose of the model maps
+    float depth_cutoff, rgb_depth_cutoff;
+    float fx[3], fy[3], cx[3], cy[3]; // level intrinsics
+    float * vmap_g_prev[3], * nmap_g_prev[3], * tmp_z;
+    float * vmap_curr[3], * nmap_curr[3];
+    uint16_t * depth_pyr[3];
+    uint8_t * next_image[3], * last_image[3];
+    float * next_depth[3], * last_depth[3];
+};
+cudaError_t launch_build_frame(const FrameBuildArgs & a, cudaStream_t s);
+
 // ---- Tier-2 association + reduction operators (ef_ops_reduce.cu) ----
 // Scratch block layout (device): [0] ticket (u32) | [128] result (32 floats / 2 ints) | [256] partial rows
 constexpr size_t kScratchTicketOff = 0;

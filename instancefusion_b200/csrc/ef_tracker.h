@@ -42,6 +42,7 @@ struct ef_tracker
     int fused_build;
     int grid_ctas;   // EF_OPT_GRID_CTAS (0 = every SM)
     int aux_streams; // EF_OPT_AUX_STREAMS
+    int frame_build; // EF_OPT_FRAME_BUILD
 
     // internal fork/join streams for builders that are independent of each other (ef_api.cu: fork_stream / join_streams)
     cudaStream_t aux[3];            // 0: current-frame depth chain, 1: model RGB-D chain, 2: model maps (single-call entry)

@@ -162,6 +162,56 @@ def test_internal_streams_do_not_change_a_bit():
         b.close()
 
 
+def _same_maps(a, b):
+    """3-plane maps: an invalid pixel is NaN in plane x only, planes y / z are not defined there (cudafuncs.cu:116-131)"""
+    rows = a.shape[0] // 3
+    bad_a, bad_b = np.isnan(a[:rows]), np.isnan(b[:rows])
+    if not np.array_equal(bad_a, bad_b):
+        return False
+    ok = ~bad_a
+    return all(np.array_equal(a[c * rows:(c + 1) * rows][ok], b[c * rows:(c + 1) * rows][ok]) for c in range(3))
+
+
+@pytest.mark.parametrize("size", [(640, 480), (1280, 720), (200, 152), (168, 120), (204, 156)])
+def test_one_launch_frame_build_does_not_change_a_bit(size):
+    """EF_OPT_FRAME_BUILD: every pyramid of the frame from one kernel launch (k_build_frame: level dependencies resolved
+    through shared-memory tiles with halos) against the chained per-level builders -- same pyramids and pose, bit for bit,
+    for host inputs (mode 2) and device inputs (mode 1), sizes whose levels are ragged against the 64x32 tiles included"""
+    import torch
+    w, h = size
+    K, pose0, pose1, f0, f1 = util.frame_pair(w, h)
+    f1 = dict(f1, depth=util.punch_holes(f1["depth"]))
+    pose0f = pose0.astype(np.float32)
+    a = ef.RGBDOdometry(w, h, K.cx, K.cy, K.fx, K.fy, solve_mode=RO.EF_SOLVE_DEVICE)
+    b = ef.RGBDOdometry(w, h, K.cx, K.cy, K.fx, K.fy, solve_mode=RO.EF_SOLVE_DEVICE)
+    c = ef.RGBDOdometry(w, h, K.cx, K.cy, K.fx, K.fy, solve_mode=RO.EF_SOLVE_DEVICE)
+    a.set_option(RO.EF_OPT_FRAME_BUILD, 0)
+    b.set_option(RO.EF_OPT_FRAME_BUILD, 2)
+    try:
+        args = (20.0, pose0f, False, 10.0, True, False, False)
+        dev = lambda f: {k: torch.from_numpy(np.ascontiguousarray(v)).cuda() for k, v in f.items() if isinstance(v, np.ndarray)}
+        g0, g1 = dev(f0), dev(f1)
+        for rep in range(3):
+            fa, fb, ga, gb = (f0, f1, g0, g1) if rep % 2 == 0 else (f1, f0, g1, g0)
+            launches = c.launch_count
+            ra = a.trackFrameToModel(fa["vmap"], fa["nmap"], fa["rgba"], fb["depth"], fb["rgba"], *args)
+            rb = b.trackFrameToModel(fa["vmap"], fa["nmap"], fa["rgba"], fb["depth"], fb["rgba"], *args)
+            rc = c.trackFrameToModel(ga["vmap"], ga["nmap"], ga["rgba"], gb["depth"], gb["rgba"], *args)
+            assert c.launch_count - launches == 2, "builder + tracker kernel"
+            assert np.array_equal(ra[0], rb[0]) and np.array_equal(ra[1], rb[1]), rep
+            assert np.array_equal(ra[0], rc[0]) and np.array_equal(ra[1], rc[1]), rep
+        for o in (b, c):
+            for lvl in range(3):
+                for name in ("vmap_curr", "nmap_curr", "vmap_g_prev", "nmap_g_prev"):
+                    assert _same_maps(a.buffer(name, lvl), o.buffer(name, lvl)), (name, lvl)
+                for name in ("last_depth", "next_depth", "last_image", "next_image", "dIdx", "dIdy", "depth_tmp"):
+                    assert np.array_equal(a.buffer(name, lvl), o.buffer(name, lvl), equal_nan=True), (name, lvl)
+    finally:
+        a.close()
+        b.close()
+        c.close()
+
+
 def test_many_calls_on_one_handle_are_stable():
     """launch-unique epochs: 200 consecutive launches on one handle, every one returns the same bits"""
     w, h = 320, 240
