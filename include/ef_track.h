@@ -77,9 +77,9 @@ typedef struct ef_track_stats
                                     are joined before the solve; 0 = everything in order on the handle's stream */
 
 #define EF_OPT_FRAME_BUILD 7     /* single-call entry ef_track_frame_to_model: 0 = the builders of the five init* calls (chained
-                                    kernels on the internal streams), 1 (default) = every pyramid of the frame from ONE kernel
-                                    launch when the inputs are device buffers, 2 = also for host inputs (five copies, then the
-                                    one launch) */
+                                    kernels on the internal streams), 1 = every pyramid of the frame from ONE kernel launch when
+                                    the inputs are device buffers, 2 (default) = also for host inputs (five copies, then the one
+                                    launch) */
 
 #define EF_SOLVE_HOST 0   /* one step kernel per operator call, 6x6 LDLT + pose update in double on the host,
                              exactly the reference's control flow (RGBDOdometry.cpp:405-585) */

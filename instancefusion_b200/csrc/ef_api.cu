@@ -160,7 +160,7 @@ EF_API int ef_tracker_create(int width, int height, float cx, float cy, float fx
     t->launches = 0;
     t->grid_ctas = 0;
     t->aux_streams = 1;
-    t->frame_build = 1;
+    t->frame_build = 2;
     for(int i = 0; i < kNumAux; i++)
     {
         t->aux[i] = nullptr;

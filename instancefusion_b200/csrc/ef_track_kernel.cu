@@ -1402,10 +1402,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_track(const __grid_constant__ T
                     else out->st.last_A[j * 6 + i] = out->st.last_A[i * 6 + j] = v;
                 }
             }
-            out->status = 1;
         }
-        else
-            out->status = 2; // no solve ran: lastA / lastb keep their previous values (host side)
+        // the host polls `status` in pinned memory (device_track_finish): result first, fence, then the flag.
+        // 2 = no solve ran: lastA / lastb keep their previous values (host side)
+        const int status = (S->se3_iterations[0] + S->se3_iterations[1] + S->se3_iterations[2] > 0) ? 1 : 2;
+        __threadfence_system();
+        *reinterpret_cast<volatile int *>(&out->status) = status;
         __threadfence_system();
     }
 }
@@ -1626,7 +1628,31 @@ int EF_TRACK_FN(device_track_finish)(ef_tracker * t, float * trans, float * rot)
 {
     DeviceTrack * d = static_cast<DeviceTrack *>(t->track_state);
     if(!d) return EF_ERR_BAD_STATE;
-    cudaError_t e = cudaStreamSynchronize(t->stream);
+    // The solver thread stores the result straight into pinned host memory and raises `status` behind a system-scope
+    // fence, so the host takes it from there as soon as it lands instead of waiting for the kernel to retire and the
+    // driver to signal the stream (saves the completion-notification latency of every frame).  The stream is still the
+    // ordering point for everything that follows on the device; errors and timing modes take the synchronising path.
+    cudaError_t e = cudaSuccess;
+    const volatile int * flag = &d->out->status;
+    if(!t->profile && !d->dbg)
+    {
+        for(long spins = 0; *flag == 0; ++spins)
+        {
+            if((spins & 1023) == 1023)
+            {
+                e = cudaStreamQuery(t->stream);
+                if(e != cudaErrorNotReady) break; // finished (the flag is visible by now) or failed
+                e = cudaSuccess;
+            }
+#if defined(__x86_64__) || defined(__i386__)
+            __builtin_ia32_pause();
+#endif
+        }
+        __atomic_thread_fence(__ATOMIC_ACQUIRE);
+        if(e == cudaSuccess && *flag == 0) e = cudaStreamSynchronize(t->stream);
+    }
+    else
+        e = cudaStreamSynchronize(t->stream);
     if(e != cudaSuccess)
     {
         t->err = std::string("track kernel: ") + cudaGetErrorString(e);

@@ -65,10 +65,13 @@ class RGBDOdometry:
         self.lastRGBCount = float(width * height)
         self.lastSO3Error = 0.0
         self.lastSO3Count = float(width * height)
-        self.lastA = np.zeros((6, 6))
-        self.lastb = np.zeros(6)
         self.so3_iterations = 0
         self.se3_iterations = [0, 0, 0]
+        # result buffers of finish() and their addresses, made once (ctypes conversions are the bulk of a call's host time)
+        self._res = np.zeros(12, np.float32)
+        self._res_t, self._res_r = C.c_void_p(self._res.ctypes.data), C.c_void_p(self._res.ctypes.data + 12)
+        self._stats_ref = C.byref(self._stats)
+        self._frame = None
         if solve_mode != EF_SOLVE_HOST:
             self.set_option(EF_OPT_SOLVE_MODE, solve_mode)
 
@@ -178,10 +181,17 @@ class RGBDOdometry:
         self.lastICPError, self.lastICPCount = s.last_icp_error, s.last_icp_count
         self.lastRGBError, self.lastRGBCount = s.last_rgb_error, s.last_rgb_count
         self.lastSO3Error, self.lastSO3Count = s.last_so3_error, s.last_so3_count
-        self.lastA = np.array(s.last_A[:]).reshape(6, 6)
-        self.lastb = np.array(s.last_b[:])
         self.so3_iterations = s.so3_iterations
-        self.se3_iterations = list(s.se3_iterations[:])
+        self.se3_iterations = list(s.se3_iterations)
+
+    # lastA / lastb of the last call (RGBDOdometry.h:72-73), unpacked from the stats block when asked for
+    @property
+    def lastA(self):
+        return np.array(self._stats.last_A[:]).reshape(6, 6)
+
+    @property
+    def lastb(self):
+        return np.array(self._stats.last_b[:])
 
     def getIncrementalTransformation(self, trans, rot, rgbOnly, icpWeight, pyramid, fastOdom, so3):
         """trans (3,) and rot (3,3 row-major) are the pose prior; returns the updated (trans, rot)."""
@@ -203,13 +213,12 @@ class RGBDOdometry:
         self._check(rc, "ef_get_incremental_transformation_launch")
 
     def finish(self):
-        tr = np.zeros(3, np.float32)
-        ro = np.zeros(9, np.float32)
-        rc = self._L.ef_get_incremental_transformation_finish(self._h, tr.ctypes.data_as(C.c_void_p), ro.ctypes.data_as(C.c_void_p),
-                                                              C.byref(self._stats))
-        self._check(rc, "ef_get_incremental_transformation_finish")
+        rc = self._L.ef_get_incremental_transformation_finish(self._h, self._res_t, self._res_r, self._stats_ref)
+        if rc != 0:
+            self._check(rc, "ef_get_incremental_transformation_finish")
         self._publish()
-        return tr, ro.reshape(3, 3)
+        res = self._res.copy()
+        return res[:3], res[3:].reshape(3, 3)
 
     # -- ElasticFusion::processFrame's frameToModel sequence (ElasticFusion.cpp:343-368) in one C call ---------
     def _frame_inputs(self, vertices, normals, model_rgba, depth, rgba, depthCutoff):
@@ -220,15 +229,24 @@ class RGBDOdometry:
         else:
             ptr = lambda a: a.data_ptr()
         self._keep_frame = (vertices, normals, model_rgba, depth, rgba)
-        return FrameInputs(ptr(vertices), ptr(normals), ptr(model_rgba), ptr(depth), ptr(rgba), float(depthCutoff), int(on_host))
+        fi = self._frame
+        if fi is None:
+            fi = self._frame = FrameInputs()
+            self._frame_ref = C.byref(fi)
+        fi.vertices_rgba32f, fi.normals_rgba32f, fi.model_rgba8 = ptr(vertices), ptr(normals), ptr(model_rgba)
+        fi.depth, fi.rgba8, fi.depth_cutoff, fi.on_host = ptr(depth), ptr(rgba), float(depthCutoff), int(on_host)
+        return fi
 
     def trackFrameToModelLaunch(self, vertices, normals, model_rgba, depth, rgba, depthCutoff, modelPose, rgbOnly, icpWeight, pyramid,
                                 fastOdom, so3):
         fi = self._frame_inputs(vertices, normals, model_rgba, depth, rgba, depthCutoff)
-        pose = np.ascontiguousarray(np.asarray(modelPose, dtype=np.float32).reshape(16))
-        rc = self._L.ef_track_frame_to_model_launch(self._h, C.byref(fi), pose.ctypes.data_as(C.c_void_p), C.c_int(int(rgbOnly)),
-                                                    C.c_float(icpWeight), C.c_int(int(pyramid)), C.c_int(int(fastOdom)), C.c_int(int(so3)))
-        self._check(rc, "ef_track_frame_to_model_launch")
+        pose = np.ascontiguousarray(modelPose, dtype=np.float32)
+        if pose.size != 16:
+            raise ValueError("modelPose must be a 4x4 matrix")
+        rc = self._L.ef_track_frame_to_model_launch(self._h, self._frame_ref, C.c_void_p(pose.ctypes.data), int(rgbOnly), C.c_float(icpWeight),
+                                                    int(pyramid), int(fastOdom), int(so3))
+        if rc != 0:
+            self._check(rc, "ef_track_frame_to_model_launch")
 
     def trackFrameToModel(self, vertices, normals, model_rgba, depth, rgba, depthCutoff, modelPose, rgbOnly, icpWeight, pyramid, fastOdom,
                           so3):
