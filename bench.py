@@ -55,6 +55,7 @@ def parse_args():
     ap.add_argument("--frames", type=int, default=301, help="distinct frames rendered into HBM")
     ap.add_argument("--solve", choices=["device", "host"], default="device")
     ap.add_argument("--so3", type=int, default=0)
+    ap.add_argument("--graph", type=int, default=0, help="--solve host: replay each iteration's launches from a CUDA graph (EF_OPT_USE_GRAPH)")
     ap.add_argument("--icp-weight", type=float, default=10.0)
     ap.add_argument("--e2e-frames", type=int, default=48, help="distinct frames kept in pinned host memory for e2e")
     ap.add_argument("--cpu-sample", type=int, default=40, help="frames of the CPU baseline sample (0 = skip)")
@@ -179,6 +180,8 @@ def run_ours(args, rank, world, device):
 
     def make():
         tr = ef.RGBDOdometry(args.width, args.height, K.cx, K.cy, K.fx, K.fy, solve_mode=mode)
+        if args.graph:
+            tr.set_option(RO.EF_OPT_USE_GRAPH, 1)
         if os.environ.get("EF_FRAME_BUILD"):  # A/B switch for experiments: EF_OPT_FRAME_BUILD 0 / 1 / 2
             tr.set_option(RO.EF_OPT_FRAME_BUILD, int(os.environ["EF_FRAME_BUILD"]))
         return tr
@@ -414,7 +417,7 @@ def main():
 
     workload = (f"synthetic {args.width}x{args.height} {args.frames}-frame handheld trajectory, joint ICP+RGB "
                 f"(icpWeight={args.icp_weight:g}, iters {{10,5,4}}, so3={args.so3}), open-loop frame-to-model")
-    config = {"workload": workload, "solve": args.solve, "frames_resident": args.frames,
+    config = {"workload": workload, "solve": args.solve + ("+graph" if args.graph else ""), "frames_resident": args.frames,
               "l2": "each step reads a different frame of a >3 GB resident sequence (inputs larger than the 126 MB L2)",
               "parallelism": f"replicas x{world} (independent sequences, no collective)"}
 

@@ -66,7 +66,10 @@ typedef struct ef_track_stats
 
 /* ef_tracker_set_option keys */
 #define EF_OPT_SOLVE_MODE 1      /* EF_SOLVE_HOST (default) | EF_SOLVE_DEVICE */
-#define EF_OPT_USE_GRAPH 2       /* 0/1: replay the frame's kernels from a CUDA graph (device mode) */
+#define EF_OPT_USE_GRAPH 2       /* 0/1 (host-solve mode): the launches of one Gauss-Newton iteration (computeRgbResidual, rgbStep, icpStep,
+                                    parameter upload, result copies) are captured once per pyramid level and replayed as ONE CUDA
+                                    graph launch + ONE synchronisation per iteration; results identical to 0.  Device-solve mode
+                                    needs no graph: its whole iteration loop is one kernel */
 #define EF_OPT_FUSED_BUILD 3     /* 0/1: fused pyramid builders (default 1) instead of one kernel per operator */
 #define EF_OPT_PROFILE 4         /* 0/1: bracket the solve of every getIncrementalTransformation with CUDA events */
 #define EF_OPT_GRID_CTAS 5       /* device mode: CTAs (= SMs) the persistent tracker kernel occupies; 0 = all.  Lets k handles

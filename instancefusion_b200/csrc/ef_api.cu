@@ -95,6 +95,23 @@ EF_API size_t ef_op_scratch_bytes(void) { return kScratchBytes; }
 
 constexpr int kNumAux = 3;
 
+// pinned result block (floats): one fetched result at 0; graph replay keeps the three results of an iteration and the
+// iteration's parameters side by side
+constexpr int kHostResultFloats = 256;
+constexpr int kHResid = 64, kHRgb = 96, kHIcp = 128, kHIter = 160;
+static_assert(kHIter * sizeof(float) + sizeof(IterParams) <= kHostResultFloats * sizeof(float), "pinned result block");
+
+static void destroy_iter_graphs(ef_tracker * t)
+{
+    for(int p = 0; p < 2; p++)
+        for(int i = 0; i < kNumPyrs; i++)
+        {
+            if(t->iter_graph[p][i]) cudaGraphExecDestroy(t->iter_graph[p][i]);
+            t->iter_graph[p][i] = nullptr;
+            t->iter_graph_key[p][i] = 0;
+        }
+}
+
 static void destroy_aux(ef_tracker * t)
 {
     for(int i = 0; i < kNumAux; i++)
@@ -177,6 +194,10 @@ EF_API int ef_tracker_create(int width, int height, float cx, float cy, float fx
     t->launch_pending = false;
     t->track_state = nullptr;
     t->h_track_out = nullptr;
+    t->graph_scratch = nullptr;
+    t->image_parity = 0;
+    for(int i = 0; i < kNumPyrs; i++) t->iter_graph[0][i] = t->iter_graph[1][i] = nullptr;
+    for(int i = 0; i < kNumPyrs; i++) t->iter_graph_key[0][i] = t->iter_graph_key[1][i] = 0;
     memset(&t->st, 0, sizeof(t->st));
     t->st.last_icp_count = t->st.last_rgb_count = t->st.last_so3_count = (float)(width * height); // RGBDOdometry.cpp:26-31
 
@@ -230,7 +251,7 @@ EF_API int ef_tracker_create(int width, int height, float cx, float cy, float fx
 
     e = cudaMalloc(&t->arena, t->arena_bytes);
     if(e == cudaSuccess) e = cudaMemsetAsync(t->arena, 0, t->arena_bytes, t->stream);
-    if(e == cudaSuccess) e = cudaMallocHost((void **)&t->h_result, 64 * sizeof(float));
+    if(e == cudaSuccess) e = cudaMallocHost((void **)&t->h_result, kHostResultFloats * sizeof(float));
     if(e != cudaSuccess)
     {
         if(t->arena) cudaFree(t->arena);
@@ -287,6 +308,8 @@ EF_API int ef_tracker_destroy(ef_tracker * t)
     if(t->ev_begin) cudaEventDestroy(t->ev_begin);
     if(t->ev_end) cudaEventDestroy(t->ev_end);
     device_track_destroy(t);
+    destroy_iter_graphs(t);
+    if(t->graph_scratch) cudaFree(t->graph_scratch);
     cudaFree(t->arena);
     cudaFreeHost(t->h_result);
     if(t->own_stream) cudaStreamDestroy(t->stream);
@@ -303,7 +326,16 @@ EF_API int ef_tracker_set_option(ef_tracker * t, int key, int value)
         if(value != EF_SOLVE_HOST && value != EF_SOLVE_DEVICE) return fail(t, EF_ERR_INVALID_ARGUMENT, "bad solve mode");
         t->solve_mode = value;
         return EF_OK;
-    case EF_OPT_USE_GRAPH: t->use_graph = value ? 1 : 0; return EF_OK;
+    case EF_OPT_USE_GRAPH:
+        if(value && !t->graph_scratch)
+        {
+            // three reduction scratch blocks (one per operator of an iteration) + the device copy of the iteration parameters
+            const size_t bytes = 3 * kScratchBytes + sizeof(IterParams);
+            EF_CUDA(t, cudaMalloc(&t->graph_scratch, bytes));
+            EF_CUDA(t, cudaMemsetAsync(t->graph_scratch, 0, bytes, t->stream));
+        }
+        t->use_graph = value ? 1 : 0;
+        return EF_OK;
     case EF_OPT_FUSED_BUILD: t->fused_build = value ? 1 : 0; return EF_OK;
     case EF_OPT_AUX_STREAMS:
     {
@@ -665,6 +697,92 @@ EF_API int ef_init_first_rgb_host(ef_tracker * t, const uint8_t * h)
 // ------------------------------------------------------------------------------------------------
 // getIncrementalTransformation, host-solve path (RGBDOdometry.cpp:267-603)
 // ------------------------------------------------------------------------------------------------
+static RgbResArgs rgb_res_args(const ef_tracker * t, int i, const float * krkInv, const float * kt)
+{
+    RgbResArgs a;
+    a.min_scale = (float)(pow(t->min_grad[i], 2.0) / pow(t->sobel_scale, 2.0)); // :442
+    a.max_depth_delta = t->max_depth_delta_rgb;
+    memcpy(a.kt, kt, sizeof(a.kt)); memcpy(a.krkinv, krkInv, sizeof(a.krkinv));
+    a.rows = t->dims[i].rows; a.cols = t->dims[i].cols;
+    a.dIdx = t->dIdx[i]; a.dIdy = t->dIdy[i]; a.d_pitch = 0;
+    a.last_depth = t->last_depth[i]; a.next_depth = t->next_depth[i]; a.depth_pitch = 0;
+    a.last_image = t->last_image[i]; a.next_image = t->next_image[i]; a.image_pitch = 0;
+    a.corres = t->corres[i];
+    return a;
+}
+
+static IcpArgs icp_args(const ef_tracker * t, int i, const float * Rcurr, const float * tcurr, const float * Rprev_inv, const float * tprev)
+{
+    IcpArgs a;
+    memcpy(a.Rcurr, Rcurr, sizeof(a.Rcurr)); memcpy(a.tcurr, tcurr, sizeof(a.tcurr));
+    memcpy(a.Rprev_inv, Rprev_inv, sizeof(a.Rprev_inv)); memcpy(a.tprev, tprev, sizeof(a.tprev));
+    level_intr(t, i, a.fx, a.fy, a.cx, a.cy);
+    a.dist_thresh = t->dist_thresh; a.angle_thresh = t->angle_thresh;
+    a.rows = t->dims[i].rows; a.cols = t->dims[i].cols;
+    a.vmap_curr = t->vmap_curr[i]; a.nmap_curr = t->nmap_curr[i];
+    a.vmap_g_prev = t->vmap_g_prev[i]; a.nmap_g_prev = t->nmap_g_prev[i];
+    a.pitch = 0;
+    return a;
+}
+
+static RgbStepArgs rgb_step_args(const ef_tracker * t, int i, float sigmaVal)
+{
+    RgbStepArgs a;
+    float cx, cy;
+    a.corres = t->corres[i];
+    a.sigma = sigmaVal;
+    a.cloud = t->cloud[i]; a.cloud_pitch = 0;
+    level_intr(t, i, a.fx, a.fy, cx, cy);
+    a.dIdx = t->dIdx[i]; a.dIdy = t->dIdy[i]; a.d_pitch = 0;
+    a.sobel_scale = t->sobel_scale;
+    a.rows = t->dims[i].rows; a.cols = t->dims[i].cols;
+    return a;
+}
+
+// EF_OPT_USE_GRAPH: one Gauss-Newton iteration of level i -- parameter upload, computeRgbResidual, rgbStep (sigma formed on
+// the device), icpStep, the three results back to pinned memory -- captured once per handle and level and replayed with ONE
+// cudaGraphLaunch and ONE synchronisation per iteration (the plain path: three launches, three copies, three
+// synchronisations).  Everything that changes between iterations or frames travels through ef::IterParams; the rest of a
+// level (buffers, intrinsics, thresholds) is fixed at handle creation, so the graph is only rebuilt when the set of
+// operators (ICP / RGB) changes.
+static int iter_graph_for(ef_tracker * t, int i, bool icp, bool rgb)
+{
+    const int key = 1 + (icp ? 2 : 0) + (rgb ? 4 : 0);
+    cudaGraphExec_t & exec = t->iter_graph[t->image_parity][i];
+    int & have = t->iter_graph_key[t->image_parity][i];
+    if(exec && have == key) return EF_OK;
+    if(exec) { cudaGraphExecDestroy(exec); exec = nullptr; have = 0; }
+    cudaStream_t s = t->stream;
+    char * gs = static_cast<char *>(t->graph_scratch);
+    const IterParams * d_it = reinterpret_cast<const IterParams *>(gs + 3 * kScratchBytes);
+    const float zero9[9] = {0}, zero3[3] = {0};
+    EF_CUDA(t, cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+    cudaError_t e = cudaMemcpyAsync(const_cast<IterParams *>(d_it), t->h_result + kHIter, sizeof(IterParams), cudaMemcpyHostToDevice, s);
+    if(rgb)
+    {
+        if(e == cudaSuccess) e = launch_rgb_residual(rgb_res_args(t, i, zero9, zero3), gs, s, d_it);
+        if(e == cudaSuccess)
+            e = launch_rgb_step(rgb_step_args(t, i, 0.f), gs + kScratchBytes, s, d_it, reinterpret_cast<const int *>(gs + kScratchResultOff));
+        if(e == cudaSuccess) e = cudaMemcpyAsync(t->h_result + kHResid, gs + kScratchResultOff, 2 * sizeof(int), cudaMemcpyDeviceToHost, s);
+        if(e == cudaSuccess)
+            e = cudaMemcpyAsync(t->h_result + kHRgb, gs + kScratchBytes + kScratchResultOff, 29 * sizeof(float), cudaMemcpyDeviceToHost, s);
+    }
+    if(icp)
+    {
+        if(e == cudaSuccess) e = launch_icp_step(icp_args(t, i, zero9, zero3, zero9, zero3), gs + 2 * kScratchBytes, s, d_it);
+        if(e == cudaSuccess)
+            e = cudaMemcpyAsync(t->h_result + kHIcp, gs + 2 * kScratchBytes + kScratchResultOff, 29 * sizeof(float), cudaMemcpyDeviceToHost, s);
+    }
+    cudaGraph_t g = nullptr;
+    const cudaError_t e2 = cudaStreamEndCapture(s, &g);
+    if(e == cudaSuccess) e = e2;
+    if(e == cudaSuccess) e = cudaGraphInstantiate(&exec, g, 0);
+    if(g) cudaGraphDestroy(g);
+    if(e != cudaSuccess) return fail(t, (int)e, "capturing the iteration graph");
+    have = key;
+    return EF_OK;
+}
+
 static int fetch_result(ef_tracker * t, int nfloats)
 {
     EF_CUDA(t, cudaMemcpyAsync(t->h_result, static_cast<char *>(t->scratch) + kScratchResultOff, nfloats * sizeof(float), cudaMemcpyDeviceToHost,
@@ -798,18 +916,31 @@ static int track_host(ef_tracker * t, float * trans, float * rot, int rgb_only, 
             hm::rgb_warp_params(resultRt, K, K_inv, krkInv, kt); // :424-434
 
             int sigma = 0, rgbSize = 0;
-            if(rgb)
+            const float * icp_sums = t->h_result, * rgb_sums = t->h_result;
+            if(t->use_graph)
             {
-                RgbResArgs a;
-                a.min_scale = (float)(pow(t->min_grad[i], 2.0) / pow(t->sobel_scale, 2.0)); // :442
-                a.max_depth_delta = t->max_depth_delta_rgb;
-                memcpy(a.kt, kt, sizeof(kt)); memcpy(a.krkinv, krkInv, sizeof(krkInv));
-                a.rows = rows; a.cols = cols;
-                a.dIdx = t->dIdx[i]; a.dIdy = t->dIdy[i]; a.d_pitch = 0;
-                a.last_depth = t->last_depth[i]; a.next_depth = t->next_depth[i]; a.depth_pitch = 0;
-                a.last_image = t->last_image[i]; a.next_image = t->next_image[i]; a.image_pitch = 0;
-                a.corres = t->corres[i];
-                EF_LAUNCH(t, launch_rgb_residual(a, t->scratch, s));
+                // one replayed graph = the whole evaluation of this iteration
+                int rc = iter_graph_for(t, i, icp, rgb);
+                if(rc) return rc;
+                IterParams * h = reinterpret_cast<IterParams *>(t->h_result + kHIter);
+                memcpy(h->Rcurr, Rcurr, sizeof(Rcurr)); memcpy(h->tcurr, tcurr, sizeof(tcurr));
+                memcpy(h->Rprev_inv, Rprev_inv, sizeof(Rprev_inv)); memcpy(h->tprev, tprev, sizeof(tprev));
+                memcpy(h->krkinv, krkInv, sizeof(krkInv)); memcpy(h->kt, kt, sizeof(kt));
+                h->rgb_only = rgb_only ? 1 : 0;
+                EF_CUDA(t, cudaGraphLaunch(t->iter_graph[t->image_parity][i], s));
+                t->launches += (rgb ? 2 : 0) + (icp ? 1 : 0);
+                EF_CUDA(t, cudaStreamSynchronize(s));
+                if(rgb)
+                {
+                    rgbSize = reinterpret_cast<const int *>(t->h_result + kHResid)[0];
+                    sigma = reinterpret_cast<const int *>(t->h_result + kHResid)[1];
+                }
+                icp_sums = t->h_result + kHIcp;
+                rgb_sums = t->h_result + kHRgb;
+            }
+            else if(rgb)
+            {
+                EF_LAUNCH(t, launch_rgb_residual(rgb_res_args(t, i, krkInv, kt), t->scratch, s));
                 const int rc = fetch_result(t, 2);
                 if(rc) return rc;
                 rgbSize = reinterpret_cast<int *>(t->h_result)[0];
@@ -827,38 +958,27 @@ static int track_host(ef_tracker * t, float * trans, float * rot, int rgb_only, 
             double A_icp[36] = {0}, b_icp[6] = {0}, A_rgb[36] = {0}, b_rgb[6] = {0};
             if(icp)
             {
-                IcpArgs a;
-                memcpy(a.Rcurr, Rcurr, sizeof(Rcurr)); memcpy(a.tcurr, tcurr, sizeof(tcurr));
-                memcpy(a.Rprev_inv, Rprev_inv, sizeof(Rprev_inv)); memcpy(a.tprev, tprev, sizeof(tprev));
-                a.fx = fx; a.fy = fy; a.cx = cx; a.cy = cy;
-                a.dist_thresh = t->dist_thresh; a.angle_thresh = t->angle_thresh;
-                a.rows = rows; a.cols = cols;
-                a.vmap_curr = t->vmap_curr[i]; a.nmap_curr = t->nmap_curr[i];
-                a.vmap_g_prev = t->vmap_g_prev[i]; a.nmap_g_prev = t->nmap_g_prev[i];
-                a.pitch = 0;
-                EF_LAUNCH(t, launch_icp_step(a, t->scratch, s));
-                const int rc = fetch_result(t, 29);
-                if(rc) return rc;
+                if(!t->use_graph)
+                {
+                    EF_LAUNCH(t, launch_icp_step(icp_args(t, i, Rcurr, tcurr, Rprev_inv, tprev), t->scratch, s));
+                    const int rc = fetch_result(t, 29);
+                    if(rc) return rc;
+                }
                 float residual[2];
-                hm::unpack_se3(t->h_result, A_icp, b_icp, residual);
+                hm::unpack_se3(icp_sums, A_icp, b_icp, residual);
                 // :515-516.  (When !icp the reference reads `residual` uninitialised; we keep the previous values.)
                 t->st.last_icp_error = sqrtf(residual[0]) / residual[1];
                 t->st.last_icp_count = residual[1];
             }
             if(rgb)
             {
-                RgbStepArgs a;
-                a.corres = t->corres[i];
-                a.sigma = sigmaVal;
-                a.cloud = t->cloud[i]; a.cloud_pitch = 0;
-                a.fx = fx; a.fy = fy;
-                a.dIdx = t->dIdx[i]; a.dIdy = t->dIdy[i]; a.d_pitch = 0;
-                a.sobel_scale = t->sobel_scale;
-                a.rows = rows; a.cols = cols;
-                EF_LAUNCH(t, launch_rgb_step(a, t->scratch, s));
-                const int rc = fetch_result(t, 29);
-                if(rc) return rc;
-                hm::unpack_se3(t->h_result, A_rgb, b_rgb, (float *)nullptr);
+                if(!t->use_graph)
+                {
+                    EF_LAUNCH(t, launch_rgb_step(rgb_step_args(t, i, sigmaVal), t->scratch, s));
+                    const int rc = fetch_result(t, 29);
+                    if(rc) return rc;
+                }
+                hm::unpack_se3(rgb_sums, A_rgb, b_rgb, (float *)nullptr);
             }
 
             double * lastA = t->st.last_A, * lastb = t->st.last_b, result[6];
@@ -904,6 +1024,7 @@ static int track_host(ef_tracker * t, float * trans, float * rot, int rgb_only, 
 static void swap_so3_images(ef_tracker * t)
 {
     for(int i = 0; i < kNumPyrs; i++) std::swap(t->last_next_image[i], t->next_image[i]); // RGBDOdometry.cpp:593-599
+    t->image_parity ^= 1;
     t->deriv_valid = false;
 }
 

@@ -73,6 +73,17 @@ constexpr size_t kScratchPartialOff = 256;
 constexpr int kMaxReduceBlocks = 2048;
 constexpr size_t kScratchBytes = kScratchPartialOff + (size_t)kMaxReduceBlocks * 32 * sizeof(float);
 
+// EF_OPT_USE_GRAPH: what changes from one Gauss-Newton iteration to the next, read from device memory by the step
+// kernels so that the launches of an iteration are fixed nodes of a replayed CUDA graph
+struct IterParams
+{
+    float Rcurr[9], tcurr[3];  // icpStep
+    float Rprev_inv[9], tprev[3]; // icpStep; constant over a frame, but the graph outlives the frame
+    float krkinv[9], kt[3];    // computeRgbResidual
+    int rgb_only;              // rgbStep: sigma = -1 (RGBDOdometry.cpp:472)
+    int pad[3];
+};
+
 struct IcpArgs
 {
     float Rcurr[9], tcurr[3], Rprev_inv[9], tprev[3];
@@ -83,7 +94,7 @@ struct IcpArgs
     size_t pitch; // bytes, same for the four maps (0 = dense)
 };
 // result: 29 floats at scratch + kScratchResultOff
-cudaError_t launch_icp_step(const IcpArgs & a, void * scratch, cudaStream_t s);
+cudaError_t launch_icp_step(const IcpArgs & a, void * scratch, cudaStream_t s, const IterParams * it = nullptr);
 
 struct RgbResArgs
 {
@@ -99,7 +110,7 @@ struct RgbResArgs
     void * corres; // rows*cols 16-byte records, linear
 };
 // result: int2 {count, sigma} at scratch + kScratchResultOff
-cudaError_t launch_rgb_residual(const RgbResArgs & a, void * scratch, cudaStream_t s);
+cudaError_t launch_rgb_residual(const RgbResArgs & a, void * scratch, cudaStream_t s, const IterParams * it = nullptr);
 
 struct RgbStepArgs
 {
@@ -113,7 +124,8 @@ struct RgbStepArgs
     float sobel_scale;
     int rows, cols;
 };
-cudaError_t launch_rgb_step(const RgbStepArgs & a, void * scratch, cudaStream_t s);
+// it != null: sigma is derived on the device from `residual` = the {count, sum} computeRgbResidual produced
+cudaError_t launch_rgb_step(const RgbStepArgs & a, void * scratch, cudaStream_t s, const IterParams * it = nullptr, const int * residual = nullptr);
 
 struct So3Args
 {

@@ -30,6 +30,15 @@ inline Mat33 to_mat(const float * m)
     return r;
 }
 
+__device__ __forceinline__ Mat33 mat_of(const float * m)
+{
+    Mat33 r;
+    r.r0 = make_float3(m[0], m[1], m[2]);
+    r.r1 = make_float3(m[3], m[4], m[5]);
+    r.r2 = make_float3(m[6], m[7], m[8]);
+    return r;
+}
+
 inline int num_sms()
 {
     static int n = 0;
@@ -62,11 +71,20 @@ inline int grid_for(int work_items)
 // about as much as the 44 MB from HBM, so the grid is sized to the real occupancy (no partial second wave) and the
 // kernel runs grid-stride.
 template<int PX>
-__global__ void __launch_bounds__(kBlock, 2) k_icp_step(const IcpParams P, const Map3 vc, const Map3 nc, const Map3 vp, const Map3 np,
+__global__ void __launch_bounds__(kBlock, 2) k_icp_step(const IcpParams P0, const Map3 vc, const Map3 nc, const Map3 vp, const Map3 np,
                                                         int groups_per_row, int total_groups, float * __restrict__ partials,
-                                                        unsigned * ticket, float * __restrict__ out)
+                                                        unsigned * ticket, float * __restrict__ out, const IterParams * __restrict__ it)
 {
     __shared__ float smem[32 * 32];
+    // graph replay (EF_OPT_USE_GRAPH): the launch is a fixed graph node, the pose of the iteration comes from memory
+    IcpParams P = P0;
+    if(it)
+    {
+        P.Rcurr = mat_of(it->Rcurr);
+        P.tcurr = make_float3(it->tcurr[0], it->tcurr[1], it->tcurr[2]);
+        P.Rprev_inv = mat_of(it->Rprev_inv);
+        P.tprev = make_float3(it->tprev[0], it->tprev[1], it->tprev[2]);
+    }
     float acc[32];
 #pragma unroll
     for(int i = 0; i < 32; i++) acc[i] = 0.f;
@@ -155,15 +173,22 @@ inline int grid_one_wave(K kernel, int work_items)
 // computeRgbResidual  (reduce.cu:739-936): writes a 16-byte DataTerm per pixel (types.cuh:75-81) and
 // reduces int2 {count, sum (int)(diff^2)} -- integer adds, so __reduce_add_sync + any order is exact.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kBlock) k_rgb_residual(const RgbResParams P, const int16_t * __restrict__ dIdx,
+__global__ void __launch_bounds__(kBlock) k_rgb_residual(const RgbResParams P0, const int16_t * __restrict__ dIdx,
                                                          const int16_t * __restrict__ dIdy, int d_pitch,
                                                          const float * __restrict__ last_depth, const float * __restrict__ next_depth,
                                                          int depth_pitch, const uint8_t * __restrict__ last_image,
                                                          const uint8_t * __restrict__ next_image, int img_pitch, int4 * __restrict__ corres,
-                                                         int * __restrict__ partials, unsigned * ticket, int * __restrict__ out)
+                                                         int * __restrict__ partials, unsigned * ticket, int * __restrict__ out,
+                                                         const IterParams * __restrict__ it)
 {
     __shared__ int s_cnt[32], s_sig[32];
     __shared__ bool is_last;
+    RgbResParams P = P0;
+    if(it)
+    {
+        P.krkinv = mat_of(it->krkinv);
+        P.kt = make_float3(it->kt[0], it->kt[1], it->kt[2]);
+    }
     const int N = P.rows * P.cols;
     int cnt = 0, sig = 0;
 
@@ -231,12 +256,23 @@ __global__ void __launch_bounds__(kBlock) k_rgb_residual(const RgbResParams P, c
 // ------------------------------------------------------------------------------------------------
 // rgbStep  (reduce.cu:494-678): consumes DataTerm records + the float3 point cloud
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kBlock) k_rgb_step(const RgbStepParams P, const int4 * __restrict__ corres, const float * __restrict__ cloud,
+__global__ void __launch_bounds__(kBlock) k_rgb_step(const RgbStepParams P0, const int4 * __restrict__ corres, const float * __restrict__ cloud,
                                                      int cloud_pitch /*floats*/, const int16_t * __restrict__ dIdx,
                                                      const int16_t * __restrict__ dIdy, int d_pitch, int N, float * __restrict__ partials,
-                                                     unsigned * ticket, float * __restrict__ out)
+                                                     unsigned * ticket, float * __restrict__ out, const IterParams * __restrict__ it,
+                                                     const int * __restrict__ residual)
 {
     __shared__ float smem[32 * 32];
+    RgbStepParams P = P0;
+    if(it)
+    {
+        // graph replay: the robust-weight scale from the {count, sum} computeRgbResidual left in device memory, formed
+        // like the host does (RGBDOdometry.cpp:461, precedence quirk kept; :472)
+        const int rgbSize = __ldcg(residual), sigma = __ldcg(residual + 1);
+        float sigmaVal = (float)sqrt((double)((__fdiv_rn((float)sigma, (float)rgbSize) == 0) ? 1 : rgbSize));
+        if(it->rgb_only) sigmaVal = -1;
+        P.sigma = sigmaVal;
+    }
     float acc[32];
 #pragma unroll
     for(int i = 0; i < 32; i++) acc[i] = 0.f;
@@ -290,7 +326,7 @@ __global__ void __launch_bounds__(kBlock) k_so3_step(const So3Params P, const ui
 // ------------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------------
-cudaError_t launch_icp_step(const IcpArgs & a, void * scratch, cudaStream_t s)
+cudaError_t launch_icp_step(const IcpArgs & a, void * scratch, cudaStream_t s, const IterParams * it)
 {
     IcpParams P;
     P.Rcurr = to_mat(a.Rcurr);
@@ -316,17 +352,17 @@ cudaError_t launch_icp_step(const IcpArgs & a, void * scratch, cudaStream_t s)
     if(vec)
     {
         const int gpr = a.cols / 4, total = gpr * a.rows;
-        k_icp_step<4><<<grid_one_wave(k_icp_step<4>, total), kBlock, 0, s>>>(P, vc, nc, vp, np, gpr, total, partials, ticket, out);
+        k_icp_step<4><<<grid_one_wave(k_icp_step<4>, total), kBlock, 0, s>>>(P, vc, nc, vp, np, gpr, total, partials, ticket, out, it);
     }
     else
     {
         const int total = a.cols * a.rows;
-        k_icp_step<1><<<grid_one_wave(k_icp_step<1>, total), kBlock, 0, s>>>(P, vc, nc, vp, np, a.cols, total, partials, ticket, out);
+        k_icp_step<1><<<grid_one_wave(k_icp_step<1>, total), kBlock, 0, s>>>(P, vc, nc, vp, np, a.cols, total, partials, ticket, out, it);
     }
     return cudaGetLastError();
 }
 
-cudaError_t launch_rgb_residual(const RgbResArgs & a, void * scratch, cudaStream_t s)
+cudaError_t launch_rgb_residual(const RgbResArgs & a, void * scratch, cudaStream_t s, const IterParams * it)
 {
     RgbResParams P;
     P.krkinv = to_mat(a.krkinv);
@@ -344,11 +380,11 @@ cudaError_t launch_rgb_residual(const RgbResArgs & a, void * scratch, cudaStream
     const int img_pitch = (int)(a.image_pitch ? a.image_pitch : (size_t)a.cols);
     k_rgb_residual<<<grid_for(a.rows * a.cols), kBlock, 0, s>>>(P, a.dIdx, a.dIdy, d_pitch, a.last_depth, a.next_depth, depth_pitch,
                                                                a.last_image, a.next_image, img_pitch, static_cast<int4 *>(a.corres), partials,
-                                                               ticket, out);
+                                                               ticket, out, it);
     return cudaGetLastError();
 }
 
-cudaError_t launch_rgb_step(const RgbStepArgs & a, void * scratch, cudaStream_t s)
+cudaError_t launch_rgb_step(const RgbStepArgs & a, void * scratch, cudaStream_t s, const IterParams * it, const int * residual)
 {
     RgbStepParams P;
     P.sigma = a.sigma;
@@ -366,7 +402,7 @@ cudaError_t launch_rgb_step(const RgbStepArgs & a, void * scratch, cudaStream_t 
     const int d_pitch = (int)((a.d_pitch ? a.d_pitch : (size_t)a.cols * 2) / 2);
     const int N = a.rows * a.cols;
     k_rgb_step<<<grid_for(N), kBlock, 0, s>>>(P, static_cast<const int4 *>(a.corres), a.cloud, cloud_pitch, a.dIdx, a.dIdy, d_pitch, N, partials,
-                                             ticket, out);
+                                             ticket, out, it, residual);
     return cudaGetLastError();
 }
 

@@ -82,7 +82,15 @@ struct ef_tracker
         float icp_weight;
     } pending;
 
-    float * h_result; // pinned, 32 floats
+    float * h_result; // pinned, ef::kHostResultFloats floats: [0, 64) one fetched result; graph replay: see ef_api.cu
+
+    // EF_OPT_USE_GRAPH (host-solve mode): the launches of one Gauss-Newton iteration of a level as a replayed CUDA graph
+    // (two sets: the SO(3) pre-alignment swaps the nextImage / lastNextImage pyramids after every call, RGBDOdometry.cpp:593-599,
+    //  so the buffers a graph was captured with come back every other call)
+    cudaGraphExec_t iter_graph[2][ef::kNumPyrs];
+    int iter_graph_key[2][ef::kNumPyrs]; // which operators the graph holds (0 = none built)
+    int image_parity;                    // number of image swaps so far, mod 2
+    void * graph_scratch;             // three reduction scratch blocks + the device copy of ef::IterParams
     bool deriv_valid; // dIdx/dIdy match next_image
 
     // EF_OPT_PROFILE

@@ -212,6 +212,38 @@ def test_one_launch_frame_build_does_not_change_a_bit(size):
         c.close()
 
 
+@pytest.mark.parametrize("size", [(640, 480), (320, 240)])
+def test_graph_replayed_iterations_do_not_change_a_bit(size):
+    """EF_OPT_USE_GRAPH (host-solve mode): the launches of one Gauss-Newton iteration replayed as a CUDA graph per pyramid
+    level, iteration parameters read from device memory, sigma formed on the device -- same sums, same pose, bit for bit,
+    across frames with different prior poses and across operator sets (the graph is rebuilt when ICP / RGB changes)"""
+    w, h = size
+    K, pose0, pose1, f0, f1 = util.frame_pair(w, h)
+    f1 = dict(f1, depth=util.punch_holes(f1["depth"]))
+    p0, p1 = pose0.astype(np.float32), pose1.astype(np.float32)
+    a = ef.RGBDOdometry(w, h, K.cx, K.cy, K.fx, K.fy, solve_mode=RO.EF_SOLVE_HOST)
+    b = ef.RGBDOdometry(w, h, K.cx, K.cy, K.fx, K.fy, solve_mode=RO.EF_SOLVE_HOST)
+    b.set_option(RO.EF_OPT_USE_GRAPH, 1)
+    try:
+        modes = (JOINT, JOINT, dict(JOINT, icpWeight=100.0), dict(JOINT, rgbOnly=True), JOINT_SO3, dict(JOINT, pyramid=False, fastOdom=True))
+        for rep, m in enumerate(modes):
+            (pa, fa, fb) = (p0, f0, f1) if rep % 2 == 0 else (p1, f1, f0)
+            _feed(a, pa, fa, fb)
+            _feed(b, pa, fa, fb)
+            la, lb = a.launch_count, b.launch_count
+            ta, Ra = a.getIncrementalTransformation(pa[:3, 3], pa[:3, :3], **m)
+            tb, Rb = b.getIncrementalTransformation(pa[:3, 3], pa[:3, :3], **m)
+            assert np.array_equal(ta, tb) and np.array_equal(Ra, Rb), (rep, m)
+            assert a.se3_iterations == b.se3_iterations and a.so3_iterations == b.so3_iterations
+            assert (a.lastICPError, a.lastICPCount, a.lastRGBError, a.lastRGBCount) == (b.lastICPError, b.lastICPCount, b.lastRGBError, b.lastRGBCount)
+            assert np.array_equal(a.lastA, b.lastA) and np.array_equal(a.lastb, b.lastb)
+            if not m["rgbOnly"]:  # (RGB-only: the replayed graph also evaluates the step the plain path skips on its early exit)
+                assert a.launch_count - la == b.launch_count - lb, "the graph holds the same kernels"
+    finally:
+        a.close()
+        b.close()
+
+
 def test_many_calls_on_one_handle_are_stable():
     """launch-unique epochs: 200 consecutive launches on one handle, every one returns the same bits"""
     w, h = 320, 240
