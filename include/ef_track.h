@@ -242,6 +242,28 @@ int ef_op_depth_bilateral(const uint16_t * d_src, size_t src_pitch, int rows, in
 int ef_op_depth_metric(const uint16_t * d_src, size_t src_pitch, int rows, int cols, float max_depth_m, float * d_dst, size_t dst_pitch,
                        void * stream);
 
+/* ---- the step around the tracker, OpenGL in the reference: the model prediction whose outputs are
+ * the `vertices_rgba32f / normals_rgba32f / model_rgba8` inputs of ef_init_icp_model / ef_init_rgb_model ---- */
+/* IndexMap::combinedPredict   IndexMap.cpp:468-575, Shaders/splat.vert:19-88, Shaders/combo_splat.frag:19-67: every surfel
+ * (float4 position|confidence, float4 colour|instance|initTime|time, float4 normal|radius at d_surfels + i * stride_bytes;
+ * stride 48 in ElasticFusion, Vertex::SIZE = 256 in InstanceFusion) is drawn as a point sprite under a GL_LESS depth test.
+ * h_t_inv16 = inverse of the prediction pose, row-major.  d_keys: ef_op_splat_scratch_bytes(rows, cols) bytes of device
+ * scratch.  Outputs rows x cols, zero where nothing was drawn: d_image_rgba8 and d_time_u16 may be null. */
+size_t ef_op_splat_scratch_bytes(int rows, int cols);
+int ef_op_splat_predict(const float * d_surfels, size_t stride_bytes, int count, const float * h_t_inv16, float cx, float cy, float fx,
+                        float fy, int rows, int cols, float max_depth, float conf_threshold, int time, int max_time, int time_delta,
+                        void * d_keys, uint8_t * d_image_rgba8, float * d_vertex_rgba32f, float * d_normal_rgba32f,
+                        uint16_t * d_time_u16, void * stream);
+/* FillIn::vertex / normal / image   FillIn.cpp, Shaders/fill_vertex.frag:19-53, fill_normal.frag:19-55, fill_rgb.frag:19-37
+ * (ElasticFusion.cpp:756-760): holes of the predicted maps (vertex z == 0, black colour) are patched from the current raw
+ * depth (millimetres) / colour image; passthrough = 1 takes every pixel from the current frame */
+int ef_op_fill_vertex(const float * d_predicted_rgba32f, const uint16_t * d_depth_mm, int rows, int cols, float cx, float cy, float fx,
+                      float fy, int passthrough, float * d_out_rgba32f, void * stream);
+int ef_op_fill_normal(const float * d_predicted_rgba32f, const uint16_t * d_depth_mm, int rows, int cols, float cx, float cy, float fx,
+                      float fy, int passthrough, float * d_out_rgba32f, void * stream);
+int ef_op_fill_rgb(const uint8_t * d_predicted_rgba8, const uint8_t * d_rgba8, int rows, int cols, int passthrough, uint8_t * d_out_rgba8,
+                   void * stream);
+
 /* icpStep                     reduce.cu:257-490.  Host outputs: A 6x6 row-major, b[6], residual[2] =
  * {sum r^2, inlier count}.  `d_scratch` >= ef_op_scratch_bytes() bytes of device memory. */
 int ef_op_icp_step(const float * h_Rcurr9, const float * h_tcurr3, const float * d_vmap_curr3, const float * d_nmap_curr3,

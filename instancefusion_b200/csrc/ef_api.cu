@@ -1363,6 +1363,49 @@ EF_API int ef_op_project_point_cloud(const float * depth, size_t dp, int rows, i
     EF_OP_RET(launch_project_points(depth, dp, rows, cols, fx / div, fy / div, cx / div, cy / div, cloud, cp, (cudaStream_t)st));
 }
 
+EF_API size_t ef_op_splat_scratch_bytes(int rows, int cols) { return (rows > 0 && cols > 0) ? (size_t)rows * cols * 8 : 0; }
+
+EF_API int ef_op_splat_predict(const float * surfels, size_t stride_bytes, int count, const float * t_inv, float cx, float cy, float fx, float fy,
+                               int rows, int cols, float max_depth, float conf_threshold, int time, int max_time, int time_delta, void * keys,
+                               uint8_t * image, float * vertex, float * normal, uint16_t * time_out, void * st)
+{
+    if(count < 0 || (count > 0 && !surfels) || !t_inv || !keys || !vertex || !normal || rows <= 0 || cols <= 0) return EF_ERR_INVALID_ARGUMENT;
+    if(stride_bytes < 48 || (stride_bytes % 16) || (reinterpret_cast<uintptr_t>(surfels) % 16)) return EF_ERR_INVALID_ARGUMENT;
+    if(ef_device_count() <= 0) return EF_ERR_NO_DEVICE;
+    SplatArgs a;
+    a.surfels = surfels; a.stride_bytes = stride_bytes; a.count = count;
+    memcpy(a.t_inv, t_inv, sizeof(a.t_inv)); // rows 0..2
+    a.cx = cx; a.cy = cy; a.fx = fx; a.fy = fy;
+    a.rows = rows; a.cols = cols;
+    a.max_depth = max_depth; a.conf_threshold = conf_threshold;
+    a.time = time; a.max_time = max_time; a.time_delta = time_delta;
+    a.keys = keys; a.image = image; a.vertex = vertex; a.normal = normal; a.time_out = time_out;
+    return (int)launch_splat_predict(a, (cudaStream_t)st);
+}
+
+EF_API int ef_op_fill_vertex(const float * predicted, const uint16_t * depth, int rows, int cols, float cx, float cy, float fx, float fy,
+                             int passthrough, float * out, void * st)
+{
+    if(!predicted || !depth || !out || rows <= 0 || cols <= 0) return EF_ERR_INVALID_ARGUMENT;
+    if(ef_device_count() <= 0) return EF_ERR_NO_DEVICE;
+    return (int)launch_fill_vertex(predicted, depth, rows, cols, cx, cy, fx, fy, passthrough, out, (cudaStream_t)st);
+}
+
+EF_API int ef_op_fill_normal(const float * predicted, const uint16_t * depth, int rows, int cols, float cx, float cy, float fx, float fy,
+                             int passthrough, float * out, void * st)
+{
+    if(!predicted || !depth || !out || rows <= 0 || cols <= 0) return EF_ERR_INVALID_ARGUMENT;
+    if(ef_device_count() <= 0) return EF_ERR_NO_DEVICE;
+    return (int)launch_fill_normal(predicted, depth, rows, cols, cx, cy, fx, fy, passthrough, out, (cudaStream_t)st);
+}
+
+EF_API int ef_op_fill_rgb(const uint8_t * predicted, const uint8_t * raw, int rows, int cols, int passthrough, uint8_t * out, void * st)
+{
+    if(!predicted || !raw || !out || rows <= 0 || cols <= 0) return EF_ERR_INVALID_ARGUMENT;
+    if(ef_device_count() <= 0) return EF_ERR_NO_DEVICE;
+    return (int)launch_fill_rgb(predicted, raw, rows, cols, passthrough, out, (cudaStream_t)st);
+}
+
 static int op_fetch(void * scratch, void * host, size_t bytes, cudaStream_t s)
 {
     cudaError_t e = cudaMemcpyAsync(host, static_cast<char *>(scratch) + kScratchResultOff, bytes, cudaMemcpyDeviceToHost, s);

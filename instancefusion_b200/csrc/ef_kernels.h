@@ -31,6 +31,29 @@ cudaError_t launch_project_points(const float * depth, size_t dp, int rows, int 
 cudaError_t launch_depth_bilateral(const uint16_t * src, size_t sp, int rows, int cols, float max_depth_m, uint16_t * dst, size_t dp, cudaStream_t s);
 cudaError_t launch_depth_metric(const uint16_t * src, size_t sp, int rows, int cols, float max_depth_m, float * dst, size_t dp, cudaStream_t s);
 
+// ---- the step around the tracker (ef_ops_predict.cu): IndexMap::combinedPredict + FillIn ----
+struct SplatArgs
+{
+    const float * surfels;
+    size_t stride_bytes;
+    int count;
+    float t_inv[12];
+    float cx, cy, fx, fy;
+    int rows, cols;
+    float max_depth, conf_threshold;
+    int time, max_time, time_delta;
+    void * keys; // rows * cols * 8 bytes
+    uint8_t * image;
+    float * vertex, * normal;
+    uint16_t * time_out;
+};
+cudaError_t launch_splat_predict(const SplatArgs & a, cudaStream_t s);
+cudaError_t launch_fill_vertex(const float * predicted, const uint16_t * depth, int rows, int cols, float cx, float cy, float fx, float fy, int passthrough,
+                               float * out, cudaStream_t s);
+cudaError_t launch_fill_normal(const float * predicted, const uint16_t * depth, int rows, int cols, float cx, float cy, float fx, float fy, int passthrough,
+                               float * out, cudaStream_t s);
+cudaError_t launch_fill_rgb(const uint8_t * predicted, const uint8_t * raw, int rows, int cols, int passthrough, uint8_t * out, cudaStream_t s);
+
 // ---- fused pyramid builders (ef_build_fused.cu); dense outputs ----
 // R == nullptr: no transform (initICP maps overload); else v' = R v + t, n' = R n at every level (initICPModel)
 cudaError_t launch_build_maps(const float * v4, const float * n4, int rows, int cols, float * const vmaps[3], float * const nmaps[3], float * tmp_z,

@@ -264,3 +264,52 @@ def so3Step(lastImage, nextImage, imageBasis, kinv, krlr):
     _chk(L.ef_op_so3_step(_p(li), _p(ni), C.c_size_t(0), vp_(H), vp_(ki), vp_(kr), r, c, _p(sc), vp_(A), vp_(b), vp_(res), _stream()),
          "ef_op_so3_step")
     return A.reshape(3, 3), b, res
+
+
+# ---- the step around the tracker: IndexMap::combinedPredict + FillIn, OpenGL in the reference ----
+def splatPredict(surfels, pose, cx, cy, fx, fy, rows, cols, maxDepth, confThreshold, time, maxTime, timeDelta):
+    """IndexMap::combinedPredict (IndexMap.cpp:468-575): surfels (N, stride/4 >= 12) float32 -- position|confidence,
+    colour|instance|initTime|time, normal|radius -- drawn from `pose` (4x4, camera-to-world).  Returns
+    (image rgba8, vertex rgba32f, normal rgba32f, time u16) as numpy."""
+    L = binding.lib()
+    s = _dev(np.ascontiguousarray(surfels, np.float32) if not isinstance(surfels, torch.Tensor) else surfels, torch.float32)
+    n, stride = (s.shape[0], s.shape[1] * 4) if s.numel() else (0, 48)
+    t_inv = np.ascontiguousarray(np.linalg.inv(np.asarray(pose, np.float64)).astype(np.float32).reshape(16))
+    keys = torch.empty(L.ef_op_splat_scratch_bytes(rows, cols), dtype=torch.uint8, device="cuda")
+    img = torch.empty((rows, cols, 4), dtype=torch.uint8, device="cuda")
+    v = torch.empty((rows, cols, 4), dtype=torch.float32, device="cuda")
+    nm = torch.empty((rows, cols, 4), dtype=torch.float32, device="cuda")
+    tm = torch.empty((rows, cols), dtype=torch.uint16, device="cuda")
+    _chk(L.ef_op_splat_predict(_p(s) if n else None, C.c_size_t(stride), n, t_inv.ctypes.data_as(C.c_void_p), C.c_float(cx), C.c_float(cy),
+                               C.c_float(fx), C.c_float(fy), rows, cols, C.c_float(maxDepth), C.c_float(confThreshold), int(time), int(maxTime),
+                               int(timeDelta), _p(keys), _p(img), _p(v), _p(nm), _p(tm), _stream()), "ef_op_splat_predict")
+    return _np(img), _np(v), _np(nm), _np(tm)
+
+
+def _fill_geom(name, predicted, depth, cx, cy, fx, fy, passthrough):
+    L = binding.lib()
+    p = _dev(predicted, torch.float32)
+    d = _dev(depth, torch.uint16)
+    r, c = d.shape
+    out = torch.empty_like(p)
+    _chk(getattr(L, name)(_p(p), _p(d), r, c, C.c_float(cx), C.c_float(cy), C.c_float(fx), C.c_float(fy), int(passthrough), _p(out), _stream()), name)
+    return _np(out)
+
+
+def fillVertex(predicted, depth, cx, cy, fx, fy, passthrough=False):
+    """FillIn::vertex (Shaders/fill_vertex.frag)"""
+    return _fill_geom("ef_op_fill_vertex", predicted, depth, cx, cy, fx, fy, passthrough)
+
+
+def fillNormal(predicted, depth, cx, cy, fx, fy, passthrough=False):
+    """FillIn::normal (Shaders/fill_normal.frag)"""
+    return _fill_geom("ef_op_fill_normal", predicted, depth, cx, cy, fx, fy, passthrough)
+
+
+def fillImage(predicted, rgba, passthrough=False):
+    """FillIn::image (Shaders/fill_rgb.frag)"""
+    L = binding.lib()
+    p, r = _dev(predicted, torch.uint8), _dev(rgba, torch.uint8)
+    out = torch.empty_like(p)
+    _chk(L.ef_op_fill_rgb(_p(p), _p(r), p.shape[0], p.shape[1], int(passthrough), _p(out), _stream()), "ef_op_fill_rgb")
+    return _np(out)

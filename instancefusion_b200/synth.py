@@ -230,3 +230,30 @@ def frame_pair(K: Intrinsics, seed: int = 1234, device="cpu"):
     f0 = render(pose0, K, seed=seed, frame_id=0, device=device)
     f1 = render(pose1, K, seed=seed, frame_id=1, device=device)
     return pose0, pose1, f0, f1
+
+
+def surfels_from_frame(pose_c2w, vmap, nmap, rgba, K: Intrinsics, time: int = 1, confidence: float = 10.0, stride_floats: int = 12):
+    """A surfel map made of ONE frame, the way GlobalModel::initialise seeds the map from the first frame
+    (elasticfusionpublic/Core/src/Shaders/init_unstable.vert, surfels.glsl:19-34): one surfel per valid pixel with
+    position | confidence, encoded colour | 0 | initTime | time, normal | radius, in the WORLD frame.
+    numpy in, numpy (N, stride_floats) float32 out (stride 12 = ElasticFusion's 48-byte vertex, 64 = InstanceFusion's 256).
+    Input for the model-prediction operator (ops.splatPredict) in tests and tools; not a fusion step."""
+    import numpy as np
+    pose = np.asarray(pose_c2w, np.float32)
+    v = np.asarray(vmap, np.float32).reshape(-1, 4)[:, :3]
+    n = np.asarray(nmap, np.float32).reshape(-1, 4)[:, :3]
+    c = np.asarray(rgba, np.uint8).reshape(-1, 4).astype(np.int32)
+    ok = (v[:, 2] > 0) & np.isfinite(n[:, 0]) & (np.abs(n).sum(1) > 0)
+    v, n, c = v[ok], n[ok], c[ok]
+    mean_focal = 0.5 * (K.fx + K.fy)
+    radius = (v[:, 2] / mean_focal) * 1.41421356237
+    radius = np.minimum(2.0 * radius, radius / np.maximum(np.abs(n[:, 2]), 1e-6))  # surfels.glsl:25-33
+    out = np.zeros((v.shape[0], stride_floats), np.float32)
+    out[:, 0:3] = v @ pose[:3, :3].T + pose[:3, 3]
+    out[:, 3] = confidence
+    out[:, 4] = ((c[:, 0] << 16) + (c[:, 1] << 8) + c[:, 2]).astype(np.float32)  # color.glsl:19-25 encodeColor
+    out[:, 6] = time
+    out[:, 7] = time
+    out[:, 8:11] = n @ pose[:3, :3].T
+    out[:, 11] = radius
+    return out

@@ -1372,3 +1372,235 @@ void efo_depth_metric(const uint16_t * src, int rows, int cols, float max_depth_
         dst[i] = (value > max_mm || value < 300u) ? 0.f : (float)value / 1000.0f;
     }
 }
+
+/* ------------------------------------------------------------------------------------------ */
+/* the step around the tracker (OpenGL in the reference): model prediction + fill-in          */
+/* IndexMap::combinedPredict IndexMap.cpp:468-575, Shaders/splat.vert:19-88,                  */
+/* Shaders/combo_splat.frag:19-67; FillIn: Shaders/fill_vertex.frag, fill_normal.frag,        */
+/* fill_rgb.frag, geometry.glsl:49-59.                                                         */
+/* PARITY UNPINNED against a GL driver (none in this image): what GL leaves to the             */
+/* implementation is fixed as follows and the CUDA kernels are compared with THIS statement:  */
+/*  - a sprite of size s centred on window (xw, yw) covers the fragments whose centres        */
+/*    (i + 0.5, j + 0.5) lie in [xw - s/2, xw + s/2) x [yw - s/2, yw + s/2); s is clamped to  */
+/*    [1, 64]; a sprite whose centre is outside the viewport is clipped;                        */
+/*  - depth buffer: 24-bit unsigned normalised, GL_LESS, surfels submitted in index order     */
+/*    (so the lower index wins a tie);                                                        */
+/*  - normalize(v) = v / sqrt(dot(v, v)), dot summed left to right, IEEE operations, no FMA   */
+/*    (this file is built with -ffp-contract=off).                                            */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct { float x, y, z; } p3;
+static inline float p3_dot(p3 a, p3 b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }
+static inline p3 p3_normalize(p3 a)
+{
+    const float len = sqrtf(p3_dot(a, a));
+    p3 r = {a.x / len, a.y / len, a.z / len};
+    return r;
+}
+static inline p3 p3_cross(p3 a, p3 b)
+{
+    p3 r = {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
+    return r;
+}
+
+typedef struct
+{
+    const float * t; /* rows 0..2 of t_inv */
+    float cx, cy, fx, fy;
+    int rows, cols;
+    float max_depth, conf_threshold;
+    int time, max_time, time_delta;
+} splat_params;
+
+typedef struct { p3 pos, nrm; float conf, rad, xw, yw, size; } surfel_view;
+
+static inline void splat_project(const splat_params * P, float x, float y, float z, float * u, float * v)
+{
+    *u = (P->fx * x) / z + P->cx; /* splat.vert:40-45 */
+    *v = (P->fy * y) / z + P->cy;
+}
+
+/* splat.vert:47-88 */
+static int splat_vertex_stage(const splat_params * P, const float * s, surfel_view * S)
+{
+    const float * t = P->t;
+    const float px = s[0], py = s[1], pz = s[2], conf = s[3], tstamp = s[7];
+    S->pos.x = ((t[0] * px + t[1] * py) + t[2] * pz) + t[3];
+    S->pos.y = ((t[4] * px + t[5] * py) + t[6] * pz) + t[7];
+    S->pos.z = ((t[8] * px + t[9] * py) + t[10] * pz) + t[11];
+    if(S->pos.z > P->max_depth || S->pos.z < 0 || conf < P->conf_threshold || (float)P->time - tstamp > (float)P->time_delta ||
+       tstamp > (float)P->max_time)
+        return 0;
+    splat_project(P, S->pos.x, S->pos.y, S->pos.z, &S->xw, &S->yw);
+    if(!(S->xw >= 0.f && S->xw <= (float)P->cols && S->yw >= 0.f && S->yw <= (float)P->rows)) return 0;
+    S->conf = conf;
+    S->rad = s[11];
+    {
+        const float nx = s[8], ny = s[9], nz = s[10];
+        p3 rn = {(t[0] * nx + t[1] * ny) + t[2] * nz, (t[4] * nx + t[5] * ny) + t[6] * nz, (t[8] * nx + t[9] * ny) + t[10] * nz};
+        S->nrm = p3_normalize(rn);
+    }
+    {
+        p3 xa = {S->nrm.y - S->nrm.z, -S->nrm.x, S->nrm.x};
+        const p3 xd = p3_normalize(xa);
+        const float scale = S->rad * 1.41421356f;
+        const p3 x1 = {xd.x * scale, xd.y * scale, xd.z * scale};
+        const p3 y1 = p3_cross(S->nrm, x1);
+        float u[4], v[4];
+        splat_project(P, S->pos.x + x1.x, S->pos.y + x1.y, S->pos.z + x1.z, &u[0], &v[0]);
+        splat_project(P, S->pos.x + y1.x, S->pos.y + y1.y, S->pos.z + y1.z, &u[1], &v[1]);
+        splat_project(P, S->pos.x - y1.x, S->pos.y - y1.y, S->pos.z - y1.z, &u[2], &v[2]);
+        splat_project(P, S->pos.x - x1.x, S->pos.y - x1.y, S->pos.z - x1.z, &u[3], &v[3]);
+        const float xmin = fminf(u[0], fminf(u[1], fminf(u[2], u[3]))), xmax = fmaxf(u[0], fmaxf(u[1], fmaxf(u[2], u[3])));
+        const float ymin = fminf(v[0], fminf(v[1], fminf(v[2], v[3]))), ymax = fmaxf(v[0], fmaxf(v[1], fmaxf(v[2], v[3])));
+        const float size = fmaxf(0.f, fmaxf(fabsf(xmax - xmin), fabsf(ymax - ymin)));
+        if(!(size == size)) return 0;
+        S->size = fminf(fmaxf(size, 1.f), 64.f);
+    }
+    return 1;
+}
+
+/* combo_splat.frag:37-67 */
+static int splat_fragment_stage(const splat_params * P, const surfel_view * S, int px, int py, float * z, unsigned * depth24)
+{
+    const float fxc = (float)px + 0.5f, fyc = (float)py + 0.5f;
+    p3 la = {(fxc - P->cx) / P->fx, (fyc - P->cy) / P->fy, 1.f};
+    const p3 l = p3_normalize(la);
+    const float k = p3_dot(S->pos, S->nrm) / p3_dot(l, S->nrm);
+    const p3 c = {k * l.x, k * l.y, k * l.z};
+    const p3 d = {c.x - S->pos.x, c.y - S->pos.y, c.z - S->pos.z};
+    if(!(p3_dot(d, d) <= S->rad * S->rad)) return 0;
+    *z = c.z;
+    {
+        const float depth = c.z / (2.f * P->max_depth) + 0.5f;
+        if(!(depth >= 0.f && depth <= 1.f)) return 0;
+        *depth24 = (unsigned)lrintf(depth * 16777215.f);
+    }
+    return 1;
+}
+
+void efo_splat_predict(const float * surfels, int stride_floats, int count, const float * t_inv16, float cx, float cy, float fx, float fy, int rows,
+                       int cols, float max_depth, float conf_threshold, int time, int max_time, int time_delta, uint8_t * image_rgba8,
+                       float * vertex_rgba32f, float * normal_rgba32f, uint16_t * time_u16)
+{
+    const splat_params P = {t_inv16, cx, cy, fx, fy, rows, cols, max_depth, conf_threshold, time, max_time, time_delta};
+    const size_t n = (size_t)rows * cols;
+    unsigned * zbuf = (unsigned *)malloc(n * sizeof(unsigned));
+    int * owner = (int *)malloc(n * sizeof(int));
+    for(size_t i = 0; i < n; i++) { zbuf[i] = 0xffffffffu; owner[i] = -1; }
+    /* the draw: surfels in submission order, GL_LESS */
+    for(int i = 0; i < count; i++)
+    {
+        surfel_view S;
+        if(!splat_vertex_stage(&P, surfels + (size_t)i * stride_floats, &S)) continue;
+        const float h = S.size * 0.5f;
+        int x0 = (int)ceilf((S.xw - h) - 0.5f), x1 = (int)ceilf((S.xw + h) - 0.5f);
+        int y0 = (int)ceilf((S.yw - h) - 0.5f), y1 = (int)ceilf((S.yw + h) - 0.5f);
+        if(x0 < 0) x0 = 0;
+        if(y0 < 0) y0 = 0;
+        if(x1 > cols) x1 = cols;
+        if(y1 > rows) y1 = rows;
+        for(int y = y0; y < y1; y++)
+            for(int x = x0; x < x1; x++)
+            {
+                float z;
+                unsigned d;
+                if(splat_fragment_stage(&P, &S, x, y, &z, &d) && d < zbuf[(size_t)y * cols + x])
+                {
+                    zbuf[(size_t)y * cols + x] = d;
+                    owner[(size_t)y * cols + x] = i;
+                }
+            }
+    }
+    /* the render targets, cleared to zero */
+    for(size_t i = 0; i < n; i++)
+    {
+        float v[4] = {0, 0, 0, 0}, nn[4] = {0, 0, 0, 0};
+        uint8_t img[4] = {0, 0, 0, 0};
+        uint16_t tm = 0;
+        if(owner[i] >= 0)
+        {
+            const float * s = surfels + (size_t)owner[i] * stride_floats;
+            const int y = (int)(i / cols), x = (int)(i - (size_t)y * cols);
+            surfel_view S;
+            float z;
+            unsigned d;
+            splat_vertex_stage(&P, s, &S);
+            splat_fragment_stage(&P, &S, x, y, &z, &d);
+            {
+                const float fxc = (float)x + 0.5f, fyc = (float)y + 0.5f;
+                const int rgb = (int)s[4]; /* color.glsl:27-34 */
+                img[0] = (rgb >> 16) & 0xff; img[1] = (rgb >> 8) & 0xff; img[2] = rgb & 0xff; img[3] = 255;
+                v[0] = ((fxc - cx) * z) * (1.f / fx); v[1] = ((fyc - cy) * z) * (1.f / fy); v[2] = z; v[3] = S.conf; /* :61 */
+                nn[0] = S.nrm.x; nn[1] = S.nrm.y; nn[2] = S.nrm.z; nn[3] = S.rad;
+                tm = (uint16_t)(unsigned)s[6]; /* :65 */
+            }
+        }
+        if(image_rgba8) memcpy(image_rgba8 + 4 * i, img, 4);
+        memcpy(vertex_rgba32f + 4 * i, v, sizeof(v));
+        memcpy(normal_rgba32f + 4 * i, nn, sizeof(nn));
+        if(time_u16) time_u16[i] = tm;
+    }
+    free(zbuf);
+    free(owner);
+}
+
+/* geometry.glsl:42-47 on the raw depth; texture fetches clamp to the edge */
+static p3 fill_raw_vertex(const uint16_t * depth, int rows, int cols, float cx, float cy, float inv_fx, float inv_fy, int x, int y)
+{
+    const int xs = x < 0 ? 0 : (x > cols - 1 ? cols - 1 : x), ys = y < 0 ? 0 : (y > rows - 1 ? rows - 1 : y);
+    const float z = (float)depth[(size_t)ys * cols + xs] / 1000.0f;
+    p3 r = {(((float)x - cx) * z) * inv_fx, (((float)y - cy) * z) * inv_fy, z};
+    return r;
+}
+
+/* Shaders/fill_vertex.frag:19-53 */
+void efo_fill_vertex(const float * predicted, const uint16_t * depth, int rows, int cols, float cx, float cy, float fx, float fy, int passthrough,
+                     float * out)
+{
+    const float ifx = 1.f / fx, ify = 1.f / fy;
+    for(int y = 0; y < rows; y++)
+        for(int x = 0; x < cols; x++)
+        {
+            const size_t i = (size_t)y * cols + x;
+            if(predicted[4 * i + 2] == 0 || passthrough == 1)
+            {
+                const p3 v = fill_raw_vertex(depth, rows, cols, cx, cy, ifx, ify, x, y);
+                out[4 * i] = v.x; out[4 * i + 1] = v.y; out[4 * i + 2] = v.z; out[4 * i + 3] = 1.f;
+            }
+            else
+                memcpy(out + 4 * i, predicted + 4 * i, 16);
+        }
+}
+
+/* Shaders/fill_normal.frag:19-55, geometry.glsl:49-59 */
+void efo_fill_normal(const float * predicted, const uint16_t * depth, int rows, int cols, float cx, float cy, float fx, float fy, int passthrough,
+                     float * out)
+{
+    const float ifx = 1.f / fx, ify = 1.f / fy;
+    for(int y = 0; y < rows; y++)
+        for(int x = 0; x < cols; x++)
+        {
+            const size_t i = (size_t)y * cols + x;
+            if(predicted[4 * i + 2] == 0 || passthrough == 1)
+            {
+                const p3 v = fill_raw_vertex(depth, rows, cols, cx, cy, ifx, ify, x, y);
+                const p3 vx = fill_raw_vertex(depth, rows, cols, cx, cy, ifx, ify, x + 1, y);
+                const p3 vy = fill_raw_vertex(depth, rows, cols, cx, cy, ifx, ify, x, y + 1);
+                const p3 dx = {vx.x - v.x, vx.y - v.y, vx.z - v.z}, dy = {vy.x - v.x, vy.y - v.y, vy.z - v.z};
+                const p3 n = p3_normalize(p3_cross(dx, dy));
+                out[4 * i] = n.x; out[4 * i + 1] = n.y; out[4 * i + 2] = n.z; out[4 * i + 3] = 1.f;
+            }
+            else
+                memcpy(out + 4 * i, predicted + 4 * i, 16);
+        }
+}
+
+/* Shaders/fill_rgb.frag:19-37 */
+void efo_fill_rgb(const uint8_t * predicted, const uint8_t * raw, int rows, int cols, int passthrough, uint8_t * out)
+{
+    for(size_t i = 0; i < (size_t)rows * cols; i++)
+    {
+        const uint8_t * s = predicted + 4 * i;
+        memcpy(out + 4 * i, ((int)s[0] + s[1] + s[2] == 0 || passthrough == 1) ? raw + 4 * i : s, 4);
+    }
+}

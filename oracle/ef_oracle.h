@@ -61,6 +61,17 @@ void efo_derivative_images(const uint8_t * src, int rows, int cols, int16_t * dx
 void efo_depth_bilateral(const uint16_t * src, int rows, int cols, float max_depth_m, uint16_t * dst);
 void efo_depth_metric(const uint16_t * src, int rows, int cols, float max_depth_m, float * dst);
 
+/* the step around the tracker (OpenGL in the reference): IndexMap::combinedPredict (Shaders/splat.vert, combo_splat.frag)
+ * and FillIn (Shaders/fill_vertex.frag, fill_normal.frag, fill_rgb.frag).  Parity against GL is unpinned; see ef_oracle.c */
+void efo_splat_predict(const float * surfels, int stride_floats, int count, const float * t_inv16, float cx, float cy, float fx, float fy, int rows,
+                       int cols, float max_depth, float conf_threshold, int time, int max_time, int time_delta, uint8_t * image_rgba8,
+                       float * vertex_rgba32f, float * normal_rgba32f, uint16_t * time_u16);
+void efo_fill_vertex(const float * predicted, const uint16_t * depth, int rows, int cols, float cx, float cy, float fx, float fy, int passthrough,
+                     float * out);
+void efo_fill_normal(const float * predicted, const uint16_t * depth, int rows, int cols, float cx, float cy, float fx, float fy, int passthrough,
+                     float * out);
+void efo_fill_rgb(const uint8_t * predicted, const uint8_t * raw, int rows, int cols, int passthrough, uint8_t * out);
+
 void efo_project_point_cloud(const float * depth, int rows, int cols, float fx, float fy, float cx, float cy, float * cloud);
 
 /* reduce.cu:257-490.  out29 = 27 upper-triangle products of [J|r] + residual + inliers,

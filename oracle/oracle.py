@@ -413,3 +413,38 @@ class OracleTracker:
         n = self.lib.efr_tracker_download(self.t, name.encode(), C.c_int(level), _fp(out))
         assert n == out.nbytes, (name, n, out.nbytes)
         return out
+
+
+# ---- model prediction + fill-in (OpenGL in the reference; CPU restatement only, parity against GL unpinned) ----
+def splat_predict(surfels, pose, cx, cy, fx, fy, rows, cols, max_depth, conf_threshold, time, max_time, time_delta):
+    s = _c(surfels, np.float32)
+    n, stride = (s.shape[0], s.shape[1]) if s.size else (0, 12)
+    t_inv = np.ascontiguousarray(np.linalg.inv(np.asarray(pose, np.float64)).astype(np.float32).reshape(16))
+    img = np.zeros((rows, cols, 4), np.uint8)
+    v = np.zeros((rows, cols, 4), np.float32)
+    nm = np.zeros((rows, cols, 4), np.float32)
+    tm = np.zeros((rows, cols), np.uint16)
+    cpu().efo_splat_predict(_fp(s) if n else None, C.c_int(stride), C.c_int(n), _fp(t_inv), C.c_float(cx), C.c_float(cy), C.c_float(fx),
+                            C.c_float(fy), C.c_int(rows), C.c_int(cols), C.c_float(max_depth), C.c_float(conf_threshold), C.c_int(time),
+                            C.c_int(max_time), C.c_int(time_delta), _fp(img), _fp(v), _fp(nm), _fp(tm))
+    return img, v, nm, tm
+
+
+def fill_vertex(predicted, depth, cx, cy, fx, fy, passthrough=False, normal=False):
+    p, d = _c(predicted, np.float32), _c(depth, np.uint16)
+    r, c = d.shape
+    out = np.zeros_like(p)
+    fn = cpu().efo_fill_normal if normal else cpu().efo_fill_vertex
+    fn(_fp(p), _fp(d), C.c_int(r), C.c_int(c), C.c_float(cx), C.c_float(cy), C.c_float(fx), C.c_float(fy), C.c_int(int(passthrough)), _fp(out))
+    return out
+
+
+def fill_normal(predicted, depth, cx, cy, fx, fy, passthrough=False):
+    return fill_vertex(predicted, depth, cx, cy, fx, fy, passthrough, normal=True)
+
+
+def fill_rgb(predicted, raw, passthrough=False):
+    p, r = _c(predicted, np.uint8), _c(raw, np.uint8)
+    out = np.zeros_like(p)
+    cpu().efo_fill_rgb(_fp(p), _fp(r), C.c_int(p.shape[0]), C.c_int(p.shape[1]), C.c_int(int(passthrough)), _fp(out))
+    return out
