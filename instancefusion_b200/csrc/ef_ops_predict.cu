@@ -15,8 +15,8 @@
 //   k_fill_*         the three fill-in passes, one thread per pixel.
 //
 // Rasterisation details OpenGL leaves to the implementation (which fragment centres a sprite of fractional size covers,
-// the largest sprite, normalize / division rounding) are fixed here and stated in oracle/ef_oracle.c, the CPU restatement
-// the tests compare against bit for bit; parity against a GL driver is unpinned (no GL in this image).  All arithmetic
+// the largest sprite, normalize / division rounding) are fixed here and stated again in the CPU restatement the tests
+// compare against bit for bit; parity against a GL driver is unpinned (no GL in this image).  All arithmetic
 // uses explicit round-to-nearest intrinsics (no FMA contraction, IEEE division and square root) so that the restatement
 // can follow it operation by operation.
 #include "ef_kernels.h"
