@@ -135,3 +135,36 @@ def test_tracking_against_the_predicted_model():
         assert np.linalg.norm(t - pose1[:3, 3]) < 3e-3 and util.rot_err(R, pose1[:3, :3]) < 2e-3
     finally:
         tr.close()
+
+
+@pytest.mark.gpu
+def test_closed_loop_over_a_trajectory_stays_on_track():
+    """12 frames of the bench trajectory in closed loop, every buffer device-resident: map seeded from frame 0 -> CUDA prediction
+    at the last ESTIMATED pose -> tracker -> next pose.  The pose error must stay at the millimetre level (the prediction samples
+    the surface through fragment CENTRES, i + 0.5, while the tracker's own maps use integer pixel coordinates -- the reference's
+    GL / CUDA conventions differ by that half pixel as well -- so the photometric term carries a bias of ~z / fx / 2)."""
+    import torch
+    import instancefusion_b200 as ef
+    from instancefusion_b200 import rgbd_odometry as RO
+    from instancefusion_b200.predict import ModelPredictor
+    w, h, n = 640, 480, 12
+    K = synth.Intrinsics.kinect(w, h)
+    gt = synth.trajectory(n, seed=2024).numpy()
+    frames = [synth.render(torch.from_numpy(gt[k]), K, seed=2024, frame_id=k, device="cuda") for k in range(n)]
+    f0 = frames[0]
+    surfels = torch.from_numpy(synth.surfels_from_frame(gt[0], f0["vmap"].cpu().numpy(), f0["nmap"].cpu().numpy(), f0["rgba"].cpu().numpy(), K)).cuda()
+    trk = ef.RGBDOdometry(w, h, K.cx, K.cy, K.fx, K.fy, solve_mode=RO.EF_SOLVE_DEVICE)
+    pred = ModelPredictor(w, h, K.cx, K.cy, K.fx, K.fy)
+    try:
+        pose = gt[0].astype(np.float32).copy()
+        errs = []
+        for k in range(1, n):
+            img, v, nm, _ = pred.predict(surfels, pose, time=k + 1, timeDelta=10 ** 6, confThreshold=9.0)
+            torch.cuda.current_stream().synchronize()
+            t, R = trk.trackFrameToModel(v, nm, img, frames[k]["depth"], frames[k]["rgba"], 20.0, pose, False, 10.0, True, False, False)
+            pose = pose.copy()
+            pose[:3, :3], pose[:3, 3] = R, t
+            errs.append(float(np.linalg.norm(t - gt[k][:3, 3])))
+        assert max(errs) < 6e-3, errs
+    finally:
+        trk.close()
