@@ -306,6 +306,13 @@ EF_HD void compose_pose(const double * resultRt, const float * Rprev, const floa
     }
 }
 
+// the same from the 3x4 block alone (row-major, 12 entries)
+EF_HD void compose_pose_affine12(const double * Rt12, const float * Rprev, const float * tprev, float * Rcurr, float * tcurr)
+{
+    const double M[16] = {Rt12[0], Rt12[1], Rt12[2], Rt12[3], Rt12[4], Rt12[5], Rt12[6], Rt12[7], Rt12[8], Rt12[9], Rt12[10], Rt12[11], 0, 0, 0, 1};
+    compose_pose(M, Rprev, tprev, Rcurr, tcurr);
+}
+
 // RGBDOdometry.cpp:424-434: from resultRt build krkInv = K R K^-1 and kt = K t of Rt = resultRt^-1
 EF_HD void rgb_warp_params(const double * resultRt, const double * K, const double * K_inv, float * krkinv9, float * kt3)
 {

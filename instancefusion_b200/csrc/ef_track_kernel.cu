@@ -71,6 +71,10 @@ constexpr int kIcpBatch = EF_TRACK_ICP_BATCH; // pixels of one thread whose load
 #define EF_TRACK_ICP_SPLIT 0
 #endif
 constexpr bool kIcpSplit = EF_TRACK_ICP_SPLIT != 0;
+#ifndef EF_TRACK_SCALAR_SOLVER
+#define EF_TRACK_SCALAR_SOLVER 1
+#endif
+constexpr bool kScalarSolver = EF_TRACK_SCALAR_SOLVER != 0; // the host step of CTA 0: every lane scalar (1) or spread over the lanes (0)
 constexpr int kWarps = kThreads / 32;
 constexpr int kMaxIters = 32;    // SE3 iterations per call (19 in the reference schedule)
 constexpr int kDbgStamps = 10;
@@ -272,7 +276,7 @@ __device__ __forceinline__ Mat33 mat_from(const float * m)
 struct Solver
 {
     double resultRt[32];                          // 3x4 block row-major in [0, 12); [12, 32) is scratch so that all lanes may store
-    double last_S[27];                            // combined normal equations of the last solve (lastA / lastb)
+    double last_S[28];                            // combined normal equations of the last solve (lastA / lastb); [27] is scratch
     double so3_R[9], so3_lastR[9];
     float Rcurr[9], tcurr[3];
     float Rprev[9], tprev[3];                     // copies of the launch constants (indexed per lane by the warp solver)
@@ -449,6 +453,144 @@ __device__ __forceinline__ void warp_solve_se3(Solver * S, const float * s_final
     __syncwarp();
 }
 
+// The same host step with NO lane parallelism: every lane of warp 0 runs the scalar routine on identical data (shared-memory
+// broadcast loads), the 27 normal-equation entries in registers.  A double shuffle costs 26 cycles and a DFMA 8 (tools/op_latency),
+// so the lane-spread version above spends most of each LDL^T pivot moving operands (196 cycles per pivot); here a pivot is
+// reciprocal -> multiply -> fused multiply-add (~80 cycles), its ~15 trailing updates are independent DFMAs, and a warp-wide
+// DFMA issues as fast as a one-lane one.  No shuffles and no lane-dependent branches, so nothing can take the WARPSYNC slow path.
+__device__ __forceinline__ void warp_solve_se3_scalar(Solver * S, const float * s_final, int icp, int rgb, float icp_weight, int level,
+                                                      bool hand_over, long long * dbg = nullptr)
+{
+    long long tk[5] = {0, 0, 0, 0, 0};
+    if(dbg) tk[0] = clock64();
+    const int lane = threadIdx.x & 31;
+    __syncwarp();
+    // combined normal equations (:547-553): lane k converts and combines entry k (one conversion per lane instead of 54 per
+    // lane), parks it in last_S -- which is lastA / lastb of this solve anyway (RGBDOdometry.h:72-73) -- and every lane
+    // then reads all 27 entries back as 14 broadcast 128-bit loads
+    const double w = icp_weight, ww = w * w;
+    const int sl = lane < 27 ? lane : 27;
+    const int lr = (sl >= 7) + (sl >= 13) + (sl >= 18) + (sl >= 22) + (sl >= 25);
+    const bool rhs = (sl - (lr * 7 - (lr * (lr - 1)) / 2) + lr) == 6;
+    const double l_icp = (double)s_final[sl], l_rgb = (double)s_final[29 + sl];
+    S->last_S[sl] = (icp && rgb) ? (rhs ? (l_rgb + w * l_icp) : (l_rgb + ww * l_icp)) : (icp ? l_icp : l_rgb);
+    __syncwarp();
+    double a[28];
+#pragma unroll
+    for(int k = 0; k < 14; k++)
+    {
+        const double2 v = reinterpret_cast<const double2 *>(S->last_S)[k];
+        a[2 * k] = v.x;
+        a[2 * k + 1] = v.y;
+    }
+
+    // x = A^-1 b (:552-564): hm::ldlt_solve_spd6_acc with the Newton reciprocal
+    double inv[6], x[6];
+#pragma unroll
+    for(int j = 0; j < 6; j++)
+    {
+        inv[j] = fast_rcp(a[hm::acc_index(j, j)]);
+        double l[6];
+#pragma unroll
+        for(int i = j + 1; i < 6; i++) l[i] = a[hm::acc_index(j, i)] * inv[j];
+#pragma unroll
+        for(int i = j + 1; i < 6; i++)
+        {
+#pragma unroll
+            for(int k = i; k < 7; k++) a[hm::acc_index(i, k)] = fma(-l[i], a[hm::acc_index(j, k)], a[hm::acc_index(i, k)]);
+        }
+#pragma unroll
+        for(int i = j + 1; i < 6; i++) a[hm::acc_index(j, i)] = l[i];
+    }
+    if(dbg) tk[1] = clock64();
+    // back substitution, column oriented: x(i) is final once the rows below it were applied
+    double wv[6];
+#pragma unroll
+    for(int i = 0; i < 6; i++) wv[i] = a[hm::acc_index(i, 6)] * inv[i];
+#pragma unroll
+    for(int i = 5; i >= 0; i--)
+    {
+        x[i] = wv[i];
+#pragma unroll
+        for(int r = 0; r < i; r++) wv[r] = fma(-a[hm::acc_index(r, i)], x[i], wv[r]);
+    }
+    if(dbg) tk[2] = clock64();
+
+    // OdometryProvider.h:35-71 rodrigues(x[3:6])
+    const double rx = x[3], ry = x[4], rz = x[5];
+    const double t2 = rx * rx + ry * ry + rz * rz;
+    double R[9];
+    if(t2 < 0.0625)
+    {
+        // two short alternating series in t^2 (see warp_solve_se3): R = (1 - B t^2) I + B r r^T + A [r]x
+        double A = 1.0 / 121645100408832000.0, B = 1.0 / 2432902008176640000.0; // 1/19!, 1/20!
+        A = fma(-t2, A, 1.0 / 355687428096000.0);    B = fma(-t2, B, 1.0 / 6402373705728000.0);
+        A = fma(-t2, A, 1.0 / 1307674368000.0);      B = fma(-t2, B, 1.0 / 20922789888000.0);
+        A = fma(-t2, A, 1.0 / 6227020800.0);         B = fma(-t2, B, 1.0 / 87178291200.0);
+        A = fma(-t2, A, 1.0 / 39916800.0);           B = fma(-t2, B, 1.0 / 479001600.0);
+        A = fma(-t2, A, 1.0 / 362880.0);             B = fma(-t2, B, 1.0 / 3628800.0);
+        A = fma(-t2, A, 1.0 / 5040.0);               B = fma(-t2, B, 1.0 / 40320.0);
+        A = fma(-t2, A, 1.0 / 120.0);                B = fma(-t2, B, 1.0 / 720.0);
+        A = fma(-t2, A, 1.0 / 6.0);                  B = fma(-t2, B, 1.0 / 24.0);
+        A = fma(-t2, A, 1.0);                        B = fma(-t2, B, 0.5);
+        const double d = fma(-B, t2, 1.0);
+        const double bx = B * rx, by = B * ry, bz = B * rz;
+        R[0] = fma(bx, rx, d);             R[1] = fma(bx, ry, -(A * rz));    R[2] = fma(bx, rz, A * ry);
+        R[3] = fma(by, rx, A * rz);        R[4] = fma(by, ry, d);            R[5] = fma(by, rz, -(A * rx));
+        R[6] = fma(bz, rx, -(A * ry));     R[7] = fma(bz, ry, A * rx);       R[8] = fma(bz, rz, d);
+    }
+    else
+    {
+        const double xr[3] = {rx, ry, rz};
+        hm::rodrigues(xr, R);
+    }
+    if(dbg) tk[3] = clock64();
+    // OdometryProvider.h:73-93: resultRt = [R | x[0:3]] * resultRt
+    double rt[12], N[12];
+#pragma unroll
+    for(int i = 0; i < 12; i++) rt[i] = S->resultRt[i];
+#pragma unroll
+    for(int r = 0; r < 3; r++)
+#pragma unroll
+        for(int c = 0; c < 4; c++)
+        {
+            double v = R[r * 3] * rt[c];
+            v = fma(R[r * 3 + 1], rt[4 + c], v);
+            v = fma(R[r * 3 + 2], rt[8 + c], v);
+            N[r * 4 + c] = (c == 3) ? v + x[r] : v;
+        }
+    // every lane stores the same values (one transaction per entry); warp 1 derives the photometric warp from them
+#pragma unroll
+    for(int i = 0; i < 12; i++) S->resultRt[i] = N[i];
+    if(hand_over) solver_pair_sync();
+
+    // :571-583: [Rcurr | tcurr] = [Rprev | tprev] * (float(resultRt))^-1 with the Isometry3f inverse (R^T, -R^T t), float
+    float Rc[9], tc[3];
+    hm::compose_pose_affine12(N, S->Rprev, S->tprev, Rc, tc);
+    if(dbg) tk[4] = clock64();
+    if(dbg && lane == 0)
+    {
+        dbg[8] = tk[1] - tk[0]; // combine + LDL^T
+        dbg[9] = tk[2] - tk[1]; // back substitution
+        dbg[5] = tk[3] - tk[2]; // exponential map
+        dbg[4] = tk[4] - tk[3]; // update + compose
+    }
+    if(lane == 0)
+    {
+#pragma unroll
+        for(int i = 0; i < 9; i++) S->Rcurr[i] = Rc[i];
+#pragma unroll
+        for(int i = 0; i < 3; i++) S->tcurr[i] = tc[i];
+        S->se3_iterations[level]++;
+        if(icp)
+        {
+            S->last_icp_error = sqrtf(s_final[27]) / s_final[28]; // :515-516
+            S->last_icp_count = s_final[28];
+        }
+    }
+    __syncwarp();
+}
+
 // :480-481 -- pose of the next SE3 iteration (warp 0 of CTA 0) -> payload[0, 12) in shared memory
 __device__ __forceinline__ void warp_make_pose(const Solver * S, float * payload /*shared*/)
 {
@@ -491,6 +633,39 @@ __device__ __forceinline__ void warp_make_rgb_params(const Solver * S, float * p
     const double kt = (k3 == 0) ? fma(cx, tz, fx * tinv) : (k3 == 1) ? fma(cy, tz, fy * tinv) : tinv;
     if(lane < 9) payload[12 + lane] = (float)KRK;
     if(lane < 3) payload[21 + lane] = (float)kt;
+    __syncwarp();
+}
+
+// the same without lane parallelism (see warp_solve_se3_scalar): every lane evaluates hm::rgb_warp_params_sparse
+__device__ __forceinline__ void warp_make_rgb_params_scalar(const Solver * S, float * payload /*shared*/, float fxf, float fyf, float cxf, float cyf,
+                                                            const double * K_inv)
+{
+    const int lane = threadIdx.x & 31;
+    __syncwarp();
+    double m[12];
+#pragma unroll
+    for(int i = 0; i < 12; i++) m[i] = S->resultRt[i];
+    // Rt = resultRt^-1 (general affine inverse: adjugate / determinant)
+    const double c0 = m[5] * m[10] - m[6] * m[9], c1 = m[2] * m[9] - m[1] * m[10], c2 = m[1] * m[6] - m[2] * m[5];
+    const double c3 = m[6] * m[8] - m[4] * m[10], c4 = m[0] * m[10] - m[2] * m[8], c5 = m[2] * m[4] - m[0] * m[6];
+    const double c6 = m[4] * m[9] - m[5] * m[8], c7 = m[1] * m[8] - m[0] * m[9], c8 = m[0] * m[5] - m[1] * m[4];
+    const double det = m[0] * c0 + m[1] * c3 + m[2] * c6;
+    const double id = 1.0 / det;
+    const double Ai[9] = {c0 * id, c1 * id, c2 * id, c3 * id, c4 * id, c5 * id, c6 * id, c7 * id, c8 * id};
+    double ti[3];
+#pragma unroll
+    for(int r = 0; r < 3; r++) ti[r] = -(Ai[r * 3] * m[3] + Ai[r * 3 + 1] * m[7] + Ai[r * 3 + 2] * m[11]);
+    double KR[9], KRK[9];
+    hm::krk_sparse(Ai, (double)fxf, (double)fyf, (double)cxf, (double)cyf, K_inv, KR, KRK);
+    const double kt0 = fma((double)cxf, ti[2], (double)fxf * ti[0]), kt1 = fma((double)cyf, ti[2], (double)fyf * ti[1]);
+    if(lane == 0)
+    {
+#pragma unroll
+        for(int i = 0; i < 9; i++) payload[12 + i] = (float)KRK[i];
+        payload[21] = (float)kt0;
+        payload[22] = (float)kt1;
+        payload[23] = (float)ti[2];
+    }
     __syncwarp();
 }
 
@@ -927,7 +1102,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_track(const __grid_constant__ T
     __shared__ int s_wcnt[kWarps], s_wsig[kWarps];
     __shared__ int s_wtot[2 * kCompactGroup * kWarps];
     __shared__ int s_flag;
-    __shared__ Solver s_solver;
+    __shared__ __align__(16) Solver s_solver;
 
     const uint4 * my_par = A.par + (size_t)((blockIdx.x == 0 ? 0 : blockIdx.x - 1) % kReplicas) * kReplicaStride;
     const unsigned grid = gridDim.x;
@@ -1093,8 +1268,14 @@ __global__ void __launch_bounds__(kThreads, 1) k_track(const __grid_constant__ T
         gather_rows(A.rows, W, kRowChunks, arr, s_rows, s_red, s_final);
         stamp(2);
         if(warp == 0)
-            warp_solve_se3(S, s_final, A.icp, A.rgb, A.icp_weight, pending_level, hand_over,
-                           (TIMING && dbg_it < kMaxIters) ? A.dbg + (size_t)dbg_it * kDbgStamps : nullptr);
+        {
+            if(kScalarSolver)
+                warp_solve_se3_scalar(S, s_final, A.icp, A.rgb, A.icp_weight, pending_level, hand_over,
+                                      (TIMING && dbg_it < kMaxIters) ? A.dbg + (size_t)dbg_it * kDbgStamps : nullptr);
+            else
+                warp_solve_se3(S, s_final, A.icp, A.rgb, A.icp_weight, pending_level, hand_over,
+                               (TIMING && dbg_it < kMaxIters) ? A.dbg + (size_t)dbg_it * kDbgStamps : nullptr);
+        }
         stamp(3);
     };
 
@@ -1165,7 +1346,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_track(const __grid_constant__ T
                     // the photometric warp K R K^-1, K t of this iteration, in parallel with warp 0's pose composition
                     solver_pair_sync();
                     float * par = s_par[rel & 1u];
-                    warp_make_rgb_params(S, par, L.fx, L.fy, L.cx, L.cy, L.K_inv);
+                    if(kScalarSolver) warp_make_rgb_params_scalar(S, par, L.fx, L.fy, L.cx, L.cy, L.K_inv);
+                    else warp_make_rgb_params(S, par, L.fx, L.fy, L.cx, L.cy, L.K_inv);
                     warp_publish(A.par, par, 4, 4, rel);
                 }
                 stamp(1);
