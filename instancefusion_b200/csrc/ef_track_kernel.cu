@@ -77,7 +77,7 @@ constexpr bool kIcpSplit = EF_TRACK_ICP_SPLIT != 0;
 constexpr bool kScalarSolver = EF_TRACK_SCALAR_SOLVER != 0; // the host step of CTA 0: every lane scalar (1) or spread over the lanes (0)
 constexpr int kWarps = kThreads / 32;
 constexpr int kMaxIters = 32;    // SE3 iterations per call (19 in the reference schedule)
-constexpr int kDbgStamps = 10;
+constexpr int kDbgStamps = 13; // 0..9 per iteration; 10..12 level start (first iteration of a level only)
 constexpr int kRowChunks = 20;   // a partial row = 20 x (3 floats + flag) = 60 floats >= 29 ICP + 29 RGB sums
 constexpr int kRowFloats = kRowChunks * 3;
 constexpr int kSo3Chunks = 4;    // SO3 rows carry 11 floats
@@ -85,7 +85,10 @@ constexpr int kLineChunks = 8;   // the parameter line = 8 x (3 floats + flag) =
 constexpr int kPayload = kLineChunks * 3;
 constexpr int kParts = kThreads / 64; // final cross-CTA sum: kParts x 64 slots
 constexpr int kGatherBatch = 12; // row chunks a CTA-0 thread requests before it examines the first (147 x 20 / 256 = 11.5)
-constexpr int kCompactGroup = 4; // passes of the level-start compaction evaluated together
+#ifndef EF_TRACK_COMPACT_GROUP
+#define EF_TRACK_COMPACT_GROUP 3
+#endif
+constexpr int kCompactGroup = EF_TRACK_COMPACT_GROUP; // passes of the level-start compaction evaluated together
 constexpr int kMaxGrid = 255;    // CTAs of one launch (sizes the control buffers)
 constexpr unsigned kNoMatch = 0xffffffffu;
 constexpr int kCandBytes = 20;   // 12-byte candidate + 8-byte match record
@@ -772,56 +775,93 @@ struct CandStore
     float * r1;
 };
 
-// Level start: the iteration-invariant gates of RGBResidual::getProducts (reduce.cu:779-811) for this CTA's pixels,
-// survivors compacted in (pass, warp, lane) order.  Returns the candidate count (uniform over the CTA).
-// the gates of one pixel (pass p of this thread); returns whether it is a candidate and its packed words
+// Everything a pixel's gates read, requested up front and unconditionally (clamped addresses) so that the loads of all
+// pixels of a group are in flight together: the level start is otherwise a chain of three L2 round trips per pixel
+// (neighbours for the derivative -> depth -> 4x4 window), 24 000 cycles at 640x480.  The four aligned 8-byte runs that hold
+// the window rows y-2 .. y+1, columns x-2 .. x+1, also hold the 3x3 stencil of the derivative: nine loads per pixel.
+struct CandLoads
+{
+    float d1;              // next depth
+    unsigned lo[4], hi[4]; // window rows y-2 .. y+1
+    unsigned gxy;          // !DERIV: dIdx | dIdy << 16
+};
+
 template<bool DERIV>
-__device__ __forceinline__ bool candidate_of(const LevelArgs & L, const RgbResParams & RP, int u, unsigned & w0, unsigned & w1, float & d1)
+__device__ __forceinline__ void candidate_loads(const LevelArgs & L, int u, CandLoads & Q)
+{
+    const int cols = L.cols, rows = L.rows;
+    const int uu = u < 0 ? 0 : u;
+    const int y = uu / cols, x = uu - y * cols;
+    if constexpr(!DERIV) Q.gxy = ((unsigned)(unsigned short)__ldg(L.dIdx + uu)) | ((unsigned)(unsigned short)__ldg(L.dIdy + uu) << 16);
+    Q.d1 = __ldg(L.next_depth + uu);
+    const int last = rows * cols - 8;
+#pragma unroll
+    for(int r = 0; r < 4; r++)
+    {
+        const int lin = min(max((y + r - 2) * cols + x - 2, 0), last); // no clamp is active where the bytes are used
+        const unsigned * wp = reinterpret_cast<const unsigned *>(L.next_image + (lin & ~3));
+        Q.lo[r] = __ldg(wp);
+        Q.hi[r] = __ldg(wp + 1);
+    }
+}
+
+// the gates of one pixel from its loads; returns whether it is a candidate and its packed words
+template<bool DERIV>
+__device__ __forceinline__ bool candidate_of(const LevelArgs & L, const RgbResParams & RP, int u, const CandLoads & Q, unsigned & w0, unsigned & w1,
+                                             float & d1)
 {
     const int cols = L.cols;
     w0 = w1 = 0;
     d1 = 0.f;
     if(u < 0) return false;
-    bool keep = false;
     const int y = u / cols, x = u - y * cols;
-    short gx = 0, gy = 0;
+    // bytes[r] = I(y + r - 2, x - 2 .. x + 1), cut out of the aligned run that holds them
+    unsigned bytes[4];
+#pragma unroll
+    for(int r = 0; r < 4; r++) bytes[r] = __funnelshift_r(Q.lo[r], Q.hi[r], 8u * (unsigned)(((y + r - 2) * cols + x - 2) & 3));
+    short gx, gy;
     if constexpr(DERIV)
     {
         // computeDerivativeImages (cudafuncs.cu:583-639) fused in: this CTA's pixels of dIdx / dIdy, kept in global
         // memory as well because they are an output of the call (ef_tracker_download) and input of host-solve mode
-        const uint8_t * img = L.next_image;
-        derivative_px([&](int j, int i) { return __ldg(img + (size_t)j * cols + i); }, L.rows, cols, x, y, gx, gy);
+        if(x >= 2 && y >= 1 && x + 1 <= cols - 1 && y + 1 <= L.rows - 1 && (y + 1) * cols + x - 2 <= L.rows * cols - 8)
+        {
+            // (the last condition: the run of row y+1 was not clamped at the end of the image)
+            // the stencil of derivative_px (same taps, same order) from the window rows y-1, y, y+1, bytes 1 .. 3
+            const float tl = (float)((bytes[1] >> 8) & 0xffu), tm = (float)((bytes[1] >> 16) & 0xffu), tr = (float)(bytes[1] >> 24);
+            const float ml = (float)((bytes[2] >> 8) & 0xffu), mr = (float)(bytes[2] >> 24);
+            const float bl = (float)((bytes[3] >> 8) & 0xffu), bm = (float)((bytes[3] >> 16) & 0xffu), br = (float)(bytes[3] >> 24);
+            float fx = 0, fy = 0;
+            fx = __fmaf_rn(tl, -0.52201f, fx); fx = __fmaf_rn(tr, 0.52201f, fx); fx = __fmaf_rn(ml, -0.79451f, fx);
+            fx = __fmaf_rn(mr, 0.79451f, fx);  fx = __fmaf_rn(bl, -0.52201f, fx); fx = __fmaf_rn(br, 0.52201f, fx);
+            fy = __fmaf_rn(tl, -0.52201f, fy); fy = __fmaf_rn(tm, -0.79451f, fy); fy = __fmaf_rn(tr, -0.52201f, fy);
+            fy = __fmaf_rn(bl, 0.52201f, fy);  fy = __fmaf_rn(bm, 0.79451f, fy);  fy = __fmaf_rn(br, 0.52201f, fy);
+            gx = fx;
+            gy = fy;
+        }
+        else
+        {
+            const uint8_t * img = L.next_image; // image border (and column 1): the general statement, shifted taps included
+            derivative_px([&](int j, int i) { return __ldg(img + (size_t)j * cols + i); }, L.rows, cols, x, y, gx, gy);
+        }
         L.dIdx[u] = gx;
         L.dIdy[u] = gy;
     }
-    // the 16-pixel border of RGBResidual (:779-783)
-    if(y >= 16 && y < L.rows - 16 && x >= 16 && x < cols - 16)
+    else
     {
-        const size_t o = (size_t)y * cols + x;
-        if constexpr(!DERIV)
-        {
-            gx = L.dIdx[o];
-            gy = L.dIdy[o];
-        }
-        d1 = L.next_depth[o];
-        if(rgb_gate(RP, x, y, gx, gy, d1))
-        {
-            // 4x4 window [y-2, y+2) x [x-2, x+2) of the next image must be non-zero (:787-793): per row the four
-            // bytes are cut out of the aligned 8-byte run that holds them
-            unsigned win = 0xffffffffu, inext = 0;
-#pragma unroll
-            for(int r = -2; r < 2; r++)
-            {
-                const size_t lin = (size_t)(y + r) * cols + x - 2;
-                const unsigned * wp = reinterpret_cast<const unsigned *>(L.next_image + (lin & ~(size_t)3));
-                const unsigned bytes = __funnelshift_r(__ldg(wp), __ldg(wp + 1), 8 * (unsigned)(lin & 3));
-                win &= __vcmpne4(bytes, 0u);
-                if(r == 0) inext = (bytes >> 16) & 0xffu; // I_next(x, y)
-            }
-            keep = (win == 0xffffffffu);
-            w0 = (unsigned)x | ((unsigned)y << 12) | (inext << 24);
-            w1 = ((unsigned)gx & 0xffffu) | ((unsigned)gy << 16);
-        }
+        gx = (short)(Q.gxy & 0xffffu);
+        gy = (short)(Q.gxy >> 16);
+    }
+    // the 16-pixel border of RGBResidual (:779-783), the gradient and depth gates
+    bool keep = false;
+    if(rgb_gate(RP, x, y, gx, gy, Q.d1))
+    {
+        // 4x4 window [y-2, y+2) x [x-2, x+2) of the next image must be non-zero (:787-793)
+        const unsigned win = __vcmpne4(bytes[0], 0u) & __vcmpne4(bytes[1], 0u) & __vcmpne4(bytes[2], 0u) & __vcmpne4(bytes[3], 0u);
+        keep = (win == 0xffffffffu);
+        d1 = Q.d1;
+        w0 = (unsigned)x | ((unsigned)y << 12) | (((bytes[2] >> 16) & 0xffu) << 24); // I_next(x, y)
+        w1 = ((unsigned)gx & 0xffffu) | ((unsigned)gy << 16);
     }
     return keep;
 }
@@ -841,9 +881,16 @@ __device__ __forceinline__ int compact_candidates(const LevelArgs & L, const Rgb
         float d1[kCompactGroup];
         bool keep[kCompactGroup];
         int * wt = s_wtot + (grp & 1) * kCompactGroup * kWarps;
+        CandLoads Q[kCompactGroup];
+        int un[kCompactGroup];
 #pragma unroll
         for(int g = 0; g < kCompactGroup; g++)
-            keep[g] = candidate_of<DERIV>(L, RP, (p0 + g < passes) ? U.unit(p0 + g) : -1, w0[g], w1[g], d1[g]);
+        {
+            un[g] = (p0 + g < passes) ? U.unit(p0 + g) : -1;
+            candidate_loads<DERIV>(L, un[g], Q[g]);
+        }
+#pragma unroll
+        for(int g = 0; g < kCompactGroup; g++) keep[g] = candidate_of<DERIV>(L, RP, un[g], Q[g], w0[g], w1[g], d1[g]);
 #pragma unroll
         for(int g = 0; g < kCompactGroup; g++)
         {
@@ -984,16 +1031,30 @@ __device__ __forceinline__ bool rgb_rows_cands(const RgbStepParams & SP, const C
 // iterations of a level; 24 B per pixel, structure of arrays, slot = pass * kThreads + thread)
 __device__ __forceinline__ void stage_current_maps(const LevelArgs & L, const UnitIter & U, int passes, float * s_vn, int cap)
 {
+    // kStageBatch passes of a thread are requested together (6 loads each): the level start is a chain of L2 round trips,
+    // one per batch, and nothing else is live in the registers at this point
+    constexpr int kStageBatch = 5;
     const size_t plane = (size_t)L.rows * L.cols;
-    for(int p = 0; p < passes; p++)
+    for(int p0 = 0; p0 < passes; p0 += kStageBatch)
     {
-        const int u = U.unit(p);
-        if(u >= 0)
+        float v[kStageBatch][6];
+        int u[kStageBatch];
+#pragma unroll
+        for(int k = 0; k < kStageBatch; k++)
         {
-            float * q = s_vn + p * kThreads + threadIdx.x;
-            q[0] = L.vc[u]; q[cap] = L.vc[plane + u]; q[2 * cap] = L.vc[2 * plane + u];
-            q[3 * cap] = L.nc[u]; q[4 * cap] = L.nc[plane + u]; q[5 * cap] = L.nc[2 * plane + u];
+            u[k] = (p0 + k < passes) ? U.unit(p0 + k) : -1;
+            const int uu = u[k] >= 0 ? u[k] : 0;
+            v[k][0] = __ldg(L.vc + uu); v[k][1] = __ldg(L.vc + plane + uu); v[k][2] = __ldg(L.vc + 2 * plane + uu);
+            v[k][3] = __ldg(L.nc + uu); v[k][4] = __ldg(L.nc + plane + uu); v[k][5] = __ldg(L.nc + 2 * plane + uu);
         }
+#pragma unroll
+        for(int k = 0; k < kStageBatch; k++)
+            if(u[k] >= 0)
+            {
+                float * q = s_vn + (p0 + k) * kThreads + threadIdx.x;
+#pragma unroll
+                for(int c = 0; c < 6; c++) q[c * cap] = v[k][c];
+            }
     }
 }
 
@@ -1301,13 +1362,17 @@ __global__ void __launch_bounds__(kThreads, 1) k_track(const __grid_constant__ T
 
         // ---- workers, level start: candidate list of this CTA (overlaps the solve of the previous level) ----
         int n_cand = 0;
+        dbg_it = it_global;
+        if(!is_solver_cta) stamp(10);
         if(!is_solver_cta && A.rgb)
         {
             __syncthreads(); // every thread is done with the previous level's records
             n_cand = A.make_derivatives ? compact_candidates<true>(L, RP, U, passes, C, s_wtot) : compact_candidates<false>(L, RP, U, passes, C, s_wtot);
         }
+        if(!is_solver_cta) stamp(11);
 
         if(!is_solver_cta && A.icp && A.icp_in_smem) stage_current_maps(L, U, passes, s_vn, A.cand_cap); // read by the staging thread only
+        if(!is_solver_cta) stamp(12);
 
         float lastRGBError = FLT_MAX;      // every thread tracks it for the uniform rgb_only break (:464)
         bool first_of_level = true;
@@ -1598,7 +1663,7 @@ struct DeviceTrack
 {
     long long * dbg;      // device, max_grid * kMaxIters * kDbgStamps stamps (EF_TRACK_TIMING=1)
     double dbg_acc[kMaxIters][kDbgStamps];
-    double wrk_mean[kMaxIters][5], wrk_max[kMaxIters][5]; // worker phase durations, mean / max over the worker CTAs
+    double wrk_mean[kMaxIters][7], wrk_max[kMaxIters][7]; // worker phase durations, mean / max over the worker CTAs
     long long * dbg_host;
     int dbg_grid;
     long long dbg_n;
@@ -1715,8 +1780,10 @@ void EF_TRACK_FN(device_track_destroy)(ef_tracker * t)
                 const double n = (double)d->dbg_n;
                 const double * m = d->wrk_mean[it];
                 const double * x = d->wrk_max[it];
-                fprintf(stderr, "  it %2d: wait-params %6.0f/%6.0f  rgb-assoc %6.0f/%6.0f  icp %6.0f/%6.0f  wait-barB %6.0f/%6.0f  rgb-rows+publish %6.0f/%6.0f\n", it,
+                fprintf(stderr, "  it %2d: wait-params %6.0f/%6.0f  rgb-assoc %6.0f/%6.0f  icp %6.0f/%6.0f  wait-barB %6.0f/%6.0f  rgb-rows+publish %6.0f/%6.0f", it,
                         m[0] / n, x[0] / n, m[1] / n, x[1] / n, m[2] / n, x[2] / n, m[3] / n, x[3] / n, m[4] / n, x[4] / n);
+                if(m[5] > 0) fprintf(stderr, "  | level start: candidates %6.0f/%6.0f  staging %6.0f/%6.0f", m[5] / n, x[5] / n, m[6] / n, x[6] / n);
+                fprintf(stderr, "\n");
             }
         }
         cudaFree(d->dbg);
@@ -1867,8 +1934,8 @@ int EF_TRACK_FN(device_track_finish)(ef_tracker * t, float * trans, float * rot)
             for(int it = 0; it < kMaxIters; it++)
             {
                 for(int k = 0; k < kDbgStamps; k++) d->dbg_acc[it][k] += (double)h[it * kDbgStamps + k];
-                static const int from[5] = {0, 4, 5, 8, 6}, to[5] = {4, 5, 8, 6, 9};
-                for(int ph = 0; ph < 5; ph++)
+                static const int from[7] = {0, 4, 5, 8, 6, 10, 11}, to[7] = {4, 5, 8, 6, 9, 11, 12};
+                for(int ph = 0; ph < 7; ph++)
                 {
                     double sum = 0, mx = 0;
                     int cnt = 0;
