@@ -19,9 +19,9 @@
 //   reduce    transpose-reduce butterfly per warp (skipped by warps that had no pixel) -> per-CTA 58-float row ->
 //             published as flagged 16-byte chunks.
 //   solve     CTA 0 polls all rows with up to 12 independent loads in flight per thread, adds them in worker order
-//             (deterministic); its WARP 0 runs the reference's host step in double with the 27 normal-equation entries
-//             spread over the lanes (LDL^T, exp map, SE(3) update, pose composition), warp 1 derives the photometric warp
-//             K R K^-1, K t meanwhile; both publish their half of the parameter line as flagged chunks, 8 replicas.
+//             (deterministic); its WARP 0 runs the reference's host step in double (LDL^T, exp map, SE(3) update, pose
+//             composition), every lane the whole scalar routine on broadcast data -- no shuffles --, warp 1 derives the
+//             photometric warp K R K^-1, K t meanwhile; both publish their half of the parameter line as flagged chunks.
 //
 // No DataTerm image, no point cloud, no reduceSum launch, no host involvement until the final pose is
 // stored straight into pinned host memory.  Co-residency of the spinning CTAs is guaranteed by a
@@ -71,10 +71,6 @@ constexpr int kIcpBatch = EF_TRACK_ICP_BATCH; // pixels of one thread whose load
 #define EF_TRACK_ICP_SPLIT 0
 #endif
 constexpr bool kIcpSplit = EF_TRACK_ICP_SPLIT != 0;
-#ifndef EF_TRACK_SCALAR_SOLVER
-#define EF_TRACK_SCALAR_SOLVER 1
-#endif
-constexpr bool kScalarSolver = EF_TRACK_SCALAR_SOLVER != 0; // the host step of CTA 0: every lane scalar (1) or spread over the lanes (0)
 constexpr int kWarps = kThreads / 32;
 constexpr int kMaxIters = 32;    // SE3 iterations per call (19 in the reference schedule)
 constexpr int kDbgStamps = 13; // 0..9 per iteration; 10..12 level start (first iteration of a level only)
@@ -273,8 +269,7 @@ __device__ __forceinline__ Mat33 mat_from(const float * m)
 }
 
 // ------------------------------------------------------------------------------------------------
-// solver state: shared memory of CTA 0, touched by its thread 0 only (kept out of registers so that the
-// double-precision host step does not inflate the register needs of the per-pixel phases)
+// solver state: shared memory of CTA 0, read by the lanes of its warps 0 and 1 (broadcast) and written by lane 0
 // ------------------------------------------------------------------------------------------------
 struct Solver
 {
@@ -302,166 +297,17 @@ __device__ __forceinline__ double fast_rcp(double d)
 // warps 0 and 1 of CTA 0: hand-over of resultRt from the solver warp to the warp that derives the photometric warp
 __device__ __forceinline__ void solver_pair_sync() { asm volatile("bar.sync 1, 64;" ::: "memory"); }
 
-__device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(kFullMask, v, src); }
-__device__ __forceinline__ float shfl_f(float v, int src) { return __shfl_sync(kFullMask, v, src); }
 
-// RGBDOdometry.cpp:515-516, :541-583 -- the reference's host step after a Gauss-Newton evaluation, run by WARP 0 of
-// CTA 0 with the data spread over the lanes: the 27 entries of the combined normal equations live one per lane, so the
-// right-looking LDL^T, the exponential map, the SE(3) update and the pose composition are a few shuffles and ONE
-// double-precision operation per lane and step -- no arrays, no local memory, ~30 registers.  All in double like the
-// reference.  s_final (shared memory): ICP accumulator [0, 29) followed by the RGB accumulator [29, 58).
+// RGBDOdometry.cpp:515-516, :541-583 -- the reference's host step after a Gauss-Newton evaluation, run by WARP 0 of CTA 0
+// with NO lane parallelism: every lane runs the scalar routine on identical data (shared-memory broadcast loads), the 27
+// normal-equation entries in registers.  A double shuffle costs 26 cycles and a DFMA 8 (tools/op_latency), so a version that
+// spreads the entries over the lanes spends most of each LDL^T pivot moving operands (measured: 196 cycles per pivot, 3 200 per
+// solve); here a pivot is reciprocal -> multiply -> fused multiply-add (~80 cycles), its ~15 trailing updates are independent
+// DFMAs, and a warp-wide DFMA issues as fast as a one-lane one (1 870 cycles per solve).  No shuffles and no lane-dependent
+// branches: nvcc does not re-converge `if(lane < n)` regions here and every later warp-collective would take the
+// WARPSYNC.COLLECTIVE slow path (~150 cycles each, measured).  All in double like the reference.
+// s_final (shared memory): ICP accumulator [0, 29) followed by the RGB accumulator [29, 58).
 __device__ __forceinline__ void warp_solve_se3(Solver * S, const float * s_final, int icp, int rgb, float icp_weight, int level,
-                                               bool hand_over, long long * dbg = nullptr)
-{
-    long long tk[5] = {0, 0, 0, 0, 0};
-    if(dbg) tk[0] = clock64();
-    const int lane = threadIdx.x & 31;
-    __syncwarp();
-    // accumulator slot `lane` = entry (r, c), r <= c <= 6, of [A | b] (types.cuh:101-152 order); rs = slot of (r, r)
-    const int r = (lane >= 7) + (lane >= 13) + (lane >= 18) + (lane >= 22) + (lane >= 25);
-    const int rs = r * 7 - (r * (r - 1)) / 2;
-    const int c = lane - rs + r;
-    const bool live = lane < 27;
-
-    // NOTE: no divergent branch may precede the last shuffle of this function -- nvcc does not re-converge the two
-    // sides of an `if(lane < n)` here and every later shuffle then takes the WARPSYNC.COLLECTIVE slow path (~150 cycles
-    // each, measured).  Lane-dependent values are therefore selected arithmetically and all stores come last.
-    const int sl = live ? lane : 0;
-    const double w = icp_weight;
-    const double s_icp = (double)s_final[sl], s_rgb = (double)s_final[29 + sl];
-    double a = (icp && rgb) ? ((c == 6) ? (s_rgb + w * s_icp) : (s_rgb + (w * w) * s_icp)) : (icp ? s_icp : s_rgb); // :547-553
-    a = live ? a : 0.0;
-    const double a_in = a;
-
-    // x = A^-1 b (:552-564): unpivoted LDL^T of the symmetric positive definite system (hm::ldlt_solve_spd6_acc is the
-    // scalar statement of the same steps).  Pivot j: every trailing entry (r, c), r > j, subtracts l(r) a(j, c) with
-    // l(r) = a(j, r) / d(j); the right-hand side column c = 6 rides along, row j itself is scaled to L(., j).
-    double myinv = 0.0;
-#pragma unroll
-    for(int j = 0; j < 6; j++)
-    {
-        const int pj = j * 7 - (j * (j - 1)) / 2;
-        const double dj = shfl_d(a, pj);
-        const double inv = fast_rcp(dj);
-        const bool trail = live && r > j;
-        const double ajr = shfl_d(a, trail ? pj + (r - j) : lane);
-        const double ajc = shfl_d(a, trail ? pj + (c - j) : lane);
-        if(trail) a -= (ajr * inv) * ajc;
-        const bool row_j = live && r == j;
-        a = (row_j && c > j && c < 6) ? a * inv : a;
-        myinv = row_j ? inv : myinv;
-    }
-    if(dbg) tk[1] = clock64();
-    // back substitution, column oriented: lane (r, 6) holds w(r); x(i) is final once rows > i were applied
-    double wv = (live && c == 6) ? a * myinv : 0.0;
-    double x[6];
-#pragma unroll
-    for(int i = 5; i >= 0; i--)
-    {
-        const int pi6 = i * 7 - (i * (i - 1)) / 2 + (6 - i);
-        const double xi = shfl_d(wv, pi6);
-        x[i] = xi;
-        const bool up = live && c == 6 && r < i;
-        const double lir = shfl_d(a, up ? rs + (i - r) : lane); // L(i, r) sits in slot (r, i)
-        if(up) wv -= lir * xi;
-    }
-
-    if(dbg) tk[2] = clock64();
-    // OdometryProvider.h:35-71 rodrigues(x[3:6]) -- element e = (er, ec) of the rotation on lane e < 9
-    const int e = lane < 9 ? lane : 0;
-    const int er = e / 3, ec = e - er * 3;
-    double rx = x[3], ry = x[4], rz = x[5];
-    const double t2 = rx * rx + ry * ry + rz * rz;
-    const double eye = (er == ec) ? 1.0 : 0.0;
-    const double ra = (er == 0) ? rx : (er == 1) ? ry : rz;
-    const double rb = (ec == 0) ? rx : (ec == 1) ? ry : rz;
-    // r_x = [0 -rz ry; rz 0 -rx; -ry rx 0]
-    double sk = 0.0;
-    sk = (e == 1) ? -rz : sk; sk = (e == 2) ? ry : sk; sk = (e == 3) ? rz : sk;
-    sk = (e == 5) ? -rx : sk; sk = (e == 6) ? -ry : sk; sk = (e == 7) ? rx : sk;
-    double Re = eye;
-    if(t2 < 0.0625)
-    {
-        // R = cos(t) I + (1 - cos t) r^ r^T + sin(t) [r^]x  with r^ = r / t  (:52-68)
-        //   = (1 - B t^2) I + B r r^T + A [r]x,  A = sin(t)/t, B = (1 - cos t)/t^2: two short alternating series in t^2
-        // (|t| < 0.25 rad: 9 terms reach 2^-60), no square root, no division, no argument reduction -- a Gauss-Newton
-        // update of a tracked frame is a few milliradians.  Equal to the closed form to double rounding; t -> 0 gives the
-        // identity, which is also what the reference returns below DBL_EPSILON (:45).
-        double A = 1.0 / 121645100408832000.0, B = 1.0 / 2432902008176640000.0; // 1/19!, 1/20!
-        A = fma(-t2, A, 1.0 / 355687428096000.0);    B = fma(-t2, B, 1.0 / 6402373705728000.0);  // 1/17!, 1/18!
-        A = fma(-t2, A, 1.0 / 1307674368000.0);      B = fma(-t2, B, 1.0 / 20922789888000.0);    // 1/15!, 1/16!
-        A = fma(-t2, A, 1.0 / 6227020800.0);         B = fma(-t2, B, 1.0 / 87178291200.0);       // 1/13!, 1/14!
-        A = fma(-t2, A, 1.0 / 39916800.0);           B = fma(-t2, B, 1.0 / 479001600.0);         // 1/11!, 1/12!
-        A = fma(-t2, A, 1.0 / 362880.0);             B = fma(-t2, B, 1.0 / 3628800.0);           // 1/9!,  1/10!
-        A = fma(-t2, A, 1.0 / 5040.0);               B = fma(-t2, B, 1.0 / 40320.0);             // 1/7!,  1/8!
-        A = fma(-t2, A, 1.0 / 120.0);                B = fma(-t2, B, 1.0 / 720.0);               // 1/5!,  1/6!
-        A = fma(-t2, A, 1.0 / 6.0);                  B = fma(-t2, B, 1.0 / 24.0);                // 1/3!,  1/4!
-        A = fma(-t2, A, 1.0);                        B = fma(-t2, B, 0.5);                       // 1/1!,  1/2!
-        Re = fma(-B, t2, 1.0) * eye + B * (ra * rb) + A * sk;
-    }
-    else
-    {
-        const double theta = sqrt(t2);
-        double sn, cs;
-        sincos(theta, &sn, &cs);
-        const double c1 = 1. - cs;
-        const double itheta = 1. / theta;
-        Re = cs * eye + c1 * ((ra * itheta) * (rb * itheta)) + sn * (sk * itheta);
-    }
-
-    if(dbg) tk[3] = clock64();
-    // OdometryProvider.h:73-93: resultRt = [R | x[0:3]] * resultRt; entry (r4, c4) of the 3x4 block on lane l < 12
-    const int l = lane < 12 ? lane : 0;
-    const int r4 = l >> 2, c4 = l & 3;
-    const double rt = S->resultRt[r4 * 4 + c4];
-    double N = shfl_d(Re, r4 * 3 + 0) * shfl_d(rt, 0 * 4 + c4);
-    N = fma(shfl_d(Re, r4 * 3 + 1), shfl_d(rt, 1 * 4 + c4), N);
-    N = fma(shfl_d(Re, r4 * 3 + 2), shfl_d(rt, 2 * 4 + c4), N);
-    N += (c4 == 3) ? ((r4 == 0) ? x[0] : (r4 == 1) ? x[1] : x[2]) : 0.0;
-    // resultRt is complete: store it (every lane stores -- lanes >= 12 into scratch -- so the warp stays converged for the
-    // shuffles below) and let warp 1 derive the photometric warp from it while this warp composes the pose
-    S->resultRt[lane] = N;
-    if(hand_over) solver_pair_sync();
-
-    // :571-583: [Rcurr | tcurr] = [Rprev | tprev] * (float(resultRt))^-1 with the Isometry3f inverse (R^T, -R^T t), float
-    const float orf = (float)N; // oR(i, k) on lane i * 4 + k, ot(i) on lane i * 4 + 3
-    const float ot0 = shfl_f(orf, 3), ot1 = shfl_f(orf, 7), ot2 = shfl_f(orf, 11);
-    const int k3 = lane < 3 ? lane : 0;
-    const float itk = -(shfl_f(orf, 0 + k3) * ot0 + shfl_f(orf, 4 + k3) * ot1 + shfl_f(orf, 8 + k3) * ot2); // it(k) on lane k < 3
-    const float q0 = shfl_f(orf, ec * 4 + 0), q1 = shfl_f(orf, ec * 4 + 1), q2 = shfl_f(orf, ec * 4 + 2);  // iR(k, ec) = oR(ec, k)
-    const float Rc = S->Rprev[er * 3] * q0 + S->Rprev[er * 3 + 1] * q1 + S->Rprev[er * 3 + 2] * q2;
-    const float it0 = shfl_f(itk, 0), it1 = shfl_f(itk, 1), it2 = shfl_f(itk, 2);
-    const float tc = S->Rprev[k3 * 3] * it0 + S->Rprev[k3 * 3 + 1] * it1 + S->Rprev[k3 * 3 + 2] * it2 + S->tprev[k3];
-    if(dbg) tk[4] = clock64();
-    // ---- all shuffles done: stores ----
-    if(dbg && lane == 0)
-    {
-        dbg[8] = tk[1] - tk[0]; // combine + LDL^T
-        dbg[9] = tk[2] - tk[1]; // back substitution
-        dbg[5] = tk[3] - tk[2]; // exponential map
-        dbg[4] = tk[4] - tk[3]; // update + compose
-    }
-    if(live) S->last_S[lane] = a_in;
-    if(lane < 9) S->Rcurr[lane] = Rc;
-    if(lane < 3) S->tcurr[lane] = tc;
-    if(lane == 0)
-    {
-        S->se3_iterations[level]++;
-        if(icp)
-        {
-            S->last_icp_error = sqrtf(s_final[27]) / s_final[28]; // :515-516
-            S->last_icp_count = s_final[28];
-        }
-    }
-    __syncwarp();
-}
-
-// The same host step with NO lane parallelism: every lane of warp 0 runs the scalar routine on identical data (shared-memory
-// broadcast loads), the 27 normal-equation entries in registers.  A double shuffle costs 26 cycles and a DFMA 8 (tools/op_latency),
-// so the lane-spread version above spends most of each LDL^T pivot moving operands (196 cycles per pivot); here a pivot is
-// reciprocal -> multiply -> fused multiply-add (~80 cycles), its ~15 trailing updates are independent DFMAs, and a warp-wide
-// DFMA issues as fast as a one-lane one.  No shuffles and no lane-dependent branches, so nothing can take the WARPSYNC slow path.
-__device__ __forceinline__ void warp_solve_se3_scalar(Solver * S, const float * s_final, int icp, int rgb, float icp_weight, int level,
                                                       bool hand_over, long long * dbg = nullptr)
 {
     long long tk[5] = {0, 0, 0, 0, 0};
@@ -525,7 +371,11 @@ __device__ __forceinline__ void warp_solve_se3_scalar(Solver * S, const float * 
     double R[9];
     if(t2 < 0.0625)
     {
-        // two short alternating series in t^2 (see warp_solve_se3): R = (1 - B t^2) I + B r r^T + A [r]x
+        // R = cos(t) I + (1 - cos t) r^ r^T + sin(t) [r^]x  with r^ = r / t  (:52-68)
+        //   = (1 - B t^2) I + B r r^T + A [r]x,  A = sin(t)/t, B = (1 - cos t)/t^2: two short alternating series in t^2
+        // (|t| < 0.25 rad: 9 terms reach 2^-60), no square root, no division, no argument reduction -- a Gauss-Newton
+        // update of a tracked frame is a few milliradians.  Equal to the closed form to double rounding; t -> 0 gives the
+        // identity, which is also what the reference returns below DBL_EPSILON (:45).
         double A = 1.0 / 121645100408832000.0, B = 1.0 / 2432902008176640000.0; // 1/19!, 1/20!
         A = fma(-t2, A, 1.0 / 355687428096000.0);    B = fma(-t2, B, 1.0 / 6402373705728000.0);
         A = fma(-t2, A, 1.0 / 1307674368000.0);      B = fma(-t2, B, 1.0 / 20922789888000.0);
@@ -602,45 +452,10 @@ __device__ __forceinline__ void warp_make_pose(const Solver * S, float * payload
     if(lane < 12) payload[lane] = (lane < 9) ? S->Rcurr[lane] : S->tcurr[lane - 9];
 }
 
-// :424-434 -- photometric warp of the next SE3 iteration (warp 0 of CTA 0) -> payload[12, 24) in shared memory:
-// krkinv[9] kt[3] with Rt = resultRt^-1 (general affine inverse: adjugate / determinant),
-// krkinv = K R K^-1, kt = K t in double (hm::rgb_warp_params_sparse is the scalar statement)
+// :424-434 -- photometric warp of the next SE3 iteration (warp 1 of CTA 0) -> payload[12, 24) in shared memory:
+// krkinv[9] kt[3] with Rt = resultRt^-1 (general affine inverse: adjugate / determinant), krkinv = K R K^-1, kt = K t in
+// double (hm::rgb_warp_params_sparse is the scalar statement); every lane evaluates it (see warp_solve_se3)
 __device__ __forceinline__ void warp_make_rgb_params(const Solver * S, float * payload /*shared*/, float fxf, float fyf, float cxf, float cyf,
-                                                     const double * K_inv)
-{
-    const int lane = threadIdx.x & 31;
-    __syncwarp();
-    // no divergent branch before the last shuffle (see warp_solve_se3): stores come last
-    const double fx = fxf, fy = fyf, cx = cxf, cy = cyf;
-    const int l = lane < 12 ? lane : 0;
-    const double m = S->resultRt[(l >> 2) * 4 + (l & 3)]; // entry (i, k) of the 3x4 block on lane i * 4 + k
-    const int e = lane < 9 ? lane : 0;
-    const int er = e / 3, ec = e - er * 3;
-    // inverse33: entry e of adj(M) = m[a] m[b] - m[c] m[d], 3x3 indices per entry packed four bits each
-    const unsigned long long ta = 0x013205124ull, tb = 0x467386578ull, tc = 0x104023215ull, td = 0x376568487ull;
-    const int ia = (int)((ta >> (4 * e)) & 15), ib = (int)((tb >> (4 * e)) & 15), ic = (int)((tc >> (4 * e)) & 15), id_ = (int)((td >> (4 * e)) & 15);
-    const double ma = shfl_d(m, (ia / 3) * 4 + ia % 3), mb = shfl_d(m, (ib / 3) * 4 + ib % 3);
-    const double mc = shfl_d(m, (ic / 3) * 4 + ic % 3), md = shfl_d(m, (id_ / 3) * 4 + id_ % 3);
-    const double cof = ma * mb - mc * md;
-    const double det = shfl_d(m, 0) * shfl_d(cof, 0) + shfl_d(m, 1) * shfl_d(cof, 3) + shfl_d(m, 2) * shfl_d(cof, 6);
-    const double Ai = cof * (1.0 / det);                   // R of Rt = resultRt^-1, entry e
-    const double t0 = shfl_d(m, 3), t1 = shfl_d(m, 7), t2 = shfl_d(m, 11);
-    const int k3 = lane < 3 ? lane : 0;
-    const double tinv = -(shfl_d(Ai, k3 * 3) * t0 + shfl_d(Ai, k3 * 3 + 1) * t1 + shfl_d(Ai, k3 * 3 + 2) * t2); // t of Rt, entry k3
-    // K R (rows: fx R0 + cx R2 ; fy R1 + cy R2 ; R2), then (K R) K^-1 with the structural zeros of K^-1 dropped
-    const double A2 = shfl_d(Ai, 6 + ec);
-    const double KR = (er == 0) ? fma(cx, A2, fx * Ai) : (er == 1) ? fma(cy, A2, fy * Ai) : Ai;
-    const double kr0 = shfl_d(KR, er * 3), kr1 = shfl_d(KR, er * 3 + 1);
-    const double KRK = (ec == 0) ? KR * K_inv[0] : (ec == 1) ? KR * K_inv[4] : fma(KR, K_inv[8], fma(kr1, K_inv[5], kr0 * K_inv[2]));
-    const double tz = shfl_d(tinv, 2);
-    const double kt = (k3 == 0) ? fma(cx, tz, fx * tinv) : (k3 == 1) ? fma(cy, tz, fy * tinv) : tinv;
-    if(lane < 9) payload[12 + lane] = (float)KRK;
-    if(lane < 3) payload[21 + lane] = (float)kt;
-    __syncwarp();
-}
-
-// the same without lane parallelism (see warp_solve_se3_scalar): every lane evaluates hm::rgb_warp_params_sparse
-__device__ __forceinline__ void warp_make_rgb_params_scalar(const Solver * S, float * payload /*shared*/, float fxf, float fyf, float cxf, float cyf,
                                                             const double * K_inv)
 {
     const int lane = threadIdx.x & 31;
@@ -1330,12 +1145,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_track(const __grid_constant__ T
         stamp(2);
         if(warp == 0)
         {
-            if(kScalarSolver)
-                warp_solve_se3_scalar(S, s_final, A.icp, A.rgb, A.icp_weight, pending_level, hand_over,
-                                      (TIMING && dbg_it < kMaxIters) ? A.dbg + (size_t)dbg_it * kDbgStamps : nullptr);
-            else
-                warp_solve_se3(S, s_final, A.icp, A.rgb, A.icp_weight, pending_level, hand_over,
-                               (TIMING && dbg_it < kMaxIters) ? A.dbg + (size_t)dbg_it * kDbgStamps : nullptr);
+            warp_solve_se3(S, s_final, A.icp, A.rgb, A.icp_weight, pending_level, hand_over,
+                           (TIMING && dbg_it < kMaxIters) ? A.dbg + (size_t)dbg_it * kDbgStamps : nullptr);
         }
         stamp(3);
     };
@@ -1411,8 +1222,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_track(const __grid_constant__ T
                     // the photometric warp K R K^-1, K t of this iteration, in parallel with warp 0's pose composition
                     solver_pair_sync();
                     float * par = s_par[rel & 1u];
-                    if(kScalarSolver) warp_make_rgb_params_scalar(S, par, L.fx, L.fy, L.cx, L.cy, L.K_inv);
-                    else warp_make_rgb_params(S, par, L.fx, L.fy, L.cx, L.cy, L.K_inv);
+                    warp_make_rgb_params(S, par, L.fx, L.fy, L.cx, L.cy, L.K_inv);
                     warp_publish(A.par, par, 4, 4, rel);
                 }
                 stamp(1);
