@@ -596,6 +596,7 @@ struct CandStore
 // the window rows y-2 .. y+1, columns x-2 .. x+1, also hold the 3x3 stencil of the derivative: nine loads per pixel.
 struct CandLoads
 {
+    int x, y;              // the pixel (0, 0 for an empty slot)
     float d1;              // next depth
     unsigned lo[4], hi[4]; // window rows y-2 .. y+1
     unsigned gxy;          // !DERIV: dIdx | dIdy << 16
@@ -607,6 +608,8 @@ __device__ __forceinline__ void candidate_loads(const LevelArgs & L, int u, Cand
     const int cols = L.cols, rows = L.rows;
     const int uu = u < 0 ? 0 : u;
     const int y = uu / cols, x = uu - y * cols;
+    Q.x = x;
+    Q.y = y;
     if constexpr(!DERIV) Q.gxy = ((unsigned)(unsigned short)__ldg(L.dIdx + uu)) | ((unsigned)(unsigned short)__ldg(L.dIdy + uu) << 16);
     Q.d1 = __ldg(L.next_depth + uu);
     const int last = rows * cols - 8;
@@ -620,64 +623,63 @@ __device__ __forceinline__ void candidate_loads(const LevelArgs & L, int u, Cand
     }
 }
 
-// the gates of one pixel from its loads; returns whether it is a candidate and its packed words
+// The gates of one pixel from its loads; returns whether it is a candidate and its packed words.  Straight-line code
+// (selects, no branches) so that the pixels of a group interleave: with two warps per scheduler a dependent instruction
+// costs ~5 cycles and the level start is the length of this instruction stream.  Only pixels on the image border (and
+// column 1), where the reference's stencil shifts its taps, take a branch -- to the general statement.
 template<bool DERIV>
 __device__ __forceinline__ bool candidate_of(const LevelArgs & L, const RgbResParams & RP, int u, const CandLoads & Q, unsigned & w0, unsigned & w1,
                                              float & d1)
 {
-    const int cols = L.cols;
-    w0 = w1 = 0;
-    d1 = 0.f;
-    if(u < 0) return false;
-    const int y = u / cols, x = u - y * cols;
+    const int cols = L.cols, x = Q.x, y = Q.y;
     // bytes[r] = I(y + r - 2, x - 2 .. x + 1), cut out of the aligned run that holds them
     unsigned bytes[4];
 #pragma unroll
     for(int r = 0; r < 4; r++) bytes[r] = __funnelshift_r(Q.lo[r], Q.hi[r], 8u * (unsigned)(((y + r - 2) * cols + x - 2) & 3));
-    short gx, gy;
+    int gx, gy;
     if constexpr(DERIV)
     {
         // computeDerivativeImages (cudafuncs.cu:583-639) fused in: this CTA's pixels of dIdx / dIdy, kept in global
-        // memory as well because they are an output of the call (ef_tracker_download) and input of host-solve mode
-        if(x >= 2 && y >= 1 && x + 1 <= cols - 1 && y + 1 <= L.rows - 1 && (y + 1) * cols + x - 2 <= L.rows * cols - 8)
+        // memory as well because they are an output of the call (ef_tracker_download) and input of host-solve mode.
+        // The stencil of derivative_px (same taps, same order) from the window rows y-1, y, y+1, bytes 1 .. 3:
+        const float tl = (float)((bytes[1] >> 8) & 0xffu), tm = (float)((bytes[1] >> 16) & 0xffu), tr = (float)(bytes[1] >> 24);
+        const float ml = (float)((bytes[2] >> 8) & 0xffu), mr = (float)(bytes[2] >> 24);
+        const float bl = (float)((bytes[3] >> 8) & 0xffu), bm = (float)((bytes[3] >> 16) & 0xffu), br = (float)(bytes[3] >> 24);
+        float fx = 0, fy = 0;
+        fx = __fmaf_rn(tl, -0.52201f, fx); fx = __fmaf_rn(tr, 0.52201f, fx); fx = __fmaf_rn(ml, -0.79451f, fx);
+        fx = __fmaf_rn(mr, 0.79451f, fx);  fx = __fmaf_rn(bl, -0.52201f, fx); fx = __fmaf_rn(br, 0.52201f, fx);
+        fy = __fmaf_rn(tl, -0.52201f, fy); fy = __fmaf_rn(tm, -0.79451f, fy); fy = __fmaf_rn(tr, -0.52201f, fy);
+        fy = __fmaf_rn(bl, 0.52201f, fy);  fy = __fmaf_rn(bm, 0.79451f, fy);  fy = __fmaf_rn(br, 0.52201f, fy);
+        gx = (short)fx;
+        gy = (short)fy;
+        // valid where no tap left the image and the run of row y+1 was not clamped at the end of the image
+        const bool interior = x >= 2 && y >= 1 && x + 1 <= cols - 1 && y + 1 <= L.rows - 1 && (y + 1) * cols + x - 2 <= L.rows * cols - 8;
+        if(u >= 0 && !interior)
         {
-            // (the last condition: the run of row y+1 was not clamped at the end of the image)
-            // the stencil of derivative_px (same taps, same order) from the window rows y-1, y, y+1, bytes 1 .. 3
-            const float tl = (float)((bytes[1] >> 8) & 0xffu), tm = (float)((bytes[1] >> 16) & 0xffu), tr = (float)(bytes[1] >> 24);
-            const float ml = (float)((bytes[2] >> 8) & 0xffu), mr = (float)(bytes[2] >> 24);
-            const float bl = (float)((bytes[3] >> 8) & 0xffu), bm = (float)((bytes[3] >> 16) & 0xffu), br = (float)(bytes[3] >> 24);
-            float fx = 0, fy = 0;
-            fx = __fmaf_rn(tl, -0.52201f, fx); fx = __fmaf_rn(tr, 0.52201f, fx); fx = __fmaf_rn(ml, -0.79451f, fx);
-            fx = __fmaf_rn(mr, 0.79451f, fx);  fx = __fmaf_rn(bl, -0.52201f, fx); fx = __fmaf_rn(br, 0.52201f, fx);
-            fy = __fmaf_rn(tl, -0.52201f, fy); fy = __fmaf_rn(tm, -0.79451f, fy); fy = __fmaf_rn(tr, -0.52201f, fy);
-            fy = __fmaf_rn(bl, 0.52201f, fy);  fy = __fmaf_rn(bm, 0.79451f, fy);  fy = __fmaf_rn(br, 0.52201f, fy);
-            gx = fx;
-            gy = fy;
+            short sx, sy;
+            const uint8_t * img = L.next_image;
+            derivative_px([&](int j, int i) { return __ldg(img + (size_t)j * cols + i); }, L.rows, cols, x, y, sx, sy);
+            gx = sx;
+            gy = sy;
         }
-        else
+        if(u >= 0)
         {
-            const uint8_t * img = L.next_image; // image border (and column 1): the general statement, shifted taps included
-            derivative_px([&](int j, int i) { return __ldg(img + (size_t)j * cols + i); }, L.rows, cols, x, y, gx, gy);
+            L.dIdx[u] = (short)gx;
+            L.dIdy[u] = (short)gy;
         }
-        L.dIdx[u] = gx;
-        L.dIdy[u] = gy;
     }
     else
     {
         gx = (short)(Q.gxy & 0xffffu);
         gy = (short)(Q.gxy >> 16);
     }
-    // the 16-pixel border of RGBResidual (:779-783), the gradient and depth gates
-    bool keep = false;
-    if(rgb_gate(RP, x, y, gx, gy, Q.d1))
-    {
-        // 4x4 window [y-2, y+2) x [x-2, x+2) of the next image must be non-zero (:787-793)
-        const unsigned win = __vcmpne4(bytes[0], 0u) & __vcmpne4(bytes[1], 0u) & __vcmpne4(bytes[2], 0u) & __vcmpne4(bytes[3], 0u);
-        keep = (win == 0xffffffffu);
-        d1 = Q.d1;
-        w0 = (unsigned)x | ((unsigned)y << 12) | (((bytes[2] >> 16) & 0xffu) << 24); // I_next(x, y)
-        w1 = ((unsigned)gx & 0xffffu) | ((unsigned)gy << 16);
-    }
+    // the 16-pixel border of RGBResidual (:779-783), the gradient and depth gates, then the 4x4 window
+    // [y-2, y+2) x [x-2, x+2) of the next image, which must be non-zero (:787-793)
+    const unsigned win = __vcmpne4(bytes[0], 0u) & __vcmpne4(bytes[1], 0u) & __vcmpne4(bytes[2], 0u) & __vcmpne4(bytes[3], 0u);
+    const bool keep = u >= 0 && rgb_gate(RP, x, y, gx, gy, Q.d1) && win == 0xffffffffu;
+    d1 = Q.d1;
+    w0 = (unsigned)x | ((unsigned)y << 12) | (((bytes[2] >> 16) & 0xffu) << 24); // I_next(x, y)
+    w1 = ((unsigned)gx & 0xffffu) | ((unsigned)gy << 16);
     return keep;
 }
 
