@@ -250,9 +250,18 @@ class RGBDOdometry:
 
     def trackFrameToModel(self, vertices, normals, model_rgba, depth, rgba, depthCutoff, modelPose, rgbOnly, icpWeight, pyramid, fastOdom,
                           so3):
-        self.trackFrameToModelLaunch(vertices, normals, model_rgba, depth, rgba, depthCutoff, modelPose, rgbOnly, icpWeight, pyramid,
-                                     fastOdom, so3)
-        return self.finish()
+        # one FFI call (ef_track_frame_to_model = launch + finish)
+        self._frame_inputs(vertices, normals, model_rgba, depth, rgba, depthCutoff)
+        pose = np.ascontiguousarray(modelPose, dtype=np.float32)
+        if pose.size != 16:
+            raise ValueError("modelPose must be a 4x4 matrix")
+        rc = self._L.ef_track_frame_to_model(self._h, self._frame_ref, C.c_void_p(pose.ctypes.data), self._res_t, self._res_r, int(rgbOnly),
+                                             C.c_float(icpWeight), int(pyramid), int(fastOdom), int(so3), self._stats_ref)
+        if rc != 0:
+            self._check(rc, "ef_track_frame_to_model")
+        self._publish()
+        res = self._res.copy()
+        return res[:3], res[3:].reshape(3, 3)
 
     def getCovariance(self):
         cov = np.zeros(36)
