@@ -1363,14 +1363,15 @@ EF_API int ef_op_project_point_cloud(const float * depth, size_t dp, int rows, i
     EF_OP_RET(launch_project_points(depth, dp, rows, cols, fx / div, fy / div, cx / div, cy / div, cloud, cp, (cudaStream_t)st));
 }
 
-EF_API size_t ef_op_splat_scratch_bytes(int rows, int cols) { return (rows > 0 && cols > 0) ? (size_t)rows * cols * 8 : 0; }
+EF_API size_t ef_op_splat_scratch_bytes(int rows, int cols) { return (rows > 0 && cols > 0) ? (size_t)rows * cols * 24 : 0; } // keys + rays
 
 EF_API int ef_op_splat_predict(const float * surfels, size_t stride_bytes, int count, const float * t_inv, float cx, float cy, float fx, float fy,
                                int rows, int cols, float max_depth, float conf_threshold, int time, int max_time, int time_delta, void * keys,
                                uint8_t * image, float * vertex, float * normal, uint16_t * time_out, void * st)
 {
     if(count < 0 || (count > 0 && !surfels) || !t_inv || !keys || !vertex || !normal || rows <= 0 || cols <= 0) return EF_ERR_INVALID_ARGUMENT;
-    if(stride_bytes < 48 || (stride_bytes % 16) || (reinterpret_cast<uintptr_t>(surfels) % 16)) return EF_ERR_INVALID_ARGUMENT;
+    if(stride_bytes < 48 || (stride_bytes % 16) || (reinterpret_cast<uintptr_t>(surfels) % 16) || (reinterpret_cast<uintptr_t>(keys) % 16))
+        return EF_ERR_INVALID_ARGUMENT;
     if(ef_device_count() <= 0) return EF_ERR_NO_DEVICE;
     SplatArgs a;
     a.surfels = surfels; a.stride_bytes = stride_bytes; a.count = count;

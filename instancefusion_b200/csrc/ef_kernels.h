@@ -42,7 +42,7 @@ struct SplatArgs
     int rows, cols;
     float max_depth, conf_threshold;
     int time, max_time, time_delta;
-    void * keys; // rows * cols * 8 bytes
+    void * keys; // rows * cols * 24 bytes: depth keys, then the per-pixel viewing rays
     uint8_t * image;
     float * vertex, * normal;
     uint16_t * time_out;

@@ -6,6 +6,7 @@
 // the predicted maps are born in device memory next to the tracker, so a closed tracking loop needs no GL context and no
 // GL -> CUDA hand-over, and only the sensor frame (1.8 MB at 640x480) has to cross PCIe.
 //
+//   k_splat_prepare  one thread per pixel: empties the depth keys and evaluates the pixel's viewing ray once.
 //   k_splat_depth    one thread per surfel: the vertex stage (cull tests, projection, sprite size from the four projected
 //                    disc extremes), then every fragment of the sprite runs the ray / disc intersection of the fragment stage
 //                    and competes with a 64-bit atomicMin on {24-bit depth | surfel index}: GL_LESS with submission order as
@@ -113,11 +114,18 @@ struct Fragment
     unsigned depth; // 24-bit window depth
 };
 
-// combo_splat.frag:37-67 for the fragment centred on (px + 0.5, py + 0.5); false = discarded
-__device__ __forceinline__ bool fragment_stage(const SplatParams & P, const SurfelView & S, int px, int py, Fragment & F)
+// combo_splat.frag:39: the viewing ray through the fragment centred on (px + 0.5, py + 0.5).  It depends on the pixel only,
+// so k_splat_prepare evaluates it once per pixel and call (three IEEE divisions and a square root: ~100 instructions that
+// every one of the ~20 fragments of every surfel would otherwise repeat) and the fragment stage reads it back.
+__device__ __forceinline__ V3 pixel_ray(const SplatParams & P, int px, int py)
 {
     const float fxc = add((float)px, 0.5f), fyc = add((float)py, 0.5f);
-    const V3 l = normalize(V3{dvd(sub(fxc, P.cx), P.fx), dvd(sub(fyc, P.cy), P.fy), 1.f}); // :39
+    return normalize(V3{dvd(sub(fxc, P.cx), P.fx), dvd(sub(fyc, P.cy), P.fy), 1.f});
+}
+
+// combo_splat.frag:37-67 for the fragment with viewing ray l; false = discarded
+__device__ __forceinline__ bool fragment_stage(const SplatParams & P, const SurfelView & S, const V3 & l, Fragment & F)
+{
     const float k = dvd(dot(S.pos, S.nrm), dot(l, S.nrm));
     const V3 c{mul(k, l.x), mul(k, l.y), mul(k, l.z)};                                     // :41
     const V3 d{sub(c.x, S.pos.x), sub(c.y, S.pos.y), sub(c.z, S.pos.z)};
@@ -147,14 +155,18 @@ __device__ __forceinline__ void load_surfel(const float * __restrict__ surfels, 
     nr = __ldg(s + 2); // normal, radius
 }
 
-__global__ void __launch_bounds__(256) k_splat_clear(unsigned long long * __restrict__ keys, int n)
+__global__ void __launch_bounds__(256) k_splat_prepare(const SplatParams P, unsigned long long * __restrict__ keys, float4 * __restrict__ rays)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if(i < n) keys[i] = kEmptyKey;
+    if(i >= P.rows * P.cols) return;
+    keys[i] = kEmptyKey;
+    const int y = i / P.cols, x = i - y * P.cols;
+    const V3 l = pixel_ray(P, x, y);
+    rays[i] = make_float4(l.x, l.y, l.z, 0.f);
 }
 
 __global__ void __launch_bounds__(256) k_splat_depth(const float * __restrict__ surfels, size_t stride_floats, int count, const SplatParams P,
-                                                     unsigned long long * __restrict__ keys)
+                                                     unsigned long long * __restrict__ keys, const float4 * __restrict__ rays)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if(i >= count) return;
@@ -168,12 +180,14 @@ __global__ void __launch_bounds__(256) k_splat_depth(const float * __restrict__ 
         for(int x = x0; x < x1; x++)
         {
             Fragment F;
-            if(fragment_stage(P, S, x, y, F)) atomicMin(keys + (size_t)y * P.cols + x, ((unsigned long long)F.depth << 32) | (unsigned)i);
+            const float4 r = __ldg(rays + (size_t)y * P.cols + x);
+            if(fragment_stage(P, S, V3{r.x, r.y, r.z}, F)) atomicMin(keys + (size_t)y * P.cols + x, ((unsigned long long)F.depth << 32) | (unsigned)i);
         }
 }
 
 __global__ void __launch_bounds__(256) k_splat_resolve(const float * __restrict__ surfels, size_t stride_floats, const SplatParams P,
-                                                       const unsigned long long * __restrict__ keys, uchar4 * __restrict__ image,
+                                                       const unsigned long long * __restrict__ keys, const float4 * __restrict__ rays,
+                                                       uchar4 * __restrict__ image,
                                                        float4 * __restrict__ vertex, float4 * __restrict__ normal, uint16_t * __restrict__ time)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -189,7 +203,8 @@ __global__ void __launch_bounds__(256) k_splat_resolve(const float * __restrict_
         load_surfel(surfels, stride_floats, (int)(unsigned)key, pc, ct, nr);
         SurfelView S;
         Fragment F;
-        if(vertex_stage(P, pc, ct, nr, S) && fragment_stage(P, S, x, y, F))
+        const float4 r = __ldg(rays + i);
+        if(vertex_stage(P, pc, ct, nr, S) && fragment_stage(P, S, V3{r.x, r.y, r.z}, F))
         {
             const float fxc = add((float)x, 0.5f), fyc = add((float)y, 0.5f);
             const int rgb = (int)ct.x; // color.glsl decodeColor; the RGBA8 target stores the bytes back
@@ -275,9 +290,10 @@ cudaError_t launch_splat_predict(const SplatArgs & a, cudaStream_t s)
     const int n = a.rows * a.cols;
     unsigned long long * keys = static_cast<unsigned long long *>(a.keys);
     const size_t stride = a.stride_bytes / sizeof(float);
-    k_splat_clear<<<(n + 255) / 256, 256, 0, s>>>(keys, n);
-    if(a.count > 0) k_splat_depth<<<(a.count + 255) / 256, 256, 0, s>>>(a.surfels, stride, a.count, P, keys);
-    k_splat_resolve<<<(n + 255) / 256, 256, 0, s>>>(a.surfels, stride, P, keys, reinterpret_cast<uchar4 *>(a.image), reinterpret_cast<float4 *>(a.vertex),
+    float4 * rays = reinterpret_cast<float4 *>(keys + n); // scratch = keys (8 B / pixel) followed by the viewing rays (16 B / pixel)
+    k_splat_prepare<<<(n + 255) / 256, 256, 0, s>>>(P, keys, rays);
+    if(a.count > 0) k_splat_depth<<<(a.count + 255) / 256, 256, 0, s>>>(a.surfels, stride, a.count, P, keys, rays);
+    k_splat_resolve<<<(n + 255) / 256, 256, 0, s>>>(a.surfels, stride, P, keys, rays, reinterpret_cast<uchar4 *>(a.image), reinterpret_cast<float4 *>(a.vertex),
                                                     reinterpret_cast<float4 *>(a.normal), a.time_out);
     return cudaGetLastError();
 }
