@@ -1124,7 +1124,11 @@ EF_API int ef_track_frame_to_model_launch(ef_tracker * t, const ef_frame_inputs 
     if(!t || !in || !pose) return EF_ERR_INVALID_ARGUMENT;
     if(!in->vertices_rgba32f || !in->normals_rgba32f || !in->model_rgba8 || !in->depth || !in->rgba8) return EF_ERR_INVALID_ARGUMENT;
     int rc = EF_OK;
-    if(t->fused_build && (in->on_host ? t->frame_build == 2 : t->frame_build >= 1))
+    // (k_build_frame reads its inputs with 8- and 16-byte loads: device inputs that are not 16-byte aligned take the chained builders)
+    const bool aligned = in->on_host || (((reinterpret_cast<uintptr_t>(in->vertices_rgba32f) | reinterpret_cast<uintptr_t>(in->normals_rgba32f) |
+                                           reinterpret_cast<uintptr_t>(in->model_rgba8) | reinterpret_cast<uintptr_t>(in->depth) |
+                                           reinterpret_cast<uintptr_t>(in->rgba8)) & 15) == 0);
+    if(t->fused_build && aligned && (in->on_host ? t->frame_build == 2 : t->frame_build >= 1))
     {
         // k_build_frame (ef_build_fused.cu): all five inputs are known at once, so every pyramid of the frame comes from
         // one launch -- no chained kernels, no stream forks and joins; the tracker kernel follows on the same stream.

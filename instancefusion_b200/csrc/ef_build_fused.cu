@@ -348,6 +348,9 @@ constexpr int kDep1W = 2 * kT2W + 5, kDep1H = 2 * kT2H + 5;        // u16 depth:
 constexpr int kDep0W = 2 * kDep1W + 3, kDep0H = 2 * kDep1H + 3;    // u16 depth: level-0 footprint
 constexpr int kRgb1W = 2 * kT2W + 3, kRgb1H = 2 * kT2H + 3;        // Gaussian pyramids: level-1 footprint
 constexpr int kRgb0W = 2 * kRgb1W + 3, kRgb0H = 2 * kRgb1H + 3;    // Gaussian pyramids: level-0 footprint
+constexpr int kStageX = 8;                                         // the staged level-0 rows start kStageX pixels left of the tile ...
+constexpr int kStageW = 4 * kT2W + 16;                             // ... and are this wide: groups of four pixels, aligned loads
+static_assert(kStageX % 4 == 0 && kStageX >= 6 && kStageW % 4 == 0 && kStageW - kStageX >= 4 * kT2W + 7, "staged rows cover both footprints");
 constexpr int kBuildJobs = 6;
 
 struct FrameBuild
@@ -381,22 +384,22 @@ struct FrameBuild
 
 struct alignas(16) BuildSmem
 {
-    union
+    union alignas(16)
     {
         struct
         {
-            uint16_t d0[kDep0H][kDep0W + 1];
+            uint16_t d0[kDep0H][kStageW];
             uint16_t d1[kDep1H][kDep1W + 1];
             uint16_t d2[kT2H + 1][kT2W + 2];
         } dep;
         struct
         {
-            float z0[kRgb0H][kRgb0W];
+            float z0[kRgb0H][kStageW];
             float z1[kRgb1H][kRgb1W];
         } zp;
         struct
         {
-            uint8_t i0[kRgb0H][kRgb0W + 3];
+            uint8_t i0[kRgb0H][kStageW];
             uint8_t i1[kRgb1H][kRgb1W + 1];
         } im;
     };
@@ -484,31 +487,33 @@ __device__ __forceinline__ void depth_level0_tile(const FrameBuild & P, int tile
 __device__ __forceinline__ void depth_level12_tile(const FrameBuild & P, BuildSmem & S, int tile)
 {
     const TileGeom G(P, tile);
-    const int ox0 = G.ox0, oy0 = G.oy0, ox1 = G.ox1, oy1 = G.oy1;
-    // level 0 footprint; kStage loads of a thread are in flight together
-    constexpr int kStage = 7;
-    for(int i0 = threadIdx.x; i0 < kDep0W * kDep0H; i0 += kStage * 256)
+    const int oy0 = G.oy0, ox1 = G.ox1, oy1 = G.oy1;
+    // level 0 footprint, four pixels (one aligned 8-byte load) per item; the items of a thread are in flight together.
+    // Rows are staged from column x0_0 - kStageX (a multiple of 4; the frame's width is one too).
+    const int sx0 = G.x0_0 - kStageX;
+    constexpr int kItems = (kStageW / 4) * kDep0H, kPer = (kItems + 255) / 256;
     {
-        uint16_t d[kStage];
+        uint2 d[kPer];
 #pragma unroll
-        for(int k = 0; k < kStage; k++)
+        for(int k = 0; k < kPer; k++)
         {
-            const int i = i0 + k * 256;
-            const int ly = i / kDep0W, lx = i - ly * kDep0W;
-            const int gx = ox0 + lx, gy = oy0 + ly;
-            d[k] = 0;
-            if(i < kDep0W * kDep0H && gx >= 0 && gy >= 0 && gx < G.cols && gy < G.rows) d[k] = __ldg(P.depth + (size_t)gy * P.dpitch + gx);
+            const int i = threadIdx.x + k * 256;
+            const int ly = i / (kStageW / 4), lg = i - ly * (kStageW / 4);
+            const int gx = sx0 + 4 * lg, gy = oy0 + ly;
+            d[k] = make_uint2(0u, 0u);
+            if(i < kItems && gx >= 0 && gy >= 0 && gx < G.cols && gy < G.rows)
+                d[k] = __ldg(reinterpret_cast<const uint2 *>(P.depth + (size_t)gy * P.dpitch + gx));
         }
 #pragma unroll
-        for(int k = 0; k < kStage; k++)
+        for(int k = 0; k < kPer; k++)
         {
-            const int i = i0 + k * 256;
-            const int ly = i / kDep0W, lx = i - ly * kDep0W;
-            if(i < kDep0W * kDep0H) S.dep.d0[ly][lx] = d[k];
+            const int i = threadIdx.x + k * 256;
+            const int ly = i / (kStageW / 4), lg = i - ly * (kStageW / 4);
+            if(i < kItems) *reinterpret_cast<uint2 *>(&S.dep.d0[ly][4 * lg]) = d[k];
         }
     }
     __syncthreads();
-    auto at0 = [&](int r, int c) { return (int)S.dep.d0[r - oy0][c - ox0]; };
+    auto at0 = [&](int r, int c) { return (int)S.dep.d0[r - oy0][c - sx0]; };
     for(int i = threadIdx.x; i < kDep1W * kDep1H; i += 256)
     {
         const int ly = i / kDep1W, lx = i - ly * kDep1W;
@@ -549,62 +554,69 @@ template<bool DEPTH>
 __device__ __forceinline__ void gauss_pyramid_tile(const FrameBuild & P, BuildSmem & S, int job, int tile)
 {
     const TileGeom G(P, tile);
-    const int ox0 = G.ox0, oy0 = G.oy0, ox1 = G.ox1, oy1 = G.oy1;
+    const int oy0 = G.oy0, ox1 = G.ox1, oy1 = G.oy1;
     const uint8_t * rgba = P.rgba[job];
     const int pitch = P.rgba_pitch[job];
     uint8_t * const * img = P.img[job];
-    // level 0 of the footprint, converted once per CTA; owned pixels are stored.  kStage texels of a thread are requested
-    // together (the inputs of a frame come from HBM).
-    constexpr int kStage = 6;
-    for(int i0 = threadIdx.x; i0 < kRgb0W * kRgb0H; i0 += kStage * 256)
+    // level 0 of the footprint, converted once per CTA, four pixels per item (aligned 16-byte RGBA load, one packed
+    // 4-byte store); owned pixels are stored.  The items of a thread are requested together (the inputs of a frame come
+    // from HBM).  Rows are staged from column x0_0 - kStageX (a multiple of 4; the frame's width is one too).
+    const int sx0 = G.x0_0 - kStageX;
+    constexpr int kItems = (kStageW / 4) * kRgb0H, kPer = (kItems + 255) / 256;
     {
-        uchar4 px[kStage];
-        float zz[kStage];
+        uint4 px[DEPTH ? 1 : kPer];
+        float zz[DEPTH ? kPer : 1][4];
 #pragma unroll
-        for(int k = 0; k < kStage; k++)
+        for(int k = 0; k < kPer; k++)
         {
-            const int i = i0 + k * 256;
-            const int ly = i / kRgb0W, lx = i - ly * kRgb0W;
-            const int gx = ox0 + lx, gy = oy0 + ly;
-            px[k] = make_uchar4(0, 0, 0, 0);
-            zz[k] = 0.f;
-            if(i < kRgb0W * kRgb0H && gx >= 0 && gy >= 0 && gx < G.cols && gy < G.rows)
+            const int i = threadIdx.x + k * 256;
+            const int ly = i / (kStageW / 4), lg = i - ly * (kStageW / 4);
+            const int gx = sx0 + 4 * lg, gy = oy0 + ly;
+            const bool in = i < kItems && gx >= 0 && gy >= 0 && gx < G.cols && gy < G.rows;
+            if constexpr(DEPTH)
             {
-                if(DEPTH) zz[k] = __ldg(P.z + ((size_t)gy * G.cols + gx) * P.z_stride);
-                else px[k] = __ldg(reinterpret_cast<const uchar4 *>(rgba + (size_t)gy * pitch) + gx);
+#pragma unroll
+                for(int c = 0; c < 4; c++) zz[k][c] = in ? __ldg(P.z + ((size_t)gy * G.cols + gx + c) * P.z_stride) : 0.f;
             }
+            else
+                px[k] = in ? __ldg(reinterpret_cast<const uint4 *>(rgba + (size_t)gy * pitch) + (gx >> 2)) : make_uint4(0u, 0u, 0u, 0u);
         }
 #pragma unroll
-        for(int k = 0; k < kStage; k++)
+        for(int k = 0; k < kPer; k++)
         {
-            const int i = i0 + k * 256;
-            const int ly = i / kRgb0W, lx = i - ly * kRgb0W;
-            const int gx = ox0 + lx, gy = oy0 + ly;
-            if(i < kRgb0W * kRgb0H && gx >= 0 && gy >= 0 && gx < G.cols && gy < G.rows)
+            const int i = threadIdx.x + k * 256;
+            const int ly = i / (kStageW / 4), lg = i - ly * (kStageW / 4);
+            const int gx = sx0 + 4 * lg, gy = oy0 + ly;
+            if(i < kItems && gx >= 0 && gy >= 0 && gx < G.cols && gy < G.rows)
             {
-                const bool own = G.own0(gx, gy);
-                if(DEPTH)
+                const bool own = G.own0(gx, gy); // tiles and groups are both aligned to 4: a group is owned as a whole
+                if constexpr(DEPTH)
                 {
-                    const float d = depth_from_z(zz[k], P.cutoff_rgb);
-                    S.zp.z0[ly][lx] = d;
+                    const float4 d = make_float4(depth_from_z(zz[k][0], P.cutoff_rgb), depth_from_z(zz[k][1], P.cutoff_rgb),
+                                                 depth_from_z(zz[k][2], P.cutoff_rgb), depth_from_z(zz[k][3], P.cutoff_rgb));
+                    *reinterpret_cast<float4 *>(&S.zp.z0[ly][4 * lg]) = d;
                     if(own)
                     {
-                        P.dep_a[0][(size_t)gy * G.cols + gx] = d;
-                        P.dep_b[0][(size_t)gy * G.cols + gx] = d;
+                        *reinterpret_cast<float4 *>(P.dep_a[0] + (size_t)gy * G.cols + gx) = d;
+                        *reinterpret_cast<float4 *>(P.dep_b[0] + (size_t)gy * G.cols + gx) = d;
                     }
                 }
                 else
                 {
-                    const uint8_t v = intensity_px(px[k]);
-                    S.im.i0[ly][lx] = v;
-                    if(own) img[0][(size_t)gy * G.cols + gx] = v;
+                    const unsigned w[4] = {px[k].x, px[k].y, px[k].z, px[k].w};
+                    unsigned packed = 0;
+#pragma unroll
+                    for(int c = 0; c < 4; c++)
+                        packed |= (unsigned)intensity_px(make_uchar4(w[c] & 0xffu, (w[c] >> 8) & 0xffu, (w[c] >> 16) & 0xffu, w[c] >> 24)) << (8 * c);
+                    *reinterpret_cast<unsigned *>(&S.im.i0[ly][4 * lg]) = packed;
+                    if(own) *reinterpret_cast<unsigned *>(img[0] + (size_t)gy * G.cols + gx) = packed;
                 }
             }
         }
     }
     __syncthreads();
-    auto i0 = [&](int r, int c) { return S.im.i0[r - oy0][c - ox0]; };
-    auto z0 = [&](int r, int c) { return S.zp.z0[r - oy0][c - ox0]; };
+    auto i0 = [&](int r, int c) { return S.im.i0[r - oy0][c - sx0]; };
+    auto z0 = [&](int r, int c) { return S.zp.z0[r - oy0][c - sx0]; };
     for(int i = threadIdx.x; i < kRgb1W * kRgb1H; i += 256)
     {
         const int ly = i / kRgb1W, lx = i - ly * kRgb1W;
