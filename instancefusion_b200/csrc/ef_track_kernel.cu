@@ -137,7 +137,10 @@ struct TrackArgs
     float Rprev[9], tprev[3], Rprev_inv[9];
     float dist_thresh, angle_thresh, max_depth_delta, sobel_scale, icp_weight;
     int icp, rgb, rgb_only, so3;
-    int cand_cap;                                 // capacity of the shared-memory candidate list
+    int cand_cap;                                 // capacity of the shared-memory candidate list (largest level)
+    int lvl_cap[kNumPyrs];                        // pixels a worker CTA owns at each level (capacity of that level's lists)
+    int lvl_off[kNumPyrs];                        // byte offset of each level's lists in dynamic shared memory
+    int prework;                                  // all levels' lists fit side by side: finer levels are prepared during the waits of coarser ones
     int make_derivatives;                         // dIdx / dIdy are not valid yet: compute them at level start
     int icp_in_smem;                              // the CTA's current-frame vertices / normals fit shared memory beside the candidates
     float prev_icp_error, prev_icp_count, prev_so3_error, prev_so3_count, prev_rgb_error, prev_rgb_count;
@@ -687,56 +690,52 @@ __device__ __forceinline__ bool candidate_of(const LevelArgs & L, const RgbResPa
 // survivors compacted in (pass, warp, lane) order.  kCompactGroup passes are evaluated together (their loads overlap)
 // and share one CTA barrier.  Returns the candidate count (uniform over the CTA).
 template<bool DERIV>
-__device__ __forceinline__ int compact_candidates(const LevelArgs & L, const RgbResParams & RP, const UnitIter & U, int passes, const CandStore & C,
-                                                  int * s_wtot /*[2][kCompactGroup][kWarps]*/)
+__device__ __forceinline__ int compact_group(const LevelArgs & L, const RgbResParams & RP, const UnitIter & U, int passes, const CandStore & C,
+                                             int * s_wtot /*[2][kCompactGroup][kWarps]*/, int grp, int base)
 {
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    int base = 0;
-    for(int p0 = 0, grp = 0; p0 < passes; p0 += kCompactGroup, grp++)
+    const int p0 = grp * kCompactGroup;
+    unsigned w0[kCompactGroup], w1[kCompactGroup], ballot[kCompactGroup];
+    float d1[kCompactGroup];
+    bool keep[kCompactGroup];
+    int * wt = s_wtot + (grp & 1) * kCompactGroup * kWarps;
+    CandLoads Q[kCompactGroup];
+    int un[kCompactGroup];
+#pragma unroll
+    for(int g = 0; g < kCompactGroup; g++)
     {
-        unsigned w0[kCompactGroup], w1[kCompactGroup], ballot[kCompactGroup];
-        float d1[kCompactGroup];
-        bool keep[kCompactGroup];
-        int * wt = s_wtot + (grp & 1) * kCompactGroup * kWarps;
-        CandLoads Q[kCompactGroup];
-        int un[kCompactGroup];
+        un[g] = (p0 + g < passes) ? U.unit(p0 + g) : -1;
+        candidate_loads<DERIV>(L, un[g], Q[g]);
+    }
 #pragma unroll
-        for(int g = 0; g < kCompactGroup; g++)
-        {
-            un[g] = (p0 + g < passes) ? U.unit(p0 + g) : -1;
-            candidate_loads<DERIV>(L, un[g], Q[g]);
-        }
+    for(int g = 0; g < kCompactGroup; g++) keep[g] = candidate_of<DERIV>(L, RP, un[g], Q[g], w0[g], w1[g], d1[g]);
 #pragma unroll
-        for(int g = 0; g < kCompactGroup; g++) keep[g] = candidate_of<DERIV>(L, RP, un[g], Q[g], w0[g], w1[g], d1[g]);
-#pragma unroll
-        for(int g = 0; g < kCompactGroup; g++)
-        {
-            ballot[g] = __ballot_sync(kFullMask, keep[g]);
-            if(lane == 0) wt[g * kWarps + warp] = __popc(ballot[g]);
-        }
-        __syncthreads();
-#pragma unroll
-        for(int g = 0; g < kCompactGroup; g++)
-        {
-            int woff = 0, tot = 0;
-#pragma unroll
-            for(int w = 0; w < kWarps; w++)
-            {
-                const int v = wt[g * kWarps + w];
-                tot += v;
-                woff += (w < (int)warp) ? v : 0;
-            }
-            if(keep[g])
-            {
-                const int pos = base + woff + __popc(ballot[g] & ((1u << lane) - 1u));
-                C.c0[pos] = w0[g];
-                C.c1[pos] = w1[g];
-                C.c2[pos] = d1[g];
-            }
-            base += tot;
-        }
+    for(int g = 0; g < kCompactGroup; g++)
+    {
+        ballot[g] = __ballot_sync(kFullMask, keep[g]);
+        if(lane == 0) wt[g * kWarps + warp] = __popc(ballot[g]);
     }
     __syncthreads();
+#pragma unroll
+    for(int g = 0; g < kCompactGroup; g++)
+    {
+        int woff = 0, tot = 0;
+#pragma unroll
+        for(int w = 0; w < kWarps; w++)
+        {
+            const int v = wt[g * kWarps + w];
+            tot += v;
+            woff += (w < (int)warp) ? v : 0;
+        }
+        if(keep[g])
+        {
+            const int pos = base + woff + __popc(ballot[g] & ((1u << lane) - 1u));
+            C.c0[pos] = w0[g];
+            C.c1[pos] = w1[g];
+            C.c2[pos] = d1[g];
+        }
+        base += tot;
+    }
     return base;
 }
 
@@ -846,33 +845,29 @@ __device__ __forceinline__ bool rgb_rows_cands(const RgbStepParams & SP, const C
 
 // Level start: the current-frame vertex / normal of this CTA's pixels -> shared memory (they do not change over the
 // iterations of a level; 24 B per pixel, structure of arrays, slot = pass * kThreads + thread)
-__device__ __forceinline__ void stage_current_maps(const LevelArgs & L, const UnitIter & U, int passes, float * s_vn, int cap)
+constexpr int kStageBatch = 5; // passes of a thread whose six loads each are requested together when the current maps are staged
+__device__ __forceinline__ void stage_batch(const LevelArgs & L, const UnitIter & U, int passes, float * s_vn, int cap, int p0)
 {
-    // kStageBatch passes of a thread are requested together (6 loads each): the level start is a chain of L2 round trips,
-    // one per batch, and nothing else is live in the registers at this point
-    constexpr int kStageBatch = 5;
+    // one batch = one L2 round trip; nothing else is live in the registers at this point
     const size_t plane = (size_t)L.rows * L.cols;
-    for(int p0 = 0; p0 < passes; p0 += kStageBatch)
+    float v[kStageBatch][6];
+    int u[kStageBatch];
+#pragma unroll
+    for(int k = 0; k < kStageBatch; k++)
     {
-        float v[kStageBatch][6];
-        int u[kStageBatch];
-#pragma unroll
-        for(int k = 0; k < kStageBatch; k++)
-        {
-            u[k] = (p0 + k < passes) ? U.unit(p0 + k) : -1;
-            const int uu = u[k] >= 0 ? u[k] : 0;
-            v[k][0] = __ldg(L.vc + uu); v[k][1] = __ldg(L.vc + plane + uu); v[k][2] = __ldg(L.vc + 2 * plane + uu);
-            v[k][3] = __ldg(L.nc + uu); v[k][4] = __ldg(L.nc + plane + uu); v[k][5] = __ldg(L.nc + 2 * plane + uu);
-        }
-#pragma unroll
-        for(int k = 0; k < kStageBatch; k++)
-            if(u[k] >= 0)
-            {
-                float * q = s_vn + (p0 + k) * kThreads + threadIdx.x;
-#pragma unroll
-                for(int c = 0; c < 6; c++) q[c * cap] = v[k][c];
-            }
+        u[k] = (p0 + k < passes) ? U.unit(p0 + k) : -1;
+        const int uu = u[k] >= 0 ? u[k] : 0;
+        v[k][0] = __ldg(L.vc + uu); v[k][1] = __ldg(L.vc + plane + uu); v[k][2] = __ldg(L.vc + 2 * plane + uu);
+        v[k][3] = __ldg(L.nc + uu); v[k][4] = __ldg(L.nc + plane + uu); v[k][5] = __ldg(L.nc + 2 * plane + uu);
     }
+#pragma unroll
+    for(int k = 0; k < kStageBatch; k++)
+        if(u[k] >= 0)
+        {
+            float * q = s_vn + (p0 + k) * kThreads + threadIdx.x;
+#pragma unroll
+            for(int c = 0; c < 6; c++) q[c * cap] = v[k][c];
+        }
 }
 
 // phase A2: ICPReduction (reduce.cu:285-347) for up to B of this thread's pixels (passes p0 .. p0 + B): all the
@@ -990,17 +985,19 @@ __global__ void __launch_bounds__(kThreads, 1) k_track(const __grid_constant__ T
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const int widx = is_solver_cta ? 0 : (int)blockIdx.x - 1;
     float * s_rows = reinterpret_cast<float *>(s_dyn);
-    CandStore C;
-    {
-        unsigned * base = reinterpret_cast<unsigned *>(s_dyn);
-        const int cap = A.cand_cap;
-        C.c0 = base;
-        C.c1 = base + cap;
-        C.c2 = reinterpret_cast<float *>(base + 2 * cap);
-        C.r0 = base + 3 * cap;
-        C.r1 = reinterpret_cast<float *>(base + 4 * cap);
-    }
-    float * s_vn = reinterpret_cast<float *>(s_dyn) + 5 * (size_t)A.cand_cap; // 6 planes of cand_cap floats (icp_in_smem)
+    // per level: five candidate arrays of lvl_cap entries, then (icp_in_smem) six planes of lvl_cap floats
+    auto cand_store = [&](int lv) {
+        CandStore c;
+        unsigned * base = reinterpret_cast<unsigned *>(reinterpret_cast<char *>(s_dyn) + A.lvl_off[lv]);
+        const int cap = A.lvl_cap[lv];
+        c.c0 = base;
+        c.c1 = base + cap;
+        c.c2 = reinterpret_cast<float *>(base + 2 * cap);
+        c.r0 = base + 3 * cap;
+        c.r1 = reinterpret_cast<float *>(base + 4 * cap);
+        return c;
+    };
+    auto vn_store = [&](int lv) { return reinterpret_cast<float *>(reinterpret_cast<char *>(s_dyn) + A.lvl_off[lv]) + 5 * (size_t)A.lvl_cap[lv]; };
     Solver * S = &s_solver;
 
     // epochs, tracked identically by every thread of the grid
@@ -1153,6 +1150,34 @@ __global__ void __launch_bounds__(kThreads, 1) k_track(const __grid_constant__ T
         stamp(3);
     };
 
+    // Level preparation in units (one compaction group or one staging batch each, ~5 000 cycles): a level's units run at its
+    // start at the latest, but when all levels' lists fit shared memory side by side (A.prework) the workers run them earlier,
+    // one per iteration of a coarser level, in the window where they would only wait for the next parameters.
+    int prep_unit[kNumPyrs] = {0, 0, 0}, prep_cand[kNumPyrs] = {0, 0, 0};
+    auto prep_passes = [&](int lv) { return UnitIter{A.lvl[lv].rows * A.lvl[lv].cols, W, widx, (int)lane, (int)warp}.passes(); };
+    auto prep_groups = [&](int lv) { return A.rgb ? (prep_passes(lv) + kCompactGroup - 1) / kCompactGroup : 0; };
+    auto prep_units = [&](int lv) {
+        return prep_groups(lv) + ((A.icp && A.icp_in_smem) ? (prep_passes(lv) + kStageBatch - 1) / kStageBatch : 0);
+    };
+    auto prepare_unit = [&](int lv) { // all threads of a worker CTA
+        const LevelArgs & PL = A.lvl[lv];
+        const UnitIter PU{PL.rows * PL.cols, W, widx, (int)lane, (int)warp};
+        const int pp = PU.passes(), groups = prep_groups(lv), unit = prep_unit[lv]++;
+        if(unit < groups)
+        {
+            RgbResParams PR;
+            PR.min_scale = PL.min_scale;
+            PR.max_depth_delta = A.max_depth_delta;
+            PR.rows = PL.rows;
+            PR.cols = PL.cols;
+            const CandStore PC = cand_store(lv);
+            prep_cand[lv] = A.make_derivatives ? compact_group<true>(PL, PR, PU, pp, PC, s_wtot, unit, prep_cand[lv])
+                                               : compact_group<false>(PL, PR, PU, pp, PC, s_wtot, unit, prep_cand[lv]);
+        }
+        else
+            stage_batch(PL, PU, pp, vn_store(lv), A.lvl_cap[lv], (unit - groups) * kStageBatch);
+    };
+
     for(int lv = kNumPyrs - 1; lv >= 0; lv--)
     {
         const LevelArgs & L = A.lvl[lv];
@@ -1173,19 +1198,23 @@ __global__ void __launch_bounds__(kThreads, 1) k_track(const __grid_constant__ T
         UnitIter U{L.rows * L.cols, W, widx, (int)lane, (int)warp};
         const int passes = U.passes();
 
-        // ---- workers, level start: candidate list of this CTA (overlaps the solve of the previous level) ----
-        int n_cand = 0;
+        // ---- workers, level start: whatever is left of this level's preparation (candidate list, staged current maps) ----
+        const CandStore C = cand_store(lv);
+        float * const s_vn = vn_store(lv);
         dbg_it = it_global;
         if(!is_solver_cta) stamp(10);
-        if(!is_solver_cta && A.rgb)
+        if(!is_solver_cta)
         {
-            __syncthreads(); // every thread is done with the previous level's records
-            n_cand = A.make_derivatives ? compact_candidates<true>(L, RP, U, passes, C, s_wtot) : compact_candidates<false>(L, RP, U, passes, C, s_wtot);
+            if(!A.prework) __syncthreads(); // the levels share one region: every thread is done with the previous level's records
+            while(prep_unit[lv] < prep_units(lv)) prepare_unit(lv);
+            __syncthreads();
         }
         if(!is_solver_cta) stamp(11);
-
-        if(!is_solver_cta && A.icp && A.icp_in_smem) stage_current_maps(L, U, passes, s_vn, A.cand_cap); // read by the staging thread only
         if(!is_solver_cta) stamp(12);
+        const int n_cand = prep_cand[lv];
+        // the next finer level with iterations: prepared one unit per iteration while this level's workers wait for parameters
+        int next_lv = lv - 1;
+        while(next_lv >= 0 && A.lvl[next_lv].iterations <= 0) next_lv--;
 
         float lastRGBError = FLT_MAX;      // every thread tracks it for the uniform rgb_only break (:464)
         bool first_of_level = true;
@@ -1239,11 +1268,22 @@ __global__ void __launch_bounds__(kThreads, 1) k_track(const __grid_constant__ T
                     IP.tcurr = make_float3(par[9], par[10], par[11]);
                     stamp(4);
                     // ---- workers, phase A0: the first ICP pixels of every thread while CTA 0 computes the warp ----
-                    anyI |= A.icp_in_smem ? icp_passes<true>(L, IP, U, 0, split, accI, s_vn, A.cand_cap) : icp_passes<false>(L, IP, U, 0, split, accI, s_vn, A.cand_cap);
+                    anyI |= A.icp_in_smem ? icp_passes<true>(L, IP, U, 0, split, accI, s_vn, A.lvl_cap[lv]) : icp_passes<false>(L, IP, U, 0, split, accI, s_vn, A.lvl_cap[lv]);
                     wait_chunks(my_par, 4, 4, rel, par);
                 }
                 else
                 {
+                    // a unit of the next level's preparation in the window where this CTA would only wait (not before the first
+                    // iteration of a level: its parameters are already there)
+                    if(A.prework && j > 0)
+                    {
+                        while(next_lv >= 0 && prep_unit[next_lv] >= prep_units(next_lv))
+                        {
+                            next_lv--;
+                            while(next_lv >= 0 && A.lvl[next_lv].iterations <= 0) next_lv--;
+                        }
+                        if(next_lv >= 0) prepare_unit(next_lv);
+                    }
                     wait_chunks(my_par, A.icp ? 0 : 4, (A.icp && A.rgb) ? 8 : 4, rel, par);
                     IP.Rcurr = mat_from(par);
                     IP.tcurr = make_float3(par[9], par[10], par[11]);
@@ -1282,8 +1322,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_track(const __grid_constant__ T
                 float vi = 0.f;
                 if(A.icp)
                 {
-                    anyI |= A.icp_in_smem ? icp_passes<true>(L, IP, U, split, passes, accI, s_vn, A.cand_cap)
-                                          : icp_passes<false>(L, IP, U, split, passes, accI, s_vn, A.cand_cap);
+                    anyI |= A.icp_in_smem ? icp_passes<true>(L, IP, U, split, passes, accI, s_vn, A.lvl_cap[lv])
+                                          : icp_passes<false>(L, IP, U, split, passes, accI, s_vn, A.lvl_cap[lv]);
                     if(__any_sync(kFullMask, anyI)) vi = warp_transpose_reduce32(accI); // a warp without pixels contributes zeros
                 }
                 if(lane < 29) s_red[warp * 64 + lane] = vi;
@@ -1483,7 +1523,8 @@ struct DeviceTrack
     uint4 * rows;
     TrackOutput * out; // pinned
     int grid;
-    int cand_cap, icp_in_smem;
+    int cand_cap, icp_in_smem, prework;
+    int lvl_cap[kNumPyrs], lvl_off[kNumPyrs];
     size_t smem_bytes;
     unsigned launch_seq;
 };
@@ -1512,6 +1553,26 @@ int EF_TRACK_FN(device_track_configure)(ef_tracker * t, int grid)
     size_t smem = (size_t)max_cand * kCandBytes;
     const bool icp_in_smem = (size_t)max_cand * (kCandBytes + kIcpBytes) <= (size_t)kMaxDynSmem;
     if(icp_in_smem) smem = (size_t)max_cand * (kCandBytes + kIcpBytes);
+    // the lists of the three levels side by side, if they fit: finer levels are then prepared while coarser ones iterate
+    const size_t per_px = kCandBytes + (icp_in_smem ? kIcpBytes : 0);
+    int lvl_cap[kNumPyrs], lvl_off[kNumPyrs];
+    size_t all = 0;
+    for(int i = 0; i < kNumPyrs; i++)
+    {
+        const int npix = t->dims[i].rows * t->dims[i].cols;
+        const int per_worker = ((npix + 31) / 32 + W - 1) / W;
+        lvl_cap[i] = per_worker * 32;
+        lvl_off[i] = (int)all;
+        all += ((size_t)lvl_cap[i] * per_px + 15) & ~(size_t)15;
+    }
+    const bool prework = all <= (size_t)kMaxDynSmem;
+    if(prework) smem = all;
+    else
+        for(int i = 0; i < kNumPyrs; i++)
+        {
+            lvl_cap[i] = max_cand; // one region, reused level after level
+            lvl_off[i] = 0;
+        }
     const size_t rows_smem = (size_t)W * kRowFloats * sizeof(float);
     if(rows_smem > smem) smem = rows_smem;
     if(smem > (size_t)kMaxDynSmem && d->grid > 0)
@@ -1521,6 +1582,12 @@ int EF_TRACK_FN(device_track_configure)(ef_tracker * t, int grid)
         return EF_ERR_UNSUPPORTED;
     }
     d->grid = grid;
+    d->prework = prework ? 1 : 0;
+    for(int i = 0; i < kNumPyrs; i++)
+    {
+        d->lvl_cap[i] = lvl_cap[i];
+        d->lvl_off[i] = lvl_off[i];
+    }
     d->cand_cap = max_cand;
     d->icp_in_smem = icp_in_smem ? 1 : 0;
     d->smem_bytes = smem;
@@ -1669,6 +1736,12 @@ int EF_TRACK_FN(device_track_launch)(ef_tracker * t, const float * trans, const 
     A.out = d->out; // UVA: pinned + mapped host memory is addressable from the device
     A.dbg = d->dbg;
     A.cand_cap = d->cand_cap;
+    A.prework = d->prework;
+    for(int i = 0; i < kNumPyrs; i++)
+    {
+        A.lvl_cap[i] = d->lvl_cap[i];
+        A.lvl_off[i] = d->lvl_off[i];
+    }
     A.make_derivatives = (A.rgb && !t->deriv_valid) ? 1 : 0;
     A.icp_in_smem = d->icp_in_smem;
 
