@@ -107,9 +107,24 @@ __device__ __forceinline__ bool grid_reduce_last_block(float block_total, float 
 
     // fixed order: warp w adds rows w, w+nwarps, ... ; then warp 0 adds the warps in index order
     const unsigned nwarps = (blockDim.x + 31u) >> 5;
+    // (kTailBatch rows of a lane are requested together and then added in the fixed order: the tail of the kernel is a chain
+    //  of L2 round trips, one per batch instead of one per row)
+    constexpr unsigned kTailBatch = 16;
     float s = 0.f;
     if(lane < SLOTS)
-        for(unsigned b = warp; b < gridDim.x; b += nwarps) s += __ldcg(partials + b * 32 + lane);
+        for(unsigned b0 = warp; b0 < gridDim.x; b0 += kTailBatch * nwarps)
+        {
+            float v[kTailBatch];
+#pragma unroll
+            for(unsigned k = 0; k < kTailBatch; k++)
+            {
+                const unsigned b = b0 + k * nwarps;
+                v[k] = b < gridDim.x ? __ldcg(partials + b * 32 + lane) : 0.f;
+            }
+#pragma unroll
+            for(unsigned k = 0; k < kTailBatch; k++)
+                if(b0 + k * nwarps < gridDim.x) s += v[k];
+        }
     __syncthreads(); // smem reuse
     if(lane < SLOTS) smem[warp * SLOTS + lane] = s;
     __syncthreads();
