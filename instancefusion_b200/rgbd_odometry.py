@@ -58,15 +58,8 @@ class RGBDOdometry:
             raise EFError(rc, "ef_tracker_create", "no CUDA device (no CPU fallback)" if rc == -2 else "")
         self._h = h
         self._stats = TrackStats()
-        # public fields of the reference class (RGBDOdometry.h:64-73)
-        self.lastICPError = 0.0
-        self.lastICPCount = float(width * height)
-        self.lastRGBError = 0.0
-        self.lastRGBCount = float(width * height)
-        self.lastSO3Error = 0.0
-        self.lastSO3Count = float(width * height)
-        self.so3_iterations = 0
-        self.se3_iterations = [0, 0, 0]
+        # initial values of the reference's public fields (RGBDOdometry.cpp:26-31)
+        self._stats.last_icp_count = self._stats.last_rgb_count = self._stats.last_so3_count = float(width * height)
         # result buffers of finish() and their addresses, made once (ctypes conversions are the bulk of a call's host time)
         self._res = np.zeros(12, np.float32)
         self._res_t, self._res_r = C.c_void_p(self._res.ctypes.data), C.c_void_p(self._res.ctypes.data + 12)
@@ -176,13 +169,16 @@ class RGBDOdometry:
     def initFirstRGB(self, rgb):
         self._rgb("ef_init_first_rgb", rgb)
 
-    def _publish(self):
-        s = self._stats
-        self.lastICPError, self.lastICPCount = s.last_icp_error, s.last_icp_count
-        self.lastRGBError, self.lastRGBCount = s.last_rgb_error, s.last_rgb_count
-        self.lastSO3Error, self.lastSO3Count = s.last_so3_error, s.last_so3_count
-        self.so3_iterations = s.so3_iterations
-        self.se3_iterations = list(s.se3_iterations)
+    # the public fields below read the stats block of the last call when they are asked for
+    # public fields of the reference class (RGBDOdometry.h:64-73)
+    lastICPError = property(lambda self: self._stats.last_icp_error)
+    lastICPCount = property(lambda self: self._stats.last_icp_count)
+    lastRGBError = property(lambda self: self._stats.last_rgb_error)
+    lastRGBCount = property(lambda self: self._stats.last_rgb_count)
+    lastSO3Error = property(lambda self: self._stats.last_so3_error)
+    lastSO3Count = property(lambda self: self._stats.last_so3_count)
+    so3_iterations = property(lambda self: self._stats.so3_iterations)
+    se3_iterations = property(lambda self: list(self._stats.se3_iterations))
 
     # lastA / lastb of the last call (RGBDOdometry.h:72-73), unpacked from the stats block when asked for
     @property
@@ -201,7 +197,6 @@ class RGBDOdometry:
                                                        C.c_int(int(rgbOnly)), C.c_float(icpWeight), C.c_int(int(pyramid)),
                                                        C.c_int(int(fastOdom)), C.c_int(int(so3)), C.byref(self._stats))
         self._check(rc, "ef_get_incremental_transformation")
-        self._publish()
         return tr, ro.reshape(3, 3)
 
     def launch(self, trans, rot, rgbOnly, icpWeight, pyramid, fastOdom, so3):
@@ -216,7 +211,6 @@ class RGBDOdometry:
         rc = self._L.ef_get_incremental_transformation_finish(self._h, self._res_t, self._res_r, self._stats_ref)
         if rc != 0:
             self._check(rc, "ef_get_incremental_transformation_finish")
-        self._publish()
         res = self._res.copy()
         return res[:3], res[3:].reshape(3, 3)
 
@@ -259,7 +253,6 @@ class RGBDOdometry:
                                              C.c_float(icpWeight), int(pyramid), int(fastOdom), int(so3), self._stats_ref)
         if rc != 0:
             self._check(rc, "ef_track_frame_to_model")
-        self._publish()
         res = self._res.copy()
         return res[:3], res[3:].reshape(3, 3)
 
