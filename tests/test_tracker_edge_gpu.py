@@ -244,6 +244,37 @@ def test_graph_replayed_iterations_do_not_change_a_bit(size):
         b.close()
 
 
+def test_unaligned_device_inputs_take_the_chained_builders():
+    """k_build_frame reads its inputs with 8- and 16-byte loads; device buffers that are not 16-byte aligned (a view into a
+    larger allocation) must still work -- through the chained builders -- and give the same bits"""
+    import torch
+    w, h = 320, 240
+    K, pose0, pose1, f0, f1 = util.frame_pair(w, h)
+    pose0f = pose0.astype(np.float32)
+    tr = ef.RGBDOdometry(w, h, K.cx, K.cy, K.fx, K.fy, solve_mode=RO.EF_SOLVE_DEVICE)
+    try:
+        args = (20.0, pose0f, False, 10.0, True, False, False)
+        g = {k: torch.from_numpy(np.ascontiguousarray(v)).cuda() for k, v in {"vmap": f0["vmap"], "nmap": f0["nmap"], "mrgba": f0["rgba"],
+                                                                             "depth": f1["depth"], "rgba": f1["rgba"]}.items()}
+
+        def shifted(t, nbytes):
+            raw = torch.empty(t.numel() * t.element_size() + 64, dtype=torch.uint8, device="cuda")
+            view = raw[nbytes:nbytes + t.numel() * t.element_size()].view(t.dtype).view(t.shape)
+            view.copy_(t)
+            assert view.data_ptr() % 16 == nbytes % 16
+            return view
+
+        before = tr.launch_count
+        ta, Ra = tr.trackFrameToModel(g["vmap"], g["nmap"], g["mrgba"], g["depth"], g["rgba"], *args)
+        assert tr.launch_count - before == 2
+        before = tr.launch_count
+        tb, Rb = tr.trackFrameToModel(g["vmap"], g["nmap"], g["mrgba"], shifted(g["depth"], 2), shifted(g["rgba"], 4), *args)
+        assert tr.launch_count - before > 2, "fell back to the chained builders"
+        assert np.array_equal(ta, tb) and np.array_equal(Ra, Rb)
+    finally:
+        tr.close()
+
+
 def test_many_calls_on_one_handle_are_stable():
     """launch-unique epochs: 200 consecutive launches on one handle, every one returns the same bits"""
     w, h = 320, 240
