@@ -111,14 +111,17 @@ struct LevelArgs
 // 128-bit load, so its three payload words and its flag are always observed together.  No fence, no separate
 // "ready" counter: whoever polls a chunk gets the data with the same load that tells it the data is there.
 // Flags are launch-unique epochs (launch_seq << 8 | n), so nothing has to be reset between launches.
-// Nobody polls a line together with more than ~20 other CTAs (148 CTAs spinning on one line serialise in its L2 slice):
+// Nobody polls a line together with more than ~5 other CTAs (148 CTAs spinning on one line serialise in its L2 slice):
 //   par      the parameter line (8 chunks), kReplicas copies 256 bytes apart; worker w reads copy w % kReplicas.
 //            Chunks 0..3 = pose (Rcurr, tcurr), published as soon as the solve is done; chunks 4..7 = photometric warp
 //            (K R K^-1, K t), published later -- the workers start their ICP pixels in between.
 //   bslot[w] worker w's barrier-B arrival {count, sum diff^2}, polled by thread w of CTA 0
 //   bres[w]  the barrier-B result for worker w {sigma, rgbError, count}, written by thread w of CTA 0
 //   rows     worker w's partial sums of a round at rows[w * chunks ..), polled by CTA 0
-constexpr int kReplicas = 8;
+#ifndef EF_TRACK_REPLICAS
+#define EF_TRACK_REPLICAS 32 // measured 4 .. 148: k_track 0.1710 ms with 8, 0.1695 with 16, 0.1681 with 32 / 64, 0.1735 with one line per CTA
+#endif
+constexpr int kReplicas = EF_TRACK_REPLICAS;
 constexpr int kReplicaStride = 16; // chunks
 // SE3 payload: Rcurr[9] tcurr[3] krkinv[9] kt[3];  SO3 payload: H[9] krlr[9] done
 
