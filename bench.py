@@ -256,6 +256,18 @@ def run_ours(args, rank, world, device):
         torch.cuda.synchronize()
         five_call = {"value": n5 / (time.perf_counter() - t5), "unit": "frames/s", "launches_per_frame": (tr.launch_count - l0) / n5,
                      "note": "the five calls of the reference's frameToModel sequence (RGBDOdometry API) instead of ef_track_frame_to_model"}
+        # ... and with EF_OPT_DEFER_BUILD: the init* calls record their arguments, one builder launch at getIncrementalTransformation
+        tr.set_option(RO.EF_OPT_DEFER_BUILD, 1)
+        for i in range(min(args.warmup, 10)):
+            step_five(i)
+        torch.cuda.synchronize()
+        l0 = tr.launch_count
+        t5 = time.perf_counter()
+        for i in range(n5):
+            step_five(args.warmup + i)
+        torch.cuda.synchronize()
+        five_call["deferred_build"] = {"value": n5 / (time.perf_counter() - t5), "launches_per_frame": (tr.launch_count - l0) / n5}
+        tr.set_option(RO.EF_OPT_DEFER_BUILD, 0)
 
     # ---- pipelined runs: `inflight` handles, each on its own share of the SMs (EF_OPT_GRID_CTAS), track
     #      consecutive frames concurrently (the open-loop protocol makes frames independent).  The solve of one

@@ -84,6 +84,12 @@ typedef struct ef_track_stats
                                     the inputs are device buffers, 2 (default) = also for host inputs (five copies, then the one
                                     launch) */
 
+#define EF_OPT_DEFER_BUILD 8     /* 0/1 (default 0): ef_init_icp_model / ef_init_rgb_model / ef_init_icp_depth / ef_init_rgb with DEVICE
+                                    pointers only record their arguments; the pyramids are built when they are first needed
+                                    (ef_get_incremental_transformation, ef_tracker_download, ...) -- all four together from ONE kernel
+                                    launch, like ef_track_frame_to_model.  The caller promises that the buffers stay valid and
+                                    unchanged until then (the reference borrows its textures only for the duration of an init call) */
+
 #define EF_SOLVE_HOST 0   /* one step kernel per operator call, 6x6 LDLT + pose update in double on the host,
                              exactly the reference's control flow (RGBDOdometry.cpp:405-585) */
 #define EF_SOLVE_DEVICE 1 /* one persistent cooperative kernel runs the SO(3) loop and all Gauss-Newton

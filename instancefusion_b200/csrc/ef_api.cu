@@ -54,6 +54,8 @@ int fail(ef_tracker * t, int code, const char * what)
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+int flush_deferred(ef_tracker * t); // EF_OPT_DEFER_BUILD: build what the recorded init* calls asked for
+
 struct ArenaPlan
 {
     size_t off = 0;
@@ -178,6 +180,8 @@ EF_API int ef_tracker_create(int width, int height, float cx, float cy, float fx
     t->grid_ctas = 0;
     t->aux_streams = 1;
     t->frame_build = 2;
+    t->defer_build = 0;
+    t->deferred.have = 0;
     for(int i = 0; i < kNumAux; i++)
     {
         t->aux[i] = nullptr;
@@ -348,6 +352,13 @@ EF_API int ef_tracker_set_option(ef_tracker * t, int key, int value)
         if(value < 0 || value > 2) return fail(t, EF_ERR_INVALID_ARGUMENT, "bad frame-build mode");
         t->frame_build = value;
         return EF_OK;
+    case EF_OPT_DEFER_BUILD:
+    {
+        const int rc = flush_deferred(t);
+        if(rc) return rc;
+        t->defer_build = value ? 1 : 0;
+        return EF_OK;
+    }
     case EF_OPT_GRID_CTAS:
         if(t->launch_pending) return fail(t, EF_ERR_BAD_STATE, "a launch is pending");
     {
@@ -379,6 +390,7 @@ EF_API int ef_tracker_get_option(ef_tracker * t, int key, int * value)
     case EF_OPT_GRID_CTAS: *value = t->grid_ctas; return EF_OK;
     case EF_OPT_AUX_STREAMS: *value = t->aux_streams; return EF_OK;
     case EF_OPT_FRAME_BUILD: *value = t->frame_build; return EF_OK;
+    case EF_OPT_DEFER_BUILD: *value = t->defer_build; return EF_OK;
     default: return EF_ERR_INVALID_ARGUMENT;
     }
 }
@@ -400,6 +412,10 @@ EF_API int ef_tracker_profile(ef_tracker * t, double * ms, long long * calls)
 EF_API int ef_tracker_synchronize(ef_tracker * t)
 {
     if(!t) return EF_ERR_INVALID_ARGUMENT;
+    {
+        const int rc_flush = flush_deferred(t);
+        if(rc_flush) return rc_flush;
+    }
     const int rc = join_streams(t);
     if(rc) return rc;
     EF_CUDA(t, cudaStreamSynchronize(t->stream));
@@ -473,6 +489,17 @@ static int init_icp_depth(ef_tracker * t, const uint16_t * d_depth, size_t pitch
 
 EF_API int ef_init_icp_depth(ef_tracker * t, const uint16_t * d_depth, size_t pitch_bytes, float depth_cutoff)
 {
+    if(t && d_depth && t->defer_build && (pitch_bytes == 0 || pitch_bytes == (size_t)t->width * 2))
+    {
+        t->deferred.depth = d_depth;
+        t->deferred.depth_cutoff = depth_cutoff;
+        t->deferred.have |= 4u;
+        return EF_OK;
+    }
+    {
+        const int rc = flush_deferred(t);
+        if(rc) return rc;
+    }
     return init_icp_depth(t, d_depth, pitch_bytes, depth_cutoff, 0.f);
 }
 
@@ -480,6 +507,10 @@ EF_API int ef_init_icp_depth(ef_tracker * t, const uint16_t * d_depth, size_t pi
 EF_API int ef_init_icp_depth_raw(ef_tracker * t, const uint16_t * d_raw_depth, size_t pitch_bytes, float max_depth_m, float depth_cutoff)
 {
     if(!(max_depth_m > 0.f)) return t ? fail(t, EF_ERR_INVALID_ARGUMENT, "max_depth_m must be positive") : EF_ERR_INVALID_ARGUMENT;
+    {
+        const int rc_flush = flush_deferred(t);
+        if(rc_flush) return rc_flush;
+    }
     return init_icp_depth(t, d_raw_depth, pitch_bytes, depth_cutoff, max_depth_m);
 }
 
@@ -515,6 +546,10 @@ EF_API int ef_init_icp_maps(ef_tracker * t, const float * d_v, const float * d_n
 {
     (void)depth_cutoff; // unused by the reference as well
     if(!t || !d_v || !d_n) return EF_ERR_INVALID_ARGUMENT;
+    {
+        const int rc_flush = flush_deferred(t);
+        if(rc_flush) return rc_flush;
+    }
     return build_maps(t, d_v, d_n, t->vmap_curr, t->nmap_curr, nullptr, nullptr);
 }
 
@@ -523,6 +558,14 @@ EF_API int ef_init_icp_model(ef_tracker * t, const float * d_v, const float * d_
 {
     (void)depth_cutoff;
     if(!t || !d_v || !d_n || !pose) return EF_ERR_INVALID_ARGUMENT;
+    if(t->defer_build)
+    {
+        t->deferred.v = d_v;
+        t->deferred.n = d_n;
+        memcpy(t->deferred.pose, pose, sizeof(t->deferred.pose));
+        t->deferred.have |= 1u;
+        return EF_OK;
+    }
     const float R[9] = {pose[0], pose[1], pose[2], pose[4], pose[5], pose[6], pose[8], pose[9], pose[10]};
     const float tv[3] = {pose[3], pose[7], pose[11]};
     return build_maps(t, d_v, d_n, t->vmap_g_prev, t->nmap_g_prev, R, tv);
@@ -551,6 +594,16 @@ static int populate_rgbd(ef_tracker * t, const uint8_t * d_rgba, size_t pitch, f
 EF_API int ef_init_rgb(ef_tracker * t, const uint8_t * d_rgba, size_t pitch)
 {
     if(!t || !d_rgba) return EF_ERR_INVALID_ARGUMENT;
+    if(t->defer_build && (pitch == 0 || pitch == (size_t)t->width * 4))
+    {
+        t->deferred.rgba = d_rgba;
+        t->deferred.have |= 8u;
+        return EF_OK;
+    }
+    {
+        const int rc = flush_deferred(t);
+        if(rc) return rc;
+    }
     t->deriv_valid = false;
     return populate_rgbd(t, d_rgba, pitch, t->next_depth, t->next_image, t->stream);
 }
@@ -558,6 +611,16 @@ EF_API int ef_init_rgb(ef_tracker * t, const uint8_t * d_rgba, size_t pitch)
 EF_API int ef_init_rgb_model(ef_tracker * t, const uint8_t * d_rgba, size_t pitch)
 {
     if(!t || !d_rgba) return EF_ERR_INVALID_ARGUMENT;
+    if(t->defer_build && (pitch == 0 || pitch == (size_t)t->width * 4))
+    {
+        t->deferred.model_rgba = d_rgba;
+        t->deferred.have |= 2u;
+        return EF_OK;
+    }
+    {
+        const int rc = flush_deferred(t);
+        if(rc) return rc;
+    }
     // reads tmp_z (already enqueued on the handle's stream), writes only the "last" pyramids: internal stream (aux 1)
     cudaStream_t s = t->fused_build ? fork_stream(t, 1) : t->stream;
     const int rc = populate_rgbd(t, d_rgba, pitch, t->last_depth, t->last_image, s);
@@ -1033,6 +1096,10 @@ EF_API int ef_get_incremental_transformation_launch(ef_tracker * t, const float 
 {
     if(!t || !trans || !rot) return EF_ERR_INVALID_ARGUMENT;
     if(t->launch_pending) return fail(t, EF_ERR_BAD_STATE, "a launch is already pending");
+    {
+        const int rc = flush_deferred(t);
+        if(rc) return rc;
+    }
     const bool icp = !rgb_only && icp_weight > 0, rgb = rgb_only || icp_weight < 100;
     if(!icp && !rgb) return fail(t, EF_ERR_INVALID_ARGUMENT, "neither ICP nor RGB selected"); // the reference asserts (:566-569)
     memcpy(t->pending.trans, trans, sizeof(t->pending.trans));
@@ -1109,6 +1176,77 @@ EF_API int ef_get_incremental_transformation(ef_tracker * t, float * trans, floa
     return ef_get_incremental_transformation_finish(t, trans, rot, stats);
 }
 
+// every pyramid of a frame-to-model frame from one launch (k_build_frame); device inputs, dense rows, 16-byte aligned
+static int build_frame(ef_tracker * t, const float * v4, const float * n4, const uint8_t * model_rgba, const uint16_t * depth, const uint8_t * rgba,
+                       const float * pose, float depth_cutoff)
+{
+    ef::FrameBuildArgs a;
+    a.rows = t->height;
+    a.cols = t->width;
+    a.v4 = v4;
+    a.n4 = n4;
+    a.model_rgba = model_rgba;
+    a.depth = depth;
+    a.rgba = rgba;
+    a.depth_pitch_bytes = 0;
+    const float R[9] = {pose[0], pose[1], pose[2], pose[4], pose[5], pose[6], pose[8], pose[9], pose[10]};
+    memcpy(a.R, R, sizeof(R));
+    a.t[0] = pose[3]; a.t[1] = pose[7]; a.t[2] = pose[11];
+    a.depth_cutoff = depth_cutoff;
+    a.rgb_depth_cutoff = t->max_depth_rgb;
+    a.tmp_z = t->tmp_z;
+    for(int i = 0; i < kNumPyrs; ++i)
+    {
+        level_intr(t, i, a.fx[i], a.fy[i], a.cx[i], a.cy[i]);
+        a.vmap_g_prev[i] = t->vmap_g_prev[i];
+        a.nmap_g_prev[i] = t->nmap_g_prev[i];
+        a.vmap_curr[i] = t->vmap_curr[i];
+        a.nmap_curr[i] = t->nmap_curr[i];
+        a.depth_pyr[i] = t->depth_tmp[i];
+        a.next_image[i] = t->next_image[i];
+        a.last_image[i] = t->last_image[i];
+        a.next_depth[i] = t->next_depth[i];
+        a.last_depth[i] = t->last_depth[i];
+    }
+    t->deriv_valid = false;
+    EF_LAUNCH(t, launch_build_frame(a, t->stream));
+    return EF_OK;
+}
+
+// EF_OPT_DEFER_BUILD: the init* calls only recorded their arguments; build now.  All four present (the frameToModel
+// sequence, ElasticFusion.cpp:343-368): one launch.  Otherwise the recorded calls run through their own builders in the
+// reference's order (initICP* before initRGB*).
+namespace
+{
+int flush_deferred(ef_tracker * t)
+{
+    if(!t || !t->deferred.have) return EF_OK;
+    const unsigned have = t->deferred.have;
+    t->deferred.have = 0;
+    const int defer = t->defer_build;
+    t->defer_build = 0; // the calls below must build
+    int rc = EF_OK;
+    const bool aligned = ((reinterpret_cast<uintptr_t>(t->deferred.v) | reinterpret_cast<uintptr_t>(t->deferred.n) |
+                           reinterpret_cast<uintptr_t>(t->deferred.model_rgba) | reinterpret_cast<uintptr_t>(t->deferred.depth) |
+                           reinterpret_cast<uintptr_t>(t->deferred.rgba)) & 15) == 0;
+    if(have == 15u && t->fused_build && aligned)
+    {
+        rc = join_streams(t);
+        if(!rc) rc = build_frame(t, t->deferred.v, t->deferred.n, t->deferred.model_rgba, t->deferred.depth, t->deferred.rgba, t->deferred.pose,
+                                 t->deferred.depth_cutoff);
+    }
+    else
+    {
+        if(!rc && (have & 1u)) rc = ef_init_icp_model(t, t->deferred.v, t->deferred.n, t->deferred.depth_cutoff, t->deferred.pose);
+        if(!rc && (have & 2u)) rc = ef_init_rgb_model(t, t->deferred.model_rgba, 0);
+        if(!rc && (have & 4u)) rc = ef_init_icp_depth(t, t->deferred.depth, 0, t->deferred.depth_cutoff);
+        if(!rc && (have & 8u)) rc = ef_init_rgb(t, t->deferred.rgba, 0);
+    }
+    t->defer_build = defer;
+    return rc;
+}
+} // namespace
+
 // ElasticFusion.cpp:343-368 in one call
 // Chain on an internal stream that starts at the fork point recorded in t->ev_fork (no new record: all chains of
 // one ef_track_frame_to_model call hang off the same point of the handle's stream)
@@ -1123,6 +1261,10 @@ EF_API int ef_track_frame_to_model_launch(ef_tracker * t, const ef_frame_inputs 
 {
     if(!t || !in || !pose) return EF_ERR_INVALID_ARGUMENT;
     if(!in->vertices_rgba32f || !in->normals_rgba32f || !in->model_rgba8 || !in->depth || !in->rgba8) return EF_ERR_INVALID_ARGUMENT;
+    {
+        const int rc_flush = flush_deferred(t);
+        if(rc_flush) return rc_flush;
+    }
     int rc = EF_OK;
     // (k_build_frame reads its inputs with 8- and 16-byte loads: device inputs that are not 16-byte aligned take the chained builders)
     const bool aligned = in->on_host || (((reinterpret_cast<uintptr_t>(in->vertices_rgba32f) | reinterpret_cast<uintptr_t>(in->normals_rgba32f) |
@@ -1134,50 +1276,23 @@ EF_API int ef_track_frame_to_model_launch(ef_tracker * t, const ef_frame_inputs 
         // one launch -- no chained kernels, no stream forks and joins; the tracker kernel follows on the same stream.
         rc = join_streams(t);
         if(rc) return rc;
-        ef::FrameBuildArgs a;
-        a.rows = t->height;
-        a.cols = t->width;
-        a.v4 = static_cast<const float *>(in->vertices_rgba32f);
-        a.n4 = static_cast<const float *>(in->normals_rgba32f);
-        a.model_rgba = static_cast<const uint8_t *>(in->model_rgba8);
-        a.depth = static_cast<const uint16_t *>(in->depth);
-        a.rgba = static_cast<const uint8_t *>(in->rgba8);
+        const float * v4 = static_cast<const float *>(in->vertices_rgba32f);
+        const float * n4 = static_cast<const float *>(in->normals_rgba32f);
+        const uint8_t * mrgba = static_cast<const uint8_t *>(in->model_rgba8);
+        const uint16_t * depth = static_cast<const uint16_t *>(in->depth);
+        const uint8_t * rgba = static_cast<const uint8_t *>(in->rgba8);
         if(in->on_host)
         {
             const size_t n = t->dims[0].n();
-            EF_CUDA(t, cudaMemcpyAsync(t->stage_v, a.v4, n * 16, cudaMemcpyHostToDevice, t->stream));
-            EF_CUDA(t, cudaMemcpyAsync(t->stage_n, a.n4, n * 16, cudaMemcpyHostToDevice, t->stream));
-            EF_CUDA(t, cudaMemcpyAsync(t->stage_rgba_model, a.model_rgba, n * 4, cudaMemcpyHostToDevice, t->stream));
-            EF_CUDA(t, cudaMemcpyAsync(t->stage_depth, a.depth, n * 2, cudaMemcpyHostToDevice, t->stream));
-            EF_CUDA(t, cudaMemcpyAsync(t->stage_rgba, a.rgba, n * 4, cudaMemcpyHostToDevice, t->stream));
-            a.v4 = t->stage_v;
-            a.n4 = t->stage_n;
-            a.model_rgba = t->stage_rgba_model;
-            a.depth = t->stage_depth;
-            a.rgba = t->stage_rgba;
+            EF_CUDA(t, cudaMemcpyAsync(t->stage_v, v4, n * 16, cudaMemcpyHostToDevice, t->stream));
+            EF_CUDA(t, cudaMemcpyAsync(t->stage_n, n4, n * 16, cudaMemcpyHostToDevice, t->stream));
+            EF_CUDA(t, cudaMemcpyAsync(t->stage_rgba_model, mrgba, n * 4, cudaMemcpyHostToDevice, t->stream));
+            EF_CUDA(t, cudaMemcpyAsync(t->stage_depth, depth, n * 2, cudaMemcpyHostToDevice, t->stream));
+            EF_CUDA(t, cudaMemcpyAsync(t->stage_rgba, rgba, n * 4, cudaMemcpyHostToDevice, t->stream));
+            v4 = t->stage_v; n4 = t->stage_n; mrgba = t->stage_rgba_model; depth = t->stage_depth; rgba = t->stage_rgba;
         }
-        a.depth_pitch_bytes = 0;
-        const float R[9] = {pose[0], pose[1], pose[2], pose[4], pose[5], pose[6], pose[8], pose[9], pose[10]};
-        memcpy(a.R, R, sizeof(R));
-        a.t[0] = pose[3]; a.t[1] = pose[7]; a.t[2] = pose[11];
-        a.depth_cutoff = in->depth_cutoff;
-        a.rgb_depth_cutoff = t->max_depth_rgb;
-        a.tmp_z = t->tmp_z;
-        for(int i = 0; i < kNumPyrs; ++i)
-        {
-            level_intr(t, i, a.fx[i], a.fy[i], a.cx[i], a.cy[i]);
-            a.vmap_g_prev[i] = t->vmap_g_prev[i];
-            a.nmap_g_prev[i] = t->nmap_g_prev[i];
-            a.vmap_curr[i] = t->vmap_curr[i];
-            a.nmap_curr[i] = t->nmap_curr[i];
-            a.depth_pyr[i] = t->depth_tmp[i];
-            a.next_image[i] = t->next_image[i];
-            a.last_image[i] = t->last_image[i];
-            a.next_depth[i] = t->next_depth[i];
-            a.last_depth[i] = t->last_depth[i];
-        }
-        t->deriv_valid = false;
-        EF_LAUNCH(t, launch_build_frame(a, t->stream));
+        rc = build_frame(t, v4, n4, mrgba, depth, rgba, pose, in->depth_cutoff);
+        if(rc) return rc;
     }
     else if(t->fused_build && t->aux_streams && !in->on_host)
     {
@@ -1269,6 +1384,10 @@ EF_API int ef_get_covariance(ef_tracker * t, double * cov)
 EF_API int ef_tracker_download(ef_tracker * t, const char * name, int level, void * dst, size_t bytes)
 {
     if(!t || !name || !dst || level < 0 || level >= kNumPyrs) return EF_ERR_INVALID_ARGUMENT;
+    {
+        const int rc_flush = flush_deferred(t);
+        if(rc_flush) return rc_flush;
+    }
     const size_t n = t->dims[level].n();
     const void * src = nullptr;
     size_t need = 0;

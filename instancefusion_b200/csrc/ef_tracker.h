@@ -43,6 +43,16 @@ struct ef_tracker
     int grid_ctas;   // EF_OPT_GRID_CTAS (0 = every SM)
     int aux_streams; // EF_OPT_AUX_STREAMS
     int frame_build; // EF_OPT_FRAME_BUILD
+    int defer_build; // EF_OPT_DEFER_BUILD
+    struct
+    {
+        unsigned have;            // 1 model maps | 2 model colour | 4 depth | 8 colour
+        const float * v, * n;
+        float pose[16];
+        const uint8_t * model_rgba, * rgba;
+        const uint16_t * depth;
+        float depth_cutoff;
+    } deferred;
 
     // internal fork/join streams for builders that are independent of each other (ef_api.cu: fork_stream / join_streams)
     cudaStream_t aux[3];            // 0: current-frame depth chain, 1: model RGB-D chain, 2: model maps (single-call entry)

@@ -244,6 +244,48 @@ def test_graph_replayed_iterations_do_not_change_a_bit(size):
         b.close()
 
 
+def test_deferred_build_through_the_reference_calls():
+    """EF_OPT_DEFER_BUILD: the four init* calls of the frameToModel sequence only record their (device) arguments, the pyramids come
+    from ONE launch when getIncrementalTransformation needs them -- same bits as building in every call; a partial sequence
+    (only the current frame changes) and a download in between flush what was recorded through the ordinary builders"""
+    import torch
+    w, h = 640, 480
+    K, pose0, pose1, f0, f1 = util.frame_pair(w, h)
+    p0 = pose0.astype(np.float32)
+    a = ef.RGBDOdometry(w, h, K.cx, K.cy, K.fx, K.fy, solve_mode=RO.EF_SOLVE_DEVICE)
+    b = ef.RGBDOdometry(w, h, K.cx, K.cy, K.fx, K.fy, solve_mode=RO.EF_SOLVE_DEVICE)
+    b.set_option(RO.EF_OPT_DEFER_BUILD, 1)
+    try:
+        dev = lambda f: {k: torch.from_numpy(np.ascontiguousarray(v)).cuda() for k, v in f.items() if isinstance(v, np.ndarray)}
+        g0, g1 = dev(f0), dev(f1)
+
+        def five(tr, gm, gc):
+            tr.initICPModel(gm["vmap"], gm["nmap"], 20.0, p0)
+            tr.initRGBModel(gm["rgba"])
+            tr.initICP(gc["depth"], 20.0)
+            tr.initRGB(gc["rgba"])
+            return tr.getIncrementalTransformation(p0[:3, 3], p0[:3, :3], **JOINT)
+
+        for rep in range(3):
+            gm, gc = (g0, g1) if rep % 2 == 0 else (g1, g0)
+            before = b.launch_count
+            ra, rb = five(a, gm, gc), five(b, gm, gc)
+            assert b.launch_count - before == 2, "one builder launch + the tracker kernel"
+            assert np.array_equal(ra[0], rb[0]) and np.array_equal(ra[1], rb[1]), rep
+        # partial sequence: only the current frame is replaced; then a download before the solve
+        for tr in (a, b):
+            tr.initICP(g0["depth"], 20.0)
+            tr.initRGB(g0["rgba"])
+        assert np.array_equal(a.buffer("next_image", 1), b.buffer("next_image", 1))
+        assert _same_maps(a.buffer("vmap_curr", 0), b.buffer("vmap_curr", 0))
+        ra = a.getIncrementalTransformation(p0[:3, 3], p0[:3, :3], **JOINT)
+        rb = b.getIncrementalTransformation(p0[:3, 3], p0[:3, :3], **JOINT)
+        assert np.array_equal(ra[0], rb[0]) and np.array_equal(ra[1], rb[1])
+    finally:
+        a.close()
+        b.close()
+
+
 def test_unaligned_device_inputs_take_the_chained_builders():
     """k_build_frame reads its inputs with 8- and 16-byte loads; device buffers that are not 16-byte aligned (a view into a
     larger allocation) must still work -- through the chained builders -- and give the same bits"""
