@@ -65,12 +65,14 @@ typedef struct ef_track_stats
 } ef_track_stats;
 
 /* ef_tracker_set_option keys */
-#define EF_OPT_SOLVE_MODE 1      /* EF_SOLVE_HOST (default) | EF_SOLVE_DEVICE */
+#define EF_OPT_SOLVE_MODE 1      /* EF_SOLVE_DEVICE (default wherever the image fits the persistent kernel, i.e. up to ~1920x1080 on a
+                                    B200) | EF_SOLVE_HOST (the fallback for larger images) */
 #define EF_OPT_USE_GRAPH 2       /* 0/1 (host-solve mode): the launches of one Gauss-Newton iteration (computeRgbResidual, rgbStep, icpStep,
                                     parameter upload, result copies) are captured once per pyramid level and replayed as ONE CUDA
                                     graph launch + ONE synchronisation per iteration; results identical to 0.  Device-solve mode
                                     needs no graph: its whole iteration loop is one kernel */
-#define EF_OPT_FUSED_BUILD 3     /* 0/1: fused pyramid builders (default 1) instead of one kernel per operator */
+#define EF_OPT_FUSED_BUILD 3     /* 0/1: fused pyramid builders (default 1 when both image sides are multiples of 4, which they need)
+                                    instead of one kernel per operator (any size) */
 #define EF_OPT_PROFILE 4         /* 0/1: bracket the solve of every getIncrementalTransformation with CUDA events */
 #define EF_OPT_GRID_CTAS 5       /* device mode: CTAs (= SMs) the persistent tracker kernel occupies; 0 = all.  Lets k handles
                                     track k independent sequences concurrently on disjoint SMs of one GPU */
@@ -95,8 +97,13 @@ typedef struct ef_track_stats
 #define EF_SOLVE_DEVICE 1 /* one persistent cooperative kernel runs the SO(3) loop and all Gauss-Newton
                              iterations; the same double-precision LDLT runs in a single device thread */
 
-/* RGBDOdometry::RGBDOdometry (Utils/RGBDOdometry.cpp:21-111).  `stream` is a cudaStream_t or NULL
- * (the handle then creates its own non-blocking stream).  Uses the current CUDA device. */
+/* RGBDOdometry::RGBDOdometry (Utils/RGBDOdometry.cpp:21-111).  Any width, height >= 16 (level i is (width >> i) x (height >> i)
+ * like the reference's).  `stream` is a cudaStream_t or NULL (the handle then creates its own non-blocking stream).
+ * The handle lives on the CUDA device that is current at this call; every later call on the handle makes that device
+ * current for its duration and restores the caller's.
+ * STREAM CONTRACT: device inputs (`d_` pointers, cudaArrays) are consumed on the handle's stream.  Work that produces them
+ * on another stream must be ordered before the call by the caller: record an event there and pass it to
+ * ef_tracker_wait_event, or synchronise.  (The reference has no such issue: everything runs on the legacy default stream.) */
 int ef_tracker_create(int width, int height, float cx, float cy, float fx, float fy, float dist_thresh, float angle_thresh,
                       void * stream, ef_tracker ** out);
 int ef_tracker_destroy(ef_tracker * t);
@@ -105,6 +112,8 @@ int ef_tracker_get_option(ef_tracker * t, int key, int * value);
 const char * ef_last_error(const ef_tracker * t);
 void * ef_tracker_stream(ef_tracker * t);
 int ef_tracker_synchronize(ef_tracker * t);
+/* the handle's stream waits for `cuda_event` (a cudaEvent_t recorded on the stream that produces the next call's device inputs) */
+int ef_tracker_wait_event(ef_tracker * t, void * cuda_event);
 
 /* default thresholds of the reference constructor (Utils/RGBDOdometry.h:38-39) */
 float ef_default_dist_thresh(void);

@@ -54,6 +54,24 @@ int fail(ef_tracker * t, int code, const char * what)
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// A handle lives on the device that was current when it was created (ef_tracker_create); every Tier-1 entry makes that
+// device current for the duration of the call and restores the caller's, so one host thread may drive handles on
+// several GPUs (the reference is single-device: it never calls cudaSetDevice after start-up).
+struct DeviceGuard
+{
+    int prev = -1;
+    bool switched = false;
+    explicit DeviceGuard(const ef_tracker * t)
+    {
+        if(t && cudaGetDevice(&prev) == cudaSuccess && prev != t->device) switched = cudaSetDevice(t->device) == cudaSuccess;
+    }
+    ~DeviceGuard()
+    {
+        if(switched) cudaSetDevice(prev);
+    }
+};
+#define EF_ON_DEVICE(t) DeviceGuard ef_device_guard_(t)
+
 int flush_deferred(ef_tracker * t); // EF_OPT_DEFER_BUILD: build what the recorded init* calls asked for
 
 struct ArenaPlan
@@ -145,6 +163,18 @@ static void fork_done(ef_tracker * t, int which, cudaStream_t s)
     else cudaStreamSynchronize(s);
 }
 
+// staging buffers of the _array / _host entry points (see stage_guard)
+enum { kStageV = 0, kStageN = 1, kStageModelRgba = 2, kStageDepth = 3, kStageRgba = 4 };
+
+// a builder on internal stream `which` reads `src`: if that is a staging buffer, remember who reads it
+static void note_stage_reader(ef_tracker * t, const void * src, int which, cudaStream_t s)
+{
+    if(s == t->stream) return;
+    const void * buf[5] = {t->stage_v, t->stage_n, t->stage_rgba_model, t->stage_depth, t->stage_rgba};
+    for(int i = 0; i < 5; i++)
+        if(src == buf[i]) t->stage_reader[i] = which;
+}
+
 static int join_streams(ef_tracker * t)
 {
     for(int i = 0; i < kNumAux; i++)
@@ -159,7 +189,9 @@ static int join_streams(ef_tracker * t)
 EF_API int ef_tracker_create(int width, int height, float cx, float cy, float fx, float fy, float dist_thresh, float angle_thresh, void * stream,
                              ef_tracker ** out)
 {
-    if(!out || width <= 0 || height <= 0 || (width % 4) || (height % 4)) return EF_ERR_INVALID_ARGUMENT;
+    // any size the reference accepts (RGBDOdometry.cpp:21-111: level i is (width >> i) x (height >> i)); the coarsest level
+    // must still hold the 8 pixels the tracker kernel's clamped window loads assume
+    if(!out || width < 16 || height < 16) return EF_ERR_INVALID_ARGUMENT;
     *out = nullptr;
     if(ef_device_count() <= 0) return EF_ERR_NO_DEVICE; // the product has no CPU path
 
@@ -173,9 +205,13 @@ EF_API int ef_tracker_create(int width, int height, float cx, float cy, float fx
     t->max_depth_rgb = 6.0f;
     t->min_grad[0] = 5; t->min_grad[1] = 3; t->min_grad[2] = 1;
     for(int i = 0; i < kNumPyrs; i++) t->dims[i] = LevelDims{height >> i, width >> i};
-    t->solve_mode = EF_SOLVE_HOST;
+    t->solve_mode = EF_SOLVE_DEVICE; // falls back to EF_SOLVE_HOST below when the image does not fit the persistent kernel
     t->use_graph = 0;
-    t->fused_build = 1;
+    // the fused builders move two / four pixels per load and store: images whose sides are not multiples of 4 take the
+    // one-kernel-per-operator builders (any size, any pitch)
+    t->vector_ok = (width % 4 == 0) && (height % 4 == 0);
+    t->fused_build = t->vector_ok ? 1 : 0;
+    for(int i = 0; i < 5; i++) t->stage_reader[i] = -1;
     t->launches = 0;
     t->grid_ctas = 0;
     t->aux_streams = 1;
@@ -296,6 +332,7 @@ EF_API int ef_tracker_create(int width, int height, float cx, float cy, float fx
         delete t;
         return rc;
     }
+    if(!device_track_supported(t)) t->solve_mode = EF_SOLVE_HOST;
     e = cudaStreamSynchronize(t->stream);
     if(e != cudaSuccess) { ef_tracker_destroy(t); return (int)e; }
     *out = t;
@@ -304,6 +341,7 @@ EF_API int ef_tracker_create(int width, int height, float cx, float cy, float fx
 
 EF_API int ef_tracker_destroy(ef_tracker * t)
 {
+    EF_ON_DEVICE(t);
     if(!t) return EF_OK;
     for(int i = 0; i < kNumAux; i++)
         if(t->aux[i]) cudaStreamSynchronize(t->aux[i]);
@@ -323,11 +361,15 @@ EF_API int ef_tracker_destroy(ef_tracker * t)
 
 EF_API int ef_tracker_set_option(ef_tracker * t, int key, int value)
 {
+    EF_ON_DEVICE(t);
     if(!t) return EF_ERR_INVALID_ARGUMENT;
     switch(key)
     {
     case EF_OPT_SOLVE_MODE:
         if(value != EF_SOLVE_HOST && value != EF_SOLVE_DEVICE) return fail(t, EF_ERR_INVALID_ARGUMENT, "bad solve mode");
+        if(t->launch_pending) return fail(t, EF_ERR_BAD_STATE, "a launch is pending");
+        if(value == EF_SOLVE_DEVICE && !device_track_supported(t))
+            return fail(t, EF_ERR_UNSUPPORTED, "image too large for the shared-memory candidate store of EF_SOLVE_DEVICE");
         t->solve_mode = value;
         return EF_OK;
     case EF_OPT_USE_GRAPH:
@@ -340,7 +382,10 @@ EF_API int ef_tracker_set_option(ef_tracker * t, int key, int value)
         }
         t->use_graph = value ? 1 : 0;
         return EF_OK;
-    case EF_OPT_FUSED_BUILD: t->fused_build = value ? 1 : 0; return EF_OK;
+    case EF_OPT_FUSED_BUILD:
+        if(value && !t->vector_ok) return fail(t, EF_ERR_UNSUPPORTED, "fused builders need image sides that are multiples of 4");
+        t->fused_build = value ? 1 : 0;
+        return EF_OK;
     case EF_OPT_AUX_STREAMS:
     {
         const int rc = join_streams(t);
@@ -409,8 +454,17 @@ EF_API int ef_tracker_profile(ef_tracker * t, double * ms, long long * calls)
     return EF_OK;
 }
 
+EF_API int ef_tracker_wait_event(ef_tracker * t, void * cuda_event)
+{
+    if(!t || !cuda_event) return EF_ERR_INVALID_ARGUMENT;
+    EF_ON_DEVICE(t);
+    EF_CUDA(t, cudaStreamWaitEvent(t->stream, (cudaEvent_t)cuda_event, 0));
+    return EF_OK;
+}
+
 EF_API int ef_tracker_synchronize(ef_tracker * t)
 {
+    EF_ON_DEVICE(t);
     if(!t) return EF_ERR_INVALID_ARGUMENT;
     {
         const int rc_flush = flush_deferred(t);
@@ -435,6 +489,7 @@ static int init_icp_depth(ef_tracker * t, const uint16_t * d_depth, size_t pitch
         // one launch per level: vertex map + normal map (+ dense copy of level 0) + bilateral pyrDown to the next level;
         // nothing else a frame builds is read here, so the three launches go to an internal stream (aux 0)
         cudaStream_t s = fork_stream(t, 0);
+        note_stage_reader(t, d_depth, 0, s);
         if(raw_max_depth_m > 0.f)
         {
             EF_LAUNCH(t, launch_depth_bilateral(d_depth, pitch_bytes, t->height, t->width, raw_max_depth_m, t->filt_depth, 0, s));
@@ -489,6 +544,7 @@ static int init_icp_depth(ef_tracker * t, const uint16_t * d_depth, size_t pitch
 
 EF_API int ef_init_icp_depth(ef_tracker * t, const uint16_t * d_depth, size_t pitch_bytes, float depth_cutoff)
 {
+    EF_ON_DEVICE(t);
     if(t && d_depth && t->defer_build && (pitch_bytes == 0 || pitch_bytes == (size_t)t->width * 2))
     {
         t->deferred.depth = d_depth;
@@ -506,6 +562,7 @@ EF_API int ef_init_icp_depth(ef_tracker * t, const uint16_t * d_depth, size_t pi
 // ElasticFusion.cpp:309 (filterDepth) + :348 (initICP) in one call
 EF_API int ef_init_icp_depth_raw(ef_tracker * t, const uint16_t * d_raw_depth, size_t pitch_bytes, float max_depth_m, float depth_cutoff)
 {
+    EF_ON_DEVICE(t);
     if(!(max_depth_m > 0.f)) return t ? fail(t, EF_ERR_INVALID_ARGUMENT, "max_depth_m must be positive") : EF_ERR_INVALID_ARGUMENT;
     {
         const int rc_flush = flush_deferred(t);
@@ -544,6 +601,7 @@ static int build_maps(ef_tracker * t, const float * d_v, const float * d_n, floa
 // RGBDOdometry.cpp:144-167
 EF_API int ef_init_icp_maps(ef_tracker * t, const float * d_v, const float * d_n, float depth_cutoff)
 {
+    EF_ON_DEVICE(t);
     (void)depth_cutoff; // unused by the reference as well
     if(!t || !d_v || !d_n) return EF_ERR_INVALID_ARGUMENT;
     {
@@ -556,6 +614,7 @@ EF_API int ef_init_icp_maps(ef_tracker * t, const float * d_v, const float * d_n
 // RGBDOdometry.cpp:169-206
 EF_API int ef_init_icp_model(ef_tracker * t, const float * d_v, const float * d_n, float depth_cutoff, const float * pose)
 {
+    EF_ON_DEVICE(t);
     (void)depth_cutoff;
     if(!t || !d_v || !d_n || !pose) return EF_ERR_INVALID_ARGUMENT;
     if(t->defer_build)
@@ -593,6 +652,7 @@ static int populate_rgbd(ef_tracker * t, const uint8_t * d_rgba, size_t pitch, f
 
 EF_API int ef_init_rgb(ef_tracker * t, const uint8_t * d_rgba, size_t pitch)
 {
+    EF_ON_DEVICE(t);
     if(!t || !d_rgba) return EF_ERR_INVALID_ARGUMENT;
     if(t->defer_build && (pitch == 0 || pitch == (size_t)t->width * 4))
     {
@@ -610,6 +670,7 @@ EF_API int ef_init_rgb(ef_tracker * t, const uint8_t * d_rgba, size_t pitch)
 
 EF_API int ef_init_rgb_model(ef_tracker * t, const uint8_t * d_rgba, size_t pitch)
 {
+    EF_ON_DEVICE(t);
     if(!t || !d_rgba) return EF_ERR_INVALID_ARGUMENT;
     if(t->defer_build && (pitch == 0 || pitch == (size_t)t->width * 4))
     {
@@ -623,6 +684,7 @@ EF_API int ef_init_rgb_model(ef_tracker * t, const uint8_t * d_rgba, size_t pitc
     }
     // reads tmp_z (already enqueued on the handle's stream), writes only the "last" pyramids: internal stream (aux 1)
     cudaStream_t s = t->fused_build ? fork_stream(t, 1) : t->stream;
+    note_stage_reader(t, d_rgba, 1, s);
     const int rc = populate_rgbd(t, d_rgba, pitch, t->last_depth, t->last_image, s);
     fork_done(t, 1, s);
     return rc;
@@ -631,6 +693,7 @@ EF_API int ef_init_rgb_model(ef_tracker * t, const uint8_t * d_rgba, size_t pitc
 // RGBDOdometry.cpp:249-265
 EF_API int ef_init_first_rgb(ef_tracker * t, const uint8_t * d_rgba, size_t pitch)
 {
+    EF_ON_DEVICE(t);
     if(!t || !d_rgba) return EF_ERR_INVALID_ARGUMENT;
     cudaStream_t s = t->stream;
     if(t->fused_build)
@@ -645,97 +708,139 @@ EF_API int ef_init_first_rgb(ef_tracker * t, const uint8_t * d_rgba, size_t pitc
     return EF_OK;
 }
 
-// ---- cudaArray variants (GL interop) ----
-static int stage_array(ef_tracker * t, void * dst, cudaArray_t arr, size_t row_bytes)
+// ---- staging buffers of the _array and _host entry points ----
+// Five buffers, one per input of a frame (model vertices, model normals, model colour, depth, colour), so that the calls of
+// one frame never share one.  Before a buffer is overwritten
+//   (1) a recorded-but-unbuilt init* call (EF_OPT_DEFER_BUILD) that points at it is built, and
+//   (2) the handle's stream waits for the internal stream whose builder last read it (the model RGB-D chain and the depth
+//       chain run beside the handle's stream, fork_stream),
+// so neither a deferred build nor a builder still in flight ever sees the next call's data.
+static int stage_guard(ef_tracker * t, int which)
+{
+    const void * buf[5] = {t->stage_v, t->stage_n, t->stage_rgba_model, t->stage_depth, t->stage_rgba};
+    const unsigned have = t->deferred.have;
+    const bool referenced = ((have & 1u) && (t->deferred.v == buf[which] || t->deferred.n == buf[which])) ||
+                            ((have & 2u) && t->deferred.model_rgba == buf[which]) || ((have & 4u) && t->deferred.depth == buf[which]) ||
+                            ((have & 8u) && t->deferred.rgba == buf[which]);
+    if(referenced)
+    {
+        const int rc = flush_deferred(t);
+        if(rc) return rc;
+    }
+    const int r = t->stage_reader[which];
+    if(r >= 0 && t->aux_dirty[r]) EF_CUDA(t, cudaStreamWaitEvent(t->stream, t->ev_join[r], 0)); // the join proper still happens later
+    t->stage_reader[which] = -1;
+    return EF_OK;
+}
+
+static int stage_array(ef_tracker * t, int which, void * dst, cudaArray_t arr, size_t row_bytes)
 {
     if(!arr) return EF_ERR_INVALID_ARGUMENT;
+    const int rc = stage_guard(t, which);
+    if(rc) return rc;
     EF_CUDA(t, cudaMemcpy2DFromArrayAsync(dst, row_bytes, arr, 0, 0, row_bytes, t->height, cudaMemcpyDeviceToDevice, t->stream));
+    return EF_OK;
+}
+
+static int stage_host(ef_tracker * t, int which, void * dst, const void * h, size_t bytes)
+{
+    const int rc = stage_guard(t, which);
+    if(rc) return rc;
+    EF_CUDA(t, cudaMemcpyAsync(dst, h, bytes, cudaMemcpyHostToDevice, t->stream));
     return EF_OK;
 }
 
 EF_API int ef_init_icp_depth_array(ef_tracker * t, void * arr, float cutoff)
 {
+    EF_ON_DEVICE(t);
     if(!t) return EF_ERR_INVALID_ARGUMENT;
-    const int rc = stage_array(t, t->stage_depth, (cudaArray_t)arr, (size_t)t->width * 2);
+    const int rc = stage_array(t, kStageDepth, t->stage_depth, (cudaArray_t)arr, (size_t)t->width * 2);
     return rc ? rc : ef_init_icp_depth(t, t->stage_depth, 0, cutoff);
 }
 
 EF_API int ef_init_icp_maps_array(ef_tracker * t, void * v, void * n, float cutoff)
 {
+    EF_ON_DEVICE(t);
     if(!t) return EF_ERR_INVALID_ARGUMENT;
-    int rc = stage_array(t, t->stage_v, (cudaArray_t)v, (size_t)t->width * 16);
-    if(!rc) rc = stage_array(t, t->stage_n, (cudaArray_t)n, (size_t)t->width * 16);
+    int rc = stage_array(t, kStageV, t->stage_v, (cudaArray_t)v, (size_t)t->width * 16);
+    if(!rc) rc = stage_array(t, kStageN, t->stage_n, (cudaArray_t)n, (size_t)t->width * 16);
     return rc ? rc : ef_init_icp_maps(t, t->stage_v, t->stage_n, cutoff);
 }
 
 EF_API int ef_init_icp_model_array(ef_tracker * t, void * v, void * n, float cutoff, const float * pose)
 {
+    EF_ON_DEVICE(t);
     if(!t) return EF_ERR_INVALID_ARGUMENT;
-    int rc = stage_array(t, t->stage_v, (cudaArray_t)v, (size_t)t->width * 16);
-    if(!rc) rc = stage_array(t, t->stage_n, (cudaArray_t)n, (size_t)t->width * 16);
+    int rc = stage_array(t, kStageV, t->stage_v, (cudaArray_t)v, (size_t)t->width * 16);
+    if(!rc) rc = stage_array(t, kStageN, t->stage_n, (cudaArray_t)n, (size_t)t->width * 16);
     return rc ? rc : ef_init_icp_model(t, t->stage_v, t->stage_n, cutoff, pose);
 }
 
 EF_API int ef_init_rgb_array(ef_tracker * t, void * arr)
 {
+    EF_ON_DEVICE(t);
     if(!t) return EF_ERR_INVALID_ARGUMENT;
-    const int rc = stage_array(t, t->stage_rgba, (cudaArray_t)arr, (size_t)t->width * 4);
+    const int rc = stage_array(t, kStageRgba, t->stage_rgba, (cudaArray_t)arr, (size_t)t->width * 4);
     return rc ? rc : ef_init_rgb(t, t->stage_rgba, 0);
 }
 
 EF_API int ef_init_rgb_model_array(ef_tracker * t, void * arr)
 {
+    EF_ON_DEVICE(t);
     if(!t) return EF_ERR_INVALID_ARGUMENT;
-    const int rc = stage_array(t, t->stage_rgba, (cudaArray_t)arr, (size_t)t->width * 4);
-    return rc ? rc : ef_init_rgb_model(t, t->stage_rgba, 0);
+    // the model image has a staging buffer of its own (see ef_init_rgb_model_host)
+    const int rc = stage_array(t, kStageModelRgba, t->stage_rgba_model, (cudaArray_t)arr, (size_t)t->width * 4);
+    return rc ? rc : ef_init_rgb_model(t, t->stage_rgba_model, 0);
 }
 
 EF_API int ef_init_first_rgb_array(ef_tracker * t, void * arr)
 {
+    EF_ON_DEVICE(t);
     if(!t) return EF_ERR_INVALID_ARGUMENT;
-    const int rc = stage_array(t, t->stage_rgba, (cudaArray_t)arr, (size_t)t->width * 4);
+    const int rc = stage_array(t, kStageRgba, t->stage_rgba, (cudaArray_t)arr, (size_t)t->width * 4);
     return rc ? rc : ef_init_first_rgb(t, t->stage_rgba, 0);
 }
 
 // ---- host-buffer variants ----
 EF_API int ef_init_icp_depth_host(ef_tracker * t, const uint16_t * h, float cutoff)
 {
+    EF_ON_DEVICE(t);
     if(!t || !h) return EF_ERR_INVALID_ARGUMENT;
-    EF_CUDA(t, cudaMemcpyAsync(t->stage_depth, h, t->dims[0].n() * 2, cudaMemcpyHostToDevice, t->stream));
-    return ef_init_icp_depth(t, t->stage_depth, 0, cutoff);
+    const int rc = stage_host(t, kStageDepth, t->stage_depth, h, t->dims[0].n() * 2);
+    return rc ? rc : ef_init_icp_depth(t, t->stage_depth, 0, cutoff);
 }
 
 EF_API int ef_init_icp_depth_raw_host(ef_tracker * t, const uint16_t * h, float max_depth_m, float cutoff)
 {
+    EF_ON_DEVICE(t);
     if(!t || !h) return EF_ERR_INVALID_ARGUMENT;
-    EF_CUDA(t, cudaMemcpyAsync(t->stage_depth, h, t->dims[0].n() * 2, cudaMemcpyHostToDevice, t->stream));
-    return ef_init_icp_depth_raw(t, t->stage_depth, 0, max_depth_m, cutoff);
+    const int rc = stage_host(t, kStageDepth, t->stage_depth, h, t->dims[0].n() * 2);
+    return rc ? rc : ef_init_icp_depth_raw(t, t->stage_depth, 0, max_depth_m, cutoff);
 }
 
 EF_API int ef_init_icp_maps_host(ef_tracker * t, const float * hv, const float * hn, float cutoff)
 {
+    EF_ON_DEVICE(t);
     if(!t || !hv || !hn) return EF_ERR_INVALID_ARGUMENT;
-    EF_CUDA(t, cudaMemcpyAsync(t->stage_v, hv, t->dims[0].n() * 16, cudaMemcpyHostToDevice, t->stream));
-    EF_CUDA(t, cudaMemcpyAsync(t->stage_n, hn, t->dims[0].n() * 16, cudaMemcpyHostToDevice, t->stream));
-    return ef_init_icp_maps(t, t->stage_v, t->stage_n, cutoff);
+    int rc = stage_host(t, kStageV, t->stage_v, hv, t->dims[0].n() * 16);
+    if(!rc) rc = stage_host(t, kStageN, t->stage_n, hn, t->dims[0].n() * 16);
+    return rc ? rc : ef_init_icp_maps(t, t->stage_v, t->stage_n, cutoff);
 }
 
 EF_API int ef_init_icp_model_host(ef_tracker * t, const float * hv, const float * hn, float cutoff, const float * pose)
 {
+    EF_ON_DEVICE(t);
     if(!t || !hv || !hn) return EF_ERR_INVALID_ARGUMENT;
-    EF_CUDA(t, cudaMemcpyAsync(t->stage_v, hv, t->dims[0].n() * 16, cudaMemcpyHostToDevice, t->stream));
-    EF_CUDA(t, cudaMemcpyAsync(t->stage_n, hn, t->dims[0].n() * 16, cudaMemcpyHostToDevice, t->stream));
-    return ef_init_icp_model(t, t->stage_v, t->stage_n, cutoff, pose);
+    int rc = stage_host(t, kStageV, t->stage_v, hv, t->dims[0].n() * 16);
+    if(!rc) rc = stage_host(t, kStageN, t->stage_n, hn, t->dims[0].n() * 16);
+    return rc ? rc : ef_init_icp_model(t, t->stage_v, t->stage_n, cutoff, pose);
 }
 
-static int stage_rgba_host(ef_tracker * t, const uint8_t * h)
-{
-    EF_CUDA(t, cudaMemcpyAsync(t->stage_rgba, h, t->dims[0].n() * 4, cudaMemcpyHostToDevice, t->stream));
-    return EF_OK;
-}
+static int stage_rgba_host(ef_tracker * t, const uint8_t * h) { return stage_host(t, kStageRgba, t->stage_rgba, h, t->dims[0].n() * 4); }
 
 EF_API int ef_init_rgb_host(ef_tracker * t, const uint8_t * h)
 {
+    EF_ON_DEVICE(t);
     if(!t || !h) return EF_ERR_INVALID_ARGUMENT;
     const int rc = stage_rgba_host(t, h);
     return rc ? rc : ef_init_rgb(t, t->stage_rgba, 0);
@@ -743,15 +848,17 @@ EF_API int ef_init_rgb_host(ef_tracker * t, const uint8_t * h)
 
 EF_API int ef_init_rgb_model_host(ef_tracker * t, const uint8_t * h)
 {
+    EF_ON_DEVICE(t);
     if(!t || !h) return EF_ERR_INVALID_ARGUMENT;
     // the model image has a staging buffer of its own: its pyramid is built on an internal stream (aux 1) and may still
     // be reading it while the copy of the next image runs on the handle's stream
-    EF_CUDA(t, cudaMemcpyAsync(t->stage_rgba_model, h, t->dims[0].n() * 4, cudaMemcpyHostToDevice, t->stream));
-    return ef_init_rgb_model(t, t->stage_rgba_model, 0);
+    const int rc = stage_host(t, kStageModelRgba, t->stage_rgba_model, h, t->dims[0].n() * 4);
+    return rc ? rc : ef_init_rgb_model(t, t->stage_rgba_model, 0);
 }
 
 EF_API int ef_init_first_rgb_host(ef_tracker * t, const uint8_t * h)
 {
+    EF_ON_DEVICE(t);
     if(!t || !h) return EF_ERR_INVALID_ARGUMENT;
     const int rc = stage_rgba_host(t, h);
     return rc ? rc : ef_init_first_rgb(t, t->stage_rgba, 0);
@@ -1094,6 +1201,7 @@ static void swap_so3_images(ef_tracker * t)
 EF_API int ef_get_incremental_transformation_launch(ef_tracker * t, const float * trans, const float * rot, int rgb_only, float icp_weight,
                                                     int pyramid, int fast_odom, int so3)
 {
+    EF_ON_DEVICE(t);
     if(!t || !trans || !rot) return EF_ERR_INVALID_ARGUMENT;
     if(t->launch_pending) return fail(t, EF_ERR_BAD_STATE, "a launch is already pending");
     {
@@ -1136,6 +1244,7 @@ EF_API int ef_get_incremental_transformation_launch(ef_tracker * t, const float 
 
 EF_API int ef_get_incremental_transformation_finish(ef_tracker * t, float * trans, float * rot, ef_track_stats * stats)
 {
+    EF_ON_DEVICE(t);
     if(!t || !trans || !rot) return EF_ERR_INVALID_ARGUMENT;
     if(!t->launch_pending) return fail(t, EF_ERR_BAD_STATE, "no launch pending");
     t->launch_pending = false;
@@ -1171,6 +1280,7 @@ EF_API int ef_get_incremental_transformation_finish(ef_tracker * t, float * tran
 EF_API int ef_get_incremental_transformation(ef_tracker * t, float * trans, float * rot, int rgb_only, float icp_weight, int pyramid,
                                              int fast_odom, int so3, ef_track_stats * stats)
 {
+    EF_ON_DEVICE(t);
     const int rc = ef_get_incremental_transformation_launch(t, trans, rot, rgb_only, icp_weight, pyramid, fast_odom, so3);
     if(rc) return rc;
     return ef_get_incremental_transformation_finish(t, trans, rot, stats);
@@ -1259,6 +1369,7 @@ static cudaStream_t fork_from_recorded(ef_tracker * t, int which)
 EF_API int ef_track_frame_to_model_launch(ef_tracker * t, const ef_frame_inputs * in, const float * pose, int rgb_only, float icp_weight, int pyramid,
                                           int fast_odom, int so3)
 {
+    EF_ON_DEVICE(t);
     if(!t || !in || !pose) return EF_ERR_INVALID_ARGUMENT;
     if(!in->vertices_rgba32f || !in->normals_rgba32f || !in->model_rgba8 || !in->depth || !in->rgba8) return EF_ERR_INVALID_ARGUMENT;
     {
@@ -1284,6 +1395,7 @@ EF_API int ef_track_frame_to_model_launch(ef_tracker * t, const ef_frame_inputs 
         if(in->on_host)
         {
             const size_t n = t->dims[0].n();
+            // (join_streams above: no builder of an earlier call still reads a staging buffer)
             EF_CUDA(t, cudaMemcpyAsync(t->stage_v, v4, n * 16, cudaMemcpyHostToDevice, t->stream));
             EF_CUDA(t, cudaMemcpyAsync(t->stage_n, n4, n * 16, cudaMemcpyHostToDevice, t->stream));
             EF_CUDA(t, cudaMemcpyAsync(t->stage_rgba_model, mrgba, n * 4, cudaMemcpyHostToDevice, t->stream));
@@ -1368,6 +1480,7 @@ EF_API int ef_track_frame_to_model_launch(ef_tracker * t, const ef_frame_inputs 
 EF_API int ef_track_frame_to_model(ef_tracker * t, const ef_frame_inputs * in, const float * pose, float * trans, float * rot, int rgb_only,
                                    float icp_weight, int pyramid, int fast_odom, int so3, ef_track_stats * stats)
 {
+    EF_ON_DEVICE(t);
     const int rc = ef_track_frame_to_model_launch(t, in, pose, rgb_only, icp_weight, pyramid, fast_odom, so3);
     if(rc) return rc;
     return ef_get_incremental_transformation_finish(t, trans, rot, stats);
@@ -1383,6 +1496,7 @@ EF_API int ef_get_covariance(ef_tracker * t, double * cov)
 
 EF_API int ef_tracker_download(ef_tracker * t, const char * name, int level, void * dst, size_t bytes)
 {
+    EF_ON_DEVICE(t);
     if(!t || !name || !dst || level < 0 || level >= kNumPyrs) return EF_ERR_INVALID_ARGUMENT;
     {
         const int rc_flush = flush_deferred(t);

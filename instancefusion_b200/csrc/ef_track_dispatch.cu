@@ -11,6 +11,7 @@ namespace ef
 #define EF_DECLARE_VARIANT(T)                                                                                                              \
     int device_track_init_t##T(ef_tracker * t);                                                                                            \
     int device_track_configure_t##T(ef_tracker * t, int grid_ctas);                                                                        \
+    bool device_track_supported_t##T(const ef_tracker * t);                                                                                \
     void device_track_destroy_t##T(ef_tracker * t);                                                                                        \
     int device_track_launch_t##T(ef_tracker * t, const float * trans, const float * rot, int rgb_only, float icp_weight, int pyramid,     \
                                  int fast_odom, int so3);                                                                                  \
@@ -35,6 +36,10 @@ int device_track_init(ef_tracker * t)
 int device_track_configure(ef_tracker * t, int grid_ctas)
 {
     return t->track_variant == 384 ? device_track_configure_t384(t, grid_ctas) : device_track_configure_t256(t, grid_ctas);
+}
+bool device_track_supported(const ef_tracker * t)
+{
+    return t->track_variant == 384 ? device_track_supported_t384(t) : device_track_supported_t256(t);
 }
 void device_track_destroy(ef_tracker * t)
 {

@@ -54,6 +54,7 @@ namespace ef
 
 void EF_TRACK_FN(device_track_destroy)(ef_tracker * t);
 int EF_TRACK_FN(device_track_configure)(ef_tracker * t, int grid);
+bool EF_TRACK_FN(device_track_supported)(const ef_tracker * t);
 
 namespace
 {
@@ -110,6 +111,11 @@ struct LevelArgs
 // Flagged 16-byte chunks (the NCCL "LL" idea): a chunk is written with ONE 128-bit store and read with ONE
 // 128-bit load, so its three payload words and its flag are always observed together.  No fence, no separate
 // "ready" counter: whoever polls a chunk gets the data with the same load that tells it the data is there.
+// The accesses are the SCALAR 128-bit forms  ld/st.relaxed.gpu.global.b128  (PTX ISA 8.3+, sm_70+): one memory
+// operation of a 128-bit scalar type under the PTX memory model, not the .v4.u32 vector forms, which the model
+// treats as four independent 32-bit accesses in unspecified order (round-1 review).  Both compile to the same
+// LDG.E.128.STRONG.GPU / STG.E.128.STRONG.GPU; tools/chunk_torture.cu hammers the pattern (every reader checks every
+// observed chunk for tearing, all SM pairs, under concurrent HBM traffic), log in profiles/r02_chunk_torture.txt.
 // Flags are launch-unique epochs (launch_seq << 8 | n), so nothing has to be reset between launches.
 // Nobody polls a line together with more than ~5 other CTAs (148 CTAs spinning on one line serialise in its L2 slice):
 //   par      the parameter line (8 chunks), kReplicas copies 256 bytes apart; worker w reads copy w % kReplicas.
@@ -155,16 +161,21 @@ struct TrackArgs
     long long * dbg;                              // optional clock64 stamps of every CTA (EF_TRACK_TIMING=1)
 };
 
-// ---- 128-bit relaxed (L2-coherent) accesses ----
+// ---- 128-bit relaxed (L2-coherent) SCALAR accesses: one memory operation each (see above) ----
 __device__ __forceinline__ uint4 ld_relaxed_v4(const uint4 * p)
 {
     uint4 v;
-    asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    asm volatile("{\n\t.reg .b128 q;\n\tld.relaxed.gpu.global.b128 q, [%4];\n\tmov.b128 {%0, %1, %2, %3}, q;\n\t}"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "l"(p)
+                 : "memory");
     return v;
 }
 __device__ __forceinline__ void st_relaxed_v4(uint4 * p, const uint4 & v)
 {
-    asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+    asm volatile("{\n\t.reg .b128 q;\n\tmov.b128 q, {%1, %2, %3, %4};\n\tst.relaxed.gpu.global.b128 [%0], q;\n\t}" ::"l"(p), "r"(v.x), "r"(v.y),
+                 "r"(v.z), "r"(v.w)
+                 : "memory");
 }
 
 // warp 0 of CTA 0, payload already in shared memory: chunks [first, first + n) of every replica of the parameter
@@ -300,6 +311,27 @@ __device__ __forceinline__ double fast_rcp(double d)
     return (d != 0.0) ? r : 0.0;
 }
 
+// The ill-conditioned case of the 6x6 solve (RGBDOdometry.cpp:552-564): the same symmetric-pivoted LDL^T as the host-solve
+// mode and the reference's Eigen ldlt() (pivot = largest remaining |diagonal|, hm::ldlt_solve).  Taken only when the
+// unpivoted fast path met a pivot below 1e-10 of the largest diagonal (plane-only ICP, too few photometric matches, a
+// nearly empty frame), where the order of elimination decides what comes out of the null space.  Rare, so out of line.
+__device__ __noinline__ void solve_pivoted(const double * S28, double * x6)
+{
+    double A[36], b[6];
+#pragma unroll
+    for(int i = 0; i < 6; i++)
+    {
+#pragma unroll
+        for(int j = i; j < 7; j++)
+        {
+            const double v = S28[hm::acc_index(i, j)];
+            if(j == 6) b[i] = v;
+            else A[j * 6 + i] = A[i * 6 + j] = v;
+        }
+    }
+    hm::ldlt_solve<double, 6>(A, b, x6);
+}
+
 // warps 0 and 1 of CTA 0: hand-over of resultRt from the solver warp to the warp that derives the photometric warp
 __device__ __forceinline__ void solver_pair_sync() { asm volatile("bar.sync 1, 64;" ::: "memory"); }
 
@@ -339,11 +371,16 @@ __device__ __forceinline__ void warp_solve_se3(Solver * S, const float * s_final
         a[2 * k + 1] = v.y;
     }
 
-    // x = A^-1 b (:552-564): hm::ldlt_solve_spd6_acc with the Newton reciprocal
+    // x = A^-1 b (:552-564): hm::ldlt_solve_spd6_acc with the Newton reciprocal.  Beside the critical path: the largest
+    // diagonal entry and the smallest pivot, which decide whether this unpivoted elimination was good enough
     double inv[6], x[6];
+    double amax = 0.0, dmin = DBL_MAX;
+#pragma unroll
+    for(int j = 0; j < 6; j++) amax = fmax(amax, fabs(a[hm::acc_index(j, j)]));
 #pragma unroll
     for(int j = 0; j < 6; j++)
     {
+        dmin = fmin(dmin, a[hm::acc_index(j, j)]); // (a negative or NaN pivot also trips the test below)
         inv[j] = fast_rcp(a[hm::acc_index(j, j)]);
         double l[6];
 #pragma unroll
@@ -369,6 +406,7 @@ __device__ __forceinline__ void warp_solve_se3(Solver * S, const float * s_final
 #pragma unroll
         for(int r = 0; r < i; r++) wv[r] = fma(-a[hm::acc_index(r, i)], x[i], wv[r]);
     }
+    if(!(dmin > 1e-10 * amax)) solve_pivoted(S->last_S, x); // warp-uniform: every lane holds the same numbers
     if(dbg) tk[2] = clock64();
 
     // OdometryProvider.h:35-71 rodrigues(x[3:6])
@@ -1597,6 +1635,12 @@ int EF_TRACK_FN(device_track_configure)(ef_tracker * t, int grid)
     return EF_OK;
 }
 
+bool EF_TRACK_FN(device_track_supported)(const ef_tracker * t)
+{
+    const DeviceTrack * d = static_cast<const DeviceTrack *>(t->track_state);
+    return d && d->smem_bytes <= (size_t)kMaxDynSmem && (size_t)t->width * t->height < (1u << 24) && t->width <= 4094 && t->height <= 4094;
+}
+
 int EF_TRACK_FN(device_track_init)(ef_tracker * t)
 {
     DeviceTrack * d = new DeviceTrack();
@@ -1682,7 +1726,7 @@ int EF_TRACK_FN(device_track_launch)(ef_tracker * t, const float * trans, const 
 {
     DeviceTrack * d = static_cast<DeviceTrack *>(t->track_state);
     if(!d) return EF_ERR_BAD_STATE;
-    if(d->smem_bytes > (size_t)kMaxDynSmem || (size_t)t->width * t->height >= (1u << 24) || t->width > 4094 || t->height > 4094)
+    if(!EF_TRACK_FN(device_track_supported)(t))
     {
         t->err = "image too large for the shared-memory candidate store of EF_SOLVE_DEVICE";
         return EF_ERR_UNSUPPORTED;

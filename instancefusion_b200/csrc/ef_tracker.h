@@ -40,6 +40,7 @@ struct ef_tracker
     int solve_mode;  // EF_SOLVE_HOST | EF_SOLVE_DEVICE
     int use_graph;
     int fused_build;
+    bool vector_ok;  // both image sides are multiples of 4: the fused (vectorised) builders apply
     int grid_ctas;   // EF_OPT_GRID_CTAS (0 = every SM)
     int aux_streams; // EF_OPT_AUX_STREAMS
     int frame_build; // EF_OPT_FRAME_BUILD
@@ -79,6 +80,7 @@ struct ef_tracker
     uint16_t * stage_depth;
     uint8_t * stage_rgba, * stage_rgba_model; // two: the model image is read on an internal stream while the next copy runs
     float * stage_v, * stage_n;
+    int stage_reader[5]; // internal stream whose builder last read each staging buffer (-1: the handle's stream), ef_api.cu stage_guard
 
     // persistent-kernel state (EF_SOLVE_DEVICE)
     int track_variant;  // threads per CTA of the tracker-kernel build this handle uses (ef_track_dispatch.cu)
@@ -120,6 +122,7 @@ namespace ef
 // EF_SOLVE_DEVICE path (ef_track_kernel.cu)
 int device_track_init(ef_tracker * t);
 int device_track_configure(ef_tracker * t, int grid_ctas);
+bool device_track_supported(const ef_tracker * t); // the image fits the persistent kernel's shared-memory candidate store
 void device_track_destroy(ef_tracker * t);
 int device_track_launch(ef_tracker * t, const float * trans, const float * rot, int rgb_only, float icp_weight, int pyramid, int fast_odom,
                         int so3);

@@ -26,12 +26,30 @@ def _is_cuda_tensor(a) -> bool:
     return hasattr(a, "is_cuda") and a.is_cuda
 
 
+def _is_cuda_array(a) -> bool:
+    """a cudaArray_t wrapper (attribute `cuda_array_handle`): the GL-interop form of a GPUTexture (RGBDOdometry.cpp:120-128)"""
+    return hasattr(a, "cuda_array_handle")
+
+
+def _arr(a):
+    return C.c_void_p(a.cuda_array_handle)
+
+
 def _dev_ptr(a, dtype_name: str):
     import torch
     want = getattr(torch, dtype_name)
     if a.dtype != want or not a.is_contiguous():
         raise ValueError(f"expected a contiguous {dtype_name} CUDA tensor, got {a.dtype}")
     return C.c_void_p(a.data_ptr())
+
+
+def _order_after_torch(handle_stream):
+    """Stream contract of include/ef_track.h: device inputs are consumed on the HANDLE's stream.  If torch's current stream
+    still has work in flight (it may be producing the tensor we are about to borrow), the handle's stream waits for it."""
+    import torch
+    cur = torch.cuda.current_stream()
+    if cur.cuda_stream != handle_stream and not cur.query():
+        torch.cuda.ExternalStream(handle_stream).wait_stream(cur)
 
 
 def _host_arr(a, dtype):
@@ -44,7 +62,7 @@ class RGBDOdometry:
     """RGBDOdometry(width, height, cx, cy, fx, fy, distThresh=0.10, angleThresh=sin(20 deg))"""
 
     def __init__(self, width, height, cx, cy, fx, fy, distThresh=None, angleThresh=None, stream=None,
-                 solve_mode=EF_SOLVE_HOST):
+                 solve_mode=None):
         self._L = binding.lib()
         if distThresh is None:
             distThresh = self._L.ef_default_dist_thresh()
@@ -66,7 +84,8 @@ class RGBDOdometry:
         self._res_t, self._res_r = C.c_void_p(self._res.ctypes.data), C.c_void_p(self._res.ctypes.data + 12)
         self._stats_ref = C.byref(self._stats)
         self._frame = None
-        if solve_mode != EF_SOLVE_HOST:
+        self._stream_int = int(self._L.ef_tracker_stream(self._h) or 0)
+        if solve_mode is not None:  # None: the library's default (EF_SOLVE_DEVICE wherever the image fits the persistent kernel)
             self.set_option(EF_OPT_SOLVE_MODE, solve_mode)
 
     # -- plumbing ---------------------------------------------------------------------------------
@@ -87,6 +106,14 @@ class RGBDOdometry:
 
     def set_option(self, key, value):
         self._check(self._L.ef_tracker_set_option(self._h, C.c_int(key), C.c_int(value)), "ef_tracker_set_option")
+
+    def get_option(self, key):
+        v = C.c_int(0)
+        self._check(self._L.ef_tracker_get_option(self._h, C.c_int(key), C.byref(v)), "ef_tracker_get_option")
+        return v.value
+
+    def _borrow(self):
+        _order_after_torch(self._stream_int)
 
     @property
     def stream(self):
@@ -110,7 +137,10 @@ class RGBDOdometry:
         """initICP(filteredDepth, depthCutoff)  or  initICP(predictedVertices, predictedNormals, depthCutoff)"""
         if len(args) == 2:
             depth, cutoff = args
-            if _is_cuda_tensor(depth):
+            if _is_cuda_array(depth):
+                self._check(self._L.ef_init_icp_depth_array(self._h, _arr(depth), C.c_float(cutoff)), "ef_init_icp_depth_array")
+            elif _is_cuda_tensor(depth):
+                self._borrow()
                 self._check(self._L.ef_init_icp_depth(self._h, _dev_ptr(depth, "uint16"), C.c_size_t(0), C.c_float(cutoff)),
                             "ef_init_icp_depth")
             else:
@@ -120,7 +150,10 @@ class RGBDOdometry:
                             "ef_init_icp_depth_host")
         elif len(args) == 3:
             v, n, cutoff = args
-            if _is_cuda_tensor(v):
+            if _is_cuda_array(v):
+                self._check(self._L.ef_init_icp_maps_array(self._h, _arr(v), _arr(n), C.c_float(cutoff)), "ef_init_icp_maps_array")
+            elif _is_cuda_tensor(v):
+                self._borrow()
                 self._check(self._L.ef_init_icp_maps(self._h, _dev_ptr(v, "float32"), _dev_ptr(n, "float32"), C.c_float(cutoff)),
                             "ef_init_icp_maps")
             else:
@@ -134,6 +167,7 @@ class RGBDOdometry:
     def initICPRaw(self, rawDepth, maxDepth, depthCutoff):
         """filterDepth + initICP (ElasticFusion.cpp:309, :348): RAW sensor depth (u16 mm) -> bilateral filter -> pyramids."""
         if _is_cuda_tensor(rawDepth):
+            self._borrow()
             self._check(self._L.ef_init_icp_depth_raw(self._h, _dev_ptr(rawDepth, "uint16"), C.c_size_t(0), C.c_float(maxDepth),
                                                       C.c_float(depthCutoff)), "ef_init_icp_depth_raw")
         else:
@@ -144,7 +178,11 @@ class RGBDOdometry:
 
     def initICPModel(self, predictedVertices, predictedNormals, depthCutoff, modelPose):
         pose = np.ascontiguousarray(np.asarray(modelPose, dtype=np.float32).reshape(16))
-        if _is_cuda_tensor(predictedVertices):
+        if _is_cuda_array(predictedVertices):
+            self._check(self._L.ef_init_icp_model_array(self._h, _arr(predictedVertices), _arr(predictedNormals), C.c_float(depthCutoff),
+                                                        pose.ctypes.data_as(C.c_void_p)), "ef_init_icp_model_array")
+        elif _is_cuda_tensor(predictedVertices):
+            self._borrow()
             self._check(self._L.ef_init_icp_model(self._h, _dev_ptr(predictedVertices, "float32"), _dev_ptr(predictedNormals, "float32"),
                                                   C.c_float(depthCutoff), pose.ctypes.data_as(C.c_void_p)), "ef_init_icp_model")
         else:
@@ -154,7 +192,10 @@ class RGBDOdometry:
                                                        C.c_float(depthCutoff), pose.ctypes.data_as(C.c_void_p)), "ef_init_icp_model_host")
 
     def _rgb(self, name, rgb):
-        if _is_cuda_tensor(rgb):
+        if _is_cuda_array(rgb):
+            self._check(getattr(self._L, name + "_array")(self._h, _arr(rgb)), name + "_array")
+        elif _is_cuda_tensor(rgb):
+            self._borrow()
             self._check(getattr(self._L, name)(self._h, _dev_ptr(rgb, "uint8"), C.c_size_t(0)), name)
         else:
             h = _host_arr(rgb, np.uint8)
@@ -223,6 +264,7 @@ class RGBDOdometry:
             ptr = lambda a: a.data_ptr() if hasattr(a, "data_ptr") else a.ctypes.data
         else:
             ptr = lambda a: a.data_ptr()
+            self._borrow()
         self._keep_frame = (vertices, normals, model_rgba, depth, rgba)
         fi = self._frame
         if fi is None:

@@ -35,7 +35,9 @@ def _feed(tr, pose0f, f0, f1):
 
 
 # widths whose coarse levels are not multiples of 4 / 32, heights that leave ragged last chunks
-@pytest.mark.parametrize("size", [(320, 240), (200, 152), (168, 120), (96, 64)])
+# ... and sizes that are not multiples of 4 or even odd, which the reference accepts like any other (level i is
+# (width >> i) x (height >> i), RGBDOdometry.cpp:21-111): they take the one-kernel-per-operator builders
+@pytest.mark.parametrize("size", [(320, 240), (200, 152), (168, 120), (96, 64), (322, 242), (321, 241), (638, 478)])
 def test_ragged_sizes_match_reference(size):
     w, h = size
     K, pose0, pose1, f0, f1 = util.frame_pair(w, h)
@@ -331,3 +333,59 @@ def test_many_calls_on_one_handle_are_stable():
             assert np.array_equal(r[0], first[0]) and np.array_equal(r[1], first[1])
     finally:
         tr.close()
+
+
+PLANE_EYES = {"one_plane": (1.2, 1.5, 4.0), "two_planes": (0.58, 1.5, 4.0), "three_planes": (0.58, 2.57, 4.0)}
+
+
+def _plane_pair(w, h, scene):
+    """a camera 1 m in front of the room's far wall.  one_plane: only that wall is in view (point-to-plane ICP constrains 3 of
+    the 6 degrees of freedom, the normal equations have exact zero pivots); two_planes: a sliver of the left wall as well
+    (translation along the edge stays free, cond ~1e17); three_planes: plus one pixel row of floor (determinate, cond ~400)"""
+    from instancefusion_b200 import synth
+    K = synth.Intrinsics.kinect(w, h)
+    eye = PLANE_EYES[scene]
+    pose0 = synth.look_at(eye, (eye[0], eye[1], 5.0), 0.0)
+    pose1 = pose0 @ synth.exp_se3((0.004, -0.003, 0.006, 0.004, -0.003, 0.002))
+    f0 = synth.render(pose0, K, seed=5, frame_id=0)
+    f1 = synth.render(pose1, K, seed=5, frame_id=1)
+    to_np = lambda f: {"depth": util.u16(f["depth"]), "rgba": f["rgba"].numpy(), "vmap": f["vmap"].numpy(), "nmap": f["nmap"].numpy()}
+    return K, pose0.numpy(), to_np(f0), to_np(f1)
+
+
+@pytest.mark.parametrize("scene", ["three_planes", "two_planes", "one_plane"])
+def test_degenerate_geometry_icp_only(scene):
+    """Ill-conditioned normal equations (round-1 advisor finding): ICP only on (nearly) a plane.  Device mode eliminates
+    without pivoting on the fast path and switches to the host mode's / Eigen's symmetric-pivoted LDL^T when a pivot falls
+    below 1e-10 of the largest diagonal.  three_planes is poorly conditioned but determinate: device, host and reference
+    agree to BASELINE's tolerance.  With fewer planes some directions are undetermined and what comes out along them is
+    rounding noise amplified by the null space -- in the reference too: there the three must stay finite and agree along
+    the directions that ARE determined (camera x = the left wall's normal, camera z = the far wall's)."""
+    w, h = 320, 240
+    K, pose0, f0, f1 = _plane_pair(w, h, scene)
+    pose0f = pose0.astype(np.float32)
+    m = dict(rgbOnly=False, icpWeight=100.0, pyramid=True, fastOdom=False, so3=False)
+    dev = ef.RGBDOdometry(w, h, K.cx, K.cy, K.fx, K.fy, solve_mode=RO.EF_SOLVE_DEVICE)
+    host = ef.RGBDOdometry(w, h, K.cx, K.cy, K.fx, K.fy, solve_mode=RO.EF_SOLVE_HOST)
+    ref = O.OracleTracker(w, h, K.cx, K.cy, K.fx, K.fy, impl="ref")
+    try:
+        for tr in (dev, host, ref):
+            _feed(tr, pose0f, f0, f1)
+        td, Rd = dev.getIncrementalTransformation(pose0f[:3, 3], pose0f[:3, :3], **m)
+        th, Rh = host.getIncrementalTransformation(pose0f[:3, 3], pose0f[:3, :3], **m)
+        tr_, Rr, st = ref.get_incremental_transformation(pose0f[:3, 3], pose0f[:3, :3], **KW(m))
+        for x in (td, Rd, th, Rh, tr_, Rr):
+            assert np.all(np.isfinite(x)), scene
+        assert dev.lastICPCount == pytest.approx(st["last_icp_count"], rel=1e-3) and host.lastICPCount == pytest.approx(st["last_icp_count"], rel=1e-3)
+        if scene == "three_planes":
+            assert np.linalg.cond(st["last_A"]) > 100
+            assert float(np.abs(td - tr_).max()) <= 1e-5 and util.rot_err(Rd, Rr) <= 1e-5, (td, tr_)
+            assert float(np.abs(th - tr_).max()) <= 1e-5 and util.rot_err(Rh, Rr) <= 1e-5, (th, tr_)
+        else:
+            axes = [pose0[:3, 2]] + ([pose0[:3, 0]] if scene == "two_planes" else [])
+            for a in axes:
+                assert abs(float((td - tr_) @ a)) <= 1e-4 and abs(float((th - tr_) @ a)) <= 1e-4, (scene, td, th, tr_)
+    finally:
+        dev.close()
+        host.close()
+        ref.close()

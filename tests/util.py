@@ -1,6 +1,7 @@
 """Shared test inputs: seeded synthetic frames (instancefusion_b200.synth) and adversarial images."""
 from __future__ import annotations
 
+import ctypes
 import functools
 import math
 
@@ -99,3 +100,115 @@ def rot_err(Ra, Rb):
 def se3_level_params(K, level):
     d = np.float32(1 << level)
     return (np.float32(K.fx) / d, np.float32(K.fy) / d, np.float32(K.cx) / d, np.float32(K.cy) / d)
+
+
+# ------------------------------------------------------------------------------------------------
+# the reference's real-data fixture (elasticfusionpublic/GPUTest/{1c,1d,2c,2d}.png, decoded by
+# tests/golden/make_gputest_fixture.py) turned into tracker inputs the way GPUTest.cpp does
+# ------------------------------------------------------------------------------------------------
+@functools.lru_cache(maxsize=1)
+def gputest_inputs():
+    """(K, f0, f1): f0 = model maps + colour from frame 1 (loadVertices / loadImage, GPUTest.cpp:62-130, :30-40),
+    f1 = depth in millimetres + colour of frame 2 (loadDepth: raw / 5, :42-60).  K = 528, 528, 320, 240 (:150-152)."""
+    import os
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "gputest_pair.npz"))
+    K = synth.Intrinsics(640, 480, 528.0, 528.0, 320.0, 240.0)
+    d1 = z["depth1_raw"]
+    f32 = np.float32
+    depth = d1.astype(f32) / f32(5000.0)
+    rows, cols = np.meshgrid(np.arange(480, dtype=f32), np.arange(640, dtype=f32), indexing="ij")
+    inv_fx, inv_fy = f32(1.0) / f32(K.fx), f32(1.0) / f32(K.fy)
+    vx = (cols - f32(K.cx)) * depth * inv_fx  # getVertex, :62-67 (float arithmetic)
+    vy = (rows - f32(K.cy)) * depth * inv_fy
+    V = np.stack([vx, vy, depth], axis=-1).astype(f32)
+    ok = np.zeros((480, 640), bool)
+    c = d1 > 0
+    ok[1:-1, 1:-1] = c[1:-1, 1:-1] & c[2:, 1:-1] & c[1:-1, 2:] & c[:-2, 1:-1] & c[1:-1, :-2]  # :86-90
+    del_x = np.zeros_like(V)
+    del_y = np.zeros_like(V)
+    del_x[:, :-1] = V[:, 1:] - V[:, :-1]
+    del_y[:-1, :] = V[1:, :] - V[:-1, :]
+    n = np.cross(del_x, del_y).astype(f32)
+    nn = np.sqrt((n * n).sum(-1, dtype=f32)).astype(f32)
+    n = (n / np.where(nn > 0, nn, f32(1))[..., None]).astype(f32)
+    vmap = np.zeros((480, 640, 4), f32)
+    nmap = np.zeros((480, 640, 4), f32)
+    vmap[..., 3] = 1
+    nmap[..., 3] = 1
+    vmap[..., :3] = np.where(ok[..., None], V, 0)
+    nmap[..., :3] = np.where(ok[..., None], n, 0)
+    # (the border row / column of GPUTest's Img buffers is never written; zeros = "no data" here)
+    vmap[0], vmap[-1], vmap[:, 0], vmap[:, -1] = 0, 0, 0, 0
+    nmap[0], nmap[-1], nmap[:, 0], nmap[:, -1] = 0, 0, 0, 0
+
+    def rgba(rgb):
+        out = np.full((480, 640, 4), 255, np.uint8)  # GL_RGB upload into an RGBA texture: alpha = 1
+        out[..., :3] = rgb
+        return out
+
+    f0 = {"vmap": vmap, "nmap": nmap, "rgba": rgba(z["rgb1"]), "depth": (d1 // 5).astype(np.uint16)}
+    f1 = {"depth": (z["depth2_raw"] // 5).astype(np.uint16), "rgba": rgba(z["rgb2"])}
+    return K, f0, f1
+
+
+# ------------------------------------------------------------------------------------------------
+# cudaArray inputs (what a GL-interop caller hands to the *_array entry points): CUDA runtime through ctypes
+# ------------------------------------------------------------------------------------------------
+class _ChannelDesc(ctypes.Structure):  # cudaChannelFormatDesc
+    _fields_ = [("x", ctypes.c_int), ("y", ctypes.c_int), ("z", ctypes.c_int), ("w", ctypes.c_int), ("f", ctypes.c_int)]
+
+
+@functools.lru_cache(maxsize=1)
+def _cudart():
+    import ctypes as C
+    import glob
+    import os
+    import torch
+    cands = glob.glob(os.path.join(os.path.dirname(os.path.dirname(torch.__file__)), "nvidia", "cuda_runtime", "lib", "libcudart.so*"))
+    cands += ["/usr/local/cuda/lib64/libcudart.so", "libcudart.so.12", "libcudart.so"]
+    for c in cands:
+        try:
+            return C.CDLL(c)
+        except OSError:
+            continue
+    raise RuntimeError("libcudart not found")
+
+
+class CudaArray:
+    """a 2-D cudaArray holding a host image: kind in {"u16", "rgba8", "rgba32f"} (the three texture formats the
+    tracker is fed with, GPUTexture / RGBDOdometry.cpp:120-128)."""
+    FORMATS = {"u16": ((16, 0, 0, 0, 1), np.uint16, 1), "rgba8": ((8, 8, 8, 8, 1), np.uint8, 4), "rgba32f": ((32, 32, 32, 32, 2), np.float32, 4)}
+
+    def __init__(self, host, kind):
+        import ctypes as C
+        bits, dt, ch = self.FORMATS[kind]
+        a = np.ascontiguousarray(host, dt)
+        h, w = a.shape[0], a.shape[1]
+        assert a.size == h * w * ch
+        rt = _cudart()
+        desc = _ChannelDesc(*bits)
+        self.arr = C.c_void_p()
+        rc = rt.cudaMallocArray(C.byref(self.arr), C.byref(desc), C.c_size_t(w), C.c_size_t(h), C.c_uint(0))
+        assert rc == 0, ("cudaMallocArray", rc)
+        row = w * ch * a.itemsize
+        rc = rt.cudaMemcpy2DToArray(self.arr, C.c_size_t(0), C.c_size_t(0), a.ctypes.data_as(C.c_void_p), C.c_size_t(row), C.c_size_t(row),
+                                    C.c_size_t(h), C.c_int(1))  # cudaMemcpyHostToDevice
+        assert rc == 0, ("cudaMemcpy2DToArray", rc)
+        rc = rt.cudaDeviceSynchronize()
+        assert rc == 0
+
+    @property
+    def cuda_array_handle(self):
+        """the cudaArray_t as an integer: what instancefusion_b200.RGBDOdometry routes to the *_array entry points"""
+        return self.arr.value
+
+    def free(self):
+        if self.arr:
+            _cudart().cudaFreeArray(self.arr)
+            self.arr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
