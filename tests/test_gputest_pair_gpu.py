@@ -47,7 +47,8 @@ def test_gputest_png_pair_matches_reference_cuda(solve_mode):
     w, h = 640, 480
     pose = np.eye(4, dtype=np.float32)  # GPUTest.cpp:213 currPose = Identity
     prod = ef.RGBDOdometry(w, h, K.cx, K.cy, K.fx, K.fy, solve_mode=solve_mode)
-    ref = O.OracleTracker(w, h, K.cx, K.cy, K.fx, K.fy, impl="ref")
+    ens = util.RefEnsemble(w, h, K)  # the reference at GPUConfig's defaults + at other launch shapes (its own spread)
+    ref = ens.ref
     try:
         _feed(prod, pose, f0, f1)
         _feed(ref, pose, f0, f1)
@@ -61,14 +62,14 @@ def test_gputest_png_pair_matches_reference_cuda(solve_mode):
                 assert int(util.ulp_diff(prod.buffer(name, lvl), ref.buffer(name, lvl)).max()) <= 1, (name, lvl)
         for name, m in MODES.items():
             _feed(prod, pose, f0, f1)
-            _feed(ref, pose, f0, f1)
+            ens.each(lambda r: _feed(r, pose, f0, f1))
             t, R = prod.getIncrementalTransformation(pose[:3, 3], pose[:3, :3], **m)
-            tr, Rr, st = ref.get_incremental_transformation(pose[:3, 3], pose[:3, :3], **_kw(m))
+            tr, Rr, st, spread = ens.track(pose[:3, 3], pose[:3, :3], **_kw(m))
             dt, dr = float(np.abs(t - tr).max()), util.rot_err(R, Rr)
-            # RGB-only on a real, noisy pair stops on the rising-error rule after a few iterations and is the one mode whose
-            # result the reference's own launch shape moves by more than 1e-5 (float sums, see test_tracker_edge_gpu.py)
-            tol = 1e-4 if m["rgbOnly"] else 1e-5
-            assert dt <= tol and dr <= tol, (name, dt, dr)
+            # BASELINE's 1e-5, or twice what the reference moves against itself on this real, noisy pair when only its launch
+            # shape changes (float sums in a different order; measured 1e-5 .. 3e-5 in the no-pyramid and RGB-only modes)
+            assert dt <= max(1e-5, 2 * spread["t"]) and dr <= max(1e-5, 2 * spread["r"]), (name, dt, dr, spread)
+            print(f"\n[gputest pair {name}] |dt| {dt:.1e} m, rotation {dr:.1e} rad (reference vs itself: {spread['t']:.1e} / {spread['r']:.1e})")
             assert prod.se3_iterations == st["se3_iterations"] and prod.so3_iterations == st["so3_iterations"], name
             if not m["rgbOnly"]:
                 assert abs(prod.lastICPCount - st["last_icp_count"]) <= 1e-4 * st["last_icp_count"], name
@@ -79,13 +80,13 @@ def test_gputest_png_pair_matches_reference_cuda(solve_mode):
                     assert np.array_equal(prod.buffer("dIdx", lvl), ref.buffer("dIdx", lvl))
                     assert np.array_equal(prod.buffer("dIdy", lvl), ref.buffer("dIdy", lvl))
             Ar = st["last_A"]
-            assert np.linalg.norm(prod.lastA - Ar) <= 1e-4 * np.linalg.norm(Ar), (name, np.linalg.norm(prod.lastA - Ar) / np.linalg.norm(Ar))
+            assert np.linalg.norm(prod.lastA - Ar) <= max(1e-4, 2 * spread["A"]) * np.linalg.norm(Ar), (name, np.linalg.norm(prod.lastA - Ar) / np.linalg.norm(Ar), spread)
             # the frames are ~3 cm / ~1 degree apart: the tracker must have moved
             if name in ("joint", "icp_only", "joint_so3"):
                 assert 0.003 < float(np.linalg.norm(t)) < 0.2, (name, t)
     finally:
         prod.close()
-        ref.close()
+        ens.close()
 
 
 def test_gputest_pair_single_call_and_arrays():

@@ -70,10 +70,11 @@ def test_tracker_matches_reference_cuda(size, solve_mode):
     f1 = dict(f1, depth=util.punch_holes(f1["depth"]))
     pose0f = pose0.astype(np.float32)
     prod = ef.RGBDOdometry(w, h, K.cx, K.cy, K.fx, K.fy, solve_mode=solve_mode)
-    ref = O.OracleTracker(w, h, K.cx, K.cy, K.fx, K.fy, impl="ref")
+    ens = util.RefEnsemble(w, h, K)  # the reference at GPUConfig's default launch shapes + its spread over other shapes
+    ref = ens.ref
     try:
         _feed(prod, pose0f, f0, f1)
-        _feed(ref, pose0f, f0, f1)
+        ens.each(lambda r: _feed(r, pose0f, f0, f1))
         _pyramids_match(prod, ref, h)
         # 80x60 is the fern relocaliser's resolution: its coarse levels (20x15) carry no usable signal, so only
         # the call Ferns actually makes is a meaningful parity case there
@@ -83,9 +84,9 @@ def test_tracker_matches_reference_cuda(size, solve_mode):
             if name != names[0]:
                 # so3 swaps next/lastNext images at the end of a call: re-feed so both start equal
                 _feed(prod, pose0f, f0, f1)
-                _feed(ref, pose0f, f0, f1)
+                ens.each(lambda r: _feed(r, pose0f, f0, f1))
             t, R = prod.getIncrementalTransformation(pose0f[:3, 3], pose0f[:3, :3], **m)
-            tr, Rr, st = ref.get_incremental_transformation(pose0f[:3, 3], pose0f[:3, :3], **_kw(m))
+            tr, Rr, st, spread = ens.track(pose0f[:3, 3], pose0f[:3, :3], **_kw(m))
             dt = float(np.abs(t - tr).max())
             dr = util.rot_err(R, Rr)
             assert dt <= POSE_TOL_M and dr <= POSE_TOL_RAD, (name, size, dt, dr)
@@ -102,13 +103,18 @@ def test_tracker_matches_reference_cuda(size, solve_mode):
                     assert np.array_equal(prod.buffer("dIdy", lvl), ref.buffer("dIdy", lvl))
             if m["so3"]:
                 assert prod.lastSO3Count == st["last_so3_count"], name
-            A, Ar = prod.lastA, st["last_A"]
-            assert np.linalg.norm(A - Ar) <= 1e-3 * np.linalg.norm(Ar), name
+            # JtJ | Jtr of the last evaluation: BASELINE's 1e-4 norm-relative (or the reference's own launch-shape spread where
+            # that is larger); Jtr vanishes at convergence, so it is measured against what a pose difference within the pose
+            # tolerance moves it by (A d)
+            A, Ar, b, br = prod.lastA, st["last_A"], prod.lastb, st["last_b"]
+            assert np.linalg.norm(A - Ar) <= max(1e-4, 2 * spread["A"]) * np.linalg.norm(Ar), (name, np.linalg.norm(A - Ar) / np.linalg.norm(Ar), spread)
+            tol_b = 1e-4 * np.linalg.norm(br) + max(1e-5, 2 * spread["t"], 2 * spread["r"]) * np.linalg.norm(Ar, 2) + 2 * spread["b"]
+            assert np.linalg.norm(b - br) <= tol_b, (name, np.linalg.norm(b - br), tol_b)
             cov = prod.getCovariance()
             assert np.allclose(cov @ prod.lastA, np.eye(6), atol=1e-6)
     finally:
         prod.close()
-        ref.close()
+        ens.close()
 
 
 @pytest.mark.parametrize("solve_mode", [RO.EF_SOLVE_HOST, RO.EF_SOLVE_DEVICE])
