@@ -174,8 +174,10 @@ int ef_get_incremental_transformation_finish(ef_tracker * t, float * trans3, flo
 /* The frameToModel call sequence of ElasticFusion::processFrame (ElasticFusion.cpp:343-368) as one call:
  *   initICPModel(vertices, normals, depth_cutoff, pose) ; initRGBModel(model_rgba8) ; initICP(depth, depth_cutoff) ;
  *   initRGB(rgba8) ; getIncrementalTransformation(trans = pose.t, rot = pose.R, ...)
- * `on_host` selects host pointers (dense rows, ideally pinned) or device pointers (dense rows) for all five
- * images.  Same results as the five separate calls; it only saves call overhead for FFI callers. */
+ * `on_host`: 0 = all five images are device pointers, 1 = all are host pointers (dense rows, ideally pinned),
+ * 2 = the SENSOR frame (depth, rgba8) is on the host and the MODEL maps (vertices, normals, model_rgba8) are device
+ * pointers -- the production data flow: the model prediction lives on the GPU (GL textures in the reference,
+ * ef_op_splat_predict here) and only the 1.8 MB sensor frame crosses PCIe.  Same results as the five separate calls. */
 typedef struct ef_frame_inputs
 {
     const float * vertices_rgba32f;
@@ -206,6 +208,12 @@ long long ef_tracker_launch_count(const ef_tracker * t);
  * getIncrementalTransformation -- the persistent tracker kernel in EF_SOLVE_DEVICE, the whole step loop in
  * EF_SOLVE_HOST -- accumulated over `calls` calls since the last read; reading resets the accumulator. */
 int ef_tracker_profile(ef_tracker * t, double * solve_ms_total, long long * calls);
+/* Per-iteration trace of the persistent tracker kernel, for handles created with EF_TRACK_TIMING=1 in the environment (the
+ * kernel then stamps clock64 at its phase boundaries; EF_TRACK_TIMING_PRINT=1 also prints the phase table when the handle
+ * is destroyed): cycles32[i] = SM clock of the solver CTA at the top of Gauss-Newton iteration i (in launch order: level 2
+ * first), relative to the kernel's start and summed over `calls` calls; cycles32[31] = the kernel's end.  EF_ERR_BAD_STATE
+ * without EF_TRACK_TIMING.  bench.py derives the per-pyramid-level share of a launch from it. */
+int ef_tracker_trace(ef_tracker * t, double * cycles32, long long * calls);
 
 /* ------------------------------------------------------------------------------------------ */
 /* Tier 2: per-operator entry points (Cuda/cudafuncs.cuh:64-177).  All asynchronous on `stream`  */

@@ -454,6 +454,12 @@ EF_API int ef_tracker_profile(ef_tracker * t, double * ms, long long * calls)
     return EF_OK;
 }
 
+EF_API int ef_tracker_trace(ef_tracker * t, double * cycles32, long long * calls)
+{
+    if(!t || !cycles32 || !calls) return EF_ERR_INVALID_ARGUMENT;
+    return device_track_trace(t, cycles32, calls);
+}
+
 EF_API int ef_tracker_wait_event(ef_tracker * t, void * cuda_event)
 {
     if(!t || !cuda_event) return EF_ERR_INVALID_ARGUMENT;
@@ -1377,11 +1383,16 @@ EF_API int ef_track_frame_to_model_launch(ef_tracker * t, const ef_frame_inputs 
         if(rc_flush) return rc_flush;
     }
     int rc = EF_OK;
+    if(in->on_host < 0 || in->on_host > 2) return fail(t, EF_ERR_INVALID_ARGUMENT, "ef_frame_inputs.on_host must be 0, 1 or 2");
+    const bool host_model = in->on_host == 1, host_sensor = in->on_host >= 1;
     // (k_build_frame reads its inputs with 8- and 16-byte loads: device inputs that are not 16-byte aligned take the chained builders)
-    const bool aligned = in->on_host || (((reinterpret_cast<uintptr_t>(in->vertices_rgba32f) | reinterpret_cast<uintptr_t>(in->normals_rgba32f) |
-                                           reinterpret_cast<uintptr_t>(in->model_rgba8) | reinterpret_cast<uintptr_t>(in->depth) |
-                                           reinterpret_cast<uintptr_t>(in->rgba8)) & 15) == 0);
-    if(t->fused_build && aligned && (in->on_host ? t->frame_build == 2 : t->frame_build >= 1))
+    uintptr_t dev_bits = 0;
+    if(!host_model)
+        dev_bits |= reinterpret_cast<uintptr_t>(in->vertices_rgba32f) | reinterpret_cast<uintptr_t>(in->normals_rgba32f) |
+                    reinterpret_cast<uintptr_t>(in->model_rgba8);
+    if(!host_sensor) dev_bits |= reinterpret_cast<uintptr_t>(in->depth) | reinterpret_cast<uintptr_t>(in->rgba8);
+    const bool aligned = (dev_bits & 15) == 0;
+    if(t->fused_build && aligned && (host_sensor ? t->frame_build == 2 : t->frame_build >= 1))
     {
         // k_build_frame (ef_build_fused.cu): all five inputs are known at once, so every pyramid of the frame comes from
         // one launch -- no chained kernels, no stream forks and joins; the tracker kernel follows on the same stream.
@@ -1392,21 +1403,25 @@ EF_API int ef_track_frame_to_model_launch(ef_tracker * t, const ef_frame_inputs 
         const uint8_t * mrgba = static_cast<const uint8_t *>(in->model_rgba8);
         const uint16_t * depth = static_cast<const uint16_t *>(in->depth);
         const uint8_t * rgba = static_cast<const uint8_t *>(in->rgba8);
-        if(in->on_host)
+        const size_t n = t->dims[0].n();
+        // (join_streams above: no builder of an earlier call still reads a staging buffer)
+        if(host_model)
         {
-            const size_t n = t->dims[0].n();
-            // (join_streams above: no builder of an earlier call still reads a staging buffer)
             EF_CUDA(t, cudaMemcpyAsync(t->stage_v, v4, n * 16, cudaMemcpyHostToDevice, t->stream));
             EF_CUDA(t, cudaMemcpyAsync(t->stage_n, n4, n * 16, cudaMemcpyHostToDevice, t->stream));
             EF_CUDA(t, cudaMemcpyAsync(t->stage_rgba_model, mrgba, n * 4, cudaMemcpyHostToDevice, t->stream));
+            v4 = t->stage_v; n4 = t->stage_n; mrgba = t->stage_rgba_model;
+        }
+        if(host_sensor)
+        {
             EF_CUDA(t, cudaMemcpyAsync(t->stage_depth, depth, n * 2, cudaMemcpyHostToDevice, t->stream));
             EF_CUDA(t, cudaMemcpyAsync(t->stage_rgba, rgba, n * 4, cudaMemcpyHostToDevice, t->stream));
-            v4 = t->stage_v; n4 = t->stage_n; mrgba = t->stage_rgba_model; depth = t->stage_depth; rgba = t->stage_rgba;
+            depth = t->stage_depth; rgba = t->stage_rgba;
         }
         rc = build_frame(t, v4, n4, mrgba, depth, rgba, pose, in->depth_cutoff);
         if(rc) return rc;
     }
-    else if(t->fused_build && t->aux_streams && !in->on_host)
+    else if(t->fused_build && t->aux_streams && in->on_host == 0)
     {
         // (Host inputs keep the five-call order below: there the copies are the bound, and builders that trickle in between
         // them delay the cooperative launches of the OTHER handles taking turns on the GPU -- measured 3 640 -> 3 040 frames/s.)
@@ -1455,21 +1470,18 @@ EF_API int ef_track_frame_to_model_launch(ef_tracker * t, const ef_frame_inputs 
             }
         }
     }
-    else if(in->on_host)
-    {
-        rc = ef_init_icp_model_host(t, static_cast<const float *>(in->vertices_rgba32f), static_cast<const float *>(in->normals_rgba32f),
-                                    in->depth_cutoff, pose);
-        if(!rc) rc = ef_init_rgb_model_host(t, static_cast<const uint8_t *>(in->model_rgba8));
-        if(!rc) rc = ef_init_icp_depth_host(t, static_cast<const uint16_t *>(in->depth), in->depth_cutoff);
-        if(!rc) rc = ef_init_rgb_host(t, static_cast<const uint8_t *>(in->rgba8));
-    }
     else
     {
-        rc = ef_init_icp_model(t, static_cast<const float *>(in->vertices_rgba32f), static_cast<const float *>(in->normals_rgba32f),
-                               in->depth_cutoff, pose);
-        if(!rc) rc = ef_init_rgb_model(t, static_cast<const uint8_t *>(in->model_rgba8), 0);
-        if(!rc) rc = ef_init_icp_depth(t, static_cast<const uint16_t *>(in->depth), 0, in->depth_cutoff);
-        if(!rc) rc = ef_init_rgb(t, static_cast<const uint8_t *>(in->rgba8), 0);
+        // the five calls, each through its host or device entry
+        const float * v4 = static_cast<const float *>(in->vertices_rgba32f);
+        const float * n4 = static_cast<const float *>(in->normals_rgba32f);
+        const uint8_t * mrgba = static_cast<const uint8_t *>(in->model_rgba8);
+        const uint16_t * depth = static_cast<const uint16_t *>(in->depth);
+        const uint8_t * rgba = static_cast<const uint8_t *>(in->rgba8);
+        rc = host_model ? ef_init_icp_model_host(t, v4, n4, in->depth_cutoff, pose) : ef_init_icp_model(t, v4, n4, in->depth_cutoff, pose);
+        if(!rc) rc = host_model ? ef_init_rgb_model_host(t, mrgba) : ef_init_rgb_model(t, mrgba, 0);
+        if(!rc) rc = host_sensor ? ef_init_icp_depth_host(t, depth, in->depth_cutoff) : ef_init_icp_depth(t, depth, 0, in->depth_cutoff);
+        if(!rc) rc = host_sensor ? ef_init_rgb_host(t, rgba) : ef_init_rgb(t, rgba, 0);
     }
     if(rc) return rc;
     const float trans[3] = {pose[3], pose[7], pose[11]};

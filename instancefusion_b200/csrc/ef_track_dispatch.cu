@@ -12,6 +12,7 @@ namespace ef
     int device_track_init_t##T(ef_tracker * t);                                                                                            \
     int device_track_configure_t##T(ef_tracker * t, int grid_ctas);                                                                        \
     bool device_track_supported_t##T(const ef_tracker * t);                                                                                \
+    int device_track_trace_t##T(ef_tracker * t, double * out32, long long * calls);                                                                                \
     void device_track_destroy_t##T(ef_tracker * t);                                                                                        \
     int device_track_launch_t##T(ef_tracker * t, const float * trans, const float * rot, int rgb_only, float icp_weight, int pyramid,     \
                                  int fast_odom, int so3);                                                                                  \
@@ -36,6 +37,10 @@ int device_track_init(ef_tracker * t)
 int device_track_configure(ef_tracker * t, int grid_ctas)
 {
     return t->track_variant == 384 ? device_track_configure_t384(t, grid_ctas) : device_track_configure_t256(t, grid_ctas);
+}
+int device_track_trace(ef_tracker * t, double * out32, long long * calls)
+{
+    return t->track_variant == 384 ? device_track_trace_t384(t, out32, calls) : device_track_trace_t256(t, out32, calls);
 }
 bool device_track_supported(const ef_tracker * t)
 {

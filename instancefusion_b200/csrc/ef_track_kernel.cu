@@ -53,6 +53,7 @@ namespace ef
 {
 
 void EF_TRACK_FN(device_track_destroy)(ef_tracker * t);
+int EF_TRACK_FN(device_track_trace)(ef_tracker * t, double * out32, long long * calls);
 int EF_TRACK_FN(device_track_configure)(ef_tracker * t, int grid);
 bool EF_TRACK_FN(device_track_supported)(const ef_tracker * t);
 
@@ -1071,6 +1072,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_track(const __grid_constant__ T
             if(threadIdx.x == 0 && dbg_it < kMaxIters) A.dbg[((size_t)blockIdx.x * kMaxIters + dbg_it) * kDbgStamps + k] = clock64();
         }
     };
+    // kernel start / end of CTA 0 live in the two last iteration slots (a call runs at most 19 SE3 iterations)
+    if constexpr(TIMING)
+    {
+        if(is_solver) A.dbg[(size_t)(kMaxIters - 2) * kDbgStamps] = clock64();
+    }
 
     // ============================================================================================
     // SO(3) pre-alignment: RGBDOdometry.cpp:294-382 (level 2, at most 10 so3Step evaluations)
@@ -1546,6 +1552,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_track(const __grid_constant__ T
         // the host polls `status` in pinned memory (device_track_finish): result first, fence, then the flag.
         // 2 = no solve ran: lastA / lastb keep their previous values (host side)
         const int status = (S->se3_iterations[0] + S->se3_iterations[1] + S->se3_iterations[2] > 0) ? 1 : 2;
+        if constexpr(TIMING) A.dbg[(size_t)(kMaxIters - 1) * kDbgStamps] = clock64();
         __threadfence_system();
         *reinterpret_cast<volatile int *>(&out->status) = status;
         __threadfence_system();
@@ -1676,17 +1683,30 @@ int EF_TRACK_FN(device_track_init)(ef_tracker * t)
     return EF_OK;
 }
 
+// EF_TRACK_TIMING=1: where CTA 0's clock stood at the top of every SE3 iteration, relative to the kernel's start, summed
+// over the calls so far: out[i] for iteration i (0 where the iteration did not run), out[kMaxIters - 1] = kernel end
+int EF_TRACK_FN(device_track_trace)(ef_tracker * t, double * out32, long long * calls)
+{
+    DeviceTrack * d = static_cast<DeviceTrack *>(t->track_state);
+    if(!d || !d->dbg) return EF_ERR_BAD_STATE;
+    const double start = d->dbg_acc[kMaxIters - 2][0];
+    for(int it = 0; it < kMaxIters; it++) out32[it] = d->dbg_acc[it][0] > 0 ? d->dbg_acc[it][0] - start : 0.0;
+    out32[kMaxIters - 2] = 0.0;
+    *calls = d->dbg_n;
+    return EF_OK;
+}
+
 void EF_TRACK_FN(device_track_destroy)(ef_tracker * t)
 {
     DeviceTrack * d = static_cast<DeviceTrack *>(t->track_state);
     if(!d) return;
     if(d->dbg)
     {
-        if(d->dbg_n > 0)
+        if(d->dbg_n > 0 && getenv("EF_TRACK_TIMING_PRINT"))
         {
             // stamps (cycles of CTA 0's SM): 0 loop top | 2 rows gathered + added | 3 solved | 1 parameters published | 6 barrier B seen
             fprintf(stderr, "[ef_track timing] avg cycles of CTA 0 per SE3 iteration over %lld calls\n", d->dbg_n);
-            for(int it = 0; it < kMaxIters; it++)
+            for(int it = 0; it < kMaxIters - 2; it++)
             {
                 const double * a = d->dbg_acc[it];
                 if(a[1] == 0) continue;
@@ -1700,7 +1720,7 @@ void EF_TRACK_FN(device_track_destroy)(ef_tracker * t)
             // worker CTAs: params wait (0->4) | photometric association + CTA sync (4->5) | ICP + warp reduce (5->8) |
             // barrier-B wait (8->6) | photometric rows + CTA reduce + publish (6->9)
             fprintf(stderr, "[ef_track timing] worker CTAs, cycles mean/max over workers\n");
-            for(int it = 0; it < kMaxIters; it++)
+            for(int it = 0; it < kMaxIters - 2; it++)
             {
                 if(d->dbg_acc[it][1] == 0) continue;
                 const double n = (double)d->dbg_n;

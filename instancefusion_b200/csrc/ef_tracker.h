@@ -122,6 +122,7 @@ namespace ef
 // EF_SOLVE_DEVICE path (ef_track_kernel.cu)
 int device_track_init(ef_tracker * t);
 int device_track_configure(ef_tracker * t, int grid_ctas);
+int device_track_trace(ef_tracker * t, double * out32, long long * calls);
 bool device_track_supported(const ef_tracker * t); // the image fits the persistent kernel's shared-memory candidate store
 void device_track_destroy(ef_tracker * t);
 int device_track_launch(ef_tracker * t, const float * trans, const float * rot, int rgb_only, float icp_weight, int pyramid, int fast_odom,

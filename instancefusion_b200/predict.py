@@ -31,7 +31,9 @@ class ModelPredictor:
         self.filled_image = torch.empty_like(self.image)
 
     def _stream(self):
-        return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        return C.c_void_p(self.stream if self.stream is not None else torch.cuda.current_stream().cuda_stream)
+
+    stream = None  # a cudaStream_t (int) to run on, e.g. RGBDOdometry.stream; None = torch's current stream
 
     def predict(self, surfels: torch.Tensor, pose, time, maxTime=None, timeDelta=200, maxDepth=20.0, confThreshold=10.0):
         """IndexMap::combinedPredict(pose, model, depthCutoff, confThreshold, time, maxTime, timeDelta, ACTIVE)"""

@@ -259,11 +259,15 @@ class RGBDOdometry:
     # -- ElasticFusion::processFrame's frameToModel sequence (ElasticFusion.cpp:343-368) in one C call ---------
     def _frame_inputs(self, vertices, normals, model_rgba, depth, rgba, depthCutoff):
         from .binding import FrameInputs
-        on_host = not _is_cuda_tensor(vertices)
-        if on_host:
-            ptr = lambda a: a.data_ptr() if hasattr(a, "data_ptr") else a.ctypes.data
-        else:
-            ptr = lambda a: a.data_ptr()
+        # 0: all device, 1: all host, 2: model maps on the device, sensor frame (depth, rgba) on the host
+        model_dev, sensor_dev = _is_cuda_tensor(vertices), _is_cuda_tensor(depth)
+        if model_dev and not (_is_cuda_tensor(normals) and _is_cuda_tensor(model_rgba)):
+            raise ValueError("vertices, normals and the model image must live on the same side")
+        if sensor_dev != _is_cuda_tensor(rgba) or (sensor_dev and not model_dev):
+            raise ValueError("supported: all device, all host, or model maps on the device with the sensor frame on the host")
+        on_host = 0 if sensor_dev else (2 if model_dev else 1)
+        ptr = lambda a: a.data_ptr() if hasattr(a, "data_ptr") else a.ctypes.data
+        if model_dev:
             self._borrow()
         self._keep_frame = (vertices, normals, model_rgba, depth, rgba)
         fi = self._frame
