@@ -95,7 +95,7 @@ def test_shim_class_tracks_like_the_reference_and_like_the_python_mirror():
             ens.each(feed)
             tr, Rr, st, spread = ens.track(p[:3, 3], p[:3, :3], rgb_only=False, icp_weight=10.0, pyramid=True, fast_odom=False, so3=True)
             dt, dr = float(np.abs(t - tr).max()), util.rot_err(R.reshape(3, 3), Rr)
-            assert dt <= max(1e-5, 2 * spread["t"]) and dr <= max(1e-5, 2 * spread["r"]), (k, dt, dr, spread)
+            assert dt <= max(1e-5, util.RefEnsemble.K * spread["t"]) and dr <= max(1e-5, util.RefEnsemble.K * spread["r"]), (k, dt, dr, spread)
             assert st6[5] == st["last_so3_count"]
     finally:
         L.efc_shim_destroy(shim)

@@ -66,13 +66,13 @@ def test_gputest_png_pair_matches_reference_cuda(solve_mode):
             t, R = prod.getIncrementalTransformation(pose[:3, 3], pose[:3, :3], **m)
             tr, Rr, st, spread = ens.track(pose[:3, 3], pose[:3, :3], **_kw(m))
             dt, dr = float(np.abs(t - tr).max()), util.rot_err(R, Rr)
-            # BASELINE's 1e-5, or twice what the reference moves against itself on this real, noisy pair when only its launch
+            # BASELINE's 1e-5, or K times what the reference moves against itself on this real, noisy pair when only its launch
             # shape changes (float sums in a different order; measured 1e-5 .. 3e-5 in the no-pyramid and RGB-only modes)
-            assert dt <= max(1e-5, 2 * spread["t"]) and dr <= max(1e-5, 2 * spread["r"]), (name, dt, dr, spread)
+            assert dt <= max(1e-5, util.RefEnsemble.K * spread["t"]) and dr <= max(1e-5, util.RefEnsemble.K * spread["r"]), (name, dt, dr, spread)
             print(f"\n[gputest pair {name}] |dt| {dt:.1e} m, rotation {dr:.1e} rad (reference vs itself: {spread['t']:.1e} / {spread['r']:.1e})")
             assert prod.se3_iterations == st["se3_iterations"] and prod.so3_iterations == st["so3_iterations"], name
             if not m["rgbOnly"]:
-                assert abs(prod.lastICPCount - st["last_icp_count"]) <= 1e-4 * st["last_icp_count"], name
+                assert abs(prod.lastICPCount - st["last_icp_count"]) <= max(1e-4 * st["last_icp_count"], util.RefEnsemble.K * spread["icp"]), (name, spread)
             if m["so3"]:
                 assert prod.lastSO3Count == st["last_so3_count"], name
             if m["rgbOnly"] or m["icpWeight"] < 100:
@@ -80,7 +80,7 @@ def test_gputest_png_pair_matches_reference_cuda(solve_mode):
                     assert np.array_equal(prod.buffer("dIdx", lvl), ref.buffer("dIdx", lvl))
                     assert np.array_equal(prod.buffer("dIdy", lvl), ref.buffer("dIdy", lvl))
             Ar = st["last_A"]
-            assert np.linalg.norm(prod.lastA - Ar) <= max(1e-4, 2 * spread["A"]) * np.linalg.norm(Ar), (name, np.linalg.norm(prod.lastA - Ar) / np.linalg.norm(Ar), spread)
+            assert np.linalg.norm(prod.lastA - Ar) <= max(1e-4, util.RefEnsemble.K * spread["A"]) * np.linalg.norm(Ar), (name, np.linalg.norm(prod.lastA - Ar) / np.linalg.norm(Ar), spread)
             # the frames are ~3 cm / ~1 degree apart: the tracker must have moved
             if name in ("joint", "icp_only", "joint_so3"):
                 assert 0.003 < float(np.linalg.norm(t)) < 0.2, (name, t)

@@ -107,8 +107,8 @@ def test_tracker_matches_reference_cuda(size, solve_mode):
             # that is larger); Jtr vanishes at convergence, so it is measured against what a pose difference within the pose
             # tolerance moves it by (A d)
             A, Ar, b, br = prod.lastA, st["last_A"], prod.lastb, st["last_b"]
-            assert np.linalg.norm(A - Ar) <= max(1e-4, 2 * spread["A"]) * np.linalg.norm(Ar), (name, np.linalg.norm(A - Ar) / np.linalg.norm(Ar), spread)
-            tol_b = 1e-4 * np.linalg.norm(br) + max(1e-5, 2 * spread["t"], 2 * spread["r"]) * np.linalg.norm(Ar, 2) + 2 * spread["b"]
+            assert np.linalg.norm(A - Ar) <= max(1e-4, util.RefEnsemble.K * spread["A"]) * np.linalg.norm(Ar), (name, np.linalg.norm(A - Ar) / np.linalg.norm(Ar), spread)
+            tol_b = 1e-4 * np.linalg.norm(br) + max(1e-5, util.RefEnsemble.K * spread["t"], util.RefEnsemble.K * spread["r"]) * np.linalg.norm(Ar, 2) + util.RefEnsemble.K * spread["b"]
             assert np.linalg.norm(b - br) <= tol_b, (name, np.linalg.norm(b - br), tol_b)
             cov = prod.getCovariance()
             assert np.allclose(cov @ prod.lastA, np.eye(6), atol=1e-6)

@@ -225,7 +225,8 @@ class RefEnsemble:
     against ITSELF on single frames of BASELINE's trajectories while most frames stay below 2e-6.  A parity test can
     therefore ask for 1e-5 -- or, on the frames where the reference itself is not reproducible to 1e-5, for its own
     spread."""
-    ALT = ((256, 96), (96, 148), (512, 32))
+    ALT = ((256, 96), (96, 148), (512, 32), (128, 296), (64, 64), (384, 56))
+    K = 3.0  # bound = K x the spread seen over these shapes (a small sample: a lower bound of what the reference can do to itself)
 
     def __init__(self, w, h, K):
         from oracle import oracle as O
@@ -243,7 +244,7 @@ class RefEnsemble:
         outs = [r.get_incremental_transformation(trans, rot, **kw) for r in self.refs]
         t0, R0, st0 = outs[0]
         nA = float(np.linalg.norm(st0["last_A"]))
-        spread = {"t": 0.0, "r": 0.0, "A": 0.0, "b": 0.0, "icp": 0.0, "rgb": 0.0}
+        spread = {"t": 0.0, "r": 0.0, "A": 0.0, "b": 0.0, "icp": 0.0, "rgb": 0.0, "icp_err": 0.0}
         for t, R, st in outs[1:]:
             spread["t"] = max(spread["t"], float(np.abs(t - t0).max()))
             spread["r"] = max(spread["r"], rot_err(R, R0))
@@ -251,6 +252,8 @@ class RefEnsemble:
             spread["b"] = max(spread["b"], float(np.linalg.norm(st["last_b"] - st0["last_b"])))
             spread["icp"] = max(spread["icp"], abs(st["last_icp_count"] - st0["last_icp_count"]))
             spread["rgb"] = max(spread["rgb"], abs(st["last_rgb_count"] - st0["last_rgb_count"]))
+            if st0["last_icp_error"] > 0:
+                spread["icp_err"] = max(spread["icp_err"], abs(st["last_icp_error"] - st0["last_icp_error"]) / st0["last_icp_error"])
         return t0, R0, st0, spread
 
     def close(self):
