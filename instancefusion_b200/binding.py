@@ -72,7 +72,8 @@ EXPORTED = [
     "ef_init_icp_depth_host", "ef_init_icp_maps_host", "ef_init_icp_model_host", "ef_init_rgb_host", "ef_init_rgb_model_host",
     "ef_init_first_rgb_host",
     "ef_get_incremental_transformation", "ef_get_incremental_transformation_launch",
-    "ef_get_incremental_transformation_finish", "ef_track_frame_to_model_launch", "ef_track_frame_to_model", "ef_get_covariance", "ef_tracker_download", "ef_tracker_launch_count", "ef_tracker_profile", "ef_tracker_trace",
+    "ef_get_incremental_transformation_finish", "ef_track_frame_to_model_launch", "ef_track_frame_to_model", "ef_batch_width", "ef_track_frames_to_model_batch_launch",
+    "ef_track_frames_to_model_batch", "ef_get_covariance", "ef_tracker_download", "ef_tracker_launch_count", "ef_tracker_profile", "ef_tracker_trace",
     "ef_op_pyr_down_u16", "ef_op_create_vmap", "ef_op_create_nmap", "ef_op_transform_maps", "ef_op_copy_maps",
     "ef_op_resize_map", "ef_op_vertices_to_depth", "ef_op_pyr_down_gauss_f32", "ef_op_pyr_down_gauss_u8",
     "ef_op_bgr_to_intensity", "ef_op_depth_bilateral", "ef_op_depth_metric", "ef_op_derivative_images", "ef_op_project_point_cloud", "ef_op_icp_step",

@@ -1372,10 +1372,9 @@ static cudaStream_t fork_from_recorded(ef_tracker * t, int which)
     return t->aux[which];
 }
 
-EF_API int ef_track_frame_to_model_launch(ef_tracker * t, const ef_frame_inputs * in, const float * pose, int rgb_only, float icp_weight, int pyramid,
-                                          int fast_odom, int so3)
+// the four builders of a frameToModel frame (initICPModel, initRGBModel, initICP, initRGB) for inputs given all at once
+static int frame_build_all(ef_tracker * t, const ef_frame_inputs * in, const float * pose)
 {
-    EF_ON_DEVICE(t);
     if(!t || !in || !pose) return EF_ERR_INVALID_ARGUMENT;
     if(!in->vertices_rgba32f || !in->normals_rgba32f || !in->model_rgba8 || !in->depth || !in->rgba8) return EF_ERR_INVALID_ARGUMENT;
     {
@@ -1483,10 +1482,103 @@ EF_API int ef_track_frame_to_model_launch(ef_tracker * t, const ef_frame_inputs 
         if(!rc) rc = host_sensor ? ef_init_icp_depth_host(t, depth, in->depth_cutoff) : ef_init_icp_depth(t, depth, 0, in->depth_cutoff);
         if(!rc) rc = host_sensor ? ef_init_rgb_host(t, rgba) : ef_init_rgb(t, rgba, 0);
     }
+    return rc;
+}
+
+EF_API int ef_track_frame_to_model_launch(ef_tracker * t, const ef_frame_inputs * in, const float * pose, int rgb_only, float icp_weight, int pyramid,
+                                          int fast_odom, int so3)
+{
+    EF_ON_DEVICE(t);
+    const int rc = frame_build_all(t, in, pose);
     if(rc) return rc;
     const float trans[3] = {pose[3], pose[7], pose[11]};
     const float rot[9] = {pose[0], pose[1], pose[2], pose[4], pose[5], pose[6], pose[8], pose[9], pose[10]};
     return ef_get_incremental_transformation_launch(t, trans, rot, rgb_only, icp_weight, pyramid, fast_odom, so3);
+}
+
+// ------------------------------------------------------------------------------------------------
+// k independent sequences per launch (BASELINE.json configs[4]: "k sequences per GPU to show SM fill")
+// ------------------------------------------------------------------------------------------------
+EF_API int ef_batch_width(void) { return device_track_batch_width(); }
+
+EF_API int ef_track_frames_to_model_batch_launch(ef_tracker * const * ts, int n, const ef_frame_inputs * in, const float * poses, int rgb_only,
+                                                 float icp_weight, int pyramid, int fast_odom, int so3)
+{
+    if(!ts || !in || !poses || n != device_track_batch_width()) return EF_ERR_INVALID_ARGUMENT;
+    for(int g = 0; g < n; g++)
+    {
+        if(!ts[g]) return EF_ERR_INVALID_ARGUMENT;
+        for(int k = 0; k < g; k++)
+            if(ts[k] == ts[g]) return EF_ERR_INVALID_ARGUMENT;
+    }
+    EF_ON_DEVICE(ts[0]);
+    const bool icp = !rgb_only && icp_weight > 0, rgb = rgb_only || icp_weight < 100;
+    if(!icp && !rgb) return fail(ts[0], EF_ERR_INVALID_ARGUMENT, "neither ICP nor RGB selected");
+    const float * trans[8], * rot[8];
+    float tr[8][3], ro[8][9];
+    for(int g = 0; g < n; g++)
+    {
+        ef_tracker * t = ts[g];
+        if(t->device != ts[0]->device) return fail(ts[0], EF_ERR_INVALID_ARGUMENT, "the handles of a batch must live on one device");
+        if(t->width != ts[0]->width || t->height != ts[0]->height) return fail(ts[0], EF_ERR_INVALID_ARGUMENT, "the handles of a batch must share one image size");
+        if(t->solve_mode != EF_SOLVE_DEVICE) return fail(t, EF_ERR_BAD_STATE, "batched tracking needs EF_SOLVE_DEVICE");
+        if(t->launch_pending) return fail(t, EF_ERR_BAD_STATE, "a launch is already pending");
+    }
+    for(int g = 0; g < n; g++)
+    {
+        ef_tracker * t = ts[g];
+        const float * pose = poses + 16 * g;
+        int rc = frame_build_all(t, in + g, pose);
+        if(rc) return rc;
+        if(rgb && !t->deriv_valid && !pyramid)
+        {
+            rc = compute_derivatives(t);
+            if(rc) return rc;
+        }
+        rc = join_streams(t);
+        if(rc) return rc;
+        const float tt[3] = {pose[3], pose[7], pose[11]};
+        const float rr[9] = {pose[0], pose[1], pose[2], pose[4], pose[5], pose[6], pose[8], pose[9], pose[10]};
+        memcpy(tr[g], tt, sizeof(tt));
+        memcpy(ro[g], rr, sizeof(rr));
+        trans[g] = tr[g];
+        rot[g] = ro[g];
+        memcpy(t->pending.trans, tt, sizeof(tt));
+        memcpy(t->pending.rot, rr, sizeof(rr));
+        t->pending.rgb_only = rgb_only; t->pending.icp_weight = icp_weight; t->pending.pyramid = pyramid;
+        t->pending.fast_odom = fast_odom; t->pending.so3 = so3;
+        // the batched kernel runs on the first handle's stream: it waits for the builders of the others ...
+        if(g > 0)
+        {
+            EF_CUDA(t, cudaEventRecord(t->ev_fork, t->stream));
+            EF_CUDA(t, cudaStreamWaitEvent(ts[0]->stream, t->ev_fork, 0));
+        }
+    }
+    const int rc = device_track_launch_batch(ts, n, trans, rot, rgb_only, icp_weight, pyramid, fast_odom, so3, ts[0]->stream);
+    if(rc) return rc;
+    // ... and whatever the other handles enqueue next on their own streams waits for it
+    EF_CUDA(ts[0], cudaEventRecord(ts[0]->ev_fork, ts[0]->stream));
+    for(int g = 0; g < n; g++)
+    {
+        if(g > 0) EF_CUDA(ts[g], cudaStreamWaitEvent(ts[g]->stream, ts[0]->ev_fork, 0));
+        if(rgb) ts[g]->deriv_valid = true;
+        ts[g]->launch_pending = true;
+    }
+    return EF_OK;
+}
+
+EF_API int ef_track_frames_to_model_batch(ef_tracker * const * ts, int n, const ef_frame_inputs * in, const float * poses, float * trans, float * rot,
+                                          int rgb_only, float icp_weight, int pyramid, int fast_odom, int so3, ef_track_stats * stats)
+{
+    if(!trans || !rot) return EF_ERR_INVALID_ARGUMENT;
+    int rc = ef_track_frames_to_model_batch_launch(ts, n, in, poses, rgb_only, icp_weight, pyramid, fast_odom, so3);
+    if(rc) return rc;
+    for(int g = 0; g < n; g++)
+    {
+        const int r = ef_get_incremental_transformation_finish(ts[g], trans + 3 * g, rot + 9 * g, stats ? stats + g : nullptr);
+        if(r && !rc) rc = r;
+    }
+    return rc;
 }
 
 EF_API int ef_track_frame_to_model(ef_tracker * t, const ef_frame_inputs * in, const float * pose, float * trans, float * rot, int rgb_only,

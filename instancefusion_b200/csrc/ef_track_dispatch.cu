@@ -20,6 +20,17 @@ namespace ef
 EF_DECLARE_VARIANT(256)
 EF_DECLARE_VARIANT(384)
 
+// the batched build (EF_TRACK_GROUPS = 2: two sequences per launch, csrc/Makefile)
+int device_track_launch_batch_g2(ef_tracker * const * ts, const float * const * trans, const float * const * rot, int rgb_only, float icp_weight,
+                                     int pyramid, int fast_odom, int so3, cudaStream_t stream);
+int device_track_batch_width() { return 2; }
+int device_track_launch_batch(ef_tracker * const * ts, int n, const float * const * trans, const float * const * rot, int rgb_only, float icp_weight,
+                              int pyramid, int fast_odom, int so3, cudaStream_t stream)
+{
+    if(n != 2) return EF_ERR_INVALID_ARGUMENT;
+    return device_track_launch_batch_g2(ts, trans, rot, rgb_only, icp_weight, pyramid, fast_odom, so3, stream);
+}
+
 static int pick_variant(const ef_tracker * t)
 {
     const char * env = getenv("EF_TRACK_VARIANT");

@@ -45,9 +45,24 @@
 #ifndef EF_TRACK_THREADS
 #define EF_TRACK_THREADS 256
 #endif
+// EF_TRACK_GROUPS > 1: the BATCHED build.  A CTA then holds EF_TRACK_GROUPS independent thread groups of EF_TRACK_THREADS
+// threads, group g of every CTA working for sequence g of the launch (its own tracker handle: own pyramids, control block,
+// shared-memory region, named barrier).  Nothing else changes -- group g of CTA 0 gathers and solves for sequence g, group
+// g of the other CTAs does its pixels -- but the SM's warp schedulers now interleave the sequences by themselves: while
+// the warps of one group wait for parameters (37-60 % of an iteration, profiles/r01_k_track_phase_trace_final.txt) the
+// other group's warps own the issue slots.  Same instructions per sequence, so the same bits as the single launch.
+#ifndef EF_TRACK_GROUPS
+#define EF_TRACK_GROUPS 1
+#endif
 #define EF_TRACK_CAT2(a, b) a##_t##b
 #define EF_TRACK_CAT(a, b) EF_TRACK_CAT2(a, b)
+#if EF_TRACK_GROUPS > 1
+#define EF_TRACK_CATG2(a, c) a##_g##c
+#define EF_TRACK_CATG(a, c) EF_TRACK_CATG2(a, c)
+#define EF_TRACK_FN(name) EF_TRACK_CATG(name, EF_TRACK_GROUPS) // (one batched build per library, whatever its group size)
+#else
 #define EF_TRACK_FN(name) EF_TRACK_CAT(name, EF_TRACK_THREADS)
+#endif
 
 namespace ef
 {
@@ -60,7 +75,19 @@ bool EF_TRACK_FN(device_track_supported)(const ef_tracker * t);
 namespace
 {
 
-constexpr int kThreads = EF_TRACK_THREADS; // 8 warps, up to 255 registers each: measured best of {128..640} (tools/sweep.sh)
+constexpr int kThreads = EF_TRACK_THREADS; // threads of a group; 8 warps, up to 255 registers each: measured best of {128..640} (tools/sweep.sh)
+constexpr int kGroups = EF_TRACK_GROUPS;   // independent sequences per launch (thread groups per CTA)
+static_assert(kGroups >= 1 && kGroups <= 4 && kThreads * kGroups <= 1024, "EF_TRACK_GROUPS");
+
+// thread index within its group / group index (warp-uniform: kThreads is a multiple of 32)
+__device__ __forceinline__ unsigned gtid() { return kGroups > 1 ? threadIdx.x % kThreads : threadIdx.x; }
+__device__ __forceinline__ unsigned ggrp() { return kGroups > 1 ? threadIdx.x / kThreads : 0u; }
+// barrier of one group: the whole CTA in the single build, named barrier 1 + g of kThreads threads in the batched one
+__device__ __forceinline__ void group_sync()
+{
+    if constexpr(kGroups == 1) __syncthreads();
+    else asm volatile("bar.sync %0, %1;" ::"r"(1u + ggrp()), "n"(kThreads) : "memory");
+}
 #ifndef EF_TRACK_ICP_BATCH
 #if EF_TRACK_THREADS >= 384
 #define EF_TRACK_ICP_BATCH 2 // 168 registers: two pixels in flight per thread
@@ -69,6 +96,13 @@ constexpr int kThreads = EF_TRACK_THREADS; // 8 warps, up to 255 registers each:
 #endif
 #endif
 constexpr int kIcpBatch = EF_TRACK_ICP_BATCH; // pixels of one thread whose loads and gathers are in flight together
+#ifndef EF_TRACK_RGB_BATCH
+#define EF_TRACK_RGB_BATCH 3
+#endif
+constexpr int kRgbBatch = EF_TRACK_RGB_BATCH; // photometric candidates of one thread in flight together (1 .. 3)
+#ifndef EF_TRACK_STAGE_BATCH
+#define EF_TRACK_STAGE_BATCH 5
+#endif
 #ifndef EF_TRACK_ICP_SPLIT
 #define EF_TRACK_ICP_SPLIT 0
 #endif
@@ -153,6 +187,7 @@ struct TrackArgs
     int prework;                                  // all levels' lists fit side by side: finer levels are prepared during the waits of coarser ones
     int make_derivatives;                         // dIdx / dIdy are not valid yet: compute them at level start
     int icp_in_smem;                              // the CTA's current-frame vertices / normals fit shared memory beside the candidates
+    int group_smem_bytes;                         // dynamic shared memory of one thread group (multiple of 16)
     float prev_icp_error, prev_icp_count, prev_so3_error, prev_so3_count, prev_rgb_error, prev_rgb_count;
     unsigned epoch_base;                          // launch_seq << 8
     uint4 * par;                                  // kReplicas parameter lines
@@ -184,7 +219,7 @@ __device__ __forceinline__ void st_relaxed_v4(uint4 * p, const uint4 & v)
 __device__ __forceinline__ void warp_publish(uint4 * par, const float * s_payload, int first, int n, unsigned epoch)
 {
     __syncwarp();
-    for(int i = threadIdx.x & 31; i < kReplicas * n; i += 32)
+    for(int i = gtid() & 31; i < kReplicas * n; i += 32)
     {
         const int r = i / n, c = first + (i - r * n);
         st_relaxed_v4(par + r * kReplicaStride + c,
@@ -196,9 +231,9 @@ __device__ __forceinline__ void warp_publish(uint4 * par, const float * s_payloa
 // they show `epoch`; payload -> smem
 __device__ __forceinline__ void wait_chunks(const uint4 * line, int first, int n, unsigned epoch, float * s_payload)
 {
-    if(threadIdx.x < 32)
+    if(gtid() < 32)
     {
-        const int lane = threadIdx.x;
+        const int lane = gtid();
         uint4 v = make_uint4(0, 0, 0, epoch);
         do
         {
@@ -212,15 +247,15 @@ __device__ __forceinline__ void wait_chunks(const uint4 * line, int first, int n
             d[2] = __uint_as_float(v.z);
         }
     }
-    __syncthreads();
+    group_sync();
 }
 
 // worker CTA: publish this CTA's partial sums (already in shared memory) as flagged chunks
 __device__ __forceinline__ void publish_row(uint4 * my_row, const float * s_row, int chunks, unsigned epoch)
 {
-    if((int)threadIdx.x < chunks)
+    if((int)gtid() < chunks)
     {
-        const int c = threadIdx.x;
+        const int c = gtid();
         st_relaxed_v4(my_row + c, make_uint4(__float_as_uint(s_row[3 * c]), __float_as_uint(s_row[3 * c + 1]), __float_as_uint(s_row[3 * c + 2]), epoch));
     }
 }
@@ -231,7 +266,7 @@ __device__ __forceinline__ void gather_rows(const uint4 * rows, int workers, int
                                             float * s_red, float * s_final)
 {
     const int total = workers * chunks;
-    for(int i0 = threadIdx.x; i0 < total; i0 += kGatherBatch * kThreads)
+    for(int i0 = gtid(); i0 < total; i0 += kGatherBatch * kThreads)
     {
         uint4 v[kGatherBatch];
         unsigned todo = 0;
@@ -256,9 +291,9 @@ __device__ __forceinline__ void gather_rows(const uint4 * rows, int workers, int
                 }
         }
     }
-    __syncthreads();
+    group_sync();
     const int nfl = chunks * 3;
-    const int slot = threadIdx.x & 63, part = threadIdx.x >> 6;
+    const int slot = gtid() & 63, part = gtid() >> 6;
     if(part < kParts)
     {
         float s = 0.f;
@@ -266,15 +301,15 @@ __device__ __forceinline__ void gather_rows(const uint4 * rows, int workers, int
             for(int w = part; w < workers; w += kParts) s += s_rows[w * nfl + slot];
         s_red[part * 64 + slot] = s;
     }
-    __syncthreads();
-    if(threadIdx.x < 64)
+    group_sync();
+    if(gtid() < 64)
     {
         float tot = 0.f;
 #pragma unroll
-        for(int p = 0; p < kParts; p++) tot += s_red[p * 64 + threadIdx.x];
-        s_final[threadIdx.x] = tot;
+        for(int p = 0; p < kParts; p++) tot += s_red[p * 64 + gtid()];
+        s_final[gtid()] = tot;
     }
-    __syncthreads();
+    group_sync();
 }
 
 __device__ __forceinline__ Mat33 mat_from(const float * m)
@@ -334,7 +369,7 @@ __device__ __noinline__ void solve_pivoted(const double * S28, double * x6)
 }
 
 // warps 0 and 1 of CTA 0: hand-over of resultRt from the solver warp to the warp that derives the photometric warp
-__device__ __forceinline__ void solver_pair_sync() { asm volatile("bar.sync 1, 64;" ::: "memory"); }
+__device__ __forceinline__ void solver_pair_sync() { asm volatile("bar.sync %0, 64;" ::"r"(1u + kGroups + ggrp()) : "memory"); }
 
 
 // RGBDOdometry.cpp:515-516, :541-583 -- the reference's host step after a Gauss-Newton evaluation, run by WARP 0 of CTA 0
@@ -351,7 +386,7 @@ __device__ __forceinline__ void warp_solve_se3(Solver * S, const float * s_final
 {
     long long tk[5] = {0, 0, 0, 0, 0};
     if(dbg) tk[0] = clock64();
-    const int lane = threadIdx.x & 31;
+    const int lane = gtid() & 31;
     __syncwarp();
     // combined normal equations (:547-553): lane k converts and combines entry k (one conversion per lane instead of 54 per
     // lane), parks it in last_S -- which is lastA / lastb of this solve anyway (RGBDOdometry.h:72-73) -- and every lane
@@ -492,7 +527,7 @@ __device__ __forceinline__ void warp_solve_se3(Solver * S, const float * s_final
 // :480-481 -- pose of the next SE3 iteration (warp 0 of CTA 0) -> payload[0, 12) in shared memory
 __device__ __forceinline__ void warp_make_pose(const Solver * S, float * payload /*shared*/)
 {
-    const int lane = threadIdx.x & 31;
+    const int lane = gtid() & 31;
     __syncwarp();
     if(lane < 12) payload[lane] = (lane < 9) ? S->Rcurr[lane] : S->tcurr[lane - 9];
 }
@@ -503,7 +538,7 @@ __device__ __forceinline__ void warp_make_pose(const Solver * S, float * payload
 __device__ __forceinline__ void warp_make_rgb_params(const Solver * S, float * payload /*shared*/, float fxf, float fyf, float cxf, float cyf,
                                                             const double * K_inv)
 {
-    const int lane = threadIdx.x & 31;
+    const int lane = gtid() & 31;
     __syncwarp();
     double m[12];
 #pragma unroll
@@ -735,7 +770,7 @@ template<bool DERIV>
 __device__ __forceinline__ int compact_group(const LevelArgs & L, const RgbResParams & RP, const UnitIter & U, int passes, const CandStore & C,
                                              int * s_wtot /*[2][kCompactGroup][kWarps]*/, int grp, int base)
 {
-    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const unsigned lane = gtid() & 31u, warp = gtid() >> 5;
     const int p0 = grp * kCompactGroup;
     unsigned w0[kCompactGroup], w1[kCompactGroup], ballot[kCompactGroup];
     float d1[kCompactGroup];
@@ -757,7 +792,7 @@ __device__ __forceinline__ int compact_group(const LevelArgs & L, const RgbResPa
         ballot[g] = __ballot_sync(kFullMask, keep[g]);
         if(lane == 0) wt[g * kWarps + warp] = __popc(ballot[g]);
     }
-    __syncthreads();
+    group_sync();
 #pragma unroll
     for(int g = 0; g < kCompactGroup; g++)
     {
@@ -797,7 +832,7 @@ __device__ __forceinline__ void rgb_assoc_batch(const LevelArgs & L, const RgbRe
 #pragma unroll
     for(int k = 0; k < B; k++)
     {
-        const int c = threadIdx.x + (j0 + k) * kThreads;
+        const int c = gtid() + (j0 + k) * kThreads;
         valid[k] = c < n_cand;
         const int cc = valid[k] ? c : 0;
         const unsigned w = C.c0[cc];
@@ -816,7 +851,7 @@ __device__ __forceinline__ void rgb_assoc_batch(const LevelArgs & L, const RgbRe
 #pragma unroll
     for(int k = 0; k < B; k++)
     {
-        const int c = threadIdx.x + (j0 + k) * kThreads;
+        const int c = gtid() + (j0 + k) * kThreads;
         const bool good = ok[k] && rgb_accept(RP, td1[k], d0s[k], (uint8_t)ls[k]);
         const float diff = static_cast<float>(inext[k]) - static_cast<float>(ls[k]); // reduce.cu:827
         const unsigned rec = good ? ((unsigned)u0[k] | ((unsigned)v0[k] << 12) | (ls[k] << 24)) : kNoMatch;
@@ -834,9 +869,9 @@ __device__ __forceinline__ void rgb_assoc_cands(const LevelArgs & L, const RgbRe
 {
     const int rounds = (n_cand + kThreads - 1) / kThreads; // uniform over the CTA
     int j = 0;
-    for(; j + 3 <= rounds; j += 3) rgb_assoc_batch<3>(L, RP, C, n_cand, j, cnt, sig);
-    if(rounds - j == 2) rgb_assoc_batch<2>(L, RP, C, n_cand, j, cnt, sig);
-    else if(rounds - j == 1) rgb_assoc_batch<1>(L, RP, C, n_cand, j, cnt, sig);
+    for(; j + kRgbBatch <= rounds; j += kRgbBatch) rgb_assoc_batch<kRgbBatch>(L, RP, C, n_cand, j, cnt, sig);
+    if(kRgbBatch > 2 && rounds - j == 2) rgb_assoc_batch<2>(L, RP, C, n_cand, j, cnt, sig);
+    else if(kRgbBatch > 1 && rounds - j == 1) rgb_assoc_batch<1>(L, RP, C, n_cand, j, cnt, sig);
 }
 
 // phase B: RGBReduction::getProducts (reduce.cu:512-595) for B of this thread's candidates, again without control
@@ -848,7 +883,7 @@ __device__ __forceinline__ bool rgb_rows_batch(const RgbStepParams & SP, const C
 #pragma unroll
     for(int k = 0; k < B; k++)
     {
-        const int c = threadIdx.x + (j0 + k) * kThreads;
+        const int c = gtid() + (j0 + k) * kThreads;
         const int cc = c < n_cand ? c : 0;
         const unsigned rec = C.r0[cc];
         const bool good = c < n_cand && rec != kNoMatch;
@@ -879,15 +914,15 @@ __device__ __forceinline__ bool rgb_rows_cands(const RgbStepParams & SP, const C
     const int rounds = (n_cand + kThreads - 1) / kThreads;
     bool any = false;
     int j = 0;
-    for(; j + 3 <= rounds; j += 3) any |= rgb_rows_batch<3>(SP, C, n_cand, j, accR);
-    if(rounds - j == 2) any |= rgb_rows_batch<2>(SP, C, n_cand, j, accR);
-    else if(rounds - j == 1) any |= rgb_rows_batch<1>(SP, C, n_cand, j, accR);
+    for(; j + kRgbBatch <= rounds; j += kRgbBatch) any |= rgb_rows_batch<kRgbBatch>(SP, C, n_cand, j, accR);
+    if(kRgbBatch > 2 && rounds - j == 2) any |= rgb_rows_batch<2>(SP, C, n_cand, j, accR);
+    else if(kRgbBatch > 1 && rounds - j == 1) any |= rgb_rows_batch<1>(SP, C, n_cand, j, accR);
     return any;
 }
 
 // Level start: the current-frame vertex / normal of this CTA's pixels -> shared memory (they do not change over the
 // iterations of a level; 24 B per pixel, structure of arrays, slot = pass * kThreads + thread)
-constexpr int kStageBatch = 5; // passes of a thread whose six loads each are requested together when the current maps are staged
+constexpr int kStageBatch = EF_TRACK_STAGE_BATCH; // passes of a thread whose six loads each are requested together when the current maps are staged
 __device__ __forceinline__ void stage_batch(const LevelArgs & L, const UnitIter & U, int passes, float * s_vn, int cap, int p0)
 {
     // one batch = one L2 round trip; nothing else is live in the registers at this point
@@ -906,7 +941,7 @@ __device__ __forceinline__ void stage_batch(const LevelArgs & L, const UnitIter 
     for(int k = 0; k < kStageBatch; k++)
         if(u[k] >= 0)
         {
-            float * q = s_vn + (p0 + k) * kThreads + threadIdx.x;
+            float * q = s_vn + (p0 + k) * kThreads + gtid();
 #pragma unroll
             for(int c = 0; c < 6; c++) q[c * cap] = v[k][c];
         }
@@ -933,7 +968,7 @@ __device__ __forceinline__ bool icp_batch(const LevelArgs & L, const IcpParams &
         if constexpr(SMEM)
         {
             // iteration-invariant: staged once per level (stage_current_maps), slot = pass * kThreads + thread
-            const float * sq = s_vn + (in1[k] ? (p0 + k) * kThreads + threadIdx.x : 0);
+            const float * sq = s_vn + (in1[k] ? (p0 + k) * kThreads + gtid() : 0);
             v[k].x = sq[0]; v[k].y = sq[cap]; v[k].z = sq[2 * cap];
             n[k].x = sq[3 * cap]; n[k].y = sq[4 * cap]; n[k].z = sq[5 * cap];
         }
@@ -1006,25 +1041,47 @@ __device__ __forceinline__ void sigma_from_sums(int sigma, int rgbSize, float & 
     rgbError = (float)(sqrt((double)sigma) / (double)(rgbSize == 0 ? 1 : rgbSize));
 }
 
-template<bool TIMING>
-__global__ void __launch_bounds__(kThreads, 1) k_track(const __grid_constant__ TrackArgs A)
+// static shared memory of one thread group
+struct GroupShared
 {
-    extern __shared__ int4 s_dyn[];             // workers: candidates + match records; CTA 0: gathered rows
-    __shared__ float s_red[kWarps * 64];
-    __shared__ float s_final[64];
-    __shared__ float s_par[2][kPayload];
-    __shared__ float s_sigma[3];                // sigmaVal, rgbError, (float)rgbSize of the current iteration
-    __shared__ int s_wcnt[kWarps], s_wsig[kWarps];
-    __shared__ int s_wtot[2 * kCompactGroup * kWarps];
-    __shared__ int s_flag;
-    __shared__ __align__(16) Solver s_solver;
+    float red[kWarps * 64];
+    float final_[64];
+    float par[2][kPayload];
+    float sigma[3];                // sigmaVal, rgbError, (float)rgbSize of the current iteration
+    int wcnt[kWarps], wsig[kWarps];
+    int wtot[2 * kCompactGroup * kWarps];
+    int flag;
+    alignas(16) Solver solver;
+};
+
+struct BatchArgs
+{
+    TrackArgs seq[kGroups];
+};
+
+template<bool TIMING>
+__global__ void __launch_bounds__(kThreads * kGroups, 1) k_track(const __grid_constant__ BatchArgs BA)
+{
+    extern __shared__ int4 s_dyn_all[];         // per group -- workers: candidates + match records; CTA 0: gathered rows
+    __shared__ GroupShared s_groups[kGroups];
+    const TrackArgs & A = BA.seq[ggrp()];
+    GroupShared & GS = s_groups[ggrp()];
+    int4 * const s_dyn = s_dyn_all + (size_t)ggrp() * (A.group_smem_bytes / sizeof(int4));
+    float * const s_red = GS.red;
+    float * const s_final = GS.final_;
+    float (* const s_par)[kPayload] = GS.par;
+    float * const s_sigma = GS.sigma;
+    int * const s_wcnt = GS.wcnt, * const s_wsig = GS.wsig;
+    int * const s_wtot = GS.wtot;
+    int & s_flag = GS.flag;
+    Solver & s_solver = GS.solver;
 
     const uint4 * my_par = A.par + (size_t)((blockIdx.x == 0 ? 0 : blockIdx.x - 1) % kReplicas) * kReplicaStride;
     const unsigned grid = gridDim.x;
     const int W = (int)grid - 1;                // worker CTAs (blockIdx 1 .. grid-1); CTA 0 only gathers and solves
     const bool is_solver_cta = (blockIdx.x == 0);
-    const bool is_solver = is_solver_cta && threadIdx.x == 0;
-    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const bool is_solver = is_solver_cta && gtid() == 0;
+    const unsigned lane = gtid() & 31u, warp = gtid() >> 5;
     const int widx = is_solver_cta ? 0 : (int)blockIdx.x - 1;
     float * s_rows = reinterpret_cast<float *>(s_dyn);
     // per level: five candidate arrays of lvl_cap entries, then (icp_in_smem) six planes of lvl_cap floats
@@ -1069,7 +1126,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_track(const __grid_constant__ T
     auto stamp = [&](int k) {
         if constexpr(TIMING)
         {
-            if(threadIdx.x == 0 && dbg_it < kMaxIters) A.dbg[((size_t)blockIdx.x * kMaxIters + dbg_it) * kDbgStamps + k] = clock64();
+            if(gtid() == 0 && dbg_it < kMaxIters) A.dbg[((size_t)blockIdx.x * kMaxIters + dbg_it) * kDbgStamps + k] = clock64();
         }
     };
     // kernel start / end of CTA 0 live in the two last iteration slots (a call runs at most 19 SE3 iterations)
@@ -1117,7 +1174,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_track(const __grid_constant__ T
                     make_so3_params(S, s_par[rel & 1u], d, L.fx, L.fy, L.cx, L.cy, L.K_inv);
                     s_flag = d;
                 }
-                __syncthreads();
+                group_sync();
                 if(warp == 0) warp_publish(A.par, s_par[rel & 1u], 0, kLineChunks, rel);
                 done = s_flag != 0;
             }
@@ -1149,15 +1206,15 @@ __global__ void __launch_bounds__(kThreads, 1) k_track(const __grid_constant__ T
             }
             const float lane_value = warp_transpose_reduce16(acc);
             if(lane < 16) s_red[warp * 16 + lane] = lane_value;
-            __syncthreads();
-            if(threadIdx.x < 16)
+            group_sync();
+            if(gtid() < 16)
             {
                 float s = 0.f;
 #pragma unroll
-                for(int w = 0; w < kWarps; w++) s += s_red[w * 16 + threadIdx.x];
-                s_final[threadIdx.x] = (threadIdx.x < 11) ? s : 0.f;
+                for(int w = 0; w < kWarps; w++) s += s_red[w * 16 + gtid()];
+                s_final[gtid()] = (gtid() < 11) ? s : 0.f;
             }
-            __syncthreads();
+            group_sync();
             publish_row(A.rows + (size_t)widx * kSo3Chunks, s_final, kSo3Chunks, arr);
         }
         if(is_solver)
@@ -1252,9 +1309,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_track(const __grid_constant__ T
         if(!is_solver_cta) stamp(10);
         if(!is_solver_cta)
         {
-            if(!A.prework) __syncthreads(); // the levels share one region: every thread is done with the previous level's records
+            if(!A.prework) group_sync(); // the levels share one region: every thread is done with the previous level's records
             while(prep_unit[lv] < prep_units(lv)) prepare_unit(lv);
-            __syncthreads();
+            group_sync();
         }
         if(!is_solver_cta) stamp(11);
         if(!is_solver_cta) stamp(12);
@@ -1352,8 +1409,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_track(const __grid_constant__ T
                 cnt = __reduce_add_sync(kFullMask, cnt);
                 sig = __reduce_add_sync(kFullMask, sig);
                 if(lane == 0) { s_wcnt[warp] = cnt; s_wsig[warp] = sig; }
-                __syncthreads();
-                if(threadIdx.x == 0)
+                group_sync();
+                if(gtid() == 0)
                 {
                     unsigned c = 0, s = 0;
 #pragma unroll
@@ -1386,7 +1443,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_track(const __grid_constant__ T
                 if(is_solver_cta)
                 {
                     int c = 0, sg = 0;
-                    for(int w = threadIdx.x; w < W; w += kThreads)
+                    for(int w = gtid(); w < W; w += kThreads)
                     {
                         uint4 v;
                         do
@@ -1399,8 +1456,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_track(const __grid_constant__ T
                     c = __reduce_add_sync(kFullMask, c);
                     sg = __reduce_add_sync(kFullMask, sg);
                     if(lane == 0) { s_wcnt[warp] = c; s_wsig[warp] = sg; }
-                    __syncthreads();
-                    if(threadIdx.x == 0)
+                    group_sync();
+                    if(gtid() == 0)
                     {
                         unsigned cc = 0, ss = 0;
 #pragma unroll
@@ -1411,13 +1468,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_track(const __grid_constant__ T
                         s_sigma[1] = rgbError;
                         s_sigma[2] = (float)(int)cc;
                     }
-                    __syncthreads();
-                    for(int w = threadIdx.x; w < W; w += kThreads)
+                    group_sync();
+                    for(int w = gtid(); w < W; w += kThreads)
                         st_relaxed_v4(A.bres + w, make_uint4(__float_as_uint(s_sigma[0]), __float_as_uint(s_sigma[1]), __float_as_uint(s_sigma[2]), rel));
                 }
                 else
                 {
-                    if(threadIdx.x == 0)
+                    if(gtid() == 0)
                     {
                         uint4 v;
                         do
@@ -1428,7 +1485,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_track(const __grid_constant__ T
                         s_sigma[1] = __uint_as_float(v.y);
                         s_sigma[2] = __uint_as_float(v.z);
                     }
-                    __syncthreads();
+                    group_sync();
                 }
                 stamp(6);
                 const float rgbError = s_sigma[1];
@@ -1469,18 +1526,18 @@ __global__ void __launch_bounds__(kThreads, 1) k_track(const __grid_constant__ T
                     if(__any_sync(kFullMask, any)) vr = warp_transpose_reduce32(accR);
                 }
                 if(lane < 29) s_red[warp * 64 + 29 + lane] = vr;
-                __syncthreads();
-                if(threadIdx.x < kRowFloats)
+                group_sync();
+                if(gtid() < kRowFloats)
                 {
                     float sum = 0.f;
-                    if(threadIdx.x < 58)
+                    if(gtid() < 58)
                     {
 #pragma unroll
-                        for(int w = 0; w < kWarps; w++) sum += s_red[w * 64 + threadIdx.x];
+                        for(int w = 0; w < kWarps; w++) sum += s_red[w * 64 + gtid()];
                     }
-                    s_final[threadIdx.x] = sum;
+                    s_final[gtid()] = sum;
                 }
-                __syncthreads();
+                group_sync();
                 publish_row(A.rows + (size_t)widx * kRowChunks, s_final, kRowChunks, arr);
                 stamp(9);
             }
@@ -1496,7 +1553,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_track(const __grid_constant__ T
         ++arr;
         if(!is_solver_cta)
         {
-            __syncthreads();
+            group_sync();
             publish_row(A.rows + (size_t)widx * kSo3Chunks, s_final, kSo3Chunks, arr);
         }
     }
@@ -1559,6 +1616,14 @@ __global__ void __launch_bounds__(kThreads, 1) k_track(const __grid_constant__ T
     }
 }
 
+struct Layout // shared-memory geometry of one thread group for a grid of `grid` CTAs
+{
+    int grid;
+    int cand_cap, icp_in_smem, prework;
+    int lvl_cap[kNumPyrs], lvl_off[kNumPyrs];
+    size_t smem_bytes; // per group, multiple of 16
+};
+
 struct DeviceTrack
 {
     long long * dbg;      // device, max_grid * kMaxIters * kDbgStamps stamps (EF_TRACK_TIMING=1)
@@ -1570,25 +1635,14 @@ struct DeviceTrack
     uint4 * par, * bslot, * bres;
     uint4 * rows;
     TrackOutput * out; // pinned
-    int grid;
-    int cand_cap, icp_in_smem, prework;
-    int lvl_cap[kNumPyrs], lvl_off[kNumPyrs];
-    size_t smem_bytes;
+    Layout lay;        // of the single launch (all of a CTA's shared memory)
     unsigned launch_seq;
 };
 
-} // namespace
-
-// (re)derive the launch geometry for a grid of `grid` CTAs: pixels per thread unit and passes per level ->
-// shared-memory records per thread.  A handle normally owns every SM; EF_OPT_GRID_CTAS lets several handles
-// share the GPU (e.g. two sequences tracked concurrently on 74 SMs each).
-int EF_TRACK_FN(device_track_configure)(ef_tracker * t, int grid)
+// pixels per thread unit and passes per level -> shared-memory records per thread, within `budget` bytes of dynamic
+// shared memory.  false: the photometric candidates of a CTA do not fit.
+bool compute_layout(const ef_tracker * t, int grid, size_t budget, Layout & L)
 {
-    DeviceTrack * d = static_cast<DeviceTrack *>(t->track_state);
-    if(!d) return EF_ERR_BAD_STATE;
-    const int max_grid = t->num_sms < kMaxGrid ? t->num_sms : kMaxGrid;
-    if(grid <= 0 || grid > max_grid) grid = max_grid;
-    if(grid < 2) grid = 2;
     const int W = grid - 1;
     int max_cand = 1;
     for(int i = 0; i < kNumPyrs; i++)
@@ -1599,53 +1653,131 @@ int EF_TRACK_FN(device_track_configure)(ef_tracker * t, int grid)
         if(per_worker * 32 > max_cand) max_cand = per_worker * 32;
     }
     size_t smem = (size_t)max_cand * kCandBytes;
-    const bool icp_in_smem = (size_t)max_cand * (kCandBytes + kIcpBytes) <= (size_t)kMaxDynSmem;
+    const bool icp_in_smem = (size_t)max_cand * (kCandBytes + kIcpBytes) <= budget;
     if(icp_in_smem) smem = (size_t)max_cand * (kCandBytes + kIcpBytes);
     // the lists of the three levels side by side, if they fit: finer levels are then prepared while coarser ones iterate
     const size_t per_px = kCandBytes + (icp_in_smem ? kIcpBytes : 0);
-    int lvl_cap[kNumPyrs], lvl_off[kNumPyrs];
     size_t all = 0;
     for(int i = 0; i < kNumPyrs; i++)
     {
         const int npix = t->dims[i].rows * t->dims[i].cols;
         const int per_worker = ((npix + 31) / 32 + W - 1) / W;
-        lvl_cap[i] = per_worker * 32;
-        lvl_off[i] = (int)all;
-        all += ((size_t)lvl_cap[i] * per_px + 15) & ~(size_t)15;
+        L.lvl_cap[i] = per_worker * 32;
+        L.lvl_off[i] = (int)all;
+        all += ((size_t)L.lvl_cap[i] * per_px + 15) & ~(size_t)15;
     }
-    const bool prework = all <= (size_t)kMaxDynSmem;
+    const bool prework = all <= budget;
     if(prework) smem = all;
     else
         for(int i = 0; i < kNumPyrs; i++)
         {
-            lvl_cap[i] = max_cand; // one region, reused level after level
-            lvl_off[i] = 0;
+            L.lvl_cap[i] = max_cand; // one region, reused level after level
+            L.lvl_off[i] = 0;
         }
     const size_t rows_smem = (size_t)W * kRowFloats * sizeof(float);
     if(rows_smem > smem) smem = rows_smem;
-    if(smem > (size_t)kMaxDynSmem && d->grid > 0)
+    L.grid = grid;
+    L.prework = prework ? 1 : 0;
+    L.cand_cap = max_cand;
+    L.icp_in_smem = icp_in_smem ? 1 : 0;
+    L.smem_bytes = (smem + 15) & ~(size_t)15;
+    return L.smem_bytes <= budget;
+}
+
+// everything a launch passes to one thread group (one sequence)
+void fill_args(ef_tracker * t, DeviceTrack * d, const Layout & lay, const float * trans, const float * rot, int rgb_only, float icp_weight, int pyramid,
+               int fast_odom, int so3, TrackArgs & A)
+{
+    memset(&A, 0, sizeof(A));
+    const int iterations[kNumPyrs] = {fast_odom ? 3 : 10, pyramid ? 5 : 0, pyramid ? 4 : 0}; // :384-386
+    for(int i = 0; i < kNumPyrs; i++)
+    {
+        LevelArgs & L = A.lvl[i];
+        L.vc = t->vmap_curr[i]; L.nc = t->nmap_curr[i]; L.vp = t->vmap_g_prev[i]; L.np = t->nmap_g_prev[i];
+        L.last_depth = t->last_depth[i]; L.next_depth = t->next_depth[i];
+        L.last_image = t->last_image[i]; L.next_image = t->next_image[i];
+        L.dIdx = t->dIdx[i]; L.dIdy = t->dIdy[i];
+        L.rows = t->dims[i].rows; L.cols = t->dims[i].cols;
+        const int div = 1 << i;
+        L.fx = t->fx / div; L.fy = t->fy / div; L.cx = t->cx / div; L.cy = t->cy / div;
+        L.inv_fx = 1.0f / L.fx; L.inv_fy = 1.0f / L.fy;
+        L.min_scale = (float)(pow(t->min_grad[i], 2.0) / pow(t->sobel_scale, 2.0)); // :442
+        L.iterations = iterations[i];
+        const double K[9] = {L.fx, 0, L.cx, 0, L.fy, L.cy, 0, 0, 1};
+        hm::inverse33(K, L.K_inv);
+    }
+    A.so3_last = t->last_next_image[2];
+    A.so3_next = t->next_image[2];
+    for(int i = 0; i < 9; i++) A.so3_kinv[i] = (float)A.lvl[2].K_inv[i];
+    memcpy(A.Rprev, rot, sizeof(A.Rprev));
+    memcpy(A.tprev, trans, sizeof(A.tprev));
+    hm::inverse33(A.Rprev, A.Rprev_inv); // :388
+    A.dist_thresh = t->dist_thresh; A.angle_thresh = t->angle_thresh;
+    A.max_depth_delta = t->max_depth_delta_rgb; A.sobel_scale = t->sobel_scale; A.icp_weight = icp_weight;
+    A.icp = (!rgb_only && icp_weight > 0) ? 1 : 0;
+    A.rgb = (rgb_only || icp_weight < 100) ? 1 : 0;
+    A.rgb_only = rgb_only ? 1 : 0;
+    A.so3 = so3 ? 1 : 0;
+    A.prev_icp_error = t->st.last_icp_error; A.prev_icp_count = t->st.last_icp_count;
+    A.prev_so3_error = t->st.last_so3_error; A.prev_so3_count = t->st.last_so3_count;
+    A.prev_rgb_error = t->st.last_rgb_error; A.prev_rgb_count = t->st.last_rgb_count;
+    // launch-unique flag epochs: nothing in the control block or the rows needs resetting between launches.  After
+    // 2^24 launches the sequence wraps; stale flags are wiped then.
+    d->launch_seq++;
+    if((d->launch_seq & 0xffffffu) == 0)
+    {
+        d->launch_seq = 1;
+        const int mg = t->num_sms < kMaxGrid ? t->num_sms : kMaxGrid;
+        cudaMemsetAsync(d->rows, 0, (size_t)mg * kRowChunks * sizeof(uint4), t->stream);
+        cudaMemsetAsync(d->par, 0, ((size_t)kReplicas * kReplicaStride + 2 * (size_t)((mg + 7) & ~7)) * sizeof(uint4), t->stream);
+    }
+    A.epoch_base = d->launch_seq << 8;
+    A.par = d->par;
+    A.bslot = d->bslot;
+    A.bres = d->bres;
+    A.rows = d->rows;
+    A.out = d->out; // UVA: pinned + mapped host memory is addressable from the device
+    A.dbg = d->dbg;
+    A.cand_cap = lay.cand_cap;
+    A.prework = lay.prework;
+    for(int i = 0; i < kNumPyrs; i++)
+    {
+        A.lvl_cap[i] = lay.lvl_cap[i];
+        A.lvl_off[i] = lay.lvl_off[i];
+    }
+    A.make_derivatives = (A.rgb && !t->deriv_valid) ? 1 : 0;
+    A.icp_in_smem = lay.icp_in_smem;
+    A.group_smem_bytes = (int)lay.smem_bytes;
+    d->out->status = 0;
+}
+
+} // namespace
+
+#if EF_TRACK_GROUPS == 1
+// (re)derive the launch geometry for a grid of `grid` CTAs.  A handle normally owns every SM; EF_OPT_GRID_CTAS lets several
+// handles share the GPU (e.g. two sequences tracked concurrently on 74 SMs each).
+int EF_TRACK_FN(device_track_configure)(ef_tracker * t, int grid)
+{
+    DeviceTrack * d = static_cast<DeviceTrack *>(t->track_state);
+    if(!d) return EF_ERR_BAD_STATE;
+    const int max_grid = t->num_sms < kMaxGrid ? t->num_sms : kMaxGrid;
+    if(grid <= 0 || grid > max_grid) grid = max_grid;
+    if(grid < 2) grid = 2;
+    Layout L;
+    if(!compute_layout(t, grid, (size_t)kMaxDynSmem, L) && d->lay.grid > 0)
     {
         // too few CTAs for this image: the photometric candidates of a CTA must fit its shared memory; keep the old grid
         t->err = "EF_OPT_GRID_CTAS: too few CTAs for the shared-memory candidate store at this image size";
         return EF_ERR_UNSUPPORTED;
     }
-    d->grid = grid;
-    d->prework = prework ? 1 : 0;
-    for(int i = 0; i < kNumPyrs; i++)
-    {
-        d->lvl_cap[i] = lvl_cap[i];
-        d->lvl_off[i] = lvl_off[i];
-    }
-    d->cand_cap = max_cand;
-    d->icp_in_smem = icp_in_smem ? 1 : 0;
-    d->smem_bytes = smem;
+    d->lay = L;
     return EF_OK;
 }
 
 bool EF_TRACK_FN(device_track_supported)(const ef_tracker * t)
 {
     const DeviceTrack * d = static_cast<const DeviceTrack *>(t->track_state);
-    return d && d->smem_bytes <= (size_t)kMaxDynSmem && (size_t)t->width * t->height < (1u << 24) && t->width <= 4094 && t->height <= 4094;
+    return d && d->lay.smem_bytes <= (size_t)kMaxDynSmem && (size_t)t->width * t->height < (1u << 24) && t->width <= 4094 && t->height <= 4094;
 }
 
 int EF_TRACK_FN(device_track_init)(ef_tracker * t)
@@ -1751,71 +1883,11 @@ int EF_TRACK_FN(device_track_launch)(ef_tracker * t, const float * trans, const 
         t->err = "image too large for the shared-memory candidate store of EF_SOLVE_DEVICE";
         return EF_ERR_UNSUPPORTED;
     }
-    TrackArgs A;
-    memset(&A, 0, sizeof(A));
-    const int iterations[kNumPyrs] = {fast_odom ? 3 : 10, pyramid ? 5 : 0, pyramid ? 4 : 0}; // :384-386
-    for(int i = 0; i < kNumPyrs; i++)
-    {
-        LevelArgs & L = A.lvl[i];
-        L.vc = t->vmap_curr[i]; L.nc = t->nmap_curr[i]; L.vp = t->vmap_g_prev[i]; L.np = t->nmap_g_prev[i];
-        L.last_depth = t->last_depth[i]; L.next_depth = t->next_depth[i];
-        L.last_image = t->last_image[i]; L.next_image = t->next_image[i];
-        L.dIdx = t->dIdx[i]; L.dIdy = t->dIdy[i];
-        L.rows = t->dims[i].rows; L.cols = t->dims[i].cols;
-        const int div = 1 << i;
-        L.fx = t->fx / div; L.fy = t->fy / div; L.cx = t->cx / div; L.cy = t->cy / div;
-        L.inv_fx = 1.0f / L.fx; L.inv_fy = 1.0f / L.fy;
-        L.min_scale = (float)(pow(t->min_grad[i], 2.0) / pow(t->sobel_scale, 2.0)); // :442
-        L.iterations = iterations[i];
-        const double K[9] = {L.fx, 0, L.cx, 0, L.fy, L.cy, 0, 0, 1};
-        hm::inverse33(K, L.K_inv);
-    }
-    A.so3_last = t->last_next_image[2];
-    A.so3_next = t->next_image[2];
-    for(int i = 0; i < 9; i++) A.so3_kinv[i] = (float)A.lvl[2].K_inv[i];
-    memcpy(A.Rprev, rot, sizeof(A.Rprev));
-    memcpy(A.tprev, trans, sizeof(A.tprev));
-    hm::inverse33(A.Rprev, A.Rprev_inv); // :388
-    A.dist_thresh = t->dist_thresh; A.angle_thresh = t->angle_thresh;
-    A.max_depth_delta = t->max_depth_delta_rgb; A.sobel_scale = t->sobel_scale; A.icp_weight = icp_weight;
-    A.icp = (!rgb_only && icp_weight > 0) ? 1 : 0;
-    A.rgb = (rgb_only || icp_weight < 100) ? 1 : 0;
-    A.rgb_only = rgb_only ? 1 : 0;
-    A.so3 = so3 ? 1 : 0;
-    A.prev_icp_error = t->st.last_icp_error; A.prev_icp_count = t->st.last_icp_count;
-    A.prev_so3_error = t->st.last_so3_error; A.prev_so3_count = t->st.last_so3_count;
-    A.prev_rgb_error = t->st.last_rgb_error; A.prev_rgb_count = t->st.last_rgb_count;
-    // launch-unique flag epochs: nothing in the control block or the rows needs resetting between launches.  After
-    // 2^24 launches the sequence wraps; stale flags are wiped then.
-    d->launch_seq++;
-    if((d->launch_seq & 0xffffffu) == 0)
-    {
-        d->launch_seq = 1;
-        cudaMemsetAsync(d->rows, 0, (size_t)(t->num_sms < kMaxGrid ? t->num_sms : kMaxGrid) * kRowChunks * sizeof(uint4), t->stream);
-        const int mg = t->num_sms < kMaxGrid ? t->num_sms : kMaxGrid;
-        cudaMemsetAsync(d->par, 0, ((size_t)kReplicas * kReplicaStride + 2 * (size_t)((mg + 7) & ~7)) * sizeof(uint4), t->stream);
-    }
-    A.epoch_base = d->launch_seq << 8;
-    A.par = d->par;
-    A.bslot = d->bslot;
-    A.bres = d->bres;
-    A.rows = d->rows;
-    A.out = d->out; // UVA: pinned + mapped host memory is addressable from the device
-    A.dbg = d->dbg;
-    A.cand_cap = d->cand_cap;
-    A.prework = d->prework;
-    for(int i = 0; i < kNumPyrs; i++)
-    {
-        A.lvl_cap[i] = d->lvl_cap[i];
-        A.lvl_off[i] = d->lvl_off[i];
-    }
-    A.make_derivatives = (A.rgb && !t->deriv_valid) ? 1 : 0;
-    A.icp_in_smem = d->icp_in_smem;
-
-    d->out->status = 0;
-    void * args[] = {&A};
+    BatchArgs B;
+    fill_args(t, d, d->lay, trans, rot, rgb_only, icp_weight, pyramid, fast_odom, so3, B.seq[0]);
+    void * args[] = {&B};
     const void * fn = d->dbg ? (const void *)k_track<true> : (const void *)k_track<false>;
-    cudaError_t e = cudaLaunchCooperativeKernel(fn, dim3(d->grid), dim3(kThreads), args, d->smem_bytes, t->stream);
+    cudaError_t e = cudaLaunchCooperativeKernel(fn, dim3(d->lay.grid), dim3(kThreads), args, d->lay.smem_bytes, t->stream);
     t->launches++;
     if(e != cudaSuccess)
     {
@@ -1891,7 +1963,7 @@ int EF_TRACK_FN(device_track_finish)(ef_tracker * t, float * trans, float * rot)
                 {
                     double sum = 0, mx = 0;
                     int cnt = 0;
-                    for(int c = 1; c < d->grid; c++)
+                    for(int c = 1; c < d->lay.grid; c++)
                     {
                         const long long * w = h + ((size_t)c * kMaxIters + it) * kDbgStamps;
                         if(w[from[ph]] == 0 || w[to[ph]] == 0) continue;
@@ -1913,5 +1985,49 @@ int EF_TRACK_FN(device_track_finish)(ef_tracker * t, float * trans, float * rot)
     }
     return EF_OK;
 }
+
+#else // EF_TRACK_GROUPS > 1: the batched build only launches; handles are created, configured and finished by their own variant
+
+// kGroups sequences (handles of one image size, each with its pyramids built and its streams joined) from ONE launch on
+// `stream`: group g of every CTA works for ts[g].  The shared memory of a CTA is split evenly, so a group keeps one level's
+// lists at a time (no preparation of finer levels ahead).  EF_ERR_UNSUPPORTED when a group's share cannot hold them.
+int EF_TRACK_FN(device_track_launch_batch)(ef_tracker * const * ts, const float * const * trans, const float * const * rot, int rgb_only, float icp_weight,
+                                           int pyramid, int fast_odom, int so3, cudaStream_t stream)
+{
+    static bool attr_set = false;
+    if(!attr_set)
+    {
+        cudaError_t e = cudaFuncSetAttribute(k_track<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
+        if(e != cudaSuccess) return (int)e;
+        attr_set = true;
+    }
+    ef_tracker * t0 = ts[0];
+    const int max_grid = t0->num_sms < kMaxGrid ? t0->num_sms : kMaxGrid;
+    Layout L;
+    if(!compute_layout(t0, max_grid, ((size_t)kMaxDynSmem / kGroups) & ~(size_t)15, L))
+    {
+        t0->err = "batched launch: image too large for a thread group's share of the shared memory";
+        return EF_ERR_UNSUPPORTED;
+    }
+    BatchArgs B;
+    for(int g = 0; g < kGroups; g++)
+    {
+        ef_tracker * t = ts[g];
+        DeviceTrack * d = static_cast<DeviceTrack *>(t->track_state);
+        if(!d || t->width != t0->width || t->height != t0->height || t->device != t0->device) return EF_ERR_INVALID_ARGUMENT;
+        fill_args(t, d, L, trans[g], rot[g], rgb_only, icp_weight, pyramid, fast_odom, so3, B.seq[g]);
+        B.seq[g].dbg = nullptr; // the clock64 trace is a single-launch diagnostic
+    }
+    void * args[] = {&B};
+    cudaError_t e = cudaLaunchCooperativeKernel((const void *)k_track<false>, dim3(L.grid), dim3(kThreads * kGroups), args, L.smem_bytes * kGroups, stream);
+    for(int g = 0; g < kGroups; g++) ts[g]->launches++;
+    if(e != cudaSuccess)
+    {
+        t0->err = std::string("cudaLaunchCooperativeKernel (batched): ") + cudaGetErrorString(e);
+        return (int)e;
+    }
+    return EF_OK;
+}
+#endif
 
 } // namespace ef

@@ -128,4 +128,8 @@ void device_track_destroy(ef_tracker * t);
 int device_track_launch(ef_tracker * t, const float * trans, const float * rot, int rgb_only, float icp_weight, int pyramid, int fast_odom,
                         int so3);
 int device_track_finish(ef_tracker * t, float * trans, float * rot);
+// the batched build of the tracker kernel: device_track_batch_width() sequences (handles) per launch
+int device_track_batch_width();
+int device_track_launch_batch(ef_tracker * const * ts, int n, const float * const * trans, const float * const * rot, int rgb_only, float icp_weight,
+                              int pyramid, int fast_odom, int so3, cudaStream_t stream);
 } // namespace ef

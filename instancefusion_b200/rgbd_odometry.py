@@ -315,3 +315,52 @@ class RGBDOdometry:
         self._check(self._L.ef_tracker_download(self._h, name.encode(), C.c_int(level), out.ctypes.data_as(C.c_void_p),
                                                 C.c_size_t(out.nbytes)), "ef_tracker_download")
         return out
+
+
+class BatchTracker:
+    """k independent sequences per kernel launch (ef_track_frames_to_model_batch): `trackers` = ef_batch_width() RGBDOdometry
+    handles of one image size.  track(frames, poses, ...) takes one frameToModel frame per handle -- frames[g] =
+    (vertices, normals, model_rgba, depth, rgba) as for RGBDOdometry.trackFrameToModel -- and returns [(trans, rot)] per handle;
+    the handles' public fields (lastICPError, lastA, ...) are updated as by their own calls."""
+
+    def __init__(self, trackers):
+        self._L = binding.lib()
+        self.n = len(trackers)
+        if self.n != self._L.ef_batch_width():
+            raise ValueError(f"a batch holds exactly {self._L.ef_batch_width()} trackers")
+        self.trackers = list(trackers)
+        self._handles = (C.c_void_p * self.n)(*[t._h for t in self.trackers])
+        self._inputs = (binding.FrameInputs * self.n)()
+        self._poses = np.zeros((self.n, 16), np.float32)
+        self._trans = np.zeros((self.n, 3), np.float32)
+        self._rot = np.zeros((self.n, 9), np.float32)
+        self._stats = (TrackStats * self.n)()
+        self._keep = None
+
+    def _fill(self, frames, poses, depthCutoff):
+        self._keep = frames
+        for g, (tr, f) in enumerate(zip(self.trackers, frames)):
+            fi = tr._frame_inputs(*f, depthCutoff)
+            C.memmove(C.byref(self._inputs[g]), C.byref(fi), C.sizeof(binding.FrameInputs))
+            self._poses[g] = np.asarray(poses[g], np.float32).reshape(16)
+
+    def launch(self, frames, poses, depthCutoff, rgbOnly, icpWeight, pyramid, fastOdom, so3):
+        self._fill(frames, poses, depthCutoff)
+        rc = self._L.ef_track_frames_to_model_batch_launch(self._handles, self.n, self._inputs, C.c_void_p(self._poses.ctypes.data), int(rgbOnly),
+                                                           C.c_float(icpWeight), int(pyramid), int(fastOdom), int(so3))
+        if rc != 0:
+            raise EFError(rc, "ef_track_frames_to_model_batch_launch", "; ".join(self._L.ef_last_error(t._h).decode() for t in self.trackers))
+
+    def finish(self):
+        return [t.finish() for t in self.trackers]
+
+    def track(self, frames, poses, depthCutoff, rgbOnly, icpWeight, pyramid, fastOdom, so3):
+        self._fill(frames, poses, depthCutoff)
+        rc = self._L.ef_track_frames_to_model_batch(self._handles, self.n, self._inputs, C.c_void_p(self._poses.ctypes.data),
+                                                    C.c_void_p(self._trans.ctypes.data), C.c_void_p(self._rot.ctypes.data), int(rgbOnly),
+                                                    C.c_float(icpWeight), int(pyramid), int(fastOdom), int(so3), self._stats)
+        if rc != 0:
+            raise EFError(rc, "ef_track_frames_to_model_batch", "; ".join(self._L.ef_last_error(t._h).decode() for t in self.trackers))
+        for g, t in enumerate(self.trackers):
+            C.memmove(C.byref(t._stats), C.byref(self._stats[g]), C.sizeof(TrackStats))
+        return [(self._trans[g].copy(), self._rot[g].reshape(3, 3).copy()) for g in range(self.n)]
