@@ -61,7 +61,10 @@
 #define EF_TRACK_CATG(a, c) EF_TRACK_CATG2(a, c)
 #define EF_TRACK_FN(name) EF_TRACK_CATG(name, EF_TRACK_GROUPS) // (one batched build per library, whatever its group size)
 #else
-#define EF_TRACK_FN(name) EF_TRACK_CAT(name, EF_TRACK_THREADS)
+#ifndef EF_TRACK_NAME_THREADS // the slot of ef_track_dispatch.cu this build fills (256 | 384); sweeps put other shapes into a slot
+#define EF_TRACK_NAME_THREADS EF_TRACK_THREADS
+#endif
+#define EF_TRACK_FN(name) EF_TRACK_CAT(name, EF_TRACK_NAME_THREADS)
 #endif
 
 namespace ef
