@@ -111,6 +111,17 @@ constexpr int kRgbBatch = EF_TRACK_RGB_BATCH; // photometric candidates of one t
 #endif
 constexpr bool kIcpSplit = EF_TRACK_ICP_SPLIT != 0;
 constexpr int kWarps = kThreads / 32;
+// Accumulator sets: the float sums of a launch are added in the order of EF_TRACK_SETS x kThreads VIRTUAL threads
+// (EF_TRACK_SETS x kWarps virtual warps), each physical thread keeping one accumulator set per virtual thread it stands for
+// (virtual thread = thread + set * kThreads; its pixels are the physical passes / candidate rounds with index = set modulo
+// EF_TRACK_SETS).  The single-launch builds use one set; the batched build runs groups of 128 threads with two, which makes
+// its summation tree the one of the 256-thread single launch: per handle it returns the same bits.
+#ifndef EF_TRACK_SETS
+#define EF_TRACK_SETS 1
+#endif
+constexpr int kSets = EF_TRACK_SETS;
+constexpr int kVWarps = kWarps * kSets;
+static_assert(kSets == 1 || kSets == 2, "EF_TRACK_SETS");
 constexpr int kMaxIters = 32;    // SE3 iterations per call (19 in the reference schedule)
 constexpr int kDbgStamps = 13; // 0..9 per iteration; 10..12 level start (first iteration of a level only)
 constexpr int kRowChunks = 20;   // a partial row = 20 x (3 floats + flag) = 60 floats >= 29 ICP + 29 RGB sums
@@ -118,7 +129,8 @@ constexpr int kRowFloats = kRowChunks * 3;
 constexpr int kSo3Chunks = 4;    // SO3 rows carry 11 floats
 constexpr int kLineChunks = 8;   // the parameter line = 8 x (3 floats + flag) = 24 floats
 constexpr int kPayload = kLineChunks * 3;
-constexpr int kParts = kThreads / 64; // final cross-CTA sum: kParts x 64 slots
+constexpr int kParts = kThreads / 64;  // final cross-CTA sum: kVParts x 64 slots, a thread adding kSets of them
+constexpr int kVParts = kParts * kSets;
 constexpr int kGatherBatch = 12; // row chunks a CTA-0 thread requests before it examines the first (147 x 20 / 256 = 11.5)
 #ifndef EF_TRACK_COMPACT_GROUP
 #define EF_TRACK_COMPACT_GROUP 3
@@ -299,17 +311,22 @@ __device__ __forceinline__ void gather_rows(const uint4 * rows, int workers, int
     const int slot = gtid() & 63, part = gtid() >> 6;
     if(part < kParts)
     {
-        float s = 0.f;
-        if(slot < nfl)
-            for(int w = part; w < workers; w += kParts) s += s_rows[w * nfl + slot];
-        s_red[part * 64 + slot] = s;
+#pragma unroll
+        for(int q = 0; q < kSets; q++)
+        {
+            const int vpart = part + q * kParts;
+            float s = 0.f;
+            if(slot < nfl)
+                for(int w = vpart; w < workers; w += kVParts) s += s_rows[w * nfl + slot];
+            s_red[vpart * 64 + slot] = s;
+        }
     }
     group_sync();
     if(gtid() < 64)
     {
         float tot = 0.f;
 #pragma unroll
-        for(int p = 0; p < kParts; p++) tot += s_red[p * 64 + gtid()];
+        for(int p = 0; p < kVParts; p++) tot += s_red[p * 64 + gtid()];
         s_final[gtid()] = tot;
     }
     group_sync();
@@ -374,6 +391,39 @@ __device__ __noinline__ void solve_pivoted(const double * S28, double * x6)
 // warps 0 and 1 of CTA 0: hand-over of resultRt from the solver warp to the warp that derives the photometric warp
 __device__ __forceinline__ void solver_pair_sync() { asm volatile("bar.sync %0, 64;" ::"r"(1u + kGroups + ggrp()) : "memory"); }
 
+
+// OdometryProvider.h:35-71 rodrigues(r) for the small rotations of a tracked frame; t2 = |r|^2
+__device__ __forceinline__ void rodrigues_small(double rx, double ry, double rz, double t2, double * R)
+{
+    if(t2 < 0.0625)
+    {
+        // R = cos(t) I + (1 - cos t) r^ r^T + sin(t) [r^]x  with r^ = r / t  (:52-68)
+        //   = (1 - B t^2) I + B r r^T + A [r]x,  A = sin(t)/t, B = (1 - cos t)/t^2: two short alternating series in t^2
+        // (|t| < 0.25 rad: 9 terms reach 2^-60), no square root, no division, no argument reduction -- a Gauss-Newton
+        // update of a tracked frame is a few milliradians.  Equal to the closed form to double rounding; t -> 0 gives the
+        // identity, which is also what the reference returns below DBL_EPSILON (:45).
+        double A = 1.0 / 121645100408832000.0, B = 1.0 / 2432902008176640000.0; // 1/19!, 1/20!
+        A = fma(-t2, A, 1.0 / 355687428096000.0);    B = fma(-t2, B, 1.0 / 6402373705728000.0);
+        A = fma(-t2, A, 1.0 / 1307674368000.0);      B = fma(-t2, B, 1.0 / 20922789888000.0);
+        A = fma(-t2, A, 1.0 / 6227020800.0);         B = fma(-t2, B, 1.0 / 87178291200.0);
+        A = fma(-t2, A, 1.0 / 39916800.0);           B = fma(-t2, B, 1.0 / 479001600.0);
+        A = fma(-t2, A, 1.0 / 362880.0);             B = fma(-t2, B, 1.0 / 3628800.0);
+        A = fma(-t2, A, 1.0 / 5040.0);               B = fma(-t2, B, 1.0 / 40320.0);
+        A = fma(-t2, A, 1.0 / 120.0);                B = fma(-t2, B, 1.0 / 720.0);
+        A = fma(-t2, A, 1.0 / 6.0);                  B = fma(-t2, B, 1.0 / 24.0);
+        A = fma(-t2, A, 1.0);                        B = fma(-t2, B, 0.5);
+        const double d = fma(-B, t2, 1.0);
+        const double bx = B * rx, by = B * ry, bz = B * rz;
+        R[0] = fma(bx, rx, d);             R[1] = fma(bx, ry, -(A * rz));    R[2] = fma(bx, rz, A * ry);
+        R[3] = fma(by, rx, A * rz);        R[4] = fma(by, ry, d);            R[5] = fma(by, rz, -(A * rx));
+        R[6] = fma(bz, rx, -(A * ry));     R[7] = fma(bz, ry, A * rx);       R[8] = fma(bz, rz, d);
+    }
+    else
+    {
+        const double xr[3] = {rx, ry, rz};
+        hm::rodrigues(xr, R);
+    }
+}
 
 // RGBDOdometry.cpp:515-516, :541-583 -- the reference's host step after a Gauss-Newton evaluation, run by WARP 0 of CTA 0
 // with NO lane parallelism: every lane runs the scalar routine on identical data (shared-memory broadcast loads), the 27
@@ -452,34 +502,7 @@ __device__ __forceinline__ void warp_solve_se3(Solver * S, const float * s_final
     const double rx = x[3], ry = x[4], rz = x[5];
     const double t2 = rx * rx + ry * ry + rz * rz;
     double R[9];
-    if(t2 < 0.0625)
-    {
-        // R = cos(t) I + (1 - cos t) r^ r^T + sin(t) [r^]x  with r^ = r / t  (:52-68)
-        //   = (1 - B t^2) I + B r r^T + A [r]x,  A = sin(t)/t, B = (1 - cos t)/t^2: two short alternating series in t^2
-        // (|t| < 0.25 rad: 9 terms reach 2^-60), no square root, no division, no argument reduction -- a Gauss-Newton
-        // update of a tracked frame is a few milliradians.  Equal to the closed form to double rounding; t -> 0 gives the
-        // identity, which is also what the reference returns below DBL_EPSILON (:45).
-        double A = 1.0 / 121645100408832000.0, B = 1.0 / 2432902008176640000.0; // 1/19!, 1/20!
-        A = fma(-t2, A, 1.0 / 355687428096000.0);    B = fma(-t2, B, 1.0 / 6402373705728000.0);
-        A = fma(-t2, A, 1.0 / 1307674368000.0);      B = fma(-t2, B, 1.0 / 20922789888000.0);
-        A = fma(-t2, A, 1.0 / 6227020800.0);         B = fma(-t2, B, 1.0 / 87178291200.0);
-        A = fma(-t2, A, 1.0 / 39916800.0);           B = fma(-t2, B, 1.0 / 479001600.0);
-        A = fma(-t2, A, 1.0 / 362880.0);             B = fma(-t2, B, 1.0 / 3628800.0);
-        A = fma(-t2, A, 1.0 / 5040.0);               B = fma(-t2, B, 1.0 / 40320.0);
-        A = fma(-t2, A, 1.0 / 120.0);                B = fma(-t2, B, 1.0 / 720.0);
-        A = fma(-t2, A, 1.0 / 6.0);                  B = fma(-t2, B, 1.0 / 24.0);
-        A = fma(-t2, A, 1.0);                        B = fma(-t2, B, 0.5);
-        const double d = fma(-B, t2, 1.0);
-        const double bx = B * rx, by = B * ry, bz = B * rz;
-        R[0] = fma(bx, rx, d);             R[1] = fma(bx, ry, -(A * rz));    R[2] = fma(bx, rz, A * ry);
-        R[3] = fma(by, rx, A * rz);        R[4] = fma(by, ry, d);            R[5] = fma(by, rz, -(A * rx));
-        R[6] = fma(bz, rx, -(A * ry));     R[7] = fma(bz, ry, A * rx);       R[8] = fma(bz, rz, d);
-    }
-    else
-    {
-        const double xr[3] = {rx, ry, rz};
-        hm::rodrigues(xr, R);
-    }
+    rodrigues_small(rx, ry, rz, t2, R);
     if(dbg) tk[3] = clock64();
     // OdometryProvider.h:73-93: resultRt = [R | x[0:3]] * resultRt
     double rt[12], N[12];
@@ -598,9 +621,11 @@ __device__ __noinline__ int solve_so3(Solver * S, const float * s_final, int it)
         for(int i = 0; i < 9; i++) S->so3_lastR[i] = S->so3_R[i];
         float delta[3];
         hm::ldlt_solve<float, 3>(jtj, jtr, delta);                               // :368
-        const double dd[3] = {delta[0], delta[1], delta[2]};
+        // (series form of the exponential map: no sincos / sqrt / division on the single solver thread, ~500 cycles less per
+        //  so3Step evaluation; equal to hm::rodrigues to double rounding)
+        const double dx = delta[0], dy = delta[1], dz = delta[2];
         double rotUpdate[9];
-        hm::rodrigues(dd, rotUpdate);
+        rodrigues_small(dx, dy, dz, dx * dx + dy * dy + dz * dz, rotUpdate);
         float ru[9], rl[9];
 #pragma unroll
         for(int i = 0; i < 9; i++)
@@ -880,12 +905,13 @@ __device__ __forceinline__ void rgb_assoc_cands(const LevelArgs & L, const RgbRe
 // phase B: RGBReduction::getProducts (reduce.cu:512-595) for B of this thread's candidates, again without control
 // flow: unmatched candidates contribute rows of exact zeros
 template<int B>
-__device__ __forceinline__ bool rgb_rows_batch(const RgbStepParams & SP, const CandStore & C, int n_cand, int j0, float * accR)
+__device__ __forceinline__ bool rgb_rows_batch(const RgbStepParams & SP, const CandStore & C, int n_cand, int j0, float (*accRs)[32])
 {
     bool any = false;
 #pragma unroll
     for(int k = 0; k < B; k++)
     {
+        float * accR = accRs[k % kSets]; // j0 is a multiple of kSets: round j0 + k belongs to virtual thread set k % kSets
         const int c = gtid() + (j0 + k) * kThreads;
         const int cc = c < n_cand ? c : 0;
         const unsigned rec = C.r0[cc];
@@ -912,7 +938,7 @@ __device__ __forceinline__ bool rgb_rows_batch(const RgbStepParams & SP, const C
     return any;
 }
 
-__device__ __forceinline__ bool rgb_rows_cands(const RgbStepParams & SP, const CandStore & C, int n_cand, float * accR)
+__device__ __forceinline__ bool rgb_rows_cands(const RgbStepParams & SP, const CandStore & C, int n_cand, float (*accR)[32])
 {
     const int rounds = (n_cand + kThreads - 1) / kThreads;
     bool any = false;
@@ -953,7 +979,7 @@ __device__ __forceinline__ void stage_batch(const LevelArgs & L, const UnitIter 
 // phase A2: ICPReduction (reduce.cu:285-347) for up to B of this thread's pixels (passes p0 .. p0 + B): all the
 // coalesced loads first, then the projections, then all the gathers, then the products
 template<int B, bool SMEM>
-__device__ __forceinline__ bool icp_batch(const LevelArgs & L, const IcpParams & IP, const UnitIter & U, int p0, int passes, float * accI,
+__device__ __forceinline__ bool icp_batch(const LevelArgs & L, const IcpParams & IP, const UnitIter & U, int p0, int passes, float (*accIs)[32],
                                           const float * s_vn, int cap)
 {
     const int cols = L.cols;
@@ -1002,6 +1028,7 @@ __device__ __forceinline__ bool icp_batch(const LevelArgs & L, const IcpParams &
     for(int k = 0; k < B; k++)
     {
         float row[7];
+        float * accI = accIs[k % kSets]; // p0 is a multiple of kSets: pass p0 + k belongs to virtual warp set k % kSets
         const bool ok = icp_finish_select(IP, vg[k], n[k], vp[k], np[k], row) && in1[k];
 #pragma unroll
         for(int i = 0; i < 7; i++) row[i] = ok ? row[i] : 0.f;
@@ -1023,10 +1050,11 @@ __device__ __forceinline__ bool icp_batch(const LevelArgs & L, const IcpParams &
 // batches -- gathers of batch k+1 issued before batch k is finished -- was measured: no gain in the ICP phase, which
 // is bound by instruction issue with two warps per scheduler, and the 255 registers it needs slow the other phases.)
 template<bool SMEM>
-__device__ __forceinline__ bool icp_passes(const LevelArgs & L, const IcpParams & IP, const UnitIter & U, int p_begin, int p_end, float * accI,
+__device__ __forceinline__ bool icp_passes(const LevelArgs & L, const IcpParams & IP, const UnitIter & U, int p_begin, int p_end, float (*accI)[32],
                                            const float * s_vn, int cap)
 {
-    static_assert(kIcpBatch >= 1 && kIcpBatch <= 4, "EF_TRACK_ICP_BATCH");
+    static_assert(kIcpBatch >= 1 && kIcpBatch <= 4 && kIcpBatch % kSets == 0, "EF_TRACK_ICP_BATCH (a multiple of EF_TRACK_SETS)");
+    static_assert(kRgbBatch % kSets == 0, "EF_TRACK_RGB_BATCH (a multiple of EF_TRACK_SETS)");
     bool any = false;
     int p = p_begin;
     for(; p + kIcpBatch <= p_end; p += kIcpBatch) any |= icp_batch<kIcpBatch, SMEM>(L, IP, U, p, p_end, accI, s_vn, cap);
@@ -1047,7 +1075,7 @@ __device__ __forceinline__ void sigma_from_sums(int sigma, int rgbSize, float & 
 // static shared memory of one thread group
 struct GroupShared
 {
-    float red[kWarps * 64];
+    float red[kVWarps * 64];
     float final_[64];
     float par[2][kPayload];
     float sigma[3];                // sigmaVal, rgbError, (float)rgbSize of the current iteration
@@ -1194,27 +1222,37 @@ __global__ void __launch_bounds__(kThreads * kGroups, 1) k_track(const __grid_co
             if(is_solver_cta) continue;
 
             // ---- workers: so3Step over this CTA's pixels ----
-            float acc[16];
+            float acc[kSets][16];
 #pragma unroll
-            for(int i = 0; i < 16; i++) acc[i] = 0.f;
-            for(int p = 0; p < passes; p++)
+            for(int q = 0; q < kSets; q++)
+#pragma unroll
+                for(int i = 0; i < 16; i++) acc[q][i] = 0.f;
+            for(int p = 0; p < passes; p += kSets)
             {
-                const int u = U.unit(p);
-                if(u >= 0)
+#pragma unroll
+                for(int q = 0; q < kSets; q++) // pass p + q belongs to virtual warp set q (p is a multiple of kSets)
                 {
-                    const int y = u / L.cols, x = u - y * L.cols;
-                    float row[4];
-                    if(so3_row(P, x, y, A.so3_last, A.so3_next, L.cols, row)) accumulate_so3(acc, row);
+                    const int u = (p + q < passes) ? U.unit(p + q) : -1;
+                    if(u >= 0)
+                    {
+                        const int y = u / L.cols, x = u - y * L.cols;
+                        float row[4];
+                        if(so3_row(P, x, y, A.so3_last, A.so3_next, L.cols, row)) accumulate_so3(acc[q], row);
+                    }
                 }
             }
-            const float lane_value = warp_transpose_reduce16(acc);
-            if(lane < 16) s_red[warp * 16 + lane] = lane_value;
+#pragma unroll
+            for(int q = 0; q < kSets; q++)
+            {
+                const float lane_value = warp_transpose_reduce16(acc[q]);
+                if(lane < 16) s_red[(warp + q * kWarps) * 16 + lane] = lane_value;
+            }
             group_sync();
             if(gtid() < 16)
             {
                 float s = 0.f;
 #pragma unroll
-                for(int w = 0; w < kWarps; w++) s += s_red[w * 16 + gtid()];
+                for(int w = 0; w < kVWarps; w++) s += s_red[w * 16 + gtid()];
                 s_final[gtid()] = (gtid() < 11) ? s : 0.f;
             }
             group_sync();
@@ -1337,9 +1375,11 @@ __global__ void __launch_bounds__(kThreads * kGroups, 1) k_track(const __grid_co
             // ICP passes done before the photometric association (EF_TRACK_ICP_SPLIT: measured slower at 640x480 -- two
             // short batches cost more L2 round trips than the hidden parameter latency saves -- so off by default)
             const int split = (kIcpSplit && A.icp && A.rgb && passes >= 4) ? passes / 2 : 0;
-            float accI[32];
+            float accI[kSets][32];
 #pragma unroll
-            for(int i = 0; i < 32; i++) accI[i] = 0.f;
+            for(int q = 0; q < kSets; q++)
+#pragma unroll
+                for(int i = 0; i < 32; i++) accI[q][i] = 0.f;
             bool anyI = false;
             if(is_solver_cta)
             {
@@ -1426,14 +1466,22 @@ __global__ void __launch_bounds__(kThreads * kGroups, 1) k_track(const __grid_co
             // ---- workers, phase A2: the remaining ICP pixels (hides the barrier-B round trip and the inter-CTA skew) ----
             if(!is_solver_cta)
             {
-                float vi = 0.f;
+                float vi[kSets];
+#pragma unroll
+                for(int q = 0; q < kSets; q++) vi[q] = 0.f;
                 if(A.icp)
                 {
                     anyI |= A.icp_in_smem ? icp_passes<true>(L, IP, U, split, passes, accI, s_vn, A.lvl_cap[lv])
                                           : icp_passes<false>(L, IP, U, split, passes, accI, s_vn, A.lvl_cap[lv]);
-                    if(__any_sync(kFullMask, anyI)) vi = warp_transpose_reduce32(accI); // a warp without pixels contributes zeros
+                    if(__any_sync(kFullMask, anyI)) // a warp without pixels contributes zeros
+                    {
+#pragma unroll
+                        for(int q = 0; q < kSets; q++) vi[q] = warp_transpose_reduce32(accI[q]);
+                    }
                 }
-                if(lane < 29) s_red[warp * 64 + lane] = vi;
+#pragma unroll
+                for(int q = 0; q < kSets; q++)
+                    if(lane < 29) s_red[(warp + q * kWarps) * 64 + lane] = vi[q];
                 stamp(8);
             }
 
@@ -1519,16 +1567,26 @@ __global__ void __launch_bounds__(kThreads * kGroups, 1) k_track(const __grid_co
 
             // ---- workers, phase B: photometric rows from the records in shared memory -> 29 more sums ----
             {
-                float vr = 0.f;
+                float vr[kSets];
+#pragma unroll
+                for(int q = 0; q < kSets; q++) vr[q] = 0.f;
                 if(A.rgb)
                 {
-                    float accR[32];
+                    float accR[kSets][32];
 #pragma unroll
-                    for(int i = 0; i < 32; i++) accR[i] = 0.f;
+                    for(int q = 0; q < kSets; q++)
+#pragma unroll
+                        for(int i = 0; i < 32; i++) accR[q][i] = 0.f;
                     const bool any = rgb_rows_cands(SP, C, n_cand, accR);
-                    if(__any_sync(kFullMask, any)) vr = warp_transpose_reduce32(accR);
+                    if(__any_sync(kFullMask, any))
+                    {
+#pragma unroll
+                        for(int q = 0; q < kSets; q++) vr[q] = warp_transpose_reduce32(accR[q]);
+                    }
                 }
-                if(lane < 29) s_red[warp * 64 + 29 + lane] = vr;
+#pragma unroll
+                for(int q = 0; q < kSets; q++)
+                    if(lane < 29) s_red[(warp + q * kWarps) * 64 + 29 + lane] = vr[q];
                 group_sync();
                 if(gtid() < kRowFloats)
                 {
@@ -1536,7 +1594,7 @@ __global__ void __launch_bounds__(kThreads * kGroups, 1) k_track(const __grid_co
                     if(gtid() < 58)
                     {
 #pragma unroll
-                        for(int w = 0; w < kWarps; w++) sum += s_red[w * 64 + gtid()];
+                        for(int w = 0; w < kVWarps; w++) sum += s_red[w * 64 + gtid()];
                     }
                     s_final[gtid()] = sum;
                 }

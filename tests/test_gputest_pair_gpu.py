@@ -72,7 +72,7 @@ def test_gputest_png_pair_matches_reference_cuda(solve_mode):
             print(f"\n[gputest pair {name}] |dt| {dt:.1e} m, rotation {dr:.1e} rad (reference vs itself: {spread['t']:.1e} / {spread['r']:.1e})")
             assert prod.se3_iterations == st["se3_iterations"] and prod.so3_iterations == st["so3_iterations"], name
             if not m["rgbOnly"]:
-                assert abs(prod.lastICPCount - st["last_icp_count"]) <= max(1e-4 * st["last_icp_count"], util.RefEnsemble.K * spread["icp"]), (name, spread)
+                assert abs(prod.lastICPCount - st["last_icp_count"]) <= max(2e-4 * st["last_icp_count"], util.RefEnsemble.K * spread["icp"]), (name, spread)
             if m["so3"]:
                 assert prod.lastSO3Count == st["last_so3_count"], name
             if m["rgbOnly"] or m["icpWeight"] < 100:
