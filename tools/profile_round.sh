@@ -8,8 +8,8 @@
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 B="python bench.py --steps 6 --warmup 3 --frames 12 --no-e2e --no-720p --no-levels --cpu-sample 0"
-timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_r02.csv $B > gpurun_out/launches_r02.out 2>&1
-timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/launches_r02_ref.csv python bench.py --impl reference --ref-sweep 0 --steps 3 --warmup 2 --frames 8 > gpurun_out/launches_r02_ref.out 2>&1
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'k_[a-z]' -c 400 --csv --log-file gpurun_out/launches_r02.csv $B > gpurun_out/launches_r02.out 2>&1
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'Kernel|reduceSum|pyrDown|bgr2Intensity' -c 3000 --csv --log-file gpurun_out/launches_r02_ref.csv python bench.py --impl reference --ref-sweep 0 --steps 3 --warmup 2 --frames 8 > gpurun_out/launches_r02_ref.out 2>&1
 timeout 400 ncu --set full --clock-control none --import-source on -k regex:k_track -s 6 -c 3 -f -o gpurun_out/prof_track_r02 $B > gpurun_out/prof_track_r02.out 2>&1
 timeout 400 ncu --set full --clock-control none --import-source on -k regex:k_track -s 6 -c 3 -f -o gpurun_out/prof_track720_r02 $B --width 1280 --height 720 --so3 1 > gpurun_out/prof_track720_r02.out 2>&1
 timeout 400 ncu --set full --clock-control none --import-source on -k regex:k_build_frame -s 6 -c 3 -f -o gpurun_out/prof_build_r02 $B > gpurun_out/prof_build_r02.out 2>&1
