@@ -80,16 +80,22 @@ namespace
 
 constexpr int kThreads = EF_TRACK_THREADS; // threads of a group; 8 warps, up to 255 registers each: measured best of {128..640} (tools/sweep.sh)
 constexpr int kGroups = EF_TRACK_GROUPS;   // independent sequences per launch (thread groups per CTA)
-static_assert(kGroups >= 1 && kGroups <= 4 && kThreads * kGroups <= 1024, "EF_TRACK_GROUPS");
+static_assert(kGroups >= 1 && kGroups <= 2 && kThreads * kGroups <= 1024, "EF_TRACK_GROUPS");
 
 // thread index within its group / group index (warp-uniform: kThreads is a multiple of 32)
 __device__ __forceinline__ unsigned gtid() { return kGroups > 1 ? threadIdx.x % kThreads : threadIdx.x; }
 __device__ __forceinline__ unsigned ggrp() { return kGroups > 1 ? threadIdx.x / kThreads : 0u; }
 // barrier of one group: the whole CTA in the single build, named barrier 1 + g of kThreads threads in the batched one
+// (immediate barrier numbers: ptxas then knows which barriers the kernel uses, and compute-sanitizer's synccheck can follow them)
 __device__ __forceinline__ void group_sync()
 {
     if constexpr(kGroups == 1) __syncthreads();
-    else asm volatile("bar.sync %0, %1;" ::"r"(1u + ggrp()), "n"(kThreads) : "memory");
+    else
+    {
+        static_assert(kGroups <= 2, "one immediate barrier number per group");
+        if(ggrp() == 0) asm volatile("bar.sync 1, %0;" ::"n"(kThreads) : "memory");
+        else asm volatile("bar.sync 2, %0;" ::"n"(kThreads) : "memory");
+    }
 }
 #ifndef EF_TRACK_ICP_BATCH
 #if EF_TRACK_THREADS >= 384
@@ -389,7 +395,17 @@ __device__ __noinline__ void solve_pivoted(const double * S28, double * x6)
 }
 
 // warps 0 and 1 of CTA 0: hand-over of resultRt from the solver warp to the warp that derives the photometric warp
-__device__ __forceinline__ void solver_pair_sync() { asm volatile("bar.sync %0, 64;" ::"r"(1u + kGroups + ggrp()) : "memory"); }
+// (out of line: both warps then wait at ONE barrier instruction -- bar.sync pairs warps by barrier number, not by address, but
+//  compute-sanitizer's synccheck reports arrivals from different addresses as divergence; a call costs ~20 cycles per iteration)
+__device__ __noinline__ void solver_pair_sync()
+{
+    if constexpr(kGroups == 1) asm volatile("bar.sync 1, 64;" ::: "memory");
+    else
+    {
+        if(ggrp() == 0) asm volatile("bar.sync 3, 64;" ::: "memory");
+        else asm volatile("bar.sync 4, 64;" ::: "memory");
+    }
+}
 
 
 // OdometryProvider.h:35-71 rodrigues(r) for the small rotations of a tracked frame; t2 = |r|^2
@@ -519,6 +535,7 @@ __device__ __forceinline__ void warp_solve_se3(Solver * S, const float * s_final
             N[r * 4 + c] = (c == 3) ? v + x[r] : v;
         }
     // every lane stores the same values (one transaction per entry); warp 1 derives the photometric warp from them
+    __syncwarp(); // all lanes have read the old matrix (they run in lock step anyway; this states it for racecheck)
 #pragma unroll
     for(int i = 0; i < 12; i++) S->resultRt[i] = N[i];
     if(hand_over) solver_pair_sync();

@@ -1,21 +1,32 @@
 #!/bin/bash
-# tools/sanitize.sh [outdir] -- the GPU parity tests of the tracker under compute-sanitizer (memcheck, then initcheck),
-# with the product library as the only instrumented code of interest.  The persistent tracker kernel spins on relaxed
-# global loads; under the sanitizer it runs 10-50x slower but must still terminate, read no uninitialised device memory
-# and touch nothing outside its arena.  Logs: <outdir>/sanitize_memcheck.log, <outdir>/sanitize_initcheck.log.
-# Small images keep the run within minutes.  Run on the GPU box:  bash tools/sanitize.sh gpurun_out
+# tools/sanitize.sh [outdir] -- GPU tests of the tracker under compute-sanitizer, memcheck then initcheck.
+# The persistent tracker kernel spins on relaxed global loads; under the sanitizer it runs 10-50x slower but must still
+# terminate, touch nothing outside its buffers and read no uninitialised device memory.
+#   memcheck : product AND reference kernels (parity tests at small sizes, degenerate geometry, cudaArray entries)
+#   initcheck: product-only tests -- the reference library itself trips initcheck (DeviceMemory::download copies its
+#              result struct's never-written tail, 228 reports in round 2), which would bury anything of ours
+# Logs: <outdir>/sanitize_memcheck.log, <outdir>/sanitize_initcheck.log (+ .pytest.log).  Run on the GPU box.
 out=${1:-gpurun_out}
 mkdir -p "$out"
 cd "$(dirname "$0")/.."
-SEL='tests/test_tracker_edge_gpu.py::test_ragged_sizes_match_reference tests/test_tracker_edge_gpu.py::test_empty_depth_and_black_image_do_not_hang_and_keep_the_pose tests/test_tracker_edge_gpu.py::test_degenerate_geometry_icp_only tests/test_array_entry_gpu.py::test_same_entry_twice_keeps_both_calls_apart'
+E=tests/test_tracker_edge_gpu.py
+MEM="$E::test_ragged_sizes_match_reference $E::test_empty_depth_and_black_image_do_not_hang_and_keep_the_pose $E::test_degenerate_geometry_icp_only tests/test_array_entry_gpu.py::test_same_entry_twice_keeps_both_calls_apart tests/test_batch_gpu.py::test_batched_launch_equals_single_launches_bit_for_bit"
+MEMK="168 or 96 or 321 or empty or plane or twice or size1"
+INIT="$E::test_empty_depth_and_black_image_do_not_hang_and_keep_the_pose $E::test_sparse_depth_matches_host_mode $E::test_sm_subsets_give_the_same_pose $E::test_unaligned_device_inputs_take_the_chained_builders $E::test_deferred_build_through_the_reference_calls tests/test_array_entry_gpu.py::test_same_entry_twice_keeps_both_calls_apart tests/test_batch_gpu.py::test_batched_launch_equals_single_launches_bit_for_bit tests/test_predict.py"
+INITK="not size0"
 rc=0
-for tool in memcheck initcheck; do
-  timeout ${SANITIZE_TIMEOUT:-900} compute-sanitizer --tool $tool --error-exitcode 86 --launch-timeout 600 \
-      --kernel-name kns=2ef --log-file "$out/sanitize_$tool.log" \
-      python -m pytest $SEL -x -q -m gpu -k "${SANITIZE_K:-168 or 96 or 321 or empty or plane or twice}" > "$out/sanitize_$tool.pytest.log" 2>&1
+run() { # tool, tests, -k expression
+  timeout ${SANITIZE_TIMEOUT:-900} compute-sanitizer --tool $1 --error-exitcode 86 --launch-timeout 600 --print-limit 400 \
+      --log-file "$out/sanitize_$1.log" python -m pytest $2 -q -m gpu -k "$3" > "$out/sanitize_$1.pytest.log" 2>&1
   code=$?
-  echo "[$tool] exit code $code" | tee -a "$out/sanitize_$tool.log"
-  tail -3 "$out/sanitize_$tool.pytest.log" | tee -a "$out/sanitize_$tool.log"
+  echo "[$1] exit code $code" | tee -a "$out/sanitize_$1.log"
+  tail -3 "$out/sanitize_$1.pytest.log" | tee -a "$out/sanitize_$1.log"
   [ $code -ne 0 ] && rc=$code
-done
+}
+run memcheck "$MEM" "$MEMK"
+run initcheck "$INIT" "$INITK"
+# shared-memory hazards and barrier misuse of the persistent kernel (named barriers per thread group in the batched build)
+SMALL="$E::test_empty_depth_and_black_image_do_not_hang_and_keep_the_pose $E::test_sparse_depth_matches_host_mode tests/test_batch_gpu.py::test_batched_launch_equals_single_launches_bit_for_bit"
+run racecheck "$SMALL" "not size0 and not size2"
+run synccheck "$SMALL" "not size0 and not size2"
 exit $rc
