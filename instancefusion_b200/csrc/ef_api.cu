@@ -934,6 +934,21 @@ static int iter_graph_for(ef_tracker * t, int i, bool icp, bool rgb)
     const float zero9[9] = {0}, zero3[3] = {0};
     EF_CUDA(t, cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
     cudaError_t e = cudaMemcpyAsync(const_cast<IterParams *>(d_it), t->h_result + kHIter, sizeof(IterParams), cudaMemcpyHostToDevice, s);
+    // two branches after the parameter upload: the photometric pair (residual -> step, which needs the residual's sums) and the
+    // ICP step, which depends on neither -- captured on an internal stream so that the graph runs them side by side
+    cudaStream_t si = s;
+    if(icp && rgb && t->aux_streams && e == cudaSuccess)
+    {
+        e = cudaEventRecord(t->ev_fork, s);
+        if(e == cudaSuccess) e = cudaStreamWaitEvent(t->aux[0], t->ev_fork, 0);
+        si = t->aux[0];
+    }
+    if(icp)
+    {
+        if(e == cudaSuccess) e = launch_icp_step(icp_args(t, i, zero9, zero3, zero9, zero3), gs + 2 * kScratchBytes, si, d_it);
+        if(e == cudaSuccess)
+            e = cudaMemcpyAsync(t->h_result + kHIcp, gs + 2 * kScratchBytes + kScratchResultOff, 29 * sizeof(float), cudaMemcpyDeviceToHost, si);
+    }
     if(rgb)
     {
         if(e == cudaSuccess) e = launch_rgb_residual(rgb_res_args(t, i, zero9, zero3), gs, s, d_it);
@@ -943,11 +958,12 @@ static int iter_graph_for(ef_tracker * t, int i, bool icp, bool rgb)
         if(e == cudaSuccess)
             e = cudaMemcpyAsync(t->h_result + kHRgb, gs + kScratchBytes + kScratchResultOff, 29 * sizeof(float), cudaMemcpyDeviceToHost, s);
     }
-    if(icp)
+    if(si != s)
     {
-        if(e == cudaSuccess) e = launch_icp_step(icp_args(t, i, zero9, zero3, zero9, zero3), gs + 2 * kScratchBytes, s, d_it);
-        if(e == cudaSuccess)
-            e = cudaMemcpyAsync(t->h_result + kHIcp, gs + 2 * kScratchBytes + kScratchResultOff, 29 * sizeof(float), cudaMemcpyDeviceToHost, s);
+        // join (also on failure: an unjoined stream would invalidate the capture's end)
+        const cudaError_t ej = cudaEventRecord(t->ev_join[0], si);
+        const cudaError_t ew = ej == cudaSuccess ? cudaStreamWaitEvent(s, t->ev_join[0], 0) : ej;
+        if(e == cudaSuccess) e = ew;
     }
     cudaGraph_t g = nullptr;
     const cudaError_t e2 = cudaStreamEndCapture(s, &g);
