@@ -30,6 +30,9 @@
 #include <string>
 
 #include "../ef_track.h"
+#ifdef EF_COMPAT_WITH_STOPWATCH
+#include "Stopwatch.h" /* Core/src/Utils/Stopwatch.h of the including project */
+#endif
 
 #ifndef EF_COMPAT_CUSTOM_TEXTURE_MAPPING
 #include "../GPUTexture.h" /* Core/src/GPUTexture.h: `cudaGraphicsResource * cudaRes`, registered at construction (GPUTexture.cpp:40-47) */
@@ -143,6 +146,18 @@ class RGBDOdometry
             for(int j = 0; j < 6; j++) lastA(i, j) = st.last_A[i * 6 + j];
             lastb(i, 0) = st.last_b[i];
         }
+#ifdef EF_COMPAT_WITH_STOPWATCH
+        /* the reference's TICK / TOCK keys of this function (RGBDOdometry.cpp:333-538), for GPUTest.cpp:283-286 and the GUI's plots;
+         * Stopwatch counts microseconds (Utils/Stopwatch.h:100-106) */
+        ef_stage_times tm;
+        if(ef_tracker_stage_times(handle, &tm) == 0 && tm.solve_mode == EF_SOLVE_HOST)
+        {
+            Stopwatch::getInstance().addStopwatchTiming("so3Step", (unsigned long long)(tm.so3_step_ms * 1000.f));
+            Stopwatch::getInstance().addStopwatchTiming("computeRgbResidual", (unsigned long long)(tm.rgb_residual_ms * 1000.f));
+            Stopwatch::getInstance().addStopwatchTiming("icpStep", (unsigned long long)(tm.icp_step_ms * 1000.f));
+            Stopwatch::getInstance().addStopwatchTiming("rgbStep", (unsigned long long)(tm.rgb_step_ms * 1000.f));
+        }
+#endif
     }
 
     /* RGBDOdometry.cpp:605-608 */

@@ -224,6 +224,23 @@ long long ef_tracker_launch_count(const ef_tracker * t);
  * getIncrementalTransformation -- the persistent tracker kernel in EF_SOLVE_DEVICE, the whole step loop in
  * EF_SOLVE_HOST -- accumulated over `calls` calls since the last read; reading resets the accumulator. */
 int ef_tracker_profile(ef_tracker * t, double * solve_ms_total, long long * calls);
+/* The reference's Stopwatch keys on this path (Utils/RGBDOdometry.cpp:333/346 "so3Step", :441/458 "computeRgbResidual", :493/512
+ * "icpStep", :523/538 "rgbStep"; Utils/Stopwatch.h:59-82): wall-clock milliseconds around the blocking operator call, the LAST
+ * call of each operator winning like the reference's TICK / TOCK pairs (GPUTest.cpp:283-286 reads exactly these), plus their sums
+ * over the last getIncrementalTransformation.  Filled in EF_SOLVE_HOST, where the operators are separate blocking calls; with
+ * EF_OPT_USE_GRAPH one replayed graph holds all operators of an iteration and its time goes to iteration_ms; in EF_SOLVE_DEVICE
+ * the whole solve is one kernel: only call_ms is set (per-level device times: ef_tracker_trace, whole-solve device time:
+ * ef_tracker_profile).  include/compat/RGBDOdometry.h forwards them to Stopwatch when EF_COMPAT_WITH_STOPWATCH is defined. */
+typedef struct ef_stage_times
+{
+    float so3_step_ms, rgb_residual_ms, icp_step_ms, rgb_step_ms;                 /* last call of each operator */
+    float so3_step_sum_ms, rgb_residual_sum_ms, icp_step_sum_ms, rgb_step_sum_ms; /* over the last getIncrementalTransformation */
+    float iteration_ms, iteration_sum_ms;                                         /* EF_OPT_USE_GRAPH: one replayed iteration */
+    float call_ms;                                                                /* the whole getIncrementalTransformation, launch to result */
+    int solve_mode;                                                               /* EF_SOLVE_HOST | EF_SOLVE_DEVICE of that call */
+} ef_stage_times;
+int ef_tracker_stage_times(ef_tracker * t, ef_stage_times * out);
+
 /* Per-iteration trace of the persistent tracker kernel, for handles created with EF_TRACK_TIMING=1 in the environment (the
  * kernel then stamps clock64 at its phase boundaries; EF_TRACK_TIMING_PRINT=1 also prints the phase table when the handle
  * is destroyed): cycles32[i] = SM clock of the solver CTA at the top of Gauss-Newton iteration i (in launch order: level 2

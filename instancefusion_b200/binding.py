@@ -26,6 +26,12 @@ class TrackStats(C.Structure):
                 ("so3_iterations", C.c_int), ("se3_iterations", C.c_int * 3)]
 
 
+class StageTimes(C.Structure):
+    """ef_stage_times (include/ef_track.h): the reference's Stopwatch keys"""
+    _fields_ = [(n, C.c_float) for n in ("so3_step_ms", "rgb_residual_ms", "icp_step_ms", "rgb_step_ms", "so3_step_sum_ms", "rgb_residual_sum_ms",
+                                         "icp_step_sum_ms", "rgb_step_sum_ms", "iteration_ms", "iteration_sum_ms", "call_ms")] + [("solve_mode", C.c_int)]
+
+
 class FrameInputs(C.Structure):
     """ef_frame_inputs (include/ef_track.h)"""
     _fields_ = [("vertices_rgba32f", C.c_void_p), ("normals_rgba32f", C.c_void_p), ("model_rgba8", C.c_void_p), ("depth", C.c_void_p),
@@ -73,7 +79,7 @@ EXPORTED = [
     "ef_init_first_rgb_host",
     "ef_get_incremental_transformation", "ef_get_incremental_transformation_launch",
     "ef_get_incremental_transformation_finish", "ef_track_frame_to_model_launch", "ef_track_frame_to_model", "ef_batch_width", "ef_track_frames_to_model_batch_launch",
-    "ef_track_frames_to_model_batch", "ef_get_covariance", "ef_tracker_download", "ef_tracker_launch_count", "ef_tracker_profile", "ef_tracker_trace",
+    "ef_track_frames_to_model_batch", "ef_get_covariance", "ef_tracker_download", "ef_tracker_launch_count", "ef_tracker_profile", "ef_tracker_trace", "ef_tracker_stage_times",
     "ef_op_pyr_down_u16", "ef_op_create_vmap", "ef_op_create_nmap", "ef_op_transform_maps", "ef_op_copy_maps",
     "ef_op_resize_map", "ef_op_vertices_to_depth", "ef_op_pyr_down_gauss_f32", "ef_op_pyr_down_gauss_u8",
     "ef_op_bgr_to_intensity", "ef_op_depth_bilateral", "ef_op_depth_metric", "ef_op_derivative_images", "ef_op_project_point_cloud", "ef_op_icp_step",

@@ -11,6 +11,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <chrono>
 #include <new>
 #include <utility>
 
@@ -239,6 +240,7 @@ EF_API int ef_tracker_create(int width, int height, float cx, float cy, float fx
     for(int i = 0; i < kNumPyrs; i++) t->iter_graph[0][i] = t->iter_graph[1][i] = nullptr;
     for(int i = 0; i < kNumPyrs; i++) t->iter_graph_key[0][i] = t->iter_graph_key[1][i] = 0;
     memset(&t->st, 0, sizeof(t->st));
+    memset(&t->stages, 0, sizeof(t->stages));
     t->st.last_icp_count = t->st.last_rgb_count = t->st.last_so3_count = (float)(width * height); // RGBDOdometry.cpp:26-31
 
     cudaError_t e = cudaGetDevice(&t->device);
@@ -451,6 +453,13 @@ EF_API int ef_tracker_profile(ef_tracker * t, double * ms, long long * calls)
     *calls = t->prof_calls;
     t->prof_ms = 0.0;
     t->prof_calls = 0;
+    return EF_OK;
+}
+
+EF_API int ef_tracker_stage_times(ef_tracker * t, ef_stage_times * out)
+{
+    if(!t || !out) return EF_ERR_INVALID_ARGUMENT;
+    *out = t->stages;
     return EF_OK;
 }
 
@@ -975,6 +984,26 @@ static int iter_graph_for(ef_tracker * t, int i, bool icp, bool rgb)
     return EF_OK;
 }
 
+// The reference brackets its four step operators with Stopwatch TICK / TOCK (Utils/RGBDOdometry.cpp:333/346 so3Step, :441/458
+// computeRgbResidual, :493/512 icpStep, :523/538 rgbStep): wall-clock milliseconds around the blocking call, the LAST pair
+// winning (Utils/Stopwatch.h:59-82; GPUTest.cpp:283-286 reads them).  Same keys, same meaning, plus the sums over one
+// getIncrementalTransformation.
+namespace
+{
+struct StageTimer
+{
+    float * last, * sum;
+    std::chrono::steady_clock::time_point t0;
+    StageTimer(float & l, float & s) : last(&l), sum(&s), t0(std::chrono::steady_clock::now()) {}
+    ~StageTimer()
+    {
+        const float ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        *last = ms;
+        *sum += ms;
+    }
+};
+} // namespace
+
 static int fetch_result(ef_tracker * t, int nfloats)
 {
     EF_CUDA(t, cudaMemcpyAsync(t->h_result, static_cast<char *>(t->scratch) + kScratchResultOff, nfloats * sizeof(float), cudaMemcpyDeviceToHost,
@@ -1046,8 +1075,12 @@ static int track_host(ef_tracker * t, float * trans, float * rot, int rgb_only, 
             a.image_pitch = 0;
             for(int k = 0; k < 9; k++) { a.image_basis[k] = (float)H[k]; a.kinv[k] = (float)K_inv[k]; a.krlr[k] = (float)KR[k]; }
             a.rows = t->dims[lvl].rows; a.cols = t->dims[lvl].cols;
-            EF_LAUNCH(t, launch_so3_step(a, t->scratch, s));
-            int rc = fetch_result(t, 11);
+            int rc;
+            {
+                StageTimer tick(t->stages.so3_step_ms, t->stages.so3_step_sum_ms);
+                EF_LAUNCH(t, launch_so3_step(a, t->scratch, s));
+                rc = fetch_result(t, 11);
+            }
             if(rc) return rc;
             float jtj[9], jtr[3], residual[2];
             hm::unpack_so3(t->h_result, jtj, jtr, residual);
@@ -1119,9 +1152,13 @@ static int track_host(ef_tracker * t, float * trans, float * rot, int rgb_only, 
                 memcpy(h->Rprev_inv, Rprev_inv, sizeof(Rprev_inv)); memcpy(h->tprev, tprev, sizeof(tprev));
                 memcpy(h->krkinv, krkInv, sizeof(krkInv)); memcpy(h->kt, kt, sizeof(kt));
                 h->rgb_only = rgb_only ? 1 : 0;
-                EF_CUDA(t, cudaGraphLaunch(t->iter_graph[t->image_parity][i], s));
-                t->launches += (rgb ? 2 : 0) + (icp ? 1 : 0);
-                EF_CUDA(t, cudaStreamSynchronize(s));
+                {
+                    // (one replayed graph = all operators of the iteration: its time goes to the iteration key)
+                    StageTimer tick(t->stages.iteration_ms, t->stages.iteration_sum_ms);
+                    EF_CUDA(t, cudaGraphLaunch(t->iter_graph[t->image_parity][i], s));
+                    t->launches += (rgb ? 2 : 0) + (icp ? 1 : 0);
+                    EF_CUDA(t, cudaStreamSynchronize(s));
+                }
                 if(rgb)
                 {
                     rgbSize = reinterpret_cast<const int *>(t->h_result + kHResid)[0];
@@ -1132,6 +1169,7 @@ static int track_host(ef_tracker * t, float * trans, float * rot, int rgb_only, 
             }
             else if(rgb)
             {
+                StageTimer tick(t->stages.rgb_residual_ms, t->stages.rgb_residual_sum_ms);
                 EF_LAUNCH(t, launch_rgb_residual(rgb_res_args(t, i, krkInv, kt), t->scratch, s));
                 const int rc = fetch_result(t, 2);
                 if(rc) return rc;
@@ -1152,6 +1190,7 @@ static int track_host(ef_tracker * t, float * trans, float * rot, int rgb_only, 
             {
                 if(!t->use_graph)
                 {
+                    StageTimer tick(t->stages.icp_step_ms, t->stages.icp_step_sum_ms);
                     EF_LAUNCH(t, launch_icp_step(icp_args(t, i, Rcurr, tcurr, Rprev_inv, tprev), t->scratch, s));
                     const int rc = fetch_result(t, 29);
                     if(rc) return rc;
@@ -1166,6 +1205,7 @@ static int track_host(ef_tracker * t, float * trans, float * rot, int rgb_only, 
             {
                 if(!t->use_graph)
                 {
+                    StageTimer tick(t->stages.rgb_step_ms, t->stages.rgb_step_sum_ms);
                     EF_LAUNCH(t, launch_rgb_step(rgb_step_args(t, i, sigmaVal), t->scratch, s));
                     const int rc = fetch_result(t, 29);
                     if(rc) return rc;
@@ -1236,6 +1276,10 @@ EF_API int ef_get_incremental_transformation_launch(ef_tracker * t, const float 
     memcpy(t->pending.rot, rot, sizeof(t->pending.rot));
     t->pending.rgb_only = rgb_only; t->pending.icp_weight = icp_weight; t->pending.pyramid = pyramid;
     t->pending.fast_odom = fast_odom; t->pending.so3 = so3;
+    t->stages.so3_step_sum_ms = t->stages.rgb_residual_sum_ms = t->stages.icp_step_sum_ms = t->stages.rgb_step_sum_ms = 0.f;
+    t->stages.iteration_sum_ms = 0.f;
+    t->stages.solve_mode = t->solve_mode;
+    t->call_begin = std::chrono::steady_clock::now();
     if(t->solve_mode == EF_SOLVE_DEVICE)
     {
         // computeDerivativeImages (RGBDOdometry.cpp:436-440) is fused into the tracker kernel: every worker CTA derives
@@ -1286,6 +1330,7 @@ EF_API int ef_get_incremental_transformation_finish(ef_tracker * t, float * tran
         }
     }
     if(rc) return rc;
+    t->stages.call_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t->call_begin).count();
     if(t->ev_pending)
     {
         float ms = 0.f;

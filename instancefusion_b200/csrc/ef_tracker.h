@@ -6,6 +6,7 @@
 
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <chrono>
 #include <string>
 
 #include "../../include/ef_track.h"
@@ -113,6 +114,8 @@ struct ef_tracker
     long long prof_calls;
 
     ef_track_stats st;
+    ef_stage_times stages;                            // Stopwatch-compatible timings (ef_tracker_stage_times)
+    std::chrono::steady_clock::time_point call_begin; // start of the pending getIncrementalTransformation
     std::string err;
     long long launches;
 };

@@ -129,6 +129,16 @@ class RGBDOdometry:
         self._check(self._L.ef_tracker_profile(self._h, C.byref(ms), C.byref(n)), "ef_tracker_profile")
         return ms.value, n.value
 
+    def stageTimes(self):
+        """{"so3Step": ms, "computeRgbResidual": ms, "icpStep": ms, "rgbStep": ms, ...}: the reference's Stopwatch keys
+        (Utils/RGBDOdometry.cpp:333-538) for the last getIncrementalTransformation (see ef_stage_times in include/ef_track.h)"""
+        st = binding.StageTimes()
+        self._check(self._L.ef_tracker_stage_times(self._h, C.byref(st)), "ef_tracker_stage_times")
+        return {"so3Step": st.so3_step_ms, "computeRgbResidual": st.rgb_residual_ms, "icpStep": st.icp_step_ms, "rgbStep": st.rgb_step_ms,
+                "so3Step_sum": st.so3_step_sum_ms, "computeRgbResidual_sum": st.rgb_residual_sum_ms, "icpStep_sum": st.icp_step_sum_ms,
+                "rgbStep_sum": st.rgb_step_sum_ms, "iteration": st.iteration_ms, "iteration_sum": st.iteration_sum_ms, "call": st.call_ms,
+                "solve_mode": st.solve_mode}
+
     def synchronize(self):
         self._check(self._L.ef_tracker_synchronize(self._h), "ef_tracker_synchronize")
 

@@ -389,3 +389,31 @@ def test_degenerate_geometry_icp_only(scene):
         dev.close()
         host.close()
         ref.close()
+
+
+def test_stopwatch_compatible_stage_times():
+    """ef_tracker_stage_times: the reference's Stopwatch keys (RGBDOdometry.cpp:333-538, read by GPUTest.cpp:283-286)"""
+    w, h = 320, 240
+    K, pose0, pose1, f0, f1 = util.frame_pair(w, h)
+    pose0f = pose0.astype(np.float32)
+    host = ef.RGBDOdometry(w, h, K.cx, K.cy, K.fx, K.fy, solve_mode=RO.EF_SOLVE_HOST)
+    dev = ef.RGBDOdometry(w, h, K.cx, K.cy, K.fx, K.fy, solve_mode=RO.EF_SOLVE_DEVICE)
+    try:
+        for tr in (host, dev):
+            _feed(tr, pose0f, f0, f1)
+            tr.getIncrementalTransformation(pose0f[:3, 3], pose0f[:3, :3], **JOINT_SO3)
+        st = host.stageTimes()
+        assert st["solve_mode"] == RO.EF_SOLVE_HOST
+        for key in ("so3Step", "computeRgbResidual", "icpStep", "rgbStep"):
+            assert 0 < st[key] <= st[key + "_sum"] < st["call"], (key, st)
+        assert st["icpStep_sum"] >= 19 * 0.5 * st["icpStep"] / 10  # 19 calls were summed
+        sd = dev.stageTimes()
+        assert sd["solve_mode"] == RO.EF_SOLVE_DEVICE and sd["call"] > 0 and sd["icpStep_sum"] == 0
+        host.set_option(RO.EF_OPT_USE_GRAPH, 1)
+        _feed(host, pose0f, f0, f1)
+        host.getIncrementalTransformation(pose0f[:3, 3], pose0f[:3, :3], **JOINT)
+        sg = host.stageTimes()
+        assert sg["iteration"] > 0 and sg["iteration_sum"] >= sg["iteration"] and sg["icpStep_sum"] == 0
+    finally:
+        host.close()
+        dev.close()
