@@ -310,6 +310,14 @@ int ef_op_splat_predict(const float * d_surfels, size_t stride_bytes, int count,
                         float fy, int rows, int cols, float max_depth, float conf_threshold, int time, int max_time, int time_delta,
                         void * d_keys, uint8_t * d_image_rgba8, float * d_vertex_rgba32f, float * d_normal_rgba32f,
                         uint16_t * d_time_u16, void * stream);
+/* The same with InstanceFusion's fifth render target (combo_splat.frag:29, :54: inst = decodeColor(colTime.y)): d_inst_rgba8 receives
+ * the instance colour of the winning surfel (second float of its colour vector), zero where nothing was drawn; may be null.
+ * (Degenerate fragments: a NaN intersection is discarded here; the shader keeps it and leaves it to the depth test, whose result
+ * for a NaN depth is implementation-defined in GL.) */
+int ef_op_splat_predict_inst(const float * d_surfels, size_t stride_bytes, int count, const float * h_t_inv16, float cx, float cy, float fx,
+                             float fy, int rows, int cols, float max_depth, float conf_threshold, int time, int max_time, int time_delta,
+                             void * d_keys, uint8_t * d_image_rgba8, float * d_vertex_rgba32f, float * d_normal_rgba32f,
+                             uint16_t * d_time_u16, uint8_t * d_inst_rgba8, void * stream);
 /* FillIn::vertex / normal / image   FillIn.cpp, Shaders/fill_vertex.frag:19-53, fill_normal.frag:19-55, fill_rgb.frag:19-37
  * (ElasticFusion.cpp:756-760): holes of the predicted maps (vertex z == 0, black colour) are patched from the current raw
  * depth (millimetres) / colour image; passthrough = 1 takes every pixel from the current frame */

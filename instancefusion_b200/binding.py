@@ -84,5 +84,5 @@ EXPORTED = [
     "ef_op_resize_map", "ef_op_vertices_to_depth", "ef_op_pyr_down_gauss_f32", "ef_op_pyr_down_gauss_u8",
     "ef_op_bgr_to_intensity", "ef_op_depth_bilateral", "ef_op_depth_metric", "ef_op_derivative_images", "ef_op_project_point_cloud", "ef_op_icp_step",
     "ef_op_rgb_residual", "ef_op_rgb_step", "ef_op_so3_step", "ef_op_scratch_bytes", "ef_abi_version", "ef_device_count",
-    "ef_op_splat_scratch_bytes", "ef_op_splat_predict", "ef_op_fill_vertex", "ef_op_fill_normal", "ef_op_fill_rgb",
+    "ef_op_splat_scratch_bytes", "ef_op_splat_predict", "ef_op_splat_predict_inst", "ef_op_fill_vertex", "ef_op_fill_normal", "ef_op_fill_rgb",
 ]

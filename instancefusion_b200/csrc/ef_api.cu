@@ -1767,9 +1767,9 @@ EF_API int ef_op_project_point_cloud(const float * depth, size_t dp, int rows, i
 
 EF_API size_t ef_op_splat_scratch_bytes(int rows, int cols) { return (rows > 0 && cols > 0) ? (size_t)rows * cols * 24 : 0; } // keys + rays
 
-EF_API int ef_op_splat_predict(const float * surfels, size_t stride_bytes, int count, const float * t_inv, float cx, float cy, float fx, float fy,
-                               int rows, int cols, float max_depth, float conf_threshold, int time, int max_time, int time_delta, void * keys,
-                               uint8_t * image, float * vertex, float * normal, uint16_t * time_out, void * st)
+static int splat_predict(const float * surfels, size_t stride_bytes, int count, const float * t_inv, float cx, float cy, float fx, float fy, int rows,
+                         int cols, float max_depth, float conf_threshold, int time, int max_time, int time_delta, void * keys, uint8_t * image,
+                         float * vertex, float * normal, uint16_t * time_out, uint8_t * inst, void * st)
 {
     if(count < 0 || (count > 0 && !surfels) || !t_inv || !keys || !vertex || !normal || rows <= 0 || cols <= 0) return EF_ERR_INVALID_ARGUMENT;
     if(stride_bytes < 48 || (stride_bytes % 16) || (reinterpret_cast<uintptr_t>(surfels) % 16) || (reinterpret_cast<uintptr_t>(keys) % 16))
@@ -1782,8 +1782,24 @@ EF_API int ef_op_splat_predict(const float * surfels, size_t stride_bytes, int c
     a.rows = rows; a.cols = cols;
     a.max_depth = max_depth; a.conf_threshold = conf_threshold;
     a.time = time; a.max_time = max_time; a.time_delta = time_delta;
-    a.keys = keys; a.image = image; a.vertex = vertex; a.normal = normal; a.time_out = time_out;
+    a.keys = keys; a.image = image; a.vertex = vertex; a.normal = normal; a.time_out = time_out; a.inst = inst;
     return (int)launch_splat_predict(a, (cudaStream_t)st);
+}
+
+EF_API int ef_op_splat_predict(const float * surfels, size_t stride_bytes, int count, const float * t_inv, float cx, float cy, float fx, float fy,
+                               int rows, int cols, float max_depth, float conf_threshold, int time, int max_time, int time_delta, void * keys,
+                               uint8_t * image, float * vertex, float * normal, uint16_t * time_out, void * st)
+{
+    return splat_predict(surfels, stride_bytes, count, t_inv, cx, cy, fx, fy, rows, cols, max_depth, conf_threshold, time, max_time, time_delta, keys,
+                         image, vertex, normal, time_out, nullptr, st);
+}
+
+EF_API int ef_op_splat_predict_inst(const float * surfels, size_t stride_bytes, int count, const float * t_inv, float cx, float cy, float fx, float fy,
+                                    int rows, int cols, float max_depth, float conf_threshold, int time, int max_time, int time_delta, void * keys,
+                                    uint8_t * image, float * vertex, float * normal, uint16_t * time_out, uint8_t * inst, void * st)
+{
+    return splat_predict(surfels, stride_bytes, count, t_inv, cx, cy, fx, fy, rows, cols, max_depth, conf_threshold, time, max_time, time_delta, keys,
+                         image, vertex, normal, time_out, inst, st);
 }
 
 EF_API int ef_op_fill_vertex(const float * predicted, const uint16_t * depth, int rows, int cols, float cx, float cy, float fx, float fy,

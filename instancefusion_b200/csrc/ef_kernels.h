@@ -46,6 +46,7 @@ struct SplatArgs
     uint8_t * image;
     float * vertex, * normal;
     uint16_t * time_out;
+    uint8_t * inst = nullptr; // InstanceFusion's fifth target (instance colour, rgba8); may be null
 };
 cudaError_t launch_splat_predict(const SplatArgs & a, cudaStream_t s);
 cudaError_t launch_fill_vertex(const float * predicted, const uint16_t * depth, int rows, int cols, float cx, float cy, float fx, float fy, int passthrough,

@@ -129,7 +129,9 @@ __device__ __forceinline__ bool fragment_stage(const SplatParams & P, const Surf
     const float k = dvd(dot(S.pos, S.nrm), dot(l, S.nrm));
     const V3 c{mul(k, l.x), mul(k, l.y), mul(k, l.z)};                                     // :41
     const V3 d{sub(c.x, S.pos.x), sub(c.y, S.pos.y), sub(c.z, S.pos.z)};
-    if(!(dot(d, d) <= mul(S.rad, S.rad))) return false;                                    // :44-50 (NaN discards)
+    // :44-50.  A NaN here (degenerate surfel) is discarded; the shader's `> sqrRad` test keeps it and hands the depth test a NaN
+    // gl_FragDepth, whose outcome GL leaves to the implementation (it fails GL_LESS on the drivers we know of): same picture
+    if(!(dot(d, d) <= mul(S.rad, S.rad))) return false;
     F.z = c.z;
     float depth = add(dvd(c.z, mul(2.f, P.max_depth)), 0.5f);                              // :66
     if(!(depth >= 0.f && depth <= 1.f)) return false;                                      // outside the depth range
@@ -188,12 +190,13 @@ __global__ void __launch_bounds__(256) k_splat_depth(const float * __restrict__ 
 __global__ void __launch_bounds__(256) k_splat_resolve(const float * __restrict__ surfels, size_t stride_floats, const SplatParams P,
                                                        const unsigned long long * __restrict__ keys, const float4 * __restrict__ rays,
                                                        uchar4 * __restrict__ image,
-                                                       float4 * __restrict__ vertex, float4 * __restrict__ normal, uint16_t * __restrict__ time)
+                                                       float4 * __restrict__ vertex, float4 * __restrict__ normal, uint16_t * __restrict__ time,
+                                                       uchar4 * __restrict__ inst)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if(i >= P.rows * P.cols) return;
     const unsigned long long key = keys[i];
-    uchar4 img = make_uchar4(0, 0, 0, 0);
+    uchar4 img = make_uchar4(0, 0, 0, 0), ins = img;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f), n = v;
     uint16_t tm = 0;
     if(key != kEmptyKey)
@@ -209,6 +212,8 @@ __global__ void __launch_bounds__(256) k_splat_resolve(const float * __restrict_
             const float fxc = add((float)x, 0.5f), fyc = add((float)y, 0.5f);
             const int rgb = (int)ct.x; // color.glsl decodeColor; the RGBA8 target stores the bytes back
             img = make_uchar4((rgb >> 16) & 0xff, (rgb >> 8) & 0xff, rgb & 0xff, 255);
+            const int irgb = (int)ct.y; // InstanceFusion's fifth render target: inst = decodeColor(colTime.y), combo_splat.frag:29, :54
+            ins = make_uchar4((irgb >> 16) & 0xff, (irgb >> 8) & 0xff, irgb & 0xff, 255);
             v = make_float4(mul(mul(sub(fxc, P.cx), F.z), dvd(1.f, P.fx)), mul(mul(sub(fyc, P.cy), F.z), dvd(1.f, P.fy)), F.z, S.conf); // :61
             n = make_float4(S.nrm.x, S.nrm.y, S.nrm.z, S.rad);
             tm = (uint16_t)(unsigned)ct.z; // :65
@@ -218,6 +223,7 @@ __global__ void __launch_bounds__(256) k_splat_resolve(const float * __restrict_
     vertex[i] = v;
     normal[i] = n;
     if(time) time[i] = tm;
+    if(inst) inst[i] = ins;
 }
 
 // ---- FillIn ----
@@ -294,7 +300,7 @@ cudaError_t launch_splat_predict(const SplatArgs & a, cudaStream_t s)
     k_splat_prepare<<<(n + 255) / 256, 256, 0, s>>>(P, keys, rays);
     if(a.count > 0) k_splat_depth<<<(a.count + 255) / 256, 256, 0, s>>>(a.surfels, stride, a.count, P, keys, rays);
     k_splat_resolve<<<(n + 255) / 256, 256, 0, s>>>(a.surfels, stride, P, keys, rays, reinterpret_cast<uchar4 *>(a.image), reinterpret_cast<float4 *>(a.vertex),
-                                                    reinterpret_cast<float4 *>(a.normal), a.time_out);
+                                                    reinterpret_cast<float4 *>(a.normal), a.time_out, reinterpret_cast<uchar4 *>(a.inst));
     return cudaGetLastError();
 }
 

@@ -26,6 +26,7 @@ class ModelPredictor:
         self.vertex = torch.empty((self.height, self.width, 4), dtype=torch.float32, device=dev)
         self.normal = torch.empty((self.height, self.width, 4), dtype=torch.float32, device=dev)
         self.time = torch.empty((self.height, self.width), dtype=torch.uint16, device=dev)
+        self.inst = torch.empty((self.height, self.width, 4), dtype=torch.uint8, device=dev)  # InstanceFusion's instance-colour target
         self.filled_vertex = torch.empty_like(self.vertex)
         self.filled_normal = torch.empty_like(self.normal)
         self.filled_image = torch.empty_like(self.image)
@@ -41,14 +42,15 @@ class ModelPredictor:
             raise ValueError("surfels: contiguous float32 CUDA tensor of shape (N, >= 12)")
         t_inv = np.ascontiguousarray(np.linalg.inv(np.asarray(pose, np.float64)).astype(np.float32).reshape(16))
         cx, cy, fx, fy = self.cam
-        rc = self._L.ef_op_splat_predict(C.c_void_p(surfels.data_ptr()), C.c_size_t(surfels.shape[1] * 4), int(surfels.shape[0]),
+        rc = self._L.ef_op_splat_predict_inst(C.c_void_p(surfels.data_ptr()), C.c_size_t(surfels.shape[1] * 4), int(surfels.shape[0]),
                                          C.c_void_p(t_inv.ctypes.data), C.c_float(cx), C.c_float(cy), C.c_float(fx), C.c_float(fy), self.height,
                                          self.width, C.c_float(maxDepth), C.c_float(confThreshold), int(time),
                                          int(time if maxTime is None else maxTime), int(timeDelta), C.c_void_p(self._keys.data_ptr()),
                                          C.c_void_p(self.image.data_ptr()), C.c_void_p(self.vertex.data_ptr()),
-                                         C.c_void_p(self.normal.data_ptr()), C.c_void_p(self.time.data_ptr()), self._stream())
+                                         C.c_void_p(self.normal.data_ptr()), C.c_void_p(self.time.data_ptr()), C.c_void_p(self.inst.data_ptr()),
+                                         self._stream())
         if rc:
-            raise EFError(rc, "ef_op_splat_predict")
+            raise EFError(rc, "ef_op_splat_predict_inst")
         return self.image, self.vertex, self.normal, self.time
 
     def fill_in(self, depth_mm: torch.Tensor, rgba: torch.Tensor, passthrough=False):

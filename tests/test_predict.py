@@ -168,3 +168,27 @@ def test_closed_loop_over_a_trajectory_stays_on_track():
         assert max(errs) < 6e-3, errs
     finally:
         trk.close()
+
+
+@pytest.mark.gpu
+def test_instance_render_target():
+    """InstanceFusion's fifth target of combo_splat.frag (location 4, :29 / :54): inst = decodeColor(colTime.y) of the surfel that
+    wins the depth test -- the same surfel whose colour lands in `image`, so with instance colour := colour XOR a constant the two
+    targets must be that XOR of each other pixel by pixel, and zero together where nothing was drawn."""
+    import torch
+    from instancefusion_b200.predict import ModelPredictor
+    w, h = 320, 240
+    K, pose0, pose1, f0, f1, surfels = _scene(w, h, 64)  # InstanceFusion's 256-byte vertex
+    col = surfels[:, 4].astype(np.int64)
+    surfels[:, 5] = (col ^ 0x00A5C3).astype(np.float32)  # 24-bit values are exact in float32
+    pred = ModelPredictor(w, h, K.cx, K.cy, K.fx, K.fy)
+    pred.predict(torch.from_numpy(surfels).cuda(), pose1, time=ARGS["time"], maxTime=ARGS["max_time"], timeDelta=ARGS["time_delta"],
+                 maxDepth=ARGS["max_depth"], confThreshold=ARGS["conf_threshold"])
+    torch.cuda.synchronize()
+    img, inst = pred.image.cpu().numpy().astype(np.int64), pred.inst.cpu().numpy().astype(np.int64)
+    drawn = img[..., 3] == 255
+    assert drawn.mean() > 0.5
+    rgb = (img[..., 0] << 16) | (img[..., 1] << 8) | img[..., 2]
+    irgb = (inst[..., 0] << 16) | (inst[..., 1] << 8) | inst[..., 2]
+    assert np.array_equal(irgb[drawn], rgb[drawn] ^ 0x00A5C3)
+    assert np.array_equal(inst[..., 3] == 255, drawn) and not inst[~drawn].any()
