@@ -205,16 +205,20 @@ __device__ __forceinline__ uint8_t intensity_px(uchar4 s)
 // verticesToDepthKernel  cudafuncs.cu:536
 __device__ __forceinline__ float depth_from_z(float z, float cutoff) { return (z > cutoff || z <= 0) ? qnan() : z; }
 
-// applyKernel taps (cudafuncs.cu:615-621)
+// applyKernel taps (cudafuncs.cu:615-621): gx = {a, 0, -a; b, 0, -b; a, 0, -a}, gy = {a, b, a; 0, 0, 0; -a, -b, -a} with
+// a = 0.52201f, b = 0.79451f, k = row * 3 + column.  Evaluated from k (a sign times one of the two literals: exact, the same
+// floats as the reference's table) instead of indexing a local array, which would live on the stack of every caller.
 __device__ __forceinline__ float sobel_x_tap(int k)
 {
-    const float t[9] = {0.52201f, 0.00000f, -0.52201f, 0.79451f, -0.00000f, -0.79451f, 0.52201f, 0.00000f, -0.52201f};
-    return t[k];
+    const int row = k / 3, col = k - row * 3;
+    const float mag = (row == 1) ? 0.79451f : 0.52201f;
+    return (col == 0) ? mag : ((col == 2) ? -mag : 0.f);
 }
 __device__ __forceinline__ float sobel_y_tap(int k)
 {
-    const float t[9] = {0.52201f, 0.79451f, 0.52201f, 0.00000f, 0.00000f, 0.00000f, -0.52201f, -0.79451f, -0.52201f};
-    return t[k];
+    const int row = k / 3, col = k - row * 3;
+    const float mag = (col == 1) ? 0.79451f : 0.52201f;
+    return (row == 0) ? mag : ((row == 2) ? -mag : 0.f);
 }
 
 // applyKernel  cudafuncs.cu:583-607: `kernelIndex` counts down over VISITED taps only (:594-603)
