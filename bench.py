@@ -736,8 +736,10 @@ def main():
                                      "tracking_error_m_median": bt["median_err_m"],
                                      "achieved_gbs_whole_frame": per_frame_bytes * fps_b / world / 1e9, "frac_whole_frame": per_frame_bytes * fps_b / world / 1e9 / peak,
                                      "note": "ef_track_frames_to_model_batch: two independent sequences per GPU, ONE persistent tracker kernel per pair of "
-                                             "frames (two thread groups per CTA; the SM interleaves the sequences while either waits for its next pose); "
-                                             "inputs resident, blocking call, one pair at a time; per handle bit-identical to `value`'s path. "
+                                             "frames (one solver CTA per sequence; the worker CTAs alternate between the sequences, one Gauss-Newton "
+                                             "iteration each, so a sequence's gather-solve-publish chain is hidden behind the other's pixels); "
+                                             "inputs resident, blocking call, one pair at a time; per handle bit-identical to a single launch on the "
+                                             "same number of worker CTAs. "
                                              "frac_whole_frame = algorithmic bytes of the solves / total frame time (builders and launch gaps included) / HBM peak"}
         elif bt:
             line["value_batched_error"] = bt["error"]

@@ -1565,7 +1565,7 @@ EF_API int ef_batch_width(void) { return device_track_batch_width(); }
 EF_API int ef_track_frames_to_model_batch_launch(ef_tracker * const * ts, int n, const ef_frame_inputs * in, const float * poses, int rgb_only,
                                                  float icp_weight, int pyramid, int fast_odom, int so3)
 {
-    if(!ts || !in || !poses || n != device_track_batch_width()) return EF_ERR_INVALID_ARGUMENT;
+    if(!ts || !in || !poses || n < 2 || n > device_track_batch_width() || n > 8) return EF_ERR_INVALID_ARGUMENT;
     for(int g = 0; g < n; g++)
     {
         if(!ts[g]) return EF_ERR_INVALID_ARGUMENT;

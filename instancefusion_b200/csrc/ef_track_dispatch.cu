@@ -20,15 +20,28 @@ namespace ef
 EF_DECLARE_VARIANT(256)
 EF_DECLARE_VARIANT(384)
 
-// the batched build (EF_TRACK_GROUPS = 2: two sequences per launch, csrc/Makefile)
+// the batched builds (csrc/Makefile): EF_TRACK_ALT -- up to 4 sequences per launch, the worker CTAs time-sliced between them
+// (the default) -- and EF_TRACK_GROUPS = 2 -- two sequences, two thread groups per CTA (EF_BATCH_MODE=groups)
 int device_track_launch_batch_g2(ef_tracker * const * ts, const float * const * trans, const float * const * rot, int rgb_only, float icp_weight,
                                      int pyramid, int fast_odom, int so3, cudaStream_t stream);
-int device_track_batch_width() { return 2; }
+int device_track_launch_batch_alt(ef_tracker * const * ts, int n, const float * const * trans, const float * const * rot, int rgb_only, float icp_weight,
+                                  int pyramid, int fast_odom, int so3, int grid_ctas, cudaStream_t stream);
+static bool batch_groups_mode()
+{
+    const char * env = getenv("EF_BATCH_MODE");
+    return env && env[0] == 'g';
+}
+int device_track_batch_width() { return batch_groups_mode() ? 2 : 4; }
 int device_track_launch_batch(ef_tracker * const * ts, int n, const float * const * trans, const float * const * rot, int rgb_only, float icp_weight,
                               int pyramid, int fast_odom, int so3, cudaStream_t stream)
 {
-    if(n != 2) return EF_ERR_INVALID_ARGUMENT;
-    return device_track_launch_batch_g2(ts, trans, rot, rgb_only, icp_weight, pyramid, fast_odom, so3, stream);
+    if(batch_groups_mode())
+    {
+        if(n != 2) return EF_ERR_INVALID_ARGUMENT;
+        return device_track_launch_batch_g2(ts, trans, rot, rgb_only, icp_weight, pyramid, fast_odom, so3, stream);
+    }
+    if(n < 2 || n > 4) return EF_ERR_INVALID_ARGUMENT;
+    return device_track_launch_batch_alt(ts, n, trans, rot, rgb_only, icp_weight, pyramid, fast_odom, so3, ts[0]->grid_ctas, stream);
 }
 
 static int pick_variant(const ef_tracker * t)

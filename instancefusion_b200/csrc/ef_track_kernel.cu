@@ -56,7 +56,17 @@
 #endif
 #define EF_TRACK_CAT2(a, b) a##_t##b
 #define EF_TRACK_CAT(a, b) EF_TRACK_CAT2(a, b)
-#if EF_TRACK_GROUPS > 1
+// EF_TRACK_ALT: the ALTERNATING build -- k sequences per launch by time-slicing the worker CTAs instead of splitting their
+// threads.  Sequence s has its own solver CTA (block s); every worker CTA (all kThreads threads, one register file) runs one
+// Gauss-Newton iteration of sequence 0, publishes its partial sums, runs an iteration of sequence 1, ... and by the time it is
+// back at sequence 0 that sequence's solver has gathered, solved and published the next pose: the serial chain of one sequence
+// (37-60 % of an iteration) is hidden behind the pixels of the others.  See k_track_alt.
+#if defined(EF_TRACK_ALT)
+#if EF_TRACK_GROUPS != 1
+#error "EF_TRACK_ALT is a build of the single-group kernel"
+#endif
+#define EF_TRACK_FN(name) name##_alt
+#elif EF_TRACK_GROUPS > 1
 #define EF_TRACK_CATG2(a, c) a##_g##c
 #define EF_TRACK_CATG(a, c) EF_TRACK_CATG2(a, c)
 #define EF_TRACK_FN(name) EF_TRACK_CATG(name, EF_TRACK_GROUPS) // (one batched build per library, whatever its group size)
@@ -185,6 +195,12 @@ struct LevelArgs
 #endif
 constexpr int kReplicas = EF_TRACK_REPLICAS;
 constexpr int kReplicaStride = 16; // chunks
+// The parameter line exists twice and publication `epoch` goes to copy epoch & 1.  Publication e + 2 needs an acknowledgement of
+// e + 1 from every worker (its rows or its barrier-B arrival), which a worker sends after it consumed e, so a copy is never
+// overwritten before everybody has read it -- however late a worker gets to its wait (the alternating build's workers arrive
+// long after the publication).  With ONE copy the pose of the first Gauss-Newton iteration followed the "SO(3) is over" message
+// with nothing in between and a worker that was not already polling would have missed the latter.
+constexpr int kParCopyStride = kReplicas * kReplicaStride; // chunks between the two copies
 // SE3 payload: Rcurr[9] tcurr[3] krkinv[9] kt[3];  SO3 payload: H[9] krlr[9] done
 
 struct TrackOutput // pinned host memory, written by the solver thread
@@ -240,6 +256,7 @@ __device__ __forceinline__ void st_relaxed_v4(uint4 * p, const uint4 & v)
 __device__ __forceinline__ void warp_publish(uint4 * par, const float * s_payload, int first, int n, unsigned epoch)
 {
     __syncwarp();
+    par += (epoch & 1u) * kParCopyStride;
     for(int i = gtid() & 31; i < kReplicas * n; i += 32)
     {
         const int r = i / n, c = first + (i - r * n);
@@ -255,6 +272,7 @@ __device__ __forceinline__ void wait_chunks(const uint4 * line, int first, int n
     if(gtid() < 32)
     {
         const int lane = gtid();
+        line += (epoch & 1u) * kParCopyStride;
         uint4 v = make_uint4(0, 0, 0, epoch);
         do
         {
@@ -1107,14 +1125,12 @@ struct BatchArgs
     TrackArgs seq[kGroups];
 };
 
+// One sequence of a launch, as seen by one thread group: the solver CTA of the sequence (is_solver_cta: gathers, solves, publishes)
+// or worker `widx` of its W workers.  s_dyn: the group's dynamic shared memory -- workers: candidates + match records; solver:
+// the gathered rows.
 template<bool TIMING>
-__global__ void __launch_bounds__(kThreads * kGroups, 1) k_track(const __grid_constant__ BatchArgs BA)
+__device__ __forceinline__ void track_body(const TrackArgs & A, GroupShared & GS, int4 * const s_dyn, const bool is_solver_cta, const int widx, const int W)
 {
-    extern __shared__ int4 s_dyn_all[];         // per group -- workers: candidates + match records; CTA 0: gathered rows
-    __shared__ GroupShared s_groups[kGroups];
-    const TrackArgs & A = BA.seq[ggrp()];
-    GroupShared & GS = s_groups[ggrp()];
-    int4 * const s_dyn = s_dyn_all + (size_t)ggrp() * (A.group_smem_bytes / sizeof(int4));
     float * const s_red = GS.red;
     float * const s_final = GS.final_;
     float (* const s_par)[kPayload] = GS.par;
@@ -1124,13 +1140,9 @@ __global__ void __launch_bounds__(kThreads * kGroups, 1) k_track(const __grid_co
     int & s_flag = GS.flag;
     Solver & s_solver = GS.solver;
 
-    const uint4 * my_par = A.par + (size_t)((blockIdx.x == 0 ? 0 : blockIdx.x - 1) % kReplicas) * kReplicaStride;
-    const unsigned grid = gridDim.x;
-    const int W = (int)grid - 1;                // worker CTAs (blockIdx 1 .. grid-1); CTA 0 only gathers and solves
-    const bool is_solver_cta = (blockIdx.x == 0);
+    const uint4 * my_par = A.par + (size_t)(widx % kReplicas) * kReplicaStride;
     const bool is_solver = is_solver_cta && gtid() == 0;
     const unsigned lane = gtid() & 31u, warp = gtid() >> 5;
-    const int widx = is_solver_cta ? 0 : (int)blockIdx.x - 1;
     float * s_rows = reinterpret_cast<float *>(s_dyn);
     // per level: five candidate arrays of lvl_cap entries, then (icp_in_smem) six planes of lvl_cap floats
     auto cand_store = [&](int lv) {
@@ -1694,6 +1706,328 @@ __global__ void __launch_bounds__(kThreads * kGroups, 1) k_track(const __grid_co
     }
 }
 
+// CTA 0 gathers and solves, CTAs 1 .. grid-1 are the workers (of every thread group's sequence in the batched build)
+template<bool TIMING>
+__global__ void __launch_bounds__(kThreads * kGroups, 1) k_track(const __grid_constant__ BatchArgs BA)
+{
+    extern __shared__ int4 s_dyn_all[];
+    __shared__ GroupShared s_groups[kGroups];
+    const TrackArgs & A = BA.seq[ggrp()];
+    track_body<TIMING>(A, s_groups[ggrp()], s_dyn_all + (size_t)ggrp() * (A.group_smem_bytes / sizeof(int4)), blockIdx.x == 0,
+                       blockIdx.x == 0 ? 0 : (int)blockIdx.x - 1, (int)gridDim.x - 1);
+}
+
+#if defined(EF_TRACK_ALT)
+// ------------------------------------------------------------------------------------------------
+// The alternating build: k sequences per launch, the worker CTAs time-sliced between them
+// ------------------------------------------------------------------------------------------------
+constexpr int kAltMax = 4; // sequences per launch (each takes one solver CTA and a share of the workers' shared memory)
+
+struct AltArgs
+{
+    TrackArgs seq[kAltMax];
+    int n;
+};
+
+// where a worker CTA stands in one of its sequences (shared memory; identical in every worker CTA of the grid)
+struct WorkerSeq
+{
+    unsigned rel, arr;   // the epochs of track_body
+    int stage;           // 0 SO(3) pre-alignment | 1 Gauss-Newton | 2 finished
+    int lv, j;           // stage 1: the iteration to run next
+    int pending;         // a row round the solver has not digested yet
+    int n_cand;          // photometric candidates of this CTA at level lv
+    float lastRGBError;
+};
+
+__device__ __forceinline__ CandStore alt_cand_store(const TrackArgs & A, int4 * s_dyn, int lv)
+{
+    CandStore c;
+    unsigned * base = reinterpret_cast<unsigned *>(reinterpret_cast<char *>(s_dyn) + A.lvl_off[lv]);
+    const int cap = A.lvl_cap[lv];
+    c.c0 = base;
+    c.c1 = base + cap;
+    c.c2 = reinterpret_cast<float *>(base + 2 * cap);
+    c.r0 = base + 3 * cap;
+    c.r1 = reinterpret_cast<float *>(base + 4 * cap);
+    return c;
+}
+
+// level lv of a sequence has iterations left to start: the first such level at or below `lv`, -1 if none
+__device__ __forceinline__ int alt_next_level(const TrackArgs & A, int lv)
+{
+    while(lv >= 0 && A.lvl[lv].iterations <= 0) lv--;
+    return lv;
+}
+
+// ONE step of one sequence in a worker CTA: an so3Step evaluation or a Gauss-Newton iteration -- from the wait for its
+// parameters (published long ago when the other sequences kept this CTA busy meanwhile) to the publication of this CTA's
+// partial sums.  The worker half of track_body, statement for statement (same pixels, same order of additions: a sequence
+// gets the bits of a single launch with the same number of workers); the loop state lives in `w`.
+__device__ __forceinline__ void alt_worker_step(const TrackArgs & A, GroupShared & GS, int4 * const s_dyn, WorkerSeq & w, const int widx, const int W)
+{
+    float * const s_red = GS.red;
+    float * const s_final = GS.final_;
+    float (* const s_par)[kPayload] = GS.par;
+    float * const s_sigma = GS.sigma;
+    int * const s_wcnt = GS.wcnt, * const s_wsig = GS.wsig;
+    const uint4 * my_par = A.par + (size_t)(widx % kReplicas) * kReplicaStride;
+    const unsigned lane = gtid() & 31u, warp = gtid() >> 5;
+
+    if(w.stage == 0)
+    {
+        // ---- SO(3) pre-alignment (RGBDOdometry.cpp:294-382): one so3Step evaluation, or the news that it is over ----
+        const LevelArgs & L = A.lvl[2];
+        ++w.rel;
+        float * par = s_par[w.rel & 1u];
+        wait_chunks(my_par, 0, kLineChunks, w.rel, par);
+        if(par[18] != 0.f)
+        {
+            w.stage = 1;
+            return;
+        }
+        So3Params P;
+        P.rows = L.rows;
+        P.cols = L.cols;
+        P.kinv = mat_from(A.so3_kinv);
+        P.image_basis = mat_from(par);
+        P.krlr = mat_from(par + 9);
+        ++w.arr;
+        const UnitIter U{L.rows * L.cols, W, widx, (int)lane, (int)warp};
+        const int passes = U.passes();
+        float acc[16];
+#pragma unroll
+        for(int i = 0; i < 16; i++) acc[i] = 0.f;
+        for(int p = 0; p < passes; p++)
+        {
+            const int u = U.unit(p);
+            if(u >= 0)
+            {
+                const int y = u / L.cols, x = u - y * L.cols;
+                float row[4];
+                if(so3_row(P, x, y, A.so3_last, A.so3_next, L.cols, row)) accumulate_so3(acc, row);
+            }
+        }
+        const float lane_value = warp_transpose_reduce16(acc);
+        if(lane < 16) s_red[warp * 16 + lane] = lane_value;
+        group_sync();
+        if(gtid() < 16)
+        {
+            float sum = 0.f;
+#pragma unroll
+            for(int k = 0; k < kWarps; k++) sum += s_red[k * 16 + gtid()];
+            s_final[gtid()] = (gtid() < 11) ? sum : 0.f;
+        }
+        group_sync();
+        publish_row(A.rows + (size_t)widx * kSo3Chunks, s_final, kSo3Chunks, w.arr);
+        return;
+    }
+
+    // ---- one Gauss-Newton iteration (RGBDOdometry.cpp:405-585) of level w.lv ----
+    const int lv = w.lv;
+    const LevelArgs & L = A.lvl[lv];
+    IcpParams IP;
+    IP.Rprev_inv = mat_from(A.Rprev_inv);
+    IP.tprev = make_float3(A.tprev[0], A.tprev[1], A.tprev[2]);
+    IP.dist_thresh = A.dist_thresh;
+    IP.angle_thresh = A.angle_thresh;
+    IP.intr = Intr{L.fx, L.fy, L.cx, L.cy};
+    IP.rows = L.rows;
+    IP.cols = L.cols;
+    RgbResParams RP;
+    RP.min_scale = L.min_scale;
+    RP.max_depth_delta = A.max_depth_delta;
+    RP.rows = L.rows;
+    RP.cols = L.cols;
+    RgbStepParams SP;
+    SP.fx = L.fx; SP.fy = L.fy; SP.inv_fx = L.inv_fx; SP.inv_fy = L.inv_fy; SP.cx = L.cx; SP.cy = L.cy;
+    SP.sobel_scale = A.sobel_scale;
+    SP.sigma = 0.f;
+    const UnitIter U{L.rows * L.cols, W, widx, (int)lane, (int)warp};
+    const int passes = U.passes();
+    const CandStore C = alt_cand_store(A, s_dyn, lv);
+    float * const s_vn = reinterpret_cast<float *>(reinterpret_cast<char *>(s_dyn) + A.lvl_off[lv]) + 5 * (size_t)A.lvl_cap[lv];
+
+    if(w.j == 0)
+    {
+        // level start: candidate list and staged current maps of this CTA's pixels (the levels of a sequence share one region;
+        // every thread is past the previous level's records: the previous step of this sequence ended with CTA barriers)
+        int n_cand = 0;
+        if(A.rgb)
+        {
+            const int groups = (passes + kCompactGroup - 1) / kCompactGroup;
+            for(int g = 0; g < groups; g++)
+                n_cand = A.make_derivatives ? compact_group<true>(L, RP, U, passes, C, GS.wtot, g, n_cand) : compact_group<false>(L, RP, U, passes, C, GS.wtot, g, n_cand);
+        }
+        if(A.icp && A.icp_in_smem)
+            for(int p0 = 0; p0 < passes; p0 += kStageBatch) stage_batch(L, U, passes, s_vn, A.lvl_cap[lv], p0);
+        group_sync();
+        w.n_cand = n_cand;
+        w.lastRGBError = FLT_MAX;
+    }
+    const int n_cand = w.n_cand;
+
+    ++w.rel;
+    float * par = s_par[w.rel & 1u];
+    wait_chunks(my_par, A.icp ? 0 : 4, (A.icp && A.rgb) ? 8 : 4, w.rel, par);
+    IP.Rcurr = mat_from(par);
+    IP.tcurr = make_float3(par[9], par[10], par[11]);
+    RP.krkinv = mat_from(par + 12);
+    RP.kt = make_float3(par[21], par[22], par[23]);
+    w.pending = 0;
+
+    // phase A1: photometric association -> records in shared memory; this CTA's barrier-B arrival
+    if(A.rgb)
+    {
+        int cnt = 0, sig = 0;
+        rgb_assoc_cands(L, RP, C, n_cand, cnt, sig);
+        cnt = __reduce_add_sync(kFullMask, cnt);
+        sig = __reduce_add_sync(kFullMask, sig);
+        if(lane == 0) { s_wcnt[warp] = cnt; s_wsig[warp] = sig; }
+        group_sync();
+        if(gtid() == 0)
+        {
+            unsigned c = 0, sg = 0;
+#pragma unroll
+            for(int k = 0; k < kWarps; k++) { c += (unsigned)s_wcnt[k]; sg += (unsigned)s_wsig[k]; }
+            st_relaxed_v4(A.bslot + widx, make_uint4(c, sg, 0u, w.rel));
+        }
+    }
+
+    // phase A2: ICP association + 29 sums (hides the barrier-B round trip)
+    {
+        float accI[1][32];
+#pragma unroll
+        for(int i = 0; i < 32; i++) accI[0][i] = 0.f;
+        float vi = 0.f;
+        if(A.icp)
+        {
+            const bool anyI = A.icp_in_smem ? icp_passes<true>(L, IP, U, 0, passes, accI, s_vn, A.lvl_cap[lv]) : icp_passes<false>(L, IP, U, 0, passes, accI, s_vn, A.lvl_cap[lv]);
+            if(__any_sync(kFullMask, anyI)) vi = warp_transpose_reduce32(accI[0]);
+        }
+        if(lane < 29) s_red[warp * 64 + lane] = vi;
+    }
+
+    // barrier B: the robust-weight scale from the sequence's solver CTA
+    bool level_break = false;
+    if(A.rgb)
+    {
+        if(gtid() == 0)
+        {
+            uint4 v;
+            do
+            {
+                v = ld_relaxed_v4(A.bres + widx);
+            } while(v.w != w.rel);
+            s_sigma[0] = __uint_as_float(v.x);
+            s_sigma[1] = __uint_as_float(v.y);
+            s_sigma[2] = __uint_as_float(v.z);
+        }
+        group_sync();
+        const float rgbError = s_sigma[1];
+        if(A.rgb_only && rgbError > w.lastRGBError) level_break = true; // :464
+        if(!level_break)
+        {
+            w.lastRGBError = rgbError;
+            SP.sigma = A.rgb_only ? -1.f : s_sigma[0]; // :472-475
+        }
+    }
+
+    if(!level_break)
+    {
+        ++w.arr;
+        w.pending = 1;
+        // phase B: photometric rows from the records -> 29 more sums; the CTA's row of this round
+        float vr = 0.f;
+        if(A.rgb)
+        {
+            float accR[1][32];
+#pragma unroll
+            for(int i = 0; i < 32; i++) accR[0][i] = 0.f;
+            const bool any = rgb_rows_cands(SP, C, n_cand, accR);
+            if(__any_sync(kFullMask, any)) vr = warp_transpose_reduce32(accR[0]);
+        }
+        if(lane < 29) s_red[warp * 64 + 29 + lane] = vr;
+        group_sync();
+        if(gtid() < kRowFloats)
+        {
+            float sum = 0.f;
+            if(gtid() < 58)
+            {
+#pragma unroll
+                for(int k = 0; k < kWarps; k++) sum += s_red[k * 64 + gtid()];
+            }
+            s_final[gtid()] = sum;
+        }
+        group_sync();
+        publish_row(A.rows + (size_t)widx * kRowChunks, s_final, kRowChunks, w.arr);
+        w.j++;
+    }
+    if(level_break || w.j >= L.iterations)
+    {
+        w.j = 0;
+        w.lv = alt_next_level(A, lv - 1);
+        if(w.lv < 0)
+        {
+            // epilogue: without a round outstanding, a round without payload tells the solver that every worker is past its
+            // last barrier-B wait
+            if(!w.pending)
+            {
+                ++w.arr;
+                group_sync();
+                publish_row(A.rows + (size_t)widx * kSo3Chunks, s_final, kSo3Chunks, w.arr);
+            }
+            w.stage = 2;
+        }
+    }
+}
+
+// Blocks 0 .. n-1: the solver CTAs of the n sequences (track_body's solver half, unchanged).  Blocks n .. grid-1: the workers,
+// which take the sequences in turn, one step each.  A worker never waits for anything that depends on its own future steps
+// (sequence s's parameters need only the rows of step-1 of sequence s from every worker), so the rotation cannot deadlock.
+__global__ void __launch_bounds__(kThreads, 1) k_track_alt(const __grid_constant__ AltArgs BA)
+{
+    extern __shared__ int4 s_dyn_all[];
+    __shared__ GroupShared s_group;
+    __shared__ WorkerSeq s_ws[kAltMax];
+    const int n = BA.n;
+    const int W = (int)gridDim.x - n;
+    if((int)blockIdx.x < n)
+    {
+        track_body<false>(BA.seq[blockIdx.x], s_group, s_dyn_all, true, 0, W);
+        return;
+    }
+    const int widx = (int)blockIdx.x - n;
+    if((int)threadIdx.x < n)
+    {
+        const TrackArgs & A = BA.seq[threadIdx.x];
+        WorkerSeq w;
+        w.rel = w.arr = A.epoch_base;
+        w.lv = alt_next_level(A, kNumPyrs - 1);
+        w.j = 0;
+        w.stage = A.so3 ? 0 : 1;
+        w.pending = 0;
+        w.n_cand = 0;
+        w.lastRGBError = FLT_MAX;
+        s_ws[threadIdx.x] = w;
+    }
+    __syncthreads();
+    for(int left = n; left > 0;)
+    {
+        for(int s = 0; s < n; s++)
+        {
+            WorkerSeq w = s_ws[s];
+            if(w.stage == 2) continue;
+            alt_worker_step(BA.seq[s], s_group, s_dyn_all + (size_t)s * (BA.seq[s].group_smem_bytes / sizeof(int4)), w, widx, W);
+            if(w.stage == 2) left--;
+            __syncthreads(); // every thread has its copy of s_ws[s] (and is done with the step's shared memory)
+            if(threadIdx.x == 0) s_ws[s] = w;
+            __syncthreads();
+        }
+    }
+}
+#endif // EF_TRACK_ALT
+
 struct Layout // shared-memory geometry of one thread group for a grid of `grid` CTAs
 {
     int grid;
@@ -1719,9 +2053,9 @@ struct DeviceTrack
 
 // pixels per thread unit and passes per level -> shared-memory records per thread, within `budget` bytes of dynamic
 // shared memory.  false: the photometric candidates of a CTA do not fit.
-bool compute_layout(const ef_tracker * t, int grid, size_t budget, Layout & L)
+bool compute_layout(const ef_tracker * t, int grid, size_t budget, Layout & L, int solvers = 1, bool allow_prework = true)
 {
-    const int W = grid - 1;
+    const int W = grid - solvers;
     int max_cand = 1;
     for(int i = 0; i < kNumPyrs; i++)
     {
@@ -1744,7 +2078,7 @@ bool compute_layout(const ef_tracker * t, int grid, size_t budget, Layout & L)
         L.lvl_off[i] = (int)all;
         all += ((size_t)L.lvl_cap[i] * per_px + 15) & ~(size_t)15;
     }
-    const bool prework = all <= budget;
+    const bool prework = allow_prework && all <= budget;
     if(prework) smem = all;
     else
         for(int i = 0; i < kNumPyrs; i++)
@@ -1807,7 +2141,7 @@ void fill_args(ef_tracker * t, DeviceTrack * d, const Layout & lay, const float 
         d->launch_seq = 1;
         const int mg = t->num_sms < kMaxGrid ? t->num_sms : kMaxGrid;
         cudaMemsetAsync(d->rows, 0, (size_t)mg * kRowChunks * sizeof(uint4), t->stream);
-        cudaMemsetAsync(d->par, 0, ((size_t)kReplicas * kReplicaStride + 2 * (size_t)((mg + 7) & ~7)) * sizeof(uint4), t->stream);
+        cudaMemsetAsync(d->par, 0, (2 * (size_t)kParCopyStride + 2 * (size_t)((mg + 7) & ~7)) * sizeof(uint4), t->stream);
     }
     A.epoch_base = d->launch_seq << 8;
     A.par = d->par;
@@ -1831,7 +2165,53 @@ void fill_args(ef_tracker * t, DeviceTrack * d, const Layout & lay, const float 
 
 } // namespace
 
-#if EF_TRACK_GROUPS == 1
+#if defined(EF_TRACK_ALT)
+// n sequences (handles of one image size on one device, pyramids built, streams joined) from ONE launch on `stream`.  Every
+// sequence gets an n-th of the workers' shared memory for one level's lists at a time.  EF_ERR_UNSUPPORTED when that share
+// cannot hold them.  grid_ctas <= 0: every SM.
+int EF_TRACK_FN(device_track_launch_batch)(ef_tracker * const * ts, int n, const float * const * trans, const float * const * rot, int rgb_only,
+                                           float icp_weight, int pyramid, int fast_odom, int so3, int grid_ctas, cudaStream_t stream)
+{
+    static bool attr_set = false;
+    if(!attr_set)
+    {
+        cudaError_t e = cudaFuncSetAttribute(k_track_alt, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
+        if(e != cudaSuccess) return (int)e;
+        attr_set = true;
+    }
+    if(n < 1 || n > kAltMax) return EF_ERR_INVALID_ARGUMENT;
+    ef_tracker * t0 = ts[0];
+    const int max_grid = t0->num_sms < kMaxGrid ? t0->num_sms : kMaxGrid;
+    int grid = (grid_ctas > 0 && grid_ctas < max_grid) ? grid_ctas : max_grid;
+    if(grid < n + 1) grid = n + 1;
+    Layout L;
+    if(grid > max_grid || !compute_layout(t0, grid, ((size_t)kMaxDynSmem / n) & ~(size_t)15, L, n, false))
+    {
+        t0->err = "batched launch: image too large for a sequence's share of the shared memory";
+        return EF_ERR_UNSUPPORTED;
+    }
+    AltArgs local; // (~3 KB)
+    AltArgs * Bp = &local;
+    Bp->n = n;
+    for(int g = 0; g < n; g++)
+    {
+        ef_tracker * t = ts[g];
+        DeviceTrack * d = static_cast<DeviceTrack *>(t->track_state);
+        if(!d || t->width != t0->width || t->height != t0->height || t->device != t0->device) return EF_ERR_INVALID_ARGUMENT;
+        fill_args(t, d, L, trans[g], rot[g], rgb_only, icp_weight, pyramid, fast_odom, so3, Bp->seq[g]);
+        Bp->seq[g].dbg = nullptr; // the clock64 trace is a single-launch diagnostic
+    }
+    void * args[] = {Bp};
+    cudaError_t e = cudaLaunchCooperativeKernel((const void *)k_track_alt, dim3(L.grid), dim3(kThreads), args, L.smem_bytes * n, stream);
+    for(int g = 0; g < n; g++) ts[g]->launches++;
+    if(e != cudaSuccess)
+    {
+        t0->err = std::string("cudaLaunchCooperativeKernel (alternating): ") + cudaGetErrorString(e);
+        return (int)e;
+    }
+    return EF_OK;
+}
+#elif EF_TRACK_GROUPS == 1
 // (re)derive the launch geometry for a grid of `grid` CTAs.  A handle normally owns every SM; EF_OPT_GRID_CTAS lets several
 // handles share the GPU (e.g. two sequences tracked concurrently on 74 SMs each).
 int EF_TRACK_FN(device_track_configure)(ef_tracker * t, int grid)
@@ -1866,10 +2246,10 @@ int EF_TRACK_FN(device_track_init)(ef_tracker * t)
     EF_TRACK_FN(device_track_configure)(t, 0);
     const int max_grid = t->num_sms < kMaxGrid ? t->num_sms : kMaxGrid;
     d->launch_seq = 0;
-    const size_t ctl_chunks = (size_t)kReplicas * kReplicaStride + 2 * (size_t)((max_grid + 7) & ~7);
+    const size_t ctl_chunks = 2 * (size_t)kParCopyStride + 2 * (size_t)((max_grid + 7) & ~7);
     cudaError_t e = cudaMalloc((void **)&d->par, ctl_chunks * sizeof(uint4));
     if(e == cudaSuccess) e = cudaMemsetAsync(d->par, 0, ctl_chunks * sizeof(uint4), t->stream);
-    d->bslot = d->par ? d->par + (size_t)kReplicas * kReplicaStride : nullptr;
+    d->bslot = d->par ? d->par + 2 * (size_t)kParCopyStride : nullptr;
     d->bres = d->par ? d->bslot + ((max_grid + 7) & ~7) : nullptr;
     if(e == cudaSuccess) e = cudaMalloc((void **)&d->rows, (size_t)max_grid * kRowChunks * sizeof(uint4));
     if(e == cudaSuccess) e = cudaMemsetAsync(d->rows, 0, (size_t)max_grid * kRowChunks * sizeof(uint4), t->stream);

@@ -336,8 +336,8 @@ class BatchTracker:
     def __init__(self, trackers):
         self._L = binding.lib()
         self.n = len(trackers)
-        if self.n != self._L.ef_batch_width():
-            raise ValueError(f"a batch holds exactly {self._L.ef_batch_width()} trackers")
+        if not 2 <= self.n <= self._L.ef_batch_width():
+            raise ValueError(f"a batch holds 2 .. {self._L.ef_batch_width()} trackers")
         self.trackers = list(trackers)
         self._handles = (C.c_void_p * self.n)(*[t._h for t in self.trackers])
         self._inputs = (binding.FrameInputs * self.n)()

@@ -1,7 +1,10 @@
-"""k sequences per launch (ef_track_frames_to_model_batch, BASELINE.json configs[4] "k sequences per GPU"): the batched
-persistent kernel gives every handle exactly the bits its own single launch gives, frame after frame, in every mode (a thread
-group of the batched build has 4 warps, a single launch 8: each of its threads keeps the accumulators of the two virtual
-threads it stands for, so the float sums are added in the single launch's order -- EF_TRACK_SETS in ef_track_kernel.cu)."""
+"""k sequences per launch (ef_track_frames_to_model_batch, BASELINE.json configs[4] "k sequences per GPU").
+
+Default = the ALTERNATING kernel (EF_TRACK_ALT in ef_track_kernel.cu): sequence s has its own solver CTA and the worker CTAs take
+the sequences in turn, one Gauss-Newton iteration each.  A sequence's pixels are dealt to 148 - k workers instead of 147, so it
+returns the bits of a single launch configured with that many workers (EF_OPT_GRID_CTAS = SMs - k + 1) and agrees with the
+default single launch within the pose tolerance.  EF_BATCH_MODE=groups selects the older build with two thread groups per CTA,
+which returns the default single launch's bits (two accumulator sets per thread, EF_TRACK_SETS)."""
 import numpy as np
 import pytest
 
@@ -31,43 +34,95 @@ def _sequences(w, h, n, seeds):
     return K, out
 
 
-@pytest.mark.parametrize("size", [(640, 480), (320, 240), (322, 242)])
-def test_batched_launch_equals_single_launches_bit_for_bit(size):
+def _sms():
+    import torch
+    return torch.cuda.get_device_properties(0).multi_processor_count
+
+
+def _run(size, k, single_grid, monkeypatch=None, groups=False):
     w, h = size
-    n = 5
-    K, seqs = _sequences(w, h, n, seeds=(2024, 7))
+    n = 4
+    K, seqs = _sequences(w, h, n, seeds=(2024, 7, 11, 99)[:k])
     single = [ef.RGBDOdometry(w, h, K.cx, K.cy, K.fx, K.fy, solve_mode=RO.EF_SOLVE_DEVICE) for _ in seqs]
+    dflt = [ef.RGBDOdometry(w, h, K.cx, K.cy, K.fx, K.fy, solve_mode=RO.EF_SOLVE_DEVICE) for _ in seqs]
     batched = [ef.RGBDOdometry(w, h, K.cx, K.cy, K.fx, K.fy, solve_mode=RO.EF_SOLVE_DEVICE) for _ in seqs]
-    bt = RO.BatchTracker(batched)
     try:
+        if single_grid:
+            for t in single:
+                t.set_option(RO.EF_OPT_GRID_CTAS, single_grid)
+        bt = RO.BatchTracker(batched)
         for g, (poses, frames) in enumerate(seqs):
-            single[g].initFirstRGB(frames[0]["rgba"])
-            batched[g].initFirstRGB(frames[0]["rgba"])
+            for t in (single[g], dflt[g], batched[g]):
+                t.initFirstRGB(frames[0]["rgba"])
         for name, m in MODES.items():
-            for k in range(1, n):  # consecutive frames: state (SO(3) image swap, last* fields) carried
+            for f in range(1, n):  # consecutive frames: state (SO(3) image swap, last* fields) carried
                 args = (20.0, m["rgbOnly"], m["icpWeight"], m["pyramid"], m["fastOdom"], m["so3"])
-                fr = [(f[k - 1]["vmap"], f[k - 1]["nmap"], f[k - 1]["rgba"], f[k]["depth"], f[k]["rgba"]) for _, f in seqs]
-                ps = [p[k - 1] for p, _ in seqs]
-                want = [single[g].trackFrameToModel(*fr[g], 20.0, ps[g], *args[1:]) for g in range(len(seqs))]
+                fr = [(s[f - 1]["vmap"], s[f - 1]["nmap"], s[f - 1]["rgba"], s[f]["depth"], s[f]["rgba"]) for _, s in seqs]
+                ps = [p[f - 1] for p, _ in seqs]
+                want = [single[g].trackFrameToModel(*fr[g], 20.0, ps[g], *args[1:]) for g in range(k)]
+                near = [dflt[g].trackFrameToModel(*fr[g], 20.0, ps[g], *args[1:]) for g in range(k)]
                 got = bt.track(fr, ps, *args)
-                for g in range(len(seqs)):
-                    assert np.array_equal(got[g][0], want[g][0]) and np.array_equal(got[g][1], want[g][1]), (name, k, g, got[g][0], want[g][0])
+                for g in range(k):
+                    assert np.array_equal(got[g][0], want[g][0]) and np.array_equal(got[g][1], want[g][1]), (name, f, g, got[g][0], want[g][0])
                     a, b = batched[g], single[g]
-                    assert a.lastICPCount == b.lastICPCount and a.lastRGBCount == b.lastRGBCount and a.lastSO3Count == b.lastSO3Count, (name, k, g)
-                    assert a.lastICPError == b.lastICPError and a.lastRGBError == b.lastRGBError, (name, k, g)
-                    assert np.array_equal(a.lastA, b.lastA) and np.array_equal(a.lastb, b.lastb), (name, k, g)
+                    assert a.lastICPCount == b.lastICPCount and a.lastRGBCount == b.lastRGBCount and a.lastSO3Count == b.lastSO3Count, (name, f, g)
+                    assert a.lastICPError == b.lastICPError and a.lastRGBError == b.lastRGBError, (name, f, g)
+                    assert np.array_equal(a.lastA, b.lastA) and np.array_equal(a.lastb, b.lastb), (name, f, g)
                     assert a.se3_iterations == b.se3_iterations and a.so3_iterations == b.so3_iterations
+                    # another number of workers = another order of float additions: the default single launch within tolerance
+                    # (a handful of frames sit on an association tie and move further, like the reference's own launch shapes)
+                    assert np.abs(got[g][0] - near[g][0]).max() < 1e-3, (name, f, g)  # (frame 1 of seed 2024: 4e-4, as between the reference's own launch shapes)
         m = MODES["joint"]
         l0 = [t.launch_count for t in batched]
         bt.track(fr, ps, 20.0, m["rgbOnly"], m["icpWeight"], m["pyramid"], m["fastOdom"], m["so3"])
-        assert [t.launch_count - x for t, x in zip(batched, l0)] == [2, 2] or w % 4 != 0
+        assert [t.launch_count - x for t, x in zip(batched, l0)] == [2] * k or w % 4 != 0
         # and the batched launch reproduces itself to the bit
         again = bt.track(fr, ps, 20.0, m["rgbOnly"], m["icpWeight"], m["pyramid"], m["fastOdom"], m["so3"])
         once_more = bt.track(fr, ps, 20.0, m["rgbOnly"], m["icpWeight"], m["pyramid"], m["fastOdom"], m["so3"])
-        for g in range(len(seqs)):
+        for g in range(k):
             assert np.array_equal(again[g][0], once_more[g][0]) and np.array_equal(again[g][1], once_more[g][1])
     finally:
-        for t in single + batched:
+        for t in single + dflt + batched:
+            t.close()
+
+
+@pytest.mark.parametrize("size,k", [((640, 480), 2), ((640, 480), 4), ((320, 240), 3), ((322, 242), 2)])
+def test_alternating_launch_equals_single_launches_bit_for_bit(size, k):
+    _run(size, k, _sms() - k + 1)
+
+
+@pytest.mark.parametrize("size", [(640, 480), (322, 242)])
+def test_thread_group_launch_equals_default_single_launches_bit_for_bit(size, monkeypatch):
+    monkeypatch.setenv("EF_BATCH_MODE", "groups")
+    _run(size, 2, 0)
+
+
+def test_sequences_of_a_batch_may_end_at_different_iterations():
+    """rgb-only tracking leaves a level as soon as the photometric error rises (RGBDOdometry.cpp:464): the sequences of a batch
+    then run different numbers of iterations and the workers keep rotating over the ones that are left."""
+    w, h = 320, 240
+    K, seqs = _sequences(w, h, 3, seeds=(5, 6))
+    a = [ef.RGBDOdometry(w, h, K.cx, K.cy, K.fx, K.fy) for _ in seqs]
+    s = [ef.RGBDOdometry(w, h, K.cx, K.cy, K.fx, K.fy) for _ in seqs]
+    try:
+        for t in s:
+            t.set_option(RO.EF_OPT_GRID_CTAS, _sms() - 1)
+        bt = RO.BatchTracker(a)
+        for g, (_, frames) in enumerate(seqs):
+            a[g].initFirstRGB(frames[0]["rgba"])
+            s[g].initFirstRGB(frames[0]["rgba"])
+        # sequence 1 starts from a pose that is off by 3 cm: its photometric error behaves differently from sequence 0's
+        fr = [(f[0]["vmap"], f[0]["nmap"], f[0]["rgba"], f[1]["depth"], f[1]["rgba"]) for _, f in seqs]
+        ps = [p[0].copy() for p, _ in seqs]
+        ps[1] = ps[1].copy()
+        ps[1].reshape(4, 4)[0, 3] += 0.03
+        got = bt.track(fr, ps, 20.0, True, 10.0, True, False, False)
+        want = [s[g].trackFrameToModel(*fr[g], 20.0, ps[g], True, 10.0, True, False, False) for g in range(2)]
+        for g in range(2):
+            assert np.array_equal(got[g][0], want[g][0]) and np.array_equal(got[g][1], want[g][1])
+            assert a[g].se3_iterations == s[g].se3_iterations
+    finally:
+        for t in a + s:
             t.close()
 
 
