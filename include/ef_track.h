@@ -92,6 +92,12 @@ typedef struct ef_track_stats
                                     launch, like ef_track_frame_to_model.  The caller promises that the buffers stay valid and
                                     unchanged until then (the reference borrows its textures only for the duration of an init call) */
 
+#define EF_OPT_HOST_FUSED 9      /* 0/1 (default 1; host-solve mode, image width a multiple of 16, sides < 4096): a Gauss-Newton iteration
+                                    is two launches and no copy -- computeRgbResidual writing 8-byte correspondences, then icpStep +
+                                    rgbStep with one fixed-order reduction storing all sums straight into mapped pinned memory, which
+                                    the host polls.  0 = one launch, one download and one synchronisation per operator, exactly the
+                                    reference's control flow (or EF_OPT_USE_GRAPH's replay of it) */
+
 #define EF_SOLVE_HOST 0   /* one step kernel per operator call, 6x6 LDLT + pose update in double on the host,
                              exactly the reference's control flow (RGBDOdometry.cpp:405-585) */
 #define EF_SOLVE_DEVICE 1 /* one persistent cooperative kernel runs the SO(3) loop and all Gauss-Newton

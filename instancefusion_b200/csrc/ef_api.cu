@@ -119,6 +119,7 @@ constexpr int kNumAux = 3;
 // pinned result block (floats): one fetched result at 0; graph replay keeps the three results of an iteration and the
 // iteration's parameters side by side
 constexpr int kHostResultFloats = 256;
+constexpr int kHostIterFloats = 128; // fused iteration (ef_iter_fused.cu): 64 sums + sequence word, written by the device (mapped)
 constexpr int kHResid = 64, kHRgb = 96, kHIcp = 128, kHIter = 160;
 static_assert(kHIter * sizeof(float) + sizeof(IterParams) <= kHostResultFloats * sizeof(float), "pinned result block");
 
@@ -215,6 +216,8 @@ EF_API int ef_tracker_create(int width, int height, float cx, float cy, float fx
     for(int i = 0; i < 5; i++) t->stage_reader[i] = -1;
     t->launches = 0;
     t->grid_ctas = 0;
+    t->host_fused = 1;
+    t->iter_seq = 0;
     t->aux_streams = 1;
     t->frame_build = 2;
     t->defer_build = 0;
@@ -288,12 +291,14 @@ EF_API int ef_tracker_create(int width, int height, float cx, float cy, float fx
     const size_t o_tmpz = plan.take(n0 * 4);
     const size_t o_filt = plan.take(n0 * 2);
     const size_t o_scratch = plan.take(kScratchBytes);
+    const size_t o_scratch2 = plan.take(kScratchBytes);
     const size_t o_sd = plan.take(n0 * 2), o_sr = plan.take(n0 * 4), o_srm = plan.take(n0 * 4), o_sv = plan.take(n0 * 16), o_sn = plan.take(n0 * 16);
     t->arena_bytes = plan.off;
 
     e = cudaMalloc(&t->arena, t->arena_bytes);
     if(e == cudaSuccess) e = cudaMemsetAsync(t->arena, 0, t->arena_bytes, t->stream);
-    if(e == cudaSuccess) e = cudaMallocHost((void **)&t->h_result, kHostResultFloats * sizeof(float));
+    if(e == cudaSuccess) e = cudaHostAlloc((void **)&t->h_result, (kHostResultFloats + kHostIterFloats) * sizeof(float), cudaHostAllocMapped);
+    if(e == cudaSuccess) memset(t->h_result, 0, (kHostResultFloats + kHostIterFloats) * sizeof(float));
     if(e != cudaSuccess)
     {
         if(t->arena) cudaFree(t->arena);
@@ -318,6 +323,7 @@ EF_API int ef_tracker_create(int width, int height, float cx, float cy, float fx
     t->tmp_z = (float *)(base + o_tmpz);
     t->filt_depth = (uint16_t *)(base + o_filt);
     t->scratch = base + o_scratch;
+    t->scratch2 = base + o_scratch2;
     t->stage_depth = (uint16_t *)(base + o_sd);
     t->stage_rgba = (uint8_t *)(base + o_sr);
     t->stage_rgba_model = (uint8_t *)(base + o_srm);
@@ -406,6 +412,7 @@ EF_API int ef_tracker_set_option(ef_tracker * t, int key, int value)
         t->defer_build = value ? 1 : 0;
         return EF_OK;
     }
+    case EF_OPT_HOST_FUSED: t->host_fused = value ? 1 : 0; return EF_OK;
     case EF_OPT_GRID_CTAS:
         if(t->launch_pending) return fail(t, EF_ERR_BAD_STATE, "a launch is pending");
     {
@@ -438,6 +445,7 @@ EF_API int ef_tracker_get_option(ef_tracker * t, int key, int * value)
     case EF_OPT_AUX_STREAMS: *value = t->aux_streams; return EF_OK;
     case EF_OPT_FRAME_BUILD: *value = t->frame_build; return EF_OK;
     case EF_OPT_DEFER_BUILD: *value = t->defer_build; return EF_OK;
+    case EF_OPT_HOST_FUSED: *value = t->host_fused; return EF_OK;
     default: return EF_ERR_INVALID_ARGUMENT;
     }
 }
@@ -1047,6 +1055,26 @@ static int track_host(ef_tracker * t, float * trans, float * rot, int rgb_only, 
         const int rc = compute_derivatives(t);
         if(rc) return rc;
     }
+    // EF_OPT_HOST_FUSED: two launches per iteration, results through mapped pinned memory (ef_iter_fused.cu).  The 8-byte
+    // correspondences and the gate image of a level live where the plain path keeps its 16-byte DataTerm records.
+    const bool fused = t->host_fused && !t->use_graph && t->width % 16 == 0 && t->width < 4096 && t->height < 4096;
+    auto rec0_of = [&](int i) { return reinterpret_cast<unsigned *>(t->corres[i]); };
+    auto rec1_of = [&](int i) { return reinterpret_cast<float *>(t->corres[i]) + t->dims[i].n(); };
+    auto gate_of = [&](int i) { return reinterpret_cast<float *>(t->corres[i]) + 2 * t->dims[i].n(); };
+    float * const h_iter = t->h_result + kHostResultFloats;
+    if(fused && rgb)
+    {
+        HmGatesArgs g;
+        for(int i = 0; i < kNumPyrs; i++)
+        {
+            g.dIdx[i] = t->dIdx[i]; g.dIdy[i] = t->dIdy[i];
+            g.next_depth[i] = t->next_depth[i]; g.next_image[i] = t->next_image[i];
+            g.gate_depth[i] = gate_of(i);
+            g.min_scale[i] = (float)(pow(t->min_grad[i], 2.0) / pow(t->sobel_scale, 2.0)); // :442
+            g.rows[i] = t->dims[i].rows; g.cols[i] = t->dims[i].cols;
+        }
+        EF_LAUNCH(t, launch_hm_gates(g, s));
+    }
 
     double resultR[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
     t->st.so3_iterations = 0;
@@ -1127,7 +1155,7 @@ static int track_host(ef_tracker * t, float * trans, float * rot, int rgb_only, 
         const int rows = t->dims[i].rows, cols = t->dims[i].cols;
         float fx, fy, cx, cy;
         level_intr(t, i, fx, fy, cx, cy);
-        if(rgb && iterations[i] > 0) // :409 (skipped when the level runs no iteration: its only consumer is rgbStep)
+        if(rgb && iterations[i] > 0 && !fused) // :409 (skipped when the level runs no iteration: its only consumer is rgbStep)
             EF_LAUNCH(t, launch_project_points(t->last_depth[i], 0, rows, cols, fx, fy, cx, cy, t->cloud[i], 0, s));
 
         const double K[9] = {fx, 0, cx, 0, fy, cy, 0, 0, 1};
@@ -1167,6 +1195,44 @@ static int track_host(ef_tracker * t, float * trans, float * rot, int rgb_only, 
                 icp_sums = t->h_result + kHIcp;
                 rgb_sums = t->h_result + kHRgb;
             }
+            else if(fused)
+            {
+                StageTimer tick(t->stages.iteration_ms, t->stages.iteration_sum_ms);
+                if(rgb) EF_LAUNCH(t, launch_hm_residual(rgb_res_args(t, i, krkInv, kt), gate_of(i), rec0_of(i), rec1_of(i), t->scratch, s));
+                HmStepArgs a;
+                a.icp = icp_args(t, i, Rcurr, tcurr, Rprev_inv, tprev);
+                a.sobel_scale = t->sobel_scale;
+                a.rec0 = rec0_of(i); a.rec1 = rec1_of(i);
+                a.next_image = t->next_image[i];
+                a.dIdx = t->dIdx[i]; a.dIdy = t->dIdy[i];
+                a.residual = reinterpret_cast<const int *>(static_cast<char *>(t->scratch) + kScratchResultOff);
+                a.do_icp = icp ? 1 : 0; a.do_rgb = rgb ? 1 : 0; a.rgb_only = rgb_only ? 1 : 0;
+                a.h_out = h_iter;
+                a.seq = ++t->iter_seq;
+                EF_LAUNCH(t, launch_hm_step(a, t->scratch2, s));
+                // the last block stores the sums and then the sequence number behind a system-scope fence: poll it
+                const volatile unsigned * flag = reinterpret_cast<const volatile unsigned *>(h_iter + 64);
+                cudaError_t e = cudaSuccess;
+                for(long spins = 0; *flag != a.seq; ++spins)
+                {
+                    if((spins & 4095) == 4095)
+                    {
+                        e = cudaStreamQuery(s);
+                        if(e != cudaErrorNotReady) break;
+                        e = cudaSuccess;
+                    }
+#if defined(__x86_64__) || defined(__i386__)
+                    __builtin_ia32_pause();
+#endif
+                }
+                __atomic_thread_fence(__ATOMIC_ACQUIRE);
+                if(e == cudaSuccess && *flag != a.seq) e = cudaStreamSynchronize(s);
+                if(e != cudaSuccess || *flag != a.seq) return fail(t, e != cudaSuccess ? (int)e : EF_ERR_BAD_STATE, "fused iteration produced no result");
+                rgbSize = reinterpret_cast<const int *>(h_iter)[62];
+                sigma = reinterpret_cast<const int *>(h_iter)[63];
+                icp_sums = h_iter;
+                rgb_sums = h_iter + 32;
+            }
             else if(rgb)
             {
                 StageTimer tick(t->stages.rgb_residual_ms, t->stages.rgb_residual_sum_ms);
@@ -1188,7 +1254,7 @@ static int track_host(ef_tracker * t, float * trans, float * rot, int rgb_only, 
             double A_icp[36] = {0}, b_icp[6] = {0}, A_rgb[36] = {0}, b_rgb[6] = {0};
             if(icp)
             {
-                if(!t->use_graph)
+                if(!t->use_graph && !fused)
                 {
                     StageTimer tick(t->stages.icp_step_ms, t->stages.icp_step_sum_ms);
                     EF_LAUNCH(t, launch_icp_step(icp_args(t, i, Rcurr, tcurr, Rprev_inv, tprev), t->scratch, s));
@@ -1203,7 +1269,7 @@ static int track_host(ef_tracker * t, float * trans, float * rot, int rgb_only, 
             }
             if(rgb)
             {
-                if(!t->use_graph)
+                if(!t->use_graph && !fused)
                 {
                     StageTimer tick(t->stages.rgb_step_ms, t->stages.rgb_step_sum_ms);
                     EF_LAUNCH(t, launch_rgb_step(rgb_step_args(t, i, sigmaVal), t->scratch, s));

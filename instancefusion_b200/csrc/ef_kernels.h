@@ -151,6 +151,34 @@ struct RgbStepArgs
 // it != null: sigma is derived on the device from `residual` = the {count, sum} computeRgbResidual produced
 cudaError_t launch_rgb_step(const RgbStepArgs & a, void * scratch, cudaStream_t s, const IterParams * it = nullptr, const int * residual = nullptr);
 
+// ---- EF_SOLVE_HOST, fused iteration (ef_iter_fused.cu): gates once per call, then two launches per Gauss-Newton iteration ----
+struct HmGatesArgs
+{
+    const int16_t * dIdx[3], * dIdy[3];
+    const float * next_depth[3];
+    const uint8_t * next_image[3];
+    float * gate_depth[3]; // out: nextDepth where the pixel passes the iteration-invariant photometric gates, NaN elsewhere
+    float min_scale[3];
+    int rows[3], cols[3];
+};
+cudaError_t launch_hm_gates(const HmGatesArgs & a, cudaStream_t s);
+// 8-byte correspondences rec0 / rec1 (one word each per pixel); {count, sum} at scratch + kScratchResultOff.  cols % 4 == 0, dense rows
+cudaError_t launch_hm_residual(const RgbResArgs & a, const float * gate_depth, unsigned * rec0, float * rec1, void * scratch, cudaStream_t s);
+struct HmStepArgs
+{
+    IcpArgs icp;           // maps, pose, level intrinsics, thresholds (dense rows)
+    float sobel_scale;
+    const unsigned * rec0;
+    const float * rec1;
+    const uint8_t * next_image;
+    const int16_t * dIdx, * dIdy;
+    const int * residual;  // device {count, sum} of launch_hm_residual
+    int do_icp, do_rgb, rgb_only;
+    float * h_out;         // mapped pinned, 65 words: [0, 29) ICP sums | [32, 61) RGB sums | [62] count [63] sum | [64] = seq when done
+    unsigned seq;
+};
+cudaError_t launch_hm_step(const HmStepArgs & a, void * scratch, cudaStream_t s);
+
 struct So3Args
 {
     const uint8_t * last_image, * next_image;

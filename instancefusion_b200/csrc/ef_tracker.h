@@ -46,6 +46,8 @@ struct ef_tracker
     int aux_streams; // EF_OPT_AUX_STREAMS
     int frame_build; // EF_OPT_FRAME_BUILD
     int defer_build; // EF_OPT_DEFER_BUILD
+    int host_fused;  // EF_OPT_HOST_FUSED
+    unsigned iter_seq; // sequence number of the last fused host-mode iteration (ef_iter_fused.cu)
     struct
     {
         unsigned have;            // 1 model maps | 2 model colour | 4 depth | 8 colour
@@ -76,6 +78,7 @@ struct ef_tracker
     void * corres[ef::kNumPyrs]; // 16-byte DataTerm records (host-solve path)
     float * cloud[ef::kNumPyrs]; // float3 point clouds (host-solve path)
     void * scratch;              // reduction scratch (ef_kernels.h layout)
+    void * scratch2;             // a second one: the fused host-mode iteration runs two reducing kernels back to back
 
     // staging for the _host and _array entry points
     uint16_t * stage_depth;

@@ -12,8 +12,8 @@ import numpy as np
 from . import binding
 from .binding import EFError, TrackStats
 
-EF_OPT_SOLVE_MODE, EF_OPT_USE_GRAPH, EF_OPT_FUSED_BUILD, EF_OPT_PROFILE, EF_OPT_GRID_CTAS, EF_OPT_AUX_STREAMS, EF_OPT_FRAME_BUILD, EF_OPT_DEFER_BUILD = \
-    1, 2, 3, 4, 5, 6, 7, 8
+EF_OPT_SOLVE_MODE, EF_OPT_USE_GRAPH, EF_OPT_FUSED_BUILD, EF_OPT_PROFILE, EF_OPT_GRID_CTAS, EF_OPT_AUX_STREAMS, EF_OPT_FRAME_BUILD, EF_OPT_DEFER_BUILD, \
+    EF_OPT_HOST_FUSED = 1, 2, 3, 4, 5, 6, 7, 8, 9
 EF_SOLVE_HOST, EF_SOLVE_DEVICE = 0, 1
 
 _LEVEL_BUFFERS = {"vmap_curr": (np.float32, 3), "nmap_curr": (np.float32, 3), "vmap_g_prev": (np.float32, 3),
