@@ -201,15 +201,18 @@ int ef_track_frame_to_model(ef_tracker * t, const ef_frame_inputs * in, const fl
                             float icp_weight, int pyramid, int fast_odom, int so3, ef_track_stats * stats);
 
 /* k INDEPENDENT sequences per kernel launch (BASELINE.json configs[4]: "k sequences per GPU to show SM fill").
- * handles[0 .. n): n = ef_batch_width() (2) distinct handles of one image size on one device, EF_SOLVE_DEVICE; inputs[g] and
+ * handles[0 .. n): n = 2 .. ef_batch_width() (4) distinct handles of one image size on one device, EF_SOLVE_DEVICE; inputs[g] and
  * poses16[16 * g ..] are what ef_track_frame_to_model takes for handle g.  Every handle's pyramids are built as usual, then
- * ONE persistent tracker kernel runs the Gauss-Newton solves of all n frames: each CTA holds n thread groups, group g working
- * for handle g, so while one sequence waits for its next pose (a serial chain of ~3 us per iteration during which a single
- * launch leaves the SMs idle) the SM's schedulers run the other's pixels.  Per handle the results are bit-identical to
- * ef_track_frame_to_model.  _launch returns once everything is enqueued; finish each handle with
- * ef_get_incremental_transformation_finish (any order) or use the blocking form, which writes trans[3 * g ..], rot[9 * g ..]
- * and stats[g] (may be NULL).  EF_ERR_UNSUPPORTED: the image is too large for a thread group's share of the shared memory
- * (about 800 x 600 on a B200). */
+ * ONE persistent tracker kernel runs the Gauss-Newton solves of all n frames: sequence g has its own solver CTA and the other
+ * CTAs take the sequences in turn, one iteration each, so the serial gather -> solve -> publish chain of one sequence (~3 us
+ * per iteration, during which a single launch leaves the SMs idle) is hidden behind the pixels of the others.  Per handle
+ * the results are bit-identical to ef_track_frame_to_model on a handle configured with EF_OPT_GRID_CTAS = SMs - n + 1 (the same
+ * number of worker CTAs) and within the pose tolerance of the default launch.  _launch returns once everything is enqueued;
+ * finish each handle with ef_get_incremental_transformation_finish (any order) or use the blocking form, which writes
+ * trans[3 * g ..], rot[9 * g ..] and stats[g] (may be NULL).  EF_ERR_UNSUPPORTED: the image is too large for a sequence's share
+ * of the workers' shared memory (about 800 x 600 for two sequences on a B200).  The first handle's EF_OPT_GRID_CTAS sizes the
+ * launch.  (Environment EF_BATCH_MODE=groups: the older build, exactly two sequences as two thread groups per CTA, the
+ * default single launch's bits.) */
 int ef_batch_width(void);
 int ef_track_frames_to_model_batch_launch(ef_tracker * const * handles, int n, const ef_frame_inputs * inputs, const float * h_poses16, int rgb_only,
                                           float icp_weight, int pyramid, int fast_odom, int so3);

@@ -86,12 +86,13 @@ def _run(size, k, single_grid, monkeypatch=None, groups=False):
             t.close()
 
 
-@pytest.mark.parametrize("size,k", [((640, 480), 2), ((640, 480), 4), ((320, 240), 3), ((322, 242), 2)])
+@pytest.mark.parametrize("size,k", [((640, 480), 2), ((640, 480), 4), ((320, 240), 3), ((322, 242), 2)],
+                         ids=["640x480-k2", "640x480-k4", "320x240-k3", "322x242-k2"])
 def test_alternating_launch_equals_single_launches_bit_for_bit(size, k):
     _run(size, k, _sms() - k + 1)
 
 
-@pytest.mark.parametrize("size", [(640, 480), (322, 242)])
+@pytest.mark.parametrize("size", [(640, 480), (322, 242)], ids=["groups-640x480", "groups-322x242"])
 def test_thread_group_launch_equals_default_single_launches_bit_for_bit(size, monkeypatch):
     monkeypatch.setenv("EF_BATCH_MODE", "groups")
     _run(size, 2, 0)
