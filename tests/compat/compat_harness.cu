@@ -126,6 +126,59 @@ EFC_API int efc_shim_frame(void * p, int first, const float * v4, const float * 
     return rc;
 }
 
+// The drop-in rate in C++: `iters` frameToModel steps of ONE frame pair through class RGBDOdometry exactly as efc_shim_frame drives
+// it -- textures resident (cudaArrays, as the reference's GL textures are), five init calls + getIncrementalTransformation, the pose
+// read back every frame -- timed with the host clock around the loop.  defer != 0: EF_OPT_DEFER_BUILD, the setting INTEGRATION.md
+// recommends for the shim (the init calls copy the texels and record; one builder launch at the solve).  Returns frames/s, < 0 on error.
+#include <chrono>
+EFC_API double efc_shim_bench(void * p, const float * v4, const float * n4, const unsigned char * model_rgba, const unsigned short * depth,
+                              const unsigned char * rgba, const float * pose16_rowmajor, int iters, int defer)
+{
+    ShimState * s = static_cast<ShimState *>(p);
+    GPUTexture tv{make_array(v4, s->w, s->h, 32, 4, cudaChannelFormatKindFloat)}, tn{make_array(n4, s->w, s->h, 32, 4, cudaChannelFormatKindFloat)};
+    GPUTexture tm{make_array(model_rgba, s->w, s->h, 8, 4, cudaChannelFormatKindUnsigned)}, tc{make_array(rgba, s->w, s->h, 8, 4, cudaChannelFormatKindUnsigned)};
+    GPUTexture td{make_array(depth, s->w, s->h, 16, 1, cudaChannelFormatKindUnsigned)};
+    double fps = -1.0;
+    try
+    {
+        Eigen::Matrix4f pose;
+        for(int r = 0; r < 4; r++)
+            for(int c = 0; c < 4; c++) pose(r, c) = pose16_rowmajor[r * 4 + c];
+        RGBDOdometry & o = *s->odom;
+        ef_tracker_set_option(o.tracker(), EF_OPT_DEFER_BUILD, defer ? 1 : 0);
+        auto frame = [&]() {
+            o.initICPModel(&tv, &tn, 20.0f, pose);
+            o.initRGBModel(&tm);
+            o.initICP(&td, 20.0f);
+            o.initRGB(&tc);
+            Eigen::Vector3f trans;
+            Eigen::Matrix<float, 3, 3, Eigen::RowMajor> rot;
+            for(int r = 0; r < 3; r++)
+            {
+                trans(r, 0) = pose(r, 3);
+                for(int c = 0; c < 3; c++) rot(r, c) = pose(r, c);
+            }
+            o.getIncrementalTransformation(trans, rot, false, 10.0f, true, false, false);
+            return trans(0, 0);
+        };
+        float sink = 0.f;
+        for(int i = 0; i < 10; i++) sink += frame();
+        cudaDeviceSynchronize();
+        const auto t0 = std::chrono::steady_clock::now();
+        for(int i = 0; i < iters; i++) sink += frame();
+        cudaDeviceSynchronize();
+        const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        fps = (sink == 12345.678f) ? 0.0 : iters / sec;
+        ef_tracker_set_option(o.tracker(), EF_OPT_DEFER_BUILD, 0);
+    }
+    catch(const std::exception &)
+    {
+        fps = -1.0;
+    }
+    for(GPUTexture * t : {&tv, &tn, &tm, &tc, &td}) cudaFreeArray(t->array);
+    return fps;
+}
+
 // ---- operator functions: the depth pyramid + vertex / normal maps, the intensity pyramid + derivatives, one icpStep ----
 EFC_API int efc_ops_depth_chain(const unsigned short * depth, int rows, int cols, float fx, float fy, float cx, float cy, float cutoff,
                                 unsigned short * depth1 /*rows/2 x cols/2*/, float * vmap1 /*3*rows/2 x cols/2*/, float * nmap1, char * err, int err_len)

@@ -104,6 +104,38 @@ def test_shim_class_tracks_like_the_reference_and_like_the_python_mirror():
 
 
 @pytest.mark.gpu
+def test_shim_class_drop_in_rate_in_cxx():
+    """The drop-in number measured where a drop-in lives: a C++ loop over `class RGBDOdometry` of include/compat/RGBDOdometry.h --
+    textures resident as cudaArrays (the reference's GL textures), the five init calls + getIncrementalTransformation per frame, the
+    pose read back every frame.  (bench.py's value_reference_api drives the same five C-ABI calls from Python.)  The rate is recorded
+    in gpurun_out/compat_shim_fps.txt; the assertion is only a sanity floor (the reference's own kernels reach ~350 frames/s)."""
+    L = _lib()
+    L.efc_shim_bench.restype = C.c_double
+    w, h = 640, 480
+    K = synth.Intrinsics.kinect(w, h)
+    poses = synth.trajectory(2, seed=2024)
+    f0 = synth.render(poses[0], K, seed=2024, frame_id=0, device="cuda")
+    f1 = synth.render(poses[1], K, seed=2024, frame_id=1, device="cuda")
+    p = np.ascontiguousarray(poses.numpy().astype(np.float32)[0])
+    v, n, m = f0["vmap"].cpu().numpy(), f0["nmap"].cpu().numpy(), f0["rgba"].cpu().numpy()
+    d, c = util.u16(f1["depth"]), f1["rgba"].cpu().numpy()
+    shim = C.c_void_p(L.efc_shim_create(w, h, C.c_float(K.cx), C.c_float(K.cy), C.c_float(K.fx), C.c_float(K.fy)))
+    assert shim.value
+    try:
+        rates = {}
+        for name, defer in (("five calls", 0), ("five calls, EF_OPT_DEFER_BUILD", 1)):
+            rates[name] = float(L.efc_shim_bench(shim, _p(v), _p(n), _p(m), _p(d), _p(c), _p(p), 300, defer))
+            assert rates[name] > 1000.0, rates
+        out = os.path.join(ROOT, "gpurun_out")
+        if os.path.isdir(out):
+            with open(os.path.join(out, "compat_shim_fps.txt"), "w") as fh:
+                for name, r in rates.items():
+                    fh.write(f"class RGBDOdometry (include/compat/RGBDOdometry.h), C++ loop, 640x480 joint ICP+RGB, {name}: {r:.0f} frames/s\n")
+    finally:
+        L.efc_shim_destroy(shim)
+
+
+@pytest.mark.gpu
 def test_operator_functions_over_the_reference_containers():
     """pyrDown / createVMap / createNMap / imageBGRToIntensity / pyrDownUcharGauss / computeDerivativeImages / copyMaps /
     resizeVMap / resizeNMap / tranformMaps / icpStep through include/compat/cudafuncs.cuh on pitched DeviceArray2D buffers

@@ -13,4 +13,8 @@ timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'
 timeout 400 ncu --set full --clock-control none --import-source on -k regex:k_track -s 6 -c 3 -f -o gpurun_out/prof_track_r02 $B > gpurun_out/prof_track_r02.out 2>&1
 timeout 400 ncu --set full --clock-control none --import-source on -k regex:k_track -s 6 -c 3 -f -o gpurun_out/prof_track720_r02 $B --width 1280 --height 720 --so3 1 > gpurun_out/prof_track720_r02.out 2>&1
 timeout 400 ncu --set full --clock-control none --import-source on -k regex:k_build_frame -s 6 -c 3 -f -o gpurun_out/prof_build_r02 $B > gpurun_out/prof_build_r02.out 2>&1
+# second session: the alternating batched kernel (two sequences per launch) and the fused host-mode iteration at 1280x720, level 0
+PYTHONPATH=. timeout 400 ncu --set full --clock-control none --import-source on -k regex:k_track_alt -s 3 -c 2 -f -o gpurun_out/prof_alt_r02 python tools/alt_run.py 2 6 > gpurun_out/prof_alt_r02.out 2>&1
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:k_hm_step -s 28 -c 2 -f -o gpurun_out/prof_hmstep720_r02 $B --solve host --width 1280 --height 720 > gpurun_out/prof_hmstep720_r02.out 2>&1
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:k_hm_residual -s 28 -c 2 -f -o gpurun_out/prof_hmres720_r02 $B --solve host --width 1280 --height 720 > gpurun_out/prof_hmres720_r02.out 2>&1
 ls -la gpurun_out/*r02*

@@ -121,6 +121,12 @@ def main():
     full_summary("prof_track_r02.ncu-rep", "k_track, 640x480 joint ICP+RGB (256 threads x 148 CTAs, one launch = 19 Gauss-Newton iterations)", "r02_k_track_ncu_full.txt", "640x480", traffic)
     full_summary("prof_track720_r02.ncu-rep", "k_track, 1280x720 SO(3) + joint ICP+RGB (384 threads x 148 CTAs)", "r02_k_track_ncu_full.txt", "1280x720", traffic)
     full_summary("prof_build_r02.ncu-rep", "k_build_frame, 640x480 (every pyramid of a frame-to-model frame from one launch)", "r02_k_build_frame_ncu_full.txt")
+    full_summary("prof_alt_r02.ncu-rep", "k_track_alt, 640x480 joint ICP+RGB, TWO sequences per launch (2 solver CTAs + 146 workers alternating between the sequences)", "r02_k_track_alt_ncu_full.txt")
+    for f in ("r02_host_fused_ncu_full.txt",):
+        if os.path.exists(os.path.join(P, f)):
+            os.remove(os.path.join(P, f))
+    full_summary("prof_hmstep720_r02.ncu-rep", "k_hm_step (host-solve mode, fused iteration: icpStep + rgbStep + reduction), 1280x720 level 0", "r02_host_fused_ncu_full.txt", "hm_step_1280x720", {})
+    full_summary("prof_hmres720_r02.ncu-rep", "k_hm_residual (host-solve mode, fused iteration: computeRgbResidual -> 8-byte correspondences), 1280x720 level 0", "r02_host_fused_ncu_full.txt", "hm_res_1280x720", {})
     if traffic:
         json.dump(traffic, open(os.path.join(P, "roofline_traffic.json"), "w"), indent=1)
         print(traffic)
