@@ -2078,7 +2078,8 @@ bool compute_layout(const ef_tracker * t, int grid, size_t budget, Layout & L, i
         L.lvl_off[i] = (int)all;
         all += ((size_t)L.lvl_cap[i] * per_px + 15) & ~(size_t)15;
     }
-    const bool prework = allow_prework && all <= budget;
+    static const bool no_prework_env = getenv("EF_TRACK_PREWORK") && getenv("EF_TRACK_PREWORK")[0] == '0'; // (experiments)
+    const bool prework = allow_prework && !no_prework_env && all <= budget;
     if(prework) smem = all;
     else
         for(int i = 0; i < kNumPyrs; i++)
