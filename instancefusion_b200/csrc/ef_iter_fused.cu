@@ -363,8 +363,8 @@ int num_sms()
 template<class K>
 int one_wave(K kernel, int work_items, int max_blocks)
 {
-    int occ = 0;
-    if(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kBlock, 0) != cudaSuccess || occ < 1) occ = 1;
+    static int occ = 0; // (one kernel per instantiation; asked once: the query costs as much as a launch)
+    if(occ < 1 && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kBlock, 0) != cudaSuccess || occ < 1)) occ = 1;
     int blocks = (work_items + kBlock - 1) / kBlock;
     const int cap = num_sms() * occ;
     if(blocks > cap) blocks = cap;

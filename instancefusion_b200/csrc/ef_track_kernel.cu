@@ -2173,12 +2173,13 @@ void fill_args(ef_tracker * t, DeviceTrack * d, const Layout & lay, const float 
 int EF_TRACK_FN(device_track_launch_batch)(ef_tracker * const * ts, int n, const float * const * trans, const float * const * rot, int rgb_only,
                                            float icp_weight, int pyramid, int fast_odom, int so3, int grid_ctas, cudaStream_t stream)
 {
-    static bool attr_set = false;
-    if(!attr_set)
+    static bool attr_set[64] = {false}; // per device: function attributes belong to the device's context
+    const int dev = ts[0]->device;
+    if(dev < 0 || dev >= 64 || !attr_set[dev])
     {
         cudaError_t e = cudaFuncSetAttribute(k_track_alt, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
         if(e != cudaSuccess) return (int)e;
-        attr_set = true;
+        if(dev >= 0 && dev < 64) attr_set[dev] = true;
     }
     if(n < 1 || n > kAltMax) return EF_ERR_INVALID_ARGUMENT;
     ef_tracker * t0 = ts[0];
@@ -2453,12 +2454,13 @@ int EF_TRACK_FN(device_track_finish)(ef_tracker * t, float * trans, float * rot)
 int EF_TRACK_FN(device_track_launch_batch)(ef_tracker * const * ts, const float * const * trans, const float * const * rot, int rgb_only, float icp_weight,
                                            int pyramid, int fast_odom, int so3, cudaStream_t stream)
 {
-    static bool attr_set = false;
-    if(!attr_set)
+    static bool attr_set[64] = {false}; // per device: function attributes belong to the device's context
+    const int dev = ts[0]->device;
+    if(dev < 0 || dev >= 64 || !attr_set[dev])
     {
         cudaError_t e = cudaFuncSetAttribute(k_track<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
         if(e != cudaSuccess) return (int)e;
-        attr_set = true;
+        if(dev >= 0 && dev < 64) attr_set[dev] = true;
     }
     ef_tracker * t0 = ts[0];
     const int max_grid = t0->num_sms < kMaxGrid ? t0->num_sms : kMaxGrid;
