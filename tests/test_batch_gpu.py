@@ -127,6 +127,37 @@ def test_sequences_of_a_batch_may_end_at_different_iterations():
             t.close()
 
 
+def test_batches_on_disjoint_sm_subsets_run_concurrently():
+    """EF_OPT_GRID_CTAS of a batch's first handle sizes its launch: two batches of two sequences on half of the SMs each, both in
+    flight at once (launch / finish), give the bits of single launches on 74 - 2 workers."""
+    w, h = 320, 240
+    half = _sms() // 2
+    K, seqs = _sequences(w, h, 3, seeds=(3, 4))
+    mk = lambda: [ef.RGBDOdometry(w, h, K.cx, K.cy, K.fx, K.fy) for _ in seqs]  # noqa: E731
+    a, b, s = mk(), mk(), mk()
+    try:
+        for grp in (a, b):
+            for t in grp:
+                t.set_option(RO.EF_OPT_GRID_CTAS, half)
+        for t in s:
+            t.set_option(RO.EF_OPT_GRID_CTAS, half - 1)
+        bta, btb = RO.BatchTracker(a), RO.BatchTracker(b)
+        args = (20.0, False, 10.0, True, False, False)
+        for f in (1, 2):
+            fr = [(q[f - 1]["vmap"], q[f - 1]["nmap"], q[f - 1]["rgba"], q[f]["depth"], q[f]["rgba"]) for _, q in seqs]
+            ps = [p[f - 1] for p, _ in seqs]
+            bta.launch(fr, ps, *args)
+            btb.launch(fr, ps, *args)
+            ra, rb = bta.finish(), btb.finish()
+            want = [s[g].trackFrameToModel(*fr[g], 20.0, ps[g], *args[1:]) for g in range(2)]
+            for g in range(2):
+                for got in (ra[g], rb[g]):
+                    assert np.array_equal(got[0], want[g][0]) and np.array_equal(got[1], want[g][1]), (f, g)
+    finally:
+        for t in a + b + s:
+            t.close()
+
+
 def test_batch_argument_checks():
     w, h = 320, 240
     K, seqs = _sequences(w, h, 2, seeds=(1, 2))
