@@ -15,6 +15,10 @@
 // Per-pixel arithmetic comes from ef_image_px.cuh / ef_math.cuh, the same functions the stand-alone operator
 // kernels use, so fused and per-operator paths produce identical bits (tests/test_tracker_gpu.py).
 #include "ef_image_px.cuh"
+#include <stdio.h>
+#include <stdlib.h>
+#include <vector>
+
 #include "ef_kernels.h"
 
 namespace ef
@@ -380,6 +384,7 @@ struct FrameBuild
     float cutoff_rgb;
     uint8_t * img[2][3];
     float * dep_a[3], * dep_b[3];
+    unsigned long long * timeline; // EF_BUILD_TIMELINE=1: {start ns, end ns, SM} of every block (diagnostic)
 };
 
 struct alignas(16) BuildSmem
@@ -667,6 +672,8 @@ __global__ void __launch_bounds__(256, 5) k_build_frame(const __grid_constant__ 
 {
     __shared__ BuildSmem S;
     const int b = blockIdx.x;
+    unsigned long long t_begin = 0;
+    if(P.timeline && threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_begin));
     if(b < P.first_block[1]) depth_level12_tile(P, S, b);
     else if(b < P.first_block[2]) gauss_pyramid_tile<true>(P, S, 0, b - P.first_block[1]);
     else if(b < P.first_block[3]) gauss_pyramid_tile<false>(P, S, 0, b - P.first_block[2]);
@@ -677,6 +684,20 @@ __global__ void __launch_bounds__(256, 5) k_build_frame(const __grid_constant__ 
         const int m = b - P.first_block[5];
         const int by = m / P.maps_bx, bx = m - by * P.maps_bx;
         build_maps_block<true>(bx, by, P.vsrc, P.nsrc, P.rows, P.cols, P.maps, P.tmp_z, P.R, P.t);
+    }
+    if(P.timeline)
+    {
+        __syncthreads();
+        if(threadIdx.x == 0)
+        {
+            unsigned long long t_end;
+            unsigned sm;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
+            P.timeline[3 * b] = t_begin;
+            P.timeline[3 * b + 1] = t_end;
+            P.timeline[3 * b + 2] = sm;
+        }
     }
 }
 
@@ -820,6 +841,42 @@ cudaError_t launch_build_frame(const FrameBuildArgs & a, cudaStream_t s)
         P.img[1][i] = a.last_image[i];
         P.dep_a[i] = a.next_depth[i];
         P.dep_b[i] = a.last_depth[i];
+    }
+    P.timeline = nullptr;
+    static const bool want_timeline = getenv("EF_BUILD_TIMELINE") && getenv("EF_BUILD_TIMELINE")[0] == '1';
+    if(want_timeline)
+    {
+        // diagnostic: where every block ran and for how long; the table of the 20th launch goes to stderr
+        static unsigned long long * d_tl = nullptr;
+        static int calls = 0;
+        const int nb = P.first_block[kBuildJobs];
+        if(!d_tl) cudaMalloc((void **)&d_tl, (size_t)3 * 8192 * sizeof(unsigned long long));
+        P.timeline = nb <= 8192 ? d_tl : nullptr;
+        k_build_frame<<<nb, 256, 0, s>>>(P);
+        if(P.timeline && ++calls == 20)
+        {
+            std::vector<unsigned long long> h((size_t)3 * nb);
+            cudaStreamSynchronize(s);
+            cudaMemcpy(h.data(), d_tl, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+            unsigned long long t0 = ~0ull, t1 = 0;
+            for(int b = 0; b < nb; b++) { t0 = h[3 * b] < t0 ? h[3 * b] : t0; t1 = h[3 * b + 1] > t1 ? h[3 * b + 1] : t1; }
+            fprintf(stderr, "[k_build_frame timeline] %d blocks, %.2f us from the first start to the last end\n", nb, (t1 - t0) * 1e-3);
+            static const char * names[kBuildJobs] = {"u16 depth levels 1+2", "float depth pyramid", "intensity pyramid (current)", "intensity pyramid (model)", "vertex/normal level 0", "model map blocks"};
+            for(int j = 0; j < kBuildJobs; j++)
+            {
+                double sum = 0, mx = 0, first = 1e30, last = 0;
+                const int n = P.first_block[j + 1] - P.first_block[j];
+                for(int b = P.first_block[j]; b < P.first_block[j + 1]; b++)
+                {
+                    const double d = (h[3 * b + 1] - h[3 * b]) * 1e-3;
+                    sum += d; mx = d > mx ? d : mx;
+                    first = (h[3 * b] - t0) * 1e-3 < first ? (h[3 * b] - t0) * 1e-3 : first;
+                    last = (h[3 * b + 1] - t0) * 1e-3 > last ? (h[3 * b + 1] - t0) * 1e-3 : last;
+                }
+                fprintf(stderr, "  %-28s %4d blocks  mean %6.2f us  max %6.2f us  first start %6.2f  last end %6.2f  (block-time %7.1f us)\n", names[j], n, sum / n, mx, first, last, sum);
+            }
+        }
+        return cudaGetLastError();
     }
     k_build_frame<<<P.first_block[kBuildJobs], 256, 0, s>>>(P);
     return cudaGetLastError();
