@@ -125,8 +125,9 @@ def main():
     for f in ("r02_host_fused_ncu_full.txt",):
         if os.path.exists(os.path.join(P, f)):
             os.remove(os.path.join(P, f))
-    full_summary("prof_hmstep720_r02.ncu-rep", "k_hm_step (host-solve mode, fused iteration: icpStep + rgbStep + reduction), 1280x720 level 0", "r02_host_fused_ncu_full.txt", "hm_step_1280x720", {})
-    full_summary("prof_hmres720_r02.ncu-rep", "k_hm_residual (host-solve mode, fused iteration: computeRgbResidual -> 8-byte correspondences), 1280x720 level 0", "r02_host_fused_ncu_full.txt", "hm_res_1280x720", {})
+    hm = {"appending": True}  # (a non-empty dict makes full_summary append the second kernel to the same file)
+    full_summary("prof_hmstep720_r02.ncu-rep", "k_hm_step (host-solve mode, fused iteration: icpStep + rgbStep + reduction), 1280x720 level 0", "r02_host_fused_ncu_full.txt", "hm_step_1280x720", hm)
+    full_summary("prof_hmres720_r02.ncu-rep", "k_hm_residual (host-solve mode, fused iteration: computeRgbResidual -> 8-byte correspondences), 1280x720 level 0", "r02_host_fused_ncu_full.txt", "hm_res_1280x720", hm)
     if traffic:
         json.dump(traffic, open(os.path.join(P, "roofline_traffic.json"), "w"), indent=1)
         print(traffic)
