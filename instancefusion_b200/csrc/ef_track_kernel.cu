@@ -38,10 +38,12 @@
 #include "ef_reduce.cuh"
 #include "ef_tracker.h"
 
-// This file is compiled TWICE (csrc/Makefile): 256 threads per CTA (8 warps, <= 255 registers) is the best shape up to
-// ~640x480, 384 threads (12 warps, <= 168 registers) from ~1280x720 on, where a thread owns ~25 pixels per level-0 iteration
-// and the extra warps hide more latency than the longer reductions cost (profiles/r01_k_track_thread_sweep.txt).
-// ef_track_dispatch.cu picks the variant per handle from the image size.
+// This file is compiled FOUR times (csrc/Makefile).  Single launches: 256 threads per CTA (8 warps, <= 255 registers) is the
+// best shape up to ~640x480, 384 threads (12 warps, <= 168 registers) from ~1280x720 on, where a thread owns ~25 pixels per
+// level-0 iteration and the extra warps hide more latency than the longer reductions cost
+// (profiles/r01_k_track_thread_sweep.txt); ef_track_dispatch.cu picks the variant per handle from the image size.  k sequences
+// per launch: the alternating build (EF_TRACK_ALT, k_track_alt below, the default of ef_track_frames_to_model_batch) and the
+// thread-group build (EF_TRACK_GROUPS = 2).
 #ifndef EF_TRACK_THREADS
 #define EF_TRACK_THREADS 256
 #endif
