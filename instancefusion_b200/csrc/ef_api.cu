@@ -145,6 +145,11 @@ static void destroy_aux(ef_tracker * t)
     }
     if(t->ev_fork) cudaEventDestroy(t->ev_fork);
     t->ev_fork = nullptr;
+    if(t->copy_stream) cudaStreamDestroy(t->copy_stream);
+    if(t->ev_stage_free) cudaEventDestroy(t->ev_stage_free);
+    if(t->ev_stage_ready) cudaEventDestroy(t->ev_stage_ready);
+    t->copy_stream = nullptr;
+    t->ev_stage_free = t->ev_stage_ready = nullptr;
 }
 
 // Fork/join of independent builders.  The current-frame depth pyramid (aux 0) and the model RGB-D pyramid (aux 1)
@@ -229,6 +234,9 @@ EF_API int ef_tracker_create(int width, int height, float cx, float cy, float fx
         t->aux_dirty[i] = false;
     }
     t->ev_fork = nullptr;
+    t->copy_stream = nullptr;
+    t->ev_stage_free = t->ev_stage_ready = nullptr;
+    t->stage_free_valid = false;
     t->profile = 0;
     t->ev_begin = t->ev_end = nullptr;
     t->ev_pending = false;
@@ -264,6 +272,9 @@ EF_API int ef_tracker_create(int width, int height, float cx, float cy, float fx
         if(e == cudaSuccess) e = cudaEventCreateWithFlags(&t->ev_join[i], cudaEventDisableTiming);
     }
     if(e == cudaSuccess) e = cudaEventCreateWithFlags(&t->ev_fork, cudaEventDisableTiming);
+    if(e == cudaSuccess) e = cudaStreamCreateWithFlags(&t->copy_stream, cudaStreamNonBlocking);
+    if(e == cudaSuccess) e = cudaEventCreateWithFlags(&t->ev_stage_free, cudaEventDisableTiming);
+    if(e == cudaSuccess) e = cudaEventCreateWithFlags(&t->ev_stage_ready, cudaEventDisableTiming);
     if(e != cudaSuccess)
     {
         destroy_aux(t);
@@ -753,6 +764,7 @@ static int stage_guard(ef_tracker * t, int which)
     const int r = t->stage_reader[which];
     if(r >= 0 && t->aux_dirty[r]) EF_CUDA(t, cudaStreamWaitEvent(t->stream, t->ev_join[r], 0)); // the join proper still happens later
     t->stage_reader[which] = -1;
+    t->stage_free_valid = false; // (the buffer is about to be written and read on the handle's stream: frame_build_all's copy stream orders itself after that)
     return EF_OK;
 }
 
@@ -1538,14 +1550,38 @@ static int frame_build_all(ef_tracker * t, const ef_frame_inputs * in, const flo
             EF_CUDA(t, cudaMemcpyAsync(t->stage_rgba_model, mrgba, n * 4, cudaMemcpyHostToDevice, t->stream));
             v4 = t->stage_v; n4 = t->stage_n; mrgba = t->stage_rgba_model;
         }
-        if(host_sensor)
+        if(host_sensor && !host_model && t->copy_stream)
+        {
+            // The production data flow: the model maps are already on the device -- typically the output of a prediction that is
+            // still running on this handle's stream -- and only the sensor frame comes from the host.  Its two copies do not
+            // depend on anything enqueued here except the last builder that READ the staging buffers, so they run on their own
+            // stream beside the prediction; the builder waits for them.
+            if(t->stage_free_valid) EF_CUDA(t, cudaStreamWaitEvent(t->copy_stream, t->ev_stage_free, 0));
+            else
+            {
+                EF_CUDA(t, cudaEventRecord(t->ev_stage_free, t->stream)); // unknown history: order after everything enqueued so far
+                EF_CUDA(t, cudaStreamWaitEvent(t->copy_stream, t->ev_stage_free, 0));
+            }
+            EF_CUDA(t, cudaMemcpyAsync(t->stage_depth, depth, n * 2, cudaMemcpyHostToDevice, t->copy_stream));
+            EF_CUDA(t, cudaMemcpyAsync(t->stage_rgba, rgba, n * 4, cudaMemcpyHostToDevice, t->copy_stream));
+            EF_CUDA(t, cudaEventRecord(t->ev_stage_ready, t->copy_stream));
+            EF_CUDA(t, cudaStreamWaitEvent(t->stream, t->ev_stage_ready, 0));
+            depth = t->stage_depth; rgba = t->stage_rgba;
+        }
+        else if(host_sensor)
         {
             EF_CUDA(t, cudaMemcpyAsync(t->stage_depth, depth, n * 2, cudaMemcpyHostToDevice, t->stream));
             EF_CUDA(t, cudaMemcpyAsync(t->stage_rgba, rgba, n * 4, cudaMemcpyHostToDevice, t->stream));
             depth = t->stage_depth; rgba = t->stage_rgba;
+            t->stage_free_valid = false;
         }
         rc = build_frame(t, v4, n4, mrgba, depth, rgba, pose, in->depth_cutoff);
         if(rc) return rc;
+        if(host_sensor && !host_model && t->copy_stream)
+        {
+            EF_CUDA(t, cudaEventRecord(t->ev_stage_free, t->stream)); // the builder that read the two staging buffers
+            t->stage_free_valid = true;
+        }
     }
     else if(t->fused_build && t->aux_streams && in->on_host == 0)
     {

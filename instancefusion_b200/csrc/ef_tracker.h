@@ -85,6 +85,11 @@ struct ef_tracker
     uint8_t * stage_rgba, * stage_rgba_model; // two: the model image is read on an internal stream while the next copy runs
     float * stage_v, * stage_n;
     int stage_reader[5]; // internal stream whose builder last read each staging buffer (-1: the handle's stream), ef_api.cu stage_guard
+    // sensor frame from the host with the model maps on the device (ef_frame_inputs.on_host == 2, the production data flow): the two
+    // copies run on their own stream, beside whatever is already enqueued on the handle's stream (the caller's model prediction)
+    cudaStream_t copy_stream;
+    cudaEvent_t ev_stage_free, ev_stage_ready; // the last builder that read stage_depth / stage_rgba is done | the copies have landed
+    bool stage_free_valid;                     // ev_stage_free covers the last use of the two staging buffers
 
     // persistent-kernel state (EF_SOLVE_DEVICE)
     int track_variant;  // threads per CTA of the tracker-kernel build this handle uses (ef_track_dispatch.cu)
