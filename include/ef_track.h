@@ -75,7 +75,10 @@ typedef struct ef_track_stats
                                     instead of one kernel per operator (any size) */
 #define EF_OPT_PROFILE 4         /* 0/1: bracket the solve of every getIncrementalTransformation with CUDA events */
 #define EF_OPT_GRID_CTAS 5       /* device mode: CTAs (= SMs) the persistent tracker kernel occupies; 0 = all.  Lets k handles
-                                    track k independent sequences concurrently on disjoint SMs of one GPU */
+                                    track k independent sequences concurrently on disjoint SMs of one GPU.  A handle on a subset
+                                    runs the symmetric build of the kernel (every CTA a worker, each solving redundantly: one L2
+                                    hop per iteration instead of two); the order of its float additions, and so its last bits,
+                                    depend on the number of CTAs */
 
 #define EF_OPT_AUX_STREAMS 6     /* 0/1 (default 1): the pyramid builders that do not depend on each other (current-frame depth
                                     pyramid, model RGB-D pyramid) run on two internal streams beside the handle's stream and
@@ -206,7 +209,7 @@ int ef_track_frame_to_model(ef_tracker * t, const ef_frame_inputs * in, const fl
  * ONE persistent tracker kernel runs the Gauss-Newton solves of all n frames: sequence g has its own solver CTA and the other
  * CTAs take the sequences in turn, one iteration each, so the serial gather -> solve -> publish chain of one sequence (~3 us
  * per iteration, during which a single launch leaves the SMs idle) is hidden behind the pixels of the others.  Per handle
- * the results are bit-identical to ef_track_frame_to_model on a handle configured with EF_OPT_GRID_CTAS = SMs - n + 1 (the same
+ * the results are bit-identical to ef_track_frame_to_model on a handle configured with EF_OPT_GRID_CTAS = SMs - n (the same
  * number of worker CTAs) and within the pose tolerance of the default launch.  _launch returns once everything is enqueued;
  * finish each handle with ef_get_incremental_transformation_finish (any order) or use the blocking form, which writes
  * trans[3 * g ..], rot[9 * g ..] and stats[g] (may be NULL).  EF_ERR_UNSUPPORTED: the image is too large for a sequence's share

@@ -161,6 +161,7 @@ constexpr int kIcpBytes = 24;    // current-frame vertex + normal of a pixel (ic
 constexpr int kMaxDynSmem = 200 * 1024;
 
 static_assert(kThreads % 32 == 0 && kThreads >= 128 && kThreads <= 1024, "EF_TRACK_THREADS");
+static_assert(kMaxGrid == 255 && kRowChunks == 20, "kSlotCopy / kRowsChunks");
 
 struct LevelArgs
 {
@@ -203,6 +204,11 @@ constexpr int kReplicaStride = 16; // chunks
 // long after the publication).  With ONE copy the pose of the first Gauss-Newton iteration followed the "SO(3) is over" message
 // with nothing in between and a worker that was not already polling would have missed the latter.
 constexpr int kParCopyStride = kReplicas * kReplicaStride; // chunks between the two copies
+// control block of a handle: 2 parameter copies | 2 x kSlotCopy barrier-B arrivals (two copies by iteration parity in the symmetric
+// body) | kSlotCopy barrier-B answers; rows: two copies of kMaxGrid rows (by round parity, symmetric body)
+constexpr size_t kSlotCopy = (255 + 7) & ~7;
+constexpr size_t kCtlChunks = 2 * (size_t)kParCopyStride + 3 * kSlotCopy;
+constexpr size_t kRowsChunks = 2 * (size_t)255 * 20;
 // SE3 payload: Rcurr[9] tcurr[3] krkinv[9] kt[3];  SO3 payload: H[9] krlr[9] done
 
 struct TrackOutput // pinned host memory, written by the solver thread
@@ -227,6 +233,7 @@ struct TrackArgs
     int make_derivatives;                         // dIdx / dIdy are not valid yet: compute them at level start
     int icp_in_smem;                              // the CTA's current-frame vertices / normals fit shared memory beside the candidates
     int group_smem_bytes;                         // dynamic shared memory of one thread group (multiple of 16)
+    int cand_base;                                // symmetric body: byte offset of the candidate lists (behind the gathered rows)
     float prev_icp_error, prev_icp_count, prev_so3_error, prev_so3_count, prev_rgb_error, prev_rgb_count;
     unsigned epoch_base;                          // launch_seq << 8
     uint4 * par;                                  // kReplicas parameter lines
@@ -1126,6 +1133,534 @@ struct BatchArgs
 {
     TrackArgs seq[kGroups];
 };
+
+#if !defined(EF_TRACK_ALT) && EF_TRACK_GROUPS == 1
+// ================================================================================================
+// The symmetric body (single launches on a SUBSET of the SMs, EF_OPT_GRID_CTAS): EVERY CTA is a worker AND solves.
+//
+// Round 1's structure -- CTA 0 gathers the rows, solves, publishes the parameters, 147 workers wait -- costs two L2 hops per
+// iteration (rows -> CTA 0, parameters -> workers: 4 400 cycles of communication before the 1 900 of the solve,
+// tools/gather2_probe.cu).  Here every CTA polls ALL rows itself, adds them in row order and runs the solve redundantly:
+// one hop (2 980 cycles in the same probe), identical bits in every CTA because the instructions and their inputs are identical,
+// no parameter line, no solver CTA.  Barrier B works the same way: every CTA reads all {count, sum} arrivals and forms the
+// robust-weight scale itself.  CTA 0 alone stores the result.
+// Measured (profiles/r02_k_track_experiments.txt): on the whole GPU this body does NOT beat track_body -- the redundant FP64 solve is
+// slower when every SM issues it (2 400 vs 1 890 cycles) and the level preparation, which track_body's workers do while they wait for
+// parameters, has no wait to hide in (171.5 -> 174.6 us) -- but a handle that owns a quarter of the SMs never had room for the
+// three levels' lists side by side, so its preparation was in the open already and the saved hop is a net gain (4 x 37 SMs:
+// 8 200 -> 8 700 frames/s).  ef_track_dispatch / device_track_configure therefore pick it for partitioned handles only.
+//   rows    G x kRowChunks flagged chunks, two copies by the parity of the round (a CTA may publish round n + 1 while a slower
+//           one still reads round n; n + 2 needs that CTA's row of n + 1, which it sends after it is done reading n)
+//   bslot   G flagged chunks, two copies by the parity of the iteration, same argument
+// ================================================================================================
+template<bool TIMING>
+__device__ __forceinline__ void track_body_sym(const TrackArgs & A, GroupShared & GS, int4 * const s_dyn, const int b, const int G)
+{
+    float * const s_red = GS.red;
+    float * const s_final = GS.final_;
+    float (* const s_par)[kPayload] = GS.par;
+    float * const s_sigma = GS.sigma;
+    int * const s_wcnt = GS.wcnt, * const s_wsig = GS.wsig;
+    int * const s_wtot = GS.wtot;
+    int & s_flag = GS.flag;
+    Solver * const S = &GS.solver;
+
+    const int W = G, widx = b;                  // every CTA owns a share of the pixels
+    const bool is_writer = (b == 0) && gtid() == 0;
+    const unsigned lane = gtid() & 31u, warp = gtid() >> 5;
+    float * const s_rows = reinterpret_cast<float *>(s_dyn); // the gathered rows, G x kRowFloats floats; the lists follow at A.cand_base
+    char * const s_lists = reinterpret_cast<char *>(s_dyn) + A.cand_base;
+    auto cand_store = [&](int lv) {
+        CandStore c;
+        unsigned * base = reinterpret_cast<unsigned *>(s_lists + A.lvl_off[lv]);
+        const int cap = A.lvl_cap[lv];
+        c.c0 = base;
+        c.c1 = base + cap;
+        c.c2 = reinterpret_cast<float *>(base + 2 * cap);
+        c.r0 = base + 3 * cap;
+        c.r1 = reinterpret_cast<float *>(base + 4 * cap);
+        return c;
+    };
+    auto vn_store = [&](int lv) { return reinterpret_cast<float *>(s_lists + A.lvl_off[lv]) + 5 * (size_t)A.lvl_cap[lv]; };
+    const size_t row_copy = (size_t)kMaxGrid * kRowChunks, slot_copy = kSlotCopy; // chunks between the two copies
+    auto rows_of = [&](unsigned round) { return A.rows + (round & 1u) * row_copy; };
+    auto slots_of = [&](unsigned it) { return A.bslot + (it & 1u) * slot_copy; };
+
+    unsigned rel = A.epoch_base; // iterations started (barrier-B arrivals)
+    unsigned arr = A.epoch_base; // row rounds
+
+    if(gtid() == 0)
+    {
+#pragma unroll
+        for(int i = 0; i < 16; i++) S->resultRt[i] = (i % 5 == 0) ? 1.0 : 0.0;
+#pragma unroll
+        for(int i = 0; i < 9; i++) S->Rcurr[i] = A.Rprev[i];
+#pragma unroll
+        for(int i = 0; i < 3; i++) S->tcurr[i] = A.tprev[i];
+#pragma unroll
+        for(int i = 0; i < 9; i++) S->Rprev[i] = A.Rprev[i];
+#pragma unroll
+        for(int i = 0; i < 3; i++) S->tprev[i] = A.tprev[i];
+        S->last_icp_error = A.prev_icp_error; S->last_icp_count = A.prev_icp_count;
+        S->last_so3_error = A.prev_so3_error; S->last_so3_count = A.prev_so3_count;
+        S->last_rgb_error = A.prev_rgb_error; S->last_rgb_count = A.prev_rgb_count;
+        S->so3_iterations = 0;
+        S->se3_iterations[0] = S->se3_iterations[1] = S->se3_iterations[2] = 0;
+    }
+    group_sync();
+
+    int dbg_it = 0;
+    auto stamp = [&](int k) {
+        if constexpr(TIMING)
+        {
+            if(gtid() == 0 && dbg_it < kMaxIters) A.dbg[((size_t)blockIdx.x * kMaxIters + dbg_it) * kDbgStamps + k] = clock64();
+        }
+    };
+    if constexpr(TIMING)
+    {
+        if(is_writer) A.dbg[(size_t)(kMaxIters - 2) * kDbgStamps] = clock64();
+    }
+
+    // ============================================================================================
+    // SO(3) pre-alignment: RGBDOdometry.cpp:294-382 (level 2, at most 10 so3Step evaluations)
+    // ============================================================================================
+    if(A.so3)
+    {
+        const LevelArgs & L = A.lvl[2];
+        So3Params P;
+        P.rows = L.rows;
+        P.cols = L.cols;
+        P.kinv = mat_from(A.so3_kinv);
+        if(gtid() == 0)
+        {
+#pragma unroll
+            for(int i = 0; i < 9; i++)
+            {
+                S->so3_R[i] = S->so3_lastR[i] = (i % 4 == 0) ? 1.0 : 0.0;
+                S->so3_R_lr[i] = (i % 4 == 0) ? 1.f : 0.f;
+            }
+            S->so3_lastError = FLT_MAX / 2;
+            S->so3_lastCount = FLT_MAX / 2;
+        }
+        UnitIter U{L.rows * L.cols, W, widx, (int)lane, (int)warp};
+        const int passes = U.passes();
+
+        for(int it = 0; it <= 10; it++)
+        {
+            ++rel;
+            // ---- everybody: digest the previous evaluation (:348-380), derive the next homography ----
+            if(it > 0) gather_rows(rows_of(arr), G, kSo3Chunks, arr, s_rows, s_red, s_final);
+            float * par = s_par[rel & 1u];
+            if(gtid() == 0)
+            {
+                int d = 0;
+                if(it > 0) d = solve_so3(S, s_final, it);
+                make_so3_params(S, par, d, L.fx, L.fy, L.cx, L.cy, L.K_inv);
+                s_flag = d;
+            }
+            group_sync();
+            if(s_flag != 0) break;
+            P.image_basis = mat_from(par);
+            P.krlr = mat_from(par + 9);
+            ++arr;
+
+            // ---- so3Step over this CTA's pixels ----
+            float acc[kSets][16];
+#pragma unroll
+            for(int q = 0; q < kSets; q++)
+#pragma unroll
+                for(int i = 0; i < 16; i++) acc[q][i] = 0.f;
+            for(int p = 0; p < passes; p += kSets)
+            {
+#pragma unroll
+                for(int q = 0; q < kSets; q++) // pass p + q belongs to virtual warp set q (p is a multiple of kSets)
+                {
+                    const int u = (p + q < passes) ? U.unit(p + q) : -1;
+                    if(u >= 0)
+                    {
+                        const int y = u / L.cols, x = u - y * L.cols;
+                        float row[4];
+                        if(so3_row(P, x, y, A.so3_last, A.so3_next, L.cols, row)) accumulate_so3(acc[q], row);
+                    }
+                }
+            }
+#pragma unroll
+            for(int q = 0; q < kSets; q++)
+            {
+                const float lane_value = warp_transpose_reduce16(acc[q]);
+                if(lane < 16) s_red[(warp + q * kWarps) * 16 + lane] = lane_value;
+            }
+            group_sync();
+            if(gtid() < 16)
+            {
+                float s = 0.f;
+#pragma unroll
+                for(int w = 0; w < kVWarps; w++) s += s_red[w * 16 + gtid()];
+                s_final[gtid()] = (gtid() < 11) ? s : 0.f;
+            }
+            group_sync();
+            publish_row(rows_of(arr) + (size_t)widx * kSo3Chunks, s_final, kSo3Chunks, arr);
+        }
+        if(gtid() == 0)
+        {
+#pragma unroll
+            for(int x = 0; x < 3; x++)
+            {
+#pragma unroll
+                for(int y = 0; y < 3; y++) S->resultRt[x * 4 + y] = S->so3_R[x * 3 + y]; // :394-403
+            }
+        }
+        group_sync();
+    }
+
+    // ============================================================================================
+    // coarse-to-fine Gauss-Newton: RGBDOdometry.cpp:405-585
+    // ============================================================================================
+    IcpParams IP;
+    IP.Rprev_inv = mat_from(A.Rprev_inv);
+    IP.tprev = make_float3(A.tprev[0], A.tprev[1], A.tprev[2]);
+    IP.dist_thresh = A.dist_thresh;
+    IP.angle_thresh = A.angle_thresh;
+
+    int it_global = 0;
+    bool pending = false; // a row round nobody has digested yet
+    int pending_level = 0;
+
+    // Level preparation in units (one compaction group or one staging batch each, ~5 000 cycles): a level's units run at its
+    // start at the latest, but when all levels' lists fit shared memory side by side (A.prework) they run earlier, one per
+    // iteration of a coarser level, in the window where the rows of the other CTAs are still on their way.
+    int prep_unit[kNumPyrs] = {0, 0, 0}, prep_cand[kNumPyrs] = {0, 0, 0};
+    auto prep_passes = [&](int lv) { return UnitIter{A.lvl[lv].rows * A.lvl[lv].cols, W, widx, (int)lane, (int)warp}.passes(); };
+    auto prep_groups = [&](int lv) { return A.rgb ? (prep_passes(lv) + kCompactGroup - 1) / kCompactGroup : 0; };
+    auto prep_units = [&](int lv) {
+        return prep_groups(lv) + ((A.icp && A.icp_in_smem) ? (prep_passes(lv) + kStageBatch - 1) / kStageBatch : 0);
+    };
+    auto prepare_unit = [&](int lv) {
+        const LevelArgs & PL = A.lvl[lv];
+        const UnitIter PU{PL.rows * PL.cols, W, widx, (int)lane, (int)warp};
+        const int pp = PU.passes(), groups = prep_groups(lv), unit = prep_unit[lv]++;
+        if(unit < groups)
+        {
+            RgbResParams PR;
+            PR.min_scale = PL.min_scale;
+            PR.max_depth_delta = A.max_depth_delta;
+            PR.rows = PL.rows;
+            PR.cols = PL.cols;
+            const CandStore PC = cand_store(lv);
+            prep_cand[lv] = A.make_derivatives ? compact_group<true>(PL, PR, PU, pp, PC, s_wtot, unit, prep_cand[lv])
+                                               : compact_group<false>(PL, PR, PU, pp, PC, s_wtot, unit, prep_cand[lv]);
+        }
+        else
+            stage_batch(PL, PU, pp, vn_store(lv), A.lvl_cap[lv], (unit - groups) * kStageBatch);
+    };
+
+    for(int lv = kNumPyrs - 1; lv >= 0; lv--)
+    {
+        const LevelArgs & L = A.lvl[lv];
+        if(L.iterations <= 0) continue;
+
+        IP.intr = Intr{L.fx, L.fy, L.cx, L.cy};
+        IP.rows = L.rows;
+        IP.cols = L.cols;
+        RgbResParams RP;
+        RP.min_scale = L.min_scale;
+        RP.max_depth_delta = A.max_depth_delta;
+        RP.rows = L.rows;
+        RP.cols = L.cols;
+        RgbStepParams SP;
+        SP.fx = L.fx; SP.fy = L.fy; SP.inv_fx = L.inv_fx; SP.inv_fy = L.inv_fy; SP.cx = L.cx; SP.cy = L.cy;
+        SP.sobel_scale = A.sobel_scale;
+        SP.sigma = 0.f;
+        UnitIter U{L.rows * L.cols, W, widx, (int)lane, (int)warp};
+        const int passes = U.passes();
+
+        // ---- level start: whatever is left of this level's preparation (candidate list, staged current maps) ----
+        const CandStore C = cand_store(lv);
+        float * const s_vn = vn_store(lv);
+        dbg_it = it_global;
+        stamp(10);
+        if(!A.prework) group_sync(); // the levels share one region: every thread is done with the previous level's records
+        while(prep_unit[lv] < prep_units(lv)) prepare_unit(lv);
+        group_sync();
+        stamp(11);
+        stamp(12);
+        const int n_cand = prep_cand[lv];
+        int next_lv = lv - 1;
+        while(next_lv >= 0 && A.lvl[next_lv].iterations <= 0) next_lv--;
+
+        float lastRGBError = FLT_MAX;      // every thread tracks it for the uniform rgb_only break (:464)
+        bool first_of_level = true;
+
+        for(int j = 0; j < L.iterations; j++)
+        {
+            const int cnt_slot = it_global++;
+            dbg_it = cnt_slot;
+            stamp(0);
+            ++rel;
+            // a unit of the next level's preparation while the other CTAs' rows are on their way
+            if(A.prework && j > 0)
+            {
+                while(next_lv >= 0 && prep_unit[next_lv] >= prep_units(next_lv))
+                {
+                    next_lv--;
+                    while(next_lv >= 0 && A.lvl[next_lv].iterations <= 0) next_lv--;
+                }
+                if(next_lv >= 0) prepare_unit(next_lv);
+            }
+            // ---- everybody: finish the previous iteration (:541-583) and derive this one's pose (:480-481) and photometric
+            //      warp (:424-434) -- warps 0 and 1 side by side, identical in every CTA ----
+            const bool was_pending = pending;
+            if(pending)
+            {
+                gather_rows(rows_of(arr), G, kRowChunks, arr, s_rows, s_red, s_final);
+                stamp(2);
+                if(warp == 0)
+                    warp_solve_se3(S, s_final, A.icp, A.rgb, A.icp_weight, pending_level, A.rgb != 0,
+                                   (TIMING && b == 0 && dbg_it < kMaxIters) ? A.dbg + (size_t)dbg_it * kDbgStamps : nullptr);
+                stamp(3);
+            }
+            if(gtid() == 0 && first_of_level) S->last_rgb_error = FLT_MAX; // :420
+            float * par = s_par[rel & 1u];
+            if(warp == 0)
+            {
+                // (with a solve pending the hand-over to warp 1 happened inside warp_solve_se3, right after the SE(3) update)
+                if(!was_pending && A.rgb) solver_pair_sync();
+                warp_make_pose(S, par);
+                stamp(7);
+            }
+            else if(warp == 1 && A.rgb)
+            {
+                solver_pair_sync();
+                warp_make_rgb_params(S, par, L.fx, L.fy, L.cx, L.cy, L.K_inv);
+            }
+            group_sync();
+            stamp(1);
+            stamp(4);
+            IP.Rcurr = mat_from(par);
+            IP.tcurr = make_float3(par[9], par[10], par[11]);
+            RP.krkinv = mat_from(par + 12);
+            RP.kt = make_float3(par[21], par[22], par[23]);
+            pending = false;
+            first_of_level = false;
+
+            // ---- phase A1: photometric association of the candidates -> records in shared memory, then the barrier-B arrival:
+            //      this CTA's {count, sum diff^2} as one flagged chunk (integer sums are exact in any order and sigma wraps
+            //      mod 2^32 exactly like the reference's int sum) ----
+            if(A.rgb)
+            {
+                int cnt = 0, sig = 0;
+                rgb_assoc_cands(L, RP, C, n_cand, cnt, sig);
+                cnt = __reduce_add_sync(kFullMask, cnt);
+                sig = __reduce_add_sync(kFullMask, sig);
+                if(lane == 0) { s_wcnt[warp] = cnt; s_wsig[warp] = sig; }
+                group_sync();
+                if(gtid() == 0)
+                {
+                    unsigned c = 0, s = 0;
+#pragma unroll
+                    for(int w = 0; w < kWarps; w++) { c += (unsigned)s_wcnt[w]; s += (unsigned)s_wsig[w]; }
+                    st_relaxed_v4(slots_of(rel) + widx, make_uint4(c, s, 0u, rel));
+                }
+            }
+            stamp(5);
+
+            // ---- phase A2: ICP association + 29 sums (hides the barrier-B hop and the inter-CTA skew) ----
+            float accI[kSets][32];
+#pragma unroll
+            for(int q = 0; q < kSets; q++)
+#pragma unroll
+                for(int i = 0; i < 32; i++) accI[q][i] = 0.f;
+            {
+                float vi[kSets];
+#pragma unroll
+                for(int q = 0; q < kSets; q++) vi[q] = 0.f;
+                if(A.icp)
+                {
+                    const bool anyI = A.icp_in_smem ? icp_passes<true>(L, IP, U, 0, passes, accI, s_vn, A.lvl_cap[lv])
+                                                    : icp_passes<false>(L, IP, U, 0, passes, accI, s_vn, A.lvl_cap[lv]);
+                    if(__any_sync(kFullMask, anyI)) // a warp without pixels contributes zeros
+                    {
+#pragma unroll
+                        for(int q = 0; q < kSets; q++) vi[q] = warp_transpose_reduce32(accI[q]);
+                    }
+                }
+#pragma unroll
+                for(int q = 0; q < kSets; q++)
+                    if(lane < 29) s_red[(warp + q * kWarps) * 64 + lane] = vi[q];
+                stamp(8);
+            }
+
+            // ---- barrier B: every CTA reads all arrivals, adds them and forms the robust-weight scale (:461-462) itself ----
+            bool level_break = false;
+            if(A.rgb)
+            {
+                int c = 0, sg = 0;
+                const uint4 * slots = slots_of(rel);
+                for(int w = gtid(); w < G; w += kThreads)
+                {
+                    uint4 v;
+                    do
+                    {
+                        v = ld_relaxed_v4(slots + w);
+                    } while(v.w != rel);
+                    c += (int)v.x;
+                    sg += (int)v.y;
+                }
+                c = __reduce_add_sync(kFullMask, c);
+                sg = __reduce_add_sync(kFullMask, sg);
+                group_sync(); // (s_wcnt / s_wsig: everybody is past the CTA total of phase A1)
+                if(lane == 0) { s_wcnt[warp] = c; s_wsig[warp] = sg; }
+                group_sync();
+                if(gtid() == 0)
+                {
+                    unsigned cc = 0, ss = 0;
+#pragma unroll
+                    for(int w = 0; w < kWarps; w++) { cc += (unsigned)s_wcnt[w]; ss += (unsigned)s_wsig[w]; }
+                    float sigmaVal, rgbError;
+                    sigma_from_sums((int)ss, (int)cc, sigmaVal, rgbError); // :461-462
+                    s_sigma[0] = sigmaVal;
+                    s_sigma[1] = rgbError;
+                    s_sigma[2] = (float)(int)cc;
+                }
+                group_sync();
+                stamp(6);
+                const float rgbError = s_sigma[1];
+                if(A.rgb_only && rgbError > lastRGBError) level_break = true; // :464 (uniform across the grid)
+                if(!level_break)
+                {
+                    lastRGBError = rgbError;
+                    if(gtid() == 0)
+                    {
+                        S->last_rgb_error = rgbError; // :469-470
+                        S->last_rgb_count = s_sigma[2];
+                    }
+                    SP.sigma = A.rgb_only ? -1.f : s_sigma[0]; // :472-475
+                }
+            }
+            else if(gtid() == 0)
+            {
+                // :461-470 run even without RGB: sigma = rgbSize = 0 -> rgbError 0, count 0
+                S->last_rgb_error = 0.f;
+                S->last_rgb_count = 0.f;
+            }
+            if(level_break) break; // no row outstanding: every CTA takes the same branch
+
+            ++arr;
+            pending = true;
+            pending_level = lv;
+
+            // ---- phase B: photometric rows from the records in shared memory -> 29 more sums; this CTA's row of the round ----
+            {
+                float vr[kSets];
+#pragma unroll
+                for(int q = 0; q < kSets; q++) vr[q] = 0.f;
+                if(A.rgb)
+                {
+                    float accR[kSets][32];
+#pragma unroll
+                    for(int q = 0; q < kSets; q++)
+#pragma unroll
+                        for(int i = 0; i < 32; i++) accR[q][i] = 0.f;
+                    const bool any = rgb_rows_cands(SP, C, n_cand, accR);
+                    if(__any_sync(kFullMask, any))
+                    {
+#pragma unroll
+                        for(int q = 0; q < kSets; q++) vr[q] = warp_transpose_reduce32(accR[q]);
+                    }
+                }
+#pragma unroll
+                for(int q = 0; q < kSets; q++)
+                    if(lane < 29) s_red[(warp + q * kWarps) * 64 + 29 + lane] = vr[q];
+                group_sync();
+                if(gtid() < kRowFloats)
+                {
+                    float sum = 0.f;
+                    if(gtid() < 58)
+                    {
+#pragma unroll
+                        for(int w = 0; w < kVWarps; w++) sum += s_red[w * 64 + gtid()];
+                    }
+                    s_final[gtid()] = sum;
+                }
+                group_sync();
+                publish_row(rows_of(arr) + (size_t)widx * kRowChunks, s_final, kRowChunks, arr);
+                stamp(9);
+            }
+        }
+    }
+
+    // ============================================================================================
+    // epilogue: last solve (every CTA; CTA 0 writes), jump rejection (:587-591), outputs
+    // ============================================================================================
+    if(b != 0) return; // (their last rows stay where they are: nothing rewrites them in this launch)
+    if(pending)
+    {
+        gather_rows(rows_of(arr), G, kRowChunks, arr, s_rows, s_red, s_final);
+        if(warp == 0) warp_solve_se3(S, s_final, A.icp, A.rgb, A.icp_weight, pending_level, false, nullptr);
+        group_sync();
+    }
+    if(is_writer)
+    {
+        float Rc[9], tc[3];
+#pragma unroll
+        for(int i = 0; i < 9; i++) Rc[i] = S->Rcurr[i];
+#pragma unroll
+        for(int i = 0; i < 3; i++) tc[i] = S->tcurr[i];
+        if(A.rgb)
+        {
+            const float d[3] = {tc[0] - A.tprev[0], tc[1] - A.tprev[1], tc[2] - A.tprev[2]};
+            if(sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]) > 0.3)
+            {
+#pragma unroll
+                for(int i = 0; i < 9; i++) Rc[i] = A.Rprev[i];
+#pragma unroll
+                for(int i = 0; i < 3; i++) tc[i] = A.tprev[i];
+            }
+        }
+        TrackOutput * out = A.out;
+#pragma unroll
+        for(int i = 0; i < 3; i++) out->trans[i] = tc[i];
+#pragma unroll
+        for(int i = 0; i < 9; i++) out->rot[i] = Rc[i];
+        out->st.last_icp_error = S->last_icp_error; out->st.last_icp_count = S->last_icp_count;
+        out->st.last_rgb_error = S->last_rgb_error; out->st.last_rgb_count = S->last_rgb_count;
+        out->st.last_so3_error = S->last_so3_error; out->st.last_so3_count = S->last_so3_count;
+        out->st.so3_iterations = S->so3_iterations;
+#pragma unroll
+        for(int i = 0; i < 3; i++) out->st.se3_iterations[i] = S->se3_iterations[i];
+        if(S->se3_iterations[0] + S->se3_iterations[1] + S->se3_iterations[2] > 0)
+        {
+            // lastA / lastb of the last solve (reduce.cu:475-486 unpack order)
+#pragma unroll
+            for(int i = 0; i < 6; i++)
+            {
+#pragma unroll
+                for(int j = i; j < 7; j++)
+                {
+                    const double v = S->last_S[hm::acc_index(i, j)];
+                    if(j == 6) out->st.last_b[i] = v;
+                    else out->st.last_A[j * 6 + i] = out->st.last_A[i * 6 + j] = v;
+                }
+            }
+        }
+        // the host polls `status` in pinned memory (device_track_finish): result first, fence, then the flag.
+        // 2 = no solve ran: lastA / lastb keep their previous values (host side)
+        const int status = (S->se3_iterations[0] + S->se3_iterations[1] + S->se3_iterations[2] > 0) ? 1 : 2;
+        if constexpr(TIMING) A.dbg[(size_t)(kMaxIters - 1) * kDbgStamps] = clock64();
+        __threadfence_system();
+        *reinterpret_cast<volatile int *>(&out->status) = status;
+        __threadfence_system();
+    }
+}
+
+template<bool TIMING>
+__global__ void __launch_bounds__(kThreads, 1) k_track_sym(const __grid_constant__ BatchArgs BA)
+{
+    extern __shared__ int4 s_dyn_sym[];
+    __shared__ GroupShared s_group;
+    track_body_sym<TIMING>(BA.seq[0], s_group, s_dyn_sym, (int)blockIdx.x, (int)gridDim.x);
+}
+#endif // symmetric body
 
 // One sequence of a launch, as seen by one thread group: the solver CTA of the sequence (is_solver_cta: gathers, solves, publishes)
 // or worker `widx` of its W workers.  s_dyn: the group's dynamic shared memory -- workers: candidates + match records; solver:
@@ -2035,6 +2570,7 @@ struct Layout // shared-memory geometry of one thread group for a grid of `grid`
     int grid;
     int cand_cap, icp_in_smem, prework;
     int lvl_cap[kNumPyrs], lvl_off[kNumPyrs];
+    int cand_base;     // bytes: where the lists start in the group's dynamic shared memory (symmetric body: behind the gathered rows)
     size_t smem_bytes; // per group, multiple of 16
 };
 
@@ -2050,14 +2586,26 @@ struct DeviceTrack
     uint4 * rows;
     TrackOutput * out; // pinned
     Layout lay;        // of the single launch (all of a CTA's shared memory)
+    Layout lay_sym;    // the same grid with the symmetric body
+    bool use_sym;      // this handle's launches run k_track_sym (a handle on a subset of the SMs)
     unsigned launch_seq;
 };
 
 // pixels per thread unit and passes per level -> shared-memory records per thread, within `budget` bytes of dynamic
 // shared memory.  false: the photometric candidates of a CTA do not fit.
+// solvers = 1: track_body (CTA 0 gathers and solves); n: the alternating build; 0: the symmetric body -- every CTA is a worker and
+// gathers all rows itself (rows and lists side by side, one level's lists at a time)
 bool compute_layout(const ef_tracker * t, int grid, size_t budget, Layout & L, int solvers = 1, bool allow_prework = true)
 {
     const int W = grid - solvers;
+    const size_t rows_beside = solvers ? 0 : (((size_t)grid * kRowFloats * sizeof(float) + 15) & ~(size_t)15);
+    L.cand_base = (int)rows_beside;
+    if(!solvers)
+    {
+        if(budget <= rows_beside) return false;
+        budget -= rows_beside;
+        allow_prework = false;
+    }
     int max_cand = 1;
     for(int i = 0; i < kNumPyrs; i++)
     {
@@ -2090,13 +2638,14 @@ bool compute_layout(const ef_tracker * t, int grid, size_t budget, Layout & L, i
             L.lvl_off[i] = 0;
         }
     const size_t rows_smem = (size_t)W * kRowFloats * sizeof(float);
-    if(rows_smem > smem) smem = rows_smem;
+    if(solvers && rows_smem > smem) smem = rows_smem;
+    smem += rows_beside;
     L.grid = grid;
     L.prework = prework ? 1 : 0;
     L.cand_cap = max_cand;
     L.icp_in_smem = icp_in_smem ? 1 : 0;
     L.smem_bytes = (smem + 15) & ~(size_t)15;
-    return L.smem_bytes <= budget;
+    return L.smem_bytes <= budget + rows_beside;
 }
 
 // everything a launch passes to one thread group (one sequence)
@@ -2142,9 +2691,8 @@ void fill_args(ef_tracker * t, DeviceTrack * d, const Layout & lay, const float 
     if((d->launch_seq & 0xffffffu) == 0)
     {
         d->launch_seq = 1;
-        const int mg = t->num_sms < kMaxGrid ? t->num_sms : kMaxGrid;
-        cudaMemsetAsync(d->rows, 0, (size_t)mg * kRowChunks * sizeof(uint4), t->stream);
-        cudaMemsetAsync(d->par, 0, (2 * (size_t)kParCopyStride + 2 * (size_t)((mg + 7) & ~7)) * sizeof(uint4), t->stream);
+        cudaMemsetAsync(d->rows, 0, kRowsChunks * sizeof(uint4), t->stream);
+        cudaMemsetAsync(d->par, 0, kCtlChunks * sizeof(uint4), t->stream);
     }
     A.epoch_base = d->launch_seq << 8;
     A.par = d->par;
@@ -2163,6 +2711,7 @@ void fill_args(ef_tracker * t, DeviceTrack * d, const Layout & lay, const float 
     A.make_derivatives = (A.rgb && !t->deriv_valid) ? 1 : 0;
     A.icp_in_smem = lay.icp_in_smem;
     A.group_smem_bytes = (int)lay.smem_bytes;
+    A.cand_base = lay.cand_base;
     d->out->status = 0;
 }
 
@@ -2233,13 +2782,18 @@ int EF_TRACK_FN(device_track_configure)(ef_tracker * t, int grid)
         return EF_ERR_UNSUPPORTED;
     }
     d->lay = L;
+    // a handle that shares the GPU runs the symmetric body (see track_body_sym); EF_TRACK_SYM=0 / 1 forces one or the other
+    const char * env = getenv("EF_TRACK_SYM");
+    const bool want_sym = env ? env[0] == '1' : grid < max_grid;
+    d->use_sym = want_sym && compute_layout(t, grid, (size_t)kMaxDynSmem, d->lay_sym, 0);
     return EF_OK;
 }
 
 bool EF_TRACK_FN(device_track_supported)(const ef_tracker * t)
 {
     const DeviceTrack * d = static_cast<const DeviceTrack *>(t->track_state);
-    return d && d->lay.smem_bytes <= (size_t)kMaxDynSmem && (size_t)t->width * t->height < (1u << 24) && t->width <= 4094 && t->height <= 4094;
+    const Layout & L = d && d->use_sym ? d->lay_sym : d->lay;
+    return d && L.smem_bytes <= (size_t)kMaxDynSmem && (size_t)t->width * t->height < (1u << 24) && t->width <= 4094 && t->height <= 4094;
 }
 
 int EF_TRACK_FN(device_track_init)(ef_tracker * t)
@@ -2250,13 +2804,13 @@ int EF_TRACK_FN(device_track_init)(ef_tracker * t)
     EF_TRACK_FN(device_track_configure)(t, 0);
     const int max_grid = t->num_sms < kMaxGrid ? t->num_sms : kMaxGrid;
     d->launch_seq = 0;
-    const size_t ctl_chunks = 2 * (size_t)kParCopyStride + 2 * (size_t)((max_grid + 7) & ~7);
+    const size_t ctl_chunks = kCtlChunks;
     cudaError_t e = cudaMalloc((void **)&d->par, ctl_chunks * sizeof(uint4));
     if(e == cudaSuccess) e = cudaMemsetAsync(d->par, 0, ctl_chunks * sizeof(uint4), t->stream);
     d->bslot = d->par ? d->par + 2 * (size_t)kParCopyStride : nullptr;
-    d->bres = d->par ? d->bslot + ((max_grid + 7) & ~7) : nullptr;
-    if(e == cudaSuccess) e = cudaMalloc((void **)&d->rows, (size_t)max_grid * kRowChunks * sizeof(uint4));
-    if(e == cudaSuccess) e = cudaMemsetAsync(d->rows, 0, (size_t)max_grid * kRowChunks * sizeof(uint4), t->stream);
+    d->bres = d->par ? d->bslot + 2 * kSlotCopy : nullptr;
+    if(e == cudaSuccess) e = cudaMalloc((void **)&d->rows, kRowsChunks * sizeof(uint4));
+    if(e == cudaSuccess) e = cudaMemsetAsync(d->rows, 0, kRowsChunks * sizeof(uint4), t->stream);
     if(e == cudaSuccess) e = cudaHostAlloc((void **)&d->out, sizeof(TrackOutput), cudaHostAllocMapped);
     const char * env = getenv("EF_TRACK_TIMING");
     if(e == cudaSuccess && env && env[0] == '1')
@@ -2268,6 +2822,8 @@ int EF_TRACK_FN(device_track_init)(ef_tracker * t)
     }
     if(e == cudaSuccess) e = cudaFuncSetAttribute(k_track<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
     if(e == cudaSuccess) e = cudaFuncSetAttribute(k_track<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
+    if(e == cudaSuccess) e = cudaFuncSetAttribute(k_track_sym<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
+    if(e == cudaSuccess) e = cudaFuncSetAttribute(k_track_sym<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
     if(e != cudaSuccess)
     {
         EF_TRACK_FN(device_track_destroy)(t);
@@ -2346,10 +2902,12 @@ int EF_TRACK_FN(device_track_launch)(ef_tracker * t, const float * trans, const 
         return EF_ERR_UNSUPPORTED;
     }
     BatchArgs B;
-    fill_args(t, d, d->lay, trans, rot, rgb_only, icp_weight, pyramid, fast_odom, so3, B.seq[0]);
+    const Layout & lay = d->use_sym ? d->lay_sym : d->lay;
+    fill_args(t, d, lay, trans, rot, rgb_only, icp_weight, pyramid, fast_odom, so3, B.seq[0]);
     void * args[] = {&B};
-    const void * fn = d->dbg ? (const void *)k_track<true> : (const void *)k_track<false>;
-    cudaError_t e = cudaLaunchCooperativeKernel(fn, dim3(d->lay.grid), dim3(kThreads), args, d->lay.smem_bytes, t->stream);
+    const void * fn = d->use_sym ? (d->dbg ? (const void *)k_track_sym<true> : (const void *)k_track_sym<false>)
+                                 : (d->dbg ? (const void *)k_track<true> : (const void *)k_track<false>);
+    cudaError_t e = cudaLaunchCooperativeKernel(fn, dim3(lay.grid), dim3(kThreads), args, lay.smem_bytes, t->stream);
     t->launches++;
     if(e != cudaSuccess)
     {

@@ -2,8 +2,9 @@
 
 Default = the ALTERNATING kernel (EF_TRACK_ALT in ef_track_kernel.cu): sequence s has its own solver CTA and the worker CTAs take
 the sequences in turn, one Gauss-Newton iteration each.  A sequence's pixels are dealt to 148 - k workers instead of 147, so it
-returns the bits of a single launch configured with that many workers (EF_OPT_GRID_CTAS = SMs - k + 1) and agrees with the
-default single launch within the pose tolerance.  EF_BATCH_MODE=groups selects the older build with two thread groups per CTA,
+returns the bits of a single launch on that many workers -- EF_OPT_GRID_CTAS = SMs - k: a handle on a subset of the SMs runs the
+symmetric body, in which every CTA is a worker, and adds the rows in the same order -- and agrees with the default single launch
+within the pose tolerance.  EF_BATCH_MODE=groups selects the older build with two thread groups per CTA,
 which returns the default single launch's bits (two accumulator sets per thread, EF_TRACK_SETS)."""
 import numpy as np
 import pytest
@@ -89,7 +90,7 @@ def _run(size, k, single_grid, monkeypatch=None, groups=False):
 @pytest.mark.parametrize("size,k", [((640, 480), 2), ((640, 480), 4), ((320, 240), 3), ((322, 242), 2)],
                          ids=["640x480-k2", "640x480-k4", "320x240-k3", "322x242-k2"])
 def test_alternating_launch_equals_single_launches_bit_for_bit(size, k):
-    _run(size, k, _sms() - k + 1)
+    _run(size, k, _sms() - k)
 
 
 @pytest.mark.parametrize("size", [(640, 480), (322, 242)], ids=["groups-640x480", "groups-322x242"])
@@ -107,7 +108,7 @@ def test_sequences_of_a_batch_may_end_at_different_iterations():
     s = [ef.RGBDOdometry(w, h, K.cx, K.cy, K.fx, K.fy) for _ in seqs]
     try:
         for t in s:
-            t.set_option(RO.EF_OPT_GRID_CTAS, _sms() - 1)
+            t.set_option(RO.EF_OPT_GRID_CTAS, _sms() - 2)
         bt = RO.BatchTracker(a)
         for g, (_, frames) in enumerate(seqs):
             a[g].initFirstRGB(frames[0]["rgba"])
@@ -129,7 +130,7 @@ def test_sequences_of_a_batch_may_end_at_different_iterations():
 
 def test_batches_on_disjoint_sm_subsets_run_concurrently():
     """EF_OPT_GRID_CTAS of a batch's first handle sizes its launch: two batches of two sequences on half of the SMs each, both in
-    flight at once (launch / finish), give the bits of single launches on 74 - 2 workers."""
+    flight at once (launch / finish), give the bits of single launches on 74 - 2 workers (EF_OPT_GRID_CTAS = 72: the symmetric body, every CTA a worker)."""
     w, h = 320, 240
     half = _sms() // 2
     K, seqs = _sequences(w, h, 3, seeds=(3, 4))
@@ -140,7 +141,7 @@ def test_batches_on_disjoint_sm_subsets_run_concurrently():
             for t in grp:
                 t.set_option(RO.EF_OPT_GRID_CTAS, half)
         for t in s:
-            t.set_option(RO.EF_OPT_GRID_CTAS, half - 1)
+            t.set_option(RO.EF_OPT_GRID_CTAS, half - 2)
         bta, btb = RO.BatchTracker(a), RO.BatchTracker(b)
         args = (20.0, False, 10.0, True, False, False)
         for f in (1, 2):

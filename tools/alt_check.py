@@ -32,7 +32,7 @@ for k in (2, 3, 4):
     single = [ef.RGBDOdometry(w, h, K.cx, K.cy, K.fx, K.fy, solve_mode=RO.EF_SOLVE_DEVICE) for _ in range(k)]
     batched = [ef.RGBDOdometry(w, h, K.cx, K.cy, K.fx, K.fy, solve_mode=RO.EF_SOLVE_DEVICE) for _ in range(k)]
     for t in single:
-        t.set_option(RO.EF_OPT_GRID_CTAS, sms - k + 1)  # the same number of workers as the batched launch gives a sequence
+        t.set_option(RO.EF_OPT_GRID_CTAS, sms - k)  # the same number of workers as the batched launch gives a sequence
     try:
         bt = RO.BatchTracker(batched)
         for g in range(k):
