@@ -17,4 +17,5 @@ timeout 400 ncu --set full --clock-control none --import-source on -k regex:k_bu
 PYTHONPATH=. timeout 400 ncu --set full --clock-control none --import-source on -k regex:k_track_alt -s 3 -c 2 -f -o gpurun_out/prof_alt_r02 python tools/alt_run.py 2 6 > gpurun_out/prof_alt_r02.out 2>&1
 timeout 400 ncu --set full --clock-control none --import-source on -k regex:k_hm_step -s 28 -c 2 -f -o gpurun_out/prof_hmstep720_r02 $B --solve host --width 1280 --height 720 > gpurun_out/prof_hmstep720_r02.out 2>&1
 timeout 400 ncu --set full --clock-control none --import-source on -k regex:k_hm_residual -s 28 -c 2 -f -o gpurun_out/prof_hmres720_r02 $B --solve host --width 1280 --height 720 > gpurun_out/prof_hmres720_r02.out 2>&1
+PYTHONPATH=. timeout 400 ncu --set full --clock-control none --import-source on -k regex:k_track_sym -s 8 -c 2 -f -o gpurun_out/prof_sym_r02 python tools/alt_part.py 4 1 > gpurun_out/prof_sym_r02.out 2>&1
 ls -la gpurun_out/*r02*

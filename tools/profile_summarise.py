@@ -122,6 +122,7 @@ def main():
     full_summary("prof_track720_r02.ncu-rep", "k_track, 1280x720 SO(3) + joint ICP+RGB (384 threads x 148 CTAs)", "r02_k_track_ncu_full.txt", "1280x720", traffic)
     full_summary("prof_build_r02.ncu-rep", "k_build_frame, 640x480 (every pyramid of a frame-to-model frame from one launch)", "r02_k_build_frame_ncu_full.txt")
     full_summary("prof_alt_r02.ncu-rep", "k_track_alt, 640x480 joint ICP+RGB, TWO sequences per launch (2 solver CTAs + 146 workers alternating between the sequences)", "r02_k_track_alt_ncu_full.txt")
+    full_summary("prof_sym_r02.ncu-rep", "k_track_sym, 640x480 joint ICP+RGB, a handle on 37 of the 148 SMs (symmetric body: every CTA gathers all rows and solves)", "r02_k_track_sym_ncu_full.txt")
     for f in ("r02_host_fused_ncu_full.txt",):
         if os.path.exists(os.path.join(P, f)):
             os.remove(os.path.join(P, f))
