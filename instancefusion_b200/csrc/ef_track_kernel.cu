@@ -900,7 +900,7 @@ __device__ __forceinline__ void rgb_assoc_batch(const LevelArgs & L, const RgbRe
     float td1[B];
     unsigned inext[B];
     bool valid[B], ok[B];
-    size_t q[B];
+    unsigned q[B]; // (pixel indices fit 32 bits: device_track_supported caps the image at 2^24 pixels)
 #pragma unroll
     for(int k = 0; k < B; k++)
     {
@@ -910,7 +910,7 @@ __device__ __forceinline__ void rgb_assoc_batch(const LevelArgs & L, const RgbRe
         const unsigned w = C.c0[cc];
         inext[k] = w >> 24;
         ok[k] = rgb_warp(RP, (int)(w & 0xfffu), (int)((w >> 12) & 0xfffu), C.c2[cc], u0[k], v0[k], td1[k]) && valid[k];
-        q[k] = ok[k] ? (size_t)v0[k] * cols + u0[k] : 0;
+        q[k] = ok[k] ? (unsigned)(v0[k] * cols + u0[k]) : 0u;
     }
     float d0s[B];
     unsigned ls[B];
@@ -999,7 +999,7 @@ constexpr int kStageBatch = EF_TRACK_STAGE_BATCH; // passes of a thread whose si
 __device__ __forceinline__ void stage_batch(const LevelArgs & L, const UnitIter & U, int passes, float * s_vn, int cap, int p0)
 {
     // one batch = one L2 round trip; nothing else is live in the registers at this point
-    const size_t plane = (size_t)L.rows * L.cols;
+    const unsigned plane = (unsigned)(L.rows * L.cols);
     float v[kStageBatch][6];
     int u[kStageBatch];
 #pragma unroll
@@ -1027,7 +1027,7 @@ __device__ __forceinline__ bool icp_batch(const LevelArgs & L, const IcpParams &
                                           const float * s_vn, int cap)
 {
     const int cols = L.cols;
-    const size_t plane = (size_t)L.rows * cols;
+    const unsigned plane = (unsigned)(L.rows * cols); // 32-bit indices: one IMAD.WIDE per gather instead of 64-bit adds
     float3 v[B], n[B];
     bool in1[B];
     bool any = false;
@@ -1054,13 +1054,13 @@ __device__ __forceinline__ bool icp_batch(const LevelArgs & L, const IcpParams &
     // from here on no control flow: the B pixels interleave (two warps per scheduler need the instruction-level
     // parallelism); rejected pixels gather pixel 0 and contribute rows of exact zeros
     float3 vg[B], vp[B], np[B];
-    size_t q[B];
+    unsigned q[B];
 #pragma unroll
     for(int k = 0; k < B; k++)
     {
         int ux, uy;
         in1[k] = icp_project(IP, v[k], vg[k], ux, uy) && in1[k];
-        q[k] = in1[k] ? (size_t)uy * cols + ux : 0;
+        q[k] = in1[k] ? (unsigned)(uy * cols + ux) : 0u;
     }
 #pragma unroll
     for(int k = 0; k < B; k++)
