@@ -112,7 +112,7 @@ typedef struct ef_track_stats
  * current for its duration and restores the caller's.
  * STREAM CONTRACT: device inputs (`d_` pointers, cudaArrays) are consumed on the handle's stream.  Work that produces them
  * on another stream must be ordered before the call by the caller: record an event there and pass it to
- * ef_tracker_wait_event, or synchronise.  (The reference has no such issue: everything runs on the legacy default stream.) */
+ * ef_tracker_wait_event (or hand the stream to ef_tracker_wait_stream), or synchronise.  (The reference has no such issue: everything runs on the legacy default stream.) */
 int ef_tracker_create(int width, int height, float cx, float cy, float fx, float fy, float dist_thresh, float angle_thresh,
                       void * stream, ef_tracker ** out);
 int ef_tracker_destroy(ef_tracker * t);
@@ -123,6 +123,9 @@ void * ef_tracker_stream(ef_tracker * t);
 int ef_tracker_synchronize(ef_tracker * t);
 /* the handle's stream waits for `cuda_event` (a cudaEvent_t recorded on the stream that produces the next call's device inputs) */
 int ef_tracker_wait_event(ef_tracker * t, void * cuda_event);
+/* the same from the producer's stream itself (a cudaStream_t; NULL = the legacy default stream): nothing happens when that stream is
+ * idle or is the handle's own stream, otherwise the handle's stream waits for everything enqueued there so far */
+int ef_tracker_wait_stream(ef_tracker * t, void * cuda_stream);
 
 /* default thresholds of the reference constructor (Utils/RGBDOdometry.h:38-39) */
 float ef_default_dist_thresh(void);

@@ -71,7 +71,7 @@ def lib() -> C.CDLL:
 # every symbol include/ef_track.h declares (checked by tests/test_abi.py against the header text)
 EXPORTED = [
     "ef_tracker_create", "ef_tracker_destroy", "ef_tracker_set_option", "ef_tracker_get_option", "ef_last_error",
-    "ef_tracker_stream", "ef_tracker_synchronize", "ef_tracker_wait_event", "ef_default_dist_thresh", "ef_default_angle_thresh",
+    "ef_tracker_stream", "ef_tracker_synchronize", "ef_tracker_wait_event", "ef_tracker_wait_stream", "ef_default_dist_thresh", "ef_default_angle_thresh",
     "ef_init_icp_depth", "ef_init_icp_depth_raw", "ef_init_icp_depth_raw_host", "ef_init_icp_maps", "ef_init_icp_model", "ef_init_rgb", "ef_init_rgb_model", "ef_init_first_rgb",
     "ef_init_icp_depth_array", "ef_init_icp_maps_array", "ef_init_icp_model_array", "ef_init_rgb_array",
     "ef_init_rgb_model_array", "ef_init_first_rgb_array",

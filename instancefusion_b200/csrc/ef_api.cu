@@ -496,6 +496,20 @@ EF_API int ef_tracker_wait_event(ef_tracker * t, void * cuda_event)
     return EF_OK;
 }
 
+EF_API int ef_tracker_wait_stream(ef_tracker * t, void * cuda_stream)
+{
+    if(!t) return EF_ERR_INVALID_ARGUMENT;
+    cudaStream_t producer = (cudaStream_t)cuda_stream;
+    if(producer == t->stream) return EF_OK;
+    EF_ON_DEVICE(t);
+    const cudaError_t q = cudaStreamQuery(producer);
+    if(q == cudaSuccess) return EF_OK; // idle: whatever it produced is complete
+    if(q != cudaErrorNotReady) return fail(t, (int)q, "cudaStreamQuery(producer stream)");
+    EF_CUDA(t, cudaEventRecord(t->ev_fork, producer)); // (ev_fork is re-recorded by every fork: a wait captures the record at the time of the call)
+    EF_CUDA(t, cudaStreamWaitEvent(t->stream, t->ev_fork, 0));
+    return EF_OK;
+}
+
 EF_API int ef_tracker_synchronize(ef_tracker * t)
 {
     EF_ON_DEVICE(t);

@@ -43,13 +43,17 @@ def _dev_ptr(a, dtype_name: str):
     return C.c_void_p(a.data_ptr())
 
 
-def _order_after_torch(handle_stream):
-    """Stream contract of include/ef_track.h: device inputs are consumed on the HANDLE's stream.  If torch's current stream
-    still has work in flight (it may be producing the tensor we are about to borrow), the handle's stream waits for it."""
+_raw_stream = None
+
+
+def _torch_raw_stream():
+    """torch's current CUDA stream as a raw cudaStream_t (an int), without building a torch.cuda.Stream object per call"""
+    global _raw_stream
     import torch
-    cur = torch.cuda.current_stream()
-    if cur.cuda_stream != handle_stream and not cur.query():
-        torch.cuda.ExternalStream(handle_stream).wait_stream(cur)
+    if _raw_stream is None:
+        fast = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+        _raw_stream = (lambda: fast(torch.cuda.current_device())) if fast else (lambda: torch.cuda.current_stream().cuda_stream)
+    return _raw_stream()
 
 
 def _host_arr(a, dtype):
@@ -113,7 +117,12 @@ class RGBDOdometry:
         return v.value
 
     def _borrow(self):
-        _order_after_torch(self._stream_int)
+        """Stream contract of include/ef_track.h: device inputs are consumed on the HANDLE's stream.  If torch's current stream
+        still has work in flight (it may be producing the tensor we are about to borrow), the handle's stream waits for it
+        (ef_tracker_wait_stream: one C call, nothing enqueued when that stream is idle)."""
+        rc = self._L.ef_tracker_wait_stream(self._h, C.c_void_p(_torch_raw_stream()))
+        if rc != 0:
+            self._check(rc, "ef_tracker_wait_stream")
 
     @property
     def stream(self):
