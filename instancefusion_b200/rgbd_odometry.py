@@ -87,6 +87,11 @@ class RGBDOdometry:
         self._res = np.zeros(12, np.float32)
         self._res_t, self._res_r = C.c_void_p(self._res.ctypes.data), C.c_void_p(self._res.ctypes.data + 12)
         self._stats_ref = C.byref(self._stats)
+        # argument buffers of the per-frame calls, with their addresses (numpy's .ctypes costs ~2 us per access)
+        self._pose = np.zeros(16, np.float32)
+        self._pose_p = C.c_void_p(self._pose.ctypes.data)
+        self._prior = np.zeros(12, np.float32)
+        self._prior_t, self._prior_r = C.c_void_p(self._prior.ctypes.data), C.c_void_p(self._prior.ctypes.data + 12)
         self._frame = None
         self._stream_int = int(self._L.ef_tracker_stream(self._h) or 0)
         if solve_mode is not None:  # None: the library's default (EF_SOLVE_DEVICE wherever the image fits the persistent kernel)
@@ -196,19 +201,19 @@ class RGBDOdometry:
                                                            C.c_float(depthCutoff)), "ef_init_icp_depth_raw_host")
 
     def initICPModel(self, predictedVertices, predictedNormals, depthCutoff, modelPose):
-        pose = np.ascontiguousarray(np.asarray(modelPose, dtype=np.float32).reshape(16))
+        self._pose[:] = np.asarray(modelPose).reshape(16)
         if _is_cuda_array(predictedVertices):
             self._check(self._L.ef_init_icp_model_array(self._h, _arr(predictedVertices), _arr(predictedNormals), C.c_float(depthCutoff),
-                                                        pose.ctypes.data_as(C.c_void_p)), "ef_init_icp_model_array")
+                                                        self._pose_p), "ef_init_icp_model_array")
         elif _is_cuda_tensor(predictedVertices):
             self._borrow()
             self._check(self._L.ef_init_icp_model(self._h, _dev_ptr(predictedVertices, "float32"), _dev_ptr(predictedNormals, "float32"),
-                                                  C.c_float(depthCutoff), pose.ctypes.data_as(C.c_void_p)), "ef_init_icp_model")
+                                                  C.c_float(depthCutoff), self._pose_p), "ef_init_icp_model")
         else:
             hv, hn = _host_arr(predictedVertices, np.float32), _host_arr(predictedNormals, np.float32)
             self._keep = (hv, hn)
             self._check(self._L.ef_init_icp_model_host(self._h, hv.ctypes.data_as(C.c_void_p), hn.ctypes.data_as(C.c_void_p),
-                                                       C.c_float(depthCutoff), pose.ctypes.data_as(C.c_void_p)), "ef_init_icp_model_host")
+                                                       C.c_float(depthCutoff), self._pose_p), "ef_init_icp_model_host")
 
     def _rgb(self, name, rgb):
         if _is_cuda_array(rgb):
@@ -252,21 +257,22 @@ class RGBDOdometry:
 
     def getIncrementalTransformation(self, trans, rot, rgbOnly, icpWeight, pyramid, fastOdom, so3):
         """trans (3,) and rot (3,3 row-major) are the pose prior; returns the updated (trans, rot)."""
-        tr = np.ascontiguousarray(np.asarray(trans, dtype=np.float32).reshape(3)).copy()
-        ro = np.ascontiguousarray(np.asarray(rot, dtype=np.float32).reshape(9)).copy()
-        rc = self._L.ef_get_incremental_transformation(self._h, tr.ctypes.data_as(C.c_void_p), ro.ctypes.data_as(C.c_void_p),
-                                                       C.c_int(int(rgbOnly)), C.c_float(icpWeight), C.c_int(int(pyramid)),
-                                                       C.c_int(int(fastOdom)), C.c_int(int(so3)), C.byref(self._stats))
-        self._check(rc, "ef_get_incremental_transformation")
-        return tr, ro.reshape(3, 3)
+        self._prior[:3] = np.asarray(trans).reshape(3)
+        self._prior[3:] = np.asarray(rot).reshape(9)
+        rc = self._L.ef_get_incremental_transformation(self._h, self._prior_t, self._prior_r, int(rgbOnly), C.c_float(icpWeight), int(pyramid),
+                                                       int(fastOdom), int(so3), self._stats_ref)
+        if rc != 0:
+            self._check(rc, "ef_get_incremental_transformation")
+        res = self._prior.copy()  # (in / out arguments of the C call)
+        return res[:3], res[3:].reshape(3, 3)
 
     def launch(self, trans, rot, rgbOnly, icpWeight, pyramid, fastOdom, so3):
-        tr = np.ascontiguousarray(np.asarray(trans, dtype=np.float32).reshape(3))
-        ro = np.ascontiguousarray(np.asarray(rot, dtype=np.float32).reshape(9))
-        rc = self._L.ef_get_incremental_transformation_launch(self._h, tr.ctypes.data_as(C.c_void_p), ro.ctypes.data_as(C.c_void_p),
-                                                              C.c_int(int(rgbOnly)), C.c_float(icpWeight), C.c_int(int(pyramid)),
-                                                              C.c_int(int(fastOdom)), C.c_int(int(so3)))
-        self._check(rc, "ef_get_incremental_transformation_launch")
+        self._prior[:3] = np.asarray(trans).reshape(3)
+        self._prior[3:] = np.asarray(rot).reshape(9)
+        rc = self._L.ef_get_incremental_transformation_launch(self._h, self._prior_t, self._prior_r, int(rgbOnly), C.c_float(icpWeight),
+                                                              int(pyramid), int(fastOdom), int(so3))
+        if rc != 0:
+            self._check(rc, "ef_get_incremental_transformation_launch")
 
     def finish(self):
         rc = self._L.ef_get_incremental_transformation_finish(self._h, self._res_t, self._res_r, self._stats_ref)
@@ -299,11 +305,9 @@ class RGBDOdometry:
 
     def trackFrameToModelLaunch(self, vertices, normals, model_rgba, depth, rgba, depthCutoff, modelPose, rgbOnly, icpWeight, pyramid,
                                 fastOdom, so3):
-        fi = self._frame_inputs(vertices, normals, model_rgba, depth, rgba, depthCutoff)
-        pose = np.ascontiguousarray(modelPose, dtype=np.float32)
-        if pose.size != 16:
-            raise ValueError("modelPose must be a 4x4 matrix")
-        rc = self._L.ef_track_frame_to_model_launch(self._h, self._frame_ref, C.c_void_p(pose.ctypes.data), int(rgbOnly), C.c_float(icpWeight),
+        self._frame_inputs(vertices, normals, model_rgba, depth, rgba, depthCutoff)
+        self._pose[:] = np.asarray(modelPose).reshape(16)  # (raises unless it is a 4x4 matrix)
+        rc = self._L.ef_track_frame_to_model_launch(self._h, self._frame_ref, self._pose_p, int(rgbOnly), C.c_float(icpWeight),
                                                     int(pyramid), int(fastOdom), int(so3))
         if rc != 0:
             self._check(rc, "ef_track_frame_to_model_launch")
@@ -312,10 +316,8 @@ class RGBDOdometry:
                           so3):
         # one FFI call (ef_track_frame_to_model = launch + finish)
         self._frame_inputs(vertices, normals, model_rgba, depth, rgba, depthCutoff)
-        pose = np.ascontiguousarray(modelPose, dtype=np.float32)
-        if pose.size != 16:
-            raise ValueError("modelPose must be a 4x4 matrix")
-        rc = self._L.ef_track_frame_to_model(self._h, self._frame_ref, C.c_void_p(pose.ctypes.data), self._res_t, self._res_r, int(rgbOnly),
+        self._pose[:] = np.asarray(modelPose).reshape(16)  # (raises unless it is a 4x4 matrix)
+        rc = self._L.ef_track_frame_to_model(self._h, self._frame_ref, self._pose_p, self._res_t, self._res_r, int(rgbOnly),
                                              C.c_float(icpWeight), int(pyramid), int(fastOdom), int(so3), self._stats_ref)
         if rc != 0:
             self._check(rc, "ef_track_frame_to_model")
@@ -354,6 +356,8 @@ class BatchTracker:
         self._trans = np.zeros((self.n, 3), np.float32)
         self._rot = np.zeros((self.n, 9), np.float32)
         self._stats = (TrackStats * self.n)()
+        self._poses_p = C.c_void_p(self._poses.ctypes.data)
+        self._trans_p, self._rot_p = C.c_void_p(self._trans.ctypes.data), C.c_void_p(self._rot.ctypes.data)
         self._keep = None
 
     def _fill(self, frames, poses, depthCutoff):
@@ -365,7 +369,7 @@ class BatchTracker:
 
     def launch(self, frames, poses, depthCutoff, rgbOnly, icpWeight, pyramid, fastOdom, so3):
         self._fill(frames, poses, depthCutoff)
-        rc = self._L.ef_track_frames_to_model_batch_launch(self._handles, self.n, self._inputs, C.c_void_p(self._poses.ctypes.data), int(rgbOnly),
+        rc = self._L.ef_track_frames_to_model_batch_launch(self._handles, self.n, self._inputs, self._poses_p, int(rgbOnly),
                                                            C.c_float(icpWeight), int(pyramid), int(fastOdom), int(so3))
         if rc != 0:
             raise EFError(rc, "ef_track_frames_to_model_batch_launch", "; ".join(self._L.ef_last_error(t._h).decode() for t in self.trackers))
@@ -375,8 +379,8 @@ class BatchTracker:
 
     def track(self, frames, poses, depthCutoff, rgbOnly, icpWeight, pyramid, fastOdom, so3):
         self._fill(frames, poses, depthCutoff)
-        rc = self._L.ef_track_frames_to_model_batch(self._handles, self.n, self._inputs, C.c_void_p(self._poses.ctypes.data),
-                                                    C.c_void_p(self._trans.ctypes.data), C.c_void_p(self._rot.ctypes.data), int(rgbOnly),
+        rc = self._L.ef_track_frames_to_model_batch(self._handles, self.n, self._inputs, self._poses_p,
+                                                    self._trans_p, self._rot_p, int(rgbOnly),
                                                     C.c_float(icpWeight), int(pyramid), int(fastOdom), int(so3), self._stats)
         if rc != 0:
             raise EFError(rc, "ef_track_frames_to_model_batch", "; ".join(self._L.ef_last_error(t._h).decode() for t in self.trackers))
